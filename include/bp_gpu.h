@@ -1,0 +1,149 @@
+/*
+ * bp_gpu.h -- C ABI of libbpgpu.so, the B200 (sm_100a) implementation of the data-parallel hot
+ * path of wborgeaud/python-bulletproofs.  Plain pointers and sizes only; loaded with ctypes
+ * (python_bulletproofs_b200/_native.py).  Every entry point names the reference interface it
+ * replaces (paths relative to /root/reference/).
+ *
+ * Conventions
+ *   - return value: 0 = ok, non-zero = error; bp_last_error() describes the last failure of
+ *     the calling thread's most recent call.
+ *   - affine point  : 64 bytes, x then y, each 32-byte LITTLE-endian, canonical (< p);
+ *                     the identity is 64 zero bytes (fastecdsa's Point.IDENTITY_ELEMENT).
+ *   - scalar        : 32-byte little-endian, any value < 2^256; reduced mod q on the device
+ *                     exactly as `es = [ei % order]` (src/pippenger/pippenger.py:26).
+ *   - all buffers are caller-owned host memory unless a handle is used; calls are synchronous
+ *     and serialised on one CUDA stream per process; one process drives one GPU (bp_init).
+ */
+#ifndef BP_GPU_H
+#define BP_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t bp_handle;   /* device-resident vector of points or scalars */
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int bp_init(int device);                 /* select GPU `device`, create the stream/workspace */
+int bp_shutdown(void);
+const char* bp_last_error(void);
+int bp_device_count(void);
+int bp_device_info(char* name, size_t cap, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- multi-scalar multiplication ---------------------------------------------------------------
+ * Pippenger.multiexp(gs, es)                      src/pippenger/pippenger.py:22-61
+ * (and through it vector_commitment, src/utils/commitments.py:9-13).
+ * n = 0 yields the identity (pippenger.py:28-29).  The length check of pippenger.py:23-24 is
+ * done by the Python wrapper, which raises the reference's exception text. */
+int bp_msm(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64]);
+
+/* device-resident operands (SURVEY.md 7 "hard part 2": marshalling 2^20 Python Points costs
+ * three orders of magnitude more than the kernel) */
+int bp_points_upload(const uint8_t* pts64, size_t n, bp_handle* h);
+int bp_scalars_upload(const uint8_t* sc32, size_t n, bp_handle* h);
+int bp_handle_free(bp_handle h);
+int bp_msm_h(bp_handle points, const uint8_t* sc32, size_t n, uint8_t out64[64]);     /* scalars from host */
+int bp_msm_hh(bp_handle points, bp_handle scalars, size_t n, uint8_t out64[64]);      /* all resident */
+/* XYZZ partial (4 x 32-byte LE: X, Y, ZZ, ZZZ) of a point slice, for sharding over GPUs
+ * (SURVEY.md 8e); bp_xyzz_sum adds `count` partials and returns the canonical affine point. */
+int bp_msm_hh_partial(bp_handle points, bp_handle scalars, size_t first, size_t n, uint8_t out128[128]);
+int bp_xyzz_sum(const uint8_t* partials128, size_t count, uint8_t out64[64]);
+
+/* many independent MSMs in one launch sequence: MSM j uses terms offsets[j] .. offsets[j+1]-1
+ * (offsets has nmsm+1 entries).  Replaces the per-round / per-proof multiexp calls of
+ * src/innerproduct/inner_product_prover.py:98-99, inner_product_verifier.py:134-143,
+ * src/rangeproofs/rangeproof_verifier.py:88-97. */
+int bp_msm_batch(const uint8_t* pts64, const uint8_t* sc32, const uint32_t* offsets, size_t nmsm, uint8_t* out64);
+
+/* window-size override for experiments (0 = automatic) and per-stage device timings (ms) of the
+ * last MSM call: [0]=digits [1]=scan [2]=scatter [3]=accumulate [4]=reduce [5]=combine [6]=total */
+int bp_msm_set_window(int c);
+int bp_msm_last_window(void);
+int bp_msm_set_profiling(int on);
+int bp_msm_stage_ms(float out7[7]);
+
+/* ---- independent scalar multiplications --------------------------------------------------------
+ * out[i] = sc[i] * pts[i]:  hsp = [(y.inv() ** i) * hs[i] ...]
+ * src/rangeproofs/rangeproof_prover.py:77, rangeproof_verifier.py:72,
+ * rangeproof_aggreg_prover.py:82, rangeproof_aggreg_verifier.py:80; ModP.__mul__(Point) utils.py:43-44 */
+int bp_scalar_mul_batch(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t* out64);
+
+/* ---- inner-product argument ---------------------------------------------------------------------
+ * One folding step, for step-wise parity tests:
+ *   g'[i] = xinv*g[i] + x*g[i+n/2],  h'[i] = x*h[i] + xinv*h[i+n/2]      (inner_product_prover.py:107-108)
+ *   a'[i] = x*a[i] + xinv*a[i+n/2],  b'[i] = xinv*b[i] + x*b[i+n/2] mod q (inner_product_prover.py:109-110)
+ * n is the current (even) length; outputs have n/2 entries.  xinv is computed on the device side. */
+int bp_ipa_fold_round(const uint8_t* g64, const uint8_t* h64, const uint8_t* a32, const uint8_t* b32, size_t n,
+                      const uint8_t x32[32], uint8_t* g_out64, uint8_t* h_out64, uint8_t* a_out32, uint8_t* b_out32);
+
+/* FastNIProver2.prove()                         src/innerproduct/inner_product_prover.py:70-110
+ * n = power of two (1 allowed: zero rounds).  `transcript` is the digest so far (the Transcript
+ * object's bytes, already including base64(seed) + "&"); the Fiat-Shamir hashing of each round
+ * runs on the host inside this call (SHA-256 / base64 / decimal printing restated in C, see
+ * csrc/transcript.h).  Outputs: Ls, Rs (log2 n points), xs (log2 n scalars), final a, b, and the
+ * full transcript digest (tout_len receives its length; error if tout_cap is too small). */
+int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64], const uint8_t* a32, const uint8_t* b32,
+                 size_t n, const uint8_t* transcript, size_t transcript_len, uint8_t* Ls64, uint8_t* Rs64, uint8_t* xs32,
+                 uint8_t a_out32[32], uint8_t b_out32[32], uint8_t* transcript_out, size_t tout_cap, size_t* tout_len);
+
+/* Verifier2.get_ss + the two multiexps of Verifier2.verify   inner_product_verifier.py:91-102,132-145
+ * accept = 1 iff  MSM(g||h||u ; a*s || b*s^-1 || a*b) == P + MSM(Ls||Rs ; x^2 || x^-2).
+ * (The transcript re-check, :104-125, is host string work done by the Python/C host layer.) */
+int bp_ipa_verify_eq(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64], const uint8_t P64[64], size_t n,
+                     const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,
+                     const uint8_t* Rs64, int* accept);
+
+/* ---- batch verification of independent 64-bit (or n-bit) single-value range proofs ---------------
+ * RangeVerifier.verify()                        src/rangeproofs/rangeproof_verifier.py:42-97
+ * over `nproofs` proofs that share one generator set (gs, hs: n points each; g, h, u).
+ * Packed proof record (little-endian scalars, 64-byte affine points), see INTEGRATION.md:
+ *   V, A, S, T1, T2 (5 x 64) | taux, mu, t_hat (3 x 32) | u_new, P_new (2 x 64) | a, b (2 x 32)
+ *   | xs (log2 n x 32) | Ls (log2 n x 64) | Rs (log2 n x 64)
+ * transcripts: the three byte strings of each proof (range transcript, Protocol-1 transcript,
+ * Protocol-2 transcript) concatenated; tr_off has 3*nproofs+1 entries.  start_transcript per proof.
+ * accept[i] = 1/0 reproduces the reference's True / Exception("Proof invalid"); accept[i] = 2 marks
+ * a non-numeric y/z/x slot (the reference raises ValueError from int(), rangeproof_verifier.py:49-53). */
+int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g64[64], const uint8_t h64[64],
+                       const uint8_t u64_[64], size_t n, const uint8_t* proofs, size_t proof_stride, size_t nproofs,
+                       const uint8_t* transcripts, const uint64_t* tr_off, const uint32_t* start_transcript,
+                       uint8_t* accept);
+size_t bp_rp_proof_stride(size_t n);
+
+/* ---- host-side Fiat-Shamir helpers (exported for tests; src/utils/utils.py:84-111) -------------- */
+int bp_mod_hash(const uint8_t* msg, size_t len, uint8_t out32[32]);            /* mod_hash(msg, q) */
+int bp_point_to_b64(const uint8_t pt64[64], char out[45], size_t* out_len);    /* point_to_b64 */
+
+/* ---- measurement --------------------------------------------------------------------------------
+ * Times `iters` back-to-back resident MSMs with CUDA events on the library stream after `warmup`
+ * untimed ones; between iterations an L2 flush (write of a 256 MiB buffer) runs outside the
+ * timed events when flush_l2 != 0.  ms_each receives per-iteration milliseconds. */
+int bp_bench_msm(bp_handle points, bp_handle scalars, size_t n, int warmup, int iters, int flush_l2, float* ms_each,
+                 uint8_t out64[64]);
+/* IMAD.WIDE.U32 issue-rate microbenchmark: returns measured 32x32+64 multiply-accumulates per
+ * second (the roofline denominator of DESIGN.md) and the lane-ops executed. */
+int bp_imad_peak(int iters, double* macs_per_s, float* ms);
+
+/* ---- arithmetic self-test hooks (known-answer tests against big-int arithmetic) ------------------
+ * fp: op 0 mul, 1 add, 2 sub, 3 inv, 4 neg  (inputs any 256-bit residue, output canonical)
+ * ec: op 0 mixed add a+b, 1 full add, 2 double a, 3 negate a; +10 runs them on a re-projected a
+ * fq: op 0 mul, 1 add, 2 sub, 3 inv, 4 neg; on_device = 0 runs the same code on the host */
+int bp_test_fp(int op, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32);
+int bp_test_ec(int op, const uint8_t* a64, const uint8_t* b64, size_t n, uint8_t* out64);
+int bp_test_fq(int op, int on_device, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32);
+
+/* ---- multi-GPU (one process per GPU) ---------------------------------------------------------------
+ * NCCL communicator over the ranks of a torchrun job; `unique_id` is the 128-byte ncclUniqueId
+ * produced by bp_nccl_unique_id on rank 0 and shared by the launcher's store. */
+int bp_nccl_unique_id(uint8_t out128[128]);
+int bp_nccl_init(int rank, int nranks, const uint8_t unique_id[128]);
+/* slice [first, first+n) of a resident MSM on this rank, ncclAllGather of the XYZZ partials over
+ * NVLink, every rank adds them and returns the same canonical affine point. */
+int bp_msm_sharded(bp_handle points, bp_handle scalars, size_t first, size_t n, uint8_t out64[64]);
+int bp_allgather_bytes(const uint8_t* send, size_t nbytes, uint8_t* recv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BP_GPU_H */

@@ -1,0 +1,158 @@
+"""ctypes binding of libbpgpu.so (include/bp_gpu.h) and the byte packers at the boundary.
+
+There is deliberately NO fallback: if the shared library is missing, or no sm_100 GPU is
+visible, the first call raises.  Points cross the boundary as 64-byte little-endian affine
+(x || y), the identity as 64 zero bytes; scalars as 32-byte little-endian.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbpgpu.so")
+
+Q = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+P = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEFFFFFC2F
+
+c_u8p = ctypes.c_char_p
+c_sz = ctypes.c_size_t
+c_h = ctypes.c_uint64
+
+# name -> (restype, argtypes): every symbol include/bp_gpu.h declares
+PROTOTYPES = {
+    "bp_init": (ctypes.c_int, [ctypes.c_int]),
+    "bp_shutdown": (ctypes.c_int, []),
+    "bp_last_error": (ctypes.c_char_p, []),
+    "bp_device_count": (ctypes.c_int, []),
+    "bp_device_info": (ctypes.c_int, [ctypes.c_char_p, c_sz, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "bp_msm": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p]),
+    "bp_points_upload": (ctypes.c_int, [c_u8p, c_sz, ctypes.POINTER(c_h)]),
+    "bp_scalars_upload": (ctypes.c_int, [c_u8p, c_sz, ctypes.POINTER(c_h)]),
+    "bp_handle_free": (ctypes.c_int, [c_h]),
+    "bp_msm_h": (ctypes.c_int, [c_h, c_u8p, c_sz, c_u8p]),
+    "bp_msm_hh": (ctypes.c_int, [c_h, c_h, c_sz, c_u8p]),
+    "bp_msm_hh_partial": (ctypes.c_int, [c_h, c_h, c_sz, c_sz, c_u8p]),
+    "bp_xyzz_sum": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
+    "bp_msm_batch": (ctypes.c_int, [c_u8p, c_u8p, ctypes.POINTER(ctypes.c_uint32), c_sz, c_u8p]),
+    "bp_msm_set_window": (ctypes.c_int, [ctypes.c_int]),
+    "bp_msm_last_window": (ctypes.c_int, []),
+    "bp_msm_set_profiling": (ctypes.c_int, [ctypes.c_int]),
+    "bp_msm_stage_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
+    "bp_scalar_mul_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p]),
+    "bp_ipa_fold_round": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
+    "bp_ipa_prove": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
+                                    c_u8p, c_sz, ctypes.POINTER(c_sz)]),
+    "bp_ipa_verify_eq": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, ctypes.POINTER(ctypes.c_int)]),
+    "bp_rp_verify_batch": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_sz, c_u8p,
+                                          ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), c_u8p]),
+    "bp_rp_proof_stride": (c_sz, [c_sz]),
+    "bp_mod_hash": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
+    "bp_point_to_b64": (ctypes.c_int, [c_u8p, c_u8p, ctypes.POINTER(c_sz)]),
+    "bp_bench_msm": (ctypes.c_int, [c_h, c_h, c_sz, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_u8p]),
+    "bp_imad_peak": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]),
+    "bp_test_fp": (ctypes.c_int, [ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
+    "bp_test_ec": (ctypes.c_int, [ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
+    "bp_test_fq": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
+    "bp_nccl_unique_id": (ctypes.c_int, [c_u8p]),
+    "bp_nccl_init": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u8p]),
+    "bp_msm_sharded": (ctypes.c_int, [c_h, c_h, c_sz, c_sz, c_u8p]),
+    "bp_allgather_bytes": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
+}
+
+_lib = None
+
+
+class BpGpuError(RuntimeError):
+    """Raised when libbpgpu reports a failure (missing GPU, CUDA error, bad arguments)."""
+
+
+def load():
+    """dlopen libbpgpu.so and attach prototypes.  Does not touch the GPU."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BpGpuError(
+                "libbpgpu.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C python_bulletproofs_b200/csrc`; there is no CPU fallback" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise BpGpuError(load().bp_last_error().decode(errors="replace"))
+
+
+def init(device=None):
+    """Bind this process to one GPU (LOCAL_RANK by default)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    check(load().bp_init(device))
+
+
+# ---- packers -------------------------------------------------------------------------------
+_ZERO64 = bytes(64)
+
+
+def pack_xy(x, y):
+    return x.to_bytes(32, "little") + y.to_bytes(32, "little")
+
+
+def pack_point(pt):
+    """Any object with .x/.y/.curve (fastecdsa-style; curve None = identity) or an (x, y) tuple / None."""
+    if pt is None:
+        return _ZERO64
+    if isinstance(pt, tuple):
+        return pack_xy(pt[0], pt[1])
+    if getattr(pt, "curve", True) is None:
+        return _ZERO64
+    return pack_xy(pt.x, pt.y)
+
+
+def pack_points(pts):
+    return b"".join([pack_point(p) for p in pts])
+
+
+def unpack_xy(b, off=0):
+    """-> (x, y) or None for the identity."""
+    chunk = b[off:off + 64]
+    if chunk == _ZERO64:
+        return None
+    return int.from_bytes(chunk[:32], "little"), int.from_bytes(chunk[32:], "little")
+
+
+def pack_scalar(k):
+    """ints / ModP / anything supporting `% int`  ->  32-byte LE of (k mod q)  (pippenger.py:26)."""
+    return (k % Q).to_bytes(32, "little")
+
+
+def pack_scalars(ks):
+    return b"".join([(k % Q).to_bytes(32, "little") for k in ks])
+
+
+def unpack_scalars(b, n):
+    return [int.from_bytes(b[32 * i:32 * i + 32], "little") for i in range(n)]
+
+
+# ---- thin call helpers ---------------------------------------------------------------------
+def msm_bytes(pts_b, sc_b, n):
+    out = ctypes.create_string_buffer(64)
+    check(load().bp_msm(pts_b, sc_b, n, out))
+    return out.raw
+
+
+def msm_batch_bytes(pts_b, sc_b, offsets):
+    nmsm = len(offsets) - 1
+    out = ctypes.create_string_buffer(64 * max(nmsm, 1))
+    off = (ctypes.c_uint32 * len(offsets))(*offsets)
+    check(load().bp_msm_batch(pts_b, sc_b, off, nmsm, out))
+    return out.raw[:64 * nmsm]
+
+
+def scalar_mul_batch_bytes(pts_b, sc_b, n):
+    out = ctypes.create_string_buffer(64 * max(n, 1))
+    check(load().bp_scalar_mul_batch(pts_b, sc_b, n, out))
+    return out.raw[:64 * n]

@@ -1,0 +1,358 @@
+// bp_gpu.cu -- C-ABI entry points of libbpgpu.so (see include/bp_gpu.h) and the host drivers
+// that sequence the kernels of msm.cuh / ipa.cuh on one CUDA stream.
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bp_gpu.h"
+#include "ctx.h"
+#include "msm.cuh"
+#include "ipa.cuh"
+#include "transcript.h"
+#include "verify.cuh"
+#include <nccl.h>
+#include <thread>
+
+namespace bp {
+
+thread_local std::string g_err;
+Ctx g;
+
+int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+// ---- the MSM pipeline on device-resident operands ----------------------------------------------
+// points/point_idx/scalars/offsets are device pointers; out_affine/out_xyzz device (either may be null)
+int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, const u32* d_offsets, u32 nmsm,
+            size_t terms_per_msm, Affine* out_affine, XYZZ* out_xyzz) {
+  cudaStream_t st = g.stream;
+  MsmShape sh = msm_shape(terms_per_msm, nmsm, g.force_c);
+  g.last_c = sh.c;
+  size_t nmw = (size_t)nmsm * sh.W, nb = nmw * sh.H;
+  bool prof = g.profiling;
+  if (prof) for (int i = 0; i < 7; i++) cudaEventRecord(g.ev[i], st), (void)0;
+  if (T == 0) {   // all identities
+    BP_CUDA(cudaMemsetAsync(out_affine ? (void*)out_affine : (void*)out_xyzz, 0, out_affine ? nmsm * sizeof(Affine) : nmsm * sizeof(XYZZ), st));
+    if (out_affine && out_xyzz) BP_CUDA(cudaMemsetAsync(out_xyzz, 0, nmsm * sizeof(XYZZ), st));
+    return 0;
+  }
+  int* digits = (int*)g.ws_digits.ensure((size_t)sh.W * T * sizeof(int));
+  u32* entries = (u32*)g.ws_entries.ensure((size_t)sh.W * T * sizeof(u32));
+  u32* count = (u32*)g.ws_count.ensure((nb + 1) * sizeof(u32));
+  u32* start = (u32*)g.ws_start.ensure((nb + 1) * sizeof(u32));
+  u32* cursor = (u32*)g.ws_cursor.ensure((nb + 1) * sizeof(u32));
+  size_t ntiles = (nb + 1 + BP_SCAN_TILE - 1) / BP_SCAN_TILE;
+  u32* tiles = (u32*)g.ws_tiles.ensure(ntiles * sizeof(u32));
+  XYZZ* buckets = (XYZZ*)g.ws_buckets.ensure(nb * sizeof(XYZZ));
+  XYZZ* segsum = (XYZZ*)g.ws_segsum.ensure(nmw * sh.nseg * sizeof(XYZZ));
+  XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure(nmw * sizeof(XYZZ));
+  if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !segsum || !winsum) return fail("workspace allocation failed");
+
+  BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
+  BP_CUDA(cudaMemsetAsync(cursor, 0, (nb + 1) * sizeof(u32), st));
+  if (prof) cudaEventRecord(g.ev[0], st);
+  k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count);
+  if (prof) cudaEventRecord(g.ev[1], st);
+  k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
+  k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
+  k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
+  if (prof) cudaEventRecord(g.ev[2], st);
+  k_scatter<<<(T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, start, cursor, entries);
+  if (prof) cudaEventRecord(g.ev[3], st);
+  k_accumulate<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(points, point_idx, start, entries, nb, buckets);
+  if (prof) cudaEventRecord(g.ev[4], st);
+  size_t nsegs = nmw * sh.nseg;
+  k_reduce_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);
+  const XYZZ* ws = segsum;
+  if (sh.nseg > 1) { k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(segsum, sh.nseg, winsum); ws = winsum; }
+  if (prof) cudaEventRecord(g.ev[5], st);
+  k_combine<<<(unsigned)((nmsm + 63) / 64), 64, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+  if (prof) cudaEventRecord(g.ev[6], st);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int msm_to_host(const Affine* d_pts, const Fq* d_sc, size_t n, uint8_t* out64) {
+  Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
+  if (!d_out) return fail("workspace allocation failed");
+  if (msm_run(d_pts, nullptr, d_sc, (u32)n, nullptr, 1, n, d_out, nullptr)) return 1;
+  BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+struct HandleRec { void* p; size_t n; int kind; };   // kind 0 = points, 1 = scalars
+static std::map<bp_handle, HandleRec> g_handles;
+static bp_handle g_next_handle = 1;
+static std::mutex g_mu;
+
+static int get_handle(bp_handle h, int kind, HandleRec* out) {
+  auto it = g_handles.find(h);
+  if (it == g_handles.end() || it->second.kind != kind) return fail("bad handle %llu", (unsigned long long)h);
+  *out = it->second;
+  return 0;
+}
+
+// ---- IMAD.WIDE peak microbenchmark -------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_imad_peak(u32* out, u32 seed, int iters) {
+  // 8 independent 64-bit accumulators per thread, 32x32+64 multiply-accumulate each step.
+  u64 acc[8];
+  u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = (u64)(a + i) << 20;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        u32 lo = (u32)acc[i], hi = (u32)(acc[i] >> 32);
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a ^ hi), "r"(b));
+        (void)lo;
+      }
+    }
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s ^= acc[i];
+  if (s == 0x1234567u) out[0] = (u32)s;   // keep the chain alive
+}
+
+}  // namespace bp
+
+using namespace bp;
+
+#define BP_NEED_INIT() do { if (!g.inited) { if (bp_init(-1)) return 1; } } while (0)
+
+extern "C" {
+
+const char* bp_last_error(void) { return g_err.c_str(); }
+
+int bp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int bp_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g.inited && (device < 0 || device == g.device)) return 0;
+  if (g.inited) return fail("bp_init: already bound to device %d", g.device);
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail("no CUDA device available (%s): libbpgpu has no CPU fallback", cudaGetErrorString(e)); }
+  if (device < 0) device = 0;
+  if (device >= n) return fail("bp_init: device %d out of range (%d devices)", device, n);
+  BP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail("bp_init: device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+  g.device = device; g.sm_count = prop.multiProcessorCount;
+  BP_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) BP_CUDA(cudaEventCreate(&g.ev[i]));
+  BP_CUDA(cudaEventCreate(&g.ev_a)); BP_CUDA(cudaEventCreate(&g.ev_b));
+  g.inited = true;
+  return 0;
+}
+
+int bp_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g.inited) return 0;
+  cudaStreamSynchronize(g.stream);
+  for (auto& kv : g_handles) cudaFree(kv.second.p);
+  g_handles.clear();
+  g.free_all();
+  nccl_shutdown();
+  cudaStreamDestroy(g.stream);
+  g.inited = false;
+  return 0;
+}
+
+int bp_device_info(char* name, size_t cap, int* sm_count, int* cc_major, int* cc_minor) {
+  BP_NEED_INIT();
+  cudaDeviceProp prop;
+  BP_CUDA(cudaGetDeviceProperties(&prop, g.device));
+  if (name && cap) { strncpy(name, prop.name, cap - 1); name[cap - 1] = 0; }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
+int bp_msm_set_window(int c) { if (c < 0 || c > 16) return fail("window must be 0..16"); g.force_c = c; return 0; }
+int bp_msm_last_window(void) { return g.last_c; }
+int bp_msm_set_profiling(int on) { g.profiling = on != 0; return 0; }
+int bp_msm_stage_ms(float out7[7]) {
+  BP_NEED_INIT();
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  for (int i = 0; i < 6; i++) { if (cudaEventElapsedTime(&out7[i], g.ev[i], g.ev[i + 1]) != cudaSuccess) { cudaGetLastError(); out7[i] = -1.f; } }
+  if (cudaEventElapsedTime(&out7[6], g.ev[0], g.ev[6]) != cudaSuccess) { cudaGetLastError(); out7[6] = -1.f; }
+  return 0;
+}
+
+int bp_msm(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64]) {
+  BP_NEED_INIT();
+  if (n == 0) { memset(out64, 0, 64); return 0; }       // pippenger.py:28-29
+  if (n >= (1u << 31)) return fail("bp_msm: n too large");
+  Affine* d_pts = (Affine*)g.ws_pts.ensure(n * sizeof(Affine));
+  Fq* d_sc = (Fq*)g.ws_sc.ensure(n * sizeof(Fq));
+  if (!d_pts || !d_sc) return fail("device allocation failed");
+  BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
+  return msm_to_host(d_pts, d_sc, n, out64);
+}
+
+static int upload(const uint8_t* src, size_t n, size_t elt, int kind, bp_handle* h) {
+  BP_NEED_INIT();
+  void* p = nullptr;
+  BP_CUDA(cudaMalloc(&p, n ? n * elt : elt));
+  if (n) BP_CUDA(cudaMemcpy(p, src, n * elt, cudaMemcpyHostToDevice));
+  std::lock_guard<std::mutex> lk(g_mu);
+  *h = g_next_handle++;
+  g_handles[*h] = HandleRec{p, n, kind};
+  return 0;
+}
+int bp_points_upload(const uint8_t* pts64, size_t n, bp_handle* h) { return upload(pts64, n, 64, 0, h); }
+int bp_scalars_upload(const uint8_t* sc32, size_t n, bp_handle* h) { return upload(sc32, n, 32, 1, h); }
+int bp_handle_free(bp_handle h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_handles.find(h);
+  if (it == g_handles.end()) return fail("bad handle");
+  cudaStreamSynchronize(g.stream);
+  cudaFree(it->second.p);
+  g_handles.erase(it);
+  return 0;
+}
+
+int bp_msm_h(bp_handle points, const uint8_t* sc32, size_t n, uint8_t out64[64]) {
+  BP_NEED_INIT();
+  HandleRec P;
+  if (get_handle(points, 0, &P)) return 1;
+  if (n > P.n) return fail("bp_msm_h: n exceeds the uploaded vector");
+  if (n == 0) { memset(out64, 0, 64); return 0; }
+  Fq* d_sc = (Fq*)g.ws_sc.ensure(n * sizeof(Fq));
+  if (!d_sc) return fail("device allocation failed");
+  BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
+  return msm_to_host((const Affine*)P.p, d_sc, n, out64);
+}
+
+int bp_msm_hh(bp_handle points, bp_handle scalars, size_t n, uint8_t out64[64]) {
+  BP_NEED_INIT();
+  HandleRec P, S;
+  if (get_handle(points, 0, &P) || get_handle(scalars, 1, &S)) return 1;
+  if (n > P.n || n > S.n) return fail("bp_msm_hh: n exceeds the uploaded vectors");
+  if (n == 0) { memset(out64, 0, 64); return 0; }
+  return msm_to_host((const Affine*)P.p, (const Fq*)S.p, n, out64);
+}
+
+int bp_msm_hh_partial(bp_handle points, bp_handle scalars, size_t first, size_t n, uint8_t out128[128]) {
+  BP_NEED_INIT();
+  HandleRec P, S;
+  if (get_handle(points, 0, &P) || get_handle(scalars, 1, &S)) return 1;
+  if (first + n > P.n || first + n > S.n) return fail("bp_msm_hh_partial: slice exceeds the uploaded vectors");
+  if (n == 0) { memset(out128, 0, 128); return 0; }
+  XYZZ* d_out = (XYZZ*)g.ws_out.ensure(sizeof(XYZZ));
+  if (msm_run((const Affine*)P.p + first, nullptr, (const Fq*)S.p + first, (u32)n, nullptr, 1, n, nullptr, d_out)) return 1;
+  BP_CUDA(cudaMemcpyAsync(out128, d_out, 128, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int bp_xyzz_sum(const uint8_t* partials128, size_t count, uint8_t out64[64]) {
+  BP_NEED_INIT();
+  if (count == 0) { memset(out64, 0, 64); return 0; }
+  XYZZ* d_in = (XYZZ*)g.ws_misc.ensure(count * sizeof(XYZZ));
+  Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
+  BP_CUDA(cudaMemcpyAsync(d_in, partials128, count * 128, cudaMemcpyHostToDevice, g.stream));
+  k_xyzz_sum<<<1, 32, 0, g.stream>>>(d_in, (u32)count, d_out);
+  BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int bp_msm_batch(const uint8_t* pts64, const uint8_t* sc32, const uint32_t* offsets, size_t nmsm, uint8_t* out64) {
+  BP_NEED_INIT();
+  if (nmsm == 0) return 0;
+  size_t T = offsets[nmsm];
+  size_t maxlen = 0;
+  for (size_t j = 0; j < nmsm; j++) { if (offsets[j + 1] < offsets[j]) return fail("bp_msm_batch: offsets not monotone"); size_t l = offsets[j + 1] - offsets[j]; if (l > maxlen) maxlen = l; }
+  if (T == 0) { memset(out64, 0, nmsm * 64); return 0; }
+  Affine* d_pts = (Affine*)g.ws_pts.ensure(T * sizeof(Affine));
+  Fq* d_sc = (Fq*)g.ws_sc.ensure(T * sizeof(Fq));
+  u32* d_off = (u32*)g.ws_off.ensure((nmsm + 1) * sizeof(u32));
+  Affine* d_out = (Affine*)g.ws_out.ensure(nmsm * sizeof(Affine));
+  if (!d_pts || !d_sc || !d_off || !d_out) return fail("device allocation failed");
+  BP_CUDA(cudaMemcpyAsync(d_pts, pts64, T * 64, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(d_sc, sc32, T * 32, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(d_off, offsets, (nmsm + 1) * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
+  size_t avg = (T + nmsm - 1) / nmsm;
+  if (msm_run(d_pts, nullptr, d_sc, (u32)T, d_off, (u32)nmsm, avg, d_out, nullptr)) return 1;
+  BP_CUDA(cudaMemcpyAsync(out64, d_out, nmsm * 64, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int bp_scalar_mul_batch(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t* out64) {
+  BP_NEED_INIT();
+  if (n == 0) return 0;
+  Affine* d_pts = (Affine*)g.ws_pts.ensure(n * sizeof(Affine));
+  Fq* d_sc = (Fq*)g.ws_sc.ensure(n * sizeof(Fq));
+  Affine* d_out = (Affine*)g.ws_out.ensure(n * sizeof(Affine));
+  if (!d_pts || !d_sc || !d_out) return fail("device allocation failed");
+  BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
+  k_scalar_mul<<<(unsigned)((n + 63) / 64), 64, 0, g.stream>>>(d_pts, d_sc, (u32)n, d_out);
+  BP_CUDA(cudaMemcpyAsync(out64, d_out, n * 64, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int bp_bench_msm(bp_handle points, bp_handle scalars, size_t n, int warmup, int iters, int flush_l2, float* ms_each, uint8_t out64[64]) {
+  BP_NEED_INIT();
+  HandleRec P, S;
+  if (get_handle(points, 0, &P) || get_handle(scalars, 1, &S)) return 1;
+  if (n > P.n || n > S.n || n == 0) return fail("bp_bench_msm: bad n");
+  Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
+  const size_t flush_bytes = 256u << 20;
+  void* d_flush = flush_l2 ? g.ws_flush.ensure(flush_bytes) : nullptr;
+  for (int it = 0; it < warmup + iters; it++) {
+    if (d_flush) BP_CUDA(cudaMemsetAsync(d_flush, it & 0xff, flush_bytes, g.stream));
+    BP_CUDA(cudaEventRecord(g.ev_a, g.stream));
+    if (msm_run((const Affine*)P.p, nullptr, (const Fq*)S.p, (u32)n, nullptr, 1, n, d_out, nullptr)) return 1;
+    BP_CUDA(cudaEventRecord(g.ev_b, g.stream));
+    BP_CUDA(cudaEventSynchronize(g.ev_b));
+    float ms = 0;
+    BP_CUDA(cudaEventElapsedTime(&ms, g.ev_a, g.ev_b));
+    if (it >= warmup) ms_each[it - warmup] = ms;
+  }
+  BP_CUDA(cudaMemcpy(out64, d_out, 64, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bp_imad_peak(int iters, double* macs_per_s, float* ms_out) {
+  BP_NEED_INIT();
+  u32* d = (u32*)g.ws_misc.ensure(256);
+  int blocks = g.sm_count * 8;
+  k_imad_peak<<<blocks, 256, 0, g.stream>>>(d, 12345u, 16);   // warm-up
+  BP_CUDA(cudaEventRecord(g.ev_a, g.stream));
+  k_imad_peak<<<blocks, 256, 0, g.stream>>>(d, 12345u, iters);
+  BP_CUDA(cudaEventRecord(g.ev_b, g.stream));
+  BP_CUDA(cudaEventSynchronize(g.ev_b));
+  float ms = 0;
+  BP_CUDA(cudaEventElapsedTime(&ms, g.ev_a, g.ev_b));
+  double macs = (double)blocks * 256.0 * (double)iters * 32.0;
+  if (macs_per_s) *macs_per_s = macs / (ms * 1e-3);
+  if (ms_out) *ms_out = ms;
+  return 0;
+}
+
+}  // extern "C"
+#include "bp_proto.inl"

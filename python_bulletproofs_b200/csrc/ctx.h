@@ -1,0 +1,56 @@
+// ctx.h -- per-process device context of libbpgpu: one GPU, one stream, grow-only workspaces.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <string>
+
+namespace bp {
+
+int fail(const char* fmt, ...);
+void nccl_shutdown();
+
+#define BP_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) { cudaGetLastError(); return ::bp::fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* ensure(size_t bytes) {
+    if (bytes <= cap && p) return p;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; }
+    cap = want;
+    return p;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Ctx {
+  bool inited = false;
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8];
+  cudaEvent_t ev_a, ev_b;
+  bool profiling = false;
+  int force_c = 0, last_c = 0;
+  // MSM workspaces
+  DevBuf ws_pts, ws_sc, ws_off, ws_out, ws_digits, ws_entries, ws_count, ws_start, ws_cursor, ws_tiles, ws_buckets, ws_segsum,
+      ws_winsum, ws_misc, ws_flush;
+  // IPA / verifier workspaces
+  DevBuf ws_g, ws_h, ws_a, ws_b, ws_g2, ws_h2, ws_a2, ws_b2, ws_idx, ws_lr, ws_terms_sc, ws_small;
+  void free_all() {
+    DevBuf* all[] = {&ws_pts, &ws_sc, &ws_off, &ws_out, &ws_digits, &ws_entries, &ws_count, &ws_start, &ws_cursor, &ws_tiles,
+                     &ws_buckets, &ws_segsum, &ws_winsum, &ws_misc, &ws_flush, &ws_g, &ws_h, &ws_a, &ws_b, &ws_g2, &ws_h2,
+                     &ws_a2, &ws_b2, &ws_idx, &ws_lr, &ws_terms_sc, &ws_small};
+    for (DevBuf* b : all) b->release();
+  }
+};
+
+extern Ctx g;
+
+}  // namespace bp

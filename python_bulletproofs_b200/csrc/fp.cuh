@@ -1,0 +1,227 @@
+// fp.cuh -- secp256k1 base-field arithmetic for sm_100a, 8 x 32-bit limbs held in registers.
+//
+// Replaces: the F_p arithmetic the reference reaches through fastecdsa/GMP on every
+// Point.__add__ (/root/reference/src/pippenger/group.py:31-32).
+//
+// Representation: little-endian limbs, "lazy" residues in [0, 2^256) (not necessarily < p).
+// p = 2^256 - C with C = 2^32 + 977, so 2^256 = C (mod p) and a 512-bit product folds with
+// 8 + 1 extra IMAD.WIDE instead of the 64 + 8 a Montgomery REDC needs ("Why
+// not Montgomery for F_p").  The 8x8 schoolbook product uses separate even/odd column
+// accumulators so that every 32x32->64 partial product is one IMAD.WIDE.U32 whose carry rides
+// the predicate chain (IMAD.WIDE.U32.X); checked with cuobjdump -sass, see profiles/.
+#pragma once
+#include <cstdint>
+
+namespace bp {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+struct __align__(16) Fp { u32 v[8]; };
+
+#define BP_DI __device__ __forceinline__
+
+// 2^256 - p
+#define BP_PC_LO 977u   // C = 2^32 + 977 : limb0 = 977, limb1 = 1
+
+BP_DI Fp fp_zero() { Fp r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+BP_DI Fp fp_one() { Fp r = fp_zero(); r.v[0] = 1; return r; }
+
+// ---- multi-limb carry chains (one asm block each so the CC flag never crosses statements) ----
+// r = a + b, returns carry
+BP_DI u32 add256(u32 r[8], const u32 a[8], const u32 b[8]) {
+  u32 c;
+  asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,%20;"
+      "addc.cc.u32 %4,%13,%21; addc.cc.u32 %5,%14,%22; addc.cc.u32 %6,%15,%23; addc.cc.u32 %7,%16,%24;"
+      "addc.u32 %8,0,0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+  return c;
+}
+// r = a - b, returns borrow (1 if a < b)
+BP_DI u32 sub256(u32 r[8], const u32 a[8], const u32 b[8]) {
+  u32 c;
+  asm("sub.cc.u32 %0,%9,%17; subc.cc.u32 %1,%10,%18; subc.cc.u32 %2,%11,%19; subc.cc.u32 %3,%12,%20;"
+      "subc.cc.u32 %4,%13,%21; subc.cc.u32 %5,%14,%22; subc.cc.u32 %6,%15,%23; subc.cc.u32 %7,%16,%24;"
+      "subc.u32 %8,0,0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+  return c & 1u;   // subc.u32 0,0 yields 0xffffffff on borrow
+}
+// r += k*C for k in {0,1}; returns carry out
+BP_DI u32 add_kc(u32 r[8], u32 k) {
+  u32 c;
+  asm("mad.lo.cc.u32 %0,%9,977,%0; addc.cc.u32 %1,%1,%9; addc.cc.u32 %2,%2,0; addc.cc.u32 %3,%3,0;"
+      "addc.cc.u32 %4,%4,0; addc.cc.u32 %5,%5,0; addc.cc.u32 %6,%6,0; addc.cc.u32 %7,%7,0; addc.u32 %8,0,0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+      : "r"(k));
+  return c;
+}
+// r -= k*C for k in {0,1}; returns borrow
+BP_DI u32 sub_kc(u32 r[8], u32 k) {
+  u32 c, lo = k * BP_PC_LO;
+  asm("sub.cc.u32 %0,%0,%9; subc.cc.u32 %1,%1,%10; subc.cc.u32 %2,%2,0; subc.cc.u32 %3,%3,0;"
+      "subc.cc.u32 %4,%4,0; subc.cc.u32 %5,%5,0; subc.cc.u32 %6,%6,0; subc.cc.u32 %7,%7,0; subc.u32 %8,0,0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+      : "r"(lo), "r"(k));
+  return c & 1u;
+}
+
+BP_DI Fp fp_add(const Fp& a, const Fp& b) {
+  Fp r;
+  u32 k = add256(r.v, a.v, b.v);
+  k = add_kc(r.v, k);        // 2^256 = C (mod p)
+  // a second wrap needs a + b >= 2^256 + p (both operands non-canonical): rare, still handled
+  asm("mad.lo.cc.u32 %0,%3,977,%0; addc.cc.u32 %1,%1,%3; addc.u32 %2,%2,0;" : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]) : "r"(k));
+  return r;
+}
+BP_DI Fp fp_sub(const Fp& a, const Fp& b) {
+  Fp r;
+  u32 k = sub256(r.v, a.v, b.v);
+  k = sub_kc(r.v, k);        // -2^256 = -C
+  sub_kc(r.v, k);            // second borrow only when the first left r < C; cannot borrow again
+  return r;
+}
+BP_DI Fp fp_dbl(const Fp& a) { return fp_add(a, a); }
+BP_DI Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }
+
+BP_DI bool fp_is_zero(const Fp& a) {   // 0 or p
+  u32 o = a.v[0] | a.v[1] | a.v[2] | a.v[3] | a.v[4] | a.v[5] | a.v[6] | a.v[7];
+  u32 n = (a.v[0] ^ 0xFFFFFC2Fu) | (a.v[1] ^ 0xFFFFFFFEu) | ~(a.v[2] & a.v[3] & a.v[4] & a.v[5] & a.v[6] & a.v[7]);
+  return o == 0 || n == 0;
+}
+// canonical representative in [0, p)
+BP_DI Fp fp_canon(const Fp& a) {
+  Fp r = a;
+  bool hi = (a.v[2] & a.v[3] & a.v[4] & a.v[5] & a.v[6] & a.v[7]) == 0xFFFFFFFFu;
+  bool ge = hi && (a.v[1] == 0xFFFFFFFFu || (a.v[1] == 0xFFFFFFFEu && a.v[0] >= 0xFFFFFC2Fu));
+  add_kc(r.v, ge ? 1u : 0u);   // a - p = a + C - 2^256
+  return r;
+}
+
+// ---- 8x8 limb product, even/odd columns --------------------------------------------------------
+BP_DI void mul_row_init(u32* acc, u32 a0, u32 a1, u32 a2, u32 a3, u32 b) {
+  asm("mul.lo.u32 %0,%8,%12; mul.hi.u32 %1,%8,%12; mul.lo.u32 %2,%9,%12; mul.hi.u32 %3,%9,%12;"
+      "mul.lo.u32 %4,%10,%12; mul.hi.u32 %5,%10,%12; mul.lo.u32 %6,%11,%12; mul.hi.u32 %7,%11,%12;"
+      : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+BP_DI void mul_row_mad(u32* acc, u32 a0, u32 a1, u32 a2, u32 a3, u32 b) {
+  asm("mad.lo.cc.u32 %0,%9,%13,%0; madc.hi.cc.u32 %1,%9,%13,%1; madc.lo.cc.u32 %2,%10,%13,%2; madc.hi.cc.u32 %3,%10,%13,%3;"
+      "madc.lo.cc.u32 %4,%11,%13,%4; madc.hi.cc.u32 %5,%11,%13,%5; madc.lo.cc.u32 %6,%12,%13,%6; madc.hi.cc.u32 %7,%12,%13,%7;"
+      "addc.u32 %8,%8,0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+// t[0..15] = a * b
+BP_DI void mul_wide(u32 t[16], const u32 a[8], const u32 b[8]) {
+  // ev[k] sits at limb position k, od[k] at limb position k+1
+  u32 ev[18], od[18];
+#pragma unroll
+  for (int k = 8; k < 18; k++) { ev[k] = 0; od[k] = 0; }
+  mul_row_init(ev, a[0], a[2], a[4], a[6], b[0]);
+  mul_row_init(od, a[1], a[3], a[5], a[7], b[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    if (i & 1) {
+      mul_row_mad(od + i - 1, a[0], a[2], a[4], a[6], b[i]);
+      mul_row_mad(ev + i + 1, a[1], a[3], a[5], a[7], b[i]);
+    } else {
+      mul_row_mad(ev + i, a[0], a[2], a[4], a[6], b[i]);
+      mul_row_mad(od + i, a[1], a[3], a[5], a[7], b[i]);
+    }
+  }
+  t[0] = ev[0];
+  asm("add.cc.u32 %0,%15,%30; addc.cc.u32 %1,%16,%31; addc.cc.u32 %2,%17,%32; addc.cc.u32 %3,%18,%33; addc.cc.u32 %4,%19,%34;"
+      "addc.cc.u32 %5,%20,%35; addc.cc.u32 %6,%21,%36; addc.cc.u32 %7,%22,%37; addc.cc.u32 %8,%23,%38; addc.cc.u32 %9,%24,%39;"
+      "addc.cc.u32 %10,%25,%40; addc.cc.u32 %11,%26,%41; addc.cc.u32 %12,%27,%42; addc.cc.u32 %13,%28,%43; addc.u32 %14,%29,%44;"
+      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]),
+        "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+      : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(ev[9]), "r"(ev[10]),
+        "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
+        "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]), "r"(od[9]),
+        "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+}
+
+// r = t mod p (lazy), t 512 bits:  t = lo + hi*2^256 = lo + hi*C
+BP_DI void fold512(u32 r[8], const u32 t[16]) {
+  // s = hi * 977 : 9 limbs (even/odd halves so every product is one IMAD.WIDE)
+  u32 s[9];
+  asm("mul.lo.u32 %0,%9,%13; mul.hi.u32 %1,%9,%13; mul.lo.u32 %2,%10,%13; mul.hi.u32 %3,%10,%13;"
+      "mul.lo.u32 %4,%11,%13; mul.hi.u32 %5,%11,%13; mul.lo.u32 %6,%12,%13; mul.hi.u32 %7,%12,%13; mov.u32 %8,0;"
+      : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8])
+      : "r"(t[8]), "r"(t[10]), "r"(t[12]), "r"(t[14]), "r"(977u));
+  asm("mad.lo.cc.u32 %0,%8,%12,%0; madc.hi.cc.u32 %1,%8,%12,%1; madc.lo.cc.u32 %2,%9,%12,%2; madc.hi.cc.u32 %3,%9,%12,%3;"
+      "madc.lo.cc.u32 %4,%10,%12,%4; madc.hi.cc.u32 %5,%10,%12,%5; madc.lo.cc.u32 %6,%11,%12,%6; madc.hi.u32 %7,%11,%12,%7;"
+      : "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]), "+r"(s[5]), "+r"(s[6]), "+r"(s[7]), "+r"(s[8])
+      : "r"(t[9]), "r"(t[11]), "r"(t[13]), "r"(t[15]), "r"(977u));
+  // u = lo + s + (hi << 32): limbs 0..8 plus a carry word `top`
+  u32 u[9], top, top2;
+  asm("add.cc.u32 %0,%10,%18; addc.cc.u32 %1,%11,%19; addc.cc.u32 %2,%12,%20; addc.cc.u32 %3,%13,%21;"
+      "addc.cc.u32 %4,%14,%22; addc.cc.u32 %5,%15,%23; addc.cc.u32 %6,%16,%24; addc.cc.u32 %7,%17,%25;"
+      "addc.cc.u32 %8,%26,0; addc.u32 %9,0,0;"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(top)
+      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
+        "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]), "r"(s[8]));
+  asm("add.cc.u32 %0,%0,%9; addc.cc.u32 %1,%1,%10; addc.cc.u32 %2,%2,%11; addc.cc.u32 %3,%3,%12;"
+      "addc.cc.u32 %4,%4,%13; addc.cc.u32 %5,%5,%14; addc.cc.u32 %6,%6,%15; addc.cc.u32 %7,%7,%16; addc.u32 %8,0,0;"
+      : "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]), "+r"(u[8]), "=r"(top2)
+      : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]));
+  top += top2;                       // e = u[8] + top*2^32 < 2^34
+  // second fold: r = u[0..7] + e*977 + (e << 32)
+  u64 m = (u64)u[8] * 977ull + (((u64)(top * 977u)) << 32);   // e*977 < 2^44
+  u32 m0 = (u32)m, m1 = (u32)(m >> 32), k, k2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = u[i];
+  asm("add.cc.u32 %0,%0,%9; addc.cc.u32 %1,%1,%10; addc.cc.u32 %2,%2,0; addc.cc.u32 %3,%3,0;"
+      "addc.cc.u32 %4,%4,0; addc.cc.u32 %5,%5,0; addc.cc.u32 %6,%6,0; addc.cc.u32 %7,%7,0; addc.u32 %8,0,0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(k)
+      : "r"(m0), "r"(m1));
+  asm("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%9; addc.cc.u32 %2,%2,0; addc.cc.u32 %3,%3,0;"
+      "addc.cc.u32 %4,%4,0; addc.cc.u32 %5,%5,0; addc.cc.u32 %6,%6,0; addc.u32 %7,0,0;"
+      : "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(k2)
+      : "r"(u[8]), "r"(top));
+  // at most one of the two adds wrapped (the sum is < 2^256 + 2^67); the wrapped value is tiny
+  k += k2;
+  asm("mad.lo.cc.u32 %0,%3,977,%0; addc.cc.u32 %1,%1,%3; addc.u32 %2,%2,0;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]) : "r"(k));
+}
+
+BP_DI Fp fp_mul(const Fp& a, const Fp& b) {
+  u32 t[16];
+  mul_wide(t, a.v, b.v);
+  Fp r;
+  fold512(r.v, t);
+  return r;
+}
+BP_DI Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
+
+BP_DI Fp fp_sqr_n(Fp a, int n) {
+  for (int i = 0; i < n; i++) a = fp_sqr(a);
+  return a;
+}
+// a^(p-2): 255 squarings + 15 multiplications (addition chain on the run structure of p-2:
+// 223 ones, 0, 22 ones, 0000, 1, 0, 11, 0, 1)
+__device__ __noinline__ Fp fp_inv(const Fp& a) {
+  Fp x2 = fp_mul(fp_sqr(a), a);
+  Fp x3 = fp_mul(fp_sqr(x2), a);
+  Fp x6 = fp_mul(fp_sqr_n(x3, 3), x3);
+  Fp x9 = fp_mul(fp_sqr_n(x6, 3), x3);
+  Fp x11 = fp_mul(fp_sqr_n(x9, 2), x2);
+  Fp x22 = fp_mul(fp_sqr_n(x11, 11), x11);
+  Fp x44 = fp_mul(fp_sqr_n(x22, 22), x22);
+  Fp x88 = fp_mul(fp_sqr_n(x44, 44), x44);
+  Fp x176 = fp_mul(fp_sqr_n(x88, 88), x88);
+  Fp x220 = fp_mul(fp_sqr_n(x176, 44), x44);
+  Fp x223 = fp_mul(fp_sqr_n(x220, 3), x3);
+  Fp t = fp_mul(fp_sqr_n(x223, 23), x22);
+  t = fp_mul(fp_sqr_n(t, 5), a);
+  t = fp_mul(fp_sqr_n(t, 3), x2);
+  t = fp_mul(fp_sqr_n(t, 2), a);
+  return t;
+}
+
+}  // namespace bp

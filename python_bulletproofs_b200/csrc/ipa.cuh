@@ -1,0 +1,129 @@
+// ipa.cuh -- kernels for the inner-product-argument rounds and the scalar-multiplication batch.
+//
+// Replaces: the body of FastNIProver2.prove's while-loop
+// (/root/reference/src/innerproduct/inner_product_prover.py:84-110) and the `hsp` list
+// comprehension (/root/reference/src/rangeproofs/rangeproof_prover.py:77 and siblings).
+//
+// Device layout of one prover instance: points  P = [ u | g_0..g_{m-1} | h_0..h_{m-1} ]
+// (affine, 64 B each), scalars a, b (32 B each, standard form, reduced).  Each round reads P, a, b
+// of length m = 2k and writes the folded vectors of length k into the ping-pong twins.
+#pragma once
+#include "ec.cuh"
+#include "fq.cuh"
+
+namespace bp {
+
+BP_DI Fq ld_fq(const Fq* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Fq r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+BP_DI void st_fq(Fq* p, const Fq& a) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+// v[i] <- v[i] mod q  (inputs are ModP.x values that may be unreduced)
+__global__ void __launch_bounds__(128) k_reduce_scalars(Fq* __restrict__ v, u32 n) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st_fq(v + i, fq_reduce(ld_fq(v + i)));
+}
+
+// k * p, left-to-right double-and-add on the bits of k (k < q).  Lanes diverge on the add only.
+BP_DI XYZZ scalar_mul_affine(const Affine& p, const Fq& k) {
+  XYZZ acc = xyzz_identity();
+  if (affine_is_identity(p)) return acc;
+  for (int i = 255; i >= 0; i--) {
+    acc = xyzz_dbl(acc);
+    if ((k.v[i >> 5] >> (i & 31)) & 1) xyzz_madd(acc, p);
+  }
+  return acc;
+}
+
+// out[i] = sc[i] * pts[i]
+__global__ void __launch_bounds__(64) k_scalar_mul(const Affine* __restrict__ pts, const Fq* __restrict__ sc, u32 n, Affine* __restrict__ out) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fq k = fq_reduce(ld_fq(sc + i));
+  Affine p = ld_affine(pts + i);
+  st_affine(out + i, xyzz_to_affine(scalar_mul_affine(p, k)));
+}
+
+// sum of `count` XYZZ partials -> canonical affine (count is tiny: one per GPU)
+__global__ void k_xyzz_sum(const XYZZ* __restrict__ in, u32 count, Affine* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  XYZZ acc = xyzz_identity();
+  for (u32 i = 0; i < count; i++) { XYZZ v = ld_xyzz(in + i); xyzz_add(acc, v); }
+  st_affine(out, xyzz_to_affine(acc));
+}
+
+// Generator folding with a SHARED pair of scalars (divergence-free Shamir ladder):
+//   i <  k : g'[i] = s_inv * g[i] + s * g[k+i]            inner_product_prover.py:107
+//   i >= k : h'[j] = s * h[j] + s_inv * h[k+j], j = i-k   inner_product_prover.py:108
+// src = [u | g (2k) | h (2k)], dst = [u | g' (k) | h' (k)]  (thread 2k copies u).
+__global__ void __launch_bounds__(64) k_fold_points(const Affine* __restrict__ src, Affine* __restrict__ dst, u32 k, Fq s, Fq s_inv) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > 2 * k) return;
+  if (i == 2 * k) { st_affine(dst, ld_affine(src)); return; }
+  const bool is_h = i >= k;
+  u32 j = is_h ? i - k : i;
+  const Affine* base = src + 1 + (is_h ? 2 * k : 0);
+  Affine lo = ld_affine(base + j), hi = ld_affine(base + k + j);
+  Fq klo = is_h ? s : s_inv, khi = is_h ? s_inv : s;
+  XYZZ acc = xyzz_identity();
+  for (int b = 255; b >= 0; b--) {
+    acc = xyzz_dbl(acc);
+    if ((klo.v[b >> 5] >> (b & 31)) & 1) xyzz_madd(acc, lo);
+    if ((khi.v[b >> 5] >> (b & 31)) & 1) xyzz_madd(acc, hi);
+  }
+  st_affine(dst + 1 + (is_h ? k : 0) + j, xyzz_to_affine(acc));
+}
+
+// a'[i] = x*a[i] + xinv*a[k+i] ; b'[i] = xinv*b[i] + x*b[k+i]   (inner_product_prover.py:109-110)
+// xm, xim = Montgomery forms of x, x^-1 so that fq_mont(v, xm) = v*x.
+__global__ void __launch_bounds__(128) k_fold_scalars(const Fq* __restrict__ a, const Fq* __restrict__ b, u32 k, Fq xm, Fq xim,
+                                                      Fq* __restrict__ a2, Fq* __restrict__ b2) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  st_fq(a2 + i, fq_add(fq_mont(ld_fq(a + i), xm), fq_mont(ld_fq(a + k + i), xim)));
+  st_fq(b2 + i, fq_add(fq_mont(ld_fq(b + i), xim), fq_mont(ld_fq(b + k + i), xm)));
+}
+
+// Builds the two (2k+1)-term MSMs of one round and their inner products:
+//   c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>                          inner_product_prover.py:96-97
+//   L   = MSM(g_hi || h_lo || u ; a_lo || b_hi || c_L)              :98
+//   R   = MSM(g_lo || h_hi || u ; a_hi || b_lo || c_R)              :99
+// One block of 256 threads.  term index t in [0, 2k+1) for L, + (2k+1) for R.
+__global__ void __launch_bounds__(256) k_build_lr(const Fq* __restrict__ a, const Fq* __restrict__ b, u32 k, Fq* __restrict__ tsc,
+                                                  u32* __restrict__ tidx) {
+  __shared__ Fq sl[256], sr[256];
+  const u32 n1 = 2 * k + 1;
+  Fq accl = fq_zero(), accr = fq_zero();
+  for (u32 i = threadIdx.x; i < k; i += 256) {
+    Fq alo = ld_fq(a + i), ahi = ld_fq(a + k + i), blo = ld_fq(b + i), bhi = ld_fq(b + k + i);
+    accl = fq_add(accl, fq_mont(alo, bhi));      // carries a factor R^-1, removed below
+    accr = fq_add(accr, fq_mont(ahi, blo));
+    // points live in [u | g (2k) | h (2k)]
+    tsc[i] = alo;            tidx[i] = 1 + k + i;            // g_hi[i]
+    tsc[k + i] = bhi;        tidx[k + i] = 1 + 2 * k + i;    // h_lo[i]
+    tsc[n1 + i] = ahi;       tidx[n1 + i] = 1 + i;           // g_lo[i]
+    tsc[n1 + k + i] = blo;   tidx[n1 + k + i] = 1 + 3 * k + i;   // h_hi[i]
+  }
+  sl[threadIdx.x] = accl; sr[threadIdx.x] = accr;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      sl[threadIdx.x] = fq_add(sl[threadIdx.x], sl[threadIdx.x + off]);
+      sr[threadIdx.x] = fq_add(sr[threadIdx.x], sr[threadIdx.x + off]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    tsc[2 * k] = fq_to_mont(sl[0]);  tidx[2 * k] = 0;            // (sum * R^-1) * R = sum ; point u
+    tsc[n1 + 2 * k] = fq_to_mont(sr[0]);  tidx[n1 + 2 * k] = 0;
+  }
+}
+
+}  // namespace bp

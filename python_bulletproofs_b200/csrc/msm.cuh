@@ -1,0 +1,240 @@
+// msm.cuh -- batched bucket-method multi-scalar multiplication on secp256k1 for sm_100a.
+//
+// Replaces: Pippenger.multiexp / Pippenger._multiexp_bin
+// (/root/reference/src/pippenger/pippenger.py:22-94).  The reference runs Pippenger's subset-table
+// method; this is the bucket method (same result: the canonical affine sum of e_i * g_i, scalars
+// taken mod q, empty input => identity).
+//
+// One pipeline serves both shapes on the hot path:
+//   * one large MSM (config C3, 2^10..2^20 terms): nmsm = 1, window c up to 16 bits;
+//   * many small independent MSMs (L/R of an IPA round, the per-proof verifier equations of
+//     config C5): nmsm up to tens of thousands, c = 4..8.
+// Stages (all on one stream, no host round trip in between):
+//   k_digits      scalars -> sign-normalised signed c-bit digits, bucket histogram (atomics)
+//   scan          exclusive prefix sum of the histogram -> bucket_start
+//   k_scatter     counting-sort scatter of (term, sign) into bucket order
+//   k_accumulate  one thread per bucket: XYZZ += (+/-)affine point, points gathered with 128-bit loads
+//   k_reduce_seg  per (msm, window, segment): running-sum trick  sum_i (i+1) * B_i
+//   k_window_sum  per (msm, window): tree-sum of the segment results in shared memory
+//   k_combine     per msm: Horner over windows (c doublings each), one inversion, canonical affine
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include "ec.cuh"
+#include "fq.cuh"
+
+namespace bp {
+
+struct MsmShape {
+  int c;          // window bits
+  int W;          // windows = ceil(256 / c)   (scalars are sign-normalised to < 2^255)
+  u32 H;          // buckets per window = 2^(c-1)
+  u32 S;          // buckets per reduce segment
+  u32 nseg;       // segments per window
+};
+
+inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
+  MsmShape s;
+  int best = 1; double bestc = 1e300;
+  for (int c = 1; c <= 16; c++) {
+    double W = (256 + c - 1) / c, H = (double)(1u << (c - 1));
+    // accumulate: W * n mixed adds (10 mul) ; reduce: 2 * W * H full adds (14 mul) ; combine: 256 dbl serial (latency, weighted)
+    double serial = nmsm > 64 ? 0.0 : 256.0 * 9 * 64;   // a lone thread runs ~64x below throughput
+    double cost = W * (double)terms_per_msm * 10 + 2 * W * H * 14 * (nmsm > 64 ? 1.0 : 1.6) + serial;
+    if (cost < bestc) { bestc = cost; best = c; }
+  }
+  s.c = force_c > 0 ? force_c : best;
+  s.W = (256 + s.c - 1) / s.c;
+  s.H = 1u << (s.c - 1);
+  s.S = s.H < 16 ? s.H : 16;
+  s.nseg = s.H / s.S;
+  return s;
+}
+
+// ---- scalar -> digits --------------------------------------------------------------------------
+BP_DI u32 scalar_bits(const Fq& k, int lo, int n) {   // n <= 16 bits from bit `lo`; bits >= 256 read as 0
+  if (lo >= 256) return 0;
+  int w = lo >> 5, sh = lo & 31;
+  u64 v = k.v[w];
+  if (w + 1 < 8) v |= (u64)k.v[w + 1] << 32;
+  return (u32)(v >> sh) & ((1u << n) - 1);
+}
+
+// msm id of term t given exclusive offsets[0..nmsm]
+BP_DI u32 find_msm(const u32* __restrict__ offsets, u32 nmsm, u32 t) {
+  u32 lo = 0, hi = nmsm;          // invariant: offsets[lo] <= t < offsets[hi]
+  while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (__ldg(offsets + mid) <= t) lo = mid; else hi = mid; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) k_digits(const Fq* __restrict__ scalars, u32 T, const u32* __restrict__ offsets, u32 nmsm,
+                                                MsmShape sh, int* __restrict__ digits, u32* __restrict__ bucket_count) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + t);
+  uint4 a = __ldg(sp), b = __ldg(sp + 1);
+  Fq k; k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
+  k = fq_reduce(k);                                   // es = [ei % order]   pippenger.py:26
+  bool neg = !fq_geq(fq_const_half(), k);             // k > q/2  ->  use q - k (< 2^255) on the negated point
+  if (neg) k = fq_sub(fq_zero(), k);
+  u32 m = nmsm > 1 ? find_msm(offsets, nmsm, t) : 0;
+  u32 carry = 0;
+  for (int w = 0; w < sh.W; w++) {
+    u32 d = scalar_bits(k, w * sh.c, sh.c) + carry;
+    int sd;
+    if (d > sh.H) { sd = (int)d - (int)(2u * sh.H); carry = 1; } else { sd = (int)d; carry = 0; }
+    if (neg) sd = -sd;
+    digits[(size_t)w * T + t] = sd;
+    if (sd != 0) {
+      u32 mag = sd < 0 ? (u32)(-sd) : (u32)sd;
+      atomicAdd(bucket_count + ((size_t)m * sh.W + w) * sh.H + (mag - 1), 1u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits, u32 T, const u32* __restrict__ offsets, u32 nmsm,
+                                                 MsmShape sh, const u32* __restrict__ bucket_start, u32* __restrict__ cursor,
+                                                 u32* __restrict__ entries) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  u32 m = nmsm > 1 ? find_msm(offsets, nmsm, t) : 0;
+  for (int w = 0; w < sh.W; w++) {
+    int sd = digits[(size_t)w * T + t];
+    if (sd == 0) continue;
+    u32 mag = sd < 0 ? (u32)(-sd) : (u32)sd;
+    size_t b = ((size_t)m * sh.W + w) * sh.H + (mag - 1);
+    u32 pos = __ldg(bucket_start + b) + atomicAdd(cursor + b, 1u);
+    entries[pos] = t | (sd < 0 ? 0x80000000u : 0u);
+  }
+}
+
+// ---- exclusive scan of u32 counts (3 passes; totals < 2^32) ---------------------------------------
+#define BP_SCAN_TILE 2048
+__global__ void __launch_bounds__(256) k_scan_tiles(const u32* __restrict__ in, u32* __restrict__ out, u32* __restrict__ tile_sum, size_t n) {
+  __shared__ u32 sm[256];
+  size_t base = (size_t)blockIdx.x * BP_SCAN_TILE + (size_t)threadIdx.x * 8;
+  u32 v[8], s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    u32 x = threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
+    __syncthreads();
+    sm[threadIdx.x] += x;
+    __syncthreads();
+  }
+  u32 excl = sm[threadIdx.x] - s;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { if (base + i < n) out[base + i] = excl; excl += v[i]; }
+  if (threadIdx.x == 255) tile_sum[blockIdx.x] = sm[255];
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(u32* __restrict__ tile_sum, size_t ntiles) {   // one block
+  __shared__ u32 sm[1024];
+  __shared__ u32 carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < ntiles; base += 1024) {
+    size_t i = base + threadIdx.x;
+    u32 s = i < ntiles ? tile_sum[i] : 0;
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      u32 x = threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
+      __syncthreads();
+      sm[threadIdx.x] += x;
+      __syncthreads();
+    }
+    if (i < ntiles) tile_sum[i] = carry + sm[threadIdx.x] - s;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sm[1023];
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_scan_add(u32* __restrict__ out, const u32* __restrict__ tile_sum, size_t n, u32* __restrict__ total_slot) {
+  size_t base = (size_t)blockIdx.x * BP_SCAN_TILE + (size_t)threadIdx.x * 8;
+  u32 add = tile_sum[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < 8; i++) if (base + i < n) out[base + i] += add;
+  (void)total_slot;
+}
+
+// ---- bucket accumulation ---------------------------------------------------------------------
+// bucket_start has nb + 1 entries (the last = total entry count).
+__global__ void __launch_bounds__(128) k_accumulate(const Affine* __restrict__ points, const u32* __restrict__ point_idx,
+                                                    const u32* __restrict__ bucket_start, const u32* __restrict__ entries,
+                                                    size_t nb, XYZZ* __restrict__ buckets) {
+  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  u32 lo = __ldg(bucket_start + b), hi = __ldg(bucket_start + b + 1);
+  XYZZ acc = xyzz_identity();
+  for (u32 i = lo; i < hi; i++) {
+    u32 e = __ldg(entries + i);
+    u32 t = e & 0x7FFFFFFFu;
+    u32 pi = point_idx ? __ldg(point_idx + t) : t;
+    Affine p = ld_affine(points + pi);
+    if (e >> 31) p.y = fp_neg(p.y);
+    xyzz_madd(acc, p);
+  }
+  st_xyzz(buckets + b, acc);
+}
+
+// acc = k * p for a small k (k < 2^16), left-to-right double-and-add
+BP_DI XYZZ xyzz_mul_small(const XYZZ& p, u32 k) {
+  XYZZ acc = xyzz_identity();
+  for (int i = 15; i >= 0; i--) {
+    acc = xyzz_dbl(acc);
+    if ((k >> i) & 1) xyzz_add(acc, p);
+  }
+  return acc;
+}
+
+// one thread per (msm*W + w, seg): sum_{i<S} (seg*S + i + 1) * B[i]
+__global__ void __launch_bounds__(128) k_reduce_seg(const XYZZ* __restrict__ buckets, MsmShape sh, size_t nmw, XYZZ* __restrict__ segsum) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nmw * sh.nseg) return;
+  size_t mw = id / sh.nseg; u32 seg = (u32)(id % sh.nseg);
+  const XYZZ* B = buckets + mw * sh.H + (size_t)seg * sh.S;
+  XYZZ run = xyzz_identity(), sum = xyzz_identity();
+  for (int i = (int)sh.S - 1; i >= 0; i--) {
+    XYZZ b = ld_xyzz(B + i);
+    xyzz_add(run, b);
+    xyzz_add(sum, run);
+  }
+  u32 off = seg * sh.S;
+  if (off) { XYZZ sc = xyzz_mul_small(run, off); xyzz_add(sum, sc); }
+  st_xyzz(segsum + id, sum);
+}
+
+// one block (256 threads) per (msm, window): winsum = sum of nseg segment results
+__global__ void __launch_bounds__(256) k_window_sum(const XYZZ* __restrict__ segsum, u32 nseg, XYZZ* __restrict__ winsum) {
+  __shared__ XYZZ sm[256];
+  size_t mw = blockIdx.x;
+  XYZZ acc = xyzz_identity();
+  for (u32 i = threadIdx.x; i < nseg; i += 256) { XYZZ v = ld_xyzz(segsum + mw * nseg + i); xyzz_add(acc, v); }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) { XYZZ v = sm[threadIdx.x + off]; xyzz_add(acc, v); sm[threadIdx.x] = acc; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_xyzz(winsum + mw, acc);
+}
+
+// one thread per msm: Horner over windows, then canonical affine (optionally XYZZ partials for sharding)
+__global__ void __launch_bounds__(64) k_combine(const XYZZ* __restrict__ winsum, MsmShape sh, size_t nmsm, Affine* __restrict__ out,
+                                                XYZZ* __restrict__ out_xyzz) {
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nmsm) return;
+  const XYZZ* ws = winsum + m * sh.W;
+  XYZZ acc = ld_xyzz(ws + sh.W - 1);
+  for (int w = sh.W - 2; w >= 0; w--) {
+    for (int d = 0; d < sh.c; d++) acc = xyzz_dbl(acc);
+    XYZZ v = ld_xyzz(ws + w);
+    xyzz_add(acc, v);
+  }
+  if (out_xyzz) st_xyzz(out_xyzz + m, acc);
+  if (out) st_affine(out + m, xyzz_to_affine(acc));
+}
+
+}  // namespace bp

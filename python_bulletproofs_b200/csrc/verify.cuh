@@ -1,0 +1,140 @@
+// verify.cuh -- device-side scalar algebra + term construction for batch verification of
+// single-value range proofs over one shared generator set.
+//
+// Replaces, per proof: RangeVerifier.verify (/root/reference/src/rangeproofs/rangeproof_verifier.py:55-97),
+// Verifier1.verify (/root/reference/src/innerproduct/inner_product_verifier.py:44-58) and
+// Verifier2.get_ss / verify (:91-102,127-147).  Every point equation of the reference is kept as
+// its own exact check (no random linear combination), rewritten as "MSM == identity":
+//   E1  t_hat*g + taux*h == z^2*V + delta*g + x*T1 + x^2*T2                 rangeproof_verifier.py:73-76
+//   E2  P_new == A + x*S + sum(-z*gs_i) + sum((z*y^i + z^2*2^i)*hsp_i) - mu*h + (x1*t_hat)*u
+//                                                              rangeproof_verifier.py:78-84,88-97; inner_product_verifier.py:51
+//   E3  u_new == x1*u                                                         inner_product_verifier.py:52
+//   E4  MSM(gs||hsp||u_new ; a*s || b*s^-1 || a*b) == P_new + MSM(Ls||Rs ; x_j^2 || x_j^-2)   :134-145
+// with hsp_i = y^-i * hs_i folded into the scalars (rangeproof_verifier.py:72).
+#pragma once
+#include "ec.cuh"
+#include "fq.cuh"
+#include "ipa.cuh"
+
+namespace bp {
+
+// per-proof scalar slots (standard form)
+enum { RS_Y = 0, RS_Z, RS_X, RS_X1, RS_THAT, RS_TAUX, RS_MU, RS_A, RS_B, RS_XS };   // then xs[0..L)
+// per-proof point slots
+enum { RP_V = 0, RP_A, RP_S, RP_T1, RP_T2, RP_UNEW, RP_PNEW, RP_LS };               // then Ls[0..L), Rs[0..L)
+
+struct RpLayout {
+  u32 n, L;            // vector length (power of two), log2 n
+  u32 nsc, npt;        // scalars / points per proof
+  u32 tpp;             // terms per proof = 4n + 14 + 2L
+  u32 fixed;           // fixed table size = 2n + 3  : [gs | hs | g | h | u]
+};
+inline RpLayout rp_layout(u32 n) {
+  RpLayout l; l.n = n; l.L = 0; while ((1u << l.L) < n) l.L++;
+  l.nsc = RS_XS + l.L; l.npt = RP_LS + 2 * l.L; l.tpp = 4 * n + 14 + 2 * l.L; l.fixed = 2 * n + 3;
+  return l;
+}
+
+// One block per proof, n threads (n >= 32 rounded up by the launcher; extra threads idle).
+// Writes the proof's tpp term scalars / point indices and its 4 MSM offsets.
+__global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, RpLayout lay, u32 nproofs, Fq* __restrict__ tsc,
+                                                    u32* __restrict__ tidx, u32* __restrict__ offsets) {
+  extern __shared__ Fq sm[];      // [0..L) x_j (mont) | [L..2L) x_j^-1 (mont) | 2L: y^-1 (mont) | 2L+1 .. : reduction scratch (blockDim)
+  const u32 p = blockIdx.x, i = threadIdx.x, n = lay.n, L = lay.L;
+  if (p >= nproofs) return;
+  const Fq* S = psc + (size_t)p * lay.nsc;
+  Fq* xm = sm; Fq* xim = sm + L; Fq* yim = sm + 2 * L; Fq* red = sm + 2 * L + 1;
+  // inversions spread over the first L+1 threads
+  if (i < L) { Fq x = ld_fq(S + RS_XS + i); xm[i] = fq_to_mont(x); xim[i] = fq_to_mont(fq_inv(x)); }
+  if (i == L) { *yim = fq_to_mont(fq_inv(ld_fq(S + RS_Y))); }
+  __syncthreads();
+  const Fq y = ld_fq(S + RS_Y), z = ld_fq(S + RS_Z), x = ld_fq(S + RS_X), x1 = ld_fq(S + RS_X1);
+  const Fq that = ld_fq(S + RS_THAT), taux = ld_fq(S + RS_TAUX), mu = ld_fq(S + RS_MU), a = ld_fq(S + RS_A), b = ld_fq(S + RS_B);
+  const Fq ym = fq_to_mont(y), zm = fq_to_mont(z), R1 = fq_const_r();
+  const Fq z2m = fq_mont(zm, zm);
+  // y^i, y^-i (Montgomery) by square-and-multiply on the bits of i
+  Fq yi = R1, yii = R1;
+  if (i < n) {
+    for (int bit = 31 - __clz(i | 1); bit >= 0; bit--) {
+      yi = fq_mont(yi, yi); yii = fq_mont(yii, yii);
+      if ((i >> bit) & 1) { yi = fq_mont(yi, ym); yii = fq_mont(yii, *yim); }
+    }
+  }
+  // block sum of y^i for delta(y, z)
+  red[i] = i < n ? yi : fq_zero();
+  __syncthreads();
+  for (u32 off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if (i < off) red[i] = fq_add(red[i], red[i + off]);
+    __syncthreads();
+  }
+  const Fq sum_y = red[0];
+  const size_t tb = (size_t)p * lay.tpp;                 // term base of this proof
+  const u32 pb = lay.fixed + p * lay.npt;                // point base of this proof
+  const u32 iG = 2 * n, iH = 2 * n + 1, iU = 2 * n + 2;
+  const u32 o1 = 0, o2 = 5, o3 = 5 + 2 * n + 5, o4 = o3 + 2;
+  if (i < n) {
+    // ---- E2, generator terms
+    Fq two_i = fq_zero(); if (i < 256) two_i.v[i >> 5] = 1u << (i & 31);   // 2^i, standard form (host enforces n <= 128)
+    two_i = fq_reduce(two_i);
+    Fq hs_sc = fq_add(z, fq_from_mont(fq_mont(fq_mont(z2m, fq_to_mont(two_i)), yii)));   // z + z^2 * 2^i * y^-i
+    st_fq(tsc + tb + o2 + 2 + i, fq_neg(z));          tidx[tb + o2 + 2 + i] = i;             // gs_i : -z
+    st_fq(tsc + tb + o2 + 2 + n + i, hs_sc);          tidx[tb + o2 + 2 + n + i] = n + i;     // hs_i
+    // ---- E4, generator terms: s_i = prod_j (bit_j(i) ? x_j : x_j^-1), bit j counted from the MSB
+    Fq s = R1, sinv = R1;
+    for (u32 j = 0; j < L; j++) {
+      bool bit = (i >> (L - 1 - j)) & 1;
+      s = fq_mont(s, bit ? xm[j] : xim[j]);
+      sinv = fq_mont(sinv, bit ? xim[j] : xm[j]);
+    }
+    st_fq(tsc + tb + o4 + i, fq_mont(a, s));                         tidx[tb + o4 + i] = i;          // a * s_i
+    st_fq(tsc + tb + o4 + n + i, fq_mont(fq_mont(b, sinv), yii));  tidx[tb + o4 + n + i] = n + i;   // b * s_i^-1 * y^-i
+  }
+  if (i < L) {
+    Fq x2 = fq_from_mont(fq_mont(xm[i], xm[i])), xi2 = fq_from_mont(fq_mont(xim[i], xim[i]));
+    st_fq(tsc + tb + o4 + 2 * n + 2 + i, fq_neg(x2));       tidx[tb + o4 + 2 * n + 2 + i] = pb + RP_LS + i;        // L_j : -x_j^2
+    st_fq(tsc + tb + o4 + 2 * n + 2 + L + i, fq_neg(xi2));  tidx[tb + o4 + 2 * n + 2 + L + i] = pb + RP_LS + L + i; // R_j : -x_j^-2
+  }
+  if (i == 0) {
+    const Fq one = fq_one(), m1 = fq_neg(one);
+    const Fq z2 = fq_from_mont(z2m), z3 = fq_mont(z2, zm);
+    // delta = (z - z^2) * sum y^i - z^3 * (2^n - 1)
+    Fq two_n = fq_zero();
+    if (n < 256) two_n.v[n >> 5] = 1u << (n & 31);
+    two_n = fq_reduce(two_n);
+    if (n >= 256) two_n = fq_pow_u64(fq_from_u64(2), n);
+    Fq delta = fq_sub(fq_mont(fq_sub(z, z2), sum_y), fq_mul(z3, fq_sub(two_n, one)));
+    Fq x2 = fq_mul(x, x);
+    // E1
+    st_fq(tsc + tb + o1 + 0, fq_sub(that, delta));  tidx[tb + o1 + 0] = iG;
+    st_fq(tsc + tb + o1 + 1, taux);                 tidx[tb + o1 + 1] = iH;
+    st_fq(tsc + tb + o1 + 2, fq_neg(z2));           tidx[tb + o1 + 2] = pb + RP_V;
+    st_fq(tsc + tb + o1 + 3, fq_neg(x));            tidx[tb + o1 + 3] = pb + RP_T1;
+    st_fq(tsc + tb + o1 + 4, fq_neg(x2));           tidx[tb + o1 + 4] = pb + RP_T2;
+    // E2 non-generator terms
+    st_fq(tsc + tb + o2 + 0, one);                  tidx[tb + o2 + 0] = pb + RP_A;
+    st_fq(tsc + tb + o2 + 1, x);                    tidx[tb + o2 + 1] = pb + RP_S;
+    st_fq(tsc + tb + o2 + 2 + 2 * n + 0, fq_neg(mu));          tidx[tb + o2 + 2 + 2 * n + 0] = iH;
+    st_fq(tsc + tb + o2 + 2 + 2 * n + 1, fq_mul(x1, that));    tidx[tb + o2 + 2 + 2 * n + 1] = iU;
+    st_fq(tsc + tb + o2 + 2 + 2 * n + 2, m1);                  tidx[tb + o2 + 2 + 2 * n + 2] = pb + RP_PNEW;
+    // E3
+    st_fq(tsc + tb + o3 + 0, x1);                   tidx[tb + o3 + 0] = iU;
+    st_fq(tsc + tb + o3 + 1, m1);                   tidx[tb + o3 + 1] = pb + RP_UNEW;
+    // E4 non-generator terms
+    st_fq(tsc + tb + o4 + 2 * n + 0, fq_mul(a, b)); tidx[tb + o4 + 2 * n + 0] = pb + RP_UNEW;
+    st_fq(tsc + tb + o4 + 2 * n + 1, m1);           tidx[tb + o4 + 2 * n + 1] = pb + RP_PNEW;
+    u32 base = p * lay.tpp;
+    offsets[4 * p + 0] = base + o1; offsets[4 * p + 1] = base + o2; offsets[4 * p + 2] = base + o3; offsets[4 * p + 3] = base + o4;
+    if (p == nproofs - 1) offsets[4 * nproofs] = base + lay.tpp;
+  }
+}
+
+// accept[p] = all four MSM results of proof p are the identity
+__global__ void k_rp_accept(const Affine* __restrict__ res, u32 nproofs, uint8_t* __restrict__ accept) {
+  u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nproofs) return;
+  bool ok = true;
+  for (int e = 0; e < 4; e++) ok = ok && affine_is_identity(ld_affine(res + 4 * p + e));
+  accept[p] = ok ? 1 : 0;
+}
+
+}  // namespace bp

@@ -1,0 +1,79 @@
+"""Inner-product argument, prover side (reference: src/innerproduct/inner_product_prover.py).
+
+`FastNIProver2.prove` hands the whole round loop to libbpgpu (bp_ipa_prove): per round the two
+(2k+1)-term commitments L, R, the shared-scalar generator folding and the a/b folding run in
+CUDA, while the Fiat-Shamir challenge is hashed on the host between the launches.
+"""
+import ctypes
+from typing import Optional
+
+from .. import _native as nat
+from ..curve import secp256k1
+from ..pippenger import PipSECP256k1
+from ..point import Point
+from ..utils.transcript import Transcript
+from ..utils.utils import ModP
+from .inner_product_verifier import Proof1, Proof2
+
+
+class NIProver:
+    """Protocol 1 (inner_product_prover.py:11-45)."""
+
+    def __init__(self, g, h, u, P, c, a, b, group, seed=b""):
+        assert len(g) == len(h) == len(a) == len(b)
+        self.g, self.h, self.u, self.P, self.c, self.a, self.b = g, h, u, P, c, a, b
+        self.group = group
+        self.transcript = Transcript(seed)
+
+    def prove(self) -> Proof1:
+        x = self.transcript.get_modp(self.group.q)
+        self.transcript.add_number(x)
+        # P_new = P + (x*c)*u ; u_new = x*u
+        P_new, u_new = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
+        inner = FastNIProver2(self.g, self.h, u_new, P_new, self.a, self.b, self.group, self.transcript.digest)
+        return Proof1(u_new, P_new, inner.prove(), self.transcript.digest)
+
+
+class FastNIProver2:
+    """Protocol 2 (inner_product_prover.py:48-110)."""
+
+    def __init__(self, g, h, u, P, a, b, group, transcript: Optional[bytes] = None):
+        assert len(g) == len(h) == len(a) == len(b)
+        assert len(a) & (len(a) - 1) == 0
+        self.log_n = len(a).bit_length() - 1
+        self.n = len(a)
+        self.g, self.h, self.u, self.P, self.a, self.b = g, h, u, P, a, b
+        self.group = group
+        self.transcript = Transcript()
+        if transcript:
+            self.transcript.digest += transcript
+            self.init_transcript_length = len(transcript.split(b"&"))
+        else:
+            self.init_transcript_length = 1
+
+    def prove(self) -> Proof2:
+        n, rounds, q = self.n, self.log_n, self.group.q
+        if q != nat.Q:
+            raise NotImplementedError("libbpgpu implements secp256k1 only")
+        start = self.transcript.digest
+        cap = len(start) + rounds * (2 * 45 + 80) + 16
+        Ls = ctypes.create_string_buffer(64 * max(rounds, 1))
+        Rs = ctypes.create_string_buffer(64 * max(rounds, 1))
+        xs = ctypes.create_string_buffer(32 * max(rounds, 1))
+        a_out, b_out = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        t_out = ctypes.create_string_buffer(cap)
+        t_len = ctypes.c_size_t(0)
+        nat.check(nat.load().bp_ipa_prove(
+            nat.pack_points(self.g), nat.pack_points(self.h), nat.pack_point(self.u),
+            nat.pack_scalars(self.a), nat.pack_scalars(self.b), n, start, len(start),
+            Ls, Rs, xs, a_out, b_out, t_out, cap, ctypes.byref(t_len)))
+        self.transcript.digest = t_out.raw[:t_len.value]
+        return Proof2(
+            ModP(int.from_bytes(a_out.raw, "little"), q),
+            ModP(int.from_bytes(b_out.raw, "little"), q),
+            [ModP(v, q) for v in nat.unpack_scalars(xs.raw, rounds)],
+            [Point.from_bytes64(Ls.raw, 64 * i) for i in range(rounds)],
+            [Point.from_bytes64(Rs.raw, 64 * i) for i in range(rounds)],
+            self.transcript.digest,
+            self.init_transcript_length,
+        )

@@ -1,0 +1,117 @@
+"""Inner-product argument, verifier side (reference: src/innerproduct/inner_product_verifier.py).
+
+Proof containers keep the reference's attribute names.  The transcript re-checks are host string
+work; the point equations run on the GPU as batched multi-scalar multiplications
+(bp_ipa_verify_eq / bp_msm_batch) and are compared exactly.
+"""
+import ctypes
+
+from .. import _native as nat
+from ..curve import secp256k1
+from ..pippenger import PipSECP256k1
+from ..point import Point
+from ..utils.utils import mod_hash, point_to_b64, ModP
+
+SUPERCURVE = secp256k1
+
+
+class Proof1:
+    """Protocol 1 proof (inner_product_verifier.py:10-17)."""
+
+    def __init__(self, u_new, P_new, proof2, transcript):
+        self.u_new = u_new
+        self.P_new = P_new
+        self.proof2 = proof2
+        self.transcript = transcript
+
+
+class Proof2:
+    """Protocol 2 proof (inner_product_verifier.py:61-73)."""
+
+    def __init__(self, a, b, xs, Ls, Rs, transcript, start_transcript: int = 0):
+        self.a = a
+        self.b = b
+        self.xs = xs
+        self.Ls = Ls
+        self.Rs = Rs
+        self.transcript = transcript
+        self.start_transcript = start_transcript
+
+
+class _Checker:
+    def assertThat(self, expr):
+        if not expr:
+            raise Exception("Proof invalid")
+
+
+class Verifier1(_Checker):
+    """Protocol 1 verifier (inner_product_verifier.py:20-58)."""
+
+    def __init__(self, g, h, u, P, c, proof1):
+        self.g, self.h, self.u, self.P, self.c, self.proof1 = g, h, u, P, c, proof1
+
+    def verify_transcript(self):
+        parts = self.proof1.transcript.split(b"&")
+        self.assertThat(parts[1] == str(mod_hash(b"&".join(parts[:1]) + b"&", SUPERCURVE.q)).encode())
+
+    def verify(self):
+        self.verify_transcript()
+        x = ModP(int(self.proof1.transcript.split(b"&")[1]), SUPERCURVE.q)
+        # P_new == P + (x*c)*u  and  u_new == x*u, both right-hand sides in one device pass
+        rhs_P, rhs_u = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
+        self.assertThat(self.proof1.P_new == rhs_P)
+        self.assertThat(self.proof1.u_new == rhs_u)
+        return Verifier2(self.g, self.h, self.proof1.u_new, self.proof1.P_new, self.proof1.proof2).verify()
+
+
+class Verifier2(_Checker):
+    """Protocol 2 verifier (inner_product_verifier.py:76-147)."""
+
+    def __init__(self, g, h, u, P, proof: Proof2):
+        self.g, self.h, self.u, self.P, self.proof = g, h, u, P, proof
+
+    def get_ss(self, xs):
+        """s_i = prod_j xs[j]^(+1 if bit j (MSB first) of i is set else -1), built in O(n) by flipping
+        one factor at a time (same values as inner_product_verifier.py:91-102)."""
+        q = SUPERCURVE.q
+        n = len(self.g)
+        log_n = n.bit_length() - 1
+        x = [int(v % q) for v in xs]
+        sq = [v * v % q for v in x]
+        first = 1
+        for v in x[:log_n]:
+            first = first * v % q
+        ss = [pow(first, -1, q) if log_n else 1] * n
+        for i in range(1, n):
+            top = i.bit_length() - 1
+            ss[i] = ss[i - (1 << top)] * sq[log_n - 1 - top] % q
+        return [ModP(s, q) for s in ss]
+
+    def verify_transcript(self):
+        proof = self.proof
+        start = proof.start_transcript
+        log_n = len(self.g).bit_length() - 1
+        parts = proof.transcript.split(b"&")
+        for i in range(log_n):
+            at = start + 3 * i
+            self.assertThat(parts[at] == point_to_b64(proof.Ls[i]))
+            self.assertThat(parts[at + 1] == point_to_b64(proof.Rs[i]))
+            expect = str(mod_hash(b"&".join(parts[:at + 2]) + b"&", SUPERCURVE.q)).encode()
+            self.assertThat(str(proof.xs[i]).encode() == parts[at + 2] == expect)
+
+    def verify(self):
+        self.verify_transcript()
+        proof = self.proof
+        n = len(self.g)
+        log_n = n.bit_length() - 1
+        for x in proof.xs[:log_n]:
+            if x % SUPERCURVE.q == 0:
+                raise Exception("modular inverse does not exist")      # ModP.inv, utils.py:69-70
+        accept = ctypes.c_int(0)
+        nat.check(nat.load().bp_ipa_verify_eq(
+            nat.pack_points(self.g), nat.pack_points(self.h), nat.pack_point(self.u), nat.pack_point(self.P), n,
+            nat.pack_scalar(proof.a), nat.pack_scalar(proof.b), nat.pack_scalars(proof.xs[:log_n]),
+            nat.pack_points(proof.Ls[:log_n]), nat.pack_points(proof.Rs[:log_n]), ctypes.byref(accept)))
+        self.assertThat(accept.value == 1)
+        print("OK")
+        return True

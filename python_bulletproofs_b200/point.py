@@ -1,0 +1,70 @@
+"""Point type with the surface the reference uses from fastecdsa.point.Point
+(`.x .y .curve`, `IDENTITY_ELEMENT`, `+`, `int * Point`, `==`).
+
+The group law itself runs on the GPU: `P + Q` and `k * P` are 2- and 1-term calls into the
+CUDA MSM (libbpgpu, no CPU fallback).  They exist for API compatibility (e.g. `commitment`,
+utils/commitments.py); the provers/verifiers of this package batch their point work into
+larger device calls instead of using these operators in loops.
+"""
+from . import _native as nat
+from .curve import secp256k1
+
+
+class Point:
+    IDENTITY_ELEMENT = None   # assigned below; also visible on instances (group.py:29 uses G.IDENTITY_ELEMENT)
+
+    __slots__ = ("x", "y", "curve")
+
+    def __init__(self, x, y, curve=secp256k1):
+        self.x, self.y, self.curve = x, y, curve
+
+    # -- boundary helpers
+    @classmethod
+    def from_bytes64(cls, b, off=0):
+        xy = nat.unpack_xy(b, off)
+        return cls.IDENTITY_ELEMENT if xy is None else cls(xy[0], xy[1], secp256k1)
+
+    def _is_identity(self):
+        return self.curve is None
+
+    # -- group law on the device
+    def __add__(self, other):
+        if not hasattr(other, "x") or not hasattr(other, "curve"):
+            return NotImplemented
+        one = (1).to_bytes(32, "little")
+        return Point.from_bytes64(nat.msm_bytes(nat.pack_point(self) + nat.pack_point(other), one + one, 2))
+
+    def __radd__(self, other):
+        return self.__add__(other)
+
+    def __neg__(self):
+        if self._is_identity():
+            return self
+        return Point(self.x, (-self.y) % self.curve.p, self.curve)
+
+    def __sub__(self, other):
+        return self + (-other)
+
+    def __mul__(self, k):
+        if not isinstance(k, int):
+            k = k % secp256k1.q          # ModP and friends
+        return Point.from_bytes64(nat.msm_bytes(nat.pack_point(self), nat.pack_scalar(k), 1))
+
+    __rmul__ = __mul__
+
+    def __eq__(self, other):
+        if not hasattr(other, "x") or not hasattr(other, "curve"):
+            return NotImplemented
+        a, b = self.curve is None, other.curve is None
+        if a or b:
+            return a and b
+        return self.x == other.x and self.y == other.y
+
+    def __hash__(self):
+        return hash((self.x, self.y, self.curve is None))
+
+    def __repr__(self):
+        return "<POINT AT INFINITY>" if self._is_identity() else "X: 0x%x\nY: 0x%x\n(On curve <%s>)" % (self.x, self.y, self.curve)
+
+
+Point.IDENTITY_ELEMENT = Point(0, 0, None)

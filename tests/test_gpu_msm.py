@@ -1,0 +1,157 @@
+"""Parity of the CUDA multi-scalar multiplication (bp_msm & friends, through the C ABI) with
+the golden outputs of the reference's Pippenger.multiexp and with the CPU oracle.  Bit-exact
+affine outputs."""
+import ctypes
+import random
+
+import pytest
+
+from oracle import ecc, protocol_oracle as po
+from python_bulletproofs_b200 import _native as nat
+from helpers import c3_inputs, explicit_case, fast_points
+from gpu_util import gpu_msm, gpu_msm_raw
+
+pytestmark = pytest.mark.gpu
+Q = ecc.Q
+
+
+def test_msm_golden_reference_outputs(golden):
+    """Every vector recorded from the unmodified reference (tests/golden/msm.json)."""
+    for case in golden("msm")["cases"]:
+        pts, ks = c3_inputs(case["lgn"], case["n"]) if case["kind"] == "c3" else explicit_case(case)
+        got = gpu_msm(pts, ks)
+        assert po.enc_point(got).hex() == case["out"], case.get("name", case.get("lgn"))
+
+
+@pytest.mark.parametrize("c", [1, 2, 3, 4, 5, 7, 8, 11, 13, 16])
+def test_msm_every_window_size(c):
+    pts, ks = c3_inputs(7)
+    want = ecc.msm(pts, ks)
+    lib = nat.load()
+    try:
+        nat.check(lib.bp_msm_set_window(c))
+        assert gpu_msm(pts, ks) == want
+        assert lib.bp_msm_last_window() == c
+    finally:
+        lib.bp_msm_set_window(0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 31, 32, 33, 255, 256, 257, 1000, 4096, 5000])
+def test_msm_vs_oracle_sizes(n):
+    rng = random.Random(n)
+    pts = fast_points(n, 1000 + n)
+    ks = [rng.getrandbits(256) for _ in range(n)]          # unreduced: the device reduces mod q
+    assert gpu_msm(pts, ks) == ecc.msm(pts, ks)
+
+
+def test_msm_adversarial_scalars():
+    """Range-proof shaped inputs (rangeproof_prover.py:42-47,83): huge buckets, 0/1/q-1 scalars,
+    repeated points, P and -P in one bucket."""
+    n = 2048
+    pts = fast_points(n, 77)
+    rng = random.Random(3)
+    z = rng.getrandbits(256) % Q
+    cases = {
+        "all_same_scalar": [z] * n,
+        "bits_and_minus_one": [rng.getrandbits(1) for _ in range(n // 2)] + [Q - 1 if rng.getrandbits(1) else 0 for _ in range(n // 2)],
+        "all_zero": [0] * n,
+        "all_q_minus_1": [Q - 1] * n,
+        "small": [rng.randrange(0, 5) for _ in range(n)],
+        "half_q": [(Q // 2) + rng.randrange(-2, 3) for _ in range(n)],
+        "pow2": [1 << rng.randrange(0, 256) for _ in range(n)],
+    }
+    for name, ks in cases.items():
+        assert gpu_msm(pts, ks) == ecc.msm(pts, ks), name
+    same_pt = [pts[0]] * n
+    ks = [rng.getrandbits(256) for _ in range(n)]
+    assert gpu_msm(same_pt, ks) == ecc.msm(same_pt, ks)
+    cancel = pts[:n // 2] + [ecc.point_neg(p) for p in pts[:n // 2]]
+    ks2 = ks[:n // 2] * 2
+    assert gpu_msm(cancel, ks2) is None
+    with_ident = [None if i % 3 == 0 else p for i, p in enumerate(pts)]
+    assert gpu_msm(with_ident, ks) == ecc.msm(with_ident, ks)
+
+
+@pytest.mark.parametrize("lgn", [14, 16])
+def test_msm_large_vs_oracle(lgn):
+    n = 1 << lgn
+    pts = fast_points(n, lgn)
+    pb = ecc.pack_points(pts)
+    rng = random.Random(lgn)
+    sb = bytes(rng.getrandbits(8) for _ in range(32 * n))
+    assert gpu_msm_raw(pb, sb, n) == ecc.msm_bytes(pb, sb, n, "bucket", ecc.max_threads())
+
+
+def test_msm_full_size_properties():
+    """BASELINE size 2^20: slice additivity + linearity + agreement with the multi-threaded oracle."""
+    n = 1 << 20
+    base = fast_points(1 << 12, 4242)
+    rng = random.Random(20)
+    pb = b"".join(ecc.pack_point(base[rng.randrange(len(base))]) for _ in range(n))
+    sb = rng.randbytes(32 * n)
+    lib = nat.load()
+    hp, hs = ctypes.c_uint64(), ctypes.c_uint64()
+    nat.check(lib.bp_points_upload(pb, n, ctypes.byref(hp)))
+    nat.check(lib.bp_scalars_upload(sb, n, ctypes.byref(hs)))
+    out = ctypes.create_string_buffer(64)
+    nat.check(lib.bp_msm_hh(hp, hs, n, out))
+    full = ecc.unpack_point(out.raw)
+    # same through the host-buffer entry point and the host-scalar entry point
+    assert gpu_msm_raw(pb, sb, n) == full
+    nat.check(lib.bp_msm_h(hp, sb, n, out))
+    assert ecc.unpack_point(out.raw) == full
+    # slice additivity: sum of 3 uneven XYZZ partials == full
+    cuts = [0, 300001, 777777, n]
+    parts = b""
+    part = ctypes.create_string_buffer(128)
+    for lo, hi in zip(cuts, cuts[1:]):
+        nat.check(lib.bp_msm_hh_partial(hp, hs, lo, hi - lo, part))
+        parts += part.raw
+    nat.check(lib.bp_xyzz_sum(parts, 3, out))
+    assert ecc.unpack_point(out.raw) == full
+    # oracle (bucket method, all host threads)
+    assert ecc.msm_bytes(pb, sb, n, "bucket", ecc.max_threads()) == full
+    lib.bp_handle_free(hp)
+    lib.bp_handle_free(hs)
+
+
+def test_msm_batch_matches_singles():
+    rng = random.Random(8)
+    sizes = [0, 1, 2, 12, 129, 64, 0, 257, 5]
+    pts, ks, offsets = [], [], [0]
+    for s in sizes:
+        pts += fast_points(s, 500 + s)
+        ks += [rng.getrandbits(256) for _ in range(s)]
+        offsets.append(len(pts))
+    raw = nat.msm_batch_bytes(ecc.pack_points(pts), b"".join(k.to_bytes(32, "little") for k in ks), offsets)
+    for j, s in enumerate(sizes):
+        lo, hi = offsets[j], offsets[j + 1]
+        assert ecc.unpack_point(raw[64 * j:64 * j + 64]) == ecc.msm(pts[lo:hi], ks[lo:hi]), j
+
+
+def test_scalar_mul_batch():
+    n = 300
+    rng = random.Random(12)
+    pts = fast_points(n, 13)
+    pts[5] = None
+    ks = [rng.getrandbits(256) for _ in range(n)]
+    ks[0], ks[1], ks[2] = 0, 1, Q - 1
+    raw = nat.scalar_mul_batch_bytes(ecc.pack_points(pts), b"".join(k.to_bytes(32, "little") for k in ks), n)
+    assert ecc.unpack_points(raw, n) == ecc.scalar_mul_batch(pts, ks)
+
+
+def test_pippenger_dropin_api():
+    """Same call / error behaviour as src/pippenger/pippenger.py:22-29."""
+    from python_bulletproofs_b200.pippenger import PipSECP256k1
+    from python_bulletproofs_b200 import Point, secp256k1
+    from python_bulletproofs_b200.utils import ModP
+    pts, ks = c3_inputs(5)
+    P = [Point(x, y, secp256k1) for x, y in pts]
+    r = PipSECP256k1.multiexp(P, [ModP(k, Q) for k in ks])
+    assert (r.x, r.y) == ecc.msm(pts, ks)
+    assert PipSECP256k1.multiexp([], []) == Point.IDENTITY_ELEMENT
+    with pytest.raises(Exception, match="Different number of group elements and exponents"):
+        PipSECP256k1.multiexp(P, ks[:-1])
+    assert (P[0] + P[1]) == Point(*ecc.py_add(pts[0], pts[1]), secp256k1)
+    assert (5 * P[0]) == (P[0] * 5) == Point(*ecc.py_mul(pts[0], 5), secp256k1)
+    assert P[0] + (-P[0]) == Point.IDENTITY_ELEMENT
