@@ -1,0 +1,154 @@
+"""Shared arithmetic of the (aggregated) range proof, written once for m >= 1 values.
+
+For m = 1 every formula of the aggregated protocol (rangeproof_aggreg_prover.py /
+rangeproof_aggreg_verifier.py) collapses to the single-value one (rangeproof_prover.py /
+rangeproof_verifier.py), including the `rho = H(str(2*n) + t)` derivation, so both public
+prover classes and both verifier classes are thin shells around this module.
+
+Division of labour: the O(nm) Z_q algebra and the transcript stay on the host in Python ints
+(SURVEY.md 8f rows N1/N3 are "next"); every elliptic-curve operation goes to the GPU as a
+multi-scalar multiplication, a scalar-multiplication batch, or the IPA round loop.
+"""
+from .. import _native as nat
+from ..innerproduct.inner_product_prover import NIProver
+from ..innerproduct.inner_product_verifier import Verifier1
+from ..pippenger import PipSECP256k1
+from ..point import Point
+from ..utils.transcript import Transcript
+from ..utils.utils import ModP, mod_hash, point_to_b64
+
+
+class Proof:
+    """Range proof container (rangeproof_verifier.py:10-22; the aggregated module's copy is identical)."""
+
+    def __init__(self, taux, mu, t_hat, T1, T2, A, S, innerProof, transcript):
+        self.taux = taux
+        self.mu = mu
+        self.t_hat = t_hat
+        self.T1 = T1
+        self.T2 = T2
+        self.A = A
+        self.S = S
+        self.innerProof = innerProof
+        self.transcript = transcript
+
+
+def _position_constants(y, z, n, nm, q):
+    """y^i and z^(2 + i//n) * 2^(i % n) for i < nm."""
+    ypow = [1] * nm
+    for i in range(1, nm):
+        ypow[i] = ypow[i - 1] * y % q
+    two = [pow(2, i, q) for i in range(n)]
+    zz = []
+    zj = z * z % q
+    for _ in range(nm // n):
+        zz += [zj * t % q for t in two]
+        zj = zj * z % q
+    return ypow, zz
+
+
+def scale_generators(hs, y, q):
+    """hsp[i] = y^-i * hs[i]  (rangeproof_prover.py:77): one batched device call."""
+    n = len(hs)
+    yinv = pow(int(y % q), -1, q)
+    ks, acc = [], 1
+    for _ in range(n):
+        ks.append(acc)
+        acc = acc * yinv % q
+    raw = nat.scalar_mul_batch_bytes(nat.pack_points(hs), nat.pack_scalars(ks), n)
+    return [Point.from_bytes64(raw, 64 * i) for i in range(n)]
+
+
+def prove(vs, n, g, h, gs, hs, gammas, u, group, transcript: Transcript):
+    q = group.q
+    m = len(vs)
+    nm = n * m
+    aL = []
+    for v in vs:
+        aL += [(v.x >> i) & 1 for i in range(n)]            # reversed(bin(v).zfill(n))[:n]
+    aR = [(bit - 1) % q for bit in aL]
+    t0 = transcript.digest
+    alpha = mod_hash(b"alpha" + t0, q).x
+    sL = [mod_hash(str(i).encode() + t0, q).x for i in range(nm)]
+    sR = [mod_hash(str(i).encode() + t0, q).x for i in range(nm, 2 * nm)]
+    rho = mod_hash(str(2 * n).encode() + t0, q).x           # reference quirk: index 2*n even when m > 1
+    # A = <aL,gs> + <aR,hs> + alpha*h ; S likewise: two (2nm+1)-term MSMs in one device pass
+    base = gs + hs + [h]
+    A, S = PipSECP256k1.multiexp_batch([base, base], [aL + aR + [alpha], sL + sR + [rho]])
+    transcript.add_list_points([A, S])
+    y = transcript.get_modp(q)
+    transcript.add_number(y)
+    z = transcript.get_modp(q)
+    transcript.add_number(z)
+    yv, zv = y.x, z.x
+    ypow, zz = _position_constants(yv, zv, n, nm, q)
+    ysR = [ypow[i] * sR[i] % q for i in range(nm)]
+    t1 = (sum(sL[i] * (ypow[i] * (aR[i] + zv) + zz[i]) for i in range(nm))
+          + sum((aL[i] - zv) * ysR[i] for i in range(nm))) % q
+    t2 = sum(sL[i] * ysR[i] for i in range(nm)) % q
+    t1_that = transcript.digest
+    tau1 = mod_hash(b"tau1" + t1_that, q).x
+    tau2 = mod_hash(b"tau2" + t1_that, q).x
+    T1, T2 = PipSECP256k1.multiexp_batch([[g, h], [g, h]], [[t1, tau1], [t2, tau2]])
+    transcript.add_list_points([T1, T2])
+    x = transcript.get_modp(q)
+    transcript.add_number(x)
+    xv = x.x
+    ls = [(aL[i] - zv + sL[i] * xv) % q for i in range(nm)]
+    rs = [(ypow[i] * (aR[i] + zv + sR[i] * xv) + zz[i]) % q for i in range(nm)]
+    t_hat = sum(a * b for a, b in zip(ls, rs)) % q
+    zpow = zv * zv % q
+    gsum = 0
+    for j in range(m):
+        gsum += zpow * gammas[j].x
+        zpow = zpow * zv % q
+    taux = (tau2 * xv * xv + tau1 * xv + gsum) % q
+    mu = (alpha + rho * xv) % q
+    hsp = scale_generators(hs, y, q)
+    # P - mu*h = A + x*S + sum(-z * gs_i) + sum((z*y^i + zz_i) * hsp_i) - mu*h : one MSM
+    P_inner = PipSECP256k1.multiexp(
+        [A, S, h] + gs + hsp,
+        [1, xv, -mu] + [-zv] * nm + [(zv * ypow[i] + zz[i]) % q for i in range(nm)])
+    inner = NIProver(gs, hsp, u, P_inner, ModP(t_hat, q), [ModP(v, q) for v in ls], [ModP(v, q) for v in rs], group)
+    return Proof(ModP(taux, q), ModP(mu, q), ModP(t_hat, q), T1, T2, A, S, inner.prove(), transcript.digest)
+
+
+class VerifierCore:
+    """verify_transcript + verify shared by RangeVerifier and AggregRangeVerifier."""
+
+    def assertThat(self, expr: bool):
+        if not expr:
+            raise Exception("Proof invalid")
+
+    def verify_transcript(self):
+        """rangeproof_verifier.py:42-53: A, S, T1, T2 must sit in slots 1, 2, 5, 6; y, z, x are READ
+        from slots 3, 4, 7 (never re-hashed)."""
+        proof = self.proof
+        p = proof.taux.p
+        slots = proof.transcript.split(b"&")
+        self.assertThat(slots[1] == point_to_b64(proof.A))
+        self.assertThat(slots[2] == point_to_b64(proof.S))
+        self.y = ModP(int(slots[3]), p)
+        self.z = ModP(int(slots[4]), p)
+        self.assertThat(slots[5] == point_to_b64(proof.T1))
+        self.assertThat(slots[6] == point_to_b64(proof.T2))
+        self.x = ModP(int(slots[7]), p)
+
+    def _verify(self, Vs):
+        self.verify_transcript()
+        q = self.proof.taux.p
+        proof, g, h, gs, hs = self.proof, self.g, self.h, self.gs, self.hs
+        nm, m = len(gs), len(Vs)
+        n = nm // m
+        xv, yv, zv = self.x.x % q, self.y.x % q, self.z.x % q
+        ypow, zz = _position_constants(yv, zv, n, nm, q)
+        zpows = [pow(zv, j + 2, q) for j in range(m + 1)]
+        delta = ((zv - zv * zv) * sum(ypow) - sum(zpows[j] * (2 ** n - 1) for j in range(1, m + 1))) % q
+        hsp = scale_generators(hs, self.y, q)
+        # t_hat*g + taux*h == sum z^(j+2) V_j + delta*g + x*T1 + x^2*T2      (one device pass, exact compare)
+        lhs, rhs, P_inner = PipSECP256k1.multiexp_batch(
+            [[g, h], list(Vs) + [g, proof.T1, proof.T2], [proof.A, proof.S, h] + gs + hsp],
+            [[proof.t_hat, proof.taux], zpows[:m] + [delta, xv, xv * xv % q],
+             [1, xv, -(proof.mu.x)] + [-zv] * nm + [(zv * ypow[i] + zz[i]) % q for i in range(nm)]])
+        self.assertThat(lhs == rhs)
+        return Verifier1(gs, hsp, self.u, P_inner, proof.t_hat, proof.innerProof).verify()

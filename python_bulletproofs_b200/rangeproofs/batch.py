@@ -1,0 +1,92 @@
+"""Batch verification of independent single-value range proofs over one generator set
+(BASELINE config 5).  Not an API of the reference -- it is the data-parallel form of calling
+`RangeVerifier(V_i, g, h, gs, hs, u, proof_i).verify()` for every i, with the same decisions.
+
+Packing of a proof follows include/bp_gpu.h (bp_rp_verify_batch); the per-proof transcript
+checks run in C on host threads, the scalar algebra and all point equations on the GPU.
+"""
+import ctypes
+
+from .. import _native as nat
+from .rangeproof_verifier import RangeVerifier
+
+
+def pack_proof(V, proof, log_n):
+    ip = proof.innerProof
+    p2 = ip.proof2
+    le = lambda s: (s % nat.Q).to_bytes(32, "little")          # noqa: E731
+    rec = [nat.pack_point(V), nat.pack_point(proof.A), nat.pack_point(proof.S), nat.pack_point(proof.T1),
+           nat.pack_point(proof.T2), le(proof.taux), le(proof.mu), le(proof.t_hat),
+           nat.pack_point(ip.u_new), nat.pack_point(ip.P_new), le(p2.a), le(p2.b)]
+    rec += [le(x) for x in p2.xs[:log_n]]
+    rec += [nat.pack_point(L) for L in p2.Ls[:log_n]] + [nat.pack_point(R) for R in p2.Rs[:log_n]]
+    return b"".join(rec), (proof.transcript, ip.transcript, p2.transcript), p2.start_transcript
+
+
+class PackedBatch:
+    """A batch in the wire layout of bp_rp_verify_batch (struct-of-records + transcript blob)."""
+
+    def __init__(self, n, records, transcripts, starts):
+        self.n = n
+        self.nproofs = len(records)
+        self.records = b"".join(records)
+        self.stride = len(records[0]) if records else nat.load().bp_rp_proof_stride(n)
+        offs, blob, pos = [0], [], 0
+        for trio in transcripts:
+            for t in trio:
+                blob.append(t)
+                pos += len(t)
+                offs.append(pos)
+        self.blob = b"".join(blob)
+        self.tr_off = (ctypes.c_uint64 * len(offs))(*offs)
+        self.starts = (ctypes.c_uint32 * max(len(starts), 1))(*starts)
+
+    @classmethod
+    def from_proofs(cls, Vs, proofs, n):
+        log_n = n.bit_length() - 1
+        recs, trs, sts = [], [], []
+        for V, pr in zip(Vs, proofs):
+            if len(pr.innerProof.proof2.xs) != log_n or len(pr.innerProof.proof2.Ls) != log_n or len(pr.innerProof.proof2.Rs) != log_n:
+                raise ValueError("proof shape does not match the generator count")
+            r, t, s = pack_proof(V, pr, log_n)
+            recs.append(r)
+            trs.append(t)
+            sts.append(s)
+        return cls(n, recs, trs, sts)
+
+
+def verify_packed(batch: PackedBatch, g, h, gs, hs, u, first=0, count=None):
+    """accept bytes (1 accept / 0 reject / 2 defer-to-Python) for proofs [first, first+count)."""
+    count = batch.nproofs - first if count is None else count
+    accept = ctypes.create_string_buffer(max(count, 1))
+    tr_off = ctypes.cast(ctypes.byref(batch.tr_off, 8 * 3 * first), ctypes.POINTER(ctypes.c_uint64))
+    starts = ctypes.cast(ctypes.byref(batch.starts, 4 * first), ctypes.POINTER(ctypes.c_uint32))
+    recs = ctypes.c_char_p(batch.records[first * batch.stride:(first + count) * batch.stride])
+    nat.check(nat.load().bp_rp_verify_batch(
+        nat.pack_points(gs), nat.pack_points(hs), nat.pack_point(g), nat.pack_point(h), nat.pack_point(u), batch.n,
+        recs, batch.stride, count, batch.blob, tr_off, starts, accept))
+    return accept.raw[:count]
+
+
+def verify_range_proofs_batch(Vs, g, h, gs, hs, u, proofs):
+    """-> list[bool].  A proof the C layer cannot classify (exotic numeric transcript slot) is replayed
+    through RangeVerifier so that the reference's exception type (ValueError / IndexError) surfaces."""
+    n = len(gs)
+    if len(Vs) != len(proofs):
+        raise Exception('Different number of commitments and proofs')
+    batch = PackedBatch.from_proofs(Vs, proofs, n)
+    acc = verify_packed(batch, g, h, gs, hs, u)
+    out = []
+    for i, a in enumerate(acc):
+        if a == 2:
+            try:
+                import contextlib, io
+                with contextlib.redirect_stdout(io.StringIO()):
+                    out.append(bool(RangeVerifier(Vs[i], g, h, gs, hs, u, proofs[i]).verify()))
+            except Exception as e:      # noqa: BLE001
+                if str(e) != "Proof invalid":
+                    raise
+                out.append(False)
+        else:
+            out.append(a == 1)
+    return out

@@ -1,0 +1,232 @@
+"""Parity of the GPU-backed provers / verifiers (the reference's class API re-hosted on libbpgpu)
+with the golden proofs recorded from the unmodified reference and with the CPU oracle:
+identical serialised proofs, identical transcripts, identical accept/reject."""
+import contextlib
+import ctypes
+import io
+import random
+
+import pytest
+
+from oracle import ecc, protocol_oracle as po
+from helpers import gens, ipa_inputs
+from python_bulletproofs_b200 import Point, secp256k1, _native as nat
+from python_bulletproofs_b200.utils import ModP, commitment, vector_commitment, inner_product, mod_hash, elliptic_hash
+from python_bulletproofs_b200.innerproduct import NIProver, FastNIProver2, Verifier1, Verifier2, Proof2
+from python_bulletproofs_b200.rangeproofs import (NIRangeProver, RangeVerifier, AggregNIRangeProver,
+                                                   AggregRangeVerifier, verify_range_proofs_batch)
+
+pytestmark = pytest.mark.gpu
+Q = ecc.Q
+
+
+def P_(t):
+    return Point.IDENTITY_ELEMENT if t is None else Point(t[0], t[1], secp256k1)
+
+
+def T_(p):
+    return None if p.curve is None else (p.x, p.y)
+
+
+def M_(v):
+    return ModP(v, Q)
+
+
+def quiet(fn):
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        try:
+            ok = fn()
+        except Exception as e:   # noqa: BLE001
+            if str(e) != "Proof invalid":
+                raise
+            return False
+    assert ok is True and buf.getvalue() == "OK\n"     # inner_product_verifier.py:146-147
+    return True
+
+
+def p2_json(p2):
+    return po.proof2_to_json({"a": p2.a.x, "b": p2.b.x, "xs": [x.x for x in p2.xs], "Ls": [T_(p) for p in p2.Ls],
+                              "Rs": [T_(p) for p in p2.Rs], "transcript": p2.transcript, "start": p2.start_transcript})
+
+
+def p1_json(p1):
+    return {"u_new": po.enc_point(T_(p1.u_new)).hex(), "P_new": po.enc_point(T_(p1.P_new)).hex(),
+            "transcript": p1.transcript.decode("latin1"), "p2": p2_json(p1.proof2)}
+
+
+def range_json(pr):
+    return {"taux": str(pr.taux.x), "mu": str(pr.mu.x), "t_hat": str(pr.t_hat.x),
+            "T1": po.enc_point(T_(pr.T1)).hex(), "T2": po.enc_point(T_(pr.T2)).hex(),
+            "A": po.enc_point(T_(pr.A)).hex(), "S": po.enc_point(T_(pr.S)).hex(),
+            "transcript": pr.transcript.decode("latin1"), "ip": p1_json(pr.innerProof)}
+
+
+def test_host_hashes_match_oracle():
+    for msg in (b"", b"abc", b"&", b"x" * 1000):
+        assert mod_hash(msg, Q).x == po.mod_hash(msg)
+        out = ctypes.create_string_buffer(32)
+        nat.check(nat.load().bp_mod_hash(msg, len(msg), out))
+        assert int.from_bytes(out.raw, "little") == po.mod_hash(msg)
+        assert T_(elliptic_hash(msg, secp256k1)) == po.elliptic_hash(msg)
+    for pt in (None, ecc.G, ecc.py_mul(ecc.G, 12345)):
+        out = ctypes.create_string_buffer(45)
+        ln = ctypes.c_size_t()
+        nat.check(nat.load().bp_point_to_b64(ecc.pack_point(pt), out, ctypes.byref(ln)))
+        assert out.raw[:ln.value] == po.b64_point(pt)
+
+
+@pytest.mark.parametrize("n", [2, 4, 16, 64, 256])
+def test_fold_round_vs_oracle(n):
+    g, h, u, a, b = ipa_inputs(min(n, 16), ["f0", "f1", "f2", "f3", "f4"])
+    rng = random.Random(n)
+    g = (g * (n // len(g) + 1))[:n]
+    h = (h * (n // len(h) + 1))[:n]
+    a = [rng.getrandbits(256) % Q for _ in range(n)]
+    b = [rng.getrandbits(256) % Q for _ in range(n)]
+    x = rng.getrandbits(256) % Q
+    k = n // 2
+    go, ho = ctypes.create_string_buffer(64 * k), ctypes.create_string_buffer(64 * k)
+    ao, bo = ctypes.create_string_buffer(32 * k), ctypes.create_string_buffer(32 * k)
+    nat.check(nat.load().bp_ipa_fold_round(ecc.pack_points(g), ecc.pack_points(h), ecc.pack_scalars(a), ecc.pack_scalars(b), n,
+                                           x.to_bytes(32, "little"), go, ho, ao, bo))
+    xi = pow(x, -1, Q)
+    assert ecc.unpack_points(go.raw, k) == ecc.fold(g[:k], g[k:], xi, x)          # inner_product_prover.py:107
+    assert ecc.unpack_points(ho.raw, k) == ecc.fold(h[:k], h[k:], x, xi)          # :108
+    assert nat.unpack_scalars(ao.raw, k) == [(x * lo + xi * hi) % Q for lo, hi in zip(a[:k], a[k:])]   # :109
+    assert nat.unpack_scalars(bo.raw, k) == [(xi * lo + x * hi) % Q for lo, hi in zip(b[:k], b[k:])]   # :110
+
+
+@pytest.mark.parametrize("name", ["ipa_small", "ipa_c2"])
+def test_ipa_golden(golden, name):
+    for case in golden(name)["cases"]:
+        N = case["N"]
+        g, h, u, a, b = ipa_inputs(N, case["seeds"])
+        g, h, u = [P_(t) for t in g], [P_(t) for t in h], P_(u)
+        a, b = [M_(v) for v in a], [M_(v) for v in b]
+        Pt = vector_commitment(g, h, a, b)
+        assert po.enc_point(T_(Pt)).hex() == case["P"]
+        c = inner_product(a, b)
+        assert str(c) == case["c"]
+        proof = NIProver(g, h, u, Pt, c, a, b, secp256k1, case["seeds"][5].encode()).prove()
+        assert p1_json(proof) == case["proof1"]
+        assert quiet(Verifier1(g, h, u, Pt, c, proof).verify) is case["verify1"]
+        assert quiet(Verifier1(g, h, u, Pt, c + M_(1), proof).verify) is case["verify1_wrong_c"]
+        P2 = Pt + c * u
+        assert po.enc_point(T_(P2)).hex() == case["P2"]
+        proof2 = FastNIProver2(g, h, u, P2, a, b, secp256k1).prove()
+        assert p2_json(proof2) == case["proof2"]
+        assert quiet(Verifier2(g, h, u, P2, proof2).verify) is case["verify2"]
+
+
+def test_ipa_soundness_smoke():
+    """src/tests/test_innerprod.py:33-98,226-268: wrong P / a / b / u / transcript => Proof invalid."""
+    N = 8
+    g, h, u, a, b = ipa_inputs(N, ["s0", "s1", "s2", "s3", "s4"])
+    g, h, u = [P_(t) for t in g], [P_(t) for t in h], P_(u)
+    a, b = [M_(v) for v in a], [M_(v) for v in b]
+    c = inner_product(a, b)
+    P2 = vector_commitment(g, h, a, b) + c * u
+    proof = FastNIProver2(g, h, u, P2, a, b, secp256k1).prove()
+    assert quiet(Verifier2(g, h, u, P2, proof).verify)
+    assert not quiet(Verifier2(g, h, u, P2 + u, proof).verify)
+    assert not quiet(Verifier2(g, h, 2 * u, P2, proof).verify)
+    for field in ("a", "b"):
+        bad = Proof2(proof.a, proof.b, proof.xs, proof.Ls, proof.Rs, proof.transcript, proof.start_transcript)
+        setattr(bad, field, getattr(bad, field) + M_(1))
+        assert not quiet(Verifier2(g, h, u, P2, bad).verify)
+    t = bytearray(proof.transcript)
+    t[len(t) // 2] ^= 1
+    bad = Proof2(proof.a, proof.b, proof.xs, proof.Ls, proof.Rs, bytes(t), proof.start_transcript)
+    assert not quiet(Verifier2(g, h, u, P2, bad).verify)
+    with pytest.raises(AssertionError):
+        FastNIProver2(g[:3], h[:3], u, P2, a[:3], b[:3], secp256k1)
+
+
+@pytest.mark.parametrize("name", ["range_small", "range_c1"])
+def test_range_golden(golden, name):
+    for case in golden(name)["cases"]:
+        n, v = case["n"], int(case["v"])
+        gs, hs, g, h, u = gens(n, case["seeds"])
+        gs, hs, g, h, u = [P_(t) for t in gs], [P_(t) for t in hs], P_(g), P_(h), P_(u)
+        gamma = mod_hash(case["seeds"][5].encode(), Q)
+        V = commitment(g, h, M_(v), gamma)
+        assert po.enc_point(T_(V)).hex() == case["V"]
+        proof = NIRangeProver(M_(v), n, g, h, gs, hs, gamma, u, secp256k1, case["seeds"][6].encode()).prove()
+        assert range_json(proof) == case["proof"]
+        assert quiet(RangeVerifier(V, g, h, gs, hs, u, proof).verify) is case["verify"]
+        assert quiet(RangeVerifier(V + g, g, h, gs, hs, u, proof).verify) is case["verify_wrong_V"]
+        s = str(proof.t_hat.x)
+        proof.t_hat = M_(int(s[:-1] + ("1" if s[-1] != "1" else "2")))
+        assert quiet(RangeVerifier(V, g, h, gs, hs, u, proof).verify) is case["verify_t_hat_flipped"]
+
+
+@pytest.mark.parametrize("name", ["aggreg_small", "aggreg_c4"])
+def test_aggreg_golden(golden, name):
+    for case in golden(name)["cases"]:
+        n, m = case["n"], case["m"]
+        gs, hs, g, h, u = gens(n * m, case["seeds"])
+        gs, hs, g, h, u = [P_(t) for t in gs], [P_(t) for t in hs], P_(g), P_(h), P_(u)
+        vs = [M_(int(v)) for v in case["vs"]]
+        gammas = [M_(int(x)) for x in case["gammas"]]
+        Vs = [commitment(g, h, vs[i], gammas[i]) for i in range(m)]
+        assert [po.enc_point(T_(V)).hex() for V in Vs] == case["Vs"]
+        proof = AggregNIRangeProver(vs, n, g, h, gs, hs, gammas, u, secp256k1, case["seeds"][6].encode()).prove()
+        assert range_json(proof) == case["proof"]
+        assert quiet(AggregRangeVerifier(Vs, g, h, gs, hs, u, proof).verify) is case["verify"]
+        Vbad = Vs[:-1] + [Vs[-1] + h]
+        assert quiet(AggregRangeVerifier(Vbad, g, h, gs, hs, u, proof).verify) is case["verify_wrong_V"]
+
+
+def test_range_transcript_tamper_value_error(golden):
+    """A non-numeric y slot raises ValueError from int(), as in rangeproof_verifier.py:49."""
+    case = golden("range_small")["cases"][1]
+    n = case["n"]
+    gs, hs, g, h, u = gens(n, case["seeds"])
+    gs, hs, g, h, u = [P_(t) for t in gs], [P_(t) for t in hs], P_(g), P_(h), P_(u)
+    gamma = mod_hash(case["seeds"][5].encode(), Q)
+    v = M_(int(case["v"]))
+    V = commitment(g, h, v, gamma)
+    proof = NIRangeProver(v, n, g, h, gs, hs, gamma, u, secp256k1, case["seeds"][6].encode()).prove()
+    parts = proof.transcript.split(b"&")
+    parts[3] = b"12x4"
+    proof.transcript = b"&".join(parts)
+    with pytest.raises(ValueError):
+        RangeVerifier(V, g, h, gs, hs, u, proof).verify()
+
+
+@pytest.mark.parametrize("n,count", [(8, 40), (64, 24)])
+def test_batch_verify_decisions(n, count):
+    """bp_rp_verify_batch vs the oracle verifier, proof by proof, incl. corrupted proofs of every kind."""
+    seeds = ["b0", "b1", "b2", "b3", "b4"]
+    ogs, ohs, og, oh, ou = gens(n, seeds)
+    gs, hs, g, h, u = [P_(t) for t in ogs], [P_(t) for t in ohs], P_(og), P_(oh), P_(ou)
+    rng = random.Random(5)
+    Vs, proofs, oVs, oproofs = [], [], [], []
+    for i in range(count):
+        v = rng.getrandbits(n)
+        gamma = mod_hash(b"gamma%d" % i, Q)
+        V = commitment(g, h, M_(v), gamma)
+        pr = NIRangeProver(M_(v), n, g, h, gs, hs, gamma, u, secp256k1, b"p%d" % i).prove()
+        kind = i % 8
+        if kind == 1:
+            s = str(pr.t_hat.x); pr.t_hat = M_(int(s[:-1] + ("1" if s[-1] != "1" else "2")))
+        elif kind == 2:
+            V = V + g
+        elif kind == 3:
+            pr.innerProof.proof2.a = pr.innerProof.proof2.a + M_(1)
+        elif kind == 4:
+            t = bytearray(pr.innerProof.proof2.transcript); t[-5] = ord("1") if t[-5] != ord("1") else ord("2")
+            pr.innerProof.proof2.transcript = bytes(t)
+        elif kind == 5:
+            pr.mu = pr.mu + M_(1)
+        elif kind == 6:
+            pr.innerProof.u_new = pr.innerProof.u_new + g
+        Vs.append(V); proofs.append(pr)
+        oVs.append(T_(V)); oproofs.append(po.range_from_json(range_json(pr)))
+    got = verify_range_proofs_batch(Vs, g, h, gs, hs, u, proofs)
+    want = [po.range_verify([oV], og, oh, ogs, ohs, ou, opr) for oV, opr in zip(oVs, oproofs)]
+    assert got == want
+    assert want.count(True) == sum(1 for i in range(count) if i % 8 in (0, 7))
+    # the class API agrees proof by proof
+    for i in (0, 1, 4):
+        assert quiet(RangeVerifier(Vs[i], g, h, gs, hs, u, proofs[i]).verify) is want[i]
