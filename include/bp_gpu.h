@@ -124,6 +124,9 @@ int bp_bench_msm(bp_handle points, bp_handle scalars, size_t n, int warmup, int 
 /* IMAD.WIDE.U32 issue-rate microbenchmark: returns measured 32x32+64 multiply-accumulates per
  * second (the roofline denominator of DESIGN.md) and the lane-ops executed. */
 int bp_imad_peak(int iters, double* macs_per_s, float* ms);
+/* other integer-pipe probes: mode 0 IMAD.WIDE.U32, 1 IMAD (32-bit), 2 carry-chained IMAD.WIDE.U32.X rows as
+ * fp_mul issues them, 3 whole field multiplications (ops = fp_mul/s) */
+int bp_pipe_probe(int mode, int iters, double* ops_per_s, float* ms);
 
 /* ---- arithmetic self-test hooks (known-answer tests against big-int arithmetic) ------------------
  * fp: op 0 mul, 1 add, 2 sub, 3 inv, 4 neg  (inputs any 256-bit residue, output canonical)
@@ -142,6 +145,16 @@ int bp_nccl_init(int rank, int nranks, const uint8_t unique_id[128]);
  * NVLink, every rank adds them and returns the same canonical affine point. */
 int bp_msm_sharded(bp_handle points, bp_handle scalars, size_t first, size_t n, uint8_t out64[64]);
 int bp_allgather_bytes(const uint8_t* send, size_t nbytes, uint8_t* recv);
+/* same with this rank's slice in HOST buffers (H2D inside the call): the end-to-end form */
+int bp_msm_sharded_host(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64]);
+/* bp_bench_msm for the sharded path: the timed region of each iteration covers the slice MSM, the
+ * all-gather and the R-way sum. */
+int bp_bench_msm_sharded(bp_handle points, bp_handle scalars, size_t first, size_t n, int warmup, int iters, int flush_l2,
+                         float* ms_each, uint8_t out64[64]);
+
+/* ---- pinned host staging memory (cudaHostAlloc) for full-rate host<->device copies ------------------- */
+void* bp_host_alloc(size_t bytes);
+int bp_host_free(void* p);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "bp_point_to_b64": (ctypes.c_int, [c_u8p, c_u8p, ctypes.POINTER(c_sz)]),
     "bp_bench_msm": (ctypes.c_int, [c_h, c_h, c_sz, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_u8p]),
     "bp_imad_peak": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]),
+    "bp_pipe_probe": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]),
     "bp_test_fp": (ctypes.c_int, [ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_test_ec": (ctypes.c_int, [ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_test_fq": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
@@ -56,6 +57,10 @@ PROTOTYPES = {
     "bp_nccl_init": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u8p]),
     "bp_msm_sharded": (ctypes.c_int, [c_h, c_h, c_sz, c_sz, c_u8p]),
     "bp_allgather_bytes": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
+    "bp_bench_msm_sharded": (ctypes.c_int, [c_h, c_h, c_sz, c_sz, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_u8p]),
+    "bp_msm_sharded_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_sz, c_u8p]),
+    "bp_host_alloc": (ctypes.c_void_p, [c_sz]),
+    "bp_host_free": (ctypes.c_int, [ctypes.c_void_p]),
 }
 
 _lib = None

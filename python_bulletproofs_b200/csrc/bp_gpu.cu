@@ -102,28 +102,70 @@ static int get_handle(bp_handle h, int kind, HandleRec* out) {
   return 0;
 }
 
-// ---- IMAD.WIDE peak microbenchmark -------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_imad_peak(u32* out, u32 seed, int iters) {
-  // 8 independent 64-bit accumulators per thread, 32x32+64 multiply-accumulate each step.
-  u64 acc[8];
+// ---- integer-pipe microbenchmarks (the measured roofline denominators) ---------------------------
+// mode 0: IMAD.WIDE.U32 (32x32+64 -> 64), 16 independent accumulators per thread
+// mode 1: IMAD (32-bit mad.lo), 16 independent accumulators
+// mode 2: IMAD.WIDE.U32 with the carry predicate chained (mad.lo.cc / madc.hi.cc pairs), as fp_mul issues them
+// mode 3: whole fp_mul (field multiplications per second; 72 IMAD.WIDE each)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pipe_probe(u32* out, u32 seed, int iters) {
   u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  if (MODE == 0) {
+    u64 acc[16];
 #pragma unroll
-  for (int i = 0; i < 8; i++) acc[i] = (u64)(a + i) << 20;
-  for (int it = 0; it < iters; it++) {
+    for (int i = 0; i < 16; i++) acc[i] = (u64)(a + i) << 20;
+    for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
+      for (int r = 0; r < 2; r++)
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        u32 lo = (u32)acc[i], hi = (u32)(acc[i] >> 32);
-        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a ^ hi), "r"(b));
-        (void)lo;
-      }
+        for (int i = 0; i < 16; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
     }
-  }
-  u64 s = 0;
+    u64 s = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) s ^= acc[i];
-  if (s == 0x1234567u) out[0] = (u32)s;   // keep the chain alive
+    for (int i = 0; i < 16; i++) s ^= acc[i];
+    if (s == 0x1234567u) out[0] = (u32)s;
+  } else if (MODE == 1) {
+    u32 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = a + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int i = 0; i < 16; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(a), "r"(b));
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s ^= acc[i];
+    if (s == 0x1234567u) out[0] = s;
+  } else if (MODE == 2) {
+    u32 acc[4][9];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int i = 0; i < 9; i++) acc[j][i] = a + i + j;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) mul_row_mad(acc[j], a, b, a ^ b, a + b, b);     // 4 IMAD.WIDE(.X) + 1 IADD3.X
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int i = 0; i < 9; i++) s ^= acc[j][i];
+    if (s == 0x1234567u) out[0] = s;
+  } else {
+    Fp x, y;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x.v[i] = a * (i + 1); y.v[i] = b + i; }
+    for (int it = 0; it < iters; it++) { x = fp_mul(x, y); y = fp_mul(y, x); }
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= x.v[i] ^ y.v[i];
+    if (s == 0x1234567u) out[0] = s;
+  }
 }
 
 }  // namespace bp
@@ -337,22 +379,32 @@ int bp_bench_msm(bp_handle points, bp_handle scalars, size_t n, int warmup, int 
   return 0;
 }
 
-int bp_imad_peak(int iters, double* macs_per_s, float* ms_out) {
-  BP_NEED_INIT();
+// ops per launch-thread-iteration for each probe mode
+static int pipe_probe(int mode, int iters, double* ops_per_s, float* ms_out) {
   u32* d = (u32*)g.ws_misc.ensure(256);
   int blocks = g.sm_count * 8;
-  k_imad_peak<<<blocks, 256, 0, g.stream>>>(d, 12345u, 16);   // warm-up
-  BP_CUDA(cudaEventRecord(g.ev_a, g.stream));
-  k_imad_peak<<<blocks, 256, 0, g.stream>>>(d, 12345u, iters);
-  BP_CUDA(cudaEventRecord(g.ev_b, g.stream));
-  BP_CUDA(cudaEventSynchronize(g.ev_b));
+  double per_iter = mode == 3 ? 2.0 : 32.0;
+  for (int pass = 0; pass < 2; pass++) {      // pass 0 = warm-up (clocks, I-cache), pass 1 timed
+    int n = pass == 0 ? (iters / 8 > 0 ? iters / 8 : 1) : iters;
+    BP_CUDA(cudaEventRecord(g.ev_a, g.stream));
+    switch (mode) {
+      case 0: k_pipe_probe<0><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 1: k_pipe_probe<1><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 2: k_pipe_probe<2><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 3: k_pipe_probe<3><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      default: return fail("bp_pipe_probe: mode 0..3");
+    }
+    BP_CUDA(cudaEventRecord(g.ev_b, g.stream));
+    BP_CUDA(cudaEventSynchronize(g.ev_b));
+  }
   float ms = 0;
   BP_CUDA(cudaEventElapsedTime(&ms, g.ev_a, g.ev_b));
-  double macs = (double)blocks * 256.0 * (double)iters * 32.0;
-  if (macs_per_s) *macs_per_s = macs / (ms * 1e-3);
+  if (ops_per_s) *ops_per_s = (double)blocks * 256.0 * (double)iters * per_iter / (ms * 1e-3);
   if (ms_out) *ms_out = ms;
   return 0;
 }
+int bp_pipe_probe(int mode, int iters, double* ops_per_s, float* ms_out) { BP_NEED_INIT(); return pipe_probe(mode, iters, ops_per_s, ms_out); }
+int bp_imad_peak(int iters, double* macs_per_s, float* ms_out) { BP_NEED_INIT(); return pipe_probe(0, iters, macs_per_s, ms_out); }
 
 }  // extern "C"
 #include "bp_proto.inl"

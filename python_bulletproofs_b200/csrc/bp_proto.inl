@@ -338,27 +338,86 @@ int bp_allgather_bytes(const uint8_t* send, size_t nbytes, uint8_t* recv) {
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
 }
+// slice MSM on this rank -> ncclAllGather of the 128-byte XYZZ partials over NVLink -> every rank adds
+// the R partials and converts to the (identical, canonical) affine result in d_out.  All on g.stream.
+static int msm_sharded_device(const Affine* pts, const Fq* sc, size_t n, Affine* d_out) {
+  int R = g_comm ? g_nranks : 1;
+  XYZZ* d_part = (XYZZ*)g.ws_lr.ensure((size_t)(R + 1) * sizeof(XYZZ));
+  if (!d_part) return fail("device allocation failed");
+  if (n == 0) BP_CUDA(cudaMemsetAsync(d_part, 0, sizeof(XYZZ), g.stream));
+  else if (msm_run(pts, nullptr, sc, (u32)n, nullptr, 1, n, nullptr, d_part)) return 1;
+  const XYZZ* all = d_part;
+  if (R > 1) {   // the single exchange step of the sharded MSM
+    BP_NCCL(ncclAllGather(d_part, d_part + 1, sizeof(XYZZ), ncclUint8, g_comm, g.stream));
+    all = d_part + 1;
+  }
+  k_xyzz_sum<<<1, 32, 0, g.stream>>>(all, (u32)R, d_out);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int bp_msm_sharded(bp_handle points, bp_handle scalars, size_t first, size_t n, uint8_t out64[64]) {
   BP_NEED_INIT();
   HandleRec P, S;
   if (get_handle(points, 0, &P) || get_handle(scalars, 1, &S)) return 1;
   if (first + n > P.n || first + n > S.n) return fail("bp_msm_sharded: slice exceeds the uploaded vectors");
-  int R = g_comm ? g_nranks : 1;
-  XYZZ* d_part = (XYZZ*)g.ws_lr.ensure((size_t)(R + 1) * sizeof(XYZZ));
   Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
-  if (!d_part || !d_out) return fail("device allocation failed");
-  if (n == 0) BP_CUDA(cudaMemsetAsync(d_part, 0, sizeof(XYZZ), g.stream));
-  else if (msm_run((const Affine*)P.p + first, nullptr, (const Fq*)S.p + first, (u32)n, nullptr, 1, n, nullptr, d_part)) return 1;
-  const XYZZ* all = d_part;
-  if (R > 1) {   // the single exchange step of the sharded MSM: 128 B per rank over NVLink
-    BP_NCCL(ncclAllGather(d_part, d_part + 1, sizeof(XYZZ), ncclUint8, g_comm, g.stream));
-    all = d_part + 1;
-  }
-  k_xyzz_sum<<<1, 32, 0, g.stream>>>(all, (u32)R, d_out);
+  if (!d_out) return fail("device allocation failed");
+  if (msm_sharded_device((const Affine*)P.p + first, (const Fq*)S.p + first, n, d_out)) return 1;
   BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
 }
+
+// host buffers in, host result out: H2D of this rank's slice + slice MSM + all-gather + sum (the end-to-end form)
+int bp_msm_sharded_host(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64]) {
+  BP_NEED_INIT();
+  if (n >= (1u << 31)) return fail("bp_msm_sharded_host: n too large");
+  Affine* d_pts = (Affine*)g.ws_pts.ensure((n ? n : 1) * sizeof(Affine));
+  Fq* d_sc = (Fq*)g.ws_sc.ensure((n ? n : 1) * sizeof(Fq));
+  Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
+  if (!d_pts || !d_sc || !d_out) return fail("device allocation failed");
+  if (n) {
+    BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.stream));
+    BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
+  }
+  if (msm_sharded_device(d_pts, d_sc, n, d_out)) return 1;
+  BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int bp_bench_msm_sharded(bp_handle points, bp_handle scalars, size_t first, size_t n, int warmup, int iters, int flush_l2,
+                         float* ms_each, uint8_t out64[64]) {
+  BP_NEED_INIT();
+  HandleRec P, S;
+  if (get_handle(points, 0, &P) || get_handle(scalars, 1, &S)) return 1;
+  if (first + n > P.n || first + n > S.n) return fail("bp_bench_msm_sharded: slice exceeds the uploaded vectors");
+  Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
+  const size_t flush_bytes = 256u << 20;
+  void* d_flush = flush_l2 ? g.ws_flush.ensure(flush_bytes) : nullptr;
+  for (int it = 0; it < warmup + iters; it++) {
+    if (d_flush) BP_CUDA(cudaMemsetAsync(d_flush, it & 0xff, flush_bytes, g.stream));
+    BP_CUDA(cudaEventRecord(g.ev_a, g.stream));
+    if (msm_sharded_device((const Affine*)P.p + first, (const Fq*)S.p + first, n, d_out)) return 1;
+    BP_CUDA(cudaEventRecord(g.ev_b, g.stream));
+    BP_CUDA(cudaEventSynchronize(g.ev_b));
+    float ms = 0;
+    BP_CUDA(cudaEventElapsedTime(&ms, g.ev_a, g.ev_b));
+    if (it >= warmup) ms_each[it - warmup] = ms;
+  }
+  BP_CUDA(cudaMemcpy(out64, d_out, 64, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// pinned host staging buffers for callers that want full-rate H2D into bp_msm & co.
+void* bp_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (!g.inited && bp_init(-1)) return nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); fail("cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+  return p;
+}
+int bp_host_free(void* p) { if (p) cudaFreeHost(p); return 0; }
 
 }  // extern "C"
 

@@ -144,6 +144,9 @@ def test_survey_appendix_d_known_answers(golden):
     assert len(c1["proof"]["ip"]["transcript"]) == 79 and c1["proof"]["ip"]["p2"]["start"] == 3
     c2 = golden("ipa_c2")["cases"][0]
     import hashlib
-    assert hashlib.sha256(c2["proof2"]["transcript"].encode("latin1")).hexdigest() == \
+    inner = c2["proof1"]["p2"]          # the Proof2 nested in NIProver's Proof1 (1767-byte transcript)
+    assert len(inner["transcript"]) == 1767
+    assert hashlib.sha256(inner["transcript"].encode("latin1")).hexdigest() == \
         "ba7e23f1170a86897644dd05e8cc55bf59fd0e51add64036cb8ccdf3892f5579"
-    assert c2["proof2"]["a"] == "45772048434343676761746858681413549692749859860001827780065551035206530309759"
+    assert inner["a"] == "45772048434343676761746858681413549692749859860001827780065551035206530309759"
+    assert inner["b"] == "89557398269276448073630310818547859234577444433827909274445100190913033905793"
