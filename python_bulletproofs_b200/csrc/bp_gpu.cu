@@ -46,7 +46,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     return 0;
   }
   int* digits = (int*)g.ws_digits.ensure((size_t)sh.W * T * sizeof(int));
-  u32* entries = (u32*)g.ws_entries.ensure((size_t)sh.W * T * sizeof(u32));
+  uint2* entries = (uint2*)g.ws_entries.ensure((size_t)sh.W * T * sizeof(uint2));
   u32* count = (u32*)g.ws_count.ensure((nb + 1) * sizeof(u32));
   u32* start = (u32*)g.ws_start.ensure((nb + 1) * sizeof(u32));
   u32* cursor = (u32*)g.ws_cursor.ensure((nb + 1) * sizeof(u32));
@@ -55,7 +55,13 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   XYZZ* buckets = (XYZZ*)g.ws_buckets.ensure(nb * sizeof(XYZZ));
   XYZZ* segsum = (XYZZ*)g.ws_segsum.ensure(nmw * sh.nseg * sizeof(XYZZ));
   XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure(nmw * sizeof(XYZZ));
-  if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !segsum || !winsum) return fail("workspace allocation failed");
+  // every (term, window) pair is at most one entry, so E <= W*T: size the chunk structures for the bound
+  size_t emax = (size_t)sh.W * T, nchunks = (emax + BP_CHUNK - 1) / BP_CHUNK;
+  XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * nchunks * sizeof(XYZZ));
+  size_t big_cap = emax / ((size_t)BP_CHUNK * BP_FIXUP_SERIAL_MAX) + 16;
+  u32* big = (u32*)g.ws_big.ensure((big_cap + 1) * sizeof(u32));
+  if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !segsum || !winsum || !part || !big)
+    return fail("workspace allocation failed");
 
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(cursor, 0, (nb + 1) * sizeof(u32), st));
@@ -68,7 +74,12 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   if (prof) cudaEventRecord(g.ev[2], st);
   k_scatter<<<(T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, start, cursor, entries);
   if (prof) cudaEventRecord(g.ev[3], st);
-  k_accumulate<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(points, point_idx, start, entries, nb, buckets);
+  BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));          // empty buckets = identity (ZZ = 0)
+  BP_CUDA(cudaMemsetAsync(big, 0, sizeof(u32), st));
+  // E (= start[nb]) stays on the device: launch for the upper bound W*T, threads past E exit at once
+  k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, start, entries, start + nb, buckets, part);
+  k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, nb, part, buckets, big, big + 1);
+  k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, part, buckets, big, big + 1);
   if (prof) cudaEventRecord(g.ev[4], st);
   size_t nsegs = nmw * sh.nseg;
   k_reduce_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);

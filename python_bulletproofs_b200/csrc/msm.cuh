@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) k_digits(const Fq* __restrict__ scalars, 
 
 __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits, u32 T, const u32* __restrict__ offsets, u32 nmsm,
                                                  MsmShape sh, const u32* __restrict__ bucket_start, u32* __restrict__ cursor,
-                                                 u32* __restrict__ entries) {
+                                                 uint2* __restrict__ entries) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   u32 m = nmsm > 1 ? find_msm(offsets, nmsm, t) : 0;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits,
     u32 mag = sd < 0 ? (u32)(-sd) : (u32)sd;
     size_t b = ((size_t)m * sh.W + w) * sh.H + (mag - 1);
     u32 pos = __ldg(bucket_start + b) + atomicAdd(cursor + b, 1u);
-    entries[pos] = t | (sd < 0 ? 0x80000000u : 0u);
+    entries[pos] = make_uint2(t | (sd < 0 ? 0x80000000u : 0u), (u32)b);     // {term | sign, bucket}
   }
 }
 
@@ -159,24 +159,110 @@ __global__ void __launch_bounds__(256) k_scan_add(u32* __restrict__ out, const u
   (void)total_slot;
 }
 
-// ---- bucket accumulation ---------------------------------------------------------------------
-// bucket_start has nb + 1 entries (the last = total entry count).
-__global__ void __launch_bounds__(128) k_accumulate(const Affine* __restrict__ points, const u32* __restrict__ point_idx,
-                                                    const u32* __restrict__ bucket_start, const u32* __restrict__ entries,
-                                                    size_t nb, XYZZ* __restrict__ buckets) {
-  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  u32 lo = __ldg(bucket_start + b), hi = __ldg(bucket_start + b + 1);
+// ---- bucket accumulation, load-balanced ----------------------------------------------------------
+// The bucket-sorted entry list (E entries) is cut into fixed chunks of BP_CHUNK entries, one thread per
+// chunk, so every lane performs the same number of mixed additions whatever the bucket-size
+// distribution is (uniform scalars, range-proof shaped scalars with thousands of equal digits, windows
+// whose top digit has only a few significant bits).  A run of equal bucket ids that lies entirely
+// inside a chunk is written straight to buckets[b]; a run cut by a chunk boundary leaves a partial in
+// part[2*chunk + 0] (piece starting at the chunk start) or part[2*chunk + 1] (piece starting inside the
+// chunk and running past its end); k_fixup adds the pieces of every bucket that spans chunks.
+// bucket_start has nb + 1 entries (the last = E).  buckets[] must be zeroed (identity) beforehand.
+#define BP_CHUNK 32
+#define BP_FIXUP_SERIAL_MAX 64
+
+BP_DI Affine load_entry_point(const Affine* __restrict__ points, const u32* __restrict__ point_idx, u32 e) {
+  u32 t = e & 0x7FFFFFFFu;
+  u32 pi = point_idx ? __ldg(point_idx + t) : t;
+  return ld_affine(points + pi);
+}
+
+#ifndef BP_ACC_MINB
+#define BP_ACC_MINB 4
+#endif
+__global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* __restrict__ points, const u32* __restrict__ point_idx,
+                                                    const u32* __restrict__ bucket_start, const uint2* __restrict__ entries,
+                                                    const u32* __restrict__ E_ptr, XYZZ* __restrict__ buckets,
+                                                    XYZZ* __restrict__ part) {
+  u32 chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 cs = chunk * BP_CHUNK;
+  const u32 E = __ldg(E_ptr);                 // = bucket_start[nb], the number of non-zero digits
+  if (cs >= E) return;
+  u32 ce = cs + BP_CHUNK < E ? cs + BP_CHUNK : E;
+  uint2 ent = __ldg(entries + cs);
+  u32 b = ent.y;
+  u32 s = __ldg(bucket_start + b), e = __ldg(bucket_start + b + 1);
+  bool first = true;
   XYZZ acc = xyzz_identity();
-  for (u32 i = lo; i < hi; i++) {
-    u32 e = __ldg(entries + i);
-    u32 t = e & 0x7FFFFFFFu;
-    u32 pi = point_idx ? __ldg(point_idx + t) : t;
-    Affine p = ld_affine(points + pi);
-    if (e >> 31) p.y = fp_neg(p.y);
+  // ONE flat loop with the same trip count in every lane: the warp stays converged on the mixed add;
+  // only the short flush at a bucket boundary diverges.
+  for (u32 i = cs; i < ce; i++) {
+    if (i == e) {                                                      // previous run is complete
+      if (first && s < cs) st_xyzz(part + 2 * (size_t)chunk, acc);     // it began in an earlier chunk
+      else st_xyzz(buckets + b, acc);                                  // whole bucket inside this chunk
+      first = false;
+      acc = xyzz_identity();
+      b = ent.y;                                                       // next non-empty bucket (ent = entries[i])
+      s = e; e = __ldg(bucket_start + b + 1);
+    }
+    u32 cur = ent.x;
+    if (i + 1 < ce) {
+      ent = __ldg(entries + i + 1);
+      u32 t = ent.x & 0x7FFFFFFFu;
+      const Affine* np = points + (point_idx ? __ldg(point_idx + t) : t);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
+    }
+    Affine p = load_entry_point(points, point_idx, cur);
+    if (cur >> 31) p.y = fp_neg(p.y);
     xyzz_madd(acc, p);
   }
+  if (e > ce) st_xyzz(part + 2 * (size_t)chunk + (first ? 0 : 1), acc);   // run continues in the next chunk
+  else if (first && s < cs) st_xyzz(part + 2 * (size_t)chunk, acc);
+  else st_xyzz(buckets + b, acc);
+}
+
+BP_DI const XYZZ* bucket_piece(const XYZZ* part, u32 s, u32 c0, u32 c) {
+  if (c == c0) return part + 2 * (size_t)c + (s == c0 * BP_CHUNK ? 0 : 1);
+  return part + 2 * (size_t)c;
+}
+
+// one thread per bucket: buckets spanning up to BP_FIXUP_SERIAL_MAX chunks are summed here, larger
+// ones are queued for k_fixup_big (one block each).
+__global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_start, size_t nb, const XYZZ* __restrict__ part,
+                                               XYZZ* __restrict__ buckets, u32* __restrict__ big_count, u32* __restrict__ big_list) {
+  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  u32 s = __ldg(bucket_start + b), e = __ldg(bucket_start + b + 1);
+  if (e == s) return;
+  u32 c0 = s / BP_CHUNK, c1 = (e - 1) / BP_CHUNK;
+  if (c0 == c1) return;
+  if (c1 - c0 >= BP_FIXUP_SERIAL_MAX) { big_list[atomicAdd(big_count, 1u)] = (u32)b; return; }
+  XYZZ acc = ld_xyzz(bucket_piece(part, s, c0, c0));
+  for (u32 c = c0 + 1; c <= c1; c++) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c)); xyzz_add(acc, v); }
   st_xyzz(buckets + b, acc);
+}
+
+// persistent blocks over the queue of giant buckets: 256 threads stride over the pieces, tree in shared memory
+__global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucket_start, const XYZZ* __restrict__ part,
+                                                   XYZZ* __restrict__ buckets, const u32* __restrict__ big_count,
+                                                   const u32* __restrict__ big_list) {
+  __shared__ XYZZ sm[256];
+  u32 n = *big_count;
+  for (u32 q = blockIdx.x; q < n; q += gridDim.x) {
+    u32 b = big_list[q];
+    u32 s = __ldg(bucket_start + b), e = __ldg(bucket_start + b + 1);
+    u32 c0 = s / BP_CHUNK, c1 = (e - 1) / BP_CHUNK;
+    XYZZ acc = xyzz_identity();
+    for (u32 c = c0 + threadIdx.x; c <= c1; c += 256) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c)); xyzz_add(acc, v); }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (threadIdx.x < off) { XYZZ v = sm[threadIdx.x + off]; xyzz_add(acc, v); sm[threadIdx.x] = acc; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) st_xyzz(buckets + b, acc);
+    __syncthreads();
+  }
 }
 
 // acc = k * p for a small k (k < 2^16), left-to-right double-and-add
