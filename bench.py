@@ -152,11 +152,13 @@ def run_ours(args):
     lib.bp_msm_set_profiling(0)
     stages = {k: round(float(v), 4) for k, v in zip(["digits", "scan", "scatter", "accumulate", "reduce", "combine", "total"], stage)}
     c = lib.bp_msm_last_window()
-    W = (256 + c - 1) // c
+    W = (129 + c - 1) // c                    # GLV: two 128-bit halves per scalar, +1 bit for the signed-digit carry
+    ent = ctypes.c_uint64()
+    nat.check(lib.bp_msm_last_entries(ctypes.byref(ent)))
     acc = statistics.median(acc_ms)
-    # algorithmic work of one k_accumulate launch: one mixed add per (term, window)  (SURVEY.md 8d formula;
-    # W = ceil(256/c) here because scalars are sign-normalised to < 2^255)
-    alg_macs = n * W * FIELD_MULS_PER_MADD * LIMB_MACS_PER_FIELD_MUL
+    # algorithmic work of the accumulation stage: one mixed add (8M + 2S = 10 field mul = 1360 limb-MAC) per
+    # non-zero signed digit; ent.value is that count, read back from the device (~ n * 256 / c).
+    alg_macs = ent.value * FIELD_MULS_PER_MADD * LIMB_MACS_PER_FIELD_MUL
     achieved = alg_macs / (acc * 1e-3) / 1e12
     peak = macs.value / 1e12
     nominal = 148 * 64 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
@@ -164,11 +166,11 @@ def run_ours(args):
                 "unit": "Tlimb-MAC/s", "frac": round(achieved / peak, 4), "traffic": None,
                 "peak_source": "bp_imad_peak: IMAD.WIDE.U32 issue-rate microbenchmark run in this process (measured)",
                 "nominal_peak": round(nominal, 2), "frac_of_nominal": round(achieved / nominal, 4),
-                "window_bits": c, "windows": W, "kernel_ms": round(acc, 4), "share_of_step": round(acc / stage[6], 3),
+                "window_bits": c, "windows": W, "glv": True, "mixed_adds_per_launch": ent.value, "kernel_ms": round(acc, 4), "share_of_step": round(acc / stage[6], 3),
                 "algorithmic_limb_macs_per_launch": alg_macs,
-                "whole_msm_limb_macs_per_pt": W * 1360 + W * (1 << (c - 1)) * 2 * FIELD_MULS_PER_ADD * LIMB_MACS_PER_FIELD_MUL / n,
-                "hbm": {"bound": "hbm", "achieved": round(n * W * 68 / (acc * 1e-3) / 1e9, 1), "unit": "GB/s",
-                        "peak": measured_hbm(), "note": "gathered 64 B point + 4 B index per (term, window); not the binding resource"}}
+                "whole_msm_limb_macs_per_pt": (alg_macs + W * (1 << (c - 1)) * 2 * FIELD_MULS_PER_ADD * LIMB_MACS_PER_FIELD_MUL) / n,
+                "hbm": {"bound": "hbm", "achieved": round(ent.value * 72 / (acc * 1e-3) / 1e9, 1), "unit": "GB/s",
+                        "peak": measured_hbm(), "note": "gathered 64 B point + 8 B entry per mixed add; not the binding resource"}}
 
     # ---- end to end through the C ABI with pinned HOST buffers (H2D + MSM + D2H inside the timed region)
     pp, ps = pinned_copy(nat, pts), pinned_copy(nat, sc)
@@ -193,7 +195,7 @@ def run_ours(args):
                        "terms_per_gpu": n, "terms_total": world * n, "window_bits": c,
                        "l2": "flushed between steps (256 MiB memset outside the timed events)",
                        "parallelism": "slice%d" % world, "seed": "0xB2000000+lgn(+1000*rank), points k_i*G"},
-            "gpu_launches": 10 * args.steps,
+            "gpu_launches": 13 * args.steps,
             "clocks": clocks, "e2e": e2e, "roofline": roofline, "stages_ms": stages, "result": result_hex}
 
     if rank == 0 and world == 1:

@@ -61,6 +61,7 @@ int bp_msm_batch(const uint8_t* pts64, const uint8_t* sc32, const uint32_t* offs
  * last MSM call: [0]=digits [1]=scan [2]=scatter [3]=accumulate [4]=reduce [5]=combine [6]=total */
 int bp_msm_set_window(int c);
 int bp_msm_last_window(void);
+int bp_msm_last_entries(uint64_t* entries);   /* mixed additions (non-zero signed digits) of the last MSM */
 int bp_msm_set_profiling(int on);
 int bp_msm_stage_ms(float out7[7]);
 

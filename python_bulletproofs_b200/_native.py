@@ -35,6 +35,7 @@ PROTOTYPES = {
     "bp_msm_batch": (ctypes.c_int, [c_u8p, c_u8p, ctypes.POINTER(ctypes.c_uint32), c_sz, c_u8p]),
     "bp_msm_set_window": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_last_window": (ctypes.c_int, []),
+    "bp_msm_last_entries": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)]),
     "bp_msm_set_profiling": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_stage_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "bp_scalar_mul_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p]),

@@ -37,6 +37,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   cudaStream_t st = g.stream;
   MsmShape sh = msm_shape(terms_per_msm, nmsm, g.force_c);
   g.last_c = sh.c;
+  g.last_nb = (size_t)nmsm * sh.W * sh.H;
   size_t nmw = (size_t)nmsm * sh.W, nb = nmw * sh.H;
   bool prof = g.profiling;
   if (prof) for (int i = 0; i < 7; i++) cudaEventRecord(g.ev[i], st), (void)0;
@@ -45,8 +46,10 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     if (out_affine && out_xyzz) BP_CUDA(cudaMemsetAsync(out_xyzz, 0, nmsm * sizeof(XYZZ), st));
     return 0;
   }
-  int* digits = (int*)g.ws_digits.ensure((size_t)sh.W * T * sizeof(int));
-  uint2* entries = (uint2*)g.ws_entries.ensure((size_t)sh.W * T * sizeof(uint2));
+  if (T >= (1u << 30)) return fail("msm: too many terms");
+  int* digits = (int*)g.ws_digits.ensure((size_t)sh.W * 2 * T * sizeof(int));
+  uint2* entries = (uint2*)g.ws_entries.ensure((size_t)sh.W * 2 * T * sizeof(uint2));
+  Affine* phi = (Affine*)g.ws_phi.ensure((size_t)T * sizeof(Affine));
   u32* count = (u32*)g.ws_count.ensure((nb + 1) * sizeof(u32));
   u32* start = (u32*)g.ws_start.ensure((nb + 1) * sizeof(u32));
   u32* cursor = (u32*)g.ws_cursor.ensure((nb + 1) * sizeof(u32));
@@ -56,28 +59,29 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   XYZZ* segsum = (XYZZ*)g.ws_segsum.ensure(nmw * sh.nseg * sizeof(XYZZ));
   XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure(nmw * sizeof(XYZZ));
   // every (term, window) pair is at most one entry, so E <= W*T: size the chunk structures for the bound
-  size_t emax = (size_t)sh.W * T, nchunks = (emax + BP_CHUNK - 1) / BP_CHUNK;
+  size_t emax = (size_t)sh.W * 2 * T, nchunks = (emax + BP_CHUNK - 1) / BP_CHUNK;
   XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * nchunks * sizeof(XYZZ));
   size_t big_cap = emax / ((size_t)BP_CHUNK * BP_FIXUP_SERIAL_MAX) + 16;
   u32* big = (u32*)g.ws_big.ensure((big_cap + 1) * sizeof(u32));
-  if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !segsum || !winsum || !part || !big)
+  if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !segsum || !winsum || !part || !big || !phi)
     return fail("workspace allocation failed");
 
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(cursor, 0, (nb + 1) * sizeof(u32), st));
   if (prof) cudaEventRecord(g.ev[0], st);
+  k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
   k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count);
   if (prof) cudaEventRecord(g.ev[1], st);
   k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
   k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
   k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
   if (prof) cudaEventRecord(g.ev[2], st);
-  k_scatter<<<(T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, start, cursor, entries);
+  k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, start, cursor, entries);
   if (prof) cudaEventRecord(g.ev[3], st);
   BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));          // empty buckets = identity (ZZ = 0)
   BP_CUDA(cudaMemsetAsync(big, 0, sizeof(u32), st));
   // E (= start[nb]) stays on the device: launch for the upper bound W*T, threads past E exit at once
-  k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, start, entries, start + nb, buckets, part);
+  k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, start + nb, buckets, part);
   k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, nb, part, buckets, big, big + 1);
   k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, part, buckets, big, big + 1);
   if (prof) cudaEventRecord(g.ev[4], st);
@@ -114,40 +118,45 @@ static int get_handle(bp_handle h, int kind, HandleRec* out) {
 }
 
 // ---- integer-pipe microbenchmarks (the measured roofline denominators) ---------------------------
-// mode 0: IMAD.WIDE.U32 (32x32+64 -> 64), 16 independent accumulators per thread
-// mode 1: IMAD (32-bit mad.lo), 16 independent accumulators
-// mode 2: IMAD.WIDE.U32 with the carry predicate chained (mad.lo.cc / madc.hi.cc pairs), as fp_mul issues them
-// mode 3: whole fp_mul (field multiplications per second; 72 IMAD.WIDE each)
+// Every probe keeps its operands data dependent so that ptxas can neither hoist the products nor turn the
+// multiply-accumulate into adds (it does both for loop-invariant operands); the SASS of each mode is
+// checked with cuobjdump (profiles/r1_pipe_probe.txt lists the opcode mix).
+// mode 0: IMAD.WIDE.U32 Rd, Ra, Rb, RZ  -- 32x32->64 product, both halves consumed as the next operands
+// mode 1: IMAD (32-bit mad.lo with accumulate)
+// mode 2: IMAD.WIDE.U32(.X) carry-chained rows (mad.lo.cc / madc.hi.cc pairs), as fp_mul issues them
+// mode 3: whole fp_mul (field multiplications per second; 72 IMAD.WIDE(.X) each)
+// mode 4: IADD3 (32-bit adds; ptxas spreads them over the ALU and the FMA pipe as IADD3 / IMAD.IADD)
+// mode 5: whole fp_sqr
 template <int MODE>
 __global__ void __launch_bounds__(256) k_pipe_probe(u32* out, u32 seed, int iters) {
   u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
   if (MODE == 0) {
-    u64 acc[16];
+    u64 p[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) acc[i] = (u64)(a + i) << 20;
+    for (int i = 0; i < 16; i++) p[i] = ((u64)(a + i) << 32) | (b + 7 * i);
     for (int it = 0; it < iters; it++) {
 #pragma unroll
       for (int r = 0; r < 2; r++)
 #pragma unroll
-        for (int i = 0; i < 16; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
+        for (int i = 0; i < 16; i++) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p[i]) : "r"((u32)p[i]), "r"((u32)(p[i] >> 32)));
     }
     u64 s = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) s ^= acc[i];
+    for (int i = 0; i < 16; i++) s ^= p[i];
     if (s == 0x1234567u) out[0] = (u32)s;
   } else if (MODE == 1) {
-    u32 acc[16];
+    u32 p[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) acc[i] = a + i;
+    for (int i = 0; i < 16; i++) p[i] = a + i;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
       for (int r = 0; r < 2; r++)
 #pragma unroll
-        for (int i = 0; i < 16; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(a), "r"(b));
+        for (int i = 0; i < 16; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(p[i]) : "r"(p[(i + 5) & 15]), "r"(b));
     }
     u32 s = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) s ^= acc[i];
+    for (int i = 0; i < 16; i++) s ^= p[i];
     if (s == 0x1234567u) out[0] = s;
   } else if (MODE == 2) {
     u32 acc[4][9];
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(256) k_pipe_probe(u32* out, u32 seed, int iter
 #pragma unroll
       for (int r = 0; r < 2; r++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) mul_row_mad(acc[j], a, b, a ^ b, a + b, b);     // 4 IMAD.WIDE(.X) + 1 IADD3.X
+        for (int j = 0; j < 4; j++) mul_row_mad(acc[j], a, b, a ^ b, a + b, acc[(j + 1) & 3][0]);   // 4 IMAD.WIDE(.X) + 1 IADD3.X
     }
     u32 s = 0;
 #pragma unroll
@@ -167,11 +176,26 @@ __global__ void __launch_bounds__(256) k_pipe_probe(u32* out, u32 seed, int iter
 #pragma unroll
       for (int i = 0; i < 9; i++) s ^= acc[j][i];
     if (s == 0x1234567u) out[0] = s;
+  } else if (MODE == 4) {
+    u32 p[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) p[i] = a + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int i = 0; i < 16; i++) asm volatile("add.u32 %0, %0, %1;" : "+r"(p[i]) : "r"(p[(i + 5) & 15]));
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s ^= p[i];
+    if (s == 0x1234567u) out[0] = s;
   } else {
     Fp x, y;
 #pragma unroll
     for (int i = 0; i < 8; i++) { x.v[i] = a * (i + 1); y.v[i] = b + i; }
-    for (int it = 0; it < iters; it++) { x = fp_mul(x, y); y = fp_mul(y, x); }
+    if (MODE == 3) { for (int it = 0; it < iters; it++) { x = fp_mul(x, y); y = fp_mul(y, x); } }
+    else { for (int it = 0; it < iters; it++) { x = fp_sqr(x); y = fp_sqr(y); } }
     u32 s = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) s ^= x.v[i] ^ y.v[i];
@@ -242,6 +266,15 @@ int bp_device_info(char* name, size_t cap, int* sm_count, int* cc_major, int* cc
 
 int bp_msm_set_window(int c) { if (c < 0 || c > 16) return fail("window must be 0..16"); g.force_c = c; return 0; }
 int bp_msm_last_window(void) { return g.last_c; }
+int bp_msm_last_entries(uint64_t* entries) {      // non-zero digits = mixed additions of the last MSM's accumulation
+  BP_NEED_INIT();
+  if (!g.ws_start.p) return fail("no MSM has run yet");
+  uint32_t e = 0;
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  BP_CUDA(cudaMemcpy(&e, (const uint32_t*)g.ws_start.p + g.last_nb, 4, cudaMemcpyDeviceToHost));
+  *entries = e;
+  return 0;
+}
 int bp_msm_set_profiling(int on) { g.profiling = on != 0; return 0; }
 int bp_msm_stage_ms(float out7[7]) {
   BP_NEED_INIT();
@@ -394,7 +427,7 @@ int bp_bench_msm(bp_handle points, bp_handle scalars, size_t n, int warmup, int 
 static int pipe_probe(int mode, int iters, double* ops_per_s, float* ms_out) {
   u32* d = (u32*)g.ws_misc.ensure(256);
   int blocks = g.sm_count * 8;
-  double per_iter = mode == 3 ? 2.0 : 32.0;
+  double per_iter = (mode == 3 || mode == 5) ? 2.0 : 32.0;
   for (int pass = 0; pass < 2; pass++) {      // pass 0 = warm-up (clocks, I-cache), pass 1 timed
     int n = pass == 0 ? (iters / 8 > 0 ? iters / 8 : 1) : iters;
     BP_CUDA(cudaEventRecord(g.ev_a, g.stream));
@@ -403,7 +436,9 @@ static int pipe_probe(int mode, int iters, double* ops_per_s, float* ms_out) {
       case 1: k_pipe_probe<1><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
       case 2: k_pipe_probe<2><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
       case 3: k_pipe_probe<3><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
-      default: return fail("bp_pipe_probe: mode 0..3");
+      case 4: k_pipe_probe<4><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 5: k_pipe_probe<5><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      default: return fail("bp_pipe_probe: mode 0..5");
     }
     BP_CUDA(cudaEventRecord(g.ev_b, g.stream));
     BP_CUDA(cudaEventSynchronize(g.ev_b));

@@ -433,6 +433,7 @@ __global__ void k_test_fp(int op, const Fp* a, const Fp* b, u32 n, Fp* out) {
     case 2: r = fp_sub(x, y); break;
     case 3: r = fp_inv(x); break;
     case 4: r = fp_neg(x); break;
+    case 5: r = fp_sqr(x); break;
     default: r = x;
   }
   st_fp(out + i, fp_canon(r));

@@ -38,9 +38,10 @@ struct Ctx {
   cudaEvent_t ev_a, ev_b;
   bool profiling = false;
   int force_c = 0, last_c = 0;
+  size_t last_nb = 0;
   // MSM workspaces
   DevBuf ws_pts, ws_sc, ws_off, ws_out, ws_digits, ws_entries, ws_count, ws_start, ws_cursor, ws_tiles, ws_buckets, ws_segsum,
-      ws_winsum, ws_misc, ws_flush, ws_entry_bucket, ws_part, ws_big;
+      ws_winsum, ws_misc, ws_flush, ws_entry_bucket, ws_part, ws_big, ws_phi;
   // IPA / verifier workspaces
   DevBuf ws_g, ws_h, ws_a, ws_b, ws_g2, ws_h2, ws_a2, ws_b2, ws_idx, ws_lr, ws_terms_sc, ws_small;
   unsigned* h_pin = nullptr;
@@ -48,7 +49,7 @@ struct Ctx {
   void free_all() {
     DevBuf* all[] = {&ws_pts, &ws_sc, &ws_off, &ws_out, &ws_digits, &ws_entries, &ws_count, &ws_start, &ws_cursor, &ws_tiles,
                      &ws_buckets, &ws_segsum, &ws_winsum, &ws_misc, &ws_flush, &ws_g, &ws_h, &ws_a, &ws_b, &ws_g2, &ws_h2,
-                     &ws_a2, &ws_b2, &ws_idx, &ws_lr, &ws_terms_sc, &ws_small, &ws_entry_bucket, &ws_part, &ws_big};
+                     &ws_a2, &ws_b2, &ws_idx, &ws_lr, &ws_terms_sc, &ws_small, &ws_entry_bucket, &ws_part, &ws_big, &ws_phi};
     for (DevBuf* b : all) b->release();
   }
 };

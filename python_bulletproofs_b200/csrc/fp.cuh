@@ -197,7 +197,79 @@ BP_DI Fp fp_mul(const Fp& a, const Fp& b) {
   fold512(r.v, t);
   return r;
 }
-BP_DI Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
+// ---- dedicated squaring: 28 cross products (doubled by a 1-bit shift) + 8 squares = 36 IMAD.WIDE instead of 64 ------
+template <int N>
+BP_DI void sqr_chain(u32* acc, u32 x0, u32 x1, u32 x2, u32 x3, u32 b) {
+  // acc[0..2N-1] += {x0..x(N-1)} * b at consecutive 64-bit slots, carry into acc[2N]
+  if (N == 1) {
+    asm("mad.lo.cc.u32 %0,%3,%4,%0; madc.hi.cc.u32 %1,%3,%4,%1; addc.u32 %2,%2,0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(x0), "r"(b));
+  } else if (N == 2) {
+    asm("mad.lo.cc.u32 %0,%5,%7,%0; madc.hi.cc.u32 %1,%5,%7,%1; madc.lo.cc.u32 %2,%6,%7,%2; madc.hi.cc.u32 %3,%6,%7,%3; addc.u32 %4,%4,0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]) : "r"(x0), "r"(x1), "r"(b));
+  } else if (N == 3) {
+    asm("mad.lo.cc.u32 %0,%7,%10,%0; madc.hi.cc.u32 %1,%7,%10,%1; madc.lo.cc.u32 %2,%8,%10,%2; madc.hi.cc.u32 %3,%8,%10,%3;"
+        "madc.lo.cc.u32 %4,%9,%10,%4; madc.hi.cc.u32 %5,%9,%10,%5; addc.u32 %6,%6,0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(b));
+  } else {
+    mul_row_mad(acc, x0, x1, x2, x3, b);
+  }
+}
+// t[0..15] = a * a
+BP_DI void sqr_wide(u32 t[16], const u32 a[8]) {
+  u32 ev[16], od[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) { ev[k] = 0; od[k] = 0; }
+  // cross products a_i * a_j, i < j; position i+j even -> ev[i+j], odd -> od[i+j-1]
+  sqr_chain<4>(od + 0, a[1], a[3], a[5], a[7], a[0]);
+  sqr_chain<3>(ev + 2, a[2], a[4], a[6], 0, a[0]);
+  sqr_chain<3>(od + 2, a[2], a[4], a[6], 0, a[1]);
+  sqr_chain<3>(ev + 4, a[3], a[5], a[7], 0, a[1]);
+  sqr_chain<3>(od + 4, a[3], a[5], a[7], 0, a[2]);
+  sqr_chain<2>(ev + 6, a[4], a[6], 0, 0, a[2]);
+  sqr_chain<2>(od + 6, a[4], a[6], 0, 0, a[3]);
+  sqr_chain<2>(ev + 8, a[5], a[7], 0, 0, a[3]);
+  sqr_chain<2>(od + 8, a[5], a[7], 0, 0, a[4]);
+  sqr_chain<1>(ev + 10, a[6], 0, 0, 0, a[4]);
+  sqr_chain<1>(od + 10, a[6], 0, 0, 0, a[5]);
+  sqr_chain<1>(ev + 12, a[7], 0, 0, 0, a[5]);
+  sqr_chain<1>(od + 12, a[7], 0, 0, 0, a[6]);
+  // c = ev + (od << 32)
+  u32 c[16];
+  c[0] = ev[0];
+  asm("add.cc.u32 %0,%15,%30; addc.cc.u32 %1,%16,%31; addc.cc.u32 %2,%17,%32; addc.cc.u32 %3,%18,%33; addc.cc.u32 %4,%19,%34;"
+      "addc.cc.u32 %5,%20,%35; addc.cc.u32 %6,%21,%36; addc.cc.u32 %7,%22,%37; addc.cc.u32 %8,%23,%38; addc.cc.u32 %9,%24,%39;"
+      "addc.cc.u32 %10,%25,%40; addc.cc.u32 %11,%26,%41; addc.cc.u32 %12,%27,%42; addc.cc.u32 %13,%28,%43; addc.u32 %14,%29,%44;"
+      : "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]), "=r"(c[8]), "=r"(c[9]), "=r"(c[10]),
+        "=r"(c[11]), "=r"(c[12]), "=r"(c[13]), "=r"(c[14]), "=r"(c[15])
+      : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(ev[9]), "r"(ev[10]),
+        "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
+        "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]), "r"(od[9]),
+        "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+  // double the cross sum (it is < 2^511)
+#pragma unroll
+  for (int k = 15; k > 0; k--) c[k] = __funnelshift_l(c[k - 1], c[k], 1);
+  c[0] <<= 1;
+  // + squares a_i^2 at limb 2i: one 16-limb carry chain of 8 IMAD.WIDE
+  asm("mad.lo.cc.u32 %0,%8,%8,%0; madc.hi.cc.u32 %1,%8,%8,%1; madc.lo.cc.u32 %2,%9,%9,%2; madc.hi.cc.u32 %3,%9,%9,%3;"
+      "madc.lo.cc.u32 %4,%10,%10,%4; madc.hi.cc.u32 %5,%10,%10,%5; madc.lo.cc.u32 %6,%11,%11,%6; madc.hi.cc.u32 %7,%11,%11,%7;"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]));
+  asm("madc.lo.cc.u32 %0,%8,%8,%0; madc.hi.cc.u32 %1,%8,%8,%1; madc.lo.cc.u32 %2,%9,%9,%2; madc.hi.cc.u32 %3,%9,%9,%3;"
+      "madc.lo.cc.u32 %4,%10,%10,%4; madc.hi.cc.u32 %5,%10,%10,%5; madc.lo.cc.u32 %6,%11,%11,%6; madc.hi.u32 %7,%11,%11,%7;"
+      : "+r"(c[8]), "+r"(c[9]), "+r"(c[10]), "+r"(c[11]), "+r"(c[12]), "+r"(c[13]), "+r"(c[14]), "+r"(c[15])
+      : "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#pragma unroll
+  for (int k = 0; k < 16; k++) t[k] = c[k];
+}
+BP_DI Fp fp_sqr(const Fp& a) {
+  u32 t[16];
+  sqr_wide(t, a.v);
+  Fp r;
+  fold512(r.v, t);
+  return r;
+}
 
 BP_DI Fp fp_sqr_n(Fp a, int n) {
   for (int i = 0; i < n; i++) a = fp_sqr(a);

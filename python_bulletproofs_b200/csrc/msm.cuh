@@ -22,29 +22,40 @@
 #include <cstdio>
 #include "ec.cuh"
 #include "fq.cuh"
+#include "glv.cuh"
 
 namespace bp {
 
 struct MsmShape {
   int c;          // window bits
-  int W;          // windows = ceil(256 / c)   (scalars are sign-normalised to < 2^255)
+  int W;          // windows = ceil(129 / c): GLV halves are < 2^128 in magnitude, +1 bit for the signed-digit carry
   u32 H;          // buckets per window = 2^(c-1)
   u32 S;          // buckets per reduce segment
   u32 nseg;       // segments per window
 };
+#define BP_GLV_BITS 129
 
 inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
   MsmShape s;
   int best = 1; double bestc = 1e300;
+  const double n = (double)terms_per_msm;
   for (int c = 1; c <= 16; c++) {
-    double W = (256 + c - 1) / c, H = (double)(1u << (c - 1));
-    // accumulate: W * n mixed adds (10 mul) ; reduce: 2 * W * H full adds (14 mul) ; combine: 256 dbl serial (latency, weighted)
-    double serial = nmsm > 64 ? 0.0 : 256.0 * 9 * 64;   // a lone thread runs ~64x below throughput
-    double cost = W * (double)terms_per_msm * 10 + 2 * W * H * 14 * (nmsm > 64 ? 1.0 : 1.6) + serial;
+    double W = (BP_GLV_BITS + c - 1) / c, H = (double)(1u << (c - 1));
+    double entries = 2.0 * n * ((double)(BP_GLV_BITS - 1) / c + 0.3);     // non-zero digits: 2 halves x ~128/c windows
+    double cost;
+    if (nmsm <= 8) {
+      // a few MSMs: measured on B200 (profiles/r1_window_sweep.txt).  Windows whose top digit keeps only a few
+      // significant bits of the 128-bit halves make hot buckets, so only c = 10, 13, 16 are used: 128 mod c is 8, 11, 0.
+      int pick = n <= 8192.0 ? 10 : (n <= 131072.0 ? 13 : 16);
+      cost = c == pick ? 0.0 : 1.0;
+    } else {
+      // many MSMs: everything is throughput; count field multiplications
+      cost = entries * 10 + 2 * W * H * 14 + c * (W - 1) * 9.0 + W * 14;
+    }
     if (cost < bestc) { bestc = cost; best = c; }
   }
   s.c = force_c > 0 ? force_c : best;
-  s.W = (256 + s.c - 1) / s.c;
+  s.W = (BP_GLV_BITS + s.c - 1) / s.c;
   s.H = 1u << (s.c - 1);
   s.S = s.H < 16 ? s.H : 16;
   s.nseg = s.H / s.S;
@@ -67,6 +78,8 @@ BP_DI u32 find_msm(const u32* __restrict__ offsets, u32 nmsm, u32 t) {
   return lo;
 }
 
+// One thread per term: k mod q -> GLV halves (k1, k2) -> sign-normalised magnitudes < 2^128 -> signed c-bit
+// digits.  Sub-term 2t carries k1 on P_t, sub-term 2t+1 carries k2 on phi(P_t).  digits is [W][2T].
 __global__ void __launch_bounds__(256) k_digits(const Fq* __restrict__ scalars, u32 T, const u32* __restrict__ offsets, u32 nmsm,
                                                 MsmShape sh, int* __restrict__ digits, u32* __restrict__ bucket_count) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,37 +88,66 @@ __global__ void __launch_bounds__(256) k_digits(const Fq* __restrict__ scalars, 
   uint4 a = __ldg(sp), b = __ldg(sp + 1);
   Fq k; k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
   k = fq_reduce(k);                                   // es = [ei % order]   pippenger.py:26
-  bool neg = !fq_geq(fq_const_half(), k);             // k > q/2  ->  use q - k (< 2^255) on the negated point
-  if (neg) k = fq_sub(fq_zero(), k);
+  Fq half[2];
+  bool hneg[2];
+  glv_split(k, half[0], hneg[0], half[1], hneg[1]);   // magnitudes < 2^128 and signs
   u32 m = nmsm > 1 ? find_msm(offsets, nmsm, t) : 0;
-  u32 carry = 0;
-  for (int w = 0; w < sh.W; w++) {
-    u32 d = scalar_bits(k, w * sh.c, sh.c) + carry;
-    int sd;
-    if (d > sh.H) { sd = (int)d - (int)(2u * sh.H); carry = 1; } else { sd = (int)d; carry = 0; }
-    if (neg) sd = -sd;
-    digits[(size_t)w * T + t] = sd;
-    if (sd != 0) {
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const Fq kk = half[j];
+    const bool neg = hneg[j];                         // negative half: the digits act on the negated point
+    u32 carry = 0;
+    for (int w = 0; w < sh.W; w++) {
+      u32 d = scalar_bits(kk, w * sh.c, sh.c) + carry;
+      int sd;
+      if (d > sh.H) { sd = (int)d - (int)(2u * sh.H); carry = 1; } else { sd = (int)d; carry = 0; }
+      if (neg) sd = -sd;
+      digits[(size_t)w * (2 * (size_t)T) + 2 * t + j] = sd;
+      // histogram with warp-aggregated atomics: lanes that hit the same bucket (common for the top window, whose
+      // digit has only a few significant bits, and for repeated scalars) issue ONE atomicAdd between them
       u32 mag = sd < 0 ? (u32)(-sd) : (u32)sd;
-      atomicAdd(bucket_count + ((size_t)m * sh.W + w) * sh.H + (mag - 1), 1u);
+      u32 bkt = sd != 0 ? (u32)(((size_t)m * sh.W + w) * sh.H + (mag - 1)) : 0xFFFFFFFFu;
+      u32 act = __activemask();
+      u32 peers = __match_any_sync(act, bkt);
+      if (sd != 0 && (u32)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(bucket_count + bkt, (u32)__popc(peers));
     }
   }
 }
 
+// one thread per sub-term: entry = {term | phi-flag << 30 | sign << 31, bucket}
 __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits, u32 T, const u32* __restrict__ offsets, u32 nmsm,
                                                  MsmShape sh, const u32* __restrict__ bucket_start, u32* __restrict__ cursor,
                                                  uint2* __restrict__ entries) {
-  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
+  u32 st = blockIdx.x * blockDim.x + threadIdx.x;
+  if (st >= 2 * T) return;
+  u32 t = st >> 1;
   u32 m = nmsm > 1 ? find_msm(offsets, nmsm, t) : 0;
   for (int w = 0; w < sh.W; w++) {
-    int sd = digits[(size_t)w * T + t];
-    if (sd == 0) continue;
+    int sd = digits[(size_t)w * (2 * (size_t)T) + st];
     u32 mag = sd < 0 ? (u32)(-sd) : (u32)sd;
-    size_t b = ((size_t)m * sh.W + w) * sh.H + (mag - 1);
-    u32 pos = __ldg(bucket_start + b) + atomicAdd(cursor + b, 1u);
-    entries[pos] = make_uint2(t | (sd < 0 ? 0x80000000u : 0u), (u32)b);     // {term | sign, bucket}
+    u32 b = sd != 0 ? (u32)(((size_t)m * sh.W + w) * sh.H + (mag - 1)) : 0xFFFFFFFFu;
+    // warp-aggregated cursor: one atomicAdd per distinct bucket per warp, lanes take consecutive slots
+    u32 act = __activemask();
+    u32 peers = __match_any_sync(act, b);
+    u32 lane = threadIdx.x & 31, leader = (u32)(__ffs(peers) - 1);
+    u32 base = 0;
+    if (sd != 0 && lane == leader) base = atomicAdd(cursor + b, (u32)__popc(peers));
+    base = __shfl_sync(act, base, leader);
+    if (sd == 0) continue;
+    u32 pos = __ldg(bucket_start + b) + base + (u32)__popc(peers & ((1u << lane) - 1));
+    entries[pos] = make_uint2(t | ((st & 1u) << 30) | (sd < 0 ? 0x80000000u : 0u), b);
   }
+}
+
+// phi[t] = (beta * x_t, y_t) for every term (through the optional index list), so that the accumulation
+// gathers a ready-made point for the k2 half instead of multiplying by beta once per (sub-term, window).
+__global__ void __launch_bounds__(128) k_phi(const Affine* __restrict__ points, const u32* __restrict__ point_idx, u32 T,
+                                             Affine* __restrict__ phi) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  Affine p = ld_affine(points + (point_idx ? __ldg(point_idx + t) : t));
+  if (!affine_is_identity(p)) { const Fp beta = {BP_BETA_LIMBS}; p.x = fp_canon(fp_mul(p.x, beta)); }
+  st_affine(phi + t, p);
 }
 
 // ---- exclusive scan of u32 counts (3 passes; totals < 2^32) ---------------------------------------
@@ -171,16 +213,17 @@ __global__ void __launch_bounds__(256) k_scan_add(u32* __restrict__ out, const u
 #define BP_CHUNK 32
 #define BP_FIXUP_SERIAL_MAX 64
 
-BP_DI Affine load_entry_point(const Affine* __restrict__ points, const u32* __restrict__ point_idx, u32 e) {
-  u32 t = e & 0x7FFFFFFFu;
-  u32 pi = point_idx ? __ldg(point_idx + t) : t;
-  return ld_affine(points + pi);
+BP_DI const Affine* entry_point_ptr(const Affine* __restrict__ points, const u32* __restrict__ point_idx,
+                                    const Affine* __restrict__ phi, u32 e) {
+  u32 t = e & 0x3FFFFFFFu;
+  if (e & 0x40000000u) return phi + t;                       // k2 half: phi(P_t), materialised per term
+  return points + (point_idx ? __ldg(point_idx + t) : t);
 }
 
 #ifndef BP_ACC_MINB
 #define BP_ACC_MINB 4
 #endif
-__global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* __restrict__ points, const u32* __restrict__ point_idx,
+__global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* __restrict__ points, const u32* __restrict__ point_idx, const Affine* __restrict__ phi,
                                                     const u32* __restrict__ bucket_start, const uint2* __restrict__ entries,
                                                     const u32* __restrict__ E_ptr, XYZZ* __restrict__ buckets,
                                                     XYZZ* __restrict__ part) {
@@ -208,11 +251,9 @@ __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* _
     u32 cur = ent.x;
     if (i + 1 < ce) {
       ent = __ldg(entries + i + 1);
-      u32 t = ent.x & 0x7FFFFFFFu;
-      const Affine* np = points + (point_idx ? __ldg(point_idx + t) : t);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(entry_point_ptr(points, point_idx, phi, ent.x)));
     }
-    Affine p = load_entry_point(points, point_idx, cur);
+    Affine p = ld_affine(entry_point_ptr(points, point_idx, phi, cur));
     if (cur >> 31) p.y = fp_neg(p.y);
     xyzz_madd(acc, p);
   }

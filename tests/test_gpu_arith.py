@@ -30,7 +30,7 @@ def _pairs(rng, n_rand, mod=None):
 
 
 @pytest.mark.parametrize("op,fn", [(0, lambda a, b: a * b % P), (1, lambda a, b: (a + b) % P), (2, lambda a, b: (a - b) % P),
-                                   (4, lambda a, b: (-a) % P)])
+                                   (4, lambda a, b: (-a) % P), (5, lambda a, b: a * a % P)])
 def test_fp_ops_lazy_inputs(op, fn):
     """Inputs are arbitrary 256-bit residues (the device keeps lazy values in [0, 2^256))."""
     rng = random.Random(100 + op)
