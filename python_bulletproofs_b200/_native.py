@@ -37,6 +37,7 @@ PROTOTYPES = {
     "bp_msm_last_window": (ctypes.c_int, []),
     "bp_msm_last_entries": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)]),
     "bp_msm_set_profiling": (ctypes.c_int, [ctypes.c_int]),
+    "bp_msm_set_pipeline_min": (ctypes.c_int, [c_sz]),
     "bp_msm_stage_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "bp_scalar_mul_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_ipa_fold_round": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),

@@ -32,13 +32,15 @@ int fail(const char* fmt, ...) {
 
 // ---- the MSM pipeline on device-resident operands ----------------------------------------------
 // points/point_idx/scalars/offsets are device pointers; out_affine/out_xyzz device (either may be null)
+static int msm_run_pipelined(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, Affine* out_affine, XYZZ* out_xyzz);
 int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, const u32* d_offsets, u32 nmsm,
             size_t terms_per_msm, Affine* out_affine, XYZZ* out_xyzz) {
+  if (nmsm == 1 && T >= g.pipeline_min_terms && !g.profiling) return msm_run_pipelined(points, point_idx, scalars, T, out_affine, out_xyzz);
   cudaStream_t st = g.stream;
   MsmShape sh = msm_shape(terms_per_msm, nmsm, g.force_c);
   g.last_c = sh.c;
-  g.last_nb = (size_t)nmsm * sh.W * sh.H;
-  size_t nmw = (size_t)nmsm * sh.W, nb = nmw * sh.H;
+  g.last_nb = (size_t)nmsm * sh.U * sh.H;
+  size_t nmw = (size_t)nmsm * sh.U, nb = nmw * sh.H;
   bool prof = g.profiling;
   if (prof) for (int i = 0; i < 7; i++) cudaEventRecord(g.ev[i], st), (void)0;
   if (T == 0) {   // all identities
@@ -62,7 +64,8 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   size_t emax = (size_t)sh.W * 2 * T, nchunks = (emax + BP_CHUNK - 1) / BP_CHUNK;
   XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * nchunks * sizeof(XYZZ));
   size_t big_cap = emax / ((size_t)BP_CHUNK * BP_FIXUP_SERIAL_MAX) + 16;
-  u32* big = (u32*)g.ws_big.ensure((big_cap + 1) * sizeof(u32));
+  u32* big = (u32*)g.ws_big.ensure((big_cap + 3) * sizeof(u32));
+  u32* zero_word = big + big_cap + 2;
   if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !segsum || !winsum || !part || !big || !phi)
     return fail("workspace allocation failed");
 
@@ -79,19 +82,116 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, start, cursor, entries);
   if (prof) cudaEventRecord(g.ev[3], st);
   BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));          // empty buckets = identity (ZZ = 0)
-  BP_CUDA(cudaMemsetAsync(big, 0, sizeof(u32), st));
+  BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
+  BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));   // [0] = queue length, kept zero word for gs = 0 lives at big[big_cap + 1]
   // E (= start[nb]) stays on the device: launch for the upper bound W*T, threads past E exit at once
-  k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, start + nb, buckets, part);
-  k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, nb, part, buckets, big, big + 1);
-  k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, part, buckets, big, big + 1);
+  k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, buckets, part);
+  k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, part, buckets, big, big + 1);
+  k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, part, buckets, big, big + 1);
   if (prof) cudaEventRecord(g.ev[4], st);
   size_t nsegs = nmw * sh.nseg;
-  k_reduce_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);
-  const XYZZ* ws = segsum;
-  if (sh.nseg > 1) { k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(segsum, sh.nseg, winsum); ws = winsum; }
+  XYZZ* seg_run = (XYZZ*)g.ws_segrun.ensure(nsegs * sizeof(XYZZ));
+  if (!seg_run) return fail("workspace allocation failed");
+  k_reduce_seg<<<(unsigned)((4 * nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
+  // level 2: groups of G segments
+  u32 G = sh.nseg < 16 ? sh.nseg : 16, ngrp = sh.nseg / G;
+  int lgS = 0, lgG = 0, ubits = 0;
+  while ((1u << lgS) < sh.S) lgS++;
+  while ((1u << lgG) < G) lgG++;
+  while ((1u << ubits) < ngrp * (1u + sh.dbl)) ubits++;
+  XYZZ* grpsum = (XYZZ*)g.ws_grpsum.ensure(nmw * ngrp * sizeof(XYZZ));
+  if (!grpsum) return fail("workspace allocation failed");
+  k_reduce_grp<<<(unsigned)((4 * nmw * ngrp + 127) / 128), 128, 0, st>>>(seg_run, segsum, sh, nmw, 0, G, lgS, lgG, ubits, grpsum);
+  const XYZZ* ws = grpsum;
+  if (ngrp > 1) { k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(grpsum, ngrp, winsum); ws = winsum; }
   if (prof) cudaEventRecord(g.ev[5], st);
-  k_combine<<<(unsigned)((nmsm + 63) / 64), 64, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+  k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
   if (prof) cudaEventRecord(g.ev[6], st);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- single large MSM, windows pipelined over streams -----------------------------------------------
+// After the sort, windows are accumulated top-down on two alternating streams; each window's bucket reduction runs
+// on its own (high-priority) stream as soon as that window's buckets are final, and one more stream folds the window
+// sums into the Horner accumulator.  The latency-bound tail kernels (a few hundred dependent point operations on a
+// handful of SMs) thereby run underneath the accumulation of the lower windows; only the last window's reduction, one
+// Horner step and the final inversion remain exposed.  Same kernels, same result as msm_run.
+static int msm_run_pipelined(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, Affine* out_affine, XYZZ* out_xyzz) {
+  cudaStream_t st = g.stream;
+  MsmShape sh = msm_shape(T, 1, g.force_c);
+  g.last_c = sh.c;
+  const size_t W = sh.U, nb = W * sh.H;      // W counts bucket units here (the top window may own two)
+  g.last_nb = nb;
+  if (T >= (1u << 30)) return fail("msm: too many terms");
+  if (g.ensure_pipeline((int)W)) return 1;
+  int* digits = (int*)g.ws_digits.ensure((size_t)sh.W * 2 * T * sizeof(int));
+  uint2* entries = (uint2*)g.ws_entries.ensure((size_t)sh.W * 2 * T * sizeof(uint2));
+  Affine* phi = (Affine*)g.ws_phi.ensure((size_t)T * sizeof(Affine));
+  u32* count = (u32*)g.ws_count.ensure((nb + 1) * sizeof(u32));
+  u32* start = (u32*)g.ws_start.ensure((nb + 1) * sizeof(u32));
+  u32* cursor = (u32*)g.ws_cursor.ensure((nb + 1) * sizeof(u32));
+  size_t ntiles = (nb + 1 + BP_SCAN_TILE - 1) / BP_SCAN_TILE;
+  u32* tiles = (u32*)g.ws_tiles.ensure(ntiles * sizeof(u32));
+  XYZZ* buckets = (XYZZ*)g.ws_buckets.ensure(nb * sizeof(XYZZ));
+  XYZZ* segsum = (XYZZ*)g.ws_segsum.ensure(W * sh.nseg * sizeof(XYZZ));
+  XYZZ* seg_run = (XYZZ*)g.ws_segrun.ensure(W * sh.nseg * sizeof(XYZZ));
+  u32 G = sh.nseg < 16 ? sh.nseg : 16, ngrp = sh.nseg / G;
+  XYZZ* grpsum = (XYZZ*)g.ws_grpsum.ensure(W * ngrp * sizeof(XYZZ));
+  XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure((W + 1) * sizeof(XYZZ));
+  XYZZ* hacc = winsum + W;                                   // Horner accumulator
+  const size_t wchunks = ((size_t)2 * T + BP_CHUNK - 1) / BP_CHUNK + 1;      // a window holds at most 2T entries
+  XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * W * wchunks * sizeof(XYZZ));
+  const size_t big_cap = (size_t)2 * T / ((size_t)BP_CHUNK * BP_FIXUP_SERIAL_MAX) + 16;
+  u32* big = (u32*)g.ws_big.ensure(W * (big_cap + 2) * sizeof(u32));
+  if (!digits || !entries || !phi || !count || !start || !cursor || !tiles || !buckets || !segsum || !seg_run || !grpsum || !winsum || !part || !big)
+    return fail("workspace allocation failed");
+  int lgS = 0, lgG = 0, ubits = 0;
+  while ((1u << lgS) < sh.S) lgS++;
+  while ((1u << lgG) < G) lgG++;
+  while ((1u << ubits) < ngrp * (1u + sh.dbl)) ubits++;
+
+  if (g.profiling) cudaEventRecord(g.ev[0], st);
+  BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
+  BP_CUDA(cudaMemsetAsync(cursor, 0, (nb + 1) * sizeof(u32), st));
+  BP_CUDA(cudaMemsetAsync(big, 0, W * (big_cap + 2) * sizeof(u32), st));
+  k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
+  k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, nullptr, 1, sh, digits, count);
+  k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
+  k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
+  k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
+  k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, nullptr, 1, sh, start, cursor, entries);
+  BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));
+  BP_CUDA(cudaEventRecord(g.pe_prep, st));
+  BP_CUDA(cudaStreamWaitEvent(g.ps_acc[0], g.pe_prep, 0));
+  BP_CUDA(cudaStreamWaitEvent(g.ps_acc[1], g.pe_prep, 0));
+  int k = 0;
+  for (int w = (int)W - 1; w >= 0; w--, k++) {
+    cudaStream_t sa = g.ps_acc[k & 1], sr = g.ps_red[w], shh = g.ps_hor;
+    const u32* gs = start + (size_t)w * sh.H;
+    XYZZ* part_w = part + 2 * (size_t)w * wchunks;
+    u32* big_w = big + (size_t)w * (big_cap + 2);
+    k_accumulate<<<(unsigned)((wchunks + 127) / 128), 128, 0, sa>>>(points, point_idx, phi, start, entries, gs, gs + sh.H, buckets, part_w);
+    BP_CUDA(cudaEventRecord(g.pe_acc[w], sa));
+    BP_CUDA(cudaStreamWaitEvent(sr, g.pe_acc[w], 0));
+    // everything after the accumulation of window w is a latency chain on few SMs: it lives on the window's own stream
+    k_fixup<<<(unsigned)((sh.H + 127) / 128), 128, 0, sr>>>(start, (size_t)w * sh.H, sh.H, gs, part_w, buckets, big_w, big_w + 1);
+    k_fixup_big<<<32, 256, 0, sr>>>(start, gs, part_w, buckets, big_w, big_w + 1);
+    const XYZZ* bw = buckets + (size_t)w * sh.H;
+    k_reduce_seg<<<(unsigned)((4 * (size_t)sh.nseg + 127) / 128), 128, 0, sr>>>(bw, sh, 1, seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg);
+    k_reduce_grp<<<(unsigned)((4 * (size_t)ngrp + 127) / 128), 128, 0, sr>>>(seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg, sh, 1, (u32)w, G, lgS, lgG,
+                                                                              ubits, grpsum + (size_t)w * ngrp);
+    if (ngrp > 1) k_window_sum<<<1, 256, 0, sr>>>(grpsum + (size_t)w * ngrp, ngrp, winsum + w);
+    else BP_CUDA(cudaMemcpyAsync(winsum + w, grpsum + (size_t)w * ngrp, sizeof(XYZZ), cudaMemcpyDeviceToDevice, sr));
+    BP_CUDA(cudaEventRecord(g.pe_red[w], sr));
+    BP_CUDA(cudaStreamWaitEvent(shh, g.pe_red[w], 0));
+    k_horner_step<<<1, 32, 0, shh>>>(hacc, winsum + w, (sh.dbl && w == (int)W - 2) ? 0 : sh.c, w == (int)W - 1 ? 1 : 0);
+  }
+  k_finish<<<1, 32, 0, g.ps_hor>>>(hacc, out_affine, out_xyzz);
+  BP_CUDA(cudaEventRecord(g.pe_done, g.ps_hor));
+  BP_CUDA(cudaStreamWaitEvent(st, g.pe_done, 0));
+  // the accumulate streams also rejoin (their last events precede pe_done through the dependency chain)
+  if (g.profiling) { for (int i = 1; i <= 6; i++) cudaEventRecord(g.ev[i], st); }
   BP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -276,6 +376,7 @@ int bp_msm_last_entries(uint64_t* entries) {      // non-zero digits = mixed add
   return 0;
 }
 int bp_msm_set_profiling(int on) { g.profiling = on != 0; return 0; }
+int bp_msm_set_pipeline_min(size_t min_terms) { g.pipeline_min_terms = min_terms ? (unsigned)min_terms : 0xFFFFFFFFu; return 0; }
 int bp_msm_stage_ms(float out7[7]) {
   BP_NEED_INIT();
   BP_CUDA(cudaStreamSynchronize(g.stream));

@@ -41,15 +41,39 @@ struct Ctx {
   size_t last_nb = 0;
   // MSM workspaces
   DevBuf ws_pts, ws_sc, ws_off, ws_out, ws_digits, ws_entries, ws_count, ws_start, ws_cursor, ws_tiles, ws_buckets, ws_segsum,
-      ws_winsum, ws_misc, ws_flush, ws_entry_bucket, ws_part, ws_big, ws_phi;
+      ws_winsum, ws_misc, ws_flush, ws_entry_bucket, ws_part, ws_big, ws_phi, ws_segrun, ws_grpsum;
   // IPA / verifier workspaces
   DevBuf ws_g, ws_h, ws_a, ws_b, ws_g2, ws_h2, ws_a2, ws_b2, ws_idx, ws_lr, ws_terms_sc, ws_small;
+  // pipelined single-MSM path: 2 accumulate streams, one reduce stream per window, one Horner stream
+  unsigned pipeline_min_terms = 0xFFFFFFFFu;   // off by default: on B200 the tail kernels starve behind the resident accumulate blocks
+  cudaStream_t ps_acc[2] = {nullptr, nullptr}, ps_red[20] = {nullptr}, ps_hor = nullptr;
+  cudaEvent_t pe_prep = nullptr, pe_done = nullptr, pe_acc[20], pe_red[20];
+  int pipe_windows = 0;
+  int ensure_pipeline(int W) {
+    if (W > 20) return fail("pipeline: too many windows");
+    if (!ps_hor) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      for (int i = 0; i < 2; i++) if (cudaStreamCreateWithPriority(&ps_acc[i], cudaStreamNonBlocking, lo) != cudaSuccess) return fail("stream creation failed");
+      if (cudaStreamCreateWithPriority(&ps_hor, cudaStreamNonBlocking, hi) != cudaSuccess) return fail("stream creation failed");
+      if (cudaEventCreateWithFlags(&pe_prep, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&pe_done, cudaEventDisableTiming) != cudaSuccess)
+        return fail("event creation failed");
+    }
+    for (; pipe_windows < W; pipe_windows++) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&ps_red[pipe_windows], cudaStreamNonBlocking, hi) != cudaSuccess) return fail("stream creation failed");
+      if (cudaEventCreateWithFlags(&pe_acc[pipe_windows], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&pe_red[pipe_windows], cudaEventDisableTiming) != cudaSuccess) return fail("event creation failed");
+    }
+    return 0;
+  }
   unsigned* h_pin = nullptr;
   unsigned* pinned_u32() { if (!h_pin && cudaHostAlloc((void**)&h_pin, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h_pin = nullptr; } return h_pin; }
   void free_all() {
     DevBuf* all[] = {&ws_pts, &ws_sc, &ws_off, &ws_out, &ws_digits, &ws_entries, &ws_count, &ws_start, &ws_cursor, &ws_tiles,
                      &ws_buckets, &ws_segsum, &ws_winsum, &ws_misc, &ws_flush, &ws_g, &ws_h, &ws_a, &ws_b, &ws_g2, &ws_h2,
-                     &ws_a2, &ws_b2, &ws_idx, &ws_lr, &ws_terms_sc, &ws_small, &ws_entry_bucket, &ws_part, &ws_big, &ws_phi};
+                     &ws_a2, &ws_b2, &ws_idx, &ws_lr, &ws_terms_sc, &ws_small, &ws_entry_bucket, &ws_part, &ws_big, &ws_phi, &ws_segrun, &ws_grpsum};
     for (DevBuf* b : all) b->release();
   }
 };

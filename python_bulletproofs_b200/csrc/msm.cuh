@@ -23,17 +23,21 @@
 #include "ec.cuh"
 #include "fq.cuh"
 #include "glv.cuh"
+#include "coop4.cuh"
 
 namespace bp {
 
 struct MsmShape {
   int c;          // window bits
-  int W;          // windows = ceil(129 / c): GLV halves are < 2^128 in magnitude, +1 bit for the signed-digit carry
-  u32 H;          // buckets per window = 2^(c-1)
+  int W;          // windows = ceil(128 / c): the GLV halves are < 2^128 in magnitude
+  int U;          // bucket units of H buckets per MSM: W, or W + 1 when c divides 128 -- the top window then takes its
+                  // digit unrecoded in [0, 2^c] (it absorbs the signed-digit carry) and owns two consecutive units
+  int dbl;        // 1 when the top window owns two units
+  u32 H;          // buckets per unit = 2^(c-1)
   u32 S;          // buckets per reduce segment
   u32 nseg;       // segments per window
 };
-#define BP_GLV_BITS 129
+#define BP_GLV_BITS 128
 
 inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
   MsmShape s;
@@ -41,7 +45,7 @@ inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
   const double n = (double)terms_per_msm;
   for (int c = 1; c <= 16; c++) {
     double W = (BP_GLV_BITS + c - 1) / c, H = (double)(1u << (c - 1));
-    double entries = 2.0 * n * ((double)(BP_GLV_BITS - 1) / c + 0.3);     // non-zero digits: 2 halves x ~128/c windows
+    double entries = 2.0 * n * W;                                          // non-zero digits: 2 halves x W windows
     double cost;
     if (nmsm <= 8) {
       // a few MSMs: measured on B200 (profiles/r1_window_sweep.txt).  Windows whose top digit keeps only a few
@@ -56,6 +60,8 @@ inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
   }
   s.c = force_c > 0 ? force_c : best;
   s.W = (BP_GLV_BITS + s.c - 1) / s.c;
+  s.dbl = (BP_GLV_BITS % s.c) == 0 ? 1 : 0;
+  s.U = s.W + s.dbl;
   s.H = 1u << (s.c - 1);
   s.S = s.H < 16 ? s.H : 16;
   s.nseg = s.H / s.S;
@@ -100,13 +106,15 @@ __global__ void __launch_bounds__(256) k_digits(const Fq* __restrict__ scalars, 
     for (int w = 0; w < sh.W; w++) {
       u32 d = scalar_bits(kk, w * sh.c, sh.c) + carry;
       int sd;
-      if (d > sh.H) { sd = (int)d - (int)(2u * sh.H); carry = 1; } else { sd = (int)d; carry = 0; }
+      // signed recoding below the top window; the top window keeps its digit (<= 2^(c-1) when c does not divide 128,
+      // <= 2^c otherwise, where it spills into the second bucket unit) so no further window is needed
+      if (w + 1 < sh.W && d > sh.H) { sd = (int)d - (int)(2u * sh.H); carry = 1; } else { sd = (int)d; carry = 0; }
       if (neg) sd = -sd;
       digits[(size_t)w * (2 * (size_t)T) + 2 * t + j] = sd;
       // histogram with warp-aggregated atomics: lanes that hit the same bucket (common for the top window, whose
       // digit has only a few significant bits, and for repeated scalars) issue ONE atomicAdd between them
       u32 mag = sd < 0 ? (u32)(-sd) : (u32)sd;
-      u32 bkt = sd != 0 ? (u32)(((size_t)m * sh.W + w) * sh.H + (mag - 1)) : 0xFFFFFFFFu;
+      u32 bkt = sd != 0 ? (u32)(((size_t)m * sh.U + w) * sh.H + (mag - 1)) : 0xFFFFFFFFu;
       u32 act = __activemask();
       u32 peers = __match_any_sync(act, bkt);
       if (sd != 0 && (u32)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(bucket_count + bkt, (u32)__popc(peers));
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits,
   for (int w = 0; w < sh.W; w++) {
     int sd = digits[(size_t)w * (2 * (size_t)T) + st];
     u32 mag = sd < 0 ? (u32)(-sd) : (u32)sd;
-    u32 b = sd != 0 ? (u32)(((size_t)m * sh.W + w) * sh.H + (mag - 1)) : 0xFFFFFFFFu;
+    u32 b = sd != 0 ? (u32)(((size_t)m * sh.U + w) * sh.H + (mag - 1)) : 0xFFFFFFFFu;
     // warp-aggregated cursor: one atomicAdd per distinct bucket per warp, lanes take consecutive slots
     u32 act = __activemask();
     u32 peers = __match_any_sync(act, b);
@@ -225,11 +233,13 @@ BP_DI const Affine* entry_point_ptr(const Affine* __restrict__ points, const u32
 #endif
 __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* __restrict__ points, const u32* __restrict__ point_idx, const Affine* __restrict__ phi,
                                                     const u32* __restrict__ bucket_start, const uint2* __restrict__ entries,
-                                                    const u32* __restrict__ E_ptr, XYZZ* __restrict__ buckets,
-                                                    XYZZ* __restrict__ part) {
+                                                    const u32* __restrict__ gs_ptr, const u32* __restrict__ ge_ptr,
+                                                    XYZZ* __restrict__ buckets, XYZZ* __restrict__ part) {
+  // entry range [gs, ge) of this launch (all windows, or one window of the pipelined single-MSM path); both bounds
+  // are bucket_start[] words, read on the device so that no host round trip separates the sort from the accumulation
   u32 chunk = blockIdx.x * blockDim.x + threadIdx.x;
-  u32 cs = chunk * BP_CHUNK;
-  const u32 E = __ldg(E_ptr);                 // = bucket_start[nb], the number of non-zero digits
+  const u32 gs = __ldg(gs_ptr), E = __ldg(ge_ptr);
+  u32 cs = gs + chunk * BP_CHUNK;
   if (cs >= E) return;
   u32 ce = cs + BP_CHUNK < E ? cs + BP_CHUNK : E;
   uint2 ent = __ldg(entries + cs);
@@ -262,6 +272,7 @@ __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* _
   else st_xyzz(buckets + b, acc);
 }
 
+// s, c0, c are relative to the launch's first entry gs
 BP_DI const XYZZ* bucket_piece(const XYZZ* part, u32 s, u32 c0, u32 c) {
   if (c == c0) return part + 2 * (size_t)c + (s == c0 * BP_CHUNK ? 0 : 1);
   return part + 2 * (size_t)c;
@@ -269,12 +280,16 @@ BP_DI const XYZZ* bucket_piece(const XYZZ* part, u32 s, u32 c0, u32 c) {
 
 // one thread per bucket: buckets spanning up to BP_FIXUP_SERIAL_MAX chunks are summed here, larger
 // ones are queued for k_fixup_big (one block each).
-__global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_start, size_t nb, const XYZZ* __restrict__ part,
-                                               XYZZ* __restrict__ buckets, u32* __restrict__ big_count, u32* __restrict__ big_list) {
+__global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_start, size_t b0, size_t nb, const u32* __restrict__ gs_ptr,
+                                               const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, u32* __restrict__ big_count,
+                                               u32* __restrict__ big_list) {
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
+  b += b0;
+  const u32 gs = __ldg(gs_ptr);
   u32 s = __ldg(bucket_start + b), e = __ldg(bucket_start + b + 1);
   if (e == s) return;
+  s -= gs; e -= gs;
   u32 c0 = s / BP_CHUNK, c1 = (e - 1) / BP_CHUNK;
   if (c0 == c1) return;
   if (c1 - c0 >= BP_FIXUP_SERIAL_MAX) { big_list[atomicAdd(big_count, 1u)] = (u32)b; return; }
@@ -284,14 +299,15 @@ __global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_st
 }
 
 // persistent blocks over the queue of giant buckets: 256 threads stride over the pieces, tree in shared memory
-__global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucket_start, const XYZZ* __restrict__ part,
-                                                   XYZZ* __restrict__ buckets, const u32* __restrict__ big_count,
-                                                   const u32* __restrict__ big_list) {
+__global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucket_start, const u32* __restrict__ gs_ptr,
+                                                   const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets,
+                                                   const u32* __restrict__ big_count, const u32* __restrict__ big_list) {
   __shared__ XYZZ sm[256];
   u32 n = *big_count;
+  const u32 gs = __ldg(gs_ptr);
   for (u32 q = blockIdx.x; q < n; q += gridDim.x) {
     u32 b = big_list[q];
-    u32 s = __ldg(bucket_start + b), e = __ldg(bucket_start + b + 1);
+    u32 s = __ldg(bucket_start + b) - gs, e = __ldg(bucket_start + b + 1) - gs;
     u32 c0 = s / BP_CHUNK, c1 = (e - 1) / BP_CHUNK;
     XYZZ acc = xyzz_identity();
     for (u32 c = c0 + threadIdx.x; c <= c1; c += 256) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c)); xyzz_add(acc, v); }
@@ -306,60 +322,121 @@ __global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucke
   }
 }
 
-// acc = k * p for a small k (k < 2^16), left-to-right double-and-add
-BP_DI XYZZ xyzz_mul_small(const XYZZ& p, u32 k) {
-  XYZZ acc = xyzz_identity();
-  for (int i = 15; i >= 0; i--) {
-    acc = xyzz_dbl(acc);
-    if ((k >> i) & 1) xyzz_add(acc, p);
-  }
-  return acc;
-}
-
-// one thread per (msm*W + w, seg): sum_{i<S} (seg*S + i + 1) * B[i]
-__global__ void __launch_bounds__(128) k_reduce_seg(const XYZZ* __restrict__ buckets, MsmShape sh, size_t nmw, XYZZ* __restrict__ segsum) {
-  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= nmw * sh.nseg) return;
-  size_t mw = id / sh.nseg; u32 seg = (u32)(id % sh.nseg);
-  const XYZZ* B = buckets + mw * sh.H + (size_t)seg * sh.S;
+// ---- tails: bucket reduction, window sums, Horner -- 4 lanes per point operation (coop4.cuh) -------------
+// Level 1 -- one QUAD per (msm*W + w, seg): plain and weighted sums of the S buckets of a segment by the running-sum
+// trick:  run = sum_i B[i],  sum = sum_i (i+1) * B[i].
+__global__ void __launch_bounds__(128) k_reduce_seg(const XYZZ* __restrict__ buckets, MsmShape sh, size_t nmw,
+                                                    XYZZ* __restrict__ seg_run, XYZZ* __restrict__ seg_sum) {
+  const size_t total = nmw * sh.nseg;
+  size_t qid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const bool active = qid < total;
+  if (!active) qid = total - 1;                       // idle quads shadow the last one (shuffles need the whole warp)
+  const XYZZ* B = buckets + qid * sh.S;               // segments are contiguous: (mw * nseg + seg) * S
   XYZZ run = xyzz_identity(), sum = xyzz_identity();
   for (int i = (int)sh.S - 1; i >= 0; i--) {
-    XYZZ b = ld_xyzz(B + i);
-    xyzz_add(run, b);
-    xyzz_add(sum, run);
+    XYZZ bk = ld_xyzz(B + i);
+    run = coop_add(run, bk, role, base);
+    sum = coop_add(sum, run, role, base);
   }
-  u32 off = seg * sh.S;
-  if (off) { XYZZ sc = xyzz_mul_small(run, off); xyzz_add(sum, sc); }
-  st_xyzz(segsum + id, sum);
+  if (active && role == 0) { st_xyzz(seg_run + qid, run); st_xyzz(seg_sum + qid, sum); }
 }
 
-// one block (256 threads) per (msm, window): winsum = sum of nseg segment results
-__global__ void __launch_bounds__(256) k_window_sum(const XYZZ* __restrict__ segsum, u32 nseg, XYZZ* __restrict__ winsum) {
-  __shared__ XYZZ sm[256];
-  size_t mw = blockIdx.x;
+// Level 2 -- one QUAD per group of G consecutive segments of one window (G = 16, or nseg when smaller).  With segment
+// j of group u starting at bucket (u*G + j)*S, the group's share of  sum_b (b+1) * B_b  is
+//   P + S * T + (u*G*S) * R,   P = sum_j seg_sum_j,  T = sum_j j * seg_run_j,  R = sum_j seg_run_j,
+// where the last product is a double-and-add over the bits of u followed by log2(G*S) doublings.
+__global__ void __launch_bounds__(128) k_reduce_grp(const XYZZ* __restrict__ seg_run, const XYZZ* __restrict__ seg_sum, MsmShape sh,
+                                                    size_t nmw, u32 unit0, u32 G, int lgS, int lgG, int ubits, XYZZ* __restrict__ grpsum) {
+  const u32 ngrp = sh.nseg / G;
+  const size_t total = nmw * ngrp;
+  size_t qid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const bool active = qid < total;
+  if (!active) qid = total - 1;
+  u32 u = (u32)(qid % ngrp);
+  if (sh.dbl && (int)((qid / ngrp + unit0) % sh.U) == sh.U - 1) u += ngrp;   // second unit of the top window: weights continue at H
+  const XYZZ* Rn = seg_run + qid * G;
+  const XYZZ* Sm = seg_sum + qid * G;
+  XYZZ run = xyzz_identity(), T = xyzz_identity(), P = xyzz_identity();
+  for (int j = (int)G - 1; j >= 0; j--) {
+    XYZZ r = ld_xyzz(Rn + j), sj = ld_xyzz(Sm + j);
+    if (j > 0) { run = coop_add(run, r, role, base); T = coop_add(T, run, role, base); }   // weights j = 0..G-1
+    else run = coop_add(run, r, role, base);
+    P = coop_add(P, sj, role, base);
+  }
+  for (int d = 0; d < lgS; d++) T = coop_dbl(T, role, base);                 // S * T
   XYZZ acc = xyzz_identity();
-  for (u32 i = threadIdx.x; i < nseg; i += 256) { XYZZ v = ld_xyzz(segsum + mw * nseg + i); xyzz_add(acc, v); }
-  sm[threadIdx.x] = acc;
+  for (int i = ubits - 1; i >= 0; i--) {                                     // u * R
+    acc = coop_dbl(acc, role, base);
+    XYZZ t = coop_add(acc, run, role, base);
+    acc = sel_xyzz((u >> i) & 1, t, acc);
+  }
+  if (ubits > 0) for (int d = 0; d < lgS + lgG; d++) acc = coop_dbl(acc, role, base);     // * G * S
+  P = coop_add(P, T, role, base);
+  P = coop_add(P, acc, role, base);
+  if (active && role == 0) st_xyzz(grpsum + qid, P);
+}
+
+// one block (256 threads = 64 quads) per (msm, window): winsum = sum of nseg segment results
+__global__ void __launch_bounds__(256) k_window_sum(const XYZZ* __restrict__ segsum, u32 nseg, XYZZ* __restrict__ winsum) {
+  __shared__ XYZZ sm[64];
+  const size_t mw = blockIdx.x;
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const u32 q = threadIdx.x >> 2;
+  XYZZ acc = xyzz_identity();
+  for (u32 i0 = 0; i0 < nseg; i0 += 64) {             // uniform trip count; out-of-range quads add the identity
+    u32 i = i0 + q;
+    XYZZ v = i < nseg ? ld_xyzz(segsum + mw * nseg + i) : xyzz_identity();
+    acc = coop_add(acc, v, role, base);
+  }
+  if (role == 0) sm[q] = acc;
   __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) {
-    if (threadIdx.x < off) { XYZZ v = sm[threadIdx.x + off]; xyzz_add(acc, v); sm[threadIdx.x] = acc; }
+  for (u32 off = 32; off > 0; off >>= 1) {
+    XYZZ v = (q < off) ? sm[q + off] : xyzz_identity();
+    acc = coop_add(acc, v, role, base);
+    __syncthreads();
+    if (q < off && role == 0) sm[q] = acc;
     __syncthreads();
   }
   if (threadIdx.x == 0) st_xyzz(winsum + mw, acc);
 }
 
-// one thread per msm: Horner over windows, then canonical affine (optionally XYZZ partials for sharding)
-__global__ void __launch_bounds__(64) k_combine(const XYZZ* __restrict__ winsum, MsmShape sh, size_t nmsm, Affine* __restrict__ out,
-                                                XYZZ* __restrict__ out_xyzz) {
-  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= nmsm) return;
-  const XYZZ* ws = winsum + m * sh.W;
-  XYZZ acc = ld_xyzz(ws + sh.W - 1);
-  for (int w = sh.W - 2; w >= 0; w--) {
-    for (int d = 0; d < sh.c; d++) acc = xyzz_dbl(acc);
-    XYZZ v = ld_xyzz(ws + w);
-    xyzz_add(acc, v);
+// pipelined single-MSM path: acc <- 2^c * acc + winsum  (first: acc <- winsum), one quad
+__global__ void __launch_bounds__(32) k_horner_step(XYZZ* __restrict__ acc_io, const XYZZ* __restrict__ ws, int ndbl, int first) {
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  XYZZ v = ld_xyzz(ws);
+  XYZZ acc = v;
+  if (!first) {
+    acc = ld_xyzz(acc_io);
+    for (int d = 0; d < ndbl; d++) acc = coop_dbl(acc, role, base);
+    acc = coop_add(acc, v, role, base);
   }
+  if (threadIdx.x == 0) st_xyzz(acc_io, acc);
+}
+__global__ void __launch_bounds__(32) k_finish(const XYZZ* __restrict__ acc_in, Affine* __restrict__ out, XYZZ* __restrict__ out_xyzz) {
+  if (threadIdx.x != 0) return;
+  XYZZ acc = ld_xyzz(acc_in);
+  if (out_xyzz) st_xyzz(out_xyzz, acc);
+  if (out) st_affine(out, xyzz_to_affine(acc));
+}
+
+// one QUAD per msm: Horner over windows (c doublings each), then canonical affine (optionally XYZZ partials for sharding)
+__global__ void __launch_bounds__(128) k_combine(const XYZZ* __restrict__ winsum, MsmShape sh, size_t nmsm, Affine* __restrict__ out,
+                                                 XYZZ* __restrict__ out_xyzz) {
+  size_t m = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const bool active = m < nmsm;
+  if (!active) m = nmsm - 1;
+  const XYZZ* ws = winsum + m * sh.U;
+  XYZZ acc = ld_xyzz(ws + sh.U - 1);
+  if (sh.dbl) { XYZZ v = ld_xyzz(ws + sh.U - 2); acc = coop_add(acc, v, role, base); }   // both units of the top window
+  for (int w = sh.W - 2; w >= 0; w--) {
+    for (int d = 0; d < sh.c; d++) acc = coop_dbl(acc, role, base);
+    XYZZ v = ld_xyzz(ws + w);
+    acc = coop_add(acc, v, role, base);
+  }
+  if (!active || role != 0) return;
   if (out_xyzz) st_xyzz(out_xyzz + m, acc);
   if (out) st_affine(out + m, xyzz_to_affine(acc));
 }
