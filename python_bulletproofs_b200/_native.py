@@ -48,6 +48,8 @@ PROTOTYPES = {
                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), c_u8p]),
     "bp_rp_proof_stride": (c_sz, [c_sz]),
     "bp_mod_hash": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
+    "bp_sha256": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
+    "bp_sha256_set_portable": (ctypes.c_int, [ctypes.c_int]),
     "bp_point_to_b64": (ctypes.c_int, [c_u8p, c_u8p, ctypes.POINTER(c_sz)]),
     "bp_bench_msm": (ctypes.c_int, [c_h, c_h, c_sz, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_u8p]),
     "bp_imad_peak": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]),

@@ -90,22 +90,31 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, part, buckets, big, big + 1);
   if (prof) cudaEventRecord(g.ev[4], st);
   size_t nsegs = nmw * sh.nseg;
-  XYZZ* seg_run = (XYZZ*)g.ws_segrun.ensure(nsegs * sizeof(XYZZ));
-  if (!seg_run) return fail("workspace allocation failed");
-  k_reduce_seg<<<(unsigned)((4 * nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
-  // level 2: groups of G segments
-  u32 G = sh.nseg < 16 ? sh.nseg : 16, ngrp = sh.nseg / G;
-  int lgS = 0, lgG = 0, ubits = 0;
-  while ((1u << lgS) < sh.S) lgS++;
-  while ((1u << lgG) < G) lgG++;
-  while ((1u << ubits) < ngrp * (1u + sh.dbl)) ubits++;
-  XYZZ* grpsum = (XYZZ*)g.ws_grpsum.ensure(nmw * ngrp * sizeof(XYZZ));
-  if (!grpsum) return fail("workspace allocation failed");
-  k_reduce_grp<<<(unsigned)((4 * nmw * ngrp + 127) / 128), 128, 0, st>>>(seg_run, segsum, sh, nmw, 0, G, lgS, lgG, ubits, grpsum);
-  const XYZZ* ws = grpsum;
-  if (ngrp > 1) { k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(grpsum, ngrp, winsum); ws = winsum; }
-  if (prof) cudaEventRecord(g.ev[5], st);
-  k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+  const bool plain_tails = nmsm >= 2048 && sh.nseg == 1;     // big batch of small MSMs: throughput forms
+  const XYZZ* ws;
+  if (plain_tails) {
+    k_reduce_unit_plain<<<(unsigned)((nmw + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);
+    ws = segsum;
+    if (prof) cudaEventRecord(g.ev[5], st);
+    k_combine_plain<<<(unsigned)((nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+  } else {
+    XYZZ* seg_run = (XYZZ*)g.ws_segrun.ensure(nsegs * sizeof(XYZZ));
+    if (!seg_run) return fail("workspace allocation failed");
+    k_reduce_seg<<<(unsigned)((4 * nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
+    // level 2: groups of G segments
+    u32 G = sh.nseg < 16 ? sh.nseg : 16, ngrp = sh.nseg / G;
+    int lgS = 0, lgG = 0, ubits = 0;
+    while ((1u << lgS) < sh.S) lgS++;
+    while ((1u << lgG) < G) lgG++;
+    while ((1u << ubits) < ngrp * (1u + sh.dbl)) ubits++;
+    XYZZ* grpsum = (XYZZ*)g.ws_grpsum.ensure(nmw * ngrp * sizeof(XYZZ));
+    if (!grpsum) return fail("workspace allocation failed");
+    k_reduce_grp<<<(unsigned)((4 * nmw * ngrp + 127) / 128), 128, 0, st>>>(seg_run, segsum, sh, nmw, 0, G, lgS, lgG, ubits, grpsum);
+    ws = grpsum;
+    if (ngrp > 1) { k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(grpsum, ngrp, winsum); ws = winsum; }
+    if (prof) cudaEventRecord(g.ev[5], st);
+    k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+  }
   if (prof) cudaEventRecord(g.ev[6], st);
   BP_CUDA(cudaGetLastError());
   return 0;

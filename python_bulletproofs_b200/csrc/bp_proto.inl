@@ -32,6 +32,12 @@ static int fold_step(const Affine* P, Affine* P2, const Fq* a, const Fq* b, Fq* 
 
 extern "C" {
 
+int bp_sha256(const uint8_t* msg, size_t len, uint8_t out32[32]) {
+  Sha256 s; s.update(msg, len); s.final(out32);
+  return 0;
+}
+int bp_sha256_set_portable(int on) { sha256_force_portable(on); return sha256_impl(); }
+
 int bp_mod_hash(const uint8_t* msg, size_t len, uint8_t out32[32]) {
   Fq x = mod_hash_q(msg, len);
   fq_to_le(out32, x);
@@ -84,8 +90,8 @@ int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64],
   Affine* PB = (Affine*)g.ws_g2.ensure((n + 1) * sizeof(Affine));
   Fq* aA = (Fq*)g.ws_a.ensure(n * sizeof(Fq)); Fq* bA = (Fq*)g.ws_b.ensure(n * sizeof(Fq));
   Fq* aB = (Fq*)g.ws_a2.ensure(n * sizeof(Fq)); Fq* bB = (Fq*)g.ws_b2.ensure(n * sizeof(Fq));
-  Fq* tsc = (Fq*)g.ws_terms_sc.ensure((2 * n + 2) * sizeof(Fq));
-  u32* tidx = (u32*)g.ws_idx.ensure((2 * n + 2) * sizeof(u32));
+  Fq* tsc = (Fq*)g.ws_terms_sc.ensure((2 * n + 4) * sizeof(Fq));
+  u32* tidx = (u32*)g.ws_idx.ensure((2 * n + 4) * sizeof(u32));
   u32* d_off = (u32*)g.ws_off.ensure(3 * sizeof(u32));
   Affine* d_lr = (Affine*)g.ws_lr.ensure(2 * sizeof(Affine));
   if (!PA || !PB || !aA || !bA || !aB || !bB || !tsc || !tidx || !d_off || !d_lr) return fail("device allocation failed");
@@ -98,14 +104,21 @@ int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64],
   // MSM terms, but the folds need reduced inputs, so reduce once here.
   k_reduce_scalars<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(aA, (u32)n);
   k_reduce_scalars<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(bA, (u32)n);
-  Affine *P = PA, *P2 = PB; Fq *a = aA, *b = bA, *a2 = aB, *b2 = bB;
+  Fq *a = aA, *b = bA, *a2 = aB, *b2 = bB;
+  // coefficient vectors of the folded generators over the original ones (see k_build_lr_sv); P = PA is never rewritten
+  Fq* cg = (Fq*)g.ws_h.ensure(2 * n * sizeof(Fq));
+  if (!cg) return fail("device allocation failed");
+  Fq* ch = cg + n;
+  k_fill_one_mont<<<(unsigned)((2 * n + 127) / 128), 128, 0, g.stream>>>(cg, (u32)(2 * n));
   size_t round = 0;
+  RunningModHash rh;
+  const u32 n1 = (u32)n + 1;
+  u32 h_off[3] = {0, n1, 2 * n1};
+  if (n > 1) BP_CUDA(cudaMemcpyAsync(d_off, h_off, sizeof h_off, cudaMemcpyHostToDevice, g.stream));
   for (size_t m = n; m > 1; m >>= 1, round++) {
-    u32 k = (u32)(m / 2), n1 = 2 * k + 1;
-    k_build_lr<<<1, 256, 0, g.stream>>>(a, b, k, tsc, tidx);
-    u32 h_off[3] = {0, n1, 2 * n1};
-    BP_CUDA(cudaMemcpyAsync(d_off, h_off, sizeof h_off, cudaMemcpyHostToDevice, g.stream));
-    if (msm_run(P, tidx, tsc, 2 * n1, d_off, 2, n1, d_lr, nullptr)) return 1;
+    u32 k = (u32)(m / 2);
+    k_build_lr_sv<<<1, 256, 0, g.stream>>>(a, b, cg, ch, (u32)n, (u32)m, tsc, tidx);
+    if (msm_run(PA, tidx, tsc, 2 * n1, d_off, 2, n1, d_lr, nullptr)) return 1;
     uint8_t lr[128];
     BP_CUDA(cudaMemcpyAsync(lr, d_lr, 128, cudaMemcpyDeviceToHost, g.stream));
     BP_CUDA(cudaStreamSynchronize(g.stream));
@@ -114,12 +127,13 @@ int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64],
     // transcript.add_list_points([L, R]); x = get_modp(q); add_number(x)      inner_product_prover.py:102-106
     digest += point_to_b64(lr); digest += '&';
     digest += point_to_b64(lr + 64); digest += '&';
-    Fq x = mod_hash_q((const uint8_t*)digest.data(), digest.size());
+    Fq x = rh.challenge((const uint8_t*)digest.data(), digest.size());
     fq_to_le(xs32 + 32 * round, x);
     digest += fq_to_decimal(x); digest += '&';
     ChallengeForms c = challenge_forms(x);
-    if (fold_step(P, P2, a, b, a2, b2, k, c)) return 1;
-    Affine* tp = P; P = P2; P2 = tp;
+    // fold a, b (inner_product_prover.py:109-110); the generator fold (:107-108) is carried by cg, ch
+    k_fold_scalars<<<(k + 127) / 128, 128, 0, g.stream>>>(a, b, k, c.xm, c.xim, a2, b2);
+    k_update_coef<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(cg, ch, (u32)n, (u32)m, c.xm, c.xim);
     Fq* t1 = a; a = a2; a2 = t1;
     Fq* t2 = b; b = b2; b2 = t2;
   }
@@ -206,19 +220,27 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   // record offsets inside a packed proof
   const size_t oV = 0, oA = 64, oS = 128, oT1 = 192, oT2 = 256, oTaux = 320, oMu = 352, oThat = 384, oUnew = 416, oPnew = 480,
                oa = 544, ob = 576, oXs = 608, oLs = oXs + 32 * L, oRs = oLs + 64 * L;
-  std::vector<uint8_t> hsc((size_t)nproofs * lay.nsc * 32), hpt((size_t)nproofs * lay.npt * 64);
+  // The batch is cut into chunks: while the GPU evaluates the equations of chunk i, the host threads run the
+  // transcript checks of chunk i+1 (pinned, double-buffered staging so the uploads are truly asynchronous).
+  const size_t CH = nproofs < 4096 ? nproofs : 2048;
+  const size_t sc_bytes = CH * lay.nsc * 32, pt_bytes = CH * lay.npt * 64;
+  uint8_t* stage = g.pinned_stage(2 * (sc_bytes + pt_bytes));
+  if (!stage) return fail("pinned staging allocation failed");
+  uint8_t* hsc_buf[2] = {stage, stage + sc_bytes + pt_bytes};
+  uint8_t* hpt_buf[2] = {stage + sc_bytes, stage + 2 * sc_bytes + pt_bytes};
   std::vector<uint8_t> host_ok(nproofs, 1);
+  size_t chunk_lo = 0;
+  int cur = 0;
   // ---- host: transcript checks + challenge extraction, threaded over proofs --------------------
   unsigned nthreads = std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
   if (nthreads > 64) nthreads = 64;
-  if (nthreads > nproofs) nthreads = (unsigned)nproofs;
   auto work = [&](size_t lo, size_t hi) {
     std::vector<std::pair<size_t, size_t>> sl;
     for (size_t p = lo; p < hi; p++) {
       const uint8_t* pr = proofs + p * proof_stride;
-      uint8_t* sc = hsc.data() + p * lay.nsc * 32;
-      uint8_t* pt = hpt.data() + p * lay.npt * 64;
+      uint8_t* sc = hsc_buf[cur] + (p - chunk_lo) * lay.nsc * 32;
+      uint8_t* pt = hpt_buf[cur] + (p - chunk_lo) * lay.npt * 64;
       memcpy(pt + 64 * RP_V, pr + oV, 64); memcpy(pt + 64 * RP_A, pr + oA, 64); memcpy(pt + 64 * RP_S, pr + oS, 64);
       memcpy(pt + 64 * RP_T1, pr + oT1, 64); memcpy(pt + 64 * RP_T2, pr + oT2, 64);
       memcpy(pt + 64 * RP_UNEW, pr + oUnew, 64); memcpy(pt + 64 * RP_PNEW, pr + oPnew, 64);
@@ -258,13 +280,14 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
         split_amp(t2, t2n, sl);
         size_t st = start_transcript[p];
         if (sl.size() < st + 3 * (size_t)L) verdict = L ? 2 : 1;
+        RunningModHash rh;
         for (u32 j = 0; j < L && verdict == 1; j++) {
           const auto& sL = sl[st + 3 * j]; const auto& sR = sl[st + 3 * j + 1]; const auto& sX = sl[st + 3 * j + 2];
           if (!slot_eq(t2, sL, point_to_b64(pr + oLs + 64 * j)) || !slot_eq(t2, sR, point_to_b64(pr + oRs + 64 * j))) { verdict = 0; break; }
           Fq xj; fq_from_le(&xj, pr + oXs + 32 * j);
           std::string xs_dec = fq_to_decimal(xj);
           // b"&".join(parts[:idx]) + b"&" is the transcript prefix up to and including the '&' before slot idx
-          Fq want = mod_hash_q(t2, sX.first);
+          Fq want = rh.challenge(t2, sX.first);
           if (!slot_eq(t2, sX, xs_dec) || !slot_eq(t2, sX, fq_to_decimal(want))) { verdict = 0; break; }
         }
       }
@@ -272,38 +295,50 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
       host_ok[p] = verdict;
     }
   };
-  {
-    std::vector<std::thread> th;
-    size_t per = (nproofs + nthreads - 1) / nthreads;
-    for (unsigned t = 0; t < nthreads; t++) {
-      size_t lo = t * per, hi = lo + per < nproofs ? lo + per : nproofs;
-      if (lo < hi) th.emplace_back(work, lo, hi);
-    }
-    for (auto& t : th) t.join();
-  }
-  // ---- device: scalar expansion, one batched MSM over 4*nproofs equations, accept bits ---------
-  size_t T = (size_t)nproofs * lay.tpp, npts = lay.fixed + (size_t)nproofs * lay.npt;
+  // ---- device buffers (sized for one chunk) and the shared generator table --------------------------
+  size_t Tc = CH * lay.tpp, npts = lay.fixed + CH * lay.npt;
   Affine* table = (Affine*)g.ws_pts.ensure(npts * sizeof(Affine));
-  Fq* psc = (Fq*)g.ws_small.ensure((size_t)nproofs * lay.nsc * sizeof(Fq));
-  Fq* tsc = (Fq*)g.ws_terms_sc.ensure(T * sizeof(Fq));
-  u32* tidx = (u32*)g.ws_idx.ensure(T * sizeof(u32));
-  u32* d_off = (u32*)g.ws_off.ensure((4 * nproofs + 1) * sizeof(u32));
-  Affine* d_res = (Affine*)g.ws_out.ensure(4 * nproofs * sizeof(Affine));
+  Fq* psc = (Fq*)g.ws_small.ensure(CH * lay.nsc * sizeof(Fq));
+  Fq* tsc = (Fq*)g.ws_terms_sc.ensure(Tc * sizeof(Fq));
+  u32* tidx = (u32*)g.ws_idx.ensure(Tc * sizeof(u32));
+  u32* d_off = (u32*)g.ws_off.ensure((4 * CH + 1) * sizeof(u32));
+  Affine* d_res = (Affine*)g.ws_out.ensure(4 * CH * sizeof(Affine));
   uint8_t* d_acc = (uint8_t*)g.ws_misc.ensure(nproofs);
-  if (!table || !psc || !tsc || !tidx || !d_off || !d_res || !d_acc) return fail("device allocation failed");
+  Fq* d_inv = (Fq*)g.ws_a.ensure(CH * (lay.L + 1) * sizeof(Fq));
+  if (!table || !psc || !tsc || !tidx || !d_off || !d_res || !d_acc || !d_inv) return fail("device allocation failed");
+  if (g.ensure_stage_events()) return 1;
   BP_CUDA(cudaMemcpyAsync(table, gs64, n * 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + n, hs64, n * 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n, g64, 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n + 1, h64, 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n + 2, u64_, 64, cudaMemcpyHostToDevice, g.stream));
-  BP_CUDA(cudaMemcpyAsync(table + lay.fixed, hpt.data(), hpt.size(), cudaMemcpyHostToDevice, g.stream));
-  BP_CUDA(cudaMemcpyAsync(psc, hsc.data(), hsc.size(), cudaMemcpyHostToDevice, g.stream));
-  k_reduce_scalars<<<(unsigned)(((size_t)nproofs * lay.nsc + 127) / 128), 128, 0, g.stream>>>(psc, (u32)(nproofs * lay.nsc));
-  u32 bd = n < 32 ? 32 : (u32)n;
-  size_t smem = (2 * L + 1 + bd) * sizeof(Fq);
-  k_rp_expand<<<(unsigned)nproofs, bd, smem, g.stream>>>(psc, lay, (u32)nproofs, tsc, tidx, d_off);
-  if (msm_run(table, tidx, tsc, (u32)T, d_off, (u32)(4 * nproofs), lay.tpp / 4, d_res, nullptr)) return 1;
-  k_rp_accept<<<(unsigned)((nproofs + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)nproofs, d_acc);
+  const u32 bd = n < 32 ? 32 : (u32)n;
+  const size_t smem = (2 * L + 1 + bd) * sizeof(Fq);
+  int chunk_no = 0;
+  for (chunk_lo = 0; chunk_lo < nproofs; chunk_lo += CH, chunk_no++) {
+    const size_t chunk_hi = chunk_lo + CH < nproofs ? chunk_lo + CH : nproofs, cn = chunk_hi - chunk_lo;
+    cur = chunk_no & 1;
+    if (chunk_no >= 2) BP_CUDA(cudaEventSynchronize(g.stage_ev[cur]));       // staging buffer free again?
+    {   // host: transcript checks of this chunk on all cores
+      std::vector<std::thread> th;
+      unsigned nt = nthreads > cn ? (unsigned)cn : nthreads;
+      size_t per = (cn + nt - 1) / nt;
+      for (unsigned t = 0; t < nt; t++) {
+        size_t lo = chunk_lo + t * per, hi = lo + per < chunk_hi ? lo + per : chunk_hi;
+        if (lo < hi) th.emplace_back(work, lo, hi);
+      }
+      for (auto& t : th) t.join();
+    }
+    // device: scalar expansion, one batched MSM over the 4*cn equations, accept bits
+    BP_CUDA(cudaMemcpyAsync(table + lay.fixed, hpt_buf[cur], cn * lay.npt * 64, cudaMemcpyHostToDevice, g.stream));
+    BP_CUDA(cudaMemcpyAsync(psc, hsc_buf[cur], cn * lay.nsc * 32, cudaMemcpyHostToDevice, g.stream));
+    BP_CUDA(cudaEventRecord(g.stage_ev[cur], g.stream));
+    k_reduce_scalars<<<(unsigned)((cn * lay.nsc + 127) / 128), 128, 0, g.stream>>>(psc, (u32)(cn * lay.nsc));
+    k_rp_invert<<<(unsigned)((cn + 63) / 64), 64, 0, g.stream>>>(psc, lay, (u32)cn, d_inv);
+    k_rp_expand<<<(unsigned)cn, bd, smem, g.stream>>>(psc, d_inv, lay, (u32)cn, tsc, tidx, d_off);
+    if (msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, (u32)(4 * cn), lay.tpp / 4, d_res, nullptr)) return 1;
+    k_rp_accept<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)cn, d_acc + chunk_lo);
+  }
   BP_CUDA(cudaMemcpyAsync(accept, d_acc, nproofs, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   for (size_t p = 0; p < nproofs; p++) if (host_ok[p] != 1) accept[p] = host_ok[p];

@@ -68,6 +68,22 @@ struct Ctx {
     }
     return 0;
   }
+  // pinned staging for the chunked batch verifier
+  unsigned char* stage_p = nullptr; size_t stage_cap = 0;
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  unsigned char* pinned_stage(size_t bytes) {
+    if (bytes <= stage_cap) return stage_p;
+    if (stage_p) cudaFreeHost(stage_p);
+    stage_p = nullptr; stage_cap = 0;
+    if (cudaHostAlloc((void**)&stage_p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    stage_cap = bytes;
+    return stage_p;
+  }
+  int ensure_stage_events() {
+    for (int i = 0; i < 2; i++)
+      if (!stage_ev[i] && cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming) != cudaSuccess) return fail("event creation failed");
+    return 0;
+  }
   unsigned* h_pin = nullptr;
   unsigned* pinned_u32() { if (!h_pin && cudaHostAlloc((void**)&h_pin, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h_pin = nullptr; } return h_pin; }
   void free_all() {

@@ -126,4 +126,63 @@ __global__ void __launch_bounds__(256) k_build_lr(const Fq* __restrict__ a, cons
   }
 }
 
+// ---- prover rounds without materialising the folded generators -----------------------------------------------
+// After j rounds the folded generator g^(j)_i is a fixed linear combination of the ORIGINAL generators,
+//   g^(j)_i = sum over t = i (mod m) of cg[t] * g_t,   cg[t] = prod_{r<j} x_r^(+1 if t lay in the upper half at round r, else -1)
+// (h likewise with inverted exponents, ch[t]), m = n / 2^j.  The round's commitments
+//   L = <a_lo, g_hi> + <b_hi, h_lo> + c_L u,   R = <a_hi, g_lo> + <b_lo, h_hi> + c_R u     (inner_product_prover.py:96-99)
+// are therefore two (n+1)-term multi-scalar multiplications over the original points with scalars a*cg / b*ch -- the
+// same group elements as the reference computes, at the cost of one batched MSM per round and no 256-bit scalar
+// multiplication per generator.  cg, ch are kept in Montgomery form; a, b in standard form.
+// One block of 256 threads.  Points live in [u | g (n) | h (n)].
+__global__ void __launch_bounds__(256) k_build_lr_sv(const Fq* __restrict__ a, const Fq* __restrict__ b, const Fq* __restrict__ cg,
+                                                     const Fq* __restrict__ ch, u32 n, u32 m, Fq* __restrict__ tsc, u32* __restrict__ tidx) {
+  __shared__ Fq sl[256], sr[256];
+  const u32 k = m >> 1, n1 = n + 1;
+  Fq accl = fq_zero(), accr = fq_zero();
+  for (u32 i = threadIdx.x; i < k; i += 256) {                 // c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>
+    accl = fq_add(accl, fq_mont(ld_fq(a + i), ld_fq(b + k + i)));
+    accr = fq_add(accr, fq_mont(ld_fq(a + k + i), ld_fq(b + i)));
+  }
+  // L terms: slots [0, n/2) g-part, [n/2, n) h-part, n = u ;  R terms follow at offset n1
+  for (u32 t = threadIdx.x; t < n; t += 256) {
+    const u32 i = t % m, blk = t / m;
+    const bool hi = i >= k;
+    const u32 slot = blk * k + (hi ? i - k : i);               // position among the n/2 terms of its kind
+    const Fq cgt = ld_fq(cg + t), cht = ld_fq(ch + t);
+    if (hi) {
+      tsc[slot] = fq_mont(ld_fq(a + i - k), cgt);              tidx[slot] = 1 + t;                       // L: a_lo[i-k] * g_t
+      tsc[n1 + n / 2 + slot] = fq_mont(ld_fq(b + i - k), cht); tidx[n1 + n / 2 + slot] = 1 + n + t;      // R: b_lo[i-k] * h_t
+    } else {
+      tsc[n1 + slot] = fq_mont(ld_fq(a + i + k), cgt);         tidx[n1 + slot] = 1 + t;                  // R: a_hi[i] * g_t
+      tsc[n / 2 + slot] = fq_mont(ld_fq(b + i + k), cht);      tidx[n / 2 + slot] = 1 + n + t;           // L: b_hi[i] * h_t
+    }
+  }
+  sl[threadIdx.x] = accl; sr[threadIdx.x] = accr;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      sl[threadIdx.x] = fq_add(sl[threadIdx.x], sl[threadIdx.x + off]);
+      sr[threadIdx.x] = fq_add(sr[threadIdx.x], sr[threadIdx.x + off]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    tsc[n] = fq_to_mont(sl[0]);       tidx[n] = 0;             // (sum * R^-1) * R ; point u
+    tsc[n1 + n] = fq_to_mont(sr[0]);  tidx[n1 + n] = 0;
+  }
+}
+// after the challenge: cg[t] *= (upper ? x : x^-1), ch[t] *= (upper ? x^-1 : x)   (xm, xim Montgomery forms)
+__global__ void __launch_bounds__(128) k_update_coef(Fq* __restrict__ cg, Fq* __restrict__ ch, u32 n, u32 m, Fq xm, Fq xim) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const bool hi = (t % m) >= (m >> 1);
+  st_fq(cg + t, fq_mont(ld_fq(cg + t), hi ? xm : xim));
+  st_fq(ch + t, fq_mont(ld_fq(ch + t), hi ? xim : xm));
+}
+__global__ void __launch_bounds__(128) k_fill_one_mont(Fq* __restrict__ v, u32 n) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) st_fq(v + t, fq_const_r());
+}
+
 }  // namespace bp

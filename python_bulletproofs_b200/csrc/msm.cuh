@@ -402,6 +402,42 @@ __global__ void __launch_bounds__(256) k_window_sum(const XYZZ* __restrict__ seg
   if (threadIdx.x == 0) st_xyzz(winsum + mw, acc);
 }
 
+// ---- throughput variants of the tails for large batches of small MSMs (one thread per unit / per MSM) -------------
+// With tens of thousands of MSMs in flight every lane already has its own independent chain, so the 4-lane
+// cooperative forms would only waste lanes.  Used when a unit is a single segment (H <= 16).
+__global__ void __launch_bounds__(128) k_reduce_unit_plain(const XYZZ* __restrict__ buckets, MsmShape sh, size_t nmw, XYZZ* __restrict__ unitsum) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nmw) return;
+  const XYZZ* B = buckets + id * sh.H;
+  XYZZ run = xyzz_identity(), sum = xyzz_identity();
+  for (int i = (int)sh.H - 1; i >= 0; i--) {
+    XYZZ b = ld_xyzz(B + i);
+    xyzz_add(run, b);
+    xyzz_add(sum, run);
+  }
+  if (sh.dbl && (int)(id % sh.U) == sh.U - 1) {        // second unit of the top window: weights H + i + 1
+    XYZZ t = run;
+    for (int d = 0; d < sh.c - 1; d++) t = xyzz_dbl(t);
+    xyzz_add(sum, t);
+  }
+  st_xyzz(unitsum + id, sum);
+}
+__global__ void __launch_bounds__(128) k_combine_plain(const XYZZ* __restrict__ winsum, MsmShape sh, size_t nmsm, Affine* __restrict__ out,
+                                                       XYZZ* __restrict__ out_xyzz) {
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nmsm) return;
+  const XYZZ* ws = winsum + m * sh.U;
+  XYZZ acc = ld_xyzz(ws + sh.U - 1);
+  if (sh.dbl) { XYZZ v = ld_xyzz(ws + sh.U - 2); xyzz_add(acc, v); }
+  for (int w = sh.W - 2; w >= 0; w--) {
+    for (int d = 0; d < sh.c; d++) acc = xyzz_dbl(acc);
+    XYZZ v = ld_xyzz(ws + w);
+    xyzz_add(acc, v);
+  }
+  if (out_xyzz) st_xyzz(out_xyzz + m, acc);
+  if (out) st_affine(out + m, xyzz_to_affine(acc));
+}
+
 // pipelined single-MSM path: acc <- 2^c * acc + winsum  (first: acc <- winsum), one quad
 __global__ void __launch_bounds__(32) k_horner_step(XYZZ* __restrict__ acc_io, const XYZZ* __restrict__ ws, int ndbl, int first) {
   const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;

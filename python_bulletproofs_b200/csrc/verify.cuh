@@ -35,18 +35,45 @@ inline RpLayout rp_layout(u32 n) {
   return l;
 }
 
+// One thread per proof: y^-1 and x_j^-1 from ONE field inversion (Montgomery's trick on the L+1 values), so that the
+// 256-step exponentiation runs on every lane of a warp at once instead of on 7 threads of each expansion block.
+// inv[p] = [y^-1, x_0^-1, ..., x_{L-1}^-1] in standard form.  (Zero inputs give zero "inverses"; such proofs are already
+// rejected by the transcript checks on the host.)
+__global__ void __launch_bounds__(64) k_rp_invert(const Fq* __restrict__ psc, RpLayout lay, u32 nproofs, Fq* __restrict__ inv) {
+  u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nproofs) return;
+  const Fq* S = psc + (size_t)p * lay.nsc;
+  const u32 cnt = lay.L + 1;
+  Fq* out = inv + (size_t)p * cnt;
+  // prefix products (standard form in out[] as scratch): out[i] = v_0 * ... * v_i
+  Fq acc = fq_one();
+  for (u32 i = 0; i < cnt; i++) {
+    Fq v = ld_fq(S + (i == 0 ? RS_Y : RS_XS + i - 1));
+    acc = fq_mul(acc, v);
+    st_fq(out + i, acc);
+  }
+  Fq t = fq_inv(acc);                                   // (v_0 ... v_L)^-1
+  for (int i = (int)cnt - 1; i >= 0; i--) {
+    Fq v = ld_fq(S + (i == 0 ? RS_Y : RS_XS + i - 1));
+    Fq prev = i > 0 ? ld_fq(out + i - 1) : fq_one();
+    st_fq(out + i, fq_mul(t, prev));                    // v_i^-1 = t * (v_0 ... v_{i-1})
+    t = fq_mul(t, v);
+  }
+}
+
 // One block per proof, n threads (n >= 32 rounded up by the launcher; extra threads idle).
 // Writes the proof's tpp term scalars / point indices and its 4 MSM offsets.
-__global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, RpLayout lay, u32 nproofs, Fq* __restrict__ tsc,
+__global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, const Fq* __restrict__ inv, RpLayout lay, u32 nproofs, Fq* __restrict__ tsc,
                                                     u32* __restrict__ tidx, u32* __restrict__ offsets) {
   extern __shared__ Fq sm[];      // [0..L) x_j (mont) | [L..2L) x_j^-1 (mont) | 2L: y^-1 (mont) | 2L+1 .. : reduction scratch (blockDim)
   const u32 p = blockIdx.x, i = threadIdx.x, n = lay.n, L = lay.L;
   if (p >= nproofs) return;
   const Fq* S = psc + (size_t)p * lay.nsc;
   Fq* xm = sm; Fq* xim = sm + L; Fq* yim = sm + 2 * L; Fq* red = sm + 2 * L + 1;
-  // inversions spread over the first L+1 threads
-  if (i < L) { Fq x = ld_fq(S + RS_XS + i); xm[i] = fq_to_mont(x); xim[i] = fq_to_mont(fq_inv(x)); }
-  if (i == L) { *yim = fq_to_mont(fq_inv(ld_fq(S + RS_Y))); }
+  // inverses come from k_rp_invert
+  const Fq* IV = inv + (size_t)p * (L + 1);
+  if (i < L) { xm[i] = fq_to_mont(ld_fq(S + RS_XS + i)); xim[i] = fq_to_mont(ld_fq(IV + 1 + i)); }
+  if (i == L) { *yim = fq_to_mont(ld_fq(IV)); }
   __syncthreads();
   const Fq y = ld_fq(S + RS_Y), z = ld_fq(S + RS_Z), x = ld_fq(S + RS_X), x1 = ld_fq(S + RS_X1);
   const Fq that = ld_fq(S + RS_THAT), taux = ld_fq(S + RS_TAUX), mu = ld_fq(S + RS_MU), a = ld_fq(S + RS_A), b = ld_fq(S + RS_B);

@@ -61,6 +61,24 @@ def test_host_c_transcript_helpers_match_oracle():
     assert b64.raw[:ln.value] == b"AA=="
 
 
+def test_sha256_both_implementations_match_hashlib():
+    """csrc/sha256_host.cc: portable and (when the CPU has them) SHA-NI compression functions."""
+    import hashlib
+    import random
+    lib = nat.load()
+    out = ctypes.create_string_buffer(32)
+    rng = random.Random(1)
+    try:
+        for force in (1, 0):
+            lib.bp_sha256_set_portable(force)
+            for n in list(range(0, 130)) + [255, 256, 1000, 4096, 5555]:
+                m = rng.randbytes(n)
+                assert lib.bp_sha256(m, n, out) == 0
+                assert out.raw == hashlib.sha256(m).digest(), (force, n)
+    finally:
+        lib.bp_sha256_set_portable(0)
+
+
 def test_host_fq_arithmetic_matches_bigint():
     import random
     rng = random.Random(4)
