@@ -91,6 +91,17 @@ int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64],
                  size_t n, const uint8_t* transcript, size_t transcript_len, uint8_t* Ls64, uint8_t* Rs64, uint8_t* xs32,
                  uint8_t a_out32[32], uint8_t b_out32[32], uint8_t* transcript_out, size_t tout_cap, size_t* tout_len);
 
+/* Same, with the h generators given as (h, hscale): the effective generators are hscale_i * h_i, which are never
+ * materialised (hscale32 = NULL means all ones).  The range-proof prover passes hs with hscale_i = y^-i instead of the
+ * list hsp of src/rangeproofs/rangeproof_prover.py:77. */
+int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscale32, const uint8_t u64_[64], const uint8_t* a32,
+                    const uint8_t* b32, size_t n, const uint8_t* transcript, size_t transcript_len, uint8_t* Ls64, uint8_t* Rs64,
+                    uint8_t* xs32, uint8_t a_out32[32], uint8_t b_out32[32], uint8_t* transcript_out, size_t tout_cap,
+                    size_t* tout_len);
+int bp_ipa_verify_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscale32, const uint8_t u64_[64], const uint8_t P64[64],
+                        size_t n, const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,
+                        const uint8_t* Rs64, int* accept);
+
 /* Verifier2.get_ss + the two multiexps of Verifier2.verify   inner_product_verifier.py:91-102,132-145
  * accept = 1 iff  MSM(g||h||u ; a*s || b*s^-1 || a*b) == P + MSM(Ls||Rs ; x^2 || x^-2).
  * (The transcript re-check, :104-125, is host string work done by the Python/C host layer.) */

@@ -43,6 +43,9 @@ PROTOTYPES = {
     "bp_ipa_fold_round": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
     "bp_ipa_prove": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
                                     c_u8p, c_sz, ctypes.POINTER(c_sz)]),
+    "bp_ipa_prove_hs": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
+                                       c_u8p, c_sz, ctypes.POINTER(c_sz)]),
+    "bp_ipa_verify_eq_hs": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, ctypes.POINTER(ctypes.c_int)]),
     "bp_ipa_verify_eq": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, ctypes.POINTER(ctypes.c_int)]),
     "bp_rp_verify_batch": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_sz, c_u8p,
                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), c_u8p]),

@@ -79,9 +79,10 @@ int bp_ipa_fold_round(const uint8_t* g64, const uint8_t* h64, const uint8_t* a32
   return 0;
 }
 
-int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64], const uint8_t* a32, const uint8_t* b32,
-                 size_t n, const uint8_t* transcript, size_t transcript_len, uint8_t* Ls64, uint8_t* Rs64, uint8_t* xs32,
-                 uint8_t a_out32[32], uint8_t b_out32[32], uint8_t* transcript_out, size_t tout_cap, size_t* tout_len) {
+int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscale32, const uint8_t u64_[64], const uint8_t* a32,
+                    const uint8_t* b32, size_t n, const uint8_t* transcript, size_t transcript_len, uint8_t* Ls64, uint8_t* Rs64,
+                    uint8_t* xs32, uint8_t a_out32[32], uint8_t b_out32[32], uint8_t* transcript_out, size_t tout_cap,
+                    size_t* tout_len) {
   BP_NEED_INIT();
   if (n == 0 || (n & (n - 1))) return fail("bp_ipa_prove: n must be a power of two");   // inner_product_prover.py:52
   std::string digest((const char*)transcript, transcript_len);
@@ -110,6 +111,10 @@ int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64],
   if (!cg) return fail("device allocation failed");
   Fq* ch = cg + n;
   k_fill_one_mont<<<(unsigned)((2 * n + 127) / 128), 128, 0, g.stream>>>(cg, (u32)(2 * n));
+  if (hscale32) {   // effective generators h_i' = hscale_i * h_i (e.g. y^-i, rangeproof_prover.py:77): start ch there
+    BP_CUDA(cudaMemcpyAsync(ch, hscale32, n * 32, cudaMemcpyHostToDevice, g.stream));
+    k_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(ch, (u32)n);
+  }
   size_t round = 0;
   RunningModHash rh;
   const u32 n1 = (u32)n + 1;
@@ -146,9 +151,16 @@ int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64],
   return 0;
 }
 
-int bp_ipa_verify_eq(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64], const uint8_t P64[64], size_t n,
-                     const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,
-                     const uint8_t* Rs64, int* accept) {
+int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64], const uint8_t* a32, const uint8_t* b32,
+                 size_t n, const uint8_t* transcript, size_t transcript_len, uint8_t* Ls64, uint8_t* Rs64, uint8_t* xs32,
+                 uint8_t a_out32[32], uint8_t b_out32[32], uint8_t* transcript_out, size_t tout_cap, size_t* tout_len) {
+  return bp_ipa_prove_hs(g64, h64, nullptr, u64_, a32, b32, n, transcript, transcript_len, Ls64, Rs64, xs32, a_out32, b_out32,
+                         transcript_out, tout_cap, tout_len);
+}
+
+int bp_ipa_verify_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscale32, const uint8_t u64_[64], const uint8_t P64[64],
+                        size_t n, const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,
+                        const uint8_t* Rs64, int* accept) {
   BP_NEED_INIT();
   if (n == 0 || (n & (n - 1))) return fail("bp_ipa_verify_eq: n must be a power of two");
   u32 L = 0; while (((size_t)1 << L) < n) L++;
@@ -176,7 +188,9 @@ int bp_ipa_verify_eq(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[
   memcpy(hp.data(), g64, n * 64); memcpy(hp.data() + n * 64, h64, n * 64); memcpy(hp.data() + 2 * n * 64, u64_, 64);
   for (size_t i = 0; i < n; i++) {
     fq_to_le(hs.data() + 32 * i, fq_mul(a, s[i]));                       // a * s_i
-    fq_to_le(hs.data() + 32 * (n + i), fq_mul(b, s[n - 1 - i]));         // b * s_i^-1  (s_i^-1 = s_{n-1-i})
+    Fq bs = fq_mul(b, s[n - 1 - i]);                                     // b * s_i^-1  (s_i^-1 = s_{n-1-i})
+    if (hscale32) { Fq sc; fq_from_le(&sc, hscale32 + 32 * i); bs = fq_mul(bs, fq_reduce(sc)); }   // h_i' = hscale_i * h_i
+    fq_to_le(hs.data() + 32 * (n + i), bs);
   }
   fq_to_le(hs.data() + 32 * 2 * n, fq_mul(a, b));
   uint8_t* p1 = hp.data() + T0 * 64; uint8_t* s1 = hs.data() + T0 * 32;
@@ -189,6 +203,12 @@ int bp_ipa_verify_eq(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[
   if (bp_msm_batch(hp.data(), hs.data(), off, 2, out)) return 1;
   *accept = memcmp(out, out + 64, 64) == 0 ? 1 : 0;
   return 0;
+}
+
+int bp_ipa_verify_eq(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64], const uint8_t P64[64], size_t n,
+                     const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,
+                     const uint8_t* Rs64, int* accept) {
+  return bp_ipa_verify_eq_hs(g64, h64, nullptr, u64_, P64, n, a32, b32, xs32, Ls64, Rs64, accept);
 }
 
 size_t bp_rp_proof_stride(size_t n) {

@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(128) k_update_coef(Fq* __restrict__ cg, Fq* __
   st_fq(cg + t, fq_mont(ld_fq(cg + t), hi ? xm : xim));
   st_fq(ch + t, fq_mont(ld_fq(ch + t), hi ? xim : xm));
 }
+__global__ void __launch_bounds__(128) k_to_mont(Fq* __restrict__ v, u32 n) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) st_fq(v + t, fq_to_mont(fq_reduce(ld_fq(v + t))));
+}
 __global__ void __launch_bounds__(128) k_fill_one_mont(Fq* __restrict__ v, u32 n) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) st_fq(v + t, fq_const_r());

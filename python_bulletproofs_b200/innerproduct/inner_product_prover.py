@@ -19,26 +19,29 @@ from .inner_product_verifier import Proof1, Proof2
 class NIProver:
     """Protocol 1 (inner_product_prover.py:11-45)."""
 
-    def __init__(self, g, h, u, P, c, a, b, group, seed=b""):
+    def __init__(self, g, h, u, P, c, a, b, group, seed=b"", _h_scale=None):
         assert len(g) == len(h) == len(a) == len(b)
         self.g, self.h, self.u, self.P, self.c, self.a, self.b = g, h, u, P, c, a, b
         self.group = group
         self.transcript = Transcript(seed)
+        self._h_scale = _h_scale      # private: effective generators are _h_scale[i] * h[i] (never materialised)
 
     def prove(self) -> Proof1:
         x = self.transcript.get_modp(self.group.q)
         self.transcript.add_number(x)
         # P_new = P + (x*c)*u ; u_new = x*u
         P_new, u_new = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
-        inner = FastNIProver2(self.g, self.h, u_new, P_new, self.a, self.b, self.group, self.transcript.digest)
+        inner = FastNIProver2(self.g, self.h, u_new, P_new, self.a, self.b, self.group, self.transcript.digest,
+                              _h_scale=self._h_scale)
         return Proof1(u_new, P_new, inner.prove(), self.transcript.digest)
 
 
 class FastNIProver2:
     """Protocol 2 (inner_product_prover.py:48-110)."""
 
-    def __init__(self, g, h, u, P, a, b, group, transcript: Optional[bytes] = None):
+    def __init__(self, g, h, u, P, a, b, group, transcript: Optional[bytes] = None, _h_scale=None):
         assert len(g) == len(h) == len(a) == len(b)
+        self._h_scale = _h_scale
         assert len(a) & (len(a) - 1) == 0
         self.log_n = len(a).bit_length() - 1
         self.n = len(a)
@@ -63,8 +66,9 @@ class FastNIProver2:
         a_out, b_out = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
         t_out = ctypes.create_string_buffer(cap)
         t_len = ctypes.c_size_t(0)
-        nat.check(nat.load().bp_ipa_prove(
-            nat.pack_points(self.g), nat.pack_points(self.h), nat.pack_point(self.u),
+        hscale = nat.pack_scalars(self._h_scale) if self._h_scale is not None else None
+        nat.check(nat.load().bp_ipa_prove_hs(
+            nat.pack_points(self.g), nat.pack_points(self.h), hscale, nat.pack_point(self.u),
             nat.pack_scalars(self.a), nat.pack_scalars(self.b), n, start, len(start),
             Ls, Rs, xs, a_out, b_out, t_out, cap, ctypes.byref(t_len)))
         self.transcript.digest = t_out.raw[:t_len.value]

@@ -47,8 +47,9 @@ class _Checker:
 class Verifier1(_Checker):
     """Protocol 1 verifier (inner_product_verifier.py:20-58)."""
 
-    def __init__(self, g, h, u, P, c, proof1):
+    def __init__(self, g, h, u, P, c, proof1, _h_scale=None):
         self.g, self.h, self.u, self.P, self.c, self.proof1 = g, h, u, P, c, proof1
+        self._h_scale = _h_scale      # private: effective generators are _h_scale[i] * h[i] (never materialised)
 
     def verify_transcript(self):
         parts = self.proof1.transcript.split(b"&")
@@ -61,14 +62,16 @@ class Verifier1(_Checker):
         rhs_P, rhs_u = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
         self.assertThat(self.proof1.P_new == rhs_P)
         self.assertThat(self.proof1.u_new == rhs_u)
-        return Verifier2(self.g, self.h, self.proof1.u_new, self.proof1.P_new, self.proof1.proof2).verify()
+        return Verifier2(self.g, self.h, self.proof1.u_new, self.proof1.P_new, self.proof1.proof2,
+                         _h_scale=self._h_scale).verify()
 
 
 class Verifier2(_Checker):
     """Protocol 2 verifier (inner_product_verifier.py:76-147)."""
 
-    def __init__(self, g, h, u, P, proof: Proof2):
+    def __init__(self, g, h, u, P, proof: Proof2, _h_scale=None):
         self.g, self.h, self.u, self.P, self.proof = g, h, u, P, proof
+        self._h_scale = _h_scale
 
     def get_ss(self, xs):
         """s_i = prod_j xs[j]^(+1 if bit j (MSB first) of i is set else -1), built in O(n) by flipping
@@ -108,8 +111,9 @@ class Verifier2(_Checker):
             if x % SUPERCURVE.q == 0:
                 raise Exception("modular inverse does not exist")      # ModP.inv, utils.py:69-70
         accept = ctypes.c_int(0)
-        nat.check(nat.load().bp_ipa_verify_eq(
-            nat.pack_points(self.g), nat.pack_points(self.h), nat.pack_point(self.u), nat.pack_point(self.P), n,
+        hscale = nat.pack_scalars(self._h_scale) if self._h_scale is not None else None
+        nat.check(nat.load().bp_ipa_verify_eq_hs(
+            nat.pack_points(self.g), nat.pack_points(self.h), hscale, nat.pack_point(self.u), nat.pack_point(self.P), n,
             nat.pack_scalar(proof.a), nat.pack_scalar(proof.b), nat.pack_scalars(proof.xs[:log_n]),
             nat.pack_points(proof.Ls[:log_n]), nat.pack_points(proof.Rs[:log_n]), ctypes.byref(accept)))
         self.assertThat(accept.value == 1)

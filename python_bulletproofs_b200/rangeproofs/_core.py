@@ -47,6 +47,16 @@ def _position_constants(y, z, n, nm, q):
     return ypow, zz
 
 
+def inverse_powers(y, n, q):
+    """[y^0, y^-1, ..., y^-(n-1)] mod q."""
+    yinv = pow(int(y) % q, -1, q)
+    out, acc = [], 1
+    for _ in range(n):
+        out.append(acc)
+        acc = acc * yinv % q
+    return out
+
+
 def scale_generators(hs, y, q):
     """hsp[i] = y^-i * hs[i]  (rangeproof_prover.py:77): one batched device call."""
     n = len(hs)
@@ -104,12 +114,14 @@ def prove(vs, n, g, h, gs, hs, gammas, u, group, transcript: Transcript):
         zpow = zpow * zv % q
     taux = (tau2 * xv * xv + tau1 * xv + gsum) % q
     mu = (alpha + rho * xv) % q
-    hsp = scale_generators(hs, y, q)
-    # P - mu*h = A + x*S + sum(-z * gs_i) + sum((z*y^i + zz_i) * hsp_i) - mu*h : one MSM
+    # hsp_i = y^-i * hs_i (rangeproof_prover.py:77) is never materialised: its scalars are folded into the MSMs
+    yinv_pow = inverse_powers(yv, nm, q)
+    # P - mu*h = A + x*S + sum(-z * gs_i) + sum((z*y^i + zz_i) * y^-i * hs_i) - mu*h : one MSM
     P_inner = PipSECP256k1.multiexp(
-        [A, S, h] + gs + hsp,
-        [1, xv, -mu] + [-zv] * nm + [(zv * ypow[i] + zz[i]) % q for i in range(nm)])
-    inner = NIProver(gs, hsp, u, P_inner, ModP(t_hat, q), [ModP(v, q) for v in ls], [ModP(v, q) for v in rs], group)
+        [A, S, h] + gs + hs,
+        [1, xv, -mu] + [-zv] * nm + [(zv + zz[i] * yinv_pow[i]) % q for i in range(nm)])
+    inner = NIProver(gs, hs, u, P_inner, ModP(t_hat, q), [ModP(v, q) for v in ls], [ModP(v, q) for v in rs], group,
+                     _h_scale=yinv_pow)
     return Proof(ModP(taux, q), ModP(mu, q), ModP(t_hat, q), T1, T2, A, S, inner.prove(), transcript.digest)
 
 
@@ -144,11 +156,13 @@ class VerifierCore:
         ypow, zz = _position_constants(yv, zv, n, nm, q)
         zpows = [pow(zv, j + 2, q) for j in range(m + 1)]
         delta = ((zv - zv * zv) * sum(ypow) - sum(zpows[j] * (2 ** n - 1) for j in range(1, m + 1))) % q
-        hsp = scale_generators(hs, self.y, q)
+        if yv == 0:
+            raise Exception("modular inverse does not exist")          # y.inv(), utils.py:69-70
+        yinv_pow = inverse_powers(yv, nm, q)                             # hsp_i = y^-i * hs_i stays implicit
         # t_hat*g + taux*h == sum z^(j+2) V_j + delta*g + x*T1 + x^2*T2      (one device pass, exact compare)
         lhs, rhs, P_inner = PipSECP256k1.multiexp_batch(
-            [[g, h], list(Vs) + [g, proof.T1, proof.T2], [proof.A, proof.S, h] + gs + hsp],
+            [[g, h], list(Vs) + [g, proof.T1, proof.T2], [proof.A, proof.S, h] + gs + hs],
             [[proof.t_hat, proof.taux], zpows[:m] + [delta, xv, xv * xv % q],
-             [1, xv, -(proof.mu.x)] + [-zv] * nm + [(zv * ypow[i] + zz[i]) % q for i in range(nm)]])
+             [1, xv, -(proof.mu.x)] + [-zv] * nm + [(zv + zz[i] * yinv_pow[i]) % q for i in range(nm)]])
         self.assertThat(lhs == rhs)
-        return Verifier1(gs, hsp, self.u, P_inner, proof.t_hat, proof.innerProof).verify()
+        return Verifier1(gs, hs, self.u, P_inner, proof.t_hat, proof.innerProof, _h_scale=yinv_pow).verify()
