@@ -61,9 +61,9 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   XYZZ* segsum = (XYZZ*)g.ws_segsum.ensure(nmw * sh.nseg * sizeof(XYZZ));
   XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure(nmw * sizeof(XYZZ));
   // every (term, window) pair is at most one entry, so E <= W*T: size the chunk structures for the bound
-  size_t emax = (size_t)sh.W * 2 * T, nchunks = (emax + BP_CHUNK - 1) / BP_CHUNK;
+  size_t emax = (size_t)sh.W * 2 * T, nchunks = (emax + sh.chunk - 1) / sh.chunk;
   XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * nchunks * sizeof(XYZZ));
-  size_t big_cap = emax / ((size_t)BP_CHUNK * BP_FIXUP_SERIAL_MAX) + 16;
+  size_t big_cap = emax / ((size_t)sh.chunk * BP_FIXUP_SERIAL_MAX) + 16;
   u32* big = (u32*)g.ws_big.ensure((big_cap + 3) * sizeof(u32));
   u32* zero_word = big + big_cap + 2;
   if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !segsum || !winsum || !part || !big || !phi)
@@ -85,12 +85,12 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));   // [0] = queue length, kept zero word for gs = 0 lives at big[big_cap + 1]
   // E (= start[nb]) stays on the device: launch for the upper bound W*T, threads past E exit at once
-  k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, buckets, part);
-  k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, part, buckets, big, big + 1);
-  k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, part, buckets, big, big + 1);
+  k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
+  k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big + 1);
+  k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
   if (prof) cudaEventRecord(g.ev[4], st);
   size_t nsegs = nmw * sh.nseg;
-  const bool plain_tails = nmsm >= 2048 && sh.nseg == 1;     // big batch of small MSMs: throughput forms
+  const bool plain_tails = nmsm >= 2048 && sh.H <= 64;     // big batch of small MSMs: throughput forms
   const XYZZ* ws;
   if (plain_tails) {
     k_reduce_unit_plain<<<(unsigned)((nmw + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);
@@ -102,7 +102,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     if (!seg_run) return fail("workspace allocation failed");
     k_reduce_seg<<<(unsigned)((4 * nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
     // level 2: groups of G segments
-    u32 G = sh.nseg < 16 ? sh.nseg : 16, ngrp = sh.nseg / G;
+    u32 G = sh.nseg < 8 ? sh.nseg : 8, ngrp = sh.nseg / G;
     int lgS = 0, lgG = 0, ubits = 0;
     while ((1u << lgS) < sh.S) lgS++;
     while ((1u << lgG) < G) lgG++;
@@ -145,13 +145,13 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
   XYZZ* buckets = (XYZZ*)g.ws_buckets.ensure(nb * sizeof(XYZZ));
   XYZZ* segsum = (XYZZ*)g.ws_segsum.ensure(W * sh.nseg * sizeof(XYZZ));
   XYZZ* seg_run = (XYZZ*)g.ws_segrun.ensure(W * sh.nseg * sizeof(XYZZ));
-  u32 G = sh.nseg < 16 ? sh.nseg : 16, ngrp = sh.nseg / G;
+  u32 G = sh.nseg < 8 ? sh.nseg : 8, ngrp = sh.nseg / G;
   XYZZ* grpsum = (XYZZ*)g.ws_grpsum.ensure(W * ngrp * sizeof(XYZZ));
   XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure((W + 1) * sizeof(XYZZ));
   XYZZ* hacc = winsum + W;                                   // Horner accumulator
-  const size_t wchunks = ((size_t)2 * T + BP_CHUNK - 1) / BP_CHUNK + 1;      // a window holds at most 2T entries
+  const size_t wchunks = ((size_t)2 * T + sh.chunk - 1) / sh.chunk + 1;      // a window holds at most 2T entries
   XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * W * wchunks * sizeof(XYZZ));
-  const size_t big_cap = (size_t)2 * T / ((size_t)BP_CHUNK * BP_FIXUP_SERIAL_MAX) + 16;
+  const size_t big_cap = (size_t)2 * T / ((size_t)sh.chunk * BP_FIXUP_SERIAL_MAX) + 16;
   u32* big = (u32*)g.ws_big.ensure(W * (big_cap + 2) * sizeof(u32));
   if (!digits || !entries || !phi || !count || !start || !cursor || !tiles || !buckets || !segsum || !seg_run || !grpsum || !winsum || !part || !big)
     return fail("workspace allocation failed");
@@ -180,12 +180,12 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
     const u32* gs = start + (size_t)w * sh.H;
     XYZZ* part_w = part + 2 * (size_t)w * wchunks;
     u32* big_w = big + (size_t)w * (big_cap + 2);
-    k_accumulate<<<(unsigned)((wchunks + 127) / 128), 128, 0, sa>>>(points, point_idx, phi, start, entries, gs, gs + sh.H, buckets, part_w);
+    k_accumulate<<<(unsigned)((wchunks + 127) / 128), 128, 0, sa>>>(points, point_idx, phi, start, entries, gs, gs + sh.H, sh.chunk, buckets, part_w);
     BP_CUDA(cudaEventRecord(g.pe_acc[w], sa));
     BP_CUDA(cudaStreamWaitEvent(sr, g.pe_acc[w], 0));
     // everything after the accumulation of window w is a latency chain on few SMs: it lives on the window's own stream
-    k_fixup<<<(unsigned)((sh.H + 127) / 128), 128, 0, sr>>>(start, (size_t)w * sh.H, sh.H, gs, part_w, buckets, big_w, big_w + 1);
-    k_fixup_big<<<32, 256, 0, sr>>>(start, gs, part_w, buckets, big_w, big_w + 1);
+    k_fixup<<<(unsigned)((sh.H + 127) / 128), 128, 0, sr>>>(start, (size_t)w * sh.H, sh.H, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
+    k_fixup_big<<<32, 256, 0, sr>>>(start, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
     const XYZZ* bw = buckets + (size_t)w * sh.H;
     k_reduce_seg<<<(unsigned)((4 * (size_t)sh.nseg + 127) / 128), 128, 0, sr>>>(bw, sh, 1, seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg);
     k_reduce_grp<<<(unsigned)((4 * (size_t)ngrp + 127) / 128), 128, 0, sr>>>(seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg, sh, 1, (u32)w, G, lgS, lgG,

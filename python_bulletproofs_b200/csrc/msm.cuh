@@ -27,6 +27,9 @@
 
 namespace bp {
 
+#define BP_CHUNK 32                // entries per accumulation thread (large problems)
+#define BP_FIXUP_SERIAL_MAX 64     // buckets spanning more chunks than this are summed by a whole block
+
 struct MsmShape {
   int c;          // window bits
   int W;          // windows = ceil(128 / c): the GLV halves are < 2^128 in magnitude
@@ -34,6 +37,7 @@ struct MsmShape {
                   // digit unrecoded in [0, 2^c] (it absorbs the signed-digit carry) and owns two consecutive units
   int dbl;        // 1 when the top window owns two units
   u32 H;          // buckets per unit = 2^(c-1)
+  u32 chunk;      // entries per accumulation thread (BP_CHUNK, or 8 for small problems where latency rules)
   u32 S;          // buckets per reduce segment
   u32 nseg;       // segments per window
 };
@@ -63,7 +67,8 @@ inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
   s.dbl = (BP_GLV_BITS % s.c) == 0 ? 1 : 0;
   s.U = s.W + s.dbl;
   s.H = 1u << (s.c - 1);
-  s.S = s.H < 16 ? s.H : 16;
+  s.chunk = (2.0 * n * s.W * (double)nmsm) < 262144.0 ? 8 : BP_CHUNK;
+  s.S = s.H < 8 ? s.H : 8;
   s.nseg = s.H / s.S;
   return s;
 }
@@ -218,8 +223,6 @@ __global__ void __launch_bounds__(256) k_scan_add(u32* __restrict__ out, const u
 // part[2*chunk + 0] (piece starting at the chunk start) or part[2*chunk + 1] (piece starting inside the
 // chunk and running past its end); k_fixup adds the pieces of every bucket that spans chunks.
 // bucket_start has nb + 1 entries (the last = E).  buckets[] must be zeroed (identity) beforehand.
-#define BP_CHUNK 32
-#define BP_FIXUP_SERIAL_MAX 64
 
 BP_DI const Affine* entry_point_ptr(const Affine* __restrict__ points, const u32* __restrict__ point_idx,
                                     const Affine* __restrict__ phi, u32 e) {
@@ -233,15 +236,15 @@ BP_DI const Affine* entry_point_ptr(const Affine* __restrict__ points, const u32
 #endif
 __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* __restrict__ points, const u32* __restrict__ point_idx, const Affine* __restrict__ phi,
                                                     const u32* __restrict__ bucket_start, const uint2* __restrict__ entries,
-                                                    const u32* __restrict__ gs_ptr, const u32* __restrict__ ge_ptr,
+                                                    const u32* __restrict__ gs_ptr, const u32* __restrict__ ge_ptr, u32 CL,
                                                     XYZZ* __restrict__ buckets, XYZZ* __restrict__ part) {
   // entry range [gs, ge) of this launch (all windows, or one window of the pipelined single-MSM path); both bounds
   // are bucket_start[] words, read on the device so that no host round trip separates the sort from the accumulation
   u32 chunk = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 gs = __ldg(gs_ptr), E = __ldg(ge_ptr);
-  u32 cs = gs + chunk * BP_CHUNK;
+  u32 cs = gs + chunk * CL;
   if (cs >= E) return;
-  u32 ce = cs + BP_CHUNK < E ? cs + BP_CHUNK : E;
+  u32 ce = cs + CL < E ? cs + CL : E;
   uint2 ent = __ldg(entries + cs);
   u32 b = ent.y;
   u32 s = __ldg(bucket_start + b), e = __ldg(bucket_start + b + 1);
@@ -273,14 +276,14 @@ __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* _
 }
 
 // s, c0, c are relative to the launch's first entry gs
-BP_DI const XYZZ* bucket_piece(const XYZZ* part, u32 s, u32 c0, u32 c) {
-  if (c == c0) return part + 2 * (size_t)c + (s == c0 * BP_CHUNK ? 0 : 1);
+BP_DI const XYZZ* bucket_piece(const XYZZ* part, u32 s, u32 c0, u32 c, u32 CL) {
+  if (c == c0) return part + 2 * (size_t)c + (s == c0 * CL ? 0 : 1);
   return part + 2 * (size_t)c;
 }
 
 // one thread per bucket: buckets spanning up to BP_FIXUP_SERIAL_MAX chunks are summed here, larger
 // ones are queued for k_fixup_big (one block each).
-__global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_start, size_t b0, size_t nb, const u32* __restrict__ gs_ptr,
+__global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_start, size_t b0, size_t nb, const u32* __restrict__ gs_ptr, u32 CL,
                                                const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, u32* __restrict__ big_count,
                                                u32* __restrict__ big_list) {
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -290,16 +293,16 @@ __global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_st
   u32 s = __ldg(bucket_start + b), e = __ldg(bucket_start + b + 1);
   if (e == s) return;
   s -= gs; e -= gs;
-  u32 c0 = s / BP_CHUNK, c1 = (e - 1) / BP_CHUNK;
+  u32 c0 = s / CL, c1 = (e - 1) / CL;
   if (c0 == c1) return;
   if (c1 - c0 >= BP_FIXUP_SERIAL_MAX) { big_list[atomicAdd(big_count, 1u)] = (u32)b; return; }
-  XYZZ acc = ld_xyzz(bucket_piece(part, s, c0, c0));
-  for (u32 c = c0 + 1; c <= c1; c++) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c)); xyzz_add(acc, v); }
+  XYZZ acc = ld_xyzz(bucket_piece(part, s, c0, c0, CL));
+  for (u32 c = c0 + 1; c <= c1; c++) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add(acc, v); }
   st_xyzz(buckets + b, acc);
 }
 
 // persistent blocks over the queue of giant buckets: 256 threads stride over the pieces, tree in shared memory
-__global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucket_start, const u32* __restrict__ gs_ptr,
+__global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucket_start, const u32* __restrict__ gs_ptr, u32 CL,
                                                    const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets,
                                                    const u32* __restrict__ big_count, const u32* __restrict__ big_list) {
   __shared__ XYZZ sm[256];
@@ -308,9 +311,9 @@ __global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucke
   for (u32 q = blockIdx.x; q < n; q += gridDim.x) {
     u32 b = big_list[q];
     u32 s = __ldg(bucket_start + b) - gs, e = __ldg(bucket_start + b + 1) - gs;
-    u32 c0 = s / BP_CHUNK, c1 = (e - 1) / BP_CHUNK;
+    u32 c0 = s / CL, c1 = (e - 1) / CL;
     XYZZ acc = xyzz_identity();
-    for (u32 c = c0 + threadIdx.x; c <= c1; c += 256) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c)); xyzz_add(acc, v); }
+    for (u32 c = c0 + threadIdx.x; c <= c1; c += 256) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add(acc, v); }
     sm[threadIdx.x] = acc;
     __syncthreads();
     for (int off = 128; off > 0; off >>= 1) {
