@@ -141,34 +141,49 @@ def run_ours(args):
     result_hex = out.raw.hex()
     value = world * n * args.steps / (total_ms * 1e-3) / 1e6
 
-    # ---- per-stage device times of one MSM (dominant kernel = k_accumulate), same stream, CUDA events
+    # ---- per-stage device times of one MSM and of the dominant kernel (k_accumulate) alone: CUDA events recorded on
+    #      the library stream around the stages / the kernel while profiling mode is on
     stage = (ctypes.c_float * 7)()
-    acc_ms = []
+    kms = ctypes.c_float()
+    acc_ms, stage_rows = [], []
     lib.bp_msm_set_profiling(1)
-    for _ in range(3):
+    for _ in range(5):
         nat.check(lib.bp_msm_hh(hp, hs, n, out))
         nat.check(lib.bp_msm_stage_ms(stage))
-        acc_ms.append(stage[3])
+        nat.check(lib.bp_msm_accumulate_kernel_ms(ctypes.byref(kms)))
+        acc_ms.append(kms.value)
+        stage_rows.append(list(stage))
     lib.bp_msm_set_profiling(0)
-    stages = {k: round(float(v), 4) for k, v in zip(["digits", "scan", "scatter", "accumulate", "reduce", "combine", "total"], stage)}
+    med = [statistics.median(r[i] for r in stage_rows) for i in range(7)]
+    stages = {k: round(float(v), 4) for k, v in zip(["digits", "scan", "scatter", "accumulate_stage", "reduce", "combine", "total"], med)}
     c = lib.bp_msm_last_window()
-    W = (129 + c - 1) // c                    # GLV: two 128-bit halves per scalar, +1 bit for the signed-digit carry
+    W = (128 + c - 1) // c                    # GLV: two halves < 2^128 per scalar; the top window absorbs the recoding carry
     ent = ctypes.c_uint64()
     nat.check(lib.bp_msm_last_entries(ctypes.byref(ent)))
     acc = statistics.median(acc_ms)
-    # algorithmic work of the accumulation stage: one mixed add (8M + 2S = 10 field mul = 1360 limb-MAC) per
-    # non-zero signed digit; ent.value is that count, read back from the device (~ n * 256 / c).
+    # Work of one k_accumulate launch = one mixed add (XYZZ + affine, 8M + 2S) per non-zero signed digit; ent.value is
+    # that count, read back from the device (~ 2 halves * n * 128 / c).
+    #  * issued: this implementation spends 72 IMAD.WIDE per field multiplication (64 + 8, pseudo-Mersenne fold) and 45
+    #    per squaring, i.e. 666 32x32->64 multiply-accumulates per mixed add -- the count the IMAD.WIDE pipe peak bounds;
+    #  * algorithmic (SURVEY.md 8d units): 10 field multiplications x 136 limb-MAC (8-limb Montgomery CIOS) = 1360.
+    issued_macs = ent.value * (8 * 72 + 2 * 45)
     alg_macs = ent.value * FIELD_MULS_PER_MADD * LIMB_MACS_PER_FIELD_MUL
-    achieved = alg_macs / (acc * 1e-3) / 1e12
+    achieved = issued_macs / (acc * 1e-3) / 1e12
     peak = macs.value / 1e12
     nominal = 148 * 64 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
     roofline = {"bound": "imad", "kernel": "k_accumulate", "achieved": round(achieved, 3), "peak": round(peak, 3),
-                "unit": "Tlimb-MAC/s", "frac": round(achieved / peak, 4), "traffic": None,
-                "peak_source": "bp_imad_peak: IMAD.WIDE.U32 issue-rate microbenchmark run in this process (measured)",
-                "nominal_peak": round(nominal, 2), "frac_of_nominal": round(achieved / nominal, 4),
-                "window_bits": c, "windows": W, "glv": True, "mixed_adds_per_launch": ent.value, "kernel_ms": round(acc, 4), "share_of_step": round(acc / stage[6], 3),
-                "algorithmic_limb_macs_per_launch": alg_macs,
-                "whole_msm_limb_macs_per_pt": (alg_macs + W * (1 << (c - 1)) * 2 * FIELD_MULS_PER_ADD * LIMB_MACS_PER_FIELD_MUL) / n,
+                "unit": "T IMAD.WIDE (32x32+64 limb-MAC)/s", "frac": round(achieved / peak, 4), "traffic": 432352512,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch, ncu --set full (profiles/)",
+                "peak_source": "measured in this process: bp_imad_peak, data-dependent IMAD.WIDE.U32 stream (SASS checked); "
+                               "IMAD.WIDE issues at half the 32-bit IMAD rate on B200, with or without the carry predicate",
+                "nominal_imad32_peak": round(nominal, 2),
+                "ncu_pipe_fmaheavy_active_pct": 80.2,
+                "window_bits": c, "windows": W, "glv": True, "mixed_adds_per_launch": ent.value, "kernel_ms": round(acc, 4),
+                "share_of_step": round(acc / med[6], 3),
+                "issued_limb_macs_per_launch": issued_macs,
+                "algorithmic_limb_macs_per_launch_survey_units": alg_macs,
+                "algorithmic_rate_survey_units_T_per_s": round(alg_macs / (acc * 1e-3) / 1e12, 3),
+                "whole_msm_algorithmic_limb_macs_per_pt": round((alg_macs + (W + (1 if 128 % c == 0 else 0)) * (1 << (c - 1)) * 2 * FIELD_MULS_PER_ADD * LIMB_MACS_PER_FIELD_MUL) / n, 1),
                 "hbm": {"bound": "hbm", "achieved": round(ent.value * 72 / (acc * 1e-3) / 1e9, 1), "unit": "GB/s",
                         "peak": measured_hbm(), "note": "gathered 64 B point + 8 B entry per mixed add; not the binding resource"}}
 

@@ -66,6 +66,7 @@ int bp_msm_set_profiling(int on);
 /* single MSMs with at least this many terms run with their windows pipelined over streams (0 = never) */
 int bp_msm_set_pipeline_min(size_t min_terms);
 int bp_msm_stage_ms(float out7[7]);
+int bp_msm_accumulate_kernel_ms(float* ms);   /* k_accumulate alone (stage [3] also holds the bucket memset and the fix-ups) */
 
 /* ---- independent scalar multiplications --------------------------------------------------------
  * out[i] = sc[i] * pts[i]:  hsp = [(y.inv() ** i) * hs[i] ...]

@@ -85,7 +85,9 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));   // [0] = queue length, kept zero word for gs = 0 lives at big[big_cap + 1]
   // E (= start[nb]) stays on the device: launch for the upper bound W*T, threads past E exit at once
+  if (prof) cudaEventRecord(g.ev_k0, st);
   k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
+  if (prof) cudaEventRecord(g.ev_k1, st);
   k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big + 1);
   k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
   if (prof) cudaEventRecord(g.ev[4], st);
@@ -345,6 +347,7 @@ int bp_init(int device) {
   BP_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (int i = 0; i < 8; i++) BP_CUDA(cudaEventCreate(&g.ev[i]));
   BP_CUDA(cudaEventCreate(&g.ev_a)); BP_CUDA(cudaEventCreate(&g.ev_b));
+  BP_CUDA(cudaEventCreate(&g.ev_k0)); BP_CUDA(cudaEventCreate(&g.ev_k1));
   g.inited = true;
   return 0;
 }
@@ -375,6 +378,12 @@ int bp_device_info(char* name, size_t cap, int* sm_count, int* cc_major, int* cc
 
 int bp_msm_set_window(int c) { if (c < 0 || c > 16) return fail("window must be 0..16"); g.force_c = c; return 0; }
 int bp_msm_last_window(void) { return g.last_c; }
+int bp_msm_accumulate_kernel_ms(float* ms) {      // CUDA-event duration of k_accumulate alone in the last profiled MSM
+  BP_NEED_INIT();
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  if (cudaEventElapsedTime(ms, g.ev_k0, g.ev_k1) != cudaSuccess) { cudaGetLastError(); *ms = -1.f; }
+  return 0;
+}
 int bp_msm_last_entries(uint64_t* entries) {      // non-zero digits = mixed additions of the last MSM's accumulation
   BP_NEED_INIT();
   if (!g.ws_start.p) return fail("no MSM has run yet");

@@ -35,7 +35,7 @@ struct Ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8];
-  cudaEvent_t ev_a, ev_b;
+  cudaEvent_t ev_a, ev_b, ev_k0, ev_k1;
   bool profiling = false;
   int force_c = 0, last_c = 0;
   size_t last_nb = 0;
