@@ -137,7 +137,6 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
     total_ms = max_over_ranks(dist, float(sum(times)))
-    clocks = sampler.stop(t0, t1)
     result_hex = out.raw.hex()
     value = world * n * args.steps / (total_ms * 1e-3) / 1e6
 
@@ -170,7 +169,7 @@ def run_ours(args):
     alg_macs = ent.value * FIELD_MULS_PER_MADD * LIMB_MACS_PER_FIELD_MUL
     achieved = issued_macs / (acc * 1e-3) / 1e12
     peak = macs.value / 1e12
-    nominal = 148 * 64 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
+    nominal = 148 * 64 * 1965.0 * 1e6 / 1e12
     roofline = {"bound": "imad", "kernel": "k_accumulate", "achieved": round(achieved, 3), "peak": round(peak, 3),
                 "unit": "T IMAD.WIDE (32x32+64 limb-MAC)/s", "frac": round(achieved / peak, 4), "traffic": 432352512,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch, ncu --set full (profiles/)",
@@ -202,6 +201,7 @@ def run_ours(args):
            "d2h_bytes_per_step": 64, "api": "bp_msm_sharded_host (C ABI, pinned host buffers)" if world > 1 else "bp_msm / bp_msm_sharded_host (C ABI, pinned host buffers)"}
     lib.bp_host_free(pp)
     lib.bp_host_free(ps)
+    clocks = sampler.stop(t0, time.time())       # sampled from the start of the timed region through the e2e loop
 
     line = {"metric": METRIC, "value": round(value, 3), "unit": "Mpts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

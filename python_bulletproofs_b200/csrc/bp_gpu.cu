@@ -35,7 +35,10 @@ int fail(const char* fmt, ...) {
 static int msm_run_pipelined(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, Affine* out_affine, XYZZ* out_xyzz);
 int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, const u32* d_offsets, u32 nmsm,
             size_t terms_per_msm, Affine* out_affine, XYZZ* out_xyzz) {
-  if (nmsm == 1 && T >= g.pipeline_min_terms && !g.profiling) return msm_run_pipelined(points, point_idx, scalars, T, out_affine, out_xyzz);
+  if (nmsm == 1 && T >= g.pipeline_min_terms && !g.profiling) {
+    if (g.pts_ready) { BP_CUDA(cudaStreamWaitEvent(g.stream, g.pts_ready, 0)); g.pts_ready = nullptr; }
+    return msm_run_pipelined(points, point_idx, scalars, T, out_affine, out_xyzz);
+  }
   cudaStream_t st = g.stream;
   MsmShape sh = msm_shape(terms_per_msm, nmsm, g.force_c);
   g.last_c = sh.c;
@@ -44,6 +47,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   bool prof = g.profiling;
   if (prof) for (int i = 0; i < 7; i++) cudaEventRecord(g.ev[i], st), (void)0;
   if (T == 0) {   // all identities
+    if (g.pts_ready) { cudaStreamWaitEvent(st, g.pts_ready, 0); g.pts_ready = nullptr; }
     BP_CUDA(cudaMemsetAsync(out_affine ? (void*)out_affine : (void*)out_xyzz, 0, out_affine ? nmsm * sizeof(Affine) : nmsm * sizeof(XYZZ), st));
     if (out_affine && out_xyzz) BP_CUDA(cudaMemsetAsync(out_xyzz, 0, nmsm * sizeof(XYZZ), st));
     return 0;
@@ -72,7 +76,6 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(cursor, 0, (nb + 1) * sizeof(u32), st));
   if (prof) cudaEventRecord(g.ev[0], st);
-  k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
   k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count);
   if (prof) cudaEventRecord(g.ev[1], st);
   k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
@@ -81,6 +84,8 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   if (prof) cudaEventRecord(g.ev[2], st);
   k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, start, cursor, entries);
   if (prof) cudaEventRecord(g.ev[3], st);
+  if (g.pts_ready) { BP_CUDA(cudaStreamWaitEvent(st, g.pts_ready, 0)); g.pts_ready = nullptr; }   // points may still be uploading
+  k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
   BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));          // empty buckets = identity (ZZ = 0)
   BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));   // [0] = queue length, kept zero word for gs = 0 lives at big[big_cap + 1]
@@ -204,6 +209,19 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
   // the accumulate streams also rejoin (their last events precede pe_done through the dependency chain)
   if (g.profiling) { for (int i = 1; i <= 6; i++) cudaEventRecord(g.ev[i], st); }
   BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Host operands -> device: scalars first on the compute stream (the digit/sort stages only need them), points on a
+// second stream so that their (twice as large) upload overlaps those stages; msm_run waits for the points right
+// before the first kernel that reads them.  The pipelined/profiling paths simply wait up front.
+static int upload_operands(Affine* d_pts, const uint8_t* pts64, Fq* d_sc, const uint8_t* sc32, size_t n) {
+  BP_CUDA(cudaEventRecord(g.ev_copy_gate, g.stream));                     // earlier work may still read d_pts
+  BP_CUDA(cudaStreamWaitEvent(g.copy_stream, g.ev_copy_gate, 0));
+  BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.copy_stream));
+  BP_CUDA(cudaEventRecord(g.ev_pts, g.copy_stream));
+  g.pts_ready = g.ev_pts;
   return 0;
 }
 
@@ -348,6 +366,8 @@ int bp_init(int device) {
   for (int i = 0; i < 8; i++) BP_CUDA(cudaEventCreate(&g.ev[i]));
   BP_CUDA(cudaEventCreate(&g.ev_a)); BP_CUDA(cudaEventCreate(&g.ev_b));
   BP_CUDA(cudaEventCreate(&g.ev_k0)); BP_CUDA(cudaEventCreate(&g.ev_k1));
+  BP_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+  BP_CUDA(cudaEventCreateWithFlags(&g.ev_pts, cudaEventDisableTiming)); BP_CUDA(cudaEventCreateWithFlags(&g.ev_copy_gate, cudaEventDisableTiming));
   g.inited = true;
   return 0;
 }
@@ -410,8 +430,7 @@ int bp_msm(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64
   Affine* d_pts = (Affine*)g.ws_pts.ensure(n * sizeof(Affine));
   Fq* d_sc = (Fq*)g.ws_sc.ensure(n * sizeof(Fq));
   if (!d_pts || !d_sc) return fail("device allocation failed");
-  BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.stream));
-  BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
+  if (upload_operands(d_pts, pts64, d_sc, sc32, n)) return 1;
   return msm_to_host(d_pts, d_sc, n, out64);
 }
 

@@ -432,10 +432,7 @@ int bp_msm_sharded_host(const uint8_t* pts64, const uint8_t* sc32, size_t n, uin
   Fq* d_sc = (Fq*)g.ws_sc.ensure((n ? n : 1) * sizeof(Fq));
   Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
   if (!d_pts || !d_sc || !d_out) return fail("device allocation failed");
-  if (n) {
-    BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.stream));
-    BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
-  }
+  if (n && upload_operands(d_pts, pts64, d_sc, sc32, n)) return 1;
   if (msm_sharded_device(d_pts, d_sc, n, d_out)) return 1;
   BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));

@@ -36,6 +36,8 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8];
   cudaEvent_t ev_a, ev_b, ev_k0, ev_k1;
+  cudaStream_t copy_stream = nullptr;           // uploads of points overlap the scalar-only stages
+  cudaEvent_t ev_pts = nullptr, ev_copy_gate = nullptr, pts_ready = nullptr;
   bool profiling = false;
   int force_c = 0, last_c = 0;
   size_t last_nb = 0;
