@@ -203,6 +203,21 @@ def run_ours(args):
     lib.bp_host_free(ps)
     clocks = sampler.stop(t0, time.time())       # sampled from the start of the timed region through the e2e loop
 
+    # multi-GPU parity: every rank's own slice result (no NCCL) is gathered through the launcher's process group and
+    # summed with the CPU oracle's group law on rank 0; it must equal the point every rank got from the sharded call
+    sharded_ok = None
+    if dist is not None:
+        nat.check(lib.bp_msm_hh(hp, hs, n, out))
+        mine = out.raw
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        if rank == 0:
+            from oracle import ecc
+            tot = None
+            for pb in parts:
+                tot = ecc.point_add(tot, ecc.unpack_point(pb))
+            sharded_ok = ecc.pack_point(tot).hex() == result_hex
+
     line = {"metric": METRIC, "value": round(value, 3), "unit": "Mpts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (256-bit modular integer)", "data": "synthetic",
@@ -216,6 +231,8 @@ def run_ours(args):
     if rank == 0 and world == 1:
         line["cpu_baseline"], bit_exact = cpu_baseline(pts, sc, n, result_hex)
         line["bit_exact_vs_oracle"] = bit_exact
+    if sharded_ok is not None:
+        line["sharded_result_equals_sum_of_slices"] = sharded_ok
     if not args.no_verify:
         try:
             line["verify"] = bench_verify(args, nat, dist, rank, world)
