@@ -141,6 +141,10 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
   g.last_nb = nb;
   if (T >= (1u << 30)) return fail("msm: too many terms");
   if (g.ensure_pipeline((int)W)) return 1;
+  if (!g.pipe_attr_set && g.pipe_acc_smem) {   // optional cap of resident accumulate blocks per SM
+    BP_CUDA(cudaFuncSetAttribute(k_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pipe_acc_smem));
+    g.pipe_attr_set = true;
+  }
   int* digits = (int*)g.ws_digits.ensure((size_t)sh.W * 2 * T * sizeof(int));
   uint2* entries = (uint2*)g.ws_entries.ensure((size_t)sh.W * 2 * T * sizeof(uint2));
   Affine* phi = (Affine*)g.ws_phi.ensure((size_t)T * sizeof(Affine));
@@ -187,17 +191,17 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
     const u32* gs = start + (size_t)w * sh.H;
     XYZZ* part_w = part + 2 * (size_t)w * wchunks;
     u32* big_w = big + (size_t)w * (big_cap + 2);
-    k_accumulate<<<(unsigned)((wchunks + 127) / 128), 128, 0, sa>>>(points, point_idx, phi, start, entries, gs, gs + sh.H, sh.chunk, buckets, part_w);
+    k_accumulate<<<(unsigned)((wchunks + 127) / 128), 128, g.pipe_acc_smem, sa>>>(points, point_idx, phi, start, entries, gs, gs + sh.H, sh.chunk, buckets, part_w);
     BP_CUDA(cudaEventRecord(g.pe_acc[w], sa));
     BP_CUDA(cudaStreamWaitEvent(sr, g.pe_acc[w], 0));
     // everything after the accumulation of window w is a latency chain on few SMs: it lives on the window's own stream
-    k_fixup<<<(unsigned)((sh.H + 127) / 128), 128, 0, sr>>>(start, (size_t)w * sh.H, sh.H, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
-    k_fixup_big<<<32, 256, 0, sr>>>(start, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
+    k_fixup<<<(unsigned)((sh.H + 63) / 64), 64, 0, sr>>>(start, (size_t)w * sh.H, sh.H, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
+    k_fixup_big<<<32, 64, 0, sr>>>(start, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
     const XYZZ* bw = buckets + (size_t)w * sh.H;
-    k_reduce_seg<<<(unsigned)((4 * (size_t)sh.nseg + 127) / 128), 128, 0, sr>>>(bw, sh, 1, seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg);
-    k_reduce_grp<<<(unsigned)((4 * (size_t)ngrp + 127) / 128), 128, 0, sr>>>(seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg, sh, 1, (u32)w, G, lgS, lgG,
+    k_reduce_seg<<<(unsigned)((4 * (size_t)sh.nseg + 31) / 32), 32, 0, sr>>>(bw, sh, 1, seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg);
+    k_reduce_grp<<<(unsigned)((4 * (size_t)ngrp + 31) / 32), 32, 0, sr>>>(seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg, sh, 1, (u32)w, G, lgS, lgG,
                                                                               ubits, grpsum + (size_t)w * ngrp);
-    if (ngrp > 1) k_window_sum<<<1, 256, 0, sr>>>(grpsum + (size_t)w * ngrp, ngrp, winsum + w);
+    if (ngrp > 1) k_window_sum<<<1, 64, 0, sr>>>(grpsum + (size_t)w * ngrp, ngrp, winsum + w);
     else BP_CUDA(cudaMemcpyAsync(winsum + w, grpsum + (size_t)w * ngrp, sizeof(XYZZ), cudaMemcpyDeviceToDevice, sr));
     BP_CUDA(cudaEventRecord(g.pe_red[w], sr));
     BP_CUDA(cudaStreamWaitEvent(shh, g.pe_red[w], 0));

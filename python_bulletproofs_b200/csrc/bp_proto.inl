@@ -16,7 +16,7 @@ void nccl_shutdown() { if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; 
 
 struct ChallengeForms { Fq x, xinv, xm, xim; };
 static ChallengeForms challenge_forms(const Fq& x) {
-  ChallengeForms c; c.x = x; c.xinv = fq_inv(x); c.xm = fq_to_mont(x); c.xim = fq_to_mont(c.xinv);
+  ChallengeForms c; c.x = x; c.xinv = fq_inv_host(x); c.xm = fq_to_mont(x); c.xim = fq_to_mont(c.xinv);
   return c;
 }
 

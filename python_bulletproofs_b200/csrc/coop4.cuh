@@ -16,6 +16,9 @@ namespace bp {
 
 #define BP_FULL_MASK 0xFFFFFFFFu
 
+// (Out-of-line variants of these operations were measured: the quad kernels got ~30 % slower from the call/spill
+// overhead, so they stay inlined; the thread-per-unit kernels of the batch path do use out-of-line point operations,
+// ec.cuh, because there instruction fetch was the top stall reason.)
 BP_DI Fp shfl_fp(const Fp& m, int src_lane) {
   Fp r;
 #pragma unroll

@@ -51,6 +51,8 @@ struct Ctx {
   cudaStream_t ps_acc[2] = {nullptr, nullptr}, ps_red[20] = {nullptr}, ps_hor = nullptr;
   cudaEvent_t pe_prep = nullptr, pe_done = nullptr, pe_acc[20], pe_red[20];
   int pipe_windows = 0;
+  size_t pipe_acc_smem = 0;             // >0 caps the accumulation at fewer resident blocks per SM (experiment: slower)
+  bool pipe_attr_set = false;
   int ensure_pipeline(int W) {
     if (W > 20) return fail("pipeline: too many windows");
     if (!ps_hor) {

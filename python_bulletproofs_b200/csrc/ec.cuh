@@ -108,6 +108,11 @@ BP_DI void xyzz_add(XYZZ& a, const XYZZ& b) {
   a.ZZ = fp_mul(fp_mul(a.ZZ, b.ZZ), PP);
   a.ZZZ = fp_mul(fp_mul(a.ZZZ, b.ZZZ), PPP);
 }
+// out-of-line forms for kernels that are not throughput bound (keeps their code inside the instruction caches)
+__device__ __noinline__ void xyzz_add_ni(XYZZ& a, const XYZZ& b) { xyzz_add(a, b); }
+__device__ __noinline__ void xyzz_madd_ni(XYZZ& a, const Affine& p) { xyzz_madd(a, p); }
+__device__ __noinline__ XYZZ xyzz_dbl_ni(const XYZZ& p) { return xyzz_dbl(p); }
+
 // canonical affine output (the parity surface): x = X*ZZ^-1, y = Y*ZZZ^-1, one inversion:
 // ZZ^-1 = ZZ^2 * ZZZ^-2 because ZZ^3 = ZZZ^2.
 BP_DI Affine xyzz_to_affine(const XYZZ& p) {

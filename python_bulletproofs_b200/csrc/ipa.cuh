@@ -36,8 +36,8 @@ BP_DI XYZZ scalar_mul_affine(const Affine& p, const Fq& k) {
   XYZZ acc = xyzz_identity();
   if (affine_is_identity(p)) return acc;
   for (int i = 255; i >= 0; i--) {
-    acc = xyzz_dbl(acc);
-    if ((k.v[i >> 5] >> (i & 31)) & 1) xyzz_madd(acc, p);
+    acc = xyzz_dbl_ni(acc);
+    if ((k.v[i >> 5] >> (i & 31)) & 1) xyzz_madd_ni(acc, p);
   }
   return acc;
 }
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(64) k_scalar_mul(const Affine* __restrict__ pt
 __global__ void k_xyzz_sum(const XYZZ* __restrict__ in, u32 count, Affine* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   XYZZ acc = xyzz_identity();
-  for (u32 i = 0; i < count; i++) { XYZZ v = ld_xyzz(in + i); xyzz_add(acc, v); }
+  for (u32 i = 0; i < count; i++) { XYZZ v = ld_xyzz(in + i); xyzz_add_ni(acc, v); }
   st_affine(out, xyzz_to_affine(acc));
 }
 
@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(64) k_fold_points(const Affine* __restrict__ s
   Fq klo = is_h ? s : s_inv, khi = is_h ? s_inv : s;
   XYZZ acc = xyzz_identity();
   for (int b = 255; b >= 0; b--) {
-    acc = xyzz_dbl(acc);
-    if ((klo.v[b >> 5] >> (b & 31)) & 1) xyzz_madd(acc, lo);
-    if ((khi.v[b >> 5] >> (b & 31)) & 1) xyzz_madd(acc, hi);
+    acc = xyzz_dbl_ni(acc);
+    if ((klo.v[b >> 5] >> (b & 31)) & 1) xyzz_madd_ni(acc, lo);
+    if ((khi.v[b >> 5] >> (b & 31)) & 1) xyzz_madd_ni(acc, hi);
   }
   st_affine(dst + 1 + (is_h ? k : 0) + j, xyzz_to_affine(acc));
 }

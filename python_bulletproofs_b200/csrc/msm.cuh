@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_st
   if (c0 == c1) return;
   if (c1 - c0 >= BP_FIXUP_SERIAL_MAX) { big_list[atomicAdd(big_count, 1u)] = (u32)b; return; }
   XYZZ acc = ld_xyzz(bucket_piece(part, s, c0, c0, CL));
-  for (u32 c = c0 + 1; c <= c1; c++) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add(acc, v); }
+  for (u32 c = c0 + 1; c <= c1; c++) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add_ni(acc, v); }
   st_xyzz(buckets + b, acc);
 }
 
@@ -313,11 +313,11 @@ __global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucke
     u32 s = __ldg(bucket_start + b) - gs, e = __ldg(bucket_start + b + 1) - gs;
     u32 c0 = s / CL, c1 = (e - 1) / CL;
     XYZZ acc = xyzz_identity();
-    for (u32 c = c0 + threadIdx.x; c <= c1; c += 256) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add(acc, v); }
+    for (u32 c = c0 + threadIdx.x; c <= c1; c += blockDim.x) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add_ni(acc, v); }
     sm[threadIdx.x] = acc;
     __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-      if (threadIdx.x < off) { XYZZ v = sm[threadIdx.x + off]; xyzz_add(acc, v); sm[threadIdx.x] = acc; }
+    for (int off = (int)blockDim.x >> 1; off > 0; off >>= 1) {
+      if (threadIdx.x < off) { XYZZ v = sm[threadIdx.x + off]; xyzz_add_ni(acc, v); sm[threadIdx.x] = acc; }
       __syncthreads();
     }
     if (threadIdx.x == 0) st_xyzz(buckets + b, acc);
@@ -386,16 +386,16 @@ __global__ void __launch_bounds__(256) k_window_sum(const XYZZ* __restrict__ seg
   __shared__ XYZZ sm[64];
   const size_t mw = blockIdx.x;
   const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
-  const u32 q = threadIdx.x >> 2;
+  const u32 q = threadIdx.x >> 2, nq = blockDim.x >> 2;      // nq quads, a power of two <= 64
   XYZZ acc = xyzz_identity();
-  for (u32 i0 = 0; i0 < nseg; i0 += 64) {             // uniform trip count; out-of-range quads add the identity
+  for (u32 i0 = 0; i0 < nseg; i0 += nq) {             // uniform trip count; out-of-range quads add the identity
     u32 i = i0 + q;
     XYZZ v = i < nseg ? ld_xyzz(segsum + mw * nseg + i) : xyzz_identity();
     acc = coop_add(acc, v, role, base);
   }
   if (role == 0) sm[q] = acc;
   __syncthreads();
-  for (u32 off = 32; off > 0; off >>= 1) {
+  for (u32 off = nq >> 1; off > 0; off >>= 1) {
     XYZZ v = (q < off) ? sm[q + off] : xyzz_identity();
     acc = coop_add(acc, v, role, base);
     __syncthreads();
@@ -415,13 +415,13 @@ __global__ void __launch_bounds__(128) k_reduce_unit_plain(const XYZZ* __restric
   XYZZ run = xyzz_identity(), sum = xyzz_identity();
   for (int i = (int)sh.H - 1; i >= 0; i--) {
     XYZZ b = ld_xyzz(B + i);
-    xyzz_add(run, b);
-    xyzz_add(sum, run);
+    xyzz_add_ni(run, b);
+    xyzz_add_ni(sum, run);
   }
   if (sh.dbl && (int)(id % sh.U) == sh.U - 1) {        // second unit of the top window: weights H + i + 1
     XYZZ t = run;
-    for (int d = 0; d < sh.c - 1; d++) t = xyzz_dbl(t);
-    xyzz_add(sum, t);
+    for (int d = 0; d < sh.c - 1; d++) t = xyzz_dbl_ni(t);
+    xyzz_add_ni(sum, t);
   }
   st_xyzz(unitsum + id, sum);
 }
@@ -431,11 +431,11 @@ __global__ void __launch_bounds__(128) k_combine_plain(const XYZZ* __restrict__ 
   if (m >= nmsm) return;
   const XYZZ* ws = winsum + m * sh.U;
   XYZZ acc = ld_xyzz(ws + sh.U - 1);
-  if (sh.dbl) { XYZZ v = ld_xyzz(ws + sh.U - 2); xyzz_add(acc, v); }
+  if (sh.dbl) { XYZZ v = ld_xyzz(ws + sh.U - 2); xyzz_add_ni(acc, v); }
   for (int w = sh.W - 2; w >= 0; w--) {
-    for (int d = 0; d < sh.c; d++) acc = xyzz_dbl(acc);
+    for (int d = 0; d < sh.c; d++) acc = xyzz_dbl_ni(acc);
     XYZZ v = ld_xyzz(ws + w);
-    xyzz_add(acc, v);
+    xyzz_add_ni(acc, v);
   }
   if (out_xyzz) st_xyzz(out_xyzz + m, acc);
   if (out) st_affine(out + m, xyzz_to_affine(acc));
