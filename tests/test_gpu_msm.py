@@ -155,3 +155,35 @@ def test_pippenger_dropin_api():
     assert (P[0] + P[1]) == Point(*ecc.py_add(pts[0], pts[1]), secp256k1)
     assert (5 * P[0]) == (P[0] * 5) == Point(*ecc.py_mul(pts[0], 5), secp256k1)
     assert P[0] + (-P[0]) == Point.IDENTITY_ELEMENT
+
+
+def test_device_resident_handles_and_pipelined_path():
+    """DevicePoints / DeviceScalars through Pippenger.multiexp, and the stream-pipelined single-MSM path
+    (off by default) must return the same point as the sequential path."""
+    from python_bulletproofs_b200.pippenger import PipSECP256k1
+    from python_bulletproofs_b200.device import DevicePoints, DeviceScalars
+    from python_bulletproofs_b200 import Point, secp256k1
+    n = 1 << 15
+    pts = fast_points(n, 31)
+    rng = random.Random(32)
+    ks = [rng.getrandbits(256) for _ in range(n)]
+    want = ecc.msm(pts, ks, "bucket", ecc.max_threads())
+    dp = DevicePoints(raw=ecc.pack_points(pts))
+    ds = DeviceScalars(ks)
+    r = PipSECP256k1.multiexp(dp, ds)
+    assert (r.x, r.y) == want
+    r = PipSECP256k1.multiexp(dp, ks)
+    assert (r.x, r.y) == want
+    lib = nat.load()
+    try:
+        nat.check(lib.bp_msm_set_pipeline_min(1))
+        r = PipSECP256k1.multiexp(dp, ds)
+        assert (r.x, r.y) == want
+        for c in (8, 13, 16):
+            nat.check(lib.bp_msm_set_window(c))
+            r = PipSECP256k1.multiexp(dp, ds)
+            assert (r.x, r.y) == want, c
+    finally:
+        lib.bp_msm_set_window(0)
+        lib.bp_msm_set_pipeline_min(0)
+    dp.free(); ds.free()

@@ -230,3 +230,24 @@ def test_batch_verify_decisions(n, count):
     # the class API agrees proof by proof
     for i in (0, 1, 4):
         assert quiet(RangeVerifier(Vs[i], g, h, gs, hs, u, proofs[i]).verify) is want[i]
+
+
+def test_h_scale_equals_materialised_generators():
+    """bp_ipa_prove_hs / bp_ipa_verify_eq_hs with (hs, y^-i) must give the same proof and decisions as the reference's
+    materialised hsp list (rangeproof_prover.py:77)."""
+    N = 32
+    g, h, u, a, b = ipa_inputs(N, ["hs0", "hs1", "hs2", "hs3", "hs4"])
+    y = po.mod_hash(b"some-y")
+    yinv = [pow(y, -i, Q) for i in range(N)]
+    hsp = ecc.scalar_mul_batch(h, yinv)
+    g_, h_, hsp_, u_ = [P_(t) for t in g], [P_(t) for t in h], [P_(t) for t in hsp], P_(u)
+    am, bm = [M_(v) for v in a], [M_(v) for v in b]
+    c = inner_product(am, bm)
+    P2 = vector_commitment(g_, hsp_, am, bm) + c * u_
+    ref = FastNIProver2(g_, hsp_, u_, P2, am, bm, secp256k1).prove()
+    got = FastNIProver2(g_, h_, u_, P2, am, bm, secp256k1, _h_scale=yinv).prove()
+    assert p2_json(got) == p2_json(ref)
+    assert p2_json(ref) == po.proof2_to_json(po.ipa_prove2(g, hsp, u, a, b))
+    assert quiet(Verifier2(g_, h_, u_, P2, got, _h_scale=yinv).verify)
+    assert quiet(Verifier2(g_, hsp_, u_, P2, got).verify)
+    assert not quiet(Verifier2(g_, h_, u_, P2, got).verify)          # wrong generators without the scale
