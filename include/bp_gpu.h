@@ -92,6 +92,10 @@ int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64],
                  size_t n, const uint8_t* transcript, size_t transcript_len, uint8_t* Ls64, uint8_t* Rs64, uint8_t* xs32,
                  uint8_t a_out32[32], uint8_t b_out32[32], uint8_t* transcript_out, size_t tout_cap, size_t* tout_len);
 
+/* From the second round on, each round's device work (fold with the previous challenge, L/R term construction, batched
+ * MSM, copy-out of L and R) is one CUDA-graph launch; bp_ipa_set_graphs(0) switches to plain stream launches. */
+int bp_ipa_set_graphs(int on);
+
 /* Same, with the h generators given as (h, hscale): the effective generators are hscale_i * h_i, which are never
  * materialised (hscale32 = NULL means all ones).  The range-proof prover passes hs with hscale_i = y^-i instead of the
  * list hsp of src/rangeproofs/rangeproof_prover.py:77. */

@@ -32,6 +32,8 @@ static int fold_step(const Affine* P, Affine* P2, const Fq* a, const Fq* b, Fq* 
 
 extern "C" {
 
+int bp_ipa_set_graphs(int on) { g.use_graphs = on != 0; return 0; }
+
 int bp_sha256(const uint8_t* msg, size_t len, uint8_t out32[32]) {
   Sha256 s; s.update(msg, len); s.final(out32);
   return 0;
@@ -105,10 +107,14 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   // MSM terms, but the folds need reduced inputs, so reduce once here.
   k_reduce_scalars<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(aA, (u32)n);
   k_reduce_scalars<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(bA, (u32)n);
-  Fq *a = aA, *b = bA, *a2 = aB, *b2 = bB;
+  Fq *a = aA, *b = bA;
   // coefficient vectors of the folded generators over the original ones (see k_build_lr_sv); P = PA is never rewritten
   Fq* cg = (Fq*)g.ws_h.ensure(2 * n * sizeof(Fq));
-  if (!cg) return fail("device allocation failed");
+  IpaRound* d_rp = (IpaRound*)g.ws_ipa_rp.ensure(sizeof(IpaRound));
+  uint8_t* pin = g.pinned_bytes(512);
+  if (!cg || !d_rp || !pin) return fail("device allocation failed");
+  IpaRound* h_rp = (IpaRound*)pin;                 // pinned mirror of the round parameters
+  uint8_t* h_lr = pin + 256;                       // pinned landing zone of L, R
   Fq* ch = cg + n;
   k_fill_one_mont<<<(unsigned)((2 * n + 127) / 128), 128, 0, g.stream>>>(cg, (u32)(2 * n));
   if (hscale32) {   // effective generators h_i' = hscale_i * h_i (e.g. y^-i, rangeproof_prover.py:77): start ch there
@@ -120,27 +126,54 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   const u32 n1 = (u32)n + 1;
   u32 h_off[3] = {0, n1, 2 * n1};
   if (n > 1) BP_CUDA(cudaMemcpyAsync(d_off, h_off, sizeof h_off, cudaMemcpyHostToDevice, g.stream));
-  for (size_t m = n; m > 1; m >>= 1, round++) {
-    u32 k = (u32)(m / 2);
-    k_build_lr_sv<<<1, 256, 0, g.stream>>>(a, b, cg, ch, (u32)n, (u32)m, tsc, tidx);
+  // One round on the stream: parameters up, fold with the previous challenge, L/R terms, batched MSM, L and R down.
+  auto enqueue_round = [&]() -> int {
+    BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
+    k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
+    k_build_lr_sv<<<1, 256, 0, g.stream>>>(a, b, cg, ch, (u32)n, &d_rp->m, tsc, tidx);
     if (msm_run(PA, tidx, tsc, 2 * n1, d_off, 2, n1, d_lr, nullptr)) return 1;
-    uint8_t lr[128];
-    BP_CUDA(cudaMemcpyAsync(lr, d_lr, 128, cudaMemcpyDeviceToHost, g.stream));
+    BP_CUDA(cudaMemcpyAsync(h_lr, d_lr, 128, cudaMemcpyDeviceToHost, g.stream));
+    return 0;
+  };
+  memset(h_rp, 0, sizeof(IpaRound));
+  cudaGraphExec_t gexec = nullptr;
+  for (size_t m = n; m > 1; m >>= 1, round++) {
+    h_rp->m = (u32)m;
+    // Round 0 runs eagerly (it also sizes every workspace); from round 1 on the same device work is ONE graph launch.
+    // The graph is captured once per n and reused across proofs while the workspaces keep their addresses.
+    if (round == 0 || !g.use_graphs) {
+      if (enqueue_round()) return 1;
+    } else {
+      if (!gexec) gexec = g.ipa_graph_lookup(n);
+      if (!gexec) {
+        cudaGraph_t graph = nullptr;
+        BP_CUDA(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed));
+        int rc = enqueue_round();
+        cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+        if (rc || ce != cudaSuccess || !graph) { cudaGetLastError(); return fail("CUDA graph capture of the IPA round failed"); }
+        ce = cudaGraphInstantiate(&gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { cudaGetLastError(); return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+        g.ipa_graph_store(n, gexec);
+      }
+      BP_CUDA(cudaGraphLaunch(gexec, g.stream));
+    }
     BP_CUDA(cudaStreamSynchronize(g.stream));
-    memcpy(Ls64 + 64 * round, lr, 64);
-    memcpy(Rs64 + 64 * round, lr + 64, 64);
+    memcpy(Ls64 + 64 * round, h_lr, 64);
+    memcpy(Rs64 + 64 * round, h_lr + 64, 64);
     // transcript.add_list_points([L, R]); x = get_modp(q); add_number(x)      inner_product_prover.py:102-106
-    digest += point_to_b64(lr); digest += '&';
-    digest += point_to_b64(lr + 64); digest += '&';
+    digest += point_to_b64(h_lr); digest += '&';
+    digest += point_to_b64(h_lr + 64); digest += '&';
     Fq x = rh.challenge((const uint8_t*)digest.data(), digest.size());
     fq_to_le(xs32 + 32 * round, x);
     digest += fq_to_decimal(x); digest += '&';
     ChallengeForms c = challenge_forms(x);
-    // fold a, b (inner_product_prover.py:109-110); the generator fold (:107-108) is carried by cg, ch
-    k_fold_scalars<<<(k + 127) / 128, 128, 0, g.stream>>>(a, b, k, c.xm, c.xim, a2, b2);
-    k_update_coef<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(cg, ch, (u32)n, (u32)m, c.xm, c.xim);
-    Fq* t1 = a; a = a2; a2 = t1;
-    Fq* t2 = b; b = b2; b2 = t2;
+    h_rp->fold = 1; h_rp->xm = c.xm; h_rp->xim = c.xim;      // applied at the start of the next round (or below)
+  }
+  if (n > 1) {   // last fold: a, b of length 1   (inner_product_prover.py:109-110)
+    h_rp->m = 1;
+    BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
+    k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
   }
   BP_CUDA(cudaMemcpyAsync(a_out32, a, 32, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaMemcpyAsync(b_out32, b, 32, cudaMemcpyDeviceToHost, g.stream));

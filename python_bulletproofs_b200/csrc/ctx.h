@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstddef>
+#include <map>
 #include <string>
 
 namespace bp {
@@ -15,11 +16,14 @@ void nccl_shutdown();
     if (e__ != cudaSuccess) { cudaGetLastError(); return ::bp::fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } \
   } while (0)
 
+inline unsigned long long& alloc_generation() { static unsigned long long gen = 0; return gen; }   // bumps when any workspace moves
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   void* ensure(size_t bytes) {
     if (bytes <= cap && p) return p;
+    alloc_generation()++;
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
     size_t want = bytes + bytes / 4 + 256;
     if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; }
@@ -87,6 +91,27 @@ struct Ctx {
     for (int i = 0; i < 2; i++)
       if (!stage_ev[i] && cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming) != cudaSuccess) return fail("event creation failed");
     return 0;
+  }
+  // IPA round graphs: one instantiated graph per vector length, valid while no workspace has been reallocated
+  bool use_graphs = true;
+  DevBuf ws_ipa_rp;
+  struct GraphRec { cudaGraphExec_t exec; unsigned long long gen; };
+  std::map<size_t, GraphRec> ipa_graphs;
+  cudaGraphExec_t ipa_graph_lookup(size_t n) {
+    auto it = ipa_graphs.find(n);
+    if (it == ipa_graphs.end()) return nullptr;
+    if (it->second.gen != alloc_generation()) { cudaGraphExecDestroy(it->second.exec); ipa_graphs.erase(it); return nullptr; }
+    return it->second.exec;
+  }
+  void ipa_graph_store(size_t n, cudaGraphExec_t e) { ipa_graphs[n] = GraphRec{e, alloc_generation()}; }
+  unsigned char* pin_bytes_p = nullptr; size_t pin_bytes_cap = 0;
+  unsigned char* pinned_bytes(size_t bytes) {
+    if (bytes <= pin_bytes_cap) return pin_bytes_p;
+    if (pin_bytes_p) cudaFreeHost(pin_bytes_p);
+    pin_bytes_p = nullptr; pin_bytes_cap = 0;
+    if (cudaHostAlloc((void**)&pin_bytes_p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    pin_bytes_cap = bytes;
+    return pin_bytes_p;
   }
   unsigned* h_pin = nullptr;
   unsigned* pinned_u32() { if (!h_pin && cudaHostAlloc((void**)&h_pin, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h_pin = nullptr; } return h_pin; }

@@ -136,8 +136,10 @@ __global__ void __launch_bounds__(256) k_build_lr(const Fq* __restrict__ a, cons
 // multiplication per generator.  cg, ch are kept in Montgomery form; a, b in standard form.
 // One block of 256 threads.  Points live in [u | g (n) | h (n)].
 __global__ void __launch_bounds__(256) k_build_lr_sv(const Fq* __restrict__ a, const Fq* __restrict__ b, const Fq* __restrict__ cg,
-                                                     const Fq* __restrict__ ch, u32 n, u32 m, Fq* __restrict__ tsc, u32* __restrict__ tidx) {
+                                                     const Fq* __restrict__ ch, u32 n, const u32* __restrict__ m_ptr, Fq* __restrict__ tsc,
+                                                     u32* __restrict__ tidx) {
   __shared__ Fq sl[256], sr[256];
+  const u32 m = *m_ptr;                                         // IpaRound::m (device resident, set per round)
   const u32 k = m >> 1, n1 = n + 1;
   Fq accl = fq_zero(), accr = fq_zero();
   for (u32 i = threadIdx.x; i < k; i += 256) {                 // c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>
@@ -179,6 +181,31 @@ __global__ void __launch_bounds__(128) k_update_coef(Fq* __restrict__ cg, Fq* __
   const bool hi = (t % m) >= (m >> 1);
   st_fq(cg + t, fq_mont(ld_fq(cg + t), hi ? xm : xim));
   st_fq(ch + t, fq_mont(ld_fq(ch + t), hi ? xim : xm));
+}
+// ---- graph-friendly forms: per-round values come from a device-resident parameter block, so that ONE captured CUDA
+// graph (fold with the previous challenge -> build L/R terms -> batched MSM -> copy L, R out) is replayed every round.
+struct IpaRound {
+  u32 m;        // vector length of this round (after folding with the previous challenge)
+  u32 fold;     // 1: first apply the previous round's challenge (xm, xim); 0: first round
+  u32 pad0, pad1;
+  Fq xm, xim;   // Montgomery forms of the previous challenge and its inverse
+};
+// a'[i] = x*a[i] + xinv*a[m+i], b'[i] = xinv*b[i] + x*b[m+i] in place (inner_product_prover.py:109-110) and the
+// coefficient update of k_update_coef for the generator fold (:107-108); m = new length, 2m = old length.
+__global__ void __launch_bounds__(128) k_round_fold(Fq* __restrict__ a, Fq* __restrict__ b, Fq* __restrict__ cg, Fq* __restrict__ ch, u32 n,
+                                                    const IpaRound* __restrict__ rp) {
+  if (!rp->fold) return;
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x, m = rp->m;
+  if (t >= n) return;
+  const Fq xm = ld_fq(&rp->xm), xim = ld_fq(&rp->xim);
+  const bool hi = (t % (2 * m)) >= m;
+  st_fq(cg + t, fq_mont(ld_fq(cg + t), hi ? xm : xim));
+  st_fq(ch + t, fq_mont(ld_fq(ch + t), hi ? xim : xm));
+  if (t < m) {
+    Fq alo = ld_fq(a + t), ahi = ld_fq(a + m + t), blo = ld_fq(b + t), bhi = ld_fq(b + m + t);
+    st_fq(a + t, fq_add(fq_mont(alo, xm), fq_mont(ahi, xim)));
+    st_fq(b + t, fq_add(fq_mont(blo, xim), fq_mont(bhi, xm)));
+  }
 }
 __global__ void __launch_bounds__(128) k_to_mont(Fq* __restrict__ v, u32 n) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
