@@ -97,7 +97,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
   if (prof) cudaEventRecord(g.ev[4], st);
   size_t nsegs = nmw * sh.nseg;
-  const bool plain_tails = nmsm >= 2048 && sh.H <= 64;     // big batch of small MSMs: throughput forms
+  const bool plain_tails = nmsm >= 2048 && sh.H <= 512;     // big batch of small MSMs: throughput forms
   const XYZZ* ws;
   if (plain_tails) {
     k_reduce_unit_plain<<<(unsigned)((nmw + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);
