@@ -52,7 +52,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     if (out_affine && out_xyzz) BP_CUDA(cudaMemsetAsync(out_xyzz, 0, nmsm * sizeof(XYZZ), st));
     return 0;
   }
-  if (T >= (1u << 30)) return fail("msm: too many terms");
+  if (T >= (1u << 30) || (unsigned long long)sh.W * 2ull * T >= 0xFFFFFFF0ull) return fail("msm: too many terms for 32-bit entry indices");
   int* digits = (int*)g.ws_digits.ensure((size_t)sh.W * 2 * T * sizeof(int));
   uint2* entries = (uint2*)g.ws_entries.ensure((size_t)sh.W * 2 * T * sizeof(uint2));
   Affine* phi = (Affine*)g.ws_phi.ensure((size_t)T * sizeof(Affine));

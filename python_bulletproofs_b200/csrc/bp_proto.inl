@@ -365,6 +365,8 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   BP_CUDA(cudaMemcpyAsync(table + 2 * n, g64, 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n + 1, h64, 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n + 2, u64_, 64, cudaMemcpyHostToDevice, g.stream));
+  k_sum_points<<<1, 128, 0, g.stream>>>(table, (u32)n, table + 2 * n + 3);          // Gsum
+  k_sum_points<<<1, 128, 0, g.stream>>>(table + n, (u32)n, table + 2 * n + 4);      // Hsum
   const u32 bd = n < 32 ? 32 : (u32)n;
   const size_t smem = (2 * L + 1 + bd) * sizeof(Fq);
   int chunk_no = 0;

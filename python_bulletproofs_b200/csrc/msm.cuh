@@ -67,7 +67,10 @@ inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
   s.dbl = (BP_GLV_BITS % s.c) == 0 ? 1 : 0;
   s.U = s.W + s.dbl;
   s.H = 1u << (s.c - 1);
-  s.chunk = (2.0 * n * s.W * (double)nmsm) < 262144.0 ? 8 : BP_CHUNK;
+  {   // entries per accumulation thread: enough threads for ~2 waves of the 148 x 512 resident slots, at most BP_CHUNK
+    double entries = 2.0 * n * s.W * (double)nmsm;
+    s.chunk = entries <= 1300000.0 ? 8 : (entries <= 2600000.0 ? 16 : BP_CHUNK);
+  }
   s.S = s.H < 8 ? s.H : 8;
   s.nseg = s.H / s.S;
   return s;

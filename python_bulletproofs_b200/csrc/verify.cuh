@@ -7,6 +7,8 @@
 // its own exact check (no random linear combination), rewritten as "MSM == identity":
 //   E1  t_hat*g + taux*h == z^2*V + delta*g + x*T1 + x^2*T2                 rangeproof_verifier.py:73-76
 //   E2  P_new == A + x*S + sum(-z*gs_i) + sum((z*y^i + z^2*2^i)*hsp_i) - mu*h + (x1*t_hat)*u
+//       evaluated as  A + x*S - z*Gsum + z*Hsum + sum(z^2*2^i*y^-i * hs_i) - mu*h + (x1*t_hat)*u - P_new == O  with the
+//       per-generator-set constants Gsum = sum gs_i, Hsum = sum hs_i (the n equal scalars -z collapse into one term)
 //                                                              rangeproof_verifier.py:78-84,88-97; inner_product_verifier.py:51
 //   E3  u_new == x1*u                                                         inner_product_verifier.py:52
 //   E4  MSM(gs||hsp||u_new ; a*s || b*s^-1 || a*b) == P_new + MSM(Ls||Rs ; x_j^2 || x_j^-2)   :134-145
@@ -26,12 +28,12 @@ enum { RP_V = 0, RP_A, RP_S, RP_T1, RP_T2, RP_UNEW, RP_PNEW, RP_LS };           
 struct RpLayout {
   u32 n, L;            // vector length (power of two), log2 n
   u32 nsc, npt;        // scalars / points per proof
-  u32 tpp;             // terms per proof = 4n + 14 + 2L
-  u32 fixed;           // fixed table size = 2n + 3  : [gs | hs | g | h | u]
+  u32 tpp;             // terms per proof = 3n + 16 + 2L
+  u32 fixed;           // fixed table size = 2n + 5  : [gs | hs | g | h | u | sum(gs) | sum(hs)]
 };
 inline RpLayout rp_layout(u32 n) {
   RpLayout l; l.n = n; l.L = 0; while ((1u << l.L) < n) l.L++;
-  l.nsc = RS_XS + l.L; l.npt = RP_LS + 2 * l.L; l.tpp = 4 * n + 14 + 2 * l.L; l.fixed = 2 * n + 3;
+  l.nsc = RS_XS + l.L; l.npt = RP_LS + 2 * l.L; l.tpp = 3 * n + 16 + 2 * l.L; l.fixed = 2 * n + 5;
   return l;
 }
 
@@ -97,15 +99,14 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
   const Fq sum_y = red[0];
   const size_t tb = (size_t)p * lay.tpp;                 // term base of this proof
   const u32 pb = lay.fixed + p * lay.npt;                // point base of this proof
-  const u32 iG = 2 * n, iH = 2 * n + 1, iU = 2 * n + 2;
-  const u32 o1 = 0, o2 = 5, o3 = 5 + 2 * n + 5, o4 = o3 + 2;
+  const u32 iG = 2 * n, iH = 2 * n + 1, iU = 2 * n + 2, iGsum = 2 * n + 3, iHsum = 2 * n + 4;
+  const u32 o1 = 0, o2 = 5, o3 = 5 + n + 7, o4 = o3 + 2;
   if (i < n) {
     // ---- E2, generator terms
     Fq two_i = fq_zero(); if (i < 256) two_i.v[i >> 5] = 1u << (i & 31);   // 2^i, standard form (host enforces n <= 128)
     two_i = fq_reduce(two_i);
-    Fq hs_sc = fq_add(z, fq_from_mont(fq_mont(fq_mont(z2m, fq_to_mont(two_i)), yii)));   // z + z^2 * 2^i * y^-i
-    st_fq(tsc + tb + o2 + 2 + i, fq_neg(z));          tidx[tb + o2 + 2 + i] = i;             // gs_i : -z
-    st_fq(tsc + tb + o2 + 2 + n + i, hs_sc);          tidx[tb + o2 + 2 + n + i] = n + i;     // hs_i
+    Fq hs_sc = fq_from_mont(fq_mont(fq_mont(z2m, fq_to_mont(two_i)), yii));              // z^2 * 2^i * y^-i  (z*hs_i is in Hsum)
+    st_fq(tsc + tb + o2 + 2 + i, hs_sc);              tidx[tb + o2 + 2 + i] = n + i;         // hs_i
     // ---- E4, generator terms: s_i = prod_j (bit_j(i) ? x_j : x_j^-1), bit j counted from the MSB
     Fq s = R1, sinv = R1;
     for (u32 j = 0; j < L; j++) {
@@ -140,9 +141,11 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
     // E2 non-generator terms
     st_fq(tsc + tb + o2 + 0, one);                  tidx[tb + o2 + 0] = pb + RP_A;
     st_fq(tsc + tb + o2 + 1, x);                    tidx[tb + o2 + 1] = pb + RP_S;
-    st_fq(tsc + tb + o2 + 2 + 2 * n + 0, fq_neg(mu));          tidx[tb + o2 + 2 + 2 * n + 0] = iH;
-    st_fq(tsc + tb + o2 + 2 + 2 * n + 1, fq_mul(x1, that));    tidx[tb + o2 + 2 + 2 * n + 1] = iU;
-    st_fq(tsc + tb + o2 + 2 + 2 * n + 2, m1);                  tidx[tb + o2 + 2 + 2 * n + 2] = pb + RP_PNEW;
+    st_fq(tsc + tb + o2 + 2 + n + 0, fq_neg(mu));              tidx[tb + o2 + 2 + n + 0] = iH;
+    st_fq(tsc + tb + o2 + 2 + n + 1, fq_mul(x1, that));        tidx[tb + o2 + 2 + n + 1] = iU;
+    st_fq(tsc + tb + o2 + 2 + n + 2, m1);                      tidx[tb + o2 + 2 + n + 2] = pb + RP_PNEW;
+    st_fq(tsc + tb + o2 + 2 + n + 3, fq_neg(z));               tidx[tb + o2 + 2 + n + 3] = iGsum;        // sum_i (-z) * gs_i
+    st_fq(tsc + tb + o2 + 2 + n + 4, z);                       tidx[tb + o2 + 2 + n + 4] = iHsum;        // sum_i z * hs_i
     // E3
     st_fq(tsc + tb + o3 + 0, x1);                   tidx[tb + o3 + 0] = iU;
     st_fq(tsc + tb + o3 + 1, m1);                   tidx[tb + o3 + 1] = pb + RP_UNEW;
@@ -153,6 +156,20 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
     offsets[4 * p + 0] = base + o1; offsets[4 * p + 1] = base + o2; offsets[4 * p + 2] = base + o3; offsets[4 * p + 3] = base + o4;
     if (p == nproofs - 1) offsets[4 * nproofs] = base + lay.tpp;
   }
+}
+
+// out = sum of n affine points (n <= 1024), one block of 128 threads: the per-generator-set constants Gsum, Hsum
+__global__ void __launch_bounds__(128) k_sum_points(const Affine* __restrict__ pts, u32 n, Affine* __restrict__ out) {
+  __shared__ XYZZ sm[128];
+  XYZZ acc = xyzz_identity();
+  for (u32 i = threadIdx.x; i < n; i += 128) { Affine p = ld_affine(pts + i); xyzz_madd_ni(acc, p); }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if (threadIdx.x < off) { XYZZ v = sm[threadIdx.x + off]; xyzz_add_ni(acc, v); sm[threadIdx.x] = acc; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_affine(out, xyzz_to_affine(acc));
 }
 
 // accept[p] = all four MSM results of proof p are the identity
