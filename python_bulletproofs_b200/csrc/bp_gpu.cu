@@ -383,6 +383,8 @@ int bp_shutdown(void) {
   for (auto& kv : g_handles) cudaFree(kv.second.p);
   g_handles.clear();
   g.free_all();
+  for (auto& kv : g.ipa_graphs) cudaGraphExecDestroy(kv.second.exec);
+  g.ipa_graphs.clear();
   nccl_shutdown();
   cudaStreamDestroy(g.stream);
   g.inited = false;
