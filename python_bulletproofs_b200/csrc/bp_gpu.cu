@@ -323,6 +323,22 @@ __global__ void __launch_bounds__(256) k_pipe_probe(u32* out, u32 seed, int iter
 #pragma unroll
     for (int i = 0; i < 16; i++) s ^= p[i];
     if (s == 0x1234567u) out[0] = s;
+  } else if (MODE >= 6) {
+    // latency probes (launched as ONE warp): dependent chains of the operations the MSM tails are made of
+    Fp x, y;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x.v[i] = a * (i + 1); y.v[i] = b + i; }
+    XYZZ P; P.X = x; P.Y = y; P.ZZ = fp_sqr(y); P.ZZZ = fp_mul(P.ZZ, y);
+    XYZZ Q; Q.X = y; Q.Y = x; Q.ZZ = fp_sqr(x); Q.ZZZ = fp_mul(Q.ZZ, x);
+    const int role = threadIdx.x & 3, base = threadIdx.x & ~3;
+    if (MODE == 6) { for (int it = 0; it < iters; it++) x = fp_mul(x, y); P.X = x; }
+    else if (MODE == 7) { for (int it = 0; it < iters; it++) P = coop_dbl(P, role, base); }
+    else if (MODE == 8) { for (int it = 0; it < iters; it++) P = xyzz_dbl(P); }
+    else { for (int it = 0; it < iters; it++) P = coop_add(P, Q, role, base); }
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= P.X.v[i] ^ P.Y.v[i] ^ P.ZZ.v[i] ^ P.ZZZ.v[i];
+    if (s == 0x1234567u) out[0] = s;
   } else {
     Fp x, y;
 #pragma unroll
@@ -582,7 +598,11 @@ static int pipe_probe(int mode, int iters, double* ops_per_s, float* ms_out) {
       case 3: k_pipe_probe<3><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
       case 4: k_pipe_probe<4><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
       case 5: k_pipe_probe<5><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
-      default: return fail("bp_pipe_probe: mode 0..5");
+      case 6: k_pipe_probe<6><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
+      case 7: k_pipe_probe<7><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
+      case 8: k_pipe_probe<8><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
+      case 9: k_pipe_probe<9><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
+      default: return fail("bp_pipe_probe: mode 0..9");
     }
     BP_CUDA(cudaEventRecord(g.ev_b, g.stream));
     BP_CUDA(cudaEventSynchronize(g.ev_b));

@@ -76,7 +76,7 @@ BP_DI XYZZ coop_add(const XYZZ& a, const XYZZ& b, int role, int base) {
   const bool pz = fp_is_zero(Pd), rz = fp_is_zero(R);
   const bool both = !ida && !idb;
   const bool need_dbl = both && pz && rz;                   // same point: double
-  if (__any_sync(BP_FULL_MASK, need_dbl)) {
+  if (__any_sync(BP_FULL_MASK, need_dbl)) {                 // (moving this pass out of line miscomputed on sm_100a; it stays inline)
     XYZZ d = coop_dbl(a, role, base);
     r = sel_xyzz(need_dbl, d, r);
   }

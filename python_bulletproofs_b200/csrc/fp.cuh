@@ -224,28 +224,36 @@ BP_DI void mul_wide_karatsuba(u32 t[16], const u32 a[8], const u32 b[8]) {
 
 // r = t mod p (lazy), t 512 bits:  t = lo + hi*2^256 = lo + hi*C
 BP_DI void fold512(u32 r[8], const u32 t[16]) {
-  // s = hi * 977 : 9 limbs (even/odd halves so every product is one IMAD.WIDE)
-  u32 s[9];
-  asm("mul.lo.u32 %0,%9,%13; mul.hi.u32 %1,%9,%13; mul.lo.u32 %2,%10,%13; mul.hi.u32 %3,%10,%13;"
-      "mul.lo.u32 %4,%11,%13; mul.hi.u32 %5,%11,%13; mul.lo.u32 %6,%12,%13; mul.hi.u32 %7,%12,%13; mov.u32 %8,0;"
-      : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8])
+  // hi * 977 as two sets of independent 32x32->64 products: se[2k..2k+1] = t[8+2k]*977 at limb 2k, so[2k..2k+1] =
+  // t[9+2k]*977 at limb 2k+1.  Both sets live in aligned register pairs with no addend, so every product is a bare
+  // IMAD.WIDE (a mad chain through the odd positions needed pairs that straddle two products: ~16 register moves per
+  // fold on the multiplier pipe, the top non-arithmetic cost in the accumulation kernel's SASS).
+  u32 se[8], so[8];
+  asm("mul.lo.u32 %0,%8,%12; mul.hi.u32 %1,%8,%12; mul.lo.u32 %2,%9,%12; mul.hi.u32 %3,%9,%12;"
+      "mul.lo.u32 %4,%10,%12; mul.hi.u32 %5,%10,%12; mul.lo.u32 %6,%11,%12; mul.hi.u32 %7,%11,%12;"
+      : "=r"(se[0]), "=r"(se[1]), "=r"(se[2]), "=r"(se[3]), "=r"(se[4]), "=r"(se[5]), "=r"(se[6]), "=r"(se[7])
       : "r"(t[8]), "r"(t[10]), "r"(t[12]), "r"(t[14]), "r"(977u));
-  asm("mad.lo.cc.u32 %0,%8,%12,%0; madc.hi.cc.u32 %1,%8,%12,%1; madc.lo.cc.u32 %2,%9,%12,%2; madc.hi.cc.u32 %3,%9,%12,%3;"
-      "madc.lo.cc.u32 %4,%10,%12,%4; madc.hi.cc.u32 %5,%10,%12,%5; madc.lo.cc.u32 %6,%11,%12,%6; madc.hi.u32 %7,%11,%12,%7;"
-      : "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]), "+r"(s[5]), "+r"(s[6]), "+r"(s[7]), "+r"(s[8])
+  asm("mul.lo.u32 %0,%8,%12; mul.hi.u32 %1,%8,%12; mul.lo.u32 %2,%9,%12; mul.hi.u32 %3,%9,%12;"
+      "mul.lo.u32 %4,%10,%12; mul.hi.u32 %5,%10,%12; mul.lo.u32 %6,%11,%12; mul.hi.u32 %7,%11,%12;"
+      : "=r"(so[0]), "=r"(so[1]), "=r"(so[2]), "=r"(so[3]), "=r"(so[4]), "=r"(so[5]), "=r"(so[6]), "=r"(so[7])
       : "r"(t[9]), "r"(t[11]), "r"(t[13]), "r"(t[15]), "r"(977u));
-  // u = lo + s + (hi << 32): limbs 0..8 plus a carry word `top`
-  u32 u[9], top, top2;
-  asm("add.cc.u32 %0,%10,%18; addc.cc.u32 %1,%11,%19; addc.cc.u32 %2,%12,%20; addc.cc.u32 %3,%13,%21;"
-      "addc.cc.u32 %4,%14,%22; addc.cc.u32 %5,%15,%23; addc.cc.u32 %6,%16,%24; addc.cc.u32 %7,%17,%25;"
-      "addc.cc.u32 %8,%26,0; addc.u32 %9,0,0;"
-      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(top)
+  // w = so + hi (both at limb 1), u = lo + se (limb 0): in these two chains ptxas folds each product into an
+  // IMAD.WIDE whose 64-bit addend is an aligned pair; the third chain u += w << 32 is plain adds.
+  u32 w[8], u[9], top, top2;
+  asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,%20;"
+      "addc.cc.u32 %4,%13,%21; addc.cc.u32 %5,%14,%22; addc.cc.u32 %6,%15,%23; addc.cc.u32 %7,%16,%24; addc.u32 %8,0,0;"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(top2)
+      : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]),
+        "r"(so[0]), "r"(so[1]), "r"(so[2]), "r"(so[3]), "r"(so[4]), "r"(so[5]), "r"(so[6]), "r"(so[7]));
+  asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,%20;"
+      "addc.cc.u32 %4,%13,%21; addc.cc.u32 %5,%14,%22; addc.cc.u32 %6,%15,%23; addc.cc.u32 %7,%16,%24; addc.u32 %8,0,0;"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8])
       : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
-        "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]), "r"(s[8]));
+        "r"(se[0]), "r"(se[1]), "r"(se[2]), "r"(se[3]), "r"(se[4]), "r"(se[5]), "r"(se[6]), "r"(se[7]));
   asm("add.cc.u32 %0,%0,%9; addc.cc.u32 %1,%1,%10; addc.cc.u32 %2,%2,%11; addc.cc.u32 %3,%3,%12;"
       "addc.cc.u32 %4,%4,%13; addc.cc.u32 %5,%5,%14; addc.cc.u32 %6,%6,%15; addc.cc.u32 %7,%7,%16; addc.u32 %8,0,0;"
-      : "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]), "+r"(u[8]), "=r"(top2)
-      : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]));
+      : "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]), "+r"(u[8]), "=r"(top)
+      : "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]));
   top += top2;                       // e = u[8] + top*2^32 < 2^34
   // second fold: r = u[0..7] + e*977 + (e << 32)
   u64 m = (u64)u[8] * 977ull + (((u64)(top * 977u)) << 32);   // e*977 < 2^44
@@ -276,43 +284,72 @@ BP_DI Fp fp_mul(const Fp& a, const Fp& b) {
   return r;
 }
 // ---- dedicated squaring: 28 cross products (doubled by a 1-bit shift) + 8 squares = 36 IMAD.WIDE instead of 64 ------
-template <int N>
-BP_DI void sqr_chain(u32* acc, u32 x0, u32 x1, u32 x2, u32 x3, u32 b) {
-  // acc[0..2N-1] += {x0..x(N-1)} * b at consecutive 64-bit slots, carry into acc[2N]
-  if (N == 1) {
-    asm("mad.lo.cc.u32 %0,%3,%4,%0; madc.hi.cc.u32 %1,%3,%4,%1; addc.u32 %2,%2,0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(x0), "r"(b));
-  } else if (N == 2) {
-    asm("mad.lo.cc.u32 %0,%5,%7,%0; madc.hi.cc.u32 %1,%5,%7,%1; madc.lo.cc.u32 %2,%6,%7,%2; madc.hi.cc.u32 %3,%6,%7,%3; addc.u32 %4,%4,0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]) : "r"(x0), "r"(x1), "r"(b));
-  } else if (N == 3) {
-    asm("mad.lo.cc.u32 %0,%7,%10,%0; madc.hi.cc.u32 %1,%7,%10,%1; madc.lo.cc.u32 %2,%8,%10,%2; madc.hi.cc.u32 %3,%8,%10,%3;"
-        "madc.lo.cc.u32 %4,%9,%10,%4; madc.hi.cc.u32 %5,%9,%10,%5; addc.u32 %6,%6,0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
-        : "r"(x0), "r"(x1), "r"(x2), "r"(b));
-  } else {
-    mul_row_mad(acc, x0, x1, x2, x3, b);
-  }
+// The cross products a_i*a_j (i < j) are taken by DIAGONALS j - i = d: the products of one diagonal sit at consecutive
+// 64-bit slots (limb 2i + d), so each diagonal is one carry chain into the even (d even) or odd (d odd) accumulator,
+// followed by a carry ripple to the accumulator's top.  The two longest diagonals start from empty accumulators and
+// are bare products.  (A row-wise layout materialised a carry word and a zeroed pair per row: ~25 extra multiplier-
+// pipe instructions per squaring in the SASS.)
+BP_DI void sqr_diag_5_2(u32* acc, u32 x0, u32 y0, u32 x1, u32 y1, u32 x2, u32 y2, u32 x3, u32 y3, u32 x4, u32 y4) {
+  asm("mad.lo.cc.u32 %0,%13,%14,%0; madc.hi.cc.u32 %1,%13,%14,%1; madc.lo.cc.u32 %2,%15,%16,%2;"
+      "madc.hi.cc.u32 %3,%15,%16,%3; madc.lo.cc.u32 %4,%17,%18,%4; madc.hi.cc.u32 %5,%17,%18,%5;"
+      "madc.lo.cc.u32 %6,%19,%20,%6; madc.hi.cc.u32 %7,%19,%20,%7; madc.lo.cc.u32 %8,%21,%22,%8;"
+      "madc.hi.cc.u32 %9,%21,%22,%9; addc.cc.u32 %10,%10,0; addc.cc.u32 %11,%11,0; addc.u32 %12,%12,0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12])
+      : "r"(x0), "r"(y0), "r"(x1), "r"(y1), "r"(x2), "r"(y2), "r"(x3), "r"(y3), "r"(x4), "r"(y4));
+}
+BP_DI void sqr_diag_4_2(u32* acc, u32 x0, u32 y0, u32 x1, u32 y1, u32 x2, u32 y2, u32 x3, u32 y3) {
+  asm("mad.lo.cc.u32 %0,%11,%12,%0; madc.hi.cc.u32 %1,%11,%12,%1; madc.lo.cc.u32 %2,%13,%14,%2;"
+      "madc.hi.cc.u32 %3,%13,%14,%3; madc.lo.cc.u32 %4,%15,%16,%4; madc.hi.cc.u32 %5,%15,%16,%5;"
+      "madc.lo.cc.u32 %6,%17,%18,%6; madc.hi.cc.u32 %7,%17,%18,%7; addc.cc.u32 %8,%8,0; addc.cc.u32 %9,%9,0;"
+      "addc.u32 %10,%10,0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10])
+      : "r"(x0), "r"(y0), "r"(x1), "r"(y1), "r"(x2), "r"(y2), "r"(x3), "r"(y3));
+}
+BP_DI void sqr_diag_3_4(u32* acc, u32 x0, u32 y0, u32 x1, u32 y1, u32 x2, u32 y2) {
+  asm("mad.lo.cc.u32 %0,%11,%12,%0; madc.hi.cc.u32 %1,%11,%12,%1; madc.lo.cc.u32 %2,%13,%14,%2;"
+      "madc.hi.cc.u32 %3,%13,%14,%3; madc.lo.cc.u32 %4,%15,%16,%4; madc.hi.cc.u32 %5,%15,%16,%5;"
+      "addc.cc.u32 %6,%6,0; addc.cc.u32 %7,%7,0; addc.cc.u32 %8,%8,0; addc.cc.u32 %9,%9,0;"
+      "addc.u32 %10,%10,0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10])
+      : "r"(x0), "r"(y0), "r"(x1), "r"(y1), "r"(x2), "r"(y2));
+}
+BP_DI void sqr_diag_2_4(u32* acc, u32 x0, u32 y0, u32 x1, u32 y1) {
+  asm("mad.lo.cc.u32 %0,%9,%10,%0; madc.hi.cc.u32 %1,%9,%10,%1; madc.lo.cc.u32 %2,%11,%12,%2;"
+      "madc.hi.cc.u32 %3,%11,%12,%3; addc.cc.u32 %4,%4,0; addc.cc.u32 %5,%5,0; addc.cc.u32 %6,%6,0;"
+      "addc.cc.u32 %7,%7,0; addc.u32 %8,%8,0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+      : "r"(x0), "r"(y0), "r"(x1), "r"(y1));
+}
+BP_DI void sqr_diag_1_6(u32* acc, u32 x0, u32 y0) {
+  asm("mad.lo.cc.u32 %0,%9,%10,%0; madc.hi.cc.u32 %1,%9,%10,%1; addc.cc.u32 %2,%2,0; addc.cc.u32 %3,%3,0;"
+      "addc.cc.u32 %4,%4,0; addc.cc.u32 %5,%5,0; addc.cc.u32 %6,%6,0; addc.cc.u32 %7,%7,0; addc.u32 %8,%8,0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+      : "r"(x0), "r"(y0));
 }
 // t[0..15] = a * a
 BP_DI void sqr_wide(u32 t[16], const u32 a[8]) {
+  // ev[k] sits at limb k, od[k] at limb k+1
   u32 ev[16], od[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) { ev[k] = 0; od[k] = 0; }
-  // cross products a_i * a_j, i < j; position i+j even -> ev[i+j], odd -> od[i+j-1]
-  sqr_chain<4>(od + 0, a[1], a[3], a[5], a[7], a[0]);
-  sqr_chain<3>(ev + 2, a[2], a[4], a[6], 0, a[0]);
-  sqr_chain<3>(od + 2, a[2], a[4], a[6], 0, a[1]);
-  sqr_chain<3>(ev + 4, a[3], a[5], a[7], 0, a[1]);
-  sqr_chain<3>(od + 4, a[3], a[5], a[7], 0, a[2]);
-  sqr_chain<2>(ev + 6, a[4], a[6], 0, 0, a[2]);
-  sqr_chain<2>(od + 6, a[4], a[6], 0, 0, a[3]);
-  sqr_chain<2>(ev + 8, a[5], a[7], 0, 0, a[3]);
-  sqr_chain<2>(od + 8, a[5], a[7], 0, 0, a[4]);
-  sqr_chain<1>(ev + 10, a[6], 0, 0, 0, a[4]);
-  sqr_chain<1>(od + 10, a[6], 0, 0, 0, a[5]);
-  sqr_chain<1>(ev + 12, a[7], 0, 0, 0, a[5]);
-  sqr_chain<1>(od + 12, a[7], 0, 0, 0, a[6]);
+  ev[0] = 0; ev[1] = 0; ev[14] = 0; ev[15] = 0; od[14] = 0; od[15] = 0;
+  // d = 1: a0a1 a1a2 ... a6a7 at od[0], od[2], ..., od[12];   d = 2: a0a2 ... a5a7 at ev[2], ..., ev[12]
+  asm("mul.lo.u32 %0,%14,%15; mul.hi.u32 %1,%14,%15; mul.lo.u32 %2,%15,%16; mul.hi.u32 %3,%15,%16;"
+      "mul.lo.u32 %4,%16,%17; mul.hi.u32 %5,%16,%17; mul.lo.u32 %6,%17,%18; mul.hi.u32 %7,%17,%18;"
+      "mul.lo.u32 %8,%18,%19; mul.hi.u32 %9,%18,%19; mul.lo.u32 %10,%19,%20; mul.hi.u32 %11,%19,%20;"
+      "mul.lo.u32 %12,%20,%21; mul.hi.u32 %13,%20,%21;"
+      : "=r"(od[0]), "=r"(od[1]), "=r"(od[2]), "=r"(od[3]), "=r"(od[4]), "=r"(od[5]), "=r"(od[6]), "=r"(od[7]), "=r"(od[8]), "=r"(od[9]),
+        "=r"(od[10]), "=r"(od[11]), "=r"(od[12]), "=r"(od[13])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+  asm("mul.lo.u32 %0,%12,%14; mul.hi.u32 %1,%12,%14; mul.lo.u32 %2,%13,%15; mul.hi.u32 %3,%13,%15;"
+      "mul.lo.u32 %4,%14,%16; mul.hi.u32 %5,%14,%16; mul.lo.u32 %6,%15,%17; mul.hi.u32 %7,%15,%17;"
+      "mul.lo.u32 %8,%16,%18; mul.hi.u32 %9,%16,%18; mul.lo.u32 %10,%17,%19; mul.hi.u32 %11,%17,%19;"
+      : "=r"(ev[2]), "=r"(ev[3]), "=r"(ev[4]), "=r"(ev[5]), "=r"(ev[6]), "=r"(ev[7]), "=r"(ev[8]), "=r"(ev[9]), "=r"(ev[10]), "=r"(ev[11]),
+        "=r"(ev[12]), "=r"(ev[13])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+  sqr_diag_5_2(od + 2, a[0], a[3], a[1], a[4], a[2], a[5], a[3], a[6], a[4], a[7]);      // d = 3 -> od[2..11], ripple to od[14]
+  sqr_diag_4_2(ev + 4, a[0], a[4], a[1], a[5], a[2], a[6], a[3], a[7]);                  // d = 4 -> ev[4..11], ripple to ev[14]
+  sqr_diag_3_4(od + 4, a[0], a[5], a[1], a[6], a[2], a[7]);                              // d = 5 -> od[4..9]
+  sqr_diag_2_4(ev + 6, a[0], a[6], a[1], a[7]);                                          // d = 6 -> ev[6..9]
+  sqr_diag_1_6(od + 6, a[0], a[7]);                                                      // d = 7 -> od[6..7]
   // c = ev + (od << 32)
   u32 c[16];
   c[0] = ev[0];
@@ -354,23 +391,32 @@ BP_DI Fp fp_sqr_n(Fp a, int n) {
   return a;
 }
 // a^(p-2): 255 squarings + 15 multiplications (addition chain on the run structure of p-2:
-// 223 ones, 0, 22 ones, 0000, 1, 0, 11, 0, 1)
+// 223 ones, 0, 22 ones, 0000, 1, 0, 11, 0, 1).  Every step is "square n times, multiply by an earlier power", done by
+// ONE out-of-line routine with a rolled loop: an inversion is always a single-thread latency chain at the end of a
+// kernel, and fully inlined it was 270 KB of straight-line code fetched cold on every call (instruction-cache misses
+// cost more than the arithmetic); this form is ~8 KB.
+__device__ __noinline__ void fp_sqrn_mul(Fp& x, int n, const Fp& m) {
+  Fp t = x;
+#pragma unroll 1
+  for (int i = 0; i < n; i++) t = fp_sqr(t);
+  x = fp_mul(t, m);
+}
 __device__ __noinline__ Fp fp_inv(const Fp& a) {
-  Fp x2 = fp_mul(fp_sqr(a), a);
-  Fp x3 = fp_mul(fp_sqr(x2), a);
-  Fp x6 = fp_mul(fp_sqr_n(x3, 3), x3);
-  Fp x9 = fp_mul(fp_sqr_n(x6, 3), x3);
-  Fp x11 = fp_mul(fp_sqr_n(x9, 2), x2);
-  Fp x22 = fp_mul(fp_sqr_n(x11, 11), x11);
-  Fp x44 = fp_mul(fp_sqr_n(x22, 22), x22);
-  Fp x88 = fp_mul(fp_sqr_n(x44, 44), x44);
-  Fp x176 = fp_mul(fp_sqr_n(x88, 88), x88);
-  Fp x220 = fp_mul(fp_sqr_n(x176, 44), x44);
-  Fp x223 = fp_mul(fp_sqr_n(x220, 3), x3);
-  Fp t = fp_mul(fp_sqr_n(x223, 23), x22);
-  t = fp_mul(fp_sqr_n(t, 5), a);
-  t = fp_mul(fp_sqr_n(t, 3), x2);
-  t = fp_mul(fp_sqr_n(t, 2), a);
+  Fp x2 = a; fp_sqrn_mul(x2, 1, a);
+  Fp x3 = x2; fp_sqrn_mul(x3, 1, a);
+  Fp x6 = x3; fp_sqrn_mul(x6, 3, x3);
+  Fp x9 = x6; fp_sqrn_mul(x9, 3, x3);
+  Fp x11 = x9; fp_sqrn_mul(x11, 2, x2);
+  Fp x22 = x11; fp_sqrn_mul(x22, 11, x11);
+  Fp x44 = x22; fp_sqrn_mul(x44, 22, x22);
+  Fp x88 = x44; fp_sqrn_mul(x88, 44, x44);
+  Fp t = x88; fp_sqrn_mul(t, 88, x88);      // x176
+  fp_sqrn_mul(t, 44, x44);                  // x220
+  fp_sqrn_mul(t, 3, x3);                    // x223
+  fp_sqrn_mul(t, 23, x22);
+  fp_sqrn_mul(t, 5, a);
+  fp_sqrn_mul(t, 3, x2);
+  fp_sqrn_mul(t, 2, a);
   return t;
 }
 

@@ -367,20 +367,26 @@ __global__ void __launch_bounds__(128) k_reduce_grp(const XYZZ* __restrict__ seg
   XYZZ run = xyzz_identity(), T = xyzz_identity(), P = xyzz_identity();
   for (int j = (int)G - 1; j >= 0; j--) {
     XYZZ r = ld_xyzz(Rn + j), sj = ld_xyzz(Sm + j);
-    if (j > 0) { run = coop_add(run, r, role, base); T = coop_add(T, run, role, base); }   // weights j = 0..G-1
-    else run = coop_add(run, r, role, base);
+    run = coop_add(run, r, role, base);
+    if (j > 0) T = coop_add(T, run, role, base);                             // weights j = 0..G-1 (uniform branch)
     P = coop_add(P, sj, role, base);
   }
-  for (int d = 0; d < lgS; d++) T = coop_dbl(T, role, base);                 // S * T
+  // S * T, then u * R by double-and-add, then * G * S: one doubling site and one addition site (code size)
   XYZZ acc = xyzz_identity();
-  for (int i = ubits - 1; i >= 0; i--) {                                     // u * R
-    acc = coop_dbl(acc, role, base);
-    XYZZ t = coop_add(acc, run, role, base);
-    acc = sel_xyzz((u >> i) & 1, t, acc);
+  const int nd = ubits > 0 ? ubits + lgS + lgG : 0;
+  for (int d = 0; d < lgS + nd; d++) {
+    const bool onT = d < lgS;
+    XYZZ x = sel_xyzz(onT, T, acc);
+    x = coop_dbl(x, role, base);
+    if (onT) T = x; else acc = x;
+    const int i = ubits - 1 - (d - lgS);                                     // bit of u consumed after this doubling
+    if (!onT && i >= 0) {
+      XYZZ t = coop_add(acc, run, role, base);
+      acc = sel_xyzz((u >> i) & 1, t, acc);
+    }
   }
-  if (ubits > 0) for (int d = 0; d < lgS + lgG; d++) acc = coop_dbl(acc, role, base);     // * G * S
-  P = coop_add(P, T, role, base);
-  P = coop_add(P, acc, role, base);
+#pragma unroll 1
+  for (int k = 0; k < 2; k++) P = coop_add(P, k == 0 ? T : acc, role, base);
   if (active && role == 0) st_xyzz(grpsum + qid, P);
 }
 

@@ -17,3 +17,11 @@ for mode in (0, 1, 2, 4, 3, 5):
         nat.check(lib.bp_pipe_probe(mode, iters, ctypes.byref(ops), ctypes.byref(ms)))
         per_clk_sm = ops.value / 148 / 1.965e9
         print("mode %d %-52s iters=%6d  %.2f ms  %.3f Tops/s  (%.1f /clk/SM at 1965 MHz)" % (mode, names[mode], iters, ms.value, ops.value / 1e12, per_clk_sm), flush=True)
+
+# latency probes: one warp, dependent chain; ms / iters = latency of one operation
+lat = {6: "fp_mul (dependent chain)", 7: "coop_dbl (4-lane doubling, 3 levels)", 8: "xyzz_dbl (one thread, 9 mults)", 9: "coop_add (4-lane addition, 4 levels)"}
+for mode in (6, 7, 8, 9):
+    iters = 4096
+    ops, ms = ctypes.c_double(), ctypes.c_float()
+    nat.check(lib.bp_pipe_probe(mode, iters, ctypes.byref(ops), ctypes.byref(ms)))
+    print("mode %d %-44s %.3f us per op (%.0f cycles at 1965 MHz)" % (mode, lat[mode], ms.value * 1e3 / iters, ms.value * 1e-3 / iters * 1.965e9), flush=True)
