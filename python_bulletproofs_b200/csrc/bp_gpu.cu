@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -107,9 +108,13 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   } else {
     XYZZ* seg_run = (XYZZ*)g.ws_segrun.ensure(nsegs * sizeof(XYZZ));
     if (!seg_run) return fail("workspace allocation failed");
-    k_reduce_seg<<<(unsigned)((4 * nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
-    // level 2: groups of G segments
-    u32 G = sh.nseg < 8 ? sh.nseg : 8, ngrp = sh.nseg / G;
+    if (sh.seg_plain) k_reduce_seg_plain<<<(unsigned)((nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
+    else k_reduce_seg<<<(unsigned)((4 * nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
+    // level 2: groups of G = 8 segments (measured at 2^20, c = 16 after the thread-per-segment first level:
+    // G = 4 / 8 / 16 / 32 -> reduce stage 0.390 / 0.296 / 0.335 / 0.423 ms; the quad form pays ~2.4x the multiplications'
+    // issue cost in glue, so many small groups turn it throughput bound)
+    const u32 Gmax = 8;
+    u32 G = sh.nseg < Gmax ? sh.nseg : Gmax, ngrp = sh.nseg / G;
     int lgS = 0, lgG = 0, ubits = 0;
     while ((1u << lgS) < sh.S) lgS++;
     while ((1u << lgG) < G) lgG++;
@@ -118,7 +123,15 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     if (!grpsum) return fail("workspace allocation failed");
     k_reduce_grp<<<(unsigned)((4 * nmw * ngrp + 127) / 128), 128, 0, st>>>(seg_run, segsum, sh, nmw, 0, G, lgS, lgG, ubits, grpsum);
     ws = grpsum;
-    if (ngrp > 1) { k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(grpsum, ngrp, winsum); ws = winsum; }
+    if (ngrp >= 1024) {
+      // level 3 in two steps: 64 quads per block sum 256 groups each, then one small block per unit adds the partials
+      const u32 split = ngrp / 256;   // ngrp is a power of two
+      XYZZ* partial = (XYZZ*)g.ws_winpart.ensure(nmw * split * sizeof(XYZZ));
+      if (!partial) return fail("workspace allocation failed");
+      k_window_sum<<<(unsigned)(nmw * split), 256, 0, st>>>(grpsum, 256, partial);
+      k_window_sum<<<(unsigned)nmw, split < 8 ? 32 : 4 * split, 0, st>>>(partial, split, winsum);
+      ws = winsum;
+    } else if (ngrp > 1) { k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(grpsum, ngrp, winsum); ws = winsum; }
     if (prof) cudaEventRecord(g.ev[5], st);
     k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
   }

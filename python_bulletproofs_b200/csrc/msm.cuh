@@ -27,7 +27,9 @@
 
 namespace bp {
 
+#ifndef BP_CHUNK
 #define BP_CHUNK 32                // entries per accumulation thread (large problems)
+#endif
 #define BP_FIXUP_SERIAL_MAX 64     // buckets spanning more chunks than this are summed by a whole block
 
 struct MsmShape {
@@ -39,6 +41,7 @@ struct MsmShape {
   u32 H;          // buckets per unit = 2^(c-1)
   u32 chunk;      // entries per accumulation thread (BP_CHUNK, or 8 for small problems where latency rules)
   u32 S;          // buckets per reduce segment
+  int seg_plain;  // 1: first reduction level runs one thread per segment (very wide units), 0: one quad per segment
   u32 nseg;       // segments per window
 };
 #define BP_GLV_BITS 128
@@ -71,7 +74,10 @@ inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
     double entries = 2.0 * n * s.W * (double)nmsm;
     s.chunk = entries <= 1300000.0 ? 8 : (entries <= 2600000.0 ? 16 : BP_CHUNK);
   }
-  s.S = s.H < 8 ? s.H : 8;
+  // first reduction level: with >= 32768 segments in flight a thread per segment of 4 buckets saturates the SMs
+  // (k_reduce_seg_plain); below that the 4-lane cooperative form over 8 buckets has the shorter chain
+  s.seg_plain = (nmsm <= 8 && (double)s.U * s.H / 4 >= 32768.0) ? 1 : 0;
+  s.S = s.seg_plain ? 4 : (s.H < 8 ? s.H : 8);
   s.nseg = s.H / s.S;
   return s;
 }
@@ -346,6 +352,23 @@ __global__ void __launch_bounds__(128) k_reduce_seg(const XYZZ* __restrict__ buc
     sum = coop_add(sum, run, role, base);
   }
   if (active && role == 0) { st_xyzz(seg_run + qid, run); st_xyzz(seg_sum + qid, sum); }
+}
+
+// Level 1, throughput form: one THREAD per segment (used when tens of thousands of segments are in flight).
+__global__ void __launch_bounds__(128) k_reduce_seg_plain(const XYZZ* __restrict__ buckets, MsmShape sh, size_t nmw,
+                                                          XYZZ* __restrict__ seg_run, XYZZ* __restrict__ seg_sum) {
+  const size_t total = nmw * sh.nseg;
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const XYZZ* B = buckets + q * sh.S;
+  XYZZ run = xyzz_identity(), sum = xyzz_identity();
+  for (int i = (int)sh.S - 1; i >= 0; i--) {
+    XYZZ bk = ld_xyzz(B + i);
+    xyzz_add_ni(run, bk);
+    xyzz_add_ni(sum, run);
+  }
+  st_xyzz(seg_run + q, run);
+  st_xyzz(seg_sum + q, sum);
 }
 
 // Level 2 -- one QUAD per group of G consecutive segments of one window (G = 16, or nseg when smaller).  With segment
