@@ -74,6 +74,13 @@ int bp_msm_accumulate_kernel_ms(float* ms);   /* k_accumulate alone (stage [3] a
  * rangeproof_aggreg_prover.py:82, rangeproof_aggreg_verifier.py:80; ModP.__mul__(Point) utils.py:43-44 */
 int bp_scalar_mul_batch(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t* out64);
 
+/* ---- batched lift-x / point decompression ---------------------------------------
+ * y = sqrt(x^3 + 7) for n candidate x coordinates (32-byte LE, must be < p); ok[i] = 1 when x is on the curve, else
+ * out[i] = zeros.  want[i]: 0 = even y, 1 = odd y (bytes_to_point, src/utils/utils.py:119-131), 2 = the root
+ * mod_sqrt(...)[0] = (x^3+7)^((p+1)/4), 3 = p - that root (elliptic_hash, src/utils/elliptic_curve_hash.py:17-23);
+ * want == NULL means 2 for all. */
+int bp_lift_x_batch(const uint8_t* xs32, const uint8_t* want, size_t n, uint8_t* out64, uint8_t* ok);
+
 /* ---- inner-product argument ---------------------------------------------------------------------
  * One folding step, for step-wise parity tests:
  *   g'[i] = xinv*g[i] + x*g[i+n/2],  h'[i] = x*h[i] + xinv*h[i+n/2]      (inner_product_prover.py:107-108)

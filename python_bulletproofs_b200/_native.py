@@ -41,6 +41,7 @@ PROTOTYPES = {
     "bp_msm_stage_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "bp_msm_accumulate_kernel_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "bp_scalar_mul_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p]),
+    "bp_lift_x_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p, c_u8p]),
     "bp_ipa_fold_round": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
     "bp_ipa_prove": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
                                     c_u8p, c_sz, ctypes.POINTER(c_sz)]),
@@ -164,6 +165,20 @@ def msm_batch_bytes(pts_b, sc_b, offsets):
     off = (ctypes.c_uint32 * len(offsets))(*offsets)
     check(load().bp_msm_batch(pts_b, sc_b, off, nmsm, out))
     return out.raw[:64 * nmsm]
+
+
+def lift_x_batch(xs, want=None):
+    """[(x, y) or None] for candidate x coordinates; want[i] in {0: even y, 1: odd y, 2: principal root, 3: its negation}."""
+    n = len(xs)
+    if n == 0:
+        return []
+    xb = b"".join(int(x).to_bytes(32, "little") for x in xs)
+    out = ctypes.create_string_buffer(64 * n)
+    ok = ctypes.create_string_buffer(n)
+    check(load().bp_lift_x_batch(xb, bytes(want) if want is not None else None, n, out, ok))
+    raw = out.raw
+    return [(int.from_bytes(raw[64 * i:64 * i + 32], "little"), int.from_bytes(raw[64 * i + 32:64 * i + 64], "little"))
+            if ok.raw[i] else None for i in range(n)]
 
 
 def scalar_mul_batch_bytes(pts_b, sc_b, n):

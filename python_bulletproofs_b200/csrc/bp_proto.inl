@@ -508,6 +508,53 @@ int bp_host_free(void* p) { if (p) cudaFreeHost(p); return 0; }
 
 }  // extern "C"
 
+// ---- batched point decompression / lift-x ------------------------------------------
+// y = (x^3 + 7)^((p+1)/4); ok = (x < p and y^2 == x^3 + 7).  want: 0 = even y, 1 = odd y (bytes_to_point,
+// /root/reference/src/utils/utils.py:119-131), 2 = the root exactly as mod_sqrt(...)[0] returns it, 3 = its negation
+// p - y (elliptic_hash, /root/reference/src/utils/elliptic_curve_hash.py:17-23, picks between these two with an md5 bit).
+namespace bp {
+__global__ void __launch_bounds__(128) k_lift_x(const Fp* __restrict__ xs, const uint8_t* __restrict__ want, u32 n,
+                                                Affine* __restrict__ out, uint8_t* __restrict__ ok) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp x = ld_fp(xs + i);
+  Fp xc = fp_canon(x);
+  bool in_range = true;                                   // canonical input required: x < p
+#pragma unroll
+  for (int k = 0; k < 8; k++) in_range = in_range && (xc.v[k] == x.v[k]);
+  Fp seven = fp_zero(); seven.v[0] = 7;
+  Fp rhs = fp_add(fp_mul(fp_sqr(x), x), seven);
+  Fp y = fp_canon(fp_sqrt(rhs));
+  Fp chk = fp_sub(fp_sqr(y), rhs);
+  bool good = in_range && fp_is_zero(chk);
+  const u32 w = want ? want[i] : 2u;
+  bool flip = false;
+  if (w == 0u) flip = (y.v[0] & 1u) != 0u;
+  else if (w == 1u) flip = (y.v[0] & 1u) == 0u;
+  else if (w == 3u) flip = true;
+  if (flip) y = fp_canon(fp_neg(y));                      // y != 0: x^3 + 7 = 0 has no root on this curve
+  Affine r; r.x = good ? x : fp_zero(); r.y = good ? y : fp_zero();
+  st_affine(out + i, r);
+  ok[i] = good ? 1 : 0;
+}
+}  // namespace bp
+extern "C" int bp_lift_x_batch(const uint8_t* xs32, const uint8_t* want, size_t n, uint8_t* out64, uint8_t* ok) {
+  BP_NEED_INIT();
+  if (n == 0) return 0;
+  if (!xs32 || !out64 || !ok) return fail("bp_lift_x_batch: null argument");
+  Fp* d_x = (Fp*)g.ws_sc.ensure(n * sizeof(Fp));
+  Affine* d_out = (Affine*)g.ws_out.ensure(n * sizeof(Affine));
+  uint8_t* d_flags = (uint8_t*)g.ws_misc.ensure(2 * n + 256);
+  if (!d_x || !d_out || !d_flags) return fail("device allocation failed");
+  BP_CUDA(cudaMemcpyAsync(d_x, xs32, n * 32, cudaMemcpyHostToDevice, g.stream));
+  if (want) BP_CUDA(cudaMemcpyAsync(d_flags, want, n, cudaMemcpyHostToDevice, g.stream));
+  k_lift_x<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(d_x, want ? d_flags : nullptr, (u32)n, d_out, d_flags + n);
+  BP_CUDA(cudaMemcpyAsync(out64, d_out, n * 64, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaMemcpyAsync(ok, d_flags + n, n, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
 // ---- arithmetic self-test hooks (used by tests/: known-answer tests vs Python big ints) -----------
 namespace bp {
 __global__ void k_test_fp(int op, const Fp* a, const Fp* b, u32 n, Fp* out) {

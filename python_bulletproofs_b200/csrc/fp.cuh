@@ -420,4 +420,26 @@ __device__ __noinline__ Fp fp_inv(const Fp& a) {
   return t;
 }
 
+// a^((p+1)/4): the square root of a quadratic residue (p = 3 mod 4); same addition-chain prefix as fp_inv, tail
+// x223 -> (23 squarings)*x22 -> (6 squarings)*x2 -> 2 squarings  [(p+1)/4 = 2^254 - 2^30 - 244].  The caller checks
+// r^2 == a (non-residues give a root of -a).  Replaces fastecdsa.util.mod_sqrt as used by
+// /root/reference/src/utils/elliptic_curve_hash.py:19 and /root/reference/src/utils/utils.py:127.
+__device__ __noinline__ Fp fp_sqrt(const Fp& a) {
+  Fp x2 = a; fp_sqrn_mul(x2, 1, a);
+  Fp x3 = x2; fp_sqrn_mul(x3, 1, a);
+  Fp x6 = x3; fp_sqrn_mul(x6, 3, x3);
+  Fp x9 = x6; fp_sqrn_mul(x9, 3, x3);
+  Fp x11 = x9; fp_sqrn_mul(x11, 2, x2);
+  Fp x22 = x11; fp_sqrn_mul(x22, 11, x11);
+  Fp x44 = x22; fp_sqrn_mul(x44, 22, x22);
+  Fp x88 = x44; fp_sqrn_mul(x88, 44, x44);
+  Fp t = x88; fp_sqrn_mul(t, 88, x88);      // x176
+  fp_sqrn_mul(t, 44, x44);                  // x220
+  fp_sqrn_mul(t, 3, x3);                    // x223
+  fp_sqrn_mul(t, 23, x22);
+  fp_sqrn_mul(t, 6, x2);
+  t = fp_sqr(t);
+  return fp_sqr(t);
+}
+
 }  // namespace bp

@@ -128,6 +128,22 @@ def bytes_to_point(b: bytes):
     return Point(x, y if y % 2 == want_odd else p - y, CURVE)
 
 
+def bytes_to_points(bs) -> list:
+    """[bytes_to_point(b) for b in bs] with the square roots taken on the GPU in one launch (bp_lift_x_batch).
+    An x that is not on the curve raises ValueError (the reference would return a point off the curve)."""
+    from .. import _native as nat
+    xs = [int.from_bytes(b[1:], "big") for b in bs]
+    want = bytes(0 if b[0] == 2 else 1 for b in bs)
+    pts = nat.lift_x_batch(xs, want)
+    if any(xy is None for xy in pts):
+        raise ValueError("bytes_to_points: x coordinate not on the curve")
+    return [Point(x, y, CURVE) for x, y in pts]
+
+
+def b64_to_points(ss) -> list:
+    return bytes_to_points([base64.b64decode(s) for s in ss])
+
+
 def inner_product(a: List[ModP], b: List[ModP]) -> ModP:
     """<a, b> in Z_p (utils.py:134-137)."""
     assert len(a) == len(b)

@@ -83,3 +83,59 @@ def test_ec_ops_including_exceptional_cases():
         assert got == [ecc.py_add(a, a) for a in A], op
     got = ecc.unpack_points(call_test("bp_test_ec", 3, pa, pb, n, 64), n)
     assert got == [ecc.point_neg(a) for a in A]
+
+
+# ---- batched lift-x / decompression / generator derivation -------------------------------------
+def test_lift_x_batch_matches_big_int_square_roots():
+    from python_bulletproofs_b200 import _native as nat
+    rng = random.Random(0x11F7)
+    xs = [rng.getrandbits(256) for _ in range(700)] + [0, 1, 2, P - 1, P, P + 5, 2 ** 256 - 1, ecc.GX]
+    want = bytes(rng.randrange(4) for _ in xs)
+    got = nat.lift_x_batch(xs, want)
+    n_on = 0
+    for x, w, xy in zip(xs, want, got):
+        rhs = (x * x * x + 7) % P
+        y = pow(rhs, (P + 1) // 4, P)
+        if x >= P or y * y % P != rhs:
+            assert xy is None, hex(x)
+            continue
+        n_on += 1
+        if w == 0:
+            y = y if y % 2 == 0 else P - y
+        elif w == 1:
+            y = y if y % 2 == 1 else P - y
+        elif w == 3:
+            y = P - y
+        assert xy == (x, y), hex(x)
+    assert 250 < n_on < 500                                    # about half of all x are on the curve
+    assert nat.lift_x_batch([ecc.GX], None) in ([(ecc.GX, ecc.GY)], [(ecc.GX, P - ecc.GY)])
+    assert nat.lift_x_batch([]) == []
+
+
+def test_elliptic_hash_batch_equals_reference_derivation():
+    from oracle import protocol_oracle as po
+    from python_bulletproofs_b200.curve import secp256k1
+    from python_bulletproofs_b200.utils import elliptic_hash, elliptic_hash_batch
+    msgs = [b"seed%d" % (i % 7) + str(i).encode() for i in range(400)] + [b"", b"\x00" * 64]
+    got = elliptic_hash_batch(msgs, secp256k1)
+    assert len(got) == len(msgs)
+    for m, g in zip(msgs, got):
+        assert (g.x, g.y) == po.elliptic_hash(m), m            # oracle: pinned by the reference's golden generators
+    for m, g in list(zip(msgs, got))[:20]:
+        h = elliptic_hash(m, secp256k1)
+        assert (g.x, g.y) == (h.x, h.y)
+
+
+def test_bytes_to_points_decompresses_like_bytes_to_point():
+    from python_bulletproofs_b200.utils import bytes_to_point, bytes_to_points, point_to_bytes, point_to_b64, b64_to_points
+    from python_bulletproofs_b200.point import Point
+    from python_bulletproofs_b200.curve import secp256k1
+    from helpers import fast_points
+    pts = [Point(x, y, secp256k1) for x, y in fast_points(200, 77)]
+    enc = [point_to_bytes(p) for p in pts]
+    dec = bytes_to_points(enc)
+    assert [(p.x, p.y) for p in dec] == [(p.x, p.y) for p in pts]
+    assert [(p.x, p.y) for p in dec[:10]] == [(q.x, q.y) for q in map(bytes_to_point, enc[:10])]
+    assert [(p.x, p.y) for p in b64_to_points([point_to_b64(p) for p in pts[:50]])] == [(p.x, p.y) for p in pts[:50]]
+    with pytest.raises(ValueError):
+        bytes_to_points([b"\x02" + (5).to_bytes(32, "big")])     # x = 5: x^3 + 7 = 132 is not a square mod p
