@@ -68,6 +68,17 @@ int bp_msm_set_pipeline_min(size_t min_terms);
 int bp_msm_stage_ms(float out7[7]);
 int bp_msm_accumulate_kernel_ms(float* ms);   /* k_accumulate alone (stage [3] also holds the bucket memset and the fix-ups) */
 
+/* ---- fixed-base tables for repeated generator sets -----------------------------------------------------
+ * The commitment / L,R / verifier call sites of a Bulletproofs instance pass the same group elements on every call
+ * (src/utils/commitments.py:9-13, src/innerproduct/inner_product_prover.py:98-99, src/rangeproofs/rangeproof_prover.py:
+ * 47,57,78-86).  The library recognises a repeated point set by a hash of its bytes and answers from a precomputed
+ * table (255 multiples per byte window, 522 KB per point) instead of the bucket method: same canonical result, ~5x
+ * lower latency for the 2..4097-term MSMs of a prover.  mode 0 = never, 1 = build at the second use of a set (default),
+ * 2 = build at first use.  bp_fb_clear drops every table. */
+int bp_fb_set_mode(int mode);
+int bp_fb_stats(uint64_t* tables, uint64_t* bytes, uint64_t* hits, uint64_t* builds);
+int bp_fb_clear(void);
+
 /* ---- independent scalar multiplications --------------------------------------------------------
  * out[i] = sc[i] * pts[i]:  hsp = [(y.inv() ** i) * hs[i] ...]
  * src/rangeproofs/rangeproof_prover.py:77, rangeproof_verifier.py:72,

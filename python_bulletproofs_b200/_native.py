@@ -42,6 +42,9 @@ PROTOTYPES = {
     "bp_msm_accumulate_kernel_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "bp_scalar_mul_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_lift_x_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p, c_u8p]),
+    "bp_fb_set_mode": (ctypes.c_int, [ctypes.c_int]),
+    "bp_fb_stats": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)] * 4),
+    "bp_fb_clear": (ctypes.c_int, []),
     "bp_ipa_fold_round": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
     "bp_ipa_prove": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
                                     c_u8p, c_sz, ctypes.POINTER(c_sz)]),

@@ -1,0 +1,95 @@
+// bp_fixed.inl -- host side of the fixed-base tables (fixedbase.cuh): a cache keyed by a hash of the generator bytes.
+// Policy (bp_fb_set_mode): 0 = never, 1 = build a table the SECOND time the same point set is seen (one-off MSMs never
+// pay the ~2 ms build), 2 = build at first sight.  Tables are evicted least-recently-used past a byte budget.
+// (included inside namespace bp by bp_gpu.cu)
+
+struct FbEntry { Affine* tab; size_t n; size_t bytes; unsigned long long stamp; };
+struct FbCache {
+  std::map<uint64_t, FbEntry> tabs;
+  std::map<uint64_t, unsigned> seen;
+  size_t bytes = 0, cap = (size_t)24 << 30;
+  size_t max_points = 4200;        // largest point set that gets a table (2049 of a 1024-wide IPA, 2 * 2048 + 1 commitments)
+  int mode = 1;
+  unsigned long long clock = 0, hits = 0, builds = 0;
+  DevBuf scratch, blockpart;
+};
+static FbCache fb;
+
+static uint64_t fb_hash(uint64_t h, const uint8_t* p, size_t nbytes) {
+  // 64-bit multiply-xorshift over 8-byte words (not cryptographic: a collision would need equal-length generator sets
+  // chosen against this hash; the key also carries the length)
+  size_t i = 0;
+  for (; i + 8 <= nbytes; i += 8) {
+    uint64_t w; memcpy(&w, p + i, 8);
+    h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+  }
+  for (; i < nbytes; i++) { h = (h ^ p[i]) * 0x100000001B3ull; }
+  return h;
+}
+
+static void fb_evict_for(size_t need) {
+  while (!fb.tabs.empty() && fb.bytes + need > fb.cap) {
+    auto victim = fb.tabs.begin();
+    for (auto it = fb.tabs.begin(); it != fb.tabs.end(); ++it) if (it->second.stamp < victim->second.stamp) victim = it;
+    cudaStreamSynchronize(g.stream);
+    cudaFree(victim->second.tab);
+    fb.bytes -= victim->second.bytes;
+    fb.tabs.erase(victim);
+    alloc_generation()++;            // captured graphs may hold the freed pointer
+  }
+}
+
+// Table for the point set `key` (n points at d_pts, readable in g.stream order), or nullptr when the set has no table
+// (mode, size, first sighting, or out of memory: the caller then takes the bucket method).
+static const Affine* fb_get(uint64_t key, const Affine* d_pts, size_t n) {
+  if (fb.mode == 0 || n == 0 || n > fb.max_points) return nullptr;
+  key ^= (uint64_t)n * 0xD6E8FEB86659FD93ull;
+  auto it = fb.tabs.find(key);
+  if (it != fb.tabs.end() && it->second.n == n) { it->second.stamp = ++fb.clock; fb.hits++; return it->second.tab; }
+  if (fb.mode == 1) {
+    if (fb.seen.size() > 8192) fb.seen.clear();
+    if (++fb.seen[key] < 2) return nullptr;
+  }
+  const size_t bytes = n * (size_t)BP_FB_WINDOWS * BP_FB_ENTRIES * sizeof(Affine);
+  if (bytes > fb.cap) return nullptr;
+  fb_evict_for(bytes);
+  const size_t ngmax = n < BP_FB_BUILD_GENS ? n : BP_FB_BUILD_GENS;
+  XYZZ* scratch = (XYZZ*)fb.scratch.ensure(ngmax * BP_FB_WINDOWS * BP_FB_ENTRIES * sizeof(XYZZ));
+  if (!scratch) return nullptr;
+  Affine* tab = nullptr;
+  if (cudaMalloc((void**)&tab, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  for (size_t g0 = 0; g0 < n; g0 += BP_FB_BUILD_GENS) {
+    const u32 ng = (u32)(n - g0 < BP_FB_BUILD_GENS ? n - g0 : BP_FB_BUILD_GENS);
+    k_fb_build<<<(ng * BP_FB_WINDOWS + 63) / 64, 64, 0, g.stream>>>(d_pts, (u32)g0, ng, scratch, tab);
+  }
+  if (cudaGetLastError() != cudaSuccess) { cudaFree(tab); return nullptr; }
+  fb.tabs[key] = FbEntry{tab, n, bytes, ++fb.clock};
+  fb.bytes += bytes;
+  fb.builds++;
+  return tab;
+}
+
+// nmsm table MSMs on g.stream: terms of MSM m are [offsets[m], offsets[m+1]) (device array), or [0, single_n) when
+// offsets == nullptr (then nmsm must be 1); max_terms bounds the longest MSM.
+static int fb_msm_run(const Affine* tab, const u32* d_idx, const Fq* d_sc, const u32* d_offsets, u32 nmsm, size_t max_terms,
+                      u32 single_n, Affine* out_affine, XYZZ* out_xyzz) {
+  const u32 nbx = (u32)((max_terms + 31) / 32);
+  if (nbx == 0 || nmsm == 0) return 0;
+  if (nmsm > 65535) return fail("fb_msm_run: too many MSMs in one launch");
+  XYZZ* part = (XYZZ*)fb.blockpart.ensure((size_t)nmsm * nbx * sizeof(XYZZ));
+  if (!part) return fail("workspace allocation failed");
+  k_fb_msm<<<dim3(nbx, nmsm), 256, 0, g.stream>>>(tab, d_idx, d_sc, d_offsets, single_n, part);
+  u32 nq = 8;
+  while (nq < nbx && nq < 64) nq <<= 1;
+  k_fb_finish<<<nmsm, 4 * nq, 0, g.stream>>>(part, nbx, out_affine, out_xyzz);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static void fb_release_all() {
+  for (auto& kv : fb.tabs) cudaFree(kv.second.tab);
+  fb.tabs.clear(); fb.seen.clear(); fb.bytes = 0;
+  fb.scratch.release(); fb.blockpart.release();
+}
+

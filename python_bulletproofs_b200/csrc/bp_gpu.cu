@@ -16,6 +16,7 @@
 #include "ipa.cuh"
 #include "transcript.h"
 #include "verify.cuh"
+#include "fixedbase.cuh"
 #include <nccl.h>
 #include <thread>
 
@@ -229,6 +230,8 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
   return 0;
 }
 
+#include "bp_fixed.inl"
+
 // Host operands -> device: scalars first on the compute stream (the digit/sort stages only need them), points on a
 // second stream so that their (twice as large) upload overlaps those stages; msm_run waits for the points right
 // before the first kernel that reads them.  The pipelined/profiling paths simply wait up front.
@@ -411,6 +414,7 @@ int bp_shutdown(void) {
   cudaStreamSynchronize(g.stream);
   for (auto& kv : g_handles) cudaFree(kv.second.p);
   g_handles.clear();
+  fb_release_all();
   g.free_all();
   for (auto& kv : g.ipa_graphs) cudaGraphExecDestroy(kv.second.exec);
   g.ipa_graphs.clear();
@@ -465,8 +469,43 @@ int bp_msm(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64
   Affine* d_pts = (Affine*)g.ws_pts.ensure(n * sizeof(Affine));
   Fq* d_sc = (Fq*)g.ws_sc.ensure(n * sizeof(Fq));
   if (!d_pts || !d_sc) return fail("device allocation failed");
+  if (fb.mode != 0 && n <= fb.max_points) {
+    // repeated generator set (a commitment call site of a prover/verifier): table lookups instead of buckets
+    const uint64_t key = fb_hash(0x6D736D31ull, pts64, n * 64);
+    auto hit = fb.tabs.find(key ^ ((uint64_t)n * 0xD6E8FEB86659FD93ull));
+    if (hit == fb.tabs.end()) BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.stream));   // needed to build
+    const Affine* tab = fb_get(key, d_pts, n);
+    if (tab) {
+      Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
+      if (!d_out) return fail("workspace allocation failed");
+      BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
+      if (fb_msm_run(tab, nullptr, d_sc, nullptr, 1, n, (u32)n, d_out, nullptr)) return 1;
+      BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
+      BP_CUDA(cudaStreamSynchronize(g.stream));
+      return 0;
+    }
+  }
   if (upload_operands(d_pts, pts64, d_sc, sc32, n)) return 1;
   return msm_to_host(d_pts, d_sc, n, out64);
+}
+
+int bp_fb_set_mode(int mode) {
+  if (mode < 0 || mode > 2) return fail("bp_fb_set_mode: 0 = off, 1 = build at the second use, 2 = build at first use");
+  fb.mode = mode;
+  return 0;
+}
+int bp_fb_stats(uint64_t* tables, uint64_t* bytes, uint64_t* hits, uint64_t* builds) {
+  if (tables) *tables = fb.tabs.size();
+  if (bytes) *bytes = fb.bytes;
+  if (hits) *hits = fb.hits;
+  if (builds) *builds = fb.builds;
+  return 0;
+}
+int bp_fb_clear(void) {
+  if (g.inited) cudaStreamSynchronize(g.stream);
+  fb_release_all();
+  alloc_generation()++;
+  return 0;
 }
 
 static int upload(const uint8_t* src, size_t n, size_t elt, int kind, bp_handle* h) {

@@ -121,6 +121,13 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
     BP_CUDA(cudaMemcpyAsync(ch, hscale32, n * 32, cudaMemcpyHostToDevice, g.stream));
     k_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(ch, (u32)n);
   }
+  // repeated generator set: L and R come from table lookups over the ORIGINAL generators (the s-vector form never
+  // rewrites PA, which is what makes a per-set table usable in every round)
+  const Affine* tab = nullptr;
+  if (fb.mode != 0 && 2 * n + 1 <= fb.max_points && n > 1) {
+    uint64_t key = fb_hash(fb_hash(fb_hash(0x69706131ull, u64_, 64), g64, n * 64), h64, n * 64);
+    tab = fb_get(key, PA, 2 * n + 1);
+  }
   size_t round = 0;
   RunningModHash rh;
   const u32 n1 = (u32)n + 1;
@@ -131,7 +138,7 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
     BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
     k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
     k_build_lr_sv<<<1, 256, 0, g.stream>>>(a, b, cg, ch, (u32)n, &d_rp->m, tsc, tidx);
-    if (msm_run(PA, tidx, tsc, 2 * n1, d_off, 2, n1, d_lr, nullptr)) return 1;
+    if (tab ? fb_msm_run(tab, tidx, tsc, d_off, 2, n1, 0, d_lr, nullptr) : msm_run(PA, tidx, tsc, 2 * n1, d_off, 2, n1, d_lr, nullptr)) return 1;
     BP_CUDA(cudaMemcpyAsync(h_lr, d_lr, 128, cudaMemcpyDeviceToHost, g.stream));
     return 0;
   };
@@ -144,7 +151,7 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
     if (round == 0 || !g.use_graphs) {
       if (enqueue_round()) return 1;
     } else {
-      if (!gexec) gexec = g.ipa_graph_lookup(n);
+      if (!gexec) gexec = g.ipa_graph_lookup(n, tab);
       if (!gexec) {
         cudaGraph_t graph = nullptr;
         BP_CUDA(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed));
@@ -154,7 +161,7 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
         ce = cudaGraphInstantiate(&gexec, graph, 0);
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) { cudaGetLastError(); return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
-        g.ipa_graph_store(n, gexec);
+        g.ipa_graph_store(n, tab, gexec);
       }
       BP_CUDA(cudaGraphLaunch(gexec, g.stream));
     }

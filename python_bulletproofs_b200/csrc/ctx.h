@@ -95,15 +95,20 @@ struct Ctx {
   // IPA round graphs: one instantiated graph per vector length, valid while no workspace has been reallocated
   bool use_graphs = true;
   DevBuf ws_ipa_rp;
-  struct GraphRec { cudaGraphExec_t exec; unsigned long long gen; };
+  struct GraphRec { cudaGraphExec_t exec; unsigned long long gen; const void* tab; };
   std::map<size_t, GraphRec> ipa_graphs;
-  cudaGraphExec_t ipa_graph_lookup(size_t n) {
-    auto it = ipa_graphs.find(n);
+  // `tab` = the fixed-base table the captured round reads (nullptr: bucket-method round); part of the key
+  cudaGraphExec_t ipa_graph_lookup(size_t n, const void* tab) {
+    auto it = ipa_graphs.find(2 * n + (tab ? 1 : 0));
     if (it == ipa_graphs.end()) return nullptr;
-    if (it->second.gen != alloc_generation()) { cudaGraphExecDestroy(it->second.exec); ipa_graphs.erase(it); return nullptr; }
+    if (it->second.gen != alloc_generation() || it->second.tab != tab) { cudaGraphExecDestroy(it->second.exec); ipa_graphs.erase(it); return nullptr; }
     return it->second.exec;
   }
-  void ipa_graph_store(size_t n, cudaGraphExec_t e) { ipa_graphs[n] = GraphRec{e, alloc_generation()}; }
+  void ipa_graph_store(size_t n, const void* tab, cudaGraphExec_t e) {
+    auto it = ipa_graphs.find(2 * n + (tab ? 1 : 0));
+    if (it != ipa_graphs.end()) cudaGraphExecDestroy(it->second.exec);
+    ipa_graphs[2 * n + (tab ? 1 : 0)] = GraphRec{e, alloc_generation(), tab};
+  }
   unsigned char* pin_bytes_p = nullptr; size_t pin_bytes_cap = 0;
   unsigned char* pinned_bytes(size_t bytes) {
     if (bytes <= pin_bytes_cap) return pin_bytes_p;

@@ -1,0 +1,153 @@
+// fixedbase.cuh -- precomputed-table ("fixed-base") multi-scalar multiplication for generator sets that are used again
+// and again: the g_i, h_i, g, h, u of a Bulletproofs instance.
+//
+// Replaces (for REPEATED generator sets only; the first use of a set always takes the bucket method of msm.cuh):
+//   Pippenger.multiexp on the commitment / L,R / verifier call sites that always pass the same group elements
+//   (/root/reference/src/utils/commitments.py:9-13, /root/reference/src/innerproduct/inner_product_prover.py:98-99,
+//    /root/reference/src/rangeproofs/rangeproof_prover.py:47,57,78-86).
+//
+// Table: for every point P_g and every byte position w of a 256-bit scalar, the 255 affine points d * 2^(8w) * P_g,
+// d = 1..255  (32 windows x 255 entries x 64 B = 522 KB per point; 130 generators of a 64-bit range proof = 68 MB, the
+// 2049 of a 1024-wide inner-product argument = 1.07 GB -- small change in 180 GB of HBM3e).  An MSM is then
+// sum_i sum_w T[g_i][w][byte_w(k_i)]: 32 mixed additions per term, NO doublings, no bucket reduction and no Horner
+// chain, which is what bounds the latency of the small MSMs of a prover (0.58 ms -> ~0.1 ms at 65 terms).
+// Scalars are taken mod q and used unsigned (no recoding, no carries between windows), so each (term, window) is
+// independent work.  Results are canonical affine points, hence bit-identical to the bucket method.
+#pragma once
+#include "ec.cuh"
+#include "fq.cuh"
+#include "coop4.cuh"
+
+namespace bp {
+
+#define BP_FB_WINDOWS 32
+#define BP_FB_ENTRIES 255
+#define BP_FB_BUILD_GENS 256          // generators per build launch (bounds the XYZZ scratch: 256*32*255*128 B = 268 MB)
+
+BP_DI size_t fb_index(u32 gi, u32 w, u32 d) { return ((size_t)gi * BP_FB_WINDOWS + w) * BP_FB_ENTRIES + (d - 1); }
+
+BP_DI Fp ld_fp_coherent(const Fp* p) {       // plain loads: the build kernel re-reads what it wrote
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Fp r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// One thread per (generator, window): B = 2^(8w) * P, then the chain B, 2B, ..., 255B in XYZZ (scratch), normalised to
+// affine with ONE field inversion per thread (Montgomery's trick over the 255 ZZZ values; the running products are
+// parked in the x half of the output slots until the backward pass overwrites them).
+__global__ void __launch_bounds__(64) k_fb_build(const Affine* __restrict__ pts, u32 g0, u32 ng, XYZZ* __restrict__ scratch,
+                                                 Affine* __restrict__ tab) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ng * BP_FB_WINDOWS) return;
+  const u32 gi = g0 + t / BP_FB_WINDOWS, w = t % BP_FB_WINDOWS;
+  Affine P = ld_affine(pts + gi);
+  Affine* out = tab + fb_index(gi, w, 1);
+  if (affine_is_identity(P)) {
+    Affine z; z.x = fp_zero(); z.y = fp_zero();
+    for (int d = 0; d < BP_FB_ENTRIES; d++) st_affine(out + d, z);
+    return;
+  }
+  XYZZ B = xyzz_from_affine(P);
+  for (u32 i = 0; i < 8 * w; i++) B = xyzz_dbl_ni(B);
+  const Affine Ba = xyzz_to_affine(B);
+  XYZZ* sc = scratch + (size_t)t * BP_FB_ENTRIES;
+  XYZZ acc = xyzz_from_affine(Ba);
+  Fp pre = fp_one();
+  for (int d = 1; d <= BP_FB_ENTRIES; d++) {
+    if (d > 1) xyzz_madd_ni(acc, Ba);                  // d = 2 is the doubling case of the complete formula
+    st_xyzz(sc + d - 1, acc);
+    pre = fp_mul(pre, acc.ZZZ);                        // d * B is never the identity (d < q, B of prime order)
+    st_fp(&out[d - 1].x, pre);
+  }
+  Fp inv = fp_inv(pre);
+  for (int d = BP_FB_ENTRIES; d >= 1; d--) {
+    XYZZ e = ld_xyzz(sc + d - 1);
+    Fp prev = d > 1 ? ld_fp_coherent(&out[d - 2].x) : fp_one();
+    Fp zi3 = fp_mul(inv, prev);                        // ZZZ_d^-1
+    inv = fp_mul(inv, e.ZZZ);
+    Fp zi2 = fp_mul(fp_sqr(e.ZZ), fp_sqr(zi3));        // ZZ^-1 = ZZ^2 * ZZZ^-2
+    Affine r; r.x = fp_canon(fp_mul(e.X, zi2)); r.y = fp_canon(fp_mul(e.Y, zi3));
+    st_affine(out + d - 1, r);
+  }
+}
+
+// Table MSM, step 1.  blockIdx.y = MSM m with terms [offsets[m], offsets[m+1]); a block of 256 threads takes 32
+// consecutive terms: thread = (term, group of 4 byte-windows) does up to 4 mixed additions, then the block folds its
+// 256 partial sums with 4-lane cooperative additions (3 serial + 6 tree levels) into blockpart[m * nbx + blockIdx.x].
+// idx (optional) maps a term to its table row; scalars are 32-byte values reduced mod q here (pippenger.py:26).
+__global__ void __launch_bounds__(256) k_fb_msm(const Affine* __restrict__ tab, const u32* __restrict__ idx, const Fq* __restrict__ sc,
+                                                const u32* __restrict__ offsets, u32 single_n, XYZZ* __restrict__ blockpart) {
+  __shared__ XYZZ sm[256];
+  const u32 m = blockIdx.y, nbx = gridDim.x;
+  const u32 lo = offsets ? offsets[m] : 0u, hi = offsets ? offsets[m + 1] : single_n;
+  const u32 t = lo + blockIdx.x * 32 + (threadIdx.x >> 3), grp = threadIdx.x & 7;
+  XYZZ acc = xyzz_identity();
+  if (t < hi) {
+    const u32* kw = reinterpret_cast<const u32*>(sc + t);
+    Fq k;
+#pragma unroll
+    for (int i = 0; i < 8; i++) k.v[i] = __ldg(kw + i);
+    k = fq_reduce(k);
+    const u32 word = k.v[grp];                                   // windows 4*grp .. 4*grp+3 are the bytes of limb grp
+    const u32 gi = idx ? __ldg(idx + t) : t;
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+      const u32 d = (word >> (8 * j)) & 0xFFu;
+      if (d) { Affine p = ld_affine(tab + fb_index(gi, 4 * grp + j, d)); xyzz_madd_ni(acc, p); }
+    }
+  }
+  st_xyzz(&sm[threadIdx.x], acc);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const u32 q = threadIdx.x >> 2;
+  XYZZ v = ld_xyzz(&sm[4 * q]);
+#pragma unroll 1
+  for (int j = 1; j < 4; j++) { XYZZ x = ld_xyzz(&sm[4 * q + j]); v = coop_add(v, x, role, base); }
+  __syncthreads();
+  if (role == 0) st_xyzz(&sm[q], v);
+  __syncthreads();
+#pragma unroll 1
+  for (u32 off = 32; off > 0; off >>= 1) {
+    XYZZ x = (q < off) ? ld_xyzz(&sm[q + off]) : xyzz_identity();
+    v = coop_add(v, x, role, base);
+    __syncthreads();
+    if (q < off && role == 0) st_xyzz(&sm[q], v);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_xyzz(blockpart + (size_t)m * nbx + blockIdx.x, v);
+}
+
+// Table MSM, step 2: one block per MSM adds its nbx block sums (quads stride over them, then a tree) and writes the
+// canonical affine result (and/or the XYZZ value, for callers that add further terms).
+__global__ void __launch_bounds__(256) k_fb_finish(const XYZZ* __restrict__ blockpart, u32 nbx, Affine* __restrict__ out,
+                                                   XYZZ* __restrict__ out_xyzz) {
+  __shared__ XYZZ sm[64];
+  const u32 m = blockIdx.x;
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const u32 q = threadIdx.x >> 2, nq = blockDim.x >> 2;
+  XYZZ acc = xyzz_identity();
+  for (u32 i0 = 0; i0 < nbx; i0 += nq) {
+    const u32 i = i0 + q;
+    XYZZ x = i < nbx ? ld_xyzz(blockpart + (size_t)m * nbx + i) : xyzz_identity();
+    acc = coop_add(acc, x, role, base);
+  }
+  if (nq > 1) {
+    if (role == 0) st_xyzz(&sm[q], acc);
+    __syncthreads();
+#pragma unroll 1
+    for (u32 off = nq >> 1; off > 0; off >>= 1) {
+      XYZZ x = (q < off) ? ld_xyzz(&sm[q + off]) : xyzz_identity();
+      acc = coop_add(acc, x, role, base);
+      __syncthreads();
+      if (q < off && role == 0) st_xyzz(&sm[q], acc);
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (out_xyzz) st_xyzz(out_xyzz + m, acc);
+    if (out) st_affine(out + m, xyzz_to_affine(acc));
+  }
+}
+
+}  // namespace bp
