@@ -588,9 +588,25 @@ int bp_msm_batch(const uint8_t* pts64, const uint8_t* sc32, const uint32_t* offs
   u32* d_off = (u32*)g.ws_off.ensure((nmsm + 1) * sizeof(u32));
   Affine* d_out = (Affine*)g.ws_out.ensure(nmsm * sizeof(Affine));
   if (!d_pts || !d_sc || !d_off || !d_out) return fail("device allocation failed");
-  BP_CUDA(cudaMemcpyAsync(d_pts, pts64, T * 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(d_sc, sc32, T * 32, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(d_off, offsets, (nmsm + 1) * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
+  if (fb.mode != 0 && maxlen <= fb.max_points && nmsm <= 65535 && T == nmsm * maxlen) {
+    // every MSM of the batch over the SAME point list (A and S of a range proof, T1 and T2): one table serves all
+    bool same = true;
+    for (size_t j = 1; j < nmsm && same; j++) same = memcmp(pts64, pts64 + (size_t)offsets[j] * 64, maxlen * 64) == 0;
+    if (same) {
+      const uint64_t key = fb_hash(0x6D736D31ull, pts64, maxlen * 64);
+      BP_CUDA(cudaMemcpyAsync(d_pts, pts64, maxlen * 64, cudaMemcpyHostToDevice, g.stream));
+      const Affine* tab = fb_get(key, d_pts, maxlen);
+      if (tab) {
+        if (fb_msm_run(tab, nullptr, d_sc, d_off, (u32)nmsm, maxlen, 0, d_out, nullptr)) return 1;
+        BP_CUDA(cudaMemcpyAsync(out64, d_out, nmsm * 64, cudaMemcpyDeviceToHost, g.stream));
+        BP_CUDA(cudaStreamSynchronize(g.stream));
+        return 0;
+      }
+    }
+  }
+  BP_CUDA(cudaMemcpyAsync(d_pts, pts64, T * 64, cudaMemcpyHostToDevice, g.stream));
   size_t avg = (T + nmsm - 1) / nmsm;
   if (msm_run(d_pts, nullptr, d_sc, (u32)T, d_off, (u32)nmsm, avg, d_out, nullptr)) return 1;
   BP_CUDA(cudaMemcpyAsync(out64, d_out, nmsm * 64, cudaMemcpyDeviceToHost, g.stream));

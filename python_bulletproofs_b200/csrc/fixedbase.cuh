@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(64) k_fb_build(const Affine* __restrict__ pts,
 // Table MSM, step 1.  blockIdx.y = MSM m with terms [offsets[m], offsets[m+1]); a block of 256 threads takes 32
 // consecutive terms: thread = (term, group of 4 byte-windows) does up to 4 mixed additions, then the block folds its
 // 256 partial sums with 4-lane cooperative additions (3 serial + 6 tree levels) into blockpart[m * nbx + blockIdx.x].
-// idx (optional) maps a term to its table row; scalars are 32-byte values reduced mod q here (pippenger.py:26).
+// idx (optional) maps a term to its table row (without it term j of every MSM reads row j); scalars are 32-byte values reduced mod q here (pippenger.py:26).
 __global__ void __launch_bounds__(256) k_fb_msm(const Affine* __restrict__ tab, const u32* __restrict__ idx, const Fq* __restrict__ sc,
                                                 const u32* __restrict__ offsets, u32 single_n, XYZZ* __restrict__ blockpart) {
   __shared__ XYZZ sm[256];
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_fb_msm(const Affine* __restrict__ tab, 
     for (int i = 0; i < 8; i++) k.v[i] = __ldg(kw + i);
     k = fq_reduce(k);
     const u32 word = k.v[grp];                                   // windows 4*grp .. 4*grp+3 are the bytes of limb grp
-    const u32 gi = idx ? __ldg(idx + t) : t;
+    const u32 gi = idx ? __ldg(idx + t) : t - lo;               // no map: term j of an MSM reads table row j
 #pragma unroll 1
     for (int j = 0; j < 4; j++) {
       const u32 d = (word >> (8 * j)) & 0xFFu;

@@ -115,3 +115,17 @@ def test_provers_emit_the_golden_proofs_with_and_without_tables(fb_mode, golden,
     tp.test_aggreg_golden(golden, "aggreg_small")
     if mode == 2:
         assert _stats()["hits"] > 10
+
+
+def test_batch_of_msms_over_one_point_list_uses_one_table(fb_mode):
+    fb_mode(2)
+    rng = random.Random(99)
+    for n, nmsm in ((2, 2), (129, 2), (65, 5)):
+        pts = fast_points(n, 9000 + n)
+        pb = ecc.pack_points(pts)
+        kss = [[rng.getrandbits(256) for _ in range(n)] for _ in range(nmsm)]
+        kss[-1][0] = 0
+        raw = nat.msm_batch_bytes(pb * nmsm, b"".join(_sc(ks) for ks in kss), [n * j for j in range(nmsm + 1)])
+        for j, ks in enumerate(kss):
+            assert ecc.unpack_point(raw[64 * j:64 * j + 64]) == ecc.msm(pts, [k % Q for k in ks]), (n, j)
+    assert _stats()["hits"] >= 2
