@@ -78,7 +78,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(cursor, 0, (nb + 1) * sizeof(u32), st));
   if (prof) cudaEventRecord(g.ev[0], st);
-  k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count);
+  k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count, g.msm_skip_below ? point_idx : nullptr, g.msm_skip_below);
   if (prof) cudaEventRecord(g.ev[1], st);
   k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
   k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
@@ -190,7 +190,7 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
   BP_CUDA(cudaMemsetAsync(cursor, 0, (nb + 1) * sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(big, 0, W * (big_cap + 2) * sizeof(u32), st));
   k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
-  k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, nullptr, 1, sh, digits, count);
+  k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, nullptr, 1, sh, digits, count, nullptr, 0);
   k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
   k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
   k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);

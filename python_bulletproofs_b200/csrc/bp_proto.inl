@@ -1,3 +1,4 @@
+#include <chrono>
 // bp_proto.inl -- host drivers of the protocol-level entry points (included by bp_gpu.cu):
 // IPA folding rounds with the Fiat-Shamir transcript on the host, the Verifier2 equation,
 // batch range-proof verification, and the NCCL plumbing for sharded MSM / batches.
@@ -282,7 +283,10 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
                oa = 544, ob = 576, oXs = 608, oLs = oXs + 32 * L, oRs = oLs + 64 * L;
   // The batch is cut into chunks: while the GPU evaluates the equations of chunk i, the host threads run the
   // transcript checks of chunk i+1 (pinned, double-buffered staging so the uploads are truly asynchronous).
-  const size_t CH = nproofs < 4096 ? nproofs : 2048;
+  // chunk length: measured on B200 at 8192 proofs -- table path 1024/2048/4096/8192 -> 26.5/22.3/19.8/24.4 ms (the
+  // latency-bound kernels are paid per chunk, the host checks of the first chunk are exposed); bucket path: 2048 best
+  size_t CH = fb.mode != 0 ? (nproofs <= 4096 ? nproofs : 4096) : (nproofs < 4096 ? nproofs : 2048);
+  if (getenv("BP_VERIFY_CHUNK")) { CH = (size_t)atol(getenv("BP_VERIFY_CHUNK")); if (CH > nproofs) CH = nproofs; if (CH == 0) CH = 1; }
   const size_t sc_bytes = CH * lay.nsc * 32, pt_bytes = CH * lay.npt * 64;
   uint8_t* stage = g.pinned_stage(2 * (sc_bytes + pt_bytes));
   if (!stage) return fail("pinned staging allocation failed");
@@ -374,6 +378,21 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   BP_CUDA(cudaMemcpyAsync(table + 2 * n + 2, u64_, 64, cudaMemcpyHostToDevice, g.stream));
   k_sum_points<<<1, 128, 0, g.stream>>>(table, (u32)n, table + 2 * n + 3);          // Gsum
   k_sum_points<<<1, 128, 0, g.stream>>>(table + n, (u32)n, table + 2 * n + 4);      // Hsum
+  // Repeated generator set: its terms (2n+1 of E4, n+4 of E2, ...: 202 of the 220 terms of a 64-bit proof) are read from
+  // the fixed-base table, 32 lookups each with no doublings and no bucket reduction; only the ~21 proof-specific terms
+  // (V, A, S, T1, T2, u', P', L_j, R_j) still go through the bucket method.  Each equation is still checked exactly.
+  const Affine* fbtab = nullptr;
+  XYZZ *d_lanes = nullptr, *d_var = nullptr, *d_tot = nullptr;
+  if (fb.mode != 0) {
+    uint64_t key = fb_hash(fb_hash(fb_hash(fb_hash(fb_hash(0x72707631ull, gs64, n * 64), hs64, n * 64), g64, 64), h64, 64), u64_, 64);
+    fbtab = fb_get(key, table, lay.fixed);
+    if (fbtab) {
+      d_lanes = (XYZZ*)g.ws_fb_lanes.ensure(4 * CH * (128 + 16) * sizeof(XYZZ));
+      d_var = (XYZZ*)g.ws_fb_var.ensure(2 * 4 * CH * sizeof(XYZZ));
+      if (!d_lanes || !d_var) return fail("device allocation failed");
+      d_tot = d_var + 4 * CH;
+    }
+  }
   const u32 bd = n < 32 ? 32 : (u32)n;
   const size_t smem = (2 * L + 1 + bd) * sizeof(Fq);
   int chunk_no = 0;
@@ -381,6 +400,7 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
     const size_t chunk_hi = chunk_lo + CH < nproofs ? chunk_lo + CH : nproofs, cn = chunk_hi - chunk_lo;
     cur = chunk_no & 1;
     if (chunk_no >= 2) BP_CUDA(cudaEventSynchronize(g.stage_ev[cur]));       // staging buffer free again?
+    auto t_h0 = std::chrono::steady_clock::now();
     {   // host: transcript checks of this chunk on all cores
       std::vector<std::thread> th;
       unsigned nt = nthreads > cn ? (unsigned)cn : nthreads;
@@ -391,6 +411,8 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
       }
       for (auto& t : th) t.join();
     }
+    if (getenv("BP_VERIFY_TIMING")) fprintf(stderr, "chunk %d: host %.3f ms (%u threads)\n", chunk_no,
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h0).count(), nthreads);
     // device: scalar expansion, one batched MSM over the 4*cn equations, accept bits
     BP_CUDA(cudaMemcpyAsync(table + lay.fixed, hpt_buf[cur], cn * lay.npt * 64, cudaMemcpyHostToDevice, g.stream));
     BP_CUDA(cudaMemcpyAsync(psc, hsc_buf[cur], cn * lay.nsc * 32, cudaMemcpyHostToDevice, g.stream));
@@ -398,8 +420,21 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
     k_reduce_scalars<<<(unsigned)((cn * lay.nsc + 127) / 128), 128, 0, g.stream>>>(psc, (u32)(cn * lay.nsc));
     k_rp_invert<<<(unsigned)((cn + 63) / 64), 64, 0, g.stream>>>(psc, lay, (u32)cn, d_inv);
     k_rp_expand<<<(unsigned)cn, bd, smem, g.stream>>>(psc, d_inv, lay, (u32)cn, tsc, tidx, d_off);
-    if (msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, (u32)(4 * cn), lay.tpp / 4, d_res, nullptr)) return 1;
-    k_rp_accept<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)cn, d_acc + chunk_lo);
+    if (fbtab) {
+      const u32 nm = (u32)(4 * cn);
+      k_rp_lookup<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
+      g.msm_skip_below = lay.fixed;                                        // bucket pass: proof-specific terms only
+      int rc = msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, nm, (lay.npt + 2 + 3) / 4, nullptr, d_var);
+      g.msm_skip_below = 0;
+      if (rc) return 1;
+      XYZZ* d_grp = d_lanes + (size_t)4 * CH * 128;
+      k_rp_fold8<<<(nm * 16 + 127) / 128, 128, 0, g.stream>>>(d_lanes, nm, d_grp);
+      k_rp_fold<<<(nm + 3) / 4, 128, 0, g.stream>>>(d_grp, d_var, nm, d_tot);
+      k_rp_accept_xyzz<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_tot, (u32)cn, d_acc + chunk_lo);
+    } else {
+      if (msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, (u32)(4 * cn), lay.tpp / 4, d_res, nullptr)) return 1;
+      k_rp_accept<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)cn, d_acc + chunk_lo);
+    }
   }
   BP_CUDA(cudaMemcpyAsync(accept, d_acc, nproofs, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));

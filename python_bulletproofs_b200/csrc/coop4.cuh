@@ -25,6 +25,12 @@ BP_DI Fp shfl_fp(const Fp& m, int src_lane) {
   for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(BP_FULL_MASK, m.v[i], src_lane);
   return r;
 }
+BP_DI Fp shfl_down_fp(const Fp& m, int delta) {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(BP_FULL_MASK, m.v[i], delta);
+  return r;
+}
 BP_DI Fp sel_fp(bool c, const Fp& a, const Fp& b) {
   Fp r;
 #pragma unroll

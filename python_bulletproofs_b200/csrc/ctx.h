@@ -44,10 +44,11 @@ struct Ctx {
   cudaEvent_t ev_pts = nullptr, ev_copy_gate = nullptr, pts_ready = nullptr;
   bool profiling = false;
   int force_c = 0, last_c = 0;
+  unsigned msm_skip_below = 0;                  // msm_run: terms with point index below this are left to the caller (see k_digits)
   size_t last_nb = 0;
   // MSM workspaces
   DevBuf ws_pts, ws_sc, ws_off, ws_out, ws_digits, ws_entries, ws_count, ws_start, ws_cursor, ws_tiles, ws_buckets, ws_segsum,
-      ws_winsum, ws_misc, ws_flush, ws_entry_bucket, ws_part, ws_big, ws_phi, ws_segrun, ws_grpsum, ws_winpart;
+      ws_winsum, ws_misc, ws_flush, ws_entry_bucket, ws_part, ws_big, ws_phi, ws_segrun, ws_grpsum, ws_winpart, ws_fb_lanes, ws_fb_var;
   // IPA / verifier workspaces
   DevBuf ws_g, ws_h, ws_a, ws_b, ws_g2, ws_h2, ws_a2, ws_b2, ws_idx, ws_lr, ws_terms_sc, ws_small;
   // pipelined single-MSM path: 2 accumulate streams, one reduce stream per window, one Horner stream
@@ -123,7 +124,7 @@ struct Ctx {
   void free_all() {
     DevBuf* all[] = {&ws_pts, &ws_sc, &ws_off, &ws_out, &ws_digits, &ws_entries, &ws_count, &ws_start, &ws_cursor, &ws_tiles,
                      &ws_buckets, &ws_segsum, &ws_winsum, &ws_misc, &ws_flush, &ws_g, &ws_h, &ws_a, &ws_b, &ws_g2, &ws_h2,
-                     &ws_a2, &ws_b2, &ws_idx, &ws_lr, &ws_terms_sc, &ws_small, &ws_entry_bucket, &ws_part, &ws_big, &ws_phi, &ws_segrun, &ws_grpsum, &ws_winpart};
+                     &ws_a2, &ws_b2, &ws_idx, &ws_lr, &ws_terms_sc, &ws_small, &ws_entry_bucket, &ws_part, &ws_big, &ws_phi, &ws_segrun, &ws_grpsum, &ws_winpart, &ws_fb_lanes, &ws_fb_var};
     for (DevBuf* b : all) b->release();
   }
 };

@@ -150,4 +150,57 @@ __global__ void __launch_bounds__(256) k_fb_finish(const XYZZ* __restrict__ bloc
   }
 }
 
+// ---- throughput form for batches of MSMs whose terms mix table rows and other points (batch verifier) ----------------
+// Step 1: one WARP per MSM, lane l owns byte-window l: for every term with a table row (idx < nfixed) one lookup and one
+// mixed addition per lane; terms with idx >= nfixed belong to the caller's other pass and are skipped (warp-uniform).
+// The 32 lane sums go to part[32 * m + l]; step 2 folds them.  Few registers here (occupancy), the cooperative adds
+// live in the second kernel.
+__global__ void __launch_bounds__(256) k_fb_lookup_warp(const Affine* __restrict__ tab, const u32* __restrict__ idx, const Fq* __restrict__ sc,
+                                                        const u32* __restrict__ offsets, u32 nmsm, u32 nfixed, XYZZ* __restrict__ part) {
+  const u32 m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= nmsm) return;
+  const u32 lo = __ldg(offsets + m), hi = __ldg(offsets + m + 1);
+  XYZZ acc = xyzz_identity();
+  for (u32 t = lo; t < hi; t++) {
+    const u32 gi = __ldg(idx + t);
+    if (gi >= nfixed) continue;
+    const u32* kw = reinterpret_cast<const u32*>(sc + t);
+    Fq k;
+#pragma unroll
+    for (int i = 0; i < 8; i++) k.v[i] = __ldg(kw + i);
+    k = fq_reduce(k);
+    const u32 d = (k.v[lane >> 2] >> (8 * (lane & 3))) & 0xFFu;
+    if (d) { Affine p = ld_affine(tab + fb_index(gi, lane, d)); xyzz_madd_ni(acc, p); }
+  }
+  st_xyzz(part + (size_t)32 * m + lane, acc);
+}
+// Step 2: one warp per MSM = 8 quads: each quad adds 4 lane sums, then a 3-level tree; optionally adds `other[m]` (the
+// caller's partial for the same MSM) and writes out[m].
+__global__ void __launch_bounds__(128) k_fb_fold_warp(const XYZZ* __restrict__ part, const XYZZ* __restrict__ other, u32 nmsm,
+                                                      XYZZ* __restrict__ out) {
+  __shared__ XYZZ sm[4][8];
+  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  u32 m = blockIdx.x * 4 + warp;
+  const bool live = m < nmsm;
+  if (!live) m = nmsm - 1;                                   // whole warps stay in the shuffles; the duplicate does not store
+  const int role = lane & 3, base = lane & ~3;
+  const u32 q = lane >> 2;
+  const XYZZ* src = part + (size_t)32 * m + 4 * q;
+  XYZZ v = ld_xyzz(src);
+#pragma unroll 1
+  for (int j = 1; j < 4; j++) { XYZZ x = ld_xyzz(src + j); v = coop_add(v, x, role, base); }
+  if (role == 0) st_xyzz(&sm[warp][q], v);
+  __syncwarp();
+#pragma unroll 1
+  for (u32 off = 4; off > 0; off >>= 1) {
+    XYZZ x = (q < off) ? ld_xyzz(&sm[warp][q + off]) : xyzz_identity();
+    v = coop_add(v, x, role, base);
+    __syncwarp();
+    if (q < off && role == 0) st_xyzz(&sm[warp][q], v);
+    __syncwarp();
+  }
+  if (other) { XYZZ x = ld_xyzz(other + m); v = coop_add(v, x, role, base); }
+  if (live && lane == 0) st_xyzz(out + m, v);
+}
+
 }  // namespace bp

@@ -100,14 +100,18 @@ BP_DI u32 find_msm(const u32* __restrict__ offsets, u32 nmsm, u32 t) {
 
 // One thread per term: k mod q -> GLV halves (k1, k2) -> sign-normalised magnitudes < 2^128 -> signed c-bit
 // digits.  Sub-term 2t carries k1 on P_t, sub-term 2t+1 carries k2 on phi(P_t).  digits is [W][2T].
+// skip_idx / skip_below (optional): terms whose point index is below skip_below count as zero scalars -- the caller
+// evaluates them elsewhere (fixed-base tables of the batch verifier) and this MSM covers the remaining terms only.
 __global__ void __launch_bounds__(256) k_digits(const Fq* __restrict__ scalars, u32 T, const u32* __restrict__ offsets, u32 nmsm,
-                                                MsmShape sh, int* __restrict__ digits, u32* __restrict__ bucket_count) {
+                                                MsmShape sh, int* __restrict__ digits, u32* __restrict__ bucket_count,
+                                                const u32* __restrict__ skip_idx, u32 skip_below) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + t);
   uint4 a = __ldg(sp), b = __ldg(sp + 1);
   Fq k; k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
   k = fq_reduce(k);                                   // es = [ei % order]   pippenger.py:26
+  if (skip_idx && __ldg(skip_idx + t) < skip_below) k = fq_zero();
   Fq half[2];
   bool hneg[2];
   glv_split(k, half[0], hneg[0], half[1], hneg[1]);   // magnitudes < 2^128 and signs

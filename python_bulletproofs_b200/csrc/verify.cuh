@@ -17,6 +17,7 @@
 #include "ec.cuh"
 #include "fq.cuh"
 #include "ipa.cuh"
+#include "fixedbase.cuh"
 
 namespace bp {
 
@@ -178,6 +179,85 @@ __global__ void k_rp_accept(const Affine* __restrict__ res, u32 nproofs, uint8_t
   if (p >= nproofs) return;
   bool ok = true;
   for (int e = 0; e < 4; e++) ok = ok && affine_is_identity(ld_affine(res + 4 * p + e));
+  accept[p] = ok ? 1 : 0;
+}
+
+// ---- table path of the batch verifier: balanced lookups -------------------------------------------------------------
+// One block of 256 threads per proof.  The four equations have very different numbers of generator terms (2, n+4, 1,
+// 2n+1), so the 8 warps are dealt out as E1:1, E2:2, E3:1, E4:4; warp slice s of an equation takes its terms s, s+nw,
+// s+2nw, ... and lane l owns byte-window l (one table lookup + one mixed addition per (term, lane)).  Terms on
+// proof-specific points (idx >= nfixed) are skipped: they go through the bucket pass.  Lane sums land in
+// part[(4p+e)*128 + 32*s + l].
+__global__ void __launch_bounds__(256) k_rp_lookup(const Affine* __restrict__ tab, const u32* __restrict__ idx, const Fq* __restrict__ sc,
+                                                   const u32* __restrict__ offsets, u32 nproofs, u32 nfixed, XYZZ* __restrict__ part) {
+  const u32 p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p >= nproofs) return;
+  // warp -> (equation, slice, slices of that equation)
+  const u32 e = warp < 4 ? 3u : (warp < 6 ? 1u : (warp == 6 ? 0u : 2u));
+  const u32 nw = e == 3 ? 4u : (e == 1 ? 2u : 1u);
+  const u32 s = e == 3 ? warp : (e == 1 ? warp - 4 : 0u);
+  const u32 lo = __ldg(offsets + 4 * p + e), hi = __ldg(offsets + 4 * p + e + 1);
+  XYZZ acc = xyzz_identity();
+  for (u32 t = lo + s; t < hi; t += nw) {
+    const u32 gi = __ldg(idx + t);
+    if (gi >= nfixed) continue;
+    const u32* kw = reinterpret_cast<const u32*>(sc + t);
+    Fq k;
+#pragma unroll
+    for (int i = 0; i < 8; i++) k.v[i] = __ldg(kw + i);
+    k = fq_reduce(k);
+    const u32 d = (k.v[lane >> 2] >> (8 * (lane & 3))) & 0xFFu;
+    if (d) { Affine q = ld_affine(tab + fb_index(gi, lane, d)); xyzz_madd_ni(acc, q); }
+  }
+  st_xyzz(part + ((size_t)(4 * p + e) * 128 + 32 * s + lane), acc);
+}
+// Fold, step 1 (throughput form): one thread adds 8 consecutive lane sums; 16 group sums per equation slot
+__global__ void __launch_bounds__(128) k_rp_fold8(const XYZZ* __restrict__ part, u32 nmsm, XYZZ* __restrict__ grp) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;          // (m, group of 8)
+  const u32 m = t >> 4, gq = t & 15;
+  if (m >= nmsm) return;
+  const u32 e = m & 3u, ng = e == 3 ? 16u : (e == 1 ? 8u : 4u);
+  if (gq >= ng) return;
+  const XYZZ* src = part + (size_t)m * 128 + 8 * gq;
+  XYZZ v = ld_xyzz(src);
+#pragma unroll 1
+  for (int j = 1; j < 8; j++) { XYZZ x = ld_xyzz(src + j); xyzz_add_ni(v, x); }
+  st_xyzz(grp + (size_t)m * 16 + gq, v);
+}
+// Fold, step 2: one warp per equation: its <= 16 group sums + the bucket pass's partial `other[m]` -> out[m]
+__global__ void __launch_bounds__(128) k_rp_fold(const XYZZ* __restrict__ part, const XYZZ* __restrict__ other, u32 nmsm,
+                                                 XYZZ* __restrict__ out) {
+  __shared__ XYZZ sm[4][8];
+  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  u32 m = blockIdx.x * 4 + warp;
+  const bool live = m < nmsm;
+  if (!live) m = nmsm - 1;
+  const u32 e = m & 3u, nl = e == 3 ? 16u : (e == 1 ? 8u : 4u);
+  const int role = lane & 3, base = lane & ~3;
+  const u32 q = lane >> 2;
+  const XYZZ* src = part + (size_t)m * 16;
+  XYZZ v = q < nl ? ld_xyzz(src + q) : xyzz_identity();
+  if (nl > 8) { XYZZ x = ld_xyzz(src + q + 8); v = coop_add(v, x, role, base); }       // warp-uniform (one equation per warp)
+  if (role == 0) st_xyzz(&sm[warp][q], v);
+  __syncwarp();
+#pragma unroll 1
+  for (u32 off = 4; off > 0; off >>= 1) {
+    XYZZ x = (q < off) ? ld_xyzz(&sm[warp][q + off]) : xyzz_identity();
+    v = coop_add(v, x, role, base);
+    __syncwarp();
+    if (q < off && role == 0) st_xyzz(&sm[warp][q], v);
+    __syncwarp();
+  }
+  if (other) { XYZZ x = ld_xyzz(other + m); v = coop_add(v, x, role, base); }
+  if (live && lane == 0) st_xyzz(out + m, v);
+}
+
+// same decision from XYZZ sums (table path: fixed-generator part + other terms already added): identity <=> ZZ == 0
+__global__ void k_rp_accept_xyzz(const XYZZ* __restrict__ res, u32 nproofs, uint8_t* __restrict__ accept) {
+  u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nproofs) return;
+  bool ok = true;
+  for (int e = 0; e < 4; e++) ok = ok && xyzz_is_identity(ld_xyzz(res + 4 * p + e));
   accept[p] = ok ? 1 : 0;
 }
 

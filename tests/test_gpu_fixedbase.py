@@ -129,3 +129,14 @@ def test_batch_of_msms_over_one_point_list_uses_one_table(fb_mode):
         for j, ks in enumerate(kss):
             assert ecc.unpack_point(raw[64 * j:64 * j + 64]) == ecc.msm(pts, [k % Q for k in ks]), (n, j)
     assert _stats()["hits"] >= 2
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_batch_verifier_decisions_with_and_without_tables(fb_mode, mode):
+    """Every corruption kind of the protocol suite's batch-verifier test, oracle-checked, under both table modes."""
+    fb_mode(mode)
+    import test_gpu_protocols as tp
+    tp.test_batch_verify_decisions(8, 40)
+    tp.test_batch_verify_decisions(64, 24)
+    if mode == 2:
+        assert _stats()["tables"] >= 2

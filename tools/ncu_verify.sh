@@ -1,6 +1,7 @@
 #!/bin/bash
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_rp_expand|k_reduce_unit_plain|k_combine_plain|k_rp_accept' -c 8 \
-    --csv --log-file gpurun_out/verify_kernels.csv python tools/verify_probe.py 2048 > /dev/null 2>&1
+# per-kernel device times of the batch verifier (development aid); the third verify_packed call runs on tables
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_rp_|k_fb_lookup|k_fb_fold|k_reduce_unit_plain|k_combine_plain' -s 16 -c 28 \
+    --csv --log-file gpurun_out/verify_kernels.csv python tools/verify_probe.py 8192 > /dev/null 2>&1
 python - <<PY
 import csv
 rows=list(csv.reader(l for l in open("gpurun_out/verify_kernels.csv") if l.startswith('"')))
