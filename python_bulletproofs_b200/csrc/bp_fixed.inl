@@ -15,6 +15,9 @@ struct FbCache {
 };
 static FbCache fb;
 
+// a forced window width (bp_msm_set_window) is an explicit request for the bucket method
+static bool fb_enabled() { return fb.mode != 0 && g.force_c == 0; }
+
 static uint64_t fb_hash(uint64_t h, const uint8_t* p, size_t nbytes) {
   // 64-bit multiply-xorshift over 8-byte words (not cryptographic: a collision would need equal-length generator sets
   // chosen against this hash; the key also carries the length)

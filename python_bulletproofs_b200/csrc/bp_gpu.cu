@@ -469,7 +469,7 @@ int bp_msm(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64
   Affine* d_pts = (Affine*)g.ws_pts.ensure(n * sizeof(Affine));
   Fq* d_sc = (Fq*)g.ws_sc.ensure(n * sizeof(Fq));
   if (!d_pts || !d_sc) return fail("device allocation failed");
-  if (fb.mode != 0 && n <= fb.max_points) {
+  if (fb_enabled() && n <= fb.max_points) {
     // repeated generator set (a commitment call site of a prover/verifier): table lookups instead of buckets
     const uint64_t key = fb_hash(0x6D736D31ull, pts64, n * 64);
     auto hit = fb.tabs.find(key ^ ((uint64_t)n * 0xD6E8FEB86659FD93ull));
@@ -590,7 +590,7 @@ int bp_msm_batch(const uint8_t* pts64, const uint8_t* sc32, const uint32_t* offs
   if (!d_pts || !d_sc || !d_off || !d_out) return fail("device allocation failed");
   BP_CUDA(cudaMemcpyAsync(d_sc, sc32, T * 32, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(d_off, offsets, (nmsm + 1) * sizeof(u32), cudaMemcpyHostToDevice, g.stream));
-  if (fb.mode != 0 && maxlen <= fb.max_points && nmsm <= 65535 && T == nmsm * maxlen) {
+  if (fb_enabled() && maxlen <= fb.max_points && nmsm <= 65535 && T == nmsm * maxlen) {
     // every MSM of the batch over the SAME point list (A and S of a range proof, T1 and T2): one table serves all
     bool same = true;
     for (size_t j = 1; j < nmsm && same; j++) same = memcmp(pts64, pts64 + (size_t)offsets[j] * 64, maxlen * 64) == 0;

@@ -125,7 +125,7 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   // repeated generator set: L and R come from table lookups over the ORIGINAL generators (the s-vector form never
   // rewrites PA, which is what makes a per-set table usable in every round)
   const Affine* tab = nullptr;
-  if (fb.mode != 0 && 2 * n + 1 <= fb.max_points && n > 1) {
+  if (fb_enabled() && 2 * n + 1 <= fb.max_points && n > 1) {
     uint64_t key = fb_hash(fb_hash(fb_hash(0x69706131ull, u64_, 64), g64, n * 64), h64, n * 64);
     tab = fb_get(key, PA, 2 * n + 1);
   }
@@ -285,7 +285,7 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   // transcript checks of chunk i+1 (pinned, double-buffered staging so the uploads are truly asynchronous).
   // chunk length: measured on B200 at 8192 proofs -- table path 1024/2048/4096/8192 -> 26.5/22.3/19.8/24.4 ms (the
   // latency-bound kernels are paid per chunk, the host checks of the first chunk are exposed); bucket path: 2048 best
-  size_t CH = fb.mode != 0 ? (nproofs <= 4096 ? nproofs : 4096) : (nproofs < 4096 ? nproofs : 2048);
+  size_t CH = fb_enabled() ? (nproofs <= 4096 ? nproofs : 4096) : (nproofs < 4096 ? nproofs : 2048);
   if (getenv("BP_VERIFY_CHUNK")) { CH = (size_t)atol(getenv("BP_VERIFY_CHUNK")); if (CH > nproofs) CH = nproofs; if (CH == 0) CH = 1; }
   const size_t sc_bytes = CH * lay.nsc * 32, pt_bytes = CH * lay.npt * 64;
   uint8_t* stage = g.pinned_stage(2 * (sc_bytes + pt_bytes));
@@ -383,7 +383,7 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   // (V, A, S, T1, T2, u', P', L_j, R_j) still go through the bucket method.  Each equation is still checked exactly.
   const Affine* fbtab = nullptr;
   XYZZ *d_lanes = nullptr, *d_var = nullptr, *d_tot = nullptr;
-  if (fb.mode != 0) {
+  if (fb_enabled()) {
     uint64_t key = fb_hash(fb_hash(fb_hash(fb_hash(fb_hash(0x72707631ull, gs64, n * 64), hs64, n * 64), g64, 64), h64, 64), u64_, 64);
     fbtab = fb_get(key, table, lay.fixed);
     if (fbtab) {
