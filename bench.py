@@ -171,12 +171,12 @@ def run_ours(args):
     peak = macs.value / 1e12
     nominal = 148 * 64 * 1965.0 * 1e6 / 1e12
     roofline = {"bound": "imad", "kernel": "k_accumulate", "achieved": round(achieved, 3), "peak": round(peak, 3),
-                "unit": "T IMAD.WIDE (32x32+64 limb-MAC)/s", "frac": round(achieved / peak, 4), "traffic": 432352512,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch, ncu --set full (profiles/)",
+                "unit": "T IMAD.WIDE (32x32+64 limb-MAC)/s", "frac": round(achieved / peak, 4), "traffic": 1547183120,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch, ncu --set full with its default cache flush between replay passes, i.e. cold L2 (profiles/r1_accumulate_v3_ncu.txt); algorithmic bytes: 16.78 M gathers x (64 B point + 8 B entry) = 1.21 GB",
                 "peak_source": "measured in this process: bp_imad_peak, data-dependent IMAD.WIDE.U32 stream (SASS checked); "
                                "IMAD.WIDE issues at half the 32-bit IMAD rate on B200, with or without the carry predicate",
                 "nominal_imad32_peak": round(nominal, 2),
-                "ncu_pipe_fmaheavy_active_pct": 80.2,
+                "ncu_pipe_fmaheavy_active_pct": 80.4,
                 "window_bits": c, "windows": W, "glv": True, "mixed_adds_per_launch": ent.value, "kernel_ms": round(acc, 4),
                 "share_of_step": round(acc / med[6], 3),
                 "issued_limb_macs_per_launch": issued_macs,
