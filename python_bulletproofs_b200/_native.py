@@ -127,7 +127,15 @@ def pack_point(pt):
         return pack_xy(pt[0], pt[1])
     if getattr(pt, "curve", True) is None:
         return _ZERO64
-    return pack_xy(pt.x, pt.y)
+    pk = getattr(pt, "_pk", None)          # this package's Point caches its wire form (generators are packed on every call)
+    if pk is not None and pk[0] is pt.x and pk[1] is pt.y:
+        return pk[2]
+    b = pack_xy(pt.x, pt.y)
+    try:
+        pt._pk = (pt.x, pt.y, b)
+    except AttributeError:                 # foreign point types (fastecdsa) have no such slot
+        pass
+    return b
 
 
 def pack_points(pts):

@@ -610,6 +610,8 @@ __global__ void k_test_fp(int op, const Fp* a, const Fp* b, u32 n, Fp* out) {
     case 3: r = fp_inv(x); break;
     case 4: r = fp_neg(x); break;
     case 5: r = fp_sqr(x); break;
+    case 6: r = fp_inv_gcd(x); break;
+    case 7: r = fp_sqrt(fp_sqr(x)); r = fp_mul(r, r); break;      // (sqrt(x^2))^2 == x^2
     default: r = x;
   }
   st_fp(out + i, fp_canon(r));

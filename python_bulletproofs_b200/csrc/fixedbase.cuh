@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) k_fb_finish(const XYZZ* __restrict__ bloc
   }
   if (threadIdx.x == 0) {
     if (out_xyzz) st_xyzz(out_xyzz + m, acc);
-    if (out) st_affine(out + m, xyzz_to_affine(acc));
+    if (out) st_affine(out + m, xyzz_to_affine(acc, true));        // thread 0 of its own block
   }
 }
 

@@ -56,7 +56,7 @@ __global__ void k_xyzz_sum(const XYZZ* __restrict__ in, u32 count, Affine* __res
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   XYZZ acc = xyzz_identity();
   for (u32 i = 0; i < count; i++) { XYZZ v = ld_xyzz(in + i); xyzz_add_ni(acc, v); }
-  st_affine(out, xyzz_to_affine(acc));
+  st_affine(out, xyzz_to_affine(acc, true));
 }
 
 // Generator folding with a SHARED pair of scalars (divergence-free Shamir ladder):

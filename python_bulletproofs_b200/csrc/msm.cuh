@@ -57,7 +57,8 @@ inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
     if (nmsm <= 8) {
       // a few MSMs: measured on B200 (profiles/r1_window_sweep.txt).  Windows whose top digit keeps only a few
       // significant bits of the 128-bit halves make hot buckets, so only c = 10, 13, 16 are used: 128 mod c is 8, 11, 0.
-      int pick = n <= 8192.0 ? 10 : (n <= 131072.0 ? 13 : 16);
+      // (n <= 64: c = 5 -- 0.47-0.50 ms against 0.52-0.54 ms at c = 10: the 512-bucket reduction is pure latency there)
+      int pick = n <= 64.0 ? 5 : (n <= 8192.0 ? 10 : (n <= 131072.0 ? 13 : 16));
       cost = c == pick ? 0.0 : 1.0;
     } else {
       // many MSMs: everything is throughput; count field multiplications
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(32) k_finish(const XYZZ* __restrict__ acc_in, 
   if (threadIdx.x != 0) return;
   XYZZ acc = ld_xyzz(acc_in);
   if (out_xyzz) st_xyzz(out_xyzz, acc);
-  if (out) st_affine(out, xyzz_to_affine(acc));
+  if (out) st_affine(out, xyzz_to_affine(acc, true));
 }
 
 // one QUAD per msm: Horner over windows (c doublings each), then canonical affine (optionally XYZZ partials for sharding)
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(128) k_combine(const XYZZ* __restrict__ winsum
   }
   if (!active || role != 0) return;
   if (out_xyzz) st_xyzz(out_xyzz + m, acc);
-  if (out) st_affine(out + m, xyzz_to_affine(acc));
+  if (out) st_affine(out + m, xyzz_to_affine(acc, nmsm <= 2));
 }
 
 }  // namespace bp

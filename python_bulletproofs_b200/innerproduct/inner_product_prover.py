@@ -19,18 +19,24 @@ from .inner_product_verifier import Proof1, Proof2
 class NIProver:
     """Protocol 1 (inner_product_prover.py:11-45)."""
 
-    def __init__(self, g, h, u, P, c, a, b, group, seed=b"", _h_scale=None):
+    def __init__(self, g, h, u, P, c, a, b, group, seed=b"", _h_scale=None, _P_msm=None):
         assert len(g) == len(h) == len(a) == len(b)
         self.g, self.h, self.u, self.P, self.c, self.a, self.b = g, h, u, P, c, a, b
         self.group = group
         self.transcript = Transcript(seed)
         self._h_scale = _h_scale      # private: effective generators are _h_scale[i] * h[i] (never materialised)
+        self._P_msm = _P_msm          # private: P given as (points, scalars) of an MSM not yet evaluated (P may be None)
 
     def prove(self) -> Proof1:
         x = self.transcript.get_modp(self.group.q)
         self.transcript.add_number(x)
-        # P_new = P + (x*c)*u ; u_new = x*u
-        P_new, u_new = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
+        # P_new = P + (x*c)*u ; u_new = x*u.  When the caller passed P as an unevaluated MSM (range-proof prover), P_new
+        # is that MSM with one more term: one device pass instead of two (P itself is not part of the proof).
+        if self._P_msm is not None:
+            pts, scs = self._P_msm
+            P_new, u_new = PipSECP256k1.multiexp_batch([list(pts) + [self.u], [self.u]], [list(scs) + [x * self.c], [x]])
+        else:
+            P_new, u_new = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
         inner = FastNIProver2(self.g, self.h, u_new, P_new, self.a, self.b, self.group, self.transcript.digest,
                               _h_scale=self._h_scale)
         return Proof1(u_new, P_new, inner.prove(), self.transcript.digest)

@@ -13,16 +13,21 @@ from .curve import secp256k1
 class Point:
     IDENTITY_ELEMENT = None   # assigned below; also visible on instances (group.py:29 uses G.IDENTITY_ELEMENT)
 
-    __slots__ = ("x", "y", "curve")
+    __slots__ = ("x", "y", "curve", "_pk")
 
     def __init__(self, x, y, curve=secp256k1):
         self.x, self.y, self.curve = x, y, curve
+        self._pk = None        # (x, y, 64-byte wire form) cached by _native.pack_point; revalidated against x, y on use
 
     # -- boundary helpers
     @classmethod
     def from_bytes64(cls, b, off=0):
         xy = nat.unpack_xy(b, off)
-        return cls.IDENTITY_ELEMENT if xy is None else cls(xy[0], xy[1], secp256k1)
+        if xy is None:
+            return cls.IDENTITY_ELEMENT
+        pt = cls(xy[0], xy[1], secp256k1)
+        pt._pk = (pt.x, pt.y, bytes(b[off:off + 64]))
+        return pt
 
     def _is_identity(self):
         return self.curve is None

@@ -116,12 +116,12 @@ def prove(vs, n, g, h, gs, hs, gammas, u, group, transcript: Transcript):
     mu = (alpha + rho * xv) % q
     # hsp_i = y^-i * hs_i (rangeproof_prover.py:77) is never materialised: its scalars are folded into the MSMs
     yinv_pow = inverse_powers(yv, nm, q)
-    # P - mu*h = A + x*S + sum(-z * gs_i) + sum((z*y^i + zz_i) * y^-i * hs_i) - mu*h : one MSM
-    P_inner = PipSECP256k1.multiexp(
-        [A, S, h] + gs + hs,
-        [1, xv, -mu] + [-zv] * nm + [(zv + zz[i] * yinv_pow[i]) % q for i in range(nm)])
-    inner = NIProver(gs, hs, u, P_inner, ModP(t_hat, q), [ModP(v, q) for v in ls], [ModP(v, q) for v in rs], group,
-                     _h_scale=yinv_pow)
+    # P - mu*h = A + x*S + sum(-z * gs_i) + sum((z*y^i + zz_i) * y^-i * hs_i) - mu*h  (rangeproof_prover.py:78-86) is
+    # handed to the IPA prover as an unevaluated MSM: Protocol 1 only needs P + (x1*t_hat)*u, one device pass.
+    inner = NIProver(gs, hs, u, None, ModP(t_hat, q), [ModP(v, q) for v in ls], [ModP(v, q) for v in rs], group,
+                     _h_scale=yinv_pow,
+                     _P_msm=([A, S, h] + gs + hs,
+                             [1, xv, -mu] + [-zv] * nm + [(zv + zz[i] * yinv_pow[i]) % q for i in range(nm)]))
     return Proof(ModP(taux, q), ModP(mu, q), ModP(t_hat, q), T1, T2, A, S, inner.prove(), transcript.digest)
 
 

@@ -46,6 +46,17 @@ def test_fp_inv():
     assert got == [pow(x, -1, P) for x in a]
 
 
+def test_fp_inv_binary_gcd_and_sqrt():
+    """fp_inv_gcd (single-thread tails) on canonical, lazy (>= p) and degenerate inputs; (sqrt(x^2))^2 == x^2."""
+    rng = random.Random(6)
+    a = [0, P, 1, 2, 3, P - 1, P - 2, P + 1, 2 ** 256 - 1, 977, 2 ** 255, 2 ** 32 + 977, (P + 1) // 2] + \
+        [rng.getrandbits(256) for _ in range(600)] + [1 << k for k in range(0, 256, 7)]
+    got = _un(call_test("bp_test_fp", 6, _le(a), _le(a), len(a), 32))
+    assert got == [pow(x % P, -1, P) if x % P else 0 for x in a]
+    got = _un(call_test("bp_test_fp", 7, _le(a), _le(a), len(a), 32))
+    assert got == [x * x % P for x in a]
+
+
 @pytest.mark.parametrize("dev", [0, 1])
 @pytest.mark.parametrize("op,fn", [(0, lambda a, b: a * b % Q), (1, lambda a, b: (a + b) % Q), (2, lambda a, b: (a - b) % Q),
                                    (4, lambda a, b: (-a) % Q)])
