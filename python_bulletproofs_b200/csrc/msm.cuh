@@ -248,6 +248,9 @@ BP_DI const Affine* entry_point_ptr(const Affine* __restrict__ points, const u32
 #ifndef BP_ACC_MINB
 #define BP_ACC_MINB 4
 #endif
+#ifndef BP_ACC_PIPELINE
+#define BP_ACC_PIPELINE 0   // 1: next point loaded into registers under the current addition -- measured slower (2.035 vs 1.984 ms: 128 registers + spill); L2 prefetch only
+#endif
 __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* __restrict__ points, const u32* __restrict__ point_idx, const Affine* __restrict__ phi,
                                                     const u32* __restrict__ bucket_start, const uint2* __restrict__ entries,
                                                     const u32* __restrict__ gs_ptr, const u32* __restrict__ ge_ptr, u32 CL,
@@ -264,6 +267,10 @@ __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* _
   u32 s = __ldg(bucket_start + b), e = __ldg(bucket_start + b + 1);
   bool first = true;
   XYZZ acc = xyzz_identity();
+#if BP_ACC_PIPELINE
+  // software pipeline: the point of entry i+1 is loaded into registers while the mixed addition of entry i runs
+  Affine pnext = ld_affine(entry_point_ptr(points, point_idx, phi, ent.x));
+#endif
   // ONE flat loop with the same trip count in every lane: the warp stays converged on the mixed add;
   // only the short flush at a bucket boundary diverges.
   for (u32 i = cs; i < ce; i++) {
@@ -276,11 +283,20 @@ __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* _
       s = e; e = __ldg(bucket_start + b + 1);
     }
     u32 cur = ent.x;
+#if BP_ACC_PIPELINE
+    Affine p = pnext;
+    if (i + 1 < ce) {
+      ent = __ldg(entries + i + 1);
+      pnext = ld_affine(entry_point_ptr(points, point_idx, phi, ent.x));
+      if (i + 2 < ce) asm volatile("prefetch.global.L2 [%0];" ::"l"(entry_point_ptr(points, point_idx, phi, __ldg(&entries[i + 2].x))));
+    }
+#else
     if (i + 1 < ce) {
       ent = __ldg(entries + i + 1);
       asm volatile("prefetch.global.L2 [%0];" ::"l"(entry_point_ptr(points, point_idx, phi, ent.x)));
     }
     Affine p = ld_affine(entry_point_ptr(points, point_idx, phi, cur));
+#endif
     if (cur >> 31) p.y = fp_neg(p.y);
     xyzz_madd(acc, p);
   }
