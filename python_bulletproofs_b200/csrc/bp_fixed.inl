@@ -6,7 +6,8 @@
 struct FbEntry { Affine* tab; size_t n; size_t bytes; unsigned long long stamp; };
 struct FbCache {
   std::map<uint64_t, FbEntry> tabs;
-  std::map<uint64_t, unsigned> seen;
+  std::map<uint64_t, unsigned> seen, seen16;
+  std::map<uint64_t, FbEntry> tabs16;       // 16-bit-window tables (batch verifier), built from the byte tables
   size_t bytes = 0, cap = (size_t)24 << 30;
   size_t max_points = 4200;        // largest point set that gets a table (2049 of a 1024-wide IPA, 2 * 2048 + 1 commitments)
   int mode = 1;
@@ -73,6 +74,30 @@ static const Affine* fb_get(uint64_t key, const Affine* d_pts, size_t n) {
   return tab;
 }
 
+// 16-bit-window table of the same point set (n <= 512 points: 67 MB each), derived from its byte table `tab8`; built one
+// sighting after the byte table in mode 1.  nullptr when absent (the caller keeps using the byte table).
+static const Affine* fb_get16(uint64_t key, const Affine* tab8, size_t n) {
+  if (!tab8 || n == 0 || n > 512) return nullptr;
+  key ^= (uint64_t)n * 0xD6E8FEB86659FD93ull;
+  auto it = fb.tabs16.find(key);
+  if (it != fb.tabs16.end() && it->second.n == n) { it->second.stamp = ++fb.clock; return it->second.tab; }
+  if (fb.mode == 1) {
+    if (fb.seen16.size() > 8192) fb.seen16.clear();
+    if (++fb.seen16[key] < 2) return nullptr;
+  }
+  const size_t bytes = n * (size_t)BP_FB16_WINDOWS * BP_FB16_ENTRIES * sizeof(Affine);
+  if (fb.bytes + bytes > fb.cap) return nullptr;                  // never evict byte tables for this
+  Affine* tab = nullptr;
+  if (cudaMalloc((void**)&tab, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  const size_t threads = n * BP_FB16_WINDOWS * 256;
+  k_fb_build16<<<(unsigned)((threads + 127) / 128), 128, 0, g.stream>>>(tab8, (u32)n, tab);
+  if (cudaGetLastError() != cudaSuccess) { cudaFree(tab); return nullptr; }
+  fb.tabs16[key] = FbEntry{tab, n, bytes, ++fb.clock};
+  fb.bytes += bytes;
+  fb.builds++;
+  return tab;
+}
+
 // nmsm table MSMs on g.stream: terms of MSM m are [offsets[m], offsets[m+1]) (device array), or [0, single_n) when
 // offsets == nullptr (then nmsm must be 1); max_terms bounds the longest MSM.
 static int fb_msm_run(const Affine* tab, const u32* d_idx, const Fq* d_sc, const u32* d_offsets, u32 nmsm, size_t max_terms,
@@ -92,6 +117,8 @@ static int fb_msm_run(const Affine* tab, const u32* d_idx, const Fq* d_sc, const
 
 static void fb_release_all() {
   for (auto& kv : fb.tabs) cudaFree(kv.second.tab);
+  for (auto& kv : fb.tabs16) cudaFree(kv.second.tab);
+  fb.tabs16.clear(); fb.seen16.clear();
   fb.tabs.clear(); fb.seen.clear(); fb.bytes = 0;
   fb.scratch.release(); fb.blockpart.release();
 }

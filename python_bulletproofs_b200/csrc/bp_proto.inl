@@ -381,11 +381,12 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   // Repeated generator set: its terms (2n+1 of E4, n+4 of E2, ...: 202 of the 220 terms of a 64-bit proof) are read from
   // the fixed-base table, 32 lookups each with no doublings and no bucket reduction; only the ~21 proof-specific terms
   // (V, A, S, T1, T2, u', P', L_j, R_j) still go through the bucket method.  Each equation is still checked exactly.
-  const Affine* fbtab = nullptr;
+  const Affine *fbtab = nullptr, *fbtab16 = nullptr;
   XYZZ *d_lanes = nullptr, *d_var = nullptr, *d_tot = nullptr;
   if (fb_enabled()) {
     uint64_t key = fb_hash(fb_hash(fb_hash(fb_hash(fb_hash(0x72707631ull, gs64, n * 64), hs64, n * 64), g64, 64), h64, 64), u64_, 64);
     fbtab = fb_get(key, table, lay.fixed);
+    fbtab16 = fb_get16(key, fbtab, lay.fixed);
     if (fbtab) {
       d_lanes = (XYZZ*)g.ws_fb_lanes.ensure(4 * CH * (128 + 16) * sizeof(XYZZ));
       d_var = (XYZZ*)g.ws_fb_var.ensure(2 * 4 * CH * sizeof(XYZZ));
@@ -396,8 +397,12 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   const u32 bd = n < 32 ? 32 : (u32)n;
   const size_t smem = (2 * L + 1 + bd) * sizeof(Fq);
   int chunk_no = 0;
-  for (chunk_lo = 0; chunk_lo < nproofs; chunk_lo += CH, chunk_no++) {
-    const size_t chunk_hi = chunk_lo + CH < nproofs ? chunk_lo + CH : nproofs, cn = chunk_hi - chunk_lo;
+  // chunk lengths: CH, except that a large batch on the table path starts with two short chunks (1/4 and 3/4 of CH) -- the
+  // host checks of the first chunk are the only ones not hidden behind GPU work, so the GPU should start early
+  const bool ramp = fb_enabled() && nproofs >= 2 * CH && CH >= 1024 && !getenv("BP_VERIFY_CHUNK");
+  size_t this_len = ramp ? CH / 4 : CH;
+  for (chunk_lo = 0; chunk_lo < nproofs; chunk_lo += this_len, this_len = (ramp && chunk_no == 0) ? CH - CH / 4 : CH, chunk_no++) {
+    const size_t chunk_hi = chunk_lo + this_len < nproofs ? chunk_lo + this_len : nproofs, cn = chunk_hi - chunk_lo;
     cur = chunk_no & 1;
     if (chunk_no >= 2) BP_CUDA(cudaEventSynchronize(g.stage_ev[cur]));       // staging buffer free again?
     auto t_h0 = std::chrono::steady_clock::now();
@@ -422,7 +427,8 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
     k_rp_expand<<<(unsigned)cn, bd, smem, g.stream>>>(psc, d_inv, lay, (u32)cn, tsc, tidx, d_off);
     if (fbtab) {
       const u32 nm = (u32)(4 * cn);
-      k_rp_lookup<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
+      if (fbtab16) k_rp_lookup16<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
+      else k_rp_lookup<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
       g.msm_skip_below = lay.fixed;                                        // bucket pass: proof-specific terms only
       int rc = msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, nm, (lay.npt + 2 + 3) / 4, nullptr, d_var);
       g.msm_skip_below = 0;

@@ -150,6 +150,53 @@ __global__ void __launch_bounds__(256) k_fb_finish(const XYZZ* __restrict__ bloc
   }
 }
 
+// ---- 16-bit windows for the batch verifier's generator table ------------------------------------------------------------
+// T16[g][w][d] = d * 2^(16w) * P_g, d = 1..65535 (16 windows, 67 MB per point: 8.9 GB for the 133 points of a 64-bit range
+// proof -- HBM3e capacity spent to halve the lookups per term).  Built from the byte table: d = 256*hi + lo is
+// T8[g][2w+1][hi] + T8[g][2w][lo], one affine addition per entry with the 255 inversions of a (g, w, hi) row shared by
+// Montgomery's trick (running products parked in the x half of the output slots).  The two summands are distinct multiples
+// of P below q, so neither the doubling nor the cancelling case of the addition can occur.
+#define BP_FB16_WINDOWS 16
+#define BP_FB16_ENTRIES 65535
+BP_DI size_t fb_index16(u32 gi, u32 w, u32 d) { return ((size_t)gi * BP_FB16_WINDOWS + w) * BP_FB16_ENTRIES + (d - 1); }
+
+__global__ void __launch_bounds__(128) k_fb_build16(const Affine* __restrict__ tab8, u32 n, Affine* __restrict__ tab16) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;          // (g, w, hi)
+  if (t >= n * BP_FB16_WINDOWS * 256) return;
+  const u32 hi = t & 255u, w = (t >> 8) % BP_FB16_WINDOWS, gi = (t >> 8) / BP_FB16_WINDOWS;
+  const Affine* lo_row = tab8 + fb_index(gi, 2 * w, 1);         // lo_row[lo - 1] = lo * 2^(16w) * P
+  Affine* out = tab16 + fb_index16(gi, w, 256 * hi + (hi ? 0 : 1));   // first entry of this row: d = 256*hi (hi > 0) or d = 1
+  if (hi == 0) {
+    for (u32 lo = 1; lo < 256; lo++) st_affine(out + lo - 1, ld_affine(lo_row + lo - 1));
+    return;
+  }
+  const Affine A = ld_affine(tab8 + fb_index(gi, 2 * w + 1, hi));
+  st_affine(out, A);                                             // lo = 0
+  if (affine_is_identity(A)) {                                   // identity generator: every multiple is the identity
+    for (u32 lo = 1; lo < 256; lo++) st_affine(out + lo, A);
+    return;
+  }
+  Fp pre = fp_one();
+  for (u32 lo = 1; lo < 256; lo++) {
+    Fp dx = fp_sub(ld_fp(&lo_row[lo - 1].x), A.x);
+    pre = fp_mul(pre, dx);
+    st_fp(&out[lo].x, pre);
+  }
+  Fp inv = fp_inv(pre);
+  for (u32 lo = 255; lo >= 1; lo--) {
+    const Affine B = ld_affine(lo_row + lo - 1);
+    Fp dx = fp_sub(B.x, A.x);
+    Fp prev = lo > 1 ? ld_fp_coherent(&out[lo - 1].x) : fp_one();
+    Fp dxi = fp_mul(inv, prev);                                  // 1 / (xB - xA)
+    inv = fp_mul(inv, dx);
+    Fp lam = fp_mul(fp_sub(B.y, A.y), dxi);
+    Fp x3 = fp_sub(fp_sub(fp_sqr(lam), A.x), B.x);
+    Fp y3 = fp_sub(fp_mul(lam, fp_sub(A.x, x3)), A.y);
+    Affine r; r.x = fp_canon(x3); r.y = fp_canon(y3);
+    st_affine(out + lo, r);
+  }
+}
+
 // ---- throughput form for batches of MSMs whose terms mix table rows and other points (batch verifier) ----------------
 // Step 1: one WARP per MSM, lane l owns byte-window l: for every term with a table row (idx < nfixed) one lookup and one
 // mixed addition per lane; terms with idx >= nfixed belong to the caller's other pass and are skipped (warp-uniform).

@@ -211,6 +211,43 @@ __global__ void __launch_bounds__(256) k_rp_lookup(const Affine* __restrict__ ta
   }
   st_xyzz(part + ((size_t)(4 * p + e) * 128 + 32 * s + lane), acc);
 }
+// Same with the 16-bit table: lane l owns window l & 15 of the (l >> 4)-th of two terms taken per step, so a term costs 16
+// lookups; the table lives in HBM (8.9 GB), hence the next entry is loaded into registers under the current addition.
+__global__ void __launch_bounds__(256) k_rp_lookup16(const Affine* __restrict__ tab16, const u32* __restrict__ idx, const Fq* __restrict__ sc,
+                                                     const u32* __restrict__ offsets, u32 nproofs, u32 nfixed, XYZZ* __restrict__ part) {
+  const u32 p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p >= nproofs) return;
+  const u32 e = warp < 4 ? 3u : (warp < 6 ? 1u : (warp == 6 ? 0u : 2u));
+  const u32 nw = e == 3 ? 4u : (e == 1 ? 2u : 1u);
+  const u32 s = e == 3 ? warp : (e == 1 ? warp - 4 : 0u);
+  const u32 lo = __ldg(offsets + 4 * p + e), hi = __ldg(offsets + 4 * p + e + 1);
+  const u32 win = lane & 15u, sub = lane >> 4;
+  XYZZ acc = xyzz_identity();
+  Affine cur; cur.x = fp_zero(); cur.y = fp_zero();
+  bool have = false;
+  for (u32 t = lo + 2 * s + sub; ; t += 2 * nw) {
+    // fetch the entry of term t (if any) while the previous one is being added
+    Affine nxt; nxt.x = fp_zero(); nxt.y = fp_zero();
+    bool nhave = false;
+    const bool in = t < hi;
+    if (in) {
+      const u32 gi = __ldg(idx + t);
+      if (gi < nfixed) {
+        const u32* kw = reinterpret_cast<const u32*>(sc + t);
+        Fq k;
+#pragma unroll
+        for (int i = 0; i < 8; i++) k.v[i] = __ldg(kw + i);
+        k = fq_reduce(k);
+        const u32 d = (k.v[win >> 1] >> (16 * (win & 1))) & 0xFFFFu;
+        if (d) { nxt = ld_affine(tab16 + fb_index16(gi, win, d)); nhave = true; }
+      }
+    }
+    if (have) xyzz_madd_ni(acc, cur);
+    cur = nxt; have = nhave;
+    if (!__any_sync(BP_FULL_MASK, in)) break;          // both term slots of the warp are past the end
+  }
+  st_xyzz(part + ((size_t)(4 * p + e) * 128 + 32 * s + lane), acc);
+}
 // Fold, step 1 (throughput form): one thread adds 8 consecutive lane sums; 16 group sums per equation slot
 __global__ void __launch_bounds__(128) k_rp_fold8(const XYZZ* __restrict__ part, u32 nmsm, XYZZ* __restrict__ grp) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;          // (m, group of 8)
