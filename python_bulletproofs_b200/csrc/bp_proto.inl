@@ -359,17 +359,20 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
       host_ok[p] = verdict;
     }
   };
-  // ---- device buffers (sized for one chunk) and the shared generator table --------------------------
-  size_t Tc = CH * lay.tpp, npts = lay.fixed + CH * lay.npt;
+  // ---- device buffers and the shared generator table -----------------------------------------------
+  // The per-chunk inputs (scalar records, proof points, inverses, expanded terms) are double-buffered: chunk i+1 is
+  // uploaded, inverted and expanded on a side stream while chunk i is still in its lookups / bucket pass on the main one.
+  size_t Tc = CH * lay.tpp, npts = lay.fixed + 2 * CH * lay.npt;
   Affine* table = (Affine*)g.ws_pts.ensure(npts * sizeof(Affine));
-  Fq* psc = (Fq*)g.ws_small.ensure(CH * lay.nsc * sizeof(Fq));
-  Fq* tsc = (Fq*)g.ws_terms_sc.ensure(Tc * sizeof(Fq));
-  u32* tidx = (u32*)g.ws_idx.ensure(Tc * sizeof(u32));
-  u32* d_off = (u32*)g.ws_off.ensure((4 * CH + 1) * sizeof(u32));
+  Fq* psc2 = (Fq*)g.ws_small.ensure(2 * CH * lay.nsc * sizeof(Fq));
+  Fq* tsc2 = (Fq*)g.ws_terms_sc.ensure(2 * Tc * sizeof(Fq));
+  u32* tidx2 = (u32*)g.ws_idx.ensure(2 * Tc * sizeof(u32));
+  u32* d_off2 = (u32*)g.ws_off.ensure(2 * (4 * CH + 1) * sizeof(u32));
   Affine* d_res = (Affine*)g.ws_out.ensure(4 * CH * sizeof(Affine));
   uint8_t* d_acc = (uint8_t*)g.ws_misc.ensure(nproofs);
-  Fq* d_inv = (Fq*)g.ws_a.ensure(CH * (lay.L + 1) * sizeof(Fq));
-  if (!table || !psc || !tsc || !tidx || !d_off || !d_res || !d_acc || !d_inv) return fail("device allocation failed");
+  Fq* d_inv2 = (Fq*)g.ws_a.ensure(2 * CH * (lay.L + 1) * sizeof(Fq));
+  if (!table || !psc2 || !tsc2 || !tidx2 || !d_off2 || !d_res || !d_acc || !d_inv2) return fail("device allocation failed");
+  if (g.ensure_aux()) return 1;
   if (g.ensure_stage_events()) return 1;
   BP_CUDA(cudaMemcpyAsync(table, gs64, n * 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + n, hs64, n * 64, cudaMemcpyHostToDevice, g.stream));
@@ -418,13 +421,21 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
     }
     if (getenv("BP_VERIFY_TIMING")) fprintf(stderr, "chunk %d: host %.3f ms (%u threads)\n", chunk_no,
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h0).count(), nthreads);
-    // device: scalar expansion, one batched MSM over the 4*cn equations, accept bits
-    BP_CUDA(cudaMemcpyAsync(table + lay.fixed, hpt_buf[cur], cn * lay.npt * 64, cudaMemcpyHostToDevice, g.stream));
-    BP_CUDA(cudaMemcpyAsync(psc, hsc_buf[cur], cn * lay.nsc * 32, cudaMemcpyHostToDevice, g.stream));
-    BP_CUDA(cudaEventRecord(g.stage_ev[cur], g.stream));
-    k_reduce_scalars<<<(unsigned)((cn * lay.nsc + 127) / 128), 128, 0, g.stream>>>(psc, (u32)(cn * lay.nsc));
-    k_rp_invert<<<(unsigned)((cn + 63) / 64), 64, 0, g.stream>>>(psc, lay, (u32)cn, d_inv);
-    k_rp_expand<<<(unsigned)cn, bd, smem, g.stream>>>(psc, d_inv, lay, (u32)cn, tsc, tidx, d_off);
+    // side stream: upload, invert, expand into the buffers of parity `cur` (free once the main stream is done with
+    // chunk i-2); main stream: lookups / bucket pass / accept bits
+    Fq* psc = psc2 + (size_t)cur * CH * lay.nsc; Fq* d_inv = d_inv2 + (size_t)cur * CH * (lay.L + 1);
+    Fq* tsc = tsc2 + (size_t)cur * Tc; u32* tidx = tidx2 + (size_t)cur * Tc; u32* d_off = d_off2 + (size_t)cur * (4 * CH + 1);
+    const u32 pt_base = lay.fixed + (u32)(cur * CH * lay.npt);
+    if (chunk_no == 0) { BP_CUDA(cudaEventRecord(g.aux_free[0], g.stream)); BP_CUDA(cudaEventRecord(g.aux_free[1], g.stream)); }   // generator table ready
+    BP_CUDA(cudaStreamWaitEvent(g.aux_stream, g.aux_free[cur], 0));
+    BP_CUDA(cudaMemcpyAsync(table + pt_base, hpt_buf[cur], cn * lay.npt * 64, cudaMemcpyHostToDevice, g.aux_stream));
+    BP_CUDA(cudaMemcpyAsync(psc, hsc_buf[cur], cn * lay.nsc * 32, cudaMemcpyHostToDevice, g.aux_stream));
+    BP_CUDA(cudaEventRecord(g.stage_ev[cur], g.aux_stream));
+    k_reduce_scalars<<<(unsigned)((cn * lay.nsc + 127) / 128), 128, 0, g.aux_stream>>>(psc, (u32)(cn * lay.nsc));
+    k_rp_invert<<<(unsigned)((cn + 63) / 64), 64, 0, g.aux_stream>>>(psc, lay, (u32)cn, d_inv);
+    k_rp_expand<<<(unsigned)cn, bd, smem, g.aux_stream>>>(psc, d_inv, lay, (u32)cn, pt_base, tsc, tidx, d_off);
+    BP_CUDA(cudaEventRecord(g.aux_ready[cur], g.aux_stream));
+    BP_CUDA(cudaStreamWaitEvent(g.stream, g.aux_ready[cur], 0));
     if (fbtab) {
       const u32 nm = (u32)(4 * cn);
       if (fbtab16) k_rp_lookup16<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
@@ -441,6 +452,7 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
       if (msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, (u32)(4 * cn), lay.tpp / 4, d_res, nullptr)) return 1;
       k_rp_accept<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)cn, d_acc + chunk_lo);
     }
+    BP_CUDA(cudaEventRecord(g.aux_free[cur], g.stream));
   }
   BP_CUDA(cudaMemcpyAsync(accept, d_acc, nproofs, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));

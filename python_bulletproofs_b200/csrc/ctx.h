@@ -88,6 +88,22 @@ struct Ctx {
     stage_cap = bytes;
     return stage_p;
   }
+  // side stream of the batch verifier: per-chunk upload / inversion / expansion under the previous chunk's MSM work
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_ready[2] = {nullptr, nullptr}, aux_free[2] = {nullptr, nullptr};
+  int ensure_aux() {
+    if (ensure_stage_events()) return 1;
+    if (!aux_stream) {   // high priority: its kernels are short latency chains that should slip in between the blocks of the main stream
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return fail("stream creation failed");
+    }
+    for (int i = 0; i < 2; i++) {
+      if (!aux_ready[i] && cudaEventCreateWithFlags(&aux_ready[i], cudaEventDisableTiming) != cudaSuccess) return fail("event creation failed");
+      if (!aux_free[i] && cudaEventCreateWithFlags(&aux_free[i], cudaEventDisableTiming) != cudaSuccess) return fail("event creation failed");
+    }
+    return 0;
+  }
   int ensure_stage_events() {
     for (int i = 0; i < 2; i++)
       if (!stage_ev[i] && cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming) != cudaSuccess) return fail("event creation failed");

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(64) k_rp_invert(const Fq* __restrict__ psc, Rp
 
 // One block per proof, n threads (n >= 32 rounded up by the launcher; extra threads idle).
 // Writes the proof's tpp term scalars / point indices and its 4 MSM offsets.
-__global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, const Fq* __restrict__ inv, RpLayout lay, u32 nproofs, Fq* __restrict__ tsc,
+__global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, const Fq* __restrict__ inv, RpLayout lay, u32 nproofs, u32 pt_base, Fq* __restrict__ tsc,
                                                     u32* __restrict__ tidx, u32* __restrict__ offsets) {
   extern __shared__ Fq sm[];      // [0..L) x_j (mont) | [L..2L) x_j^-1 (mont) | 2L: y^-1 (mont) | 2L+1 .. : reduction scratch (blockDim)
   const u32 p = blockIdx.x, i = threadIdx.x, n = lay.n, L = lay.L;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
   }
   const Fq sum_y = red[0];
   const size_t tb = (size_t)p * lay.tpp;                 // term base of this proof
-  const u32 pb = lay.fixed + p * lay.npt;                // point base of this proof
+  const u32 pb = pt_base + p * lay.npt;                  // point base of this proof (pt_base >= lay.fixed: after the generators)
   const u32 iG = 2 * n, iH = 2 * n + 1, iU = 2 * n + 2, iGsum = 2 * n + 3, iHsum = 2 * n + 4;
   const u32 o1 = 0, o2 = 5, o3 = 5 + n + 7, o4 = o3 + 2;
   if (i < n) {
