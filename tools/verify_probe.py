@@ -13,11 +13,13 @@ hs = [elliptic_hash(str(i).encode() + pre + b"1", secp256k1) for i in range(n)]
 g1, h1, u1 = (elliptic_hash(pre + s, secp256k1) for s in (b"2", b"3", b"4"))
 rng = random.Random(5)
 Vl, pl = [], []
-for i in range(32):
+DISTINCT = int(os.environ.get("BP_PROBE_DISTINCT", "32"))      # distinct proofs, tiled up to `total`
+for i in range(DISTINCT):
     vv = ModP(rng.getrandbits(64), q); gm = mod_hash(b"gamma%d" % i, q)
     Vl.append(commitment(g1, h1, vv, gm)); pl.append(NIRangeProver(vv, n, g1, h1, gs, hs, gm, u1, secp256k1, b"p%d" % i).prove())
 total = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-batch = PackedBatch.from_proofs((Vl * (total // 32)), (pl * (total // 32)), n)
+batch = PackedBatch.from_proofs((Vl * (total // DISTINCT)), (pl * (total // DISTINCT)), n)
+print("%d proofs, %d distinct" % (total, DISTINCT), flush=True)
 for it in range(3):
     t = time.perf_counter(); acc = verify_packed(batch, g1, h1, gs, hs, u1); dt = time.perf_counter() - t
     print("verify_packed %d: %.2f ms  window c=%d" % (total, dt * 1e3, nat.load().bp_msm_last_window()), flush=True)
