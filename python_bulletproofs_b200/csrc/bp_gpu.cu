@@ -76,7 +76,6 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     return fail("workspace allocation failed");
 
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
-  BP_CUDA(cudaMemsetAsync(cursor, 0, (nb + 1) * sizeof(u32), st));
   if (prof) cudaEventRecord(g.ev[0], st);
   k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count, g.msm_skip_below ? point_idx : nullptr, g.msm_skip_below);
   if (prof) cudaEventRecord(g.ev[1], st);
@@ -84,7 +83,8 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
   k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
   if (prof) cudaEventRecord(g.ev[2], st);
-  k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, start, cursor, entries);
+  BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));   // cursors start at the bucket offsets
+  k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, cursor, entries);
   if (prof) cudaEventRecord(g.ev[3], st);
   if (g.pts_ready) { BP_CUDA(cudaStreamWaitEvent(st, g.pts_ready, 0)); g.pts_ready = nullptr; }   // points may still be uploading
   k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
@@ -190,14 +190,14 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
 
   if (g.profiling) cudaEventRecord(g.ev[0], st);
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
-  BP_CUDA(cudaMemsetAsync(cursor, 0, (nb + 1) * sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(big, 0, W * (big_cap + 2) * sizeof(u32), st));
   k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
   k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, nullptr, 1, sh, digits, count, nullptr, 0);
   k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
   k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
   k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
-  k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, nullptr, 1, sh, start, cursor, entries);
+  BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+  k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, nullptr, 1, sh, cursor, entries);
   BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));
   BP_CUDA(cudaEventRecord(g.pe_prep, st));
   BP_CUDA(cudaStreamWaitEvent(g.ps_acc[0], g.pe_prep, 0));

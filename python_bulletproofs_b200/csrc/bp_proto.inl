@@ -445,8 +445,8 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
       g.msm_skip_below = 0;
       if (rc) return 1;
       XYZZ* d_grp = d_lanes + (size_t)4 * CH * 128;
-      k_rp_fold8<<<(nm * 16 + 127) / 128, 128, 0, g.stream>>>(d_lanes, nm, d_grp);
-      k_rp_fold<<<(nm + 3) / 4, 128, 0, g.stream>>>(d_grp, d_var, nm, d_tot);
+      k_rp_fold8<<<(nm * 16 + 127) / 128, 128, 0, g.stream>>>(d_lanes, nm, (u32)cn, d_grp);
+      k_rp_fold<<<(nm + 3) / 4, 128, 0, g.stream>>>(d_grp, d_var, nm, (u32)cn, d_tot);
       k_rp_accept_xyzz<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_tot, (u32)cn, d_acc + chunk_lo);
     } else {
       if (msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, (u32)(4 * cn), lay.tpp / 4, d_res, nullptr)) return 1;

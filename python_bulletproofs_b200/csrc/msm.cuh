@@ -141,10 +141,10 @@ __global__ void __launch_bounds__(256) k_digits(const Fq* __restrict__ scalars, 
   }
 }
 
-// one thread per sub-term: entry = {term | phi-flag << 30 | sign << 31, bucket}
+// one thread per sub-term: entry = {term | phi-flag << 30 | sign << 31, bucket}; cursor[b] starts at bucket_start[b], so the
+// atomic hands out absolute slots (one L2 transaction less per entry than offset + separate base load)
 __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits, u32 T, const u32* __restrict__ offsets, u32 nmsm,
-                                                 MsmShape sh, const u32* __restrict__ bucket_start, u32* __restrict__ cursor,
-                                                 uint2* __restrict__ entries) {
+                                                 MsmShape sh, u32* __restrict__ cursor, uint2* __restrict__ entries) {
   u32 st = blockIdx.x * blockDim.x + threadIdx.x;
   if (st >= 2 * T) return;
   u32 t = st >> 1;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits,
     if (sd != 0 && lane == leader) base = atomicAdd(cursor + b, (u32)__popc(peers));
     base = __shfl_sync(act, base, leader);
     if (sd == 0) continue;
-    u32 pos = __ldg(bucket_start + b) + base + (u32)__popc(peers & ((1u << lane) - 1));
+    u32 pos = base + (u32)__popc(peers & ((1u << lane) - 1));     // cursor[] was initialised to bucket_start[]: absolute slot
     entries[pos] = make_uint2(t | ((st & 1u) << 30) | (sd < 0 ? 0x80000000u : 0u), b);
   }
 }

@@ -98,16 +98,20 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
     __syncthreads();
   }
   const Fq sum_y = red[0];
-  const size_t tb = (size_t)p * lay.tpp;                 // term base of this proof
+  // Terms and MSMs are laid out KIND-MAJOR: all E1 equations of the chunk first, then all E2, E3, E4 (MSM index
+  // m = e * nproofs + p).  Warps of the thread-per-unit reduction / Horner kernels then hold equations of one kind, so the
+  // light ones (E3: one term, E2, E1) no longer wait for a heavy E4 neighbour in the same warp.
+  const size_t len1 = 5, len2 = n + 7, len3 = 2, len4 = 2 * n + 2 + 2 * L;
+  const size_t tb1 = (size_t)p * len1, tb2 = (size_t)nproofs * len1 + (size_t)p * len2,
+               tb3 = (size_t)nproofs * (len1 + len2) + (size_t)p * len3, tb4 = (size_t)nproofs * (len1 + len2 + len3) + (size_t)p * len4;
   const u32 pb = pt_base + p * lay.npt;                  // point base of this proof (pt_base >= lay.fixed: after the generators)
   const u32 iG = 2 * n, iH = 2 * n + 1, iU = 2 * n + 2, iGsum = 2 * n + 3, iHsum = 2 * n + 4;
-  const u32 o1 = 0, o2 = 5, o3 = 5 + n + 7, o4 = o3 + 2;
   if (i < n) {
     // ---- E2, generator terms
     Fq two_i = fq_zero(); if (i < 256) two_i.v[i >> 5] = 1u << (i & 31);   // 2^i, standard form (host enforces n <= 128)
     two_i = fq_reduce(two_i);
     Fq hs_sc = fq_from_mont(fq_mont(fq_mont(z2m, fq_to_mont(two_i)), yii));              // z^2 * 2^i * y^-i  (z*hs_i is in Hsum)
-    st_fq(tsc + tb + o2 + 2 + i, hs_sc);              tidx[tb + o2 + 2 + i] = n + i;         // hs_i
+    st_fq(tsc + tb2 + 2 + i, hs_sc);              tidx[tb2 + 2 + i] = n + i;         // hs_i
     // ---- E4, generator terms: s_i = prod_j (bit_j(i) ? x_j : x_j^-1), bit j counted from the MSB
     Fq s = R1, sinv = R1;
     for (u32 j = 0; j < L; j++) {
@@ -115,13 +119,13 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
       s = fq_mont(s, bit ? xm[j] : xim[j]);
       sinv = fq_mont(sinv, bit ? xim[j] : xm[j]);
     }
-    st_fq(tsc + tb + o4 + i, fq_mont(a, s));                         tidx[tb + o4 + i] = i;          // a * s_i
-    st_fq(tsc + tb + o4 + n + i, fq_mont(fq_mont(b, sinv), yii));  tidx[tb + o4 + n + i] = n + i;   // b * s_i^-1 * y^-i
+    st_fq(tsc + tb4 + i, fq_mont(a, s));                         tidx[tb4 + i] = i;          // a * s_i
+    st_fq(tsc + tb4 + n + i, fq_mont(fq_mont(b, sinv), yii));  tidx[tb4 + n + i] = n + i;   // b * s_i^-1 * y^-i
   }
   if (i < L) {
     Fq x2 = fq_from_mont(fq_mont(xm[i], xm[i])), xi2 = fq_from_mont(fq_mont(xim[i], xim[i]));
-    st_fq(tsc + tb + o4 + 2 * n + 2 + i, fq_neg(x2));       tidx[tb + o4 + 2 * n + 2 + i] = pb + RP_LS + i;        // L_j : -x_j^2
-    st_fq(tsc + tb + o4 + 2 * n + 2 + L + i, fq_neg(xi2));  tidx[tb + o4 + 2 * n + 2 + L + i] = pb + RP_LS + L + i; // R_j : -x_j^-2
+    st_fq(tsc + tb4 + 2 * n + 2 + i, fq_neg(x2));       tidx[tb4 + 2 * n + 2 + i] = pb + RP_LS + i;        // L_j : -x_j^2
+    st_fq(tsc + tb4 + 2 * n + 2 + L + i, fq_neg(xi2));  tidx[tb4 + 2 * n + 2 + L + i] = pb + RP_LS + L + i; // R_j : -x_j^-2
   }
   if (i == 0) {
     const Fq one = fq_one(), m1 = fq_neg(one);
@@ -134,28 +138,27 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
     Fq delta = fq_sub(fq_mont(fq_sub(z, z2), sum_y), fq_mul(z3, fq_sub(two_n, one)));
     Fq x2 = fq_mul(x, x);
     // E1
-    st_fq(tsc + tb + o1 + 0, fq_sub(that, delta));  tidx[tb + o1 + 0] = iG;
-    st_fq(tsc + tb + o1 + 1, taux);                 tidx[tb + o1 + 1] = iH;
-    st_fq(tsc + tb + o1 + 2, fq_neg(z2));           tidx[tb + o1 + 2] = pb + RP_V;
-    st_fq(tsc + tb + o1 + 3, fq_neg(x));            tidx[tb + o1 + 3] = pb + RP_T1;
-    st_fq(tsc + tb + o1 + 4, fq_neg(x2));           tidx[tb + o1 + 4] = pb + RP_T2;
+    st_fq(tsc + tb1 + 0, fq_sub(that, delta));  tidx[tb1 + 0] = iG;
+    st_fq(tsc + tb1 + 1, taux);                 tidx[tb1 + 1] = iH;
+    st_fq(tsc + tb1 + 2, fq_neg(z2));           tidx[tb1 + 2] = pb + RP_V;
+    st_fq(tsc + tb1 + 3, fq_neg(x));            tidx[tb1 + 3] = pb + RP_T1;
+    st_fq(tsc + tb1 + 4, fq_neg(x2));           tidx[tb1 + 4] = pb + RP_T2;
     // E2 non-generator terms
-    st_fq(tsc + tb + o2 + 0, one);                  tidx[tb + o2 + 0] = pb + RP_A;
-    st_fq(tsc + tb + o2 + 1, x);                    tidx[tb + o2 + 1] = pb + RP_S;
-    st_fq(tsc + tb + o2 + 2 + n + 0, fq_neg(mu));              tidx[tb + o2 + 2 + n + 0] = iH;
-    st_fq(tsc + tb + o2 + 2 + n + 1, fq_mul(x1, that));        tidx[tb + o2 + 2 + n + 1] = iU;
-    st_fq(tsc + tb + o2 + 2 + n + 2, m1);                      tidx[tb + o2 + 2 + n + 2] = pb + RP_PNEW;
-    st_fq(tsc + tb + o2 + 2 + n + 3, fq_neg(z));               tidx[tb + o2 + 2 + n + 3] = iGsum;        // sum_i (-z) * gs_i
-    st_fq(tsc + tb + o2 + 2 + n + 4, z);                       tidx[tb + o2 + 2 + n + 4] = iHsum;        // sum_i z * hs_i
+    st_fq(tsc + tb2 + 0, one);                  tidx[tb2 + 0] = pb + RP_A;
+    st_fq(tsc + tb2 + 1, x);                    tidx[tb2 + 1] = pb + RP_S;
+    st_fq(tsc + tb2 + 2 + n + 0, fq_neg(mu));              tidx[tb2 + 2 + n + 0] = iH;
+    st_fq(tsc + tb2 + 2 + n + 1, fq_mul(x1, that));        tidx[tb2 + 2 + n + 1] = iU;
+    st_fq(tsc + tb2 + 2 + n + 2, m1);                      tidx[tb2 + 2 + n + 2] = pb + RP_PNEW;
+    st_fq(tsc + tb2 + 2 + n + 3, fq_neg(z));               tidx[tb2 + 2 + n + 3] = iGsum;        // sum_i (-z) * gs_i
+    st_fq(tsc + tb2 + 2 + n + 4, z);                       tidx[tb2 + 2 + n + 4] = iHsum;        // sum_i z * hs_i
     // E3
-    st_fq(tsc + tb + o3 + 0, x1);                   tidx[tb + o3 + 0] = iU;
-    st_fq(tsc + tb + o3 + 1, m1);                   tidx[tb + o3 + 1] = pb + RP_UNEW;
+    st_fq(tsc + tb3 + 0, x1);                   tidx[tb3 + 0] = iU;
+    st_fq(tsc + tb3 + 1, m1);                   tidx[tb3 + 1] = pb + RP_UNEW;
     // E4 non-generator terms
-    st_fq(tsc + tb + o4 + 2 * n + 0, fq_mul(a, b)); tidx[tb + o4 + 2 * n + 0] = pb + RP_UNEW;
-    st_fq(tsc + tb + o4 + 2 * n + 1, m1);           tidx[tb + o4 + 2 * n + 1] = pb + RP_PNEW;
-    u32 base = p * lay.tpp;
-    offsets[4 * p + 0] = base + o1; offsets[4 * p + 1] = base + o2; offsets[4 * p + 2] = base + o3; offsets[4 * p + 3] = base + o4;
-    if (p == nproofs - 1) offsets[4 * nproofs] = base + lay.tpp;
+    st_fq(tsc + tb4 + 2 * n + 0, fq_mul(a, b)); tidx[tb4 + 2 * n + 0] = pb + RP_UNEW;
+    st_fq(tsc + tb4 + 2 * n + 1, m1);           tidx[tb4 + 2 * n + 1] = pb + RP_PNEW;
+    offsets[p] = (u32)tb1; offsets[nproofs + p] = (u32)tb2; offsets[2 * nproofs + p] = (u32)tb3; offsets[3 * nproofs + p] = (u32)tb4;
+    if (p == nproofs - 1) offsets[4 * nproofs] = nproofs * lay.tpp;
   }
 }
 
@@ -178,7 +181,7 @@ __global__ void k_rp_accept(const Affine* __restrict__ res, u32 nproofs, uint8_t
   u32 p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs) return;
   bool ok = true;
-  for (int e = 0; e < 4; e++) ok = ok && affine_is_identity(ld_affine(res + 4 * p + e));
+  for (u32 e = 0; e < 4; e++) ok = ok && affine_is_identity(ld_affine(res + e * nproofs + p));
   accept[p] = ok ? 1 : 0;
 }
 
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(256) k_rp_lookup(const Affine* __restrict__ ta
   const u32 e = warp < 4 ? 3u : (warp < 6 ? 1u : (warp == 6 ? 0u : 2u));
   const u32 nw = e == 3 ? 4u : (e == 1 ? 2u : 1u);
   const u32 s = e == 3 ? warp : (e == 1 ? warp - 4 : 0u);
-  const u32 lo = __ldg(offsets + 4 * p + e), hi = __ldg(offsets + 4 * p + e + 1);
+  const u32 lo = __ldg(offsets + e * nproofs + p), hi = __ldg(offsets + e * nproofs + p + 1);
   XYZZ acc = xyzz_identity();
   for (u32 t = lo + s; t < hi; t += nw) {
     const u32 gi = __ldg(idx + t);
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(256) k_rp_lookup(const Affine* __restrict__ ta
     const u32 d = (k.v[lane >> 2] >> (8 * (lane & 3))) & 0xFFu;
     if (d) { Affine q = ld_affine(tab + fb_index(gi, lane, d)); xyzz_madd_ni(acc, q); }
   }
-  st_xyzz(part + ((size_t)(4 * p + e) * 128 + 32 * s + lane), acc);
+  st_xyzz(part + ((size_t)(e * nproofs + p) * 128 + 32 * s + lane), acc);
 }
 // Same with the 16-bit table: lane l owns window l & 15 of the (l >> 4)-th of two terms taken per step, so a term costs 16
 // lookups; the table lives in HBM (8.9 GB), hence the next entry is loaded into registers under the current addition.
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(256) k_rp_lookup16(const Affine* __restrict__ 
   const u32 e = warp < 4 ? 3u : (warp < 6 ? 1u : (warp == 6 ? 0u : 2u));
   const u32 nw = e == 3 ? 4u : (e == 1 ? 2u : 1u);
   const u32 s = e == 3 ? warp : (e == 1 ? warp - 4 : 0u);
-  const u32 lo = __ldg(offsets + 4 * p + e), hi = __ldg(offsets + 4 * p + e + 1);
+  const u32 lo = __ldg(offsets + e * nproofs + p), hi = __ldg(offsets + e * nproofs + p + 1);
   const u32 win = lane & 15u, sub = lane >> 4;
   XYZZ acc = xyzz_identity();
   Affine cur; cur.x = fp_zero(); cur.y = fp_zero();
@@ -246,14 +249,14 @@ __global__ void __launch_bounds__(256) k_rp_lookup16(const Affine* __restrict__ 
     cur = nxt; have = nhave;
     if (!__any_sync(BP_FULL_MASK, in)) break;          // both term slots of the warp are past the end
   }
-  st_xyzz(part + ((size_t)(4 * p + e) * 128 + 32 * s + lane), acc);
+  st_xyzz(part + ((size_t)(e * nproofs + p) * 128 + 32 * s + lane), acc);
 }
 // Fold, step 1 (throughput form): one thread adds 8 consecutive lane sums; 16 group sums per equation slot
-__global__ void __launch_bounds__(128) k_rp_fold8(const XYZZ* __restrict__ part, u32 nmsm, XYZZ* __restrict__ grp) {
+__global__ void __launch_bounds__(128) k_rp_fold8(const XYZZ* __restrict__ part, u32 nmsm, u32 nproofs, XYZZ* __restrict__ grp) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;          // (m, group of 8)
   const u32 m = t >> 4, gq = t & 15;
   if (m >= nmsm) return;
-  const u32 e = m & 3u, ng = e == 3 ? 16u : (e == 1 ? 8u : 4u);
+  const u32 e = m / nproofs, ng = e == 3 ? 16u : (e == 1 ? 8u : 4u);
   if (gq >= ng) return;
   const XYZZ* src = part + (size_t)m * 128 + 8 * gq;
   XYZZ v = ld_xyzz(src);
@@ -262,14 +265,14 @@ __global__ void __launch_bounds__(128) k_rp_fold8(const XYZZ* __restrict__ part,
   st_xyzz(grp + (size_t)m * 16 + gq, v);
 }
 // Fold, step 2: one warp per equation: its <= 16 group sums + the bucket pass's partial `other[m]` -> out[m]
-__global__ void __launch_bounds__(128) k_rp_fold(const XYZZ* __restrict__ part, const XYZZ* __restrict__ other, u32 nmsm,
+__global__ void __launch_bounds__(128) k_rp_fold(const XYZZ* __restrict__ part, const XYZZ* __restrict__ other, u32 nmsm, u32 nproofs,
                                                  XYZZ* __restrict__ out) {
   __shared__ XYZZ sm[4][8];
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   u32 m = blockIdx.x * 4 + warp;
   const bool live = m < nmsm;
   if (!live) m = nmsm - 1;
-  const u32 e = m & 3u, nl = e == 3 ? 16u : (e == 1 ? 8u : 4u);
+  const u32 e = m / nproofs, nl = e == 3 ? 16u : (e == 1 ? 8u : 4u);
   const int role = lane & 3, base = lane & ~3;
   const u32 q = lane >> 2;
   const XYZZ* src = part + (size_t)m * 16;
@@ -294,7 +297,7 @@ __global__ void k_rp_accept_xyzz(const XYZZ* __restrict__ res, u32 nproofs, uint
   u32 p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs) return;
   bool ok = true;
-  for (int e = 0; e < 4; e++) ok = ok && xyzz_is_identity(ld_xyzz(res + 4 * p + e));
+  for (u32 e = 0; e < 4; e++) ok = ok && xyzz_is_identity(ld_xyzz(res + e * nproofs + p));
   accept[p] = ok ? 1 : 0;
 }
 
