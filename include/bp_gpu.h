@@ -150,6 +150,9 @@ size_t bp_rp_proof_stride(size_t n);
 
 /* ---- host-side Fiat-Shamir helpers (exported for tests; src/utils/utils.py:84-111) -------------- */
 int bp_mod_hash(const uint8_t* msg, size_t len, uint8_t out32[32]);            /* mod_hash(msg, q) */
+/* out[i] = mod_hash(str(first + i) + suffix, q), i < count: the sL / sR blinding vectors
+ * (src/rangeproofs/rangeproof_prover.py:48-55, rangeproof_aggreg_prover.py:53-60); host only */
+int bp_mod_hash_indexed(const uint8_t* suffix, size_t len, uint32_t first, uint32_t count, uint8_t* out32);
 int bp_sha256(const uint8_t* msg, size_t len, uint8_t out32[32]);              /* hashlib.sha256(msg).digest() */
 int bp_sha256_set_portable(int on);   /* 1: force the portable compression function; returns the active one (1 = SHA-NI) */
 int bp_point_to_b64(const uint8_t pt64[64], char out[45], size_t* out_len);    /* point_to_b64 */

@@ -57,6 +57,7 @@ PROTOTYPES = {
                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), c_u8p]),
     "bp_rp_proof_stride": (c_sz, [c_sz]),
     "bp_mod_hash": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
+    "bp_mod_hash_indexed": (ctypes.c_int, [c_u8p, c_sz, ctypes.c_uint32, ctypes.c_uint32, c_u8p]),
     "bp_sha256": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
     "bp_sha256_set_portable": (ctypes.c_int, [ctypes.c_int]),
     "bp_point_to_b64": (ctypes.c_int, [c_u8p, c_u8p, ctypes.POINTER(c_sz)]),
@@ -139,7 +140,15 @@ def pack_point(pt):
 
 
 def pack_points(pts):
-    return b"".join([pack_point(p) for p in pts])
+    out = []
+    add = out.append
+    for p in pts:      # fast path inlined: a cached wire form that still matches the point's coordinates
+        pk = getattr(p, "_pk", None)
+        if pk is not None and pk[0] is p.x and pk[1] is p.y:
+            add(pk[2])
+        else:
+            add(pack_point(p))
+    return b"".join(out)
 
 
 def unpack_xy(b, off=0):
@@ -176,6 +185,14 @@ def msm_batch_bytes(pts_b, sc_b, offsets):
     off = (ctypes.c_uint32 * len(offsets))(*offsets)
     check(load().bp_msm_batch(pts_b, sc_b, off, nmsm, out))
     return out.raw[:64 * nmsm]
+
+
+def mod_hash_indexed(suffix, first, count):
+    """[mod_hash(str(i).encode() + suffix, q).x for i in range(first, first + count)] hashed in C (host only)."""
+    out = ctypes.create_string_buffer(32 * max(count, 1))
+    check(load().bp_mod_hash_indexed(suffix, len(suffix), first, count, out))
+    raw = out.raw
+    return [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(count)]
 
 
 def lift_x_batch(xs, want=None):

@@ -47,6 +47,20 @@ int bp_mod_hash(const uint8_t* msg, size_t len, uint8_t out32[32]) {
   return 0;
 }
 
+int bp_mod_hash_indexed(const uint8_t* suffix, size_t len, uint32_t first, uint32_t count, uint8_t* out32) {
+  // out[i] = mod_hash(str(first + i).encode() + suffix, q): the blinding vectors sL, sR of a range proof
+  // (rangeproof_prover.py:48-55, rangeproof_aggreg_prover.py:53-60) -- 2nm hashes per proof, 2.2 us each in Python
+  std::string msg;
+  msg.reserve(len + 12);
+  for (uint32_t i = 0; i < count; i++) {
+    msg = std::to_string(first + i);
+    msg.append((const char*)suffix, len);
+    Fq x = mod_hash_q((const uint8_t*)msg.data(), msg.size());
+    fq_to_le(out32 + 32 * (size_t)i, x);
+  }
+  return 0;
+}
+
 int bp_point_to_b64(const uint8_t pt64[64], char out[45], size_t* out_len) {
   std::string s = point_to_b64(pt64);
   memcpy(out, s.data(), s.size());

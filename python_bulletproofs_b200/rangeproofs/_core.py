@@ -79,8 +79,12 @@ def prove(vs, n, g, h, gs, hs, gammas, u, group, transcript: Transcript):
     aR = [(bit - 1) % q for bit in aL]
     t0 = transcript.digest
     alpha = mod_hash(b"alpha" + t0, q).x
-    sL = [mod_hash(str(i).encode() + t0, q).x for i in range(nm)]
-    sR = [mod_hash(str(i).encode() + t0, q).x for i in range(nm, 2 * nm)]
+    if q == nat.Q:      # the 2nm blinding hashes in C (bp_mod_hash_indexed)
+        sLR = nat.mod_hash_indexed(t0, 0, 2 * nm)
+        sL, sR = sLR[:nm], sLR[nm:]
+    else:
+        sL = [mod_hash(str(i).encode() + t0, q).x for i in range(nm)]
+        sR = [mod_hash(str(i).encode() + t0, q).x for i in range(nm, 2 * nm)]
     rho = mod_hash(str(2 * n).encode() + t0, q).x           # reference quirk: index 2*n even when m > 1
     # A = <aL,gs> + <aR,hs> + alpha*h ; S likewise: two (2nm+1)-term MSMs in one device pass
     base = gs + hs + [h]

@@ -59,6 +59,9 @@ def test_host_c_transcript_helpers_match_oracle():
         assert b64.raw[:ln.value] == po.b64_point(pt)
     lib.bp_point_to_b64(bytes(64), b64, ctypes.byref(ln))
     assert b64.raw[:ln.value] == b"AA=="
+    # the indexed form used for the sL / sR blinding vectors (rangeproof_prover.py:48-55)
+    for suffix, first, count in ((b"", 0, 3), (b"abc&def&", 0, 130), (b"t" * 200, 120, 140), (b"x", 99990, 25), (b"y", 0, 0)):
+        assert nat.mod_hash_indexed(suffix, first, count) == [po.mod_hash(str(i).encode() + suffix) for i in range(first, first + count)]
 
 
 def test_sha256_both_implementations_match_hashlib():
