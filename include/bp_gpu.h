@@ -85,6 +85,19 @@ int bp_fb_clear(void);
  * rangeproof_aggreg_prover.py:82, rangeproof_aggreg_verifier.py:80; ModP.__mul__(Point) utils.py:43-44 */
 int bp_scalar_mul_batch(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t* out64);
 
+/* ---- range-proof prover: polynomial algebra over Z_q on the host --------------------------
+ * _get_polynomial_coeffs / _final_compute of src/rangeproofs/rangeproof_prover.py:93-112 and
+ * rangeproof_aggreg_prover.py:117-146 for m values of n bits (aL_bits: n*m bytes 0/1, value-major; sL, sR: n*m scalars):
+ *   poly1 (after y, z):  t1, t2
+ *   poly2 (after x):     ls, rs (the vectors handed to the inner-product argument), t_hat = <ls, rs>, yinv[i] = y^-i and
+ *                        hsc[i] = z + z^(2 + i/n) 2^(i mod n) y^-i  (the h-generator scalars of the P multiexp, :78-86)
+ * Pure host code (4 x 64-bit Montgomery arithmetic), no GPU needed. */
+int bp_rp_prover_poly1(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_t* sR32, size_t n, size_t m, const uint8_t y32[32],
+                       const uint8_t z32[32], uint8_t t1_out[32], uint8_t t2_out[32]);
+int bp_rp_prover_poly2(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_t* sR32, size_t n, size_t m, const uint8_t y32[32],
+                       const uint8_t z32[32], const uint8_t x32[32], uint8_t* ls32, uint8_t* rs32, uint8_t* yinv32, uint8_t* hsc32,
+                       uint8_t that_out[32]);
+
 /* ---- batched lift-x / point decompression ---------------------------------------
  * y = sqrt(x^3 + 7) for n candidate x coordinates (32-byte LE, must be < p); ok[i] = 1 when x is on the curve, else
  * out[i] = zeros.  want[i]: 0 = even y, 1 = odd y (bytes_to_point, src/utils/utils.py:119-131), 2 = the root

@@ -42,6 +42,8 @@ PROTOTYPES = {
     "bp_msm_accumulate_kernel_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "bp_scalar_mul_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_lift_x_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p, c_u8p]),
+    "bp_rp_prover_poly1": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p]),
+    "bp_rp_prover_poly2": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
     "bp_fb_set_mode": (ctypes.c_int, [ctypes.c_int]),
     "bp_fb_stats": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)] * 4),
     "bp_fb_clear": (ctypes.c_int, []),
@@ -187,12 +189,33 @@ def msm_batch_bytes(pts_b, sc_b, offsets):
     return out.raw[:64 * nmsm]
 
 
-def mod_hash_indexed(suffix, first, count):
-    """[mod_hash(str(i).encode() + suffix, q).x for i in range(first, first + count)] hashed in C (host only)."""
+def mod_hash_indexed_raw(suffix, first, count):
+    """mod_hash(str(i).encode() + suffix, q) for i in range(first, first + count), as count 32-byte LE scalars (hashed in C)."""
     out = ctypes.create_string_buffer(32 * max(count, 1))
     check(load().bp_mod_hash_indexed(suffix, len(suffix), first, count, out))
-    raw = out.raw
+    return out.raw[:32 * count]
+
+
+def mod_hash_indexed(suffix, first, count):
+    raw = mod_hash_indexed_raw(suffix, first, count)
     return [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(count)]
+
+
+def rp_prover_poly1(bits, sL_b, sR_b, n, m, y, z):
+    """(t1, t2) of the range-proof polynomial, computed in C (bp_rp_prover_poly1)."""
+    t1, t2 = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+    check(load().bp_rp_prover_poly1(bits, sL_b, sR_b, n, m, (y % Q).to_bytes(32, "little"), (z % Q).to_bytes(32, "little"), t1, t2))
+    return int.from_bytes(t1.raw, "little"), int.from_bytes(t2.raw, "little")
+
+
+def rp_prover_poly2(bits, sL_b, sR_b, n, m, y, z, x):
+    """(ls, rs, y^-i, z + zz_i y^-i) as packed scalar vectors and t_hat as an int (bp_rp_prover_poly2)."""
+    nm = n * m
+    ls, rs, yinv, hsc = (ctypes.create_string_buffer(32 * nm) for _ in range(4))
+    that = ctypes.create_string_buffer(32)
+    check(load().bp_rp_prover_poly2(bits, sL_b, sR_b, n, m, (y % Q).to_bytes(32, "little"), (z % Q).to_bytes(32, "little"),
+                                    (x % Q).to_bytes(32, "little"), ls, rs, yinv, hsc, that))
+    return ls.raw, rs.raw, yinv.raw, hsc.raw, int.from_bytes(that.raw, "little")
 
 
 def lift_x_batch(xs, want=None):

@@ -17,6 +17,7 @@
 #include "transcript.h"
 #include "verify.cuh"
 #include "fixedbase.cuh"
+#include "rp_algebra.h"
 #include <nccl.h>
 #include <thread>
 

@@ -61,6 +61,60 @@ int bp_mod_hash_indexed(const uint8_t* suffix, size_t len, uint32_t first, uint3
   return 0;
 }
 
+int bp_rp_prover_poly1(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_t* sR32, size_t n, size_t m, const uint8_t y32[32],
+                       const uint8_t z32[32], uint8_t t1_out[32], uint8_t t2_out[32]) {
+  using namespace rpa;
+  const size_t nm = n * m;
+  if (nm == 0) return fail("bp_rp_prover_poly1: empty vectors");
+  const H4 y = reduce(ld(y32)), z = reduce(ld(z32));
+  Consts c = position_constants(y, z, n, m);
+  const H4 zneg = sub(zero(), z), zm1 = sub(z, one());
+  H4 t1 = zero(), t2 = zero();
+  for (size_t i = 0; i < nm; i++) {
+    const H4 sL = reduce(ld(sL32 + 32 * i)), sR = reduce(ld(sR32 + 32 * i));
+    const bool bit = aL_bits[i] != 0;
+    const H4 aRz = bit ? z : zm1;                          // aR_i + z  with aR = aL - 1
+    const H4 aLz = bit ? add(one(), zneg) : zneg;          // aL_i - z
+    const H4 ysR = mul_sm(sR, c.ym[i]);                    // y^i * sR_i
+    const H4 inner = add(mul_sm(aRz, c.ym[i]), c.zz[i]);   // y^i (aR_i + z) + zz_i
+    const H4 sLm = to_m(sL);
+    t1 = add(t1, add(mul_sm(inner, sLm), mul_sm(aLz, to_m(ysR))));
+    t2 = add(t2, mul_sm(ysR, sLm));
+  }
+  st(t1_out, t1); st(t2_out, t2);
+  return 0;
+}
+
+int bp_rp_prover_poly2(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_t* sR32, size_t n, size_t m, const uint8_t y32[32],
+                       const uint8_t z32[32], const uint8_t x32[32], uint8_t* ls32, uint8_t* rs32, uint8_t* yinv32, uint8_t* hsc32,
+                       uint8_t that_out[32]) {
+  using namespace rpa;
+  const size_t nm = n * m;
+  if (nm == 0) return fail("bp_rp_prover_poly2: empty vectors");
+  const H4 y = reduce(ld(y32)), z = reduce(ld(z32)), x = reduce(ld(x32));
+  Fq yq; memcpy(yq.v, y.v, 32);
+  if (fq_is_zero(yq)) return fail("modular inverse does not exist");
+  Fq yiq = fq_inv_host(yq);
+  H4 yinv; memcpy(yinv.v, yiq.v, 32);
+  Consts c = position_constants(y, z, n, m);
+  const H4 xM = to_m(x), yinvM = to_m(yinv);
+  const H4 zneg = sub(zero(), z), zm1 = sub(z, one());
+  H4 that = zero(), yi = one();                             // y^-i, standard
+  for (size_t i = 0; i < nm; i++) {
+    const H4 sL = reduce(ld(sL32 + 32 * i)), sR = reduce(ld(sR32 + 32 * i));
+    const bool bit = aL_bits[i] != 0;
+    const H4 l = add(bit ? add(one(), zneg) : zneg, mul_sm(sL, xM));                       // aL_i - z + sL_i x
+    const H4 r = add(mul_sm(add(bit ? z : zm1, mul_sm(sR, xM)), c.ym[i]), c.zz[i]);        // y^i (aR_i + z + sR_i x) + zz_i
+    that = add(that, mul_sm(l, to_m(r)));
+    st(ls32 + 32 * i, l); st(rs32 + 32 * i, r);
+    st(yinv32 + 32 * i, yi);
+    st(hsc32 + 32 * i, add(z, mul_sm(c.zz[i], to_m(yi))));                                 // z + zz_i y^-i
+    yi = mul_sm(yi, yinvM);
+  }
+  st(that_out, that);
+  return 0;
+}
+
 int bp_point_to_b64(const uint8_t pt64[64], char out[45], size_t* out_len) {
   std::string s = point_to_b64(pt64);
   memcpy(out, s.data(), s.size());

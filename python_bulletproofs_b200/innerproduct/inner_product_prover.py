@@ -19,38 +19,50 @@ from .inner_product_verifier import Proof1, Proof2
 class NIProver:
     """Protocol 1 (inner_product_prover.py:11-45)."""
 
-    def __init__(self, g, h, u, P, c, a, b, group, seed=b"", _h_scale=None, _P_msm=None):
-        assert len(g) == len(h) == len(a) == len(b)
+    def __init__(self, g, h, u, P, c, a, b, group, seed=b"", _h_scale=None, _P_msm=None, _packed=None):
+        assert _packed is not None or len(g) == len(h) == len(a) == len(b)
         self.g, self.h, self.u, self.P, self.c, self.a, self.b = g, h, u, P, c, a, b
         self.group = group
         self.transcript = Transcript(seed)
         self._h_scale = _h_scale      # private: effective generators are _h_scale[i] * h[i] (never materialised)
         self._P_msm = _P_msm          # private: P given as (points, scalars) of an MSM not yet evaluated (P may be None)
+        # private: wire-form operands from the range prover's C algebra -- dict(n, g, h, a, b, h_scale, P_pts, P_sc, P_cnt)
+        # of packed bytes; a, b, _h_scale and _P_msm are then ignored
+        self._packed = _packed
 
     def prove(self) -> Proof1:
         x = self.transcript.get_modp(self.group.q)
         self.transcript.add_number(x)
         # P_new = P + (x*c)*u ; u_new = x*u.  When the caller passed P as an unevaluated MSM (range-proof prover), P_new
         # is that MSM with one more term: one device pass instead of two (P itself is not part of the proof).
-        if self._P_msm is not None:
+        if self._packed is not None:
+            pk = self._packed
+            ub = nat.pack_point(self.u)
+            cnt = pk["P_cnt"]
+            raw = nat.msm_batch_bytes(pk["P_pts"] + ub + ub, pk["P_sc"] + nat.pack_scalar(x * self.c) + nat.pack_scalar(x),
+                                      [0, cnt + 1, cnt + 2])
+            P_new, u_new = Point.from_bytes64(raw, 0), Point.from_bytes64(raw, 64)
+        elif self._P_msm is not None:
             pts, scs = self._P_msm
             P_new, u_new = PipSECP256k1.multiexp_batch([list(pts) + [self.u], [self.u]], [list(scs) + [x * self.c], [x]])
         else:
             P_new, u_new = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
         inner = FastNIProver2(self.g, self.h, u_new, P_new, self.a, self.b, self.group, self.transcript.digest,
-                              _h_scale=self._h_scale)
+                              _h_scale=self._h_scale, _packed=self._packed)
         return Proof1(u_new, P_new, inner.prove(), self.transcript.digest)
 
 
 class FastNIProver2:
     """Protocol 2 (inner_product_prover.py:48-110)."""
 
-    def __init__(self, g, h, u, P, a, b, group, transcript: Optional[bytes] = None, _h_scale=None):
-        assert len(g) == len(h) == len(a) == len(b)
+    def __init__(self, g, h, u, P, a, b, group, transcript: Optional[bytes] = None, _h_scale=None, _packed=None):
+        self._packed = _packed
+        n_ = _packed["n"] if _packed is not None else len(a)
+        assert _packed is not None or len(g) == len(h) == len(a) == len(b)
         self._h_scale = _h_scale
-        assert len(a) & (len(a) - 1) == 0
-        self.log_n = len(a).bit_length() - 1
-        self.n = len(a)
+        assert n_ & (n_ - 1) == 0
+        self.log_n = n_.bit_length() - 1
+        self.n = n_
         self.g, self.h, self.u, self.P, self.a, self.b = g, h, u, P, a, b
         self.group = group
         self.transcript = Transcript()
@@ -72,10 +84,14 @@ class FastNIProver2:
         a_out, b_out = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
         t_out = ctypes.create_string_buffer(cap)
         t_len = ctypes.c_size_t(0)
-        hscale = nat.pack_scalars(self._h_scale) if self._h_scale is not None else None
+        if self._packed is not None:
+            pk = self._packed
+            gb, hb, hscale, ab, bb = pk["g"], pk["h"], pk["h_scale"], pk["a"], pk["b"]
+        else:
+            hscale = nat.pack_scalars(self._h_scale) if self._h_scale is not None else None
+            gb, hb, ab, bb = nat.pack_points(self.g), nat.pack_points(self.h), nat.pack_scalars(self.a), nat.pack_scalars(self.b)
         nat.check(nat.load().bp_ipa_prove_hs(
-            nat.pack_points(self.g), nat.pack_points(self.h), hscale, nat.pack_point(self.u),
-            nat.pack_scalars(self.a), nat.pack_scalars(self.b), n, start, len(start),
+            gb, hb, hscale, nat.pack_point(self.u), ab, bb, n, start, len(start),
             Ls, Rs, xs, a_out, b_out, t_out, cap, ctypes.byref(t_len)))
         self.transcript.digest = t_out.raw[:t_len.value]
         return Proof2(

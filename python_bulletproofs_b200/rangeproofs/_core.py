@@ -5,9 +5,10 @@ rangeproof_aggreg_verifier.py) collapses to the single-value one (rangeproof_pro
 rangeproof_verifier.py), including the `rho = H(str(2*n) + t)` derivation, so both public
 prover classes and both verifier classes are thin shells around this module.
 
-Division of labour: the O(nm) Z_q algebra and the transcript stay on the host in Python ints
-(SURVEY.md 8f rows N1/N3 are "next"); every elliptic-curve operation goes to the GPU as a
-multi-scalar multiplication, a scalar-multiplication batch, or the IPA round loop.
+Division of labour: the transcript stays on the host in Python; the prover's O(nm) Z_q algebra runs in C on the host
+(bp_rp_prover_poly1/2, bp_mod_hash_indexed) and hands packed scalar vectors straight to the device
+calls; every elliptic-curve operation goes to the GPU as a multi-scalar multiplication or the IPA round loop.  The
+pure-Python form of the same algebra (`_prove_python`) is what runs for a group order other than secp256k1's.
 """
 from .. import _native as nat
 from ..innerproduct.inner_product_prover import NIProver
@@ -69,7 +70,65 @@ def scale_generators(hs, y, q):
     return [Point.from_bytes64(raw, 64 * i) for i in range(n)]
 
 
+_ONE_B, _ZERO_B = (1).to_bytes(32, "little"), bytes(32)
+
+
 def prove(vs, n, g, h, gs, hs, gammas, u, group, transcript: Transcript):
+    """Same proof, byte for byte, as `_prove_python`; vectors travel as packed bytes between the C algebra and the device calls."""
+    q = group.q
+    if q != nat.Q:
+        return _prove_python(vs, n, g, h, gs, hs, gammas, u, group, transcript)
+    m = len(vs)
+    nm = n * m
+    bits = bytes((v.x >> i) & 1 for v in vs for i in range(n))              # aL, value-major
+    t0 = transcript.digest
+    alpha = mod_hash(b"alpha" + t0, q).x
+    sLR = nat.mod_hash_indexed_raw(t0, 0, 2 * nm)                              # sL | sR
+    sL_b, sR_b = sLR[:32 * nm], sLR[32 * nm:]
+    rho = mod_hash(str(2 * n).encode() + t0, q).x                              # reference quirk: index 2*n even when m > 1
+    gs_b, hs_b, h_b, g_b = nat.pack_points(gs), nat.pack_points(hs), nat.pack_point(h), nat.pack_point(g)
+    base_b = gs_b + hs_b + h_b
+    qm1_b = (q - 1).to_bytes(32, "little")
+    aL_b = b"".join([_ONE_B if b else _ZERO_B for b in bits])
+    aR_b = b"".join([_ZERO_B if b else qm1_b for b in bits])                   # aR = aL - 1 mod q
+    raw = nat.msm_batch_bytes(base_b + base_b, aL_b + aR_b + nat.pack_scalar(alpha) + sLR + nat.pack_scalar(rho),
+                              [0, 2 * nm + 1, 4 * nm + 2])
+    A, S = Point.from_bytes64(raw, 0), Point.from_bytes64(raw, 64)
+    transcript.add_list_points([A, S])
+    y = transcript.get_modp(q)
+    transcript.add_number(y)
+    z = transcript.get_modp(q)
+    transcript.add_number(z)
+    yv, zv = y.x, z.x
+    t1, t2 = nat.rp_prover_poly1(bits, sL_b, sR_b, n, m, yv, zv)
+    t1_that = transcript.digest
+    tau1 = mod_hash(b"tau1" + t1_that, q).x
+    tau2 = mod_hash(b"tau2" + t1_that, q).x
+    gh_b = g_b + h_b
+    raw = nat.msm_batch_bytes(gh_b + gh_b, nat.pack_scalars([t1, tau1, t2, tau2]), [0, 2, 4])
+    T1, T2 = Point.from_bytes64(raw, 0), Point.from_bytes64(raw, 64)
+    transcript.add_list_points([T1, T2])
+    x = transcript.get_modp(q)
+    transcript.add_number(x)
+    xv = x.x
+    ls_b, rs_b, yinv_b, hsc_b, t_hat = nat.rp_prover_poly2(bits, sL_b, sR_b, n, m, yv, zv, xv)
+    zpow = zv * zv % q
+    gsum = 0
+    for j in range(m):
+        gsum += zpow * gammas[j].x
+        zpow = zpow * zv % q
+    taux = (tau2 * xv * xv + tau1 * xv + gsum) % q
+    mu = (alpha + rho * xv) % q
+    # P - mu*h = A + x*S - mu*h + sum(-z * gs_i) + sum((z + zz_i*y^-i) * hs_i), handed to Protocol 1 unevaluated
+    packed = {"n": nm, "g": gs_b, "h": hs_b, "a": ls_b, "b": rs_b, "h_scale": yinv_b,
+              "P_pts": nat.pack_point(A) + nat.pack_point(S) + h_b + gs_b + hs_b,
+              "P_sc": nat.pack_scalars([1, xv, -mu]) + nat.pack_scalar(-zv) * nm + hsc_b,
+              "P_cnt": 3 + 2 * nm}
+    inner = NIProver(gs, hs, u, None, ModP(t_hat, q), None, None, group, _packed=packed)
+    return Proof(ModP(taux, q), ModP(mu, q), ModP(t_hat, q), T1, T2, A, S, inner.prove(), transcript.digest)
+
+
+def _prove_python(vs, n, g, h, gs, hs, gammas, u, group, transcript: Transcript):
     q = group.q
     m = len(vs)
     nm = n * m
@@ -79,12 +138,8 @@ def prove(vs, n, g, h, gs, hs, gammas, u, group, transcript: Transcript):
     aR = [(bit - 1) % q for bit in aL]
     t0 = transcript.digest
     alpha = mod_hash(b"alpha" + t0, q).x
-    if q == nat.Q:      # the 2nm blinding hashes in C (bp_mod_hash_indexed)
-        sLR = nat.mod_hash_indexed(t0, 0, 2 * nm)
-        sL, sR = sLR[:nm], sLR[nm:]
-    else:
-        sL = [mod_hash(str(i).encode() + t0, q).x for i in range(nm)]
-        sR = [mod_hash(str(i).encode() + t0, q).x for i in range(nm, 2 * nm)]
+    sL = [mod_hash(str(i).encode() + t0, q).x for i in range(nm)]
+    sR = [mod_hash(str(i).encode() + t0, q).x for i in range(nm, 2 * nm)]
     rho = mod_hash(str(2 * n).encode() + t0, q).x           # reference quirk: index 2*n even when m > 1
     # A = <aL,gs> + <aR,hs> + alpha*h ; S likewise: two (2nm+1)-term MSMs in one device pass
     base = gs + hs + [h]

@@ -251,3 +251,24 @@ def test_h_scale_equals_materialised_generators():
     assert quiet(Verifier2(g_, h_, u_, P2, got, _h_scale=yinv).verify)
     assert quiet(Verifier2(g_, hsp_, u_, P2, got).verify)
     assert not quiet(Verifier2(g_, h_, u_, P2, got).verify)          # wrong generators without the scale
+
+
+@pytest.mark.parametrize("n,m", [(8, 1), (64, 1), (4, 2), (16, 4)])
+def test_c_algebra_prover_equals_python_algebra_prover(n, m):
+    """rangeproofs/_core.prove (polynomial algebra in C, packed vectors) against _prove_python (the same algebra in Python
+    ints) and against the oracle prover: identical proofs, byte for byte."""
+    from python_bulletproofs_b200.rangeproofs import _core
+    from python_bulletproofs_b200.utils.transcript import Transcript
+    seeds = ["ca%d" % i for i in range(7)]
+    ogs, ohs, og, oh, ou = gens(n * m, seeds)
+    gs, hs, g, h, u = [P_(t) for t in ogs], [P_(t) for t in ohs], P_(og), P_(oh), P_(ou)
+    rng = random.Random(n * 100 + m)
+    vs = [M_(rng.getrandbits(n)) for _ in range(m)]
+    if m > 1:
+        vs[0] = M_(0); vs[-1] = M_(2 ** n - 1)
+    gammas = [mod_hash(b"gm%d" % j, Q) for j in range(m)]
+    a = _core.prove(vs, n, g, h, gs, hs, gammas, u, secp256k1, Transcript(b"seedX"))
+    b = _core._prove_python(vs, n, g, h, gs, hs, gammas, u, secp256k1, Transcript(b"seedX"))
+    assert range_json(a) == range_json(b)
+    want = po.range_prove([v.x for v in vs], n, og, oh, ogs, ohs, [gm.x for gm in gammas], ou, b"seedX")
+    assert range_json(a) == po.range_to_json(want)
