@@ -97,6 +97,10 @@ int bp_rp_prover_poly1(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_
 int bp_rp_prover_poly2(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_t* sR32, size_t n, size_t m, const uint8_t y32[32],
                        const uint8_t z32[32], const uint8_t x32[32], uint8_t* ls32, uint8_t* rs32, uint8_t* yinv32, uint8_t* hsc32,
                        uint8_t that_out[32]);
+/* verifier side: yinv[i] = y^-i, hsc[i] = z + z^(2 + i/n) 2^(i mod n) y^-i and
+ * delta(y, z) = (z - z^2) sum y^i - sum_{j=1..m} z^(j+2) (2^n - 1)   (rangeproof_verifier.py:69-72, aggregated :72-80) */
+int bp_rp_verifier_scalars(size_t n, size_t m, const uint8_t y32[32], const uint8_t z32[32], uint8_t* yinv32, uint8_t* hsc32,
+                           uint8_t delta_out[32]);
 
 /* ---- batched lift-x / point decompression ---------------------------------------
  * y = sqrt(x^3 + 7) for n candidate x coordinates (32-byte LE, must be < p); ok[i] = 1 when x is on the curve, else

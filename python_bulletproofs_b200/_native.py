@@ -42,6 +42,7 @@ PROTOTYPES = {
     "bp_msm_accumulate_kernel_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "bp_scalar_mul_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_lift_x_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p, c_u8p]),
+    "bp_rp_verifier_scalars": (ctypes.c_int, [c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
     "bp_rp_prover_poly1": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p]),
     "bp_rp_prover_poly2": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
     "bp_fb_set_mode": (ctypes.c_int, [ctypes.c_int]),
@@ -199,6 +200,14 @@ def mod_hash_indexed_raw(suffix, first, count):
 def mod_hash_indexed(suffix, first, count):
     raw = mod_hash_indexed_raw(suffix, first, count)
     return [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(count)]
+
+
+def rp_verifier_scalars(n, m, y, z):
+    """(y^-i packed, (z + zz_i y^-i) packed, delta as int) -- bp_rp_verifier_scalars."""
+    nm = n * m
+    yinv, hsc, delta = ctypes.create_string_buffer(32 * nm), ctypes.create_string_buffer(32 * nm), ctypes.create_string_buffer(32)
+    check(load().bp_rp_verifier_scalars(n, m, (y % Q).to_bytes(32, "little"), (z % Q).to_bytes(32, "little"), yinv, hsc, delta))
+    return yinv.raw, hsc.raw, int.from_bytes(delta.raw, "little")
 
 
 def rp_prover_poly1(bits, sL_b, sR_b, n, m, y, z):

@@ -115,6 +115,36 @@ int bp_rp_prover_poly2(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_
   return 0;
 }
 
+int bp_rp_verifier_scalars(size_t n, size_t m, const uint8_t y32[32], const uint8_t z32[32], uint8_t* yinv32, uint8_t* hsc32,
+                           uint8_t delta_out[32]) {
+  using namespace rpa;
+  const size_t nm = n * m;
+  if (nm == 0) return fail("bp_rp_verifier_scalars: empty vectors");
+  const H4 y = reduce(ld(y32)), z = reduce(ld(z32));
+  Fq yq; memcpy(yq.v, y.v, 32);
+  if (fq_is_zero(yq)) return fail("modular inverse does not exist");                 // y.inv(), utils.py:69-70
+  Fq yiq = fq_inv_host(yq);
+  H4 yinv; memcpy(yinv.v, yiq.v, 32);
+  Consts c = position_constants(y, z, n, m);
+  const H4 yinvM = to_m(yinv), zM = to_m(z);
+  H4 yi = one(), sum_y = zero();
+  for (size_t i = 0; i < nm; i++) {
+    sum_y = add(sum_y, from_m(c.ym[i]));
+    st(yinv32 + 32 * i, yi);
+    st(hsc32 + 32 * i, add(z, mul_sm(c.zz[i], to_m(yi))));                             // z + zz_i y^-i
+    yi = mul_sm(yi, yinvM);
+  }
+  // delta = (z - z^2) * sum y^i - sum_{j=1..m} z^(j+2) * (2^n - 1)      rangeproof_verifier.py:69-71, aggreg :72-79
+  const H4 z2 = mul_sm(z, zM);
+  H4 two_n = one();
+  for (size_t i = 0; i < n; i++) two_n = add(two_n, two_n);
+  const H4 tn1M = to_m(sub(two_n, one()));
+  H4 delta = mul_sm(sub(z, z2), to_m(sum_y)), zj = mul_sm(z2, zM);                     // z^3
+  for (size_t j = 1; j <= m; j++) { delta = sub(delta, mul_sm(zj, tn1M)); zj = mul_sm(zj, zM); }
+  st(delta_out, delta);
+  return 0;
+}
+
 int bp_point_to_b64(const uint8_t pt64[64], char out[45], size_t* out_len) {
   std::string s = point_to_b64(pt64);
   memcpy(out, s.data(), s.size());

@@ -111,7 +111,8 @@ class Verifier2(_Checker):
             if x % SUPERCURVE.q == 0:
                 raise Exception("modular inverse does not exist")      # ModP.inv, utils.py:69-70
         accept = ctypes.c_int(0)
-        hscale = nat.pack_scalars(self._h_scale) if self._h_scale is not None else None
+        hs_ = self._h_scale            # list of scalars, or already packed bytes (range verifier's C scalar preparation)
+        hscale = None if hs_ is None else (hs_ if isinstance(hs_, (bytes, bytearray)) else nat.pack_scalars(hs_))
         nat.check(nat.load().bp_ipa_verify_eq_hs(
             nat.pack_points(self.g), nat.pack_points(self.h), hscale, nat.pack_point(self.u), nat.pack_point(self.P), n,
             nat.pack_scalar(proof.a), nat.pack_scalar(proof.b), nat.pack_scalars(proof.xs[:log_n]),

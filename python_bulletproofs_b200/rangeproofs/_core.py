@@ -212,16 +212,27 @@ class VerifierCore:
         nm, m = len(gs), len(Vs)
         n = nm // m
         xv, yv, zv = self.x.x % q, self.y.x % q, self.z.x % q
-        ypow, zz = _position_constants(yv, zv, n, nm, q)
         zpows = [pow(zv, j + 2, q) for j in range(m + 1)]
-        delta = ((zv - zv * zv) * sum(ypow) - sum(zpows[j] * (2 ** n - 1) for j in range(1, m + 1))) % q
         if yv == 0:
             raise Exception("modular inverse does not exist")          # y.inv(), utils.py:69-70
-        yinv_pow = inverse_powers(yv, nm, q)                             # hsp_i = y^-i * hs_i stays implicit
-        # t_hat*g + taux*h == sum z^(j+2) V_j + delta*g + x*T1 + x^2*T2      (one device pass, exact compare)
-        lhs, rhs, P_inner = PipSECP256k1.multiexp_batch(
-            [[g, h], list(Vs) + [g, proof.T1, proof.T2], [proof.A, proof.S, h] + gs + hs],
-            [[proof.t_hat, proof.taux], zpows[:m] + [delta, xv, xv * xv % q],
-             [1, xv, -(proof.mu.x)] + [-zv] * nm + [(zv + zz[i] * yinv_pow[i]) % q for i in range(nm)]])
+        if q == nat.Q:
+            # scalar preparation in C (bp_rp_verifier_scalars), vectors as packed bytes; hsp_i = y^-i * hs_i stays implicit
+            yinv_pow, hsc_b, delta = nat.rp_verifier_scalars(n, m, yv, zv)
+            gs_b, hs_b, g_b, h_b = nat.pack_points(gs), nat.pack_points(hs), nat.pack_point(g), nat.pack_point(h)
+            raw = nat.msm_batch_bytes(
+                g_b + h_b + nat.pack_points(list(Vs) + [g, proof.T1, proof.T2]) + nat.pack_points([proof.A, proof.S]) + h_b + gs_b + hs_b,
+                nat.pack_scalars([proof.t_hat, proof.taux] + zpows[:m] + [delta, xv, xv * xv % q] + [1, xv, -(proof.mu.x)])
+                + nat.pack_scalar(-zv) * nm + hsc_b,
+                [0, 2, 2 + m + 3, 2 + m + 3 + 3 + 2 * nm])
+            lhs, rhs, P_inner = (Point.from_bytes64(raw, 64 * j) for j in range(3))
+        else:
+            ypow, zz = _position_constants(yv, zv, n, nm, q)
+            delta = ((zv - zv * zv) * sum(ypow) - sum(zpows[j] * (2 ** n - 1) for j in range(1, m + 1))) % q
+            yinv_pow = inverse_powers(yv, nm, q)                             # hsp_i = y^-i * hs_i stays implicit
+            # t_hat*g + taux*h == sum z^(j+2) V_j + delta*g + x*T1 + x^2*T2      (one device pass, exact compare)
+            lhs, rhs, P_inner = PipSECP256k1.multiexp_batch(
+                [[g, h], list(Vs) + [g, proof.T1, proof.T2], [proof.A, proof.S, h] + gs + hs],
+                [[proof.t_hat, proof.taux], zpows[:m] + [delta, xv, xv * xv % q],
+                 [1, xv, -(proof.mu.x)] + [-zv] * nm + [(zv + zz[i] * yinv_pow[i]) % q for i in range(nm)]])
         self.assertThat(lhs == rhs)
         return Verifier1(gs, hs, self.u, P_inner, proof.t_hat, proof.innerProof, _h_scale=yinv_pow).verify()
