@@ -13,6 +13,9 @@
  *                     exactly as `es = [ei % order]` (src/pippenger/pippenger.py:26).
  *   - all buffers are caller-owned host memory unless a handle is used; calls are synchronous
  *     and serialised on one CUDA stream per process; one process drives one GPU (bp_init).
+ *   - threading: the library keeps per-process state (workspaces, the table cache of "fixed-base tables", captured
+ *     graphs); like the reference it is meant to be called from ONE thread at a time.  It starts host threads of its own
+ *     only inside bp_rp_verify_batch (transcript checks of a chunk, joined before the call returns).
  */
 #ifndef BP_GPU_H
 #define BP_GPU_H
