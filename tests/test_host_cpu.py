@@ -184,3 +184,42 @@ def test_two_rank_gloo_sharding(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "rank %d ok" % r in o, o
+
+
+def test_host_c_range_proof_algebra_matches_python_formulas():
+    """bp_rp_prover_poly1/2 and bp_rp_verifier_scalars (csrc/rp_algebra.h, host only) against the formulas of
+    rangeproof_prover.py:93-112 / rangeproof_aggreg_prover.py:117-146 / rangeproof_verifier.py:69-72 in Python ints."""
+    import random
+    from python_bulletproofs_b200.rangeproofs._core import _position_constants, inverse_powers
+    q = ecc.Q
+    rng = random.Random(11)
+    for n, m in ((1, 1), (8, 1), (64, 1), (4, 3), (64, 16)):
+        nm = n * m
+        bits = bytes(rng.getrandbits(1) for _ in range(nm))
+        sL = [rng.randrange(q) for _ in range(nm)]
+        sR = [rng.randrange(q) for _ in range(nm)]
+        sL[0], sR[-1] = 0, q - 1
+        y, z, x = rng.randrange(1, q), rng.randrange(q), rng.randrange(q)
+        if n == 8:
+            y, z, x = q - 1, 0, 1
+        aL = list(bits)
+        aR = [(b - 1) % q for b in aL]
+        ypow, zz = _position_constants(y, z, n, nm, q)
+        ysR = [ypow[i] * sR[i] % q for i in range(nm)]
+        t1 = (sum(sL[i] * (ypow[i] * (aR[i] + z) + zz[i]) for i in range(nm)) + sum((aL[i] - z) * ysR[i] for i in range(nm))) % q
+        t2 = sum(sL[i] * ysR[i] for i in range(nm)) % q
+        sLb, sRb = nat.pack_scalars(sL), nat.pack_scalars(sR)
+        assert nat.rp_prover_poly1(bits, sLb, sRb, n, m, y, z) == (t1, t2)
+        ls = [(aL[i] - z + sL[i] * x) % q for i in range(nm)]
+        rs = [(ypow[i] * (aR[i] + z + sR[i] * x) + zz[i]) % q for i in range(nm)]
+        yinv = inverse_powers(y, nm, q)
+        hsc = [(z + zz[i] * yinv[i]) % q for i in range(nm)]
+        got = nat.rp_prover_poly2(bits, sLb, sRb, n, m, y, z, x)
+        assert [nat.unpack_scalars(got[k], nm) for k in range(4)] == [ls, rs, yinv, hsc]
+        assert got[4] == sum(a * b for a, b in zip(ls, rs)) % q
+        zp = [pow(z, j + 2, q) for j in range(m + 1)]
+        delta = ((z - z * z) * sum(ypow) - sum(zp[j] * (2 ** n - 1) for j in range(1, m + 1))) % q
+        vy, vh, vd = nat.rp_verifier_scalars(n, m, y, z)
+        assert (nat.unpack_scalars(vy, nm), nat.unpack_scalars(vh, nm), vd) == (yinv, hsc, delta)
+    with pytest.raises(nat.BpGpuError):
+        nat.rp_verifier_scalars(4, 1, 0, 5)                        # y = 0: "modular inverse does not exist"
