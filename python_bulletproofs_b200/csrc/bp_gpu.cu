@@ -43,6 +43,23 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     return msm_run_pipelined(points, point_idx, scalars, T, out_affine, out_xyzz);
   }
   cudaStream_t st = g.stream;
+  // host-operand MSM whose points are still arriving in two halves (upload_operands): run it as TWO half-size MSMs over one
+  // digit/sort pass -- buckets (half, unit, digit) -- accumulate the first half while the second is on the wire, reduce both
+  // in one batch of tails and add the two results
+  const bool halves = g.halves_pending && nmsm == 1 && !point_idx && !d_offsets && T >= 4;
+  g.halves_pending = false;
+  const u32 T_half = T / 2;
+  XYZZ* pair_out = nullptr;
+  Affine* final_affine = out_affine; XYZZ* final_xyzz = out_xyzz;
+  if (halves) {
+    u32* d_ho = (u32*)g.ws_halfoff.ensure(4 * sizeof(u32) + 2 * sizeof(XYZZ));
+    if (!d_ho) return fail("workspace allocation failed");
+    const u32 h_ho[3] = {0, T_half, T};
+    BP_CUDA(cudaMemcpyAsync(d_ho, h_ho, sizeof h_ho, cudaMemcpyHostToDevice, st));    // (pageable 12-byte copy: staged by the driver)
+    d_offsets = d_ho; nmsm = 2; terms_per_msm = T_half;
+    pair_out = (XYZZ*)(d_ho + 4);
+    out_affine = nullptr; out_xyzz = pair_out;
+  }
   MsmShape sh = msm_shape(terms_per_msm, nmsm, g.force_c);
   g.last_c = sh.c;
   g.last_nb = (size_t)nmsm * sh.U * sh.H;
@@ -69,7 +86,8 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure(nmw * sizeof(XYZZ));
   // every (term, window) pair is at most one entry, so E <= W*T: size the chunk structures for the bound
   size_t emax = (size_t)sh.W * 2 * T, nchunks = (emax + sh.chunk - 1) / sh.chunk;
-  XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * nchunks * sizeof(XYZZ));
+  const size_t hchunks = ((size_t)sh.W * 2 * (T - T_half) + sh.chunk - 1) / sh.chunk + 1;      // per half (the larger one)
+  XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * (halves ? 2 * hchunks : nchunks) * sizeof(XYZZ));
   size_t big_cap = emax / ((size_t)sh.chunk * BP_FIXUP_SERIAL_MAX) + 16;
   u32* big = (u32*)g.ws_big.ensure((big_cap + 3) * sizeof(u32));
   u32* zero_word = big + big_cap + 2;
@@ -87,17 +105,34 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));   // cursors start at the bucket offsets
   k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, cursor, entries);
   if (prof) cudaEventRecord(g.ev[3], st);
-  if (g.pts_ready) { BP_CUDA(cudaStreamWaitEvent(st, g.pts_ready, 0)); g.pts_ready = nullptr; }   // points may still be uploading
-  k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
   BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));          // empty buckets = identity (ZZ = 0)
   BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));   // [0] = queue length, kept zero word for gs = 0 lives at big[big_cap + 1]
-  // E (= start[nb]) stays on the device: launch for the upper bound W*T, threads past E exit at once
-  if (prof) cudaEventRecord(g.ev_k0, st);
-  k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
-  if (prof) cudaEventRecord(g.ev_k1, st);
-  k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big + 1);
-  k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
+  if (halves) {
+    const size_t hb = (size_t)sh.U * sh.H;                  // buckets of one half; entries of half k are [start[k*hb], start[(k+1)*hb])
+    for (int k = 0; k < 2; k++) {
+      const u32 t0 = k ? T_half : 0, tn = k ? T - T_half : T_half;
+      BP_CUDA(cudaStreamWaitEvent(st, g.ev_half[k], 0));    // this half of the points has landed
+      k_phi<<<(tn + 127) / 128, 128, 0, st>>>(points + t0, nullptr, tn, phi + t0);
+      const u32* gs = k ? start + hb : zero_word;
+      XYZZ* part_k = part + 2 * (size_t)k * hchunks;
+      if (prof && k == 0) cudaEventRecord(g.ev_k0, st);
+      k_accumulate<<<(unsigned)((hchunks + 127) / 128), 128, 0, st>>>(points, nullptr, phi, start, entries, gs, start + (k + 1) * hb, sh.chunk, buckets, part_k);
+      if (prof && k == 1) cudaEventRecord(g.ev_k1, st);
+      if (k == 1) BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));
+      k_fixup<<<(unsigned)((hb + 127) / 128), 128, 0, st>>>(start, k * hb, hb, gs, sh.chunk, part_k, buckets, big, big + 1);
+      k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, gs, sh.chunk, part_k, buckets, big, big + 1);
+    }
+  } else {
+    if (g.pts_ready) { BP_CUDA(cudaStreamWaitEvent(st, g.pts_ready, 0)); g.pts_ready = nullptr; }   // points may still be uploading
+    k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
+    // E (= start[nb]) stays on the device: launch for the upper bound W*T, threads past E exit at once
+    if (prof) cudaEventRecord(g.ev_k0, st);
+    k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
+    if (prof) cudaEventRecord(g.ev_k1, st);
+    k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big + 1);
+    k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
+  }
   if (prof) cudaEventRecord(g.ev[4], st);
   size_t nsegs = nmw * sh.nseg;
   const bool plain_tails = nmsm >= 2048 && sh.H <= 512;     // big batch of small MSMs: throughput forms
@@ -140,6 +175,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     if (prof) cudaEventRecord(g.ev[5], st);
     k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
   }
+  if (halves) k_xyzz_pair<<<1, 32, 0, st>>>(pair_out, final_affine, final_xyzz);      // result = half 0 + half 1
   if (prof) cudaEventRecord(g.ev[6], st);
   BP_CUDA(cudaGetLastError());
   return 0;
@@ -242,6 +278,21 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
 static int upload_operands(Affine* d_pts, const uint8_t* pts64, Fq* d_sc, const uint8_t* sc32, size_t n) {
   BP_CUDA(cudaEventRecord(g.ev_copy_gate, g.stream));                     // earlier work may still read d_pts
   BP_CUDA(cudaStreamWaitEvent(g.copy_stream, g.ev_copy_gate, 0));
+  if (n >= ((size_t)1 << 17) && g.force_c == 0 && !g.profiling && n < g.pipeline_min_terms) {
+    // big MSM: everything on the copy stream in the order it is needed -- scalars, first half of the points, second half --
+    // each at full link speed; msm_run sorts as soon as the scalars are in and accumulates half by half (see there)
+    const size_t h = n / 2;
+    BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.copy_stream));
+    BP_CUDA(cudaEventRecord(g.ev_sc, g.copy_stream));
+    BP_CUDA(cudaMemcpyAsync(d_pts, pts64, h * 64, cudaMemcpyHostToDevice, g.copy_stream));
+    BP_CUDA(cudaEventRecord(g.ev_half[0], g.copy_stream));
+    BP_CUDA(cudaMemcpyAsync(d_pts + h, pts64 + h * 64, (n - h) * 64, cudaMemcpyHostToDevice, g.copy_stream));
+    BP_CUDA(cudaEventRecord(g.ev_half[1], g.copy_stream));
+    BP_CUDA(cudaStreamWaitEvent(g.stream, g.ev_sc, 0));
+    g.halves_pending = true;
+    g.pts_ready = nullptr;
+    return 0;
+  }
   BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.copy_stream));
   BP_CUDA(cudaEventRecord(g.ev_pts, g.copy_stream));
@@ -408,6 +459,8 @@ int bp_init(int device) {
   BP_CUDA(cudaEventCreate(&g.ev_k0)); BP_CUDA(cudaEventCreate(&g.ev_k1));
   BP_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
   BP_CUDA(cudaEventCreateWithFlags(&g.ev_pts, cudaEventDisableTiming)); BP_CUDA(cudaEventCreateWithFlags(&g.ev_copy_gate, cudaEventDisableTiming));
+  BP_CUDA(cudaEventCreateWithFlags(&g.ev_sc, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) BP_CUDA(cudaEventCreateWithFlags(&g.ev_half[i], cudaEventDisableTiming));
   g.inited = true;
   return 0;
 }

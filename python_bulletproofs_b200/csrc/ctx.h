@@ -42,6 +42,11 @@ struct Ctx {
   cudaEvent_t ev_a, ev_b, ev_k0, ev_k1;
   cudaStream_t copy_stream = nullptr;           // uploads of points overlap the scalar-only stages
   cudaEvent_t ev_pts = nullptr, ev_copy_gate = nullptr, pts_ready = nullptr;
+  // large host-operand MSMs: the points arrive in two halves (ev_half[0], ev_half[1]); msm_run then runs the MSM as two
+  // half-size MSMs over one sort so that the first half is accumulated while the second is still on the wire
+  cudaEvent_t ev_half[2] = {nullptr, nullptr}, ev_sc = nullptr;
+  bool halves_pending = false;
+  DevBuf ws_halfoff;
   bool profiling = false;
   int force_c = 0, last_c = 0;
   unsigned msm_skip_below = 0;                  // msm_run: terms with point index below this are left to the caller (see k_digits)

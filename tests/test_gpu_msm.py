@@ -82,6 +82,28 @@ def test_msm_large_vs_oracle(lgn):
     assert gpu_msm_raw(pb, sb, n) == ecc.msm_bytes(pb, sb, n, "bucket", ecc.max_threads())
 
 
+@pytest.mark.parametrize("n", [(1 << 17), (1 << 17) + 3, 300001])
+def test_host_operand_msm_in_two_halves(n):
+    """bp_msm with >= 2^17 host terms uploads the points in two halves and accumulates the first while the second is on
+    the wire (msm_run, halves): same result as the device-resident path and the oracle, odd sizes and hot buckets included."""
+    base = fast_points(1 << 10, 777)
+    rng = random.Random(n)
+    pb = b"".join(ecc.pack_point(base[rng.randrange(len(base))]) for _ in range(n))
+    ks = [rng.getrandbits(256) for _ in range(n)]
+    for i in range(0, n, 7):
+        ks[i] = (1, 0, Q - 1, 2 ** 128, 5)[(i // 7) % 5]           # many equal scalars: giant buckets in both halves
+    sb = b"".join(k.to_bytes(32, "little") for k in ks)
+    got = gpu_msm_raw(pb, sb, n)
+    assert got == ecc.msm_bytes(pb, sb, n, "bucket", ecc.max_threads())
+    lib = nat.load()
+    hp = ctypes.c_uint64()
+    nat.check(lib.bp_points_upload(pb, n, ctypes.byref(hp)))
+    out = ctypes.create_string_buffer(64)
+    nat.check(lib.bp_msm_h(hp, sb, n, out))
+    assert ecc.unpack_point(out.raw) == got
+    lib.bp_handle_free(hp)
+
+
 def test_msm_full_size_properties():
     """BASELINE size 2^20: slice additivity + linearity + agreement with the multi-threaded oracle."""
     n = 1 << 20
