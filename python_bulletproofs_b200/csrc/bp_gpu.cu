@@ -48,7 +48,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   // in one batch of tails and add the two results
   const bool halves = g.halves_pending && nmsm == 1 && !point_idx && !d_offsets && T >= 4;
   g.halves_pending = false;
-  const u32 T_half = T / 2;
+  const u32 T_half = halves && g.halves_split > 0 && g.halves_split < T ? (u32)g.halves_split : T / 2;   // terms in the first part
   XYZZ* pair_out = nullptr;
   Affine* final_affine = out_affine; XYZZ* final_xyzz = out_xyzz;
   if (halves) {
@@ -86,7 +86,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure(nmw * sizeof(XYZZ));
   // every (term, window) pair is at most one entry, so E <= W*T: size the chunk structures for the bound
   size_t emax = (size_t)sh.W * 2 * T, nchunks = (emax + sh.chunk - 1) / sh.chunk;
-  const size_t hchunks = ((size_t)sh.W * 2 * (T - T_half) + sh.chunk - 1) / sh.chunk + 1;      // per half (the larger one)
+  const size_t hchunks = ((size_t)sh.W * 2 * (T - T_half > T_half ? T - T_half : T_half) + sh.chunk - 1) / sh.chunk + 1;      // per part (the larger one)
   XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * (halves ? 2 * hchunks : nchunks) * sizeof(XYZZ));
   size_t big_cap = emax / ((size_t)sh.chunk * BP_FIXUP_SERIAL_MAX) + 16;
   u32* big = (u32*)g.ws_big.ensure((big_cap + 3) * sizeof(u32));
@@ -281,7 +281,9 @@ static int upload_operands(Affine* d_pts, const uint8_t* pts64, Fq* d_sc, const 
   if (n >= ((size_t)1 << 17) && g.force_c == 0 && !g.profiling && n < g.pipeline_min_terms) {
     // big MSM: everything on the copy stream in the order it is needed -- scalars, first half of the points, second half --
     // each at full link speed; msm_run sorts as soon as the scalars are in and accumulates half by half (see there)
-    const size_t h = n / 2;
+    // first part 3/8 of the points: its accumulation then ends about when the rest has landed (measured link / kernel rates)
+    const size_t h = n * 3 / 8;
+    g.halves_split = h;
     BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.copy_stream));
     BP_CUDA(cudaEventRecord(g.ev_sc, g.copy_stream));
     BP_CUDA(cudaMemcpyAsync(d_pts, pts64, h * 64, cudaMemcpyHostToDevice, g.copy_stream));

@@ -46,6 +46,7 @@ struct Ctx {
   // half-size MSMs over one sort so that the first half is accumulated while the second is still on the wire
   cudaEvent_t ev_half[2] = {nullptr, nullptr}, ev_sc = nullptr;
   bool halves_pending = false;
+  size_t halves_split = 0;
   DevBuf ws_halfoff;
   bool profiling = false;
   int force_c = 0, last_c = 0;
