@@ -396,6 +396,10 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   // ---- host: transcript checks + challenge extraction, threaded over proofs --------------------
   unsigned nthreads = std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
+  if (const char* lws = getenv("LOCAL_WORLD_SIZE")) {      // one process per GPU on a shared host (torchrun): share the cores
+    long w = atol(lws);
+    if (w > 1) nthreads = nthreads / (unsigned)w ? nthreads / (unsigned)w : 1;
+  }
   if (nthreads > 64) nthreads = 64;
   auto work = [&](size_t lo, size_t hi) {
     std::vector<std::pair<size_t, size_t>> sl;
