@@ -77,7 +77,7 @@ int bp_msm_accumulate_kernel_ms(float* ms);   /* k_accumulate alone (stage [3] a
  * 47,57,78-86).  The library recognises a repeated point set by a hash of its bytes and answers from a precomputed
  * table (255 multiples per byte window, 522 KB per point) instead of the bucket method: same canonical result, ~5x
  * lower latency for the 2..4097-term MSMs of a prover.  mode 0 = never, 1 = build at the second use of a set (default),
- * 2 = build at first use.  bp_fb_clear drops every table. */
+ * 2 = build at first use.  bp_fb_clear drops every table.  A cache hit is confirmed by comparing the generator bytes. */
 int bp_fb_set_mode(int mode);
 int bp_fb_stats(uint64_t* tables, uint64_t* bytes, uint64_t* hits, uint64_t* builds);
 int bp_fb_clear(void);

@@ -3,7 +3,23 @@
 // pay the ~2 ms build), 2 = build at first sight.  Tables are evicted least-recently-used past a byte budget.
 // (included inside namespace bp by bp_gpu.cu)
 
-struct FbEntry { Affine* tab; size_t n; size_t bytes; unsigned long long stamp; };
+// `src` = the generator bytes the table was built from: a cache hit is confirmed by comparing them (a 64-bit hash alone
+// would let two different generator sets share a table)
+struct FbEntry { Affine* tab; size_t n; size_t bytes; unsigned long long stamp; std::vector<uint8_t> src; };
+struct FbSrc {                           // up to 5 byte ranges that make up a generator set, in hashing order
+  const uint8_t* p[5]; size_t len[5]; int cnt;
+  uint64_t hash(uint64_t seed) const;
+  bool equals(const std::vector<uint8_t>& v) const {
+    size_t off = 0;
+    for (int i = 0; i < cnt; i++) { if (off + len[i] > v.size() || memcmp(v.data() + off, p[i], len[i]) != 0) return false; off += len[i]; }
+    return off == v.size();
+  }
+  std::vector<uint8_t> copy() const {
+    std::vector<uint8_t> v;
+    for (int i = 0; i < cnt; i++) v.insert(v.end(), p[i], p[i] + len[i]);
+    return v;
+  }
+};
 struct FbCache {
   std::map<uint64_t, FbEntry> tabs;
   std::map<uint64_t, unsigned> seen, seen16;
@@ -20,8 +36,7 @@ static FbCache fb;
 static bool fb_enabled() { return fb.mode != 0 && g.force_c == 0; }
 
 static uint64_t fb_hash(uint64_t h, const uint8_t* p, size_t nbytes) {
-  // 64-bit multiply-xorshift over 8-byte words (not cryptographic: a collision would need equal-length generator sets
-  // chosen against this hash; the key also carries the length)
+  // 64-bit multiply-xorshift over 8-byte words: only the cache INDEX -- a hit is confirmed against the stored generator bytes
   size_t i = 0;
   for (; i + 8 <= nbytes; i += 8) {
     uint64_t w; memcpy(&w, p + i, 8);
@@ -31,6 +46,8 @@ static uint64_t fb_hash(uint64_t h, const uint8_t* p, size_t nbytes) {
   for (; i < nbytes; i++) { h = (h ^ p[i]) * 0x100000001B3ull; }
   return h;
 }
+
+uint64_t FbSrc::hash(uint64_t seed) const { uint64_t h = seed; for (int i = 0; i < cnt; i++) h = fb_hash(h, p[i], len[i]); return h; }
 
 static void fb_evict_for(size_t need) {
   while (!fb.tabs.empty() && fb.bytes + need > fb.cap) {
@@ -46,11 +63,15 @@ static void fb_evict_for(size_t need) {
 
 // Table for the point set `key` (n points at d_pts, readable in g.stream order), or nullptr when the set has no table
 // (mode, size, first sighting, or out of memory: the caller then takes the bucket method).
-static const Affine* fb_get(uint64_t key, const Affine* d_pts, size_t n) {
+static const Affine* fb_get(uint64_t key, const FbSrc& src, const Affine* d_pts, size_t n) {
   if (fb.mode == 0 || n == 0 || n > fb.max_points) return nullptr;
   key ^= (uint64_t)n * 0xD6E8FEB86659FD93ull;
   auto it = fb.tabs.find(key);
-  if (it != fb.tabs.end() && it->second.n == n) { it->second.stamp = ++fb.clock; fb.hits++; return it->second.tab; }
+  if (it != fb.tabs.end()) {
+    if (it->second.n != n || !src.equals(it->second.src)) return nullptr;      // hash collision: this set keeps the bucket method
+    it->second.stamp = ++fb.clock; fb.hits++;
+    return it->second.tab;
+  }
   if (fb.mode == 1) {
     if (fb.seen.size() > 8192) fb.seen.clear();
     if (++fb.seen[key] < 2) return nullptr;
@@ -68,7 +89,7 @@ static const Affine* fb_get(uint64_t key, const Affine* d_pts, size_t n) {
     k_fb_build<<<(ng * BP_FB_WINDOWS + 63) / 64, 64, 0, g.stream>>>(d_pts, (u32)g0, ng, scratch, tab);
   }
   if (cudaGetLastError() != cudaSuccess) { cudaFree(tab); return nullptr; }
-  fb.tabs[key] = FbEntry{tab, n, bytes, ++fb.clock};
+  fb.tabs[key] = FbEntry{tab, n, bytes, ++fb.clock, src.copy()};
   fb.bytes += bytes;
   fb.builds++;
   return tab;
@@ -92,7 +113,7 @@ static const Affine* fb_get16(uint64_t key, const Affine* tab8, size_t n) {
   const size_t threads = n * BP_FB16_WINDOWS * 256;
   k_fb_build16<<<(unsigned)((threads + 127) / 128), 128, 0, g.stream>>>(tab8, (u32)n, tab);
   if (cudaGetLastError() != cudaSuccess) { cudaFree(tab); return nullptr; }
-  fb.tabs16[key] = FbEntry{tab, n, bytes, ++fb.clock};
+  fb.tabs16[key] = FbEntry{tab, n, bytes, ++fb.clock, {}};      // (valid only together with its confirmed byte table)
   fb.bytes += bytes;
   fb.builds++;
   return tab;

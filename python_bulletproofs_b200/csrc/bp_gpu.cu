@@ -530,10 +530,11 @@ int bp_msm(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64
   if (!d_pts || !d_sc) return fail("device allocation failed");
   if (fb_enabled() && n <= fb.max_points) {
     // repeated generator set (a commitment call site of a prover/verifier): table lookups instead of buckets
-    const uint64_t key = fb_hash(0x6D736D31ull, pts64, n * 64);
+    const FbSrc src = {{pts64}, {n * 64}, 1};
+    const uint64_t key = src.hash(0x6D736D31ull);
     auto hit = fb.tabs.find(key ^ ((uint64_t)n * 0xD6E8FEB86659FD93ull));
     if (hit == fb.tabs.end()) BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.stream));   // needed to build
-    const Affine* tab = fb_get(key, d_pts, n);
+    const Affine* tab = fb_get(key, src, d_pts, n);
     if (tab) {
       Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
       if (!d_out) return fail("workspace allocation failed");
@@ -654,9 +655,10 @@ int bp_msm_batch(const uint8_t* pts64, const uint8_t* sc32, const uint32_t* offs
     bool same = true;
     for (size_t j = 1; j < nmsm && same; j++) same = memcmp(pts64, pts64 + (size_t)offsets[j] * 64, maxlen * 64) == 0;
     if (same) {
-      const uint64_t key = fb_hash(0x6D736D31ull, pts64, maxlen * 64);
+      const FbSrc src = {{pts64}, {maxlen * 64}, 1};
+      const uint64_t key = src.hash(0x6D736D31ull);
       BP_CUDA(cudaMemcpyAsync(d_pts, pts64, maxlen * 64, cudaMemcpyHostToDevice, g.stream));
-      const Affine* tab = fb_get(key, d_pts, maxlen);
+      const Affine* tab = fb_get(key, src, d_pts, maxlen);
       if (tab) {
         if (fb_msm_run(tab, nullptr, d_sc, d_off, (u32)nmsm, maxlen, 0, d_out, nullptr)) return 1;
         BP_CUDA(cudaMemcpyAsync(out64, d_out, nmsm * 64, cudaMemcpyDeviceToHost, g.stream));

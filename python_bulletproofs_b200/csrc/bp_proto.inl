@@ -224,8 +224,8 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   // rewrites PA, which is what makes a per-set table usable in every round)
   const Affine* tab = nullptr;
   if (fb_enabled() && 2 * n + 1 <= fb.max_points && n > 1) {
-    uint64_t key = fb_hash(fb_hash(fb_hash(0x69706131ull, u64_, 64), g64, n * 64), h64, n * 64);
-    tab = fb_get(key, PA, 2 * n + 1);
+    const FbSrc src = {{u64_, g64, h64}, {64, n * 64, n * 64}, 3};
+    tab = fb_get(src.hash(0x69706131ull), src, PA, 2 * n + 1);
   }
   size_t round = 0;
   RunningModHash rh;
@@ -489,8 +489,9 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   const Affine *fbtab = nullptr, *fbtab16 = nullptr;
   XYZZ *d_lanes = nullptr, *d_var = nullptr, *d_tot = nullptr;
   if (fb_enabled()) {
-    uint64_t key = fb_hash(fb_hash(fb_hash(fb_hash(fb_hash(0x72707631ull, gs64, n * 64), hs64, n * 64), g64, 64), h64, 64), u64_, 64);
-    fbtab = fb_get(key, table, lay.fixed);
+    const FbSrc src = {{gs64, hs64, g64, h64, u64_}, {n * 64, n * 64, 64, 64, 64}, 5};
+    const uint64_t key = src.hash(0x72707631ull);
+    fbtab = fb_get(key, src, table, lay.fixed);
     fbtab16 = fb_get16(key, fbtab, lay.fixed);
     if (fbtab) {
       d_lanes = (XYZZ*)g.ws_fb_lanes.ensure(4 * CH * (128 + 16) * sizeof(XYZZ));
