@@ -58,7 +58,9 @@ inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
       // a few MSMs: measured on B200 (profiles/r1_window_sweep.txt).  Windows whose top digit keeps only a few
       // significant bits of the 128-bit halves make hot buckets, so only c = 10, 13, 16 are used: 128 mod c is 8, 11, 0.
       // (n <= 64: c = 5 -- 0.47-0.50 ms against 0.52-0.54 ms at c = 10: the 512-bucket reduction is pure latency there)
-      int pick = n <= 64.0 ? 5 : (n <= 8192.0 ? 10 : (n <= 131072.0 ? 13 : 16));
+      // re-measured after the tail kernels got faster: c = 13 wins from 2^10 (0.534 vs 0.537 ms) to 2^16 (0.758 vs 0.790 at c = 16),
+      // c = 16 from 2^17 (0.916 vs 0.977 ms at c = 13)
+      int pick = n <= 64.0 ? 5 : (n < 1024.0 ? 10 : (n <= 65536.0 ? 13 : 16));
       cost = c == pick ? 0.0 : 1.0;
     } else {
       // many MSMs: everything is throughput; count field multiplications
