@@ -153,7 +153,8 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     // level 2: groups of G = 8 segments (measured at 2^20, c = 16 after the thread-per-segment first level:
     // G = 4 / 8 / 16 / 32 -> reduce stage 0.390 / 0.296 / 0.335 / 0.423 ms; the quad form pays ~2.4x the multiplications'
     // issue cost in glue, so many small groups turn it throughput bound)
-    const u32 Gmax = 8;
+    // (quad first level, S = 8, c = 13: G = 2 / 4 / 8 / 16 -> reduce stage 0.148 / 0.157 / 0.179 / 0.235 ms at 2^16)
+    const u32 Gmax = sh.seg_plain ? 8 : 2;
     u32 G = sh.nseg < Gmax ? sh.nseg : Gmax, ngrp = sh.nseg / G;
     int lgS = 0, lgG = 0, ubits = 0;
     while ((1u << lgS) < sh.S) lgS++;

@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include "ec.cuh"
 #include "fq.cuh"
 #include "glv.cuh"
