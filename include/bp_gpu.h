@@ -161,7 +161,10 @@ int bp_ipa_verify_eq(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[
  * transcripts: the three byte strings of each proof (range transcript, Protocol-1 transcript,
  * Protocol-2 transcript) concatenated; tr_off has 3*nproofs+1 entries.  start_transcript per proof.
  * accept[i] = 1/0 reproduces the reference's True / Exception("Proof invalid"); accept[i] = 2 marks
- * a non-numeric y/z/x slot (the reference raises ValueError from int(), rangeproof_verifier.py:49-53). */
+ * a non-numeric y/z/x slot (the reference raises ValueError from int(), rangeproof_verifier.py:49-53).
+ * Host threads for the transcript checks: all cores, divided by LOCAL_WORLD_SIZE when several ranks share a node.
+ * Development switches read from the environment: BP_VERIFY_CHUNK (proofs per chunk), BP_VERIFY_TIMING (host time per
+ * chunk on stderr). */
 int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g64[64], const uint8_t h64[64],
                        const uint8_t u64_[64], size_t n, const uint8_t* proofs, size_t proof_stride, size_t nproofs,
                        const uint8_t* transcripts, const uint64_t* tr_off, const uint32_t* start_transcript,
