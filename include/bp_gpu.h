@@ -145,6 +145,13 @@ int bp_ipa_verify_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* h
                         size_t n, const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,
                         const uint8_t* Rs64, int* accept);
 
+/* Verifier1 + Verifier2 in one device pass (inner_product_verifier.py:44-58 on top of :127-147): additionally checks
+ * P_new == P + xc*u and u_new == x*u with xc = x*c, x the Protocol-1 challenge; the Verifier2 equation then uses u_new, P_new */
+int bp_ipa_verify1_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscale32, const uint8_t u64_[64], const uint8_t P64[64],
+                         const uint8_t xc32[32], const uint8_t x32[32], const uint8_t u_new64[64], const uint8_t P_new64[64], size_t n,
+                         const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64, const uint8_t* Rs64,
+                         int* accept);
+
 /* Verifier2.get_ss + the two multiexps of Verifier2.verify   inner_product_verifier.py:91-102,132-145
  * accept = 1 iff  MSM(g||h||u ; a*s || b*s^-1 || a*b) == P + MSM(Ls||Rs ; x^2 || x^-2).
  * (The transcript re-check, :104-125, is host string work done by the Python/C host layer.) */

@@ -54,6 +54,8 @@ PROTOTYPES = {
     "bp_ipa_set_graphs": (ctypes.c_int, [ctypes.c_int]),
     "bp_ipa_prove_hs": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
                                        c_u8p, c_sz, ctypes.POINTER(c_sz)]),
+    "bp_ipa_verify1_eq_hs": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
+                                            ctypes.POINTER(ctypes.c_int)]),
     "bp_ipa_verify_eq_hs": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, ctypes.POINTER(ctypes.c_int)]),
     "bp_ipa_verify_eq": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, ctypes.POINTER(ctypes.c_int)]),
     "bp_rp_verify_batch": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_sz, c_u8p,

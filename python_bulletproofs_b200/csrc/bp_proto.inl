@@ -297,9 +297,12 @@ int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64],
                          transcript_out, tout_cap, tout_len);
 }
 
-int bp_ipa_verify_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscale32, const uint8_t u64_[64], const uint8_t P64[64],
-                        size_t n, const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,
-                        const uint8_t* Rs64, int* accept) {
+// p1 (optional) = Protocol 1's own two checks, evaluated in the same device pass: {P, u, x*c, x} of Verifier1 --
+// then u64_ / P64 are the PROOF's u_new / P_new and must equal x*u and P + (x*c)*u   (inner_product_verifier.py:51-52)
+struct IpaP1 { const uint8_t* P; const uint8_t* u; const uint8_t* xc; const uint8_t* x; };
+static int ipa_verify_eq_impl(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscale32, const uint8_t u64_[64], const uint8_t P64[64],
+                              size_t n, const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,
+                              const uint8_t* Rs64, const IpaP1* pr1, int* accept) {
   BP_NEED_INIT();
   if (n == 0 || (n & (n - 1))) return fail("bp_ipa_verify_eq: n must be a power of two");
   u32 L = 0; while (((size_t)1 << L) < n) L++;
@@ -323,7 +326,7 @@ int bp_ipa_verify_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* h
     s[i] = fq_mont(s[i - ((size_t)1 << t)], fq_to_mont(x2[j]));   // x_j^-1 -> x_j : multiply by x_j^2
   }
   size_t T0 = 2 * n + 1, T1 = 2 * L + 1, T = T0 + T1;
-  std::vector<uint8_t> hp(T * 64), hs(T * 32);
+  std::vector<uint8_t> hp((T + 3) * 64), hs((T + 3) * 32);
   memcpy(hp.data(), g64, n * 64); memcpy(hp.data() + n * 64, h64, n * 64); memcpy(hp.data() + 2 * n * 64, u64_, 64);
   for (size_t i = 0; i < n; i++) {
     fq_to_le(hs.data() + 32 * i, fq_mul(a, s[i]));                       // a * s_i
@@ -337,12 +340,34 @@ int bp_ipa_verify_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* h
   memcpy(p1 + 2 * L * 64, P64, 64);
   for (u32 j = 0; j < L; j++) { fq_to_le(s1 + 32 * j, x2[j]); fq_to_le(s1 + 32 * (L + j), xi2[j]); }
   fq_to_le(s1 + 32 * 2 * L, fq_one());
-  uint32_t off[3] = {0, (uint32_t)T0, (uint32_t)T};
-  uint8_t out[128];
-  if (bp_msm_batch(hp.data(), hs.data(), off, 2, out)) return 1;
-  *accept = memcmp(out, out + 64, 64) == 0 ? 1 : 0;
+  uint32_t off[5] = {0, (uint32_t)T0, (uint32_t)T, (uint32_t)T + 2, (uint32_t)T + 3};
+  uint8_t out[256];
+  if (pr1) {
+    uint8_t* pp = hp.data() + T * 64; uint8_t* ss = hs.data() + T * 32;
+    memcpy(pp, pr1->P, 64); memcpy(pp + 64, pr1->u, 64); memcpy(pp + 128, pr1->u, 64);
+    fq_to_le(ss, fq_one()); memcpy(ss + 32, pr1->xc, 32); memcpy(ss + 64, pr1->x, 32);
+  }
+  if (bp_msm_batch(hp.data(), hs.data(), off, pr1 ? 4 : 2, out)) return 1;
+  bool ok = memcmp(out, out + 64, 64) == 0;
+  if (pr1) ok = ok && memcmp(out + 128, P64, 64) == 0 && memcmp(out + 192, u64_, 64) == 0;
+  *accept = ok ? 1 : 0;
   return 0;
 }
+
+int bp_ipa_verify_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscale32, const uint8_t u64_[64], const uint8_t P64[64],
+                        size_t n, const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,
+                        const uint8_t* Rs64, int* accept) {
+  return ipa_verify_eq_impl(g64, h64, hscale32, u64_, P64, n, a32, b32, xs32, Ls64, Rs64, nullptr, accept);
+}
+
+int bp_ipa_verify1_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscale32, const uint8_t u64_[64], const uint8_t P64[64],
+                         const uint8_t xc32[32], const uint8_t x32[32], const uint8_t u_new64[64], const uint8_t P_new64[64], size_t n,
+                         const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64, const uint8_t* Rs64,
+                         int* accept) {
+  IpaP1 pr1 = {P64, u64_, xc32, x32};
+  return ipa_verify_eq_impl(g64, h64, hscale32, u_new64, P_new64, n, a32, b32, xs32, Ls64, Rs64, &pr1, accept);
+}
+
 
 int bp_ipa_verify_eq(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64], const uint8_t P64[64], size_t n,
                      const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,

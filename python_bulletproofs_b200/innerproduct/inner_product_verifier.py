@@ -58,12 +58,24 @@ class Verifier1(_Checker):
     def verify(self):
         self.verify_transcript()
         x = ModP(int(self.proof1.transcript.split(b"&")[1]), SUPERCURVE.q)
-        # P_new == P + (x*c)*u  and  u_new == x*u, both right-hand sides in one device pass
-        rhs_P, rhs_u = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
-        self.assertThat(self.proof1.P_new == rhs_P)
-        self.assertThat(self.proof1.u_new == rhs_u)
-        return Verifier2(self.g, self.h, self.proof1.u_new, self.proof1.P_new, self.proof1.proof2,
-                         _h_scale=self._h_scale).verify()
+        # P_new == P + (x*c)*u, u_new == x*u and Verifier2's equation in ONE device pass (bp_ipa_verify1_eq_hs); the
+        # transcript checks of Verifier2 stay in Python and run first, as they would inside Verifier2.verify
+        v2 = Verifier2(self.g, self.h, self.proof1.u_new, self.proof1.P_new, self.proof1.proof2, _h_scale=self._h_scale)
+        if not v2._device_ready():
+            rhs_P, rhs_u = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
+            self.assertThat(self.proof1.P_new == rhs_P)
+            self.assertThat(self.proof1.u_new == rhs_u)
+            return v2.verify()
+        # order of failures as in the reference: Protocol-1 equations (Proof invalid) before anything of Protocol 2; the
+        # merged call cannot tell which equation failed, so on rejection the separate checks are replayed
+        ok = v2._verify_merged(self.P, self.u, x * self.c, x)
+        if not ok:
+            rhs_P, rhs_u = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
+            self.assertThat(self.proof1.P_new == rhs_P)
+            self.assertThat(self.proof1.u_new == rhs_u)
+            return v2.verify()
+        print("OK")
+        return True
 
 
 class Verifier2(_Checker):
@@ -102,21 +114,47 @@ class Verifier2(_Checker):
             expect = str(mod_hash(b"&".join(parts[:at + 2]) + b"&", SUPERCURVE.q)).encode()
             self.assertThat(str(proof.xs[i]).encode() == parts[at + 2] == expect)
 
-    def verify(self):
-        self.verify_transcript()
+    def _device_ready(self):
+        n = len(self.g)
+        return n >= 1 and n & (n - 1) == 0 and len(self.h) == n
+
+    def _call(self, p1):
         proof = self.proof
         n = len(self.g)
         log_n = n.bit_length() - 1
-        for x in proof.xs[:log_n]:
-            if x % SUPERCURVE.q == 0:
-                raise Exception("modular inverse does not exist")      # ModP.inv, utils.py:69-70
         accept = ctypes.c_int(0)
         hs_ = self._h_scale            # list of scalars, or already packed bytes (range verifier's C scalar preparation)
         hscale = None if hs_ is None else (hs_ if isinstance(hs_, (bytes, bytearray)) else nat.pack_scalars(hs_))
-        nat.check(nat.load().bp_ipa_verify_eq_hs(
-            nat.pack_points(self.g), nat.pack_points(self.h), hscale, nat.pack_point(self.u), nat.pack_point(self.P), n,
-            nat.pack_scalar(proof.a), nat.pack_scalar(proof.b), nat.pack_scalars(proof.xs[:log_n]),
-            nat.pack_points(proof.Ls[:log_n]), nat.pack_points(proof.Rs[:log_n]), ctypes.byref(accept)))
-        self.assertThat(accept.value == 1)
+        common = (n, nat.pack_scalar(proof.a), nat.pack_scalar(proof.b), nat.pack_scalars(proof.xs[:log_n]),
+                  nat.pack_points(proof.Ls[:log_n]), nat.pack_points(proof.Rs[:log_n]), ctypes.byref(accept))
+        gb, hb = nat.pack_points(self.g), nat.pack_points(self.h)
+        if p1 is None:
+            nat.check(nat.load().bp_ipa_verify_eq_hs(gb, hb, hscale, nat.pack_point(self.u), nat.pack_point(self.P), *common))
+        else:
+            P0, u0, xc, x = p1
+            nat.check(nat.load().bp_ipa_verify1_eq_hs(gb, hb, hscale, nat.pack_point(u0), nat.pack_point(P0), nat.pack_scalar(xc),
+                                                      nat.pack_scalar(x), nat.pack_point(self.u), nat.pack_point(self.P), *common))
+        return accept.value == 1
+
+    def _check_challenges(self):
+        log_n = len(self.g).bit_length() - 1
+        for x in self.proof.xs[:log_n]:
+            if x % SUPERCURVE.q == 0:
+                raise Exception("modular inverse does not exist")      # ModP.inv, utils.py:69-70
+
+    def _verify_merged(self, P0, u0, xc, x):
+        """Verifier1's two equations + this verifier's equation in one device pass; False = some check failed (the caller
+        replays them separately to raise in the reference's order)."""
+        try:
+            self.verify_transcript()
+            self._check_challenges()
+        except Exception:
+            return False
+        return self._call((P0, u0, xc, x))
+
+    def verify(self):
+        self.verify_transcript()
+        self._check_challenges()
+        self.assertThat(self._call(None))
         print("OK")
         return True
