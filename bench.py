@@ -308,7 +308,7 @@ def bench_verify(args, nat, dist, rank, world):
     lo, hi = (0, total) if world == 1 else __import__("python_bulletproofs_b200.sharding", fromlist=["x"]).slice_bounds(total, rank, world)
     times = []
     acc = b""
-    for it in range(1 + 3):
+    for it in range(2 + 8):      # the first calls build the generator tables (byte windows, then 16-bit windows)
         if dist is not None:
             dist.barrier()
         a = time.perf_counter()
@@ -317,7 +317,7 @@ def bench_verify(args, nat, dist, rank, world):
             from python_bulletproofs_b200 import sharding
             acc = sharding.gather_accept(acc, [b - a_ for a_, b in sharding.all_slices(total, world)])
         times.append(max_over_ranks(dist, time.perf_counter() - a))
-    best = min(times[1:])
+    best = min(times[2:])
     want = bytes([0 if (i % distinct) % 16 == 15 else 1 for i in range(total)])
     return {"metric": "64-bit range-proof verifies/s", "value": round(total / best, 1), "unit": "verifies/s", "n_gpus": world,
             "scaling": "strong", "proofs": total, "distinct_proofs": distinct, "decisions_ok": acc == want,
