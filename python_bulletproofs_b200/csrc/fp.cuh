@@ -20,6 +20,7 @@ typedef uint64_t u64;
 struct __align__(16) Fp { u32 v[8]; };
 
 #define BP_DI __device__ __forceinline__
+#define BP_HAVE_FP_MUL_WIDE 1
 
 // 2^256 - p
 #define BP_PC_LO 977u   // C = 2^32 + 977 : limb0 = 977, limb1 = 1

@@ -138,8 +138,14 @@ __global__ void __launch_bounds__(256) k_digits(const Fq* __restrict__ scalars, 
       u32 mag = sd < 0 ? (u32)(-sd) : (u32)sd;
       u32 bkt = sd != 0 ? (u32)(((size_t)m * sh.U + w) * sh.H + (mag - 1)) : 0xFFFFFFFFu;
       u32 act = __activemask();
-      u32 peers = __match_any_sync(act, bkt);
-      if (sd != 0 && (u32)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(bucket_count + bkt, (u32)__popc(peers));
+      // aggregation only when the warp shows a repeated bucket among neighbouring lanes (hot buckets: repeated scalars,
+      // small windows); MATCH.ANY costs more than the atomics it saves when every lane hits its own bucket
+      const u32 nb1 = __shfl_xor_sync(act, bkt, 1), nb2 = __shfl_xor_sync(act, bkt, 2);      // (both shuffles before the ||: no lane may skip one)
+      const bool rep = __any_sync(act, bkt == nb1 || bkt == nb2);
+      if (rep) {
+        u32 peers = __match_any_sync(act, bkt);
+        if (sd != 0 && (u32)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(bucket_count + bkt, (u32)__popc(peers));
+      } else if (sd != 0) atomicAdd(bucket_count + bkt, 1u);
     }
   }
 }
@@ -156,7 +162,8 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits,
     int sd = digits[(size_t)w * (2 * (size_t)T) + st];
     u32 mag = sd < 0 ? (u32)(-sd) : (u32)sd;
     u32 b = sd != 0 ? (u32)(((size_t)m * sh.U + w) * sh.H + (mag - 1)) : 0xFFFFFFFFu;
-    // warp-aggregated cursor: one atomicAdd per distinct bucket per warp, lanes take consecutive slots
+    // warp-aggregated cursor: one atomicAdd per distinct bucket per warp, lanes take consecutive slots (here the returning
+    // atomics dominate: making the MATCH.ANY conditional as in k_digits measured no gain)
     u32 act = __activemask();
     u32 peers = __match_any_sync(act, b);
     u32 lane = threadIdx.x & 31, leader = (u32)(__ffs(peers) - 1);
