@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_st
   if (c0 == c1) return;
   if (c1 - c0 >= BP_FIXUP_SERIAL_MAX) { big_list[atomicAdd(big_count, 1u)] = (u32)b; return; }
   XYZZ acc = ld_xyzz(bucket_piece(part, s, c0, c0, CL));
-  for (u32 c = c0 + 1; c <= c1; c++) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add_ni(acc, v); }
+  for (u32 c = c0 + 1; c <= c1; c++) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add(acc, v); }
   st_xyzz(buckets + b, acc);
 }
 
