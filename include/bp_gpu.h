@@ -99,7 +99,7 @@ int bp_rp_prover_poly1(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_
                        const uint8_t z32[32], uint8_t t1_out[32], uint8_t t2_out[32]);
 int bp_rp_prover_poly2(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_t* sR32, size_t n, size_t m, const uint8_t y32[32],
                        const uint8_t z32[32], const uint8_t x32[32], uint8_t* ls32, uint8_t* rs32, uint8_t* yinv32, uint8_t* hsc32,
-                       uint8_t that_out[32]);
+                       uint8_t* rsy32 /* optional: rs[i] * y^-i */, uint8_t that_out[32]);
 /* verifier side: yinv[i] = y^-i, hsc[i] = z + z^(2 + i/n) 2^(i mod n) y^-i and
  * delta(y, z) = (z - z^2) sum y^i - sum_{j=1..m} z^(j+2) (2^n - 1)   (rangeproof_verifier.py:69-72, aggregated :72-80) */
 int bp_rp_verifier_scalars(size_t n, size_t m, const uint8_t y32[32], const uint8_t z32[32], uint8_t* yinv32, uint8_t* hsc32,
@@ -144,6 +144,11 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
 int bp_ipa_verify_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscale32, const uint8_t u64_[64], const uint8_t P64[64],
                         size_t n, const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,
                         const uint8_t* Rs64, int* accept);
+
+/* The statement of the argument, P = sum a_i g_i + sum bs_i h_i + c u (NIProver's P + (x c) u, inner_product_prover.py:25-45,
+ * without the caller first evaluating P): one multiexp over [u | g | h], served by the same table as bp_ipa_prove_hs. */
+int bp_ipa_statement(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64], const uint8_t* a32, const uint8_t* bs32,
+                     const uint8_t c32[32], size_t n, uint8_t P_out64[64]);
 
 /* Verifier1 + Verifier2 in one device pass (inner_product_verifier.py:44-58 on top of :127-147): additionally checks
  * P_new == P + xc*u and u_new == x*u with xc = x*c, x the Protocol-1 challenge; the Verifier2 equation then uses u_new, P_new */

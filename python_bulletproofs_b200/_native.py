@@ -44,7 +44,8 @@ PROTOTYPES = {
     "bp_lift_x_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p, c_u8p]),
     "bp_rp_verifier_scalars": (ctypes.c_int, [c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
     "bp_rp_prover_poly1": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p]),
-    "bp_rp_prover_poly2": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
+    "bp_rp_prover_poly2": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
+    "bp_ipa_statement": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_fb_set_mode": (ctypes.c_int, [ctypes.c_int]),
     "bp_fb_stats": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)] * 4),
     "bp_fb_clear": (ctypes.c_int, []),
@@ -220,13 +221,13 @@ def rp_prover_poly1(bits, sL_b, sR_b, n, m, y, z):
 
 
 def rp_prover_poly2(bits, sL_b, sR_b, n, m, y, z, x):
-    """(ls, rs, y^-i, z + zz_i y^-i) as packed scalar vectors and t_hat as an int (bp_rp_prover_poly2)."""
+    """(ls, rs, y^-i, z + zz_i y^-i) as packed scalar vectors, t_hat as an int, then rs_i y^-i packed (bp_rp_prover_poly2)."""
     nm = n * m
-    ls, rs, yinv, hsc = (ctypes.create_string_buffer(32 * nm) for _ in range(4))
+    ls, rs, yinv, hsc, rsy = (ctypes.create_string_buffer(32 * nm) for _ in range(5))
     that = ctypes.create_string_buffer(32)
     check(load().bp_rp_prover_poly2(bits, sL_b, sR_b, n, m, (y % Q).to_bytes(32, "little"), (z % Q).to_bytes(32, "little"),
-                                    (x % Q).to_bytes(32, "little"), ls, rs, yinv, hsc, that))
-    return ls.raw, rs.raw, yinv.raw, hsc.raw, int.from_bytes(that.raw, "little")
+                                    (x % Q).to_bytes(32, "little"), ls, rs, yinv, hsc, rsy, that))
+    return ls.raw, rs.raw, yinv.raw, hsc.raw, int.from_bytes(that.raw, "little"), rsy.raw
 
 
 def lift_x_batch(xs, want=None):

@@ -87,7 +87,7 @@ int bp_rp_prover_poly1(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_
 
 int bp_rp_prover_poly2(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_t* sR32, size_t n, size_t m, const uint8_t y32[32],
                        const uint8_t z32[32], const uint8_t x32[32], uint8_t* ls32, uint8_t* rs32, uint8_t* yinv32, uint8_t* hsc32,
-                       uint8_t that_out[32]) {
+                       uint8_t* rsy32, uint8_t that_out[32]) {
   using namespace rpa;
   const size_t nm = n * m;
   if (nm == 0) return fail("bp_rp_prover_poly2: empty vectors");
@@ -109,6 +109,7 @@ int bp_rp_prover_poly2(const uint8_t* aL_bits, const uint8_t* sL32, const uint8_
     st(ls32 + 32 * i, l); st(rs32 + 32 * i, r);
     st(yinv32 + 32 * i, yi);
     st(hsc32 + 32 * i, add(z, mul_sm(c.zz[i], to_m(yi))));                                 // z + zz_i y^-i
+    if (rsy32) st(rsy32 + 32 * i, mul_sm(r, to_m(yi)));                                    // r_i y^-i: coefficient of h_i in P
     yi = mul_sm(yi, yinvM);
   }
   st(that_out, that);
@@ -368,6 +369,35 @@ int bp_ipa_verify1_eq_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* 
   return ipa_verify_eq_impl(g64, h64, hscale32, u_new64, P_new64, n, a32, b32, xs32, Ls64, Rs64, &pr1, accept);
 }
 
+
+// P = sum a_i g_i + sum bs_i h_i + c u  -- the statement of the inner-product argument (inner_product_prover.py:25-45 computes
+// it as P + (x c) u from a P the range prover had to evaluate first, rangeproof_prover.py:78-86).  Over the same point set
+// [u | g | h] and with the same table key as bp_ipa_prove_hs, so a repeated generator set answers from the IPA's own table.
+int bp_ipa_statement(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64], const uint8_t* a32, const uint8_t* bs32,
+                     const uint8_t c32[32], size_t n, uint8_t P_out64[64]) {
+  BP_NEED_INIT();
+  if (n == 0) return fail("bp_ipa_statement: empty vectors");
+  const size_t T = 2 * n + 1;
+  Affine* PA = (Affine*)g.ws_g.ensure(T * sizeof(Affine));
+  Fq* d_sc = (Fq*)g.ws_terms_sc.ensure(T * sizeof(Fq));
+  Affine* d_out = (Affine*)g.ws_lr.ensure(2 * sizeof(Affine));
+  if (!PA || !d_sc || !d_out) return fail("device allocation failed");
+  BP_CUDA(cudaMemcpyAsync(PA, u64_, 64, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(PA + 1, g64, n * 64, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(PA + 1 + n, h64, n * 64, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(d_sc, c32, 32, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(d_sc + 1, a32, n * 32, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(d_sc + 1 + n, bs32, n * 32, cudaMemcpyHostToDevice, g.stream));
+  const Affine* tab = nullptr;
+  if (fb_enabled() && T <= fb.max_points && n > 1) {
+    const FbSrc src = {{u64_, g64, h64}, {64, n * 64, n * 64}, 3};
+    tab = fb_get(src.hash(0x69706131ull), src, PA, T);
+  }
+  if (tab ? fb_msm_run(tab, nullptr, d_sc, nullptr, 1, T, (u32)T, d_out, nullptr) : msm_run(PA, nullptr, d_sc, (u32)T, nullptr, 1, T, d_out, nullptr)) return 1;
+  BP_CUDA(cudaMemcpyAsync(P_out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
 
 int bp_ipa_verify_eq(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64], const uint8_t P64[64], size_t n,
                      const uint8_t a32[32], const uint8_t b32[32], const uint8_t* xs32, const uint8_t* Ls64,

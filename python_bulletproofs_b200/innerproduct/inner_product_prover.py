@@ -26,7 +26,7 @@ class NIProver:
         self.transcript = Transcript(seed)
         self._h_scale = _h_scale      # private: effective generators are _h_scale[i] * h[i] (never materialised)
         self._P_msm = _P_msm          # private: P given as (points, scalars) of an MSM not yet evaluated (P may be None)
-        # private: wire-form operands from the range prover's C algebra -- dict(n, g, h, a, b, h_scale, P_pts, P_sc, P_cnt)
+        # private: wire-form operands from the range prover's C algebra -- dict(n, g, h, a, b, h_scale, bs = b*h_scale)
         # of packed bytes; a, b, _h_scale and _P_msm are then ignored
         self._packed = _packed
 
@@ -37,11 +37,11 @@ class NIProver:
         # is that MSM with one more term: one device pass instead of two (P itself is not part of the proof).
         if self._packed is not None:
             pk = self._packed
-            ub = nat.pack_point(self.u)
-            cnt = pk["P_cnt"]
-            raw = nat.msm_batch_bytes(pk["P_pts"] + ub + ub, pk["P_sc"] + nat.pack_scalar(x * self.c) + nat.pack_scalar(x),
-                                      [0, cnt + 1, cnt + 2])
-            P_new, u_new = Point.from_bytes64(raw, 0), Point.from_bytes64(raw, 64)
+            u_new = PipSECP256k1.multiexp([self.u], [x])
+            out = ctypes.create_string_buffer(64)
+            nat.check(nat.load().bp_ipa_statement(pk["g"], pk["h"], nat.pack_point(u_new), pk["a"], pk["bs"],
+                                                  nat.pack_scalar(self.c), pk["n"], out))
+            P_new = Point.from_bytes64(out.raw, 0)          # = P + (x*c)*u with u_new = x*u:  sum a_i g_i + sum bs_i h_i + c*u_new
         elif self._P_msm is not None:
             pts, scs = self._P_msm
             P_new, u_new = PipSECP256k1.multiexp_batch([list(pts) + [self.u], [self.u]], [list(scs) + [x * self.c], [x]])

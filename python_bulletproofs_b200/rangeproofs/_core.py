@@ -111,7 +111,7 @@ def prove(vs, n, g, h, gs, hs, gammas, u, group, transcript: Transcript):
     x = transcript.get_modp(q)
     transcript.add_number(x)
     xv = x.x
-    ls_b, rs_b, yinv_b, hsc_b, t_hat = nat.rp_prover_poly2(bits, sL_b, sR_b, n, m, yv, zv, xv)
+    ls_b, rs_b, yinv_b, hsc_b, t_hat, rsy_b = nat.rp_prover_poly2(bits, sL_b, sR_b, n, m, yv, zv, xv)
     zpow = zv * zv % q
     gsum = 0
     for j in range(m):
@@ -119,11 +119,11 @@ def prove(vs, n, g, h, gs, hs, gammas, u, group, transcript: Transcript):
         zpow = zpow * zv % q
     taux = (tau2 * xv * xv + tau1 * xv + gsum) % q
     mu = (alpha + rho * xv) % q
-    # P - mu*h = A + x*S - mu*h + sum(-z * gs_i) + sum((z + zz_i*y^-i) * hs_i), handed to Protocol 1 unevaluated
-    packed = {"n": nm, "g": gs_b, "h": hs_b, "a": ls_b, "b": rs_b, "h_scale": yinv_b,
-              "P_pts": nat.pack_point(A) + nat.pack_point(S) + h_b + gs_b + hs_b,
-              "P_sc": nat.pack_scalars([1, xv, -mu]) + nat.pack_scalar(-zv) * nm + hsc_b,
-              "P_cnt": 3 + 2 * nm}
+    # P = A + x*S - mu*h + sum(-z * gs_i) + sum((z + zz_i*y^-i) * hs_i) (rangeproof_prover.py:78-86) is, in the prover's own
+    # scalars, sum l_i gs_i + sum (r_i y^-i) hs_i (the h terms cancel: mu = alpha + rho x).  Protocol 1 therefore gets its
+    # statement P + (x1 t_hat) u as ONE multiexp over the fixed generators (bp_ipa_statement, served by the IPA's table);
+    # A and S, which change with every proof, never enter a multiexp again.
+    packed = {"n": nm, "g": gs_b, "h": hs_b, "a": ls_b, "b": rs_b, "h_scale": yinv_b, "bs": rsy_b}
     inner = NIProver(gs, hs, u, None, ModP(t_hat, q), None, None, group, _packed=packed)
     return Proof(ModP(taux, q), ModP(mu, q), ModP(t_hat, q), T1, T2, A, S, inner.prove(), transcript.digest)
 

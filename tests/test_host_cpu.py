@@ -217,6 +217,7 @@ def test_host_c_range_proof_algebra_matches_python_formulas():
         got = nat.rp_prover_poly2(bits, sLb, sRb, n, m, y, z, x)
         assert [nat.unpack_scalars(got[k], nm) for k in range(4)] == [ls, rs, yinv, hsc]
         assert got[4] == sum(a * b for a, b in zip(ls, rs)) % q
+        assert nat.unpack_scalars(got[5], nm) == [r * yi % q for r, yi in zip(rs, yinv)]
         zp = [pow(z, j + 2, q) for j in range(m + 1)]
         delta = ((z - z * z) * sum(ypow) - sum(zp[j] * (2 ** n - 1) for j in range(1, m + 1))) % q
         vy, vh, vd = nat.rp_verifier_scalars(n, m, y, z)
