@@ -16,6 +16,19 @@ from ..utils.utils import ModP
 from .inner_product_verifier import Proof1, Proof2
 
 
+_U_NEW = {}      # (u.x, u.y, x) -> x*u: with the default seed Protocol 1's challenge is a constant, so is u_new per generator u
+
+
+def _scaled_u(u, x):
+    key = (u.x, u.y, int(x % nat.Q))
+    hit = _U_NEW.get(key)
+    if hit is None:
+        if len(_U_NEW) > 256:
+            _U_NEW.clear()
+        hit = _U_NEW[key] = PipSECP256k1.multiexp([u], [x])
+    return hit
+
+
 class NIProver:
     """Protocol 1 (inner_product_prover.py:11-45)."""
 
@@ -37,7 +50,7 @@ class NIProver:
         # is that MSM with one more term: one device pass instead of two (P itself is not part of the proof).
         if self._packed is not None:
             pk = self._packed
-            u_new = PipSECP256k1.multiexp([self.u], [x])
+            u_new = _scaled_u(self.u, x)
             out = ctypes.create_string_buffer(64)
             nat.check(nat.load().bp_ipa_statement(pk["g"], pk["h"], nat.pack_point(u_new), pk["a"], pk["bs"],
                                                   nat.pack_scalar(self.c), pk["n"], out))
