@@ -82,6 +82,10 @@ int bp_fb_set_mode(int mode);
 int bp_fb_stats(uint64_t* tables, uint64_t* bytes, uint64_t* hits, uint64_t* builds);
 int bp_fb_clear(void);
 
+/* ---- a + b for two points: fastecdsa Point.__add__ where the reference adds outside a multiexp
+ * (src/innerproduct/inner_product_prover.py:33, src/utils/commitments.py:6).  One launch, one inversion. */
+int bp_point_add(const uint8_t a64[64], const uint8_t b64[64], uint8_t out64[64]);
+
 /* ---- independent scalar multiplications --------------------------------------------------------
  * out[i] = sc[i] * pts[i]:  hsp = [(y.inv() ** i) * hs[i] ...]
  * src/rangeproofs/rangeproof_prover.py:77, rangeproof_verifier.py:72,

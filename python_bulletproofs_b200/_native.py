@@ -41,6 +41,7 @@ PROTOTYPES = {
     "bp_msm_stage_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "bp_msm_accumulate_kernel_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "bp_scalar_mul_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p]),
+    "bp_point_add": (ctypes.c_int, [c_u8p, c_u8p, c_u8p]),
     "bp_lift_x_batch": (ctypes.c_int, [c_u8p, c_u8p, c_sz, c_u8p, c_u8p]),
     "bp_rp_verifier_scalars": (ctypes.c_int, [c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p]),
     "bp_rp_prover_poly1": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_u8p, c_u8p, c_u8p]),

@@ -789,6 +789,29 @@ extern "C" int bp_lift_x_batch(const uint8_t* xs32, const uint8_t* want, size_t 
   return 0;
 }
 
+// ---- a + b for two affine points (fastecdsa Point.__add__ as the reference uses it outside multiexps, e.g.
+// /root/reference/src/innerproduct/inner_product_prover.py:33, /root/reference/src/utils/commitments.py:6) ---------------
+namespace bp {
+__global__ void __launch_bounds__(32) k_point_add(const Affine* __restrict__ ab, Affine* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  XYZZ acc = xyzz_from_affine(ld_affine(ab));
+  Affine b = ld_affine(ab + 1);
+  xyzz_madd_ni(acc, b);                              // complete: identity operands, a = b, a = -b
+  st_affine(out, xyzz_to_affine(acc, true));
+}
+}  // namespace bp
+extern "C" int bp_point_add(const uint8_t a64[64], const uint8_t b64[64], uint8_t out64[64]) {
+  BP_NEED_INIT();
+  Affine* d = (Affine*)g.ws_lr.ensure(4 * sizeof(Affine));
+  if (!d) return fail("device allocation failed");
+  BP_CUDA(cudaMemcpyAsync(d, a64, 64, cudaMemcpyHostToDevice, g.stream));
+  BP_CUDA(cudaMemcpyAsync(d + 1, b64, 64, cudaMemcpyHostToDevice, g.stream));
+  k_point_add<<<1, 32, 0, g.stream>>>(d, d + 2);
+  BP_CUDA(cudaMemcpyAsync(out64, d + 2, 64, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
 // ---- arithmetic self-test hooks (used by tests/: known-answer tests vs Python big ints) -----------
 namespace bp {
 __global__ void k_test_fp(int op, const Fp* a, const Fp* b, u32 n, Fp* out) {

@@ -59,7 +59,9 @@ class NIProver:
             pts, scs = self._P_msm
             P_new, u_new = PipSECP256k1.multiexp_batch([list(pts) + [self.u], [self.u]], [list(scs) + [x * self.c], [x]])
         else:
-            P_new, u_new = PipSECP256k1.multiexp_batch([[self.P, self.u], [self.u]], [[1, x * self.c], [x]])
+            # u_new = x*u (cached per generator), P_new = P + (x*c)*u: a one-term multiexp on u (table) and one point addition
+            u_new = _scaled_u(self.u, x)
+            P_new = self.P + PipSECP256k1.multiexp([self.u], [x * self.c])
         inner = FastNIProver2(self.g, self.h, u_new, P_new, self.a, self.b, self.group, self.transcript.digest,
                               _h_scale=self._h_scale, _packed=self._packed)
         return Proof1(u_new, P_new, inner.prove(), self.transcript.digest)

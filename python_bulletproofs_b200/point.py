@@ -1,11 +1,13 @@
 """Point type with the surface the reference uses from fastecdsa.point.Point
 (`.x .y .curve`, `IDENTITY_ELEMENT`, `+`, `int * Point`, `==`).
 
-The group law itself runs on the GPU: `P + Q` and `k * P` are 2- and 1-term calls into the
-CUDA MSM (libbpgpu, no CPU fallback).  They exist for API compatibility (e.g. `commitment`,
+The group law itself runs on the GPU: `P + Q` is one launch of the complete addition (bp_point_add), `k * P` a 1-term
+call into the CUDA MSM (libbpgpu, no CPU fallback).  They exist for API compatibility (e.g. `commitment`,
 utils/commitments.py); the provers/verifiers of this package batch their point work into
 larger device calls instead of using these operators in loops.
 """
+import ctypes
+
 from . import _native as nat
 from .curve import secp256k1
 
@@ -36,8 +38,9 @@ class Point:
     def __add__(self, other):
         if not hasattr(other, "x") or not hasattr(other, "curve"):
             return NotImplemented
-        one = (1).to_bytes(32, "little")
-        return Point.from_bytes64(nat.msm_bytes(nat.pack_point(self) + nat.pack_point(other), one + one, 2))
+        out = ctypes.create_string_buffer(64)
+        nat.check(nat.load().bp_point_add(nat.pack_point(self), nat.pack_point(other), out))
+        return Point.from_bytes64(out.raw, 0)
 
     def __radd__(self, other):
         return self.__add__(other)

@@ -150,3 +150,18 @@ def test_bytes_to_points_decompresses_like_bytes_to_point():
     assert [(p.x, p.y) for p in b64_to_points([point_to_b64(p) for p in pts[:50]])] == [(p.x, p.y) for p in pts[:50]]
     with pytest.raises(ValueError):
         bytes_to_points([b"\x02" + (5).to_bytes(32, "big")])     # x = 5: x^3 + 7 = 132 is not a square mod p
+
+
+def test_point_add_entry_point_is_complete():
+    """bp_point_add (Point.__add__): random pairs and every exceptional case of the group law vs the oracle."""
+    from python_bulletproofs_b200 import _native as nat
+    from helpers import fast_points
+    import ctypes
+    pts = fast_points(24, 31337)
+    P0, P1 = pts[0], pts[1]
+    cases = [(P0, P1), (P0, P0), (P0, (P0[0], P - P0[1])), (None, P0), (P0, None), (None, None)] + list(zip(pts[2:13], pts[13:24]))
+    lib = nat.load()
+    out = ctypes.create_string_buffer(64)
+    for a, b in cases:
+        nat.check(lib.bp_point_add(ecc.pack_point(a), ecc.pack_point(b), out))
+        assert ecc.unpack_point(out.raw) == ecc.py_add(a, b), (a, b)
