@@ -567,15 +567,15 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
     cur = chunk_no & 1;
     if (chunk_no >= 2) BP_CUDA(cudaEventSynchronize(g.stage_ev[cur]));       // staging buffer free again?
     auto t_h0 = std::chrono::steady_clock::now();
-    {   // host: transcript checks of this chunk on all cores
-      std::vector<std::thread> th;
-      unsigned nt = nthreads > cn ? (unsigned)cn : nthreads;
-      size_t per = (cn + nt - 1) / nt;
-      for (unsigned t = 0; t < nt; t++) {
-        size_t lo = chunk_lo + t * per, hi = lo + per < chunk_hi ? lo + per : chunk_hi;
-        if (lo < hi) th.emplace_back(work, lo, hi);
+    {   // host: transcript checks of this chunk on all cores (OpenMP keeps its worker pool alive between chunks and calls;
+        // creating 16 std::threads per chunk cost ~0.4 ms each time)
+      const long nt = (long)(nthreads > cn ? (unsigned)cn : nthreads);
+      const size_t per = (cn + (size_t)nt - 1) / (size_t)nt;
+#pragma omp parallel for schedule(static, 1) num_threads((int)nt)
+      for (long t = 0; t < nt; t++) {
+        size_t lo = chunk_lo + (size_t)t * per, hi = lo + per < chunk_hi ? lo + per : chunk_hi;
+        if (lo < hi) work(lo, hi);
       }
-      for (auto& t : th) t.join();
     }
     if (getenv("BP_VERIFY_TIMING")) fprintf(stderr, "chunk %d: host %.3f ms (%u threads)\n", chunk_no,
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h0).count(), nthreads);
