@@ -66,6 +66,9 @@ int bp_msm_set_window(int c);
 int bp_msm_last_window(void);
 int bp_msm_last_entries(uint64_t* entries);   /* mixed additions (non-zero signed digits) of the last MSM */
 int bp_msm_set_profiling(int on);
+/* kernels this library has launched so far in this process (kernel nodes of a replayed CUDA graph count at every replay);
+ * bench.py reports the difference across its timed region as "gpu_launches" */
+int bp_launch_count(uint64_t* launches);
 /* single MSMs with at least this many terms run with their windows pipelined over streams (0 = never) */
 int bp_msm_set_pipeline_min(size_t min_terms);
 int bp_msm_stage_ms(float out7[7]);

@@ -37,6 +37,7 @@ PROTOTYPES = {
     "bp_msm_last_window": (ctypes.c_int, []),
     "bp_msm_last_entries": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)]),
     "bp_msm_set_profiling": (ctypes.c_int, [ctypes.c_int]),
+    "bp_launch_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)]),
     "bp_msm_set_pipeline_min": (ctypes.c_int, [c_sz]),
     "bp_msm_stage_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "bp_msm_accumulate_kernel_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
@@ -132,6 +133,8 @@ def pack_point(pt):
     if pt is None:
         return _ZERO64
     if isinstance(pt, tuple):
+        if not (0 <= pt[0] < P and 0 <= pt[1] < P and (pt[1] * pt[1] - pt[0] * pt[0] * pt[0] - 7) % P == 0):
+            raise ValueError("coordinates are not on curve <secp256k1>")
         return pack_xy(pt[0], pt[1])
     if getattr(pt, "curve", True) is None:
         return _ZERO64
@@ -188,6 +191,8 @@ def msm_bytes(pts_b, sc_b, n):
 
 def msm_batch_bytes(pts_b, sc_b, offsets):
     nmsm = len(offsets) - 1
+    if len(pts_b) != 64 * offsets[-1] or len(sc_b) != 32 * offsets[-1]:     # the C side copies offsets[-1] records
+        raise AssertionError("msm_batch_bytes: %d point bytes / %d scalar bytes for %d terms" % (len(pts_b), len(sc_b), offsets[-1]))
     out = ctypes.create_string_buffer(64 * max(nmsm, 1))
     off = (ctypes.c_uint32 * len(offsets))(*offsets)
     check(load().bp_msm_batch(pts_b, sc_b, off, nmsm, out))

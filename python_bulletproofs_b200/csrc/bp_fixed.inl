@@ -5,7 +5,7 @@
 
 // `src` = the generator bytes the table was built from: a cache hit is confirmed by comparing them (a 64-bit hash alone
 // would let two different generator sets share a table)
-struct FbEntry { Affine* tab; size_t n; size_t bytes; unsigned long long stamp; std::vector<uint8_t> src; };
+struct FbEntry { Affine* tab; size_t n; size_t bytes; unsigned long long stamp; std::vector<uint8_t> src; const Affine* parent = nullptr; };
 struct FbSrc {                           // up to 5 byte ranges that make up a generator set, in hashing order
   const uint8_t* p[5]; size_t len[5]; int cnt;
   uint64_t hash(uint64_t seed) const;
@@ -54,6 +54,10 @@ static void fb_evict_for(size_t need) {
     auto victim = fb.tabs.begin();
     for (auto it = fb.tabs.begin(); it != fb.tabs.end(); ++it) if (it->second.stamp < victim->second.stamp) victim = it;
     cudaStreamSynchronize(g.stream);
+    for (auto it = fb.tabs16.begin(); it != fb.tabs16.end();) {      // a 16-bit table is only valid next to the byte table it was built from
+      if (it->second.parent == victim->second.tab) { cudaFree(it->second.tab); fb.bytes -= it->second.bytes; it = fb.tabs16.erase(it); }
+      else ++it;
+    }
     cudaFree(victim->second.tab);
     fb.bytes -= victim->second.bytes;
     fb.tabs.erase(victim);
@@ -86,7 +90,7 @@ static const Affine* fb_get(uint64_t key, const FbSrc& src, const Affine* d_pts,
   if (cudaMalloc((void**)&tab, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   for (size_t g0 = 0; g0 < n; g0 += BP_FB_BUILD_GENS) {
     const u32 ng = (u32)(n - g0 < BP_FB_BUILD_GENS ? n - g0 : BP_FB_BUILD_GENS);
-    k_fb_build<<<(ng * BP_FB_WINDOWS + 63) / 64, 64, 0, g.stream>>>(d_pts, (u32)g0, ng, scratch, tab);
+    ++g.nlaunch, k_fb_build<<<(ng * BP_FB_WINDOWS + 63) / 64, 64, 0, g.stream>>>(d_pts, (u32)g0, ng, scratch, tab);
   }
   if (cudaGetLastError() != cudaSuccess) { cudaFree(tab); return nullptr; }
   fb.tabs[key] = FbEntry{tab, n, bytes, ++fb.clock, src.copy()};
@@ -101,7 +105,13 @@ static const Affine* fb_get16(uint64_t key, const Affine* tab8, size_t n) {
   if (!tab8 || n == 0 || n > 512) return nullptr;
   key ^= (uint64_t)n * 0xD6E8FEB86659FD93ull;
   auto it = fb.tabs16.find(key);
-  if (it != fb.tabs16.end() && it->second.n == n) { it->second.stamp = ++fb.clock; return it->second.tab; }
+  if (it != fb.tabs16.end()) {
+    // confirmed through its parent: `tab8` was matched byte for byte against the caller's generators (fb_get), and this entry
+    // was built from exactly that table; anything else under the same key is a collision and keeps the byte table
+    if (it->second.n != n || it->second.parent != tab8) return nullptr;
+    it->second.stamp = ++fb.clock;
+    return it->second.tab;
+  }
   if (fb.mode == 1) {
     if (fb.seen16.size() > 8192) fb.seen16.clear();
     if (++fb.seen16[key] < 2) return nullptr;
@@ -111,9 +121,9 @@ static const Affine* fb_get16(uint64_t key, const Affine* tab8, size_t n) {
   Affine* tab = nullptr;
   if (cudaMalloc((void**)&tab, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   const size_t threads = n * BP_FB16_WINDOWS * 256;
-  k_fb_build16<<<(unsigned)((threads + 127) / 128), 128, 0, g.stream>>>(tab8, (u32)n, tab);
+  ++g.nlaunch, k_fb_build16<<<(unsigned)((threads + 127) / 128), 128, 0, g.stream>>>(tab8, (u32)n, tab);
   if (cudaGetLastError() != cudaSuccess) { cudaFree(tab); return nullptr; }
-  fb.tabs16[key] = FbEntry{tab, n, bytes, ++fb.clock, {}};      // (valid only together with its confirmed byte table)
+  fb.tabs16[key] = FbEntry{tab, n, bytes, ++fb.clock, {}, tab8};
   fb.bytes += bytes;
   fb.builds++;
   return tab;
@@ -128,10 +138,10 @@ static int fb_msm_run(const Affine* tab, const u32* d_idx, const Fq* d_sc, const
   if (nmsm > 65535) return fail("fb_msm_run: too many MSMs in one launch");
   XYZZ* part = (XYZZ*)fb.blockpart.ensure((size_t)nmsm * nbx * sizeof(XYZZ));
   if (!part) return fail("workspace allocation failed");
-  k_fb_msm<<<dim3(nbx, nmsm), 256, 0, g.stream>>>(tab, d_idx, d_sc, d_offsets, single_n, part);
+  ++g.nlaunch, k_fb_msm<<<dim3(nbx, nmsm), 256, 0, g.stream>>>(tab, d_idx, d_sc, d_offsets, single_n, part);
   u32 nq = 8;
   while (nq < nbx && nq < 64) nq <<= 1;
-  k_fb_finish<<<nmsm, 4 * nq, 0, g.stream>>>(part, nbx, out_affine, out_xyzz);
+  ++g.nlaunch, k_fb_finish<<<nmsm, 4 * nq, 0, g.stream>>>(part, nbx, out_affine, out_xyzz);
   BP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -36,19 +36,25 @@ int fail(const char* fmt, ...) {
 // ---- the MSM pipeline on device-resident operands ----------------------------------------------
 // points/point_idx/scalars/offsets are device pointers; out_affine/out_xyzz device (either may be null)
 static int msm_run_pipelined(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, Affine* out_affine, XYZZ* out_xyzz);
+// Per-call options of msm_run (passed by value: nothing a failed call could leave behind for the next one).
+//   skip_below  terms whose point index is below this count as zero scalars (the caller evaluates them elsewhere, see k_digits)
+//   pts_ready   event the points are complete at (host-operand MSM whose points upload on the copy stream)
+//   halves      the points arrive in two parts (g.ev_half[0], g.ev_half[1]), the first `split` terms first (upload_operands)
+struct MsmOpts { u32 skip_below = 0; cudaEvent_t pts_ready = nullptr; bool halves = false; size_t split = 0; };
 int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, const u32* d_offsets, u32 nmsm,
-            size_t terms_per_msm, Affine* out_affine, XYZZ* out_xyzz) {
+            size_t terms_per_msm, Affine* out_affine, XYZZ* out_xyzz, MsmOpts opt = MsmOpts()) {
   if (nmsm == 1 && T >= g.pipeline_min_terms && !g.profiling) {
-    if (g.pts_ready) { BP_CUDA(cudaStreamWaitEvent(g.stream, g.pts_ready, 0)); g.pts_ready = nullptr; }
+    if (opt.pts_ready) BP_CUDA(cudaStreamWaitEvent(g.stream, opt.pts_ready, 0));
+    if (opt.halves) BP_CUDA(cudaStreamWaitEvent(g.stream, g.ev_half[1], 0));
     return msm_run_pipelined(points, point_idx, scalars, T, out_affine, out_xyzz);
   }
   cudaStream_t st = g.stream;
   // host-operand MSM whose points are still arriving in two halves (upload_operands): run it as TWO half-size MSMs over one
   // digit/sort pass -- buckets (half, unit, digit) -- accumulate the first half while the second is on the wire, reduce both
   // in one batch of tails and add the two results
-  const bool halves = g.halves_pending && nmsm == 1 && !point_idx && !d_offsets && T >= 4;
-  g.halves_pending = false;
-  const u32 T_half = halves && g.halves_split > 0 && g.halves_split < T ? (u32)g.halves_split : T / 2;   // terms in the first part
+  const bool halves = opt.halves && nmsm == 1 && !point_idx && !d_offsets && T >= 4;
+  if (opt.halves && !halves) BP_CUDA(cudaStreamWaitEvent(st, g.ev_half[1], 0));      // (cannot happen today: such MSMs have >= 2^17 terms)
+  const u32 T_half = halves && opt.split > 0 && opt.split < T ? (u32)opt.split : T / 2;   // terms in the first part
   XYZZ* pair_out = nullptr;
   Affine* final_affine = out_affine; XYZZ* final_xyzz = out_xyzz;
   if (halves) {
@@ -67,7 +73,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   bool prof = g.profiling;
   if (prof) for (int i = 0; i < 7; i++) cudaEventRecord(g.ev[i], st), (void)0;
   if (T == 0) {   // all identities
-    if (g.pts_ready) { cudaStreamWaitEvent(st, g.pts_ready, 0); g.pts_ready = nullptr; }
+    if (opt.pts_ready) cudaStreamWaitEvent(st, opt.pts_ready, 0);
     BP_CUDA(cudaMemsetAsync(out_affine ? (void*)out_affine : (void*)out_xyzz, 0, out_affine ? nmsm * sizeof(Affine) : nmsm * sizeof(XYZZ), st));
     if (out_affine && out_xyzz) BP_CUDA(cudaMemsetAsync(out_xyzz, 0, nmsm * sizeof(XYZZ), st));
     return 0;
@@ -96,14 +102,14 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
 
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
   if (prof) cudaEventRecord(g.ev[0], st);
-  k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count, g.msm_skip_below ? point_idx : nullptr, g.msm_skip_below);
+  ++g.nlaunch, k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count, opt.skip_below ? point_idx : nullptr, opt.skip_below);
   if (prof) cudaEventRecord(g.ev[1], st);
-  k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
-  k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
-  k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
+  ++g.nlaunch, k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
+  ++g.nlaunch, k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
+  ++g.nlaunch, k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
   if (prof) cudaEventRecord(g.ev[2], st);
   BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));   // cursors start at the bucket offsets
-  k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, cursor, entries);
+  ++g.nlaunch, k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, cursor, entries);
   if (prof) cudaEventRecord(g.ev[3], st);
   BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));          // empty buckets = identity (ZZ = 0)
   BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
@@ -113,43 +119,43 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     for (int k = 0; k < 2; k++) {
       const u32 t0 = k ? T_half : 0, tn = k ? T - T_half : T_half;
       BP_CUDA(cudaStreamWaitEvent(st, g.ev_half[k], 0));    // this half of the points has landed
-      k_phi<<<(tn + 127) / 128, 128, 0, st>>>(points + t0, nullptr, tn, phi + t0);
+      ++g.nlaunch, k_phi<<<(tn + 127) / 128, 128, 0, st>>>(points + t0, nullptr, tn, phi + t0);
       const u32* gs = k ? start + hb : zero_word;
       XYZZ* part_k = part + 2 * (size_t)k * hchunks;
       if (prof && k == 0) cudaEventRecord(g.ev_k0, st);
-      k_accumulate<<<(unsigned)((hchunks + 127) / 128), 128, 0, st>>>(points, nullptr, phi, start, entries, gs, start + (k + 1) * hb, sh.chunk, buckets, part_k);
+      ++g.nlaunch, k_accumulate<<<(unsigned)((hchunks + 127) / 128), 128, 0, st>>>(points, nullptr, phi, start, entries, gs, start + (k + 1) * hb, sh.chunk, buckets, part_k);
       if (prof && k == 1) cudaEventRecord(g.ev_k1, st);
       if (k == 1) BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));
-      k_fixup<<<(unsigned)((hb + 127) / 128), 128, 0, st>>>(start, k * hb, hb, gs, sh.chunk, part_k, buckets, big, big + 1);
-      k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, gs, sh.chunk, part_k, buckets, big, big + 1);
+      ++g.nlaunch, k_fixup<<<(unsigned)((hb + 127) / 128), 128, 0, st>>>(start, k * hb, hb, gs, sh.chunk, part_k, buckets, big, big + 1);
+      ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, gs, sh.chunk, part_k, buckets, big, big + 1);
     }
   } else {
-    if (g.pts_ready) { BP_CUDA(cudaStreamWaitEvent(st, g.pts_ready, 0)); g.pts_ready = nullptr; }   // points may still be uploading
-    k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
+    if (opt.pts_ready) BP_CUDA(cudaStreamWaitEvent(st, opt.pts_ready, 0));   // points may still be uploading
+    ++g.nlaunch, k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
     // E (= start[nb]) stays on the device: launch for the upper bound W*T, threads past E exit at once
     if (prof) cudaEventRecord(g.ev_k0, st);
-    k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
+    ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
     if (prof) cudaEventRecord(g.ev_k1, st);
-    k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big + 1);
-    k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
+    ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big + 1);
+    ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
   }
   if (prof) cudaEventRecord(g.ev[4], st);
   size_t nsegs = nmw * sh.nseg;
   const bool plain_tails = nmsm >= 2048 && sh.H <= 512;     // big batch of small MSMs: throughput forms
   const XYZZ* ws;
   if (plain_tails) {
-    k_reduce_unit_plain<<<(unsigned)((nmw + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);
+    ++g.nlaunch, k_reduce_unit_plain<<<(unsigned)((nmw + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);
     ws = segsum;
     if (prof) cudaEventRecord(g.ev[5], st);
     // Horner + output: one thread per MSM saturates the machine only for very many MSMs; below that the chain of
     // ~126 doublings is pure latency and the 4-lane form (2.3 -> 1.3 us per doubling) wins
-    if (nmsm <= 12288 && !out_affine) k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
-    else k_combine_plain<<<(unsigned)((nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+    if (nmsm <= 12288 && !out_affine) ++g.nlaunch, k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+    else ++g.nlaunch, k_combine_plain<<<(unsigned)((nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
   } else {
     XYZZ* seg_run = (XYZZ*)g.ws_segrun.ensure(nsegs * sizeof(XYZZ));
     if (!seg_run) return fail("workspace allocation failed");
-    if (sh.seg_plain) k_reduce_seg_plain<<<(unsigned)((nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
-    else k_reduce_seg<<<(unsigned)((4 * nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
+    if (sh.seg_plain) ++g.nlaunch, k_reduce_seg_plain<<<(unsigned)((nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
+    else ++g.nlaunch, k_reduce_seg<<<(unsigned)((4 * nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
     // level 2: groups of G = 8 segments (measured at 2^20, c = 16 after the thread-per-segment first level:
     // G = 4 / 8 / 16 / 32 -> reduce stage 0.390 / 0.296 / 0.335 / 0.423 ms; the quad form pays ~2.4x the multiplications'
     // issue cost in glue, so many small groups turn it throughput bound)
@@ -162,21 +168,21 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     while ((1u << ubits) < ngrp * (1u + sh.dbl)) ubits++;
     XYZZ* grpsum = (XYZZ*)g.ws_grpsum.ensure(nmw * ngrp * sizeof(XYZZ));
     if (!grpsum) return fail("workspace allocation failed");
-    k_reduce_grp<<<(unsigned)((4 * nmw * ngrp + 127) / 128), 128, 0, st>>>(seg_run, segsum, sh, nmw, 0, G, lgS, lgG, ubits, grpsum);
+    ++g.nlaunch, k_reduce_grp<<<(unsigned)((4 * nmw * ngrp + 127) / 128), 128, 0, st>>>(seg_run, segsum, sh, nmw, 0, G, lgS, lgG, ubits, grpsum);
     ws = grpsum;
     if (ngrp >= 1024) {
       // level 3 in two steps: 64 quads per block sum 256 groups each, then one small block per unit adds the partials
       const u32 split = ngrp / 256;   // ngrp is a power of two
       XYZZ* partial = (XYZZ*)g.ws_winpart.ensure(nmw * split * sizeof(XYZZ));
       if (!partial) return fail("workspace allocation failed");
-      k_window_sum<<<(unsigned)(nmw * split), 256, 0, st>>>(grpsum, 256, partial);
-      k_window_sum<<<(unsigned)nmw, split < 8 ? 32 : 4 * split, 0, st>>>(partial, split, winsum);
+      ++g.nlaunch, k_window_sum<<<(unsigned)(nmw * split), 256, 0, st>>>(grpsum, 256, partial);
+      ++g.nlaunch, k_window_sum<<<(unsigned)nmw, split < 8 ? 32 : 4 * split, 0, st>>>(partial, split, winsum);
       ws = winsum;
-    } else if (ngrp > 1) { k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(grpsum, ngrp, winsum); ws = winsum; }
+    } else if (ngrp > 1) { ++g.nlaunch, k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(grpsum, ngrp, winsum); ws = winsum; }
     if (prof) cudaEventRecord(g.ev[5], st);
-    k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+    ++g.nlaunch, k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
   }
-  if (halves) k_xyzz_pair<<<1, 32, 0, st>>>(pair_out, final_affine, final_xyzz);      // result = half 0 + half 1
+  if (halves) ++g.nlaunch, k_xyzz_pair<<<1, 32, 0, st>>>(pair_out, final_affine, final_xyzz);      // result = half 0 + half 1
   if (prof) cudaEventRecord(g.ev[6], st);
   BP_CUDA(cudaGetLastError());
   return 0;
@@ -229,13 +235,13 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
   if (g.profiling) cudaEventRecord(g.ev[0], st);
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(big, 0, W * (big_cap + 2) * sizeof(u32), st));
-  k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
-  k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, nullptr, 1, sh, digits, count, nullptr, 0);
-  k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
-  k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
-  k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
+  ++g.nlaunch, k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
+  ++g.nlaunch, k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, nullptr, 1, sh, digits, count, nullptr, 0);
+  ++g.nlaunch, k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
+  ++g.nlaunch, k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
+  ++g.nlaunch, k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
   BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
-  k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, nullptr, 1, sh, cursor, entries);
+  ++g.nlaunch, k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, nullptr, 1, sh, cursor, entries);
   BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));
   BP_CUDA(cudaEventRecord(g.pe_prep, st));
   BP_CUDA(cudaStreamWaitEvent(g.ps_acc[0], g.pe_prep, 0));
@@ -246,23 +252,23 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
     const u32* gs = start + (size_t)w * sh.H;
     XYZZ* part_w = part + 2 * (size_t)w * wchunks;
     u32* big_w = big + (size_t)w * (big_cap + 2);
-    k_accumulate<<<(unsigned)((wchunks + 127) / 128), 128, g.pipe_acc_smem, sa>>>(points, point_idx, phi, start, entries, gs, gs + sh.H, sh.chunk, buckets, part_w);
+    ++g.nlaunch, k_accumulate<<<(unsigned)((wchunks + 127) / 128), 128, g.pipe_acc_smem, sa>>>(points, point_idx, phi, start, entries, gs, gs + sh.H, sh.chunk, buckets, part_w);
     BP_CUDA(cudaEventRecord(g.pe_acc[w], sa));
     BP_CUDA(cudaStreamWaitEvent(sr, g.pe_acc[w], 0));
     // everything after the accumulation of window w is a latency chain on few SMs: it lives on the window's own stream
-    k_fixup<<<(unsigned)((sh.H + 63) / 64), 64, 0, sr>>>(start, (size_t)w * sh.H, sh.H, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
-    k_fixup_big<<<32, 64, 0, sr>>>(start, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
+    ++g.nlaunch, k_fixup<<<(unsigned)((sh.H + 63) / 64), 64, 0, sr>>>(start, (size_t)w * sh.H, sh.H, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
+    ++g.nlaunch, k_fixup_big<<<32, 64, 0, sr>>>(start, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
     const XYZZ* bw = buckets + (size_t)w * sh.H;
-    k_reduce_seg<<<(unsigned)((4 * (size_t)sh.nseg + 31) / 32), 32, 0, sr>>>(bw, sh, 1, seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg);
-    k_reduce_grp<<<(unsigned)((4 * (size_t)ngrp + 31) / 32), 32, 0, sr>>>(seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg, sh, 1, (u32)w, G, lgS, lgG,
+    ++g.nlaunch, k_reduce_seg<<<(unsigned)((4 * (size_t)sh.nseg + 31) / 32), 32, 0, sr>>>(bw, sh, 1, seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg);
+    ++g.nlaunch, k_reduce_grp<<<(unsigned)((4 * (size_t)ngrp + 31) / 32), 32, 0, sr>>>(seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg, sh, 1, (u32)w, G, lgS, lgG,
                                                                               ubits, grpsum + (size_t)w * ngrp);
-    if (ngrp > 1) k_window_sum<<<1, 64, 0, sr>>>(grpsum + (size_t)w * ngrp, ngrp, winsum + w);
+    if (ngrp > 1) ++g.nlaunch, k_window_sum<<<1, 64, 0, sr>>>(grpsum + (size_t)w * ngrp, ngrp, winsum + w);
     else BP_CUDA(cudaMemcpyAsync(winsum + w, grpsum + (size_t)w * ngrp, sizeof(XYZZ), cudaMemcpyDeviceToDevice, sr));
     BP_CUDA(cudaEventRecord(g.pe_red[w], sr));
     BP_CUDA(cudaStreamWaitEvent(shh, g.pe_red[w], 0));
-    k_horner_step<<<1, 32, 0, shh>>>(hacc, winsum + w, (sh.dbl && w == (int)W - 2) ? 0 : sh.c, w == (int)W - 1 ? 1 : 0);
+    ++g.nlaunch, k_horner_step<<<1, 32, 0, shh>>>(hacc, winsum + w, (sh.dbl && w == (int)W - 2) ? 0 : sh.c, w == (int)W - 1 ? 1 : 0);
   }
-  k_finish<<<1, 32, 0, g.ps_hor>>>(hacc, out_affine, out_xyzz);
+  ++g.nlaunch, k_finish<<<1, 32, 0, g.ps_hor>>>(hacc, out_affine, out_xyzz);
   BP_CUDA(cudaEventRecord(g.pe_done, g.ps_hor));
   BP_CUDA(cudaStreamWaitEvent(st, g.pe_done, 0));
   // the accumulate streams also rejoin (their last events precede pe_done through the dependency chain)
@@ -276,7 +282,8 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
 // Host operands -> device: scalars first on the compute stream (the digit/sort stages only need them), points on a
 // second stream so that their (twice as large) upload overlaps those stages; msm_run waits for the points right
 // before the first kernel that reads them.  The pipelined/profiling paths simply wait up front.
-static int upload_operands(Affine* d_pts, const uint8_t* pts64, Fq* d_sc, const uint8_t* sc32, size_t n) {
+static int upload_operands(Affine* d_pts, const uint8_t* pts64, Fq* d_sc, const uint8_t* sc32, size_t n, MsmOpts* opt) {
+  *opt = MsmOpts();
   BP_CUDA(cudaEventRecord(g.ev_copy_gate, g.stream));                     // earlier work may still read d_pts
   BP_CUDA(cudaStreamWaitEvent(g.copy_stream, g.ev_copy_gate, 0));
   if (n >= ((size_t)1 << 17) && g.force_c == 0 && !g.profiling && n < g.pipeline_min_terms) {
@@ -284,7 +291,7 @@ static int upload_operands(Affine* d_pts, const uint8_t* pts64, Fq* d_sc, const 
     // each at full link speed; msm_run sorts as soon as the scalars are in and accumulates half by half (see there)
     // first part 3/8 of the points: its accumulation then ends about when the rest has landed (measured link / kernel rates)
     const size_t h = n * 3 / 8;
-    g.halves_split = h;
+    opt->split = h;
     BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.copy_stream));
     BP_CUDA(cudaEventRecord(g.ev_sc, g.copy_stream));
     BP_CUDA(cudaMemcpyAsync(d_pts, pts64, h * 64, cudaMemcpyHostToDevice, g.copy_stream));
@@ -292,21 +299,20 @@ static int upload_operands(Affine* d_pts, const uint8_t* pts64, Fq* d_sc, const 
     BP_CUDA(cudaMemcpyAsync(d_pts + h, pts64 + h * 64, (n - h) * 64, cudaMemcpyHostToDevice, g.copy_stream));
     BP_CUDA(cudaEventRecord(g.ev_half[1], g.copy_stream));
     BP_CUDA(cudaStreamWaitEvent(g.stream, g.ev_sc, 0));
-    g.halves_pending = true;
-    g.pts_ready = nullptr;
+    opt->halves = true;
     return 0;
   }
   BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.copy_stream));
   BP_CUDA(cudaEventRecord(g.ev_pts, g.copy_stream));
-  g.pts_ready = g.ev_pts;
+  opt->pts_ready = g.ev_pts;
   return 0;
 }
 
-static int msm_to_host(const Affine* d_pts, const Fq* d_sc, size_t n, uint8_t* out64) {
+static int msm_to_host(const Affine* d_pts, const Fq* d_sc, size_t n, uint8_t* out64, MsmOpts opt = MsmOpts()) {
   Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
-  if (!d_out) return fail("workspace allocation failed");
-  if (msm_run(d_pts, nullptr, d_sc, (u32)n, nullptr, 1, n, d_out, nullptr)) return 1;
+  if (!d_out) { cudaStreamSynchronize(g.copy_stream); return fail("workspace allocation failed"); }
+  if (msm_run(d_pts, nullptr, d_sc, (u32)n, nullptr, 1, n, d_out, nullptr, opt)) { cudaStreamSynchronize(g.copy_stream); return 1; }
   BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
@@ -449,7 +455,10 @@ int bp_init(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail("no CUDA device available (%s): libbpgpu has no CPU fallback", cudaGetErrorString(e)); }
-  if (device < 0) device = 0;
+  if (device < 0) {   // lazy initialisation (first library call without bp_init): one process per GPU under torchrun => LOCAL_RANK
+    const char* lr = getenv("LOCAL_RANK");
+    device = lr && *lr ? atoi(lr) % n : 0;
+  }
   if (device >= n) return fail("bp_init: device %d out of range (%d devices)", device, n);
   BP_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -512,6 +521,7 @@ int bp_msm_last_entries(uint64_t* entries) {      // non-zero digits = mixed add
   *entries = e;
   return 0;
 }
+int bp_launch_count(uint64_t* launches) { *launches = g.nlaunch; return 0; }
 int bp_msm_set_profiling(int on) { g.profiling = on != 0; return 0; }
 int bp_msm_set_pipeline_min(size_t min_terms) { g.pipeline_min_terms = min_terms ? (unsigned)min_terms : 0xFFFFFFFFu; return 0; }
 int bp_msm_stage_ms(float out7[7]) {
@@ -546,8 +556,9 @@ int bp_msm(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64
       return 0;
     }
   }
-  if (upload_operands(d_pts, pts64, d_sc, sc32, n)) return 1;
-  return msm_to_host(d_pts, d_sc, n, out64);
+  MsmOpts opt;
+  if (upload_operands(d_pts, pts64, d_sc, sc32, n, &opt)) return 1;
+  return msm_to_host(d_pts, d_sc, n, out64, opt);
 }
 
 int bp_fb_set_mode(int mode) {
@@ -631,7 +642,7 @@ int bp_xyzz_sum(const uint8_t* partials128, size_t count, uint8_t out64[64]) {
   XYZZ* d_in = (XYZZ*)g.ws_misc.ensure(count * sizeof(XYZZ));
   Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
   BP_CUDA(cudaMemcpyAsync(d_in, partials128, count * 128, cudaMemcpyHostToDevice, g.stream));
-  k_xyzz_sum<<<1, 32, 0, g.stream>>>(d_in, (u32)count, d_out);
+  ++g.nlaunch, k_xyzz_sum<<<1, 32, 0, g.stream>>>(d_in, (u32)count, d_out);
   BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
@@ -685,7 +696,7 @@ int bp_scalar_mul_batch(const uint8_t* pts64, const uint8_t* sc32, size_t n, uin
   if (!d_pts || !d_sc || !d_out) return fail("device allocation failed");
   BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
-  k_scalar_mul<<<(unsigned)((n + 63) / 64), 64, 0, g.stream>>>(d_pts, d_sc, (u32)n, d_out);
+  ++g.nlaunch, k_scalar_mul<<<(unsigned)((n + 63) / 64), 64, 0, g.stream>>>(d_pts, d_sc, (u32)n, d_out);
   BP_CUDA(cudaMemcpyAsync(out64, d_out, n * 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
@@ -722,16 +733,16 @@ static int pipe_probe(int mode, int iters, double* ops_per_s, float* ms_out) {
     int n = pass == 0 ? (iters / 8 > 0 ? iters / 8 : 1) : iters;
     BP_CUDA(cudaEventRecord(g.ev_a, g.stream));
     switch (mode) {
-      case 0: k_pipe_probe<0><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
-      case 1: k_pipe_probe<1><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
-      case 2: k_pipe_probe<2><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
-      case 3: k_pipe_probe<3><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
-      case 4: k_pipe_probe<4><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
-      case 5: k_pipe_probe<5><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
-      case 6: k_pipe_probe<6><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
-      case 7: k_pipe_probe<7><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
-      case 8: k_pipe_probe<8><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
-      case 9: k_pipe_probe<9><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
+      case 0: ++g.nlaunch, k_pipe_probe<0><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 1: ++g.nlaunch, k_pipe_probe<1><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 2: ++g.nlaunch, k_pipe_probe<2><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 3: ++g.nlaunch, k_pipe_probe<3><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 4: ++g.nlaunch, k_pipe_probe<4><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 5: ++g.nlaunch, k_pipe_probe<5><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 6: ++g.nlaunch, k_pipe_probe<6><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
+      case 7: ++g.nlaunch, k_pipe_probe<7><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
+      case 8: ++g.nlaunch, k_pipe_probe<8><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
+      case 9: ++g.nlaunch, k_pipe_probe<9><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
       default: return fail("bp_pipe_probe: mode 0..9");
     }
     BP_CUDA(cudaEventRecord(g.ev_b, g.stream));

@@ -23,8 +23,8 @@ static ChallengeForms challenge_forms(const Fq& x) {
 
 // one folding step on device buffers: P=[u|g|h] (2k each) -> P2=[u|g'|h'] ; a,b (2k) -> a2,b2 (k)
 static int fold_step(const Affine* P, Affine* P2, const Fq* a, const Fq* b, Fq* a2, Fq* b2, u32 k, const ChallengeForms& c) {
-  k_fold_points<<<(2 * k + 1 + 63) / 64, 64, 0, g.stream>>>(P, P2, k, c.x, c.xinv);
-  k_fold_scalars<<<(k + 127) / 128, 128, 0, g.stream>>>(a, b, k, c.xm, c.xim, a2, b2);
+  ++g.nlaunch, k_fold_points<<<(2 * k + 1 + 63) / 64, 64, 0, g.stream>>>(P, P2, k, c.x, c.xinv);
+  ++g.nlaunch, k_fold_scalars<<<(k + 127) / 128, 128, 0, g.stream>>>(a, b, k, c.xm, c.xim, a2, b2);
   BP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -205,8 +205,8 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   BP_CUDA(cudaMemcpyAsync(bA, b32, n * 32, cudaMemcpyHostToDevice, g.stream));
   // scalars may arrive unreduced (ModP.x): a -> a mod q happens in fq_reduce inside k_digits for
   // MSM terms, but the folds need reduced inputs, so reduce once here.
-  k_reduce_scalars<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(aA, (u32)n);
-  k_reduce_scalars<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(bA, (u32)n);
+  ++g.nlaunch, k_reduce_scalars<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(aA, (u32)n);
+  ++g.nlaunch, k_reduce_scalars<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(bA, (u32)n);
   Fq *a = aA, *b = bA;
   // coefficient vectors of the folded generators over the original ones (see k_build_lr_sv); P = PA is never rewritten
   Fq* cg = (Fq*)g.ws_h.ensure(2 * n * sizeof(Fq));
@@ -216,10 +216,10 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   IpaRound* h_rp = (IpaRound*)pin;                 // pinned mirror of the round parameters
   uint8_t* h_lr = pin + 256;                       // pinned landing zone of L, R
   Fq* ch = cg + n;
-  k_fill_one_mont<<<(unsigned)((2 * n + 127) / 128), 128, 0, g.stream>>>(cg, (u32)(2 * n));
+  ++g.nlaunch, k_fill_one_mont<<<(unsigned)((2 * n + 127) / 128), 128, 0, g.stream>>>(cg, (u32)(2 * n));
   if (hscale32) {   // effective generators h_i' = hscale_i * h_i (e.g. y^-i, rangeproof_prover.py:77): start ch there
     BP_CUDA(cudaMemcpyAsync(ch, hscale32, n * 32, cudaMemcpyHostToDevice, g.stream));
-    k_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(ch, (u32)n);
+    ++g.nlaunch, k_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(ch, (u32)n);
   }
   // repeated generator set: L and R come from table lookups over the ORIGINAL generators (the s-vector form never
   // rewrites PA, which is what makes a per-set table usable in every round)
@@ -236,8 +236,8 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   // One round on the stream: parameters up, fold with the previous challenge, L/R terms, batched MSM, L and R down.
   auto enqueue_round = [&]() -> int {
     BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
-    k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
-    k_build_lr_sv<<<1, 256, 0, g.stream>>>(a, b, cg, ch, (u32)n, &d_rp->m, tsc, tidx);
+    ++g.nlaunch, k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
+    ++g.nlaunch, k_build_lr_sv<<<1, 256, 0, g.stream>>>(a, b, cg, ch, (u32)n, &d_rp->m, tsc, tidx);
     if (tab ? fb_msm_run(tab, tidx, tsc, d_off, 2, n1, 0, d_lr, nullptr) : msm_run(PA, tidx, tsc, 2 * n1, d_off, 2, n1, d_lr, nullptr)) return 1;
     BP_CUDA(cudaMemcpyAsync(h_lr, d_lr, 128, cudaMemcpyDeviceToHost, g.stream));
     return 0;
@@ -254,16 +254,20 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
       if (!gexec) gexec = g.ipa_graph_lookup(n, tab);
       if (!gexec) {
         cudaGraph_t graph = nullptr;
+        const unsigned long long l0 = g.nlaunch;
         BP_CUDA(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed));
         int rc = enqueue_round();
+        const unsigned nk = (unsigned)(g.nlaunch - l0);
+        g.nlaunch = l0;                                  // captured, not launched: counted at every cudaGraphLaunch below
         cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
         if (rc || ce != cudaSuccess || !graph) { cudaGetLastError(); return fail("CUDA graph capture of the IPA round failed"); }
         ce = cudaGraphInstantiate(&gexec, graph, 0);
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) { cudaGetLastError(); return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
-        g.ipa_graph_store(n, tab, gexec);
+        g.ipa_graph_store(n, tab, gexec, nk);
       }
       BP_CUDA(cudaGraphLaunch(gexec, g.stream));
+      g.nlaunch += g.ipa_graph_kernels(n, tab);
     }
     BP_CUDA(cudaStreamSynchronize(g.stream));
     memcpy(Ls64 + 64 * round, h_lr, 64);
@@ -280,7 +284,7 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   if (n > 1) {   // last fold: a, b of length 1   (inner_product_prover.py:109-110)
     h_rp->m = 1;
     BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
-    k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
+    ++g.nlaunch, k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
   }
   BP_CUDA(cudaMemcpyAsync(a_out32, a, 32, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaMemcpyAsync(b_out32, b, 32, cudaMemcpyDeviceToHost, g.stream));
@@ -536,8 +540,8 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   BP_CUDA(cudaMemcpyAsync(table + 2 * n, g64, 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n + 1, h64, 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n + 2, u64_, 64, cudaMemcpyHostToDevice, g.stream));
-  k_sum_points<<<1, 128, 0, g.stream>>>(table, (u32)n, table + 2 * n + 3);          // Gsum
-  k_sum_points<<<1, 128, 0, g.stream>>>(table + n, (u32)n, table + 2 * n + 4);      // Hsum
+  ++g.nlaunch, k_sum_points<<<1, 128, 0, g.stream>>>(table, (u32)n, table + 2 * n + 3);          // Gsum
+  ++g.nlaunch, k_sum_points<<<1, 128, 0, g.stream>>>(table + n, (u32)n, table + 2 * n + 4);      // Hsum
   // Repeated generator set: its terms (2n+1 of E4, n+4 of E2, ...: 202 of the 220 terms of a 64-bit proof) are read from
   // the fixed-base table, 32 lookups each with no doublings and no bucket reduction; only the ~21 proof-specific terms
   // (V, A, S, T1, T2, u', P', L_j, R_j) still go through the bucket method.  Each equation is still checked exactly.
@@ -589,7 +593,7 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
     BP_CUDA(cudaMemcpyAsync(table + pt_base, hpt_buf[cur], cn * lay.npt * 64, cudaMemcpyHostToDevice, g.aux_stream));
     BP_CUDA(cudaMemcpyAsync(psc, hsc_buf[cur], cn * lay.nsc * 32, cudaMemcpyHostToDevice, g.aux_stream));
     BP_CUDA(cudaEventRecord(g.stage_ev[cur], g.aux_stream));
-    k_reduce_scalars<<<(unsigned)((cn * lay.nsc + 127) / 128), 128, 0, g.aux_stream>>>(psc, (u32)(cn * lay.nsc));
+    ++g.nlaunch, k_reduce_scalars<<<(unsigned)((cn * lay.nsc + 127) / 128), 128, 0, g.aux_stream>>>(psc, (u32)(cn * lay.nsc));
     if (cn <= 8) {
       // a handful of proofs (RangeVerifier.verify routes single proofs here): the one field inversion per proof is a
       // 0.38 ms latency chain on the device but 35 us on a host core
@@ -605,26 +609,24 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
       BP_CUDA(cudaMemcpyAsync(d_inv, hv.data(), hv.size() * sizeof(Fq), cudaMemcpyHostToDevice, g.aux_stream));
       BP_CUDA(cudaStreamSynchronize(g.aux_stream));        // hv is a stack-scoped pageable buffer
     } else {
-      k_rp_invert<<<(unsigned)((cn + 63) / 64), 64, 0, g.aux_stream>>>(psc, lay, (u32)cn, d_inv);
+      ++g.nlaunch, k_rp_invert<<<(unsigned)((cn + 63) / 64), 64, 0, g.aux_stream>>>(psc, lay, (u32)cn, d_inv);
     }
-    k_rp_expand<<<(unsigned)cn, bd, smem, g.aux_stream>>>(psc, d_inv, lay, (u32)cn, pt_base, tsc, tidx, d_off);
+    ++g.nlaunch, k_rp_expand<<<(unsigned)cn, bd, smem, g.aux_stream>>>(psc, d_inv, lay, (u32)cn, pt_base, tsc, tidx, d_off);
     BP_CUDA(cudaEventRecord(g.aux_ready[cur], g.aux_stream));
     BP_CUDA(cudaStreamWaitEvent(g.stream, g.aux_ready[cur], 0));
     if (fbtab) {
       const u32 nm = (u32)(4 * cn);
-      if (fbtab16) k_rp_lookup16<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
-      else k_rp_lookup<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
-      g.msm_skip_below = lay.fixed;                                        // bucket pass: proof-specific terms only
-      int rc = msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, nm, (lay.npt + 2 + 3) / 4, nullptr, d_var);
-      g.msm_skip_below = 0;
-      if (rc) return 1;
+      if (fbtab16) ++g.nlaunch, k_rp_lookup16<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
+      else ++g.nlaunch, k_rp_lookup<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
+      MsmOpts skip; skip.skip_below = lay.fixed;                           // bucket pass: proof-specific terms only
+      if (msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, nm, (lay.npt + 2 + 3) / 4, nullptr, d_var, skip)) return 1;
       XYZZ* d_grp = d_lanes + (size_t)4 * CH * 128;
-      k_rp_fold8<<<(nm * 16 + 127) / 128, 128, 0, g.stream>>>(d_lanes, nm, (u32)cn, d_grp);
-      k_rp_fold<<<(nm + 3) / 4, 128, 0, g.stream>>>(d_grp, d_var, nm, (u32)cn, d_tot);
-      k_rp_accept_xyzz<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_tot, (u32)cn, d_acc + chunk_lo);
+      ++g.nlaunch, k_rp_fold8<<<(nm * 16 + 127) / 128, 128, 0, g.stream>>>(d_lanes, nm, (u32)cn, d_grp);
+      ++g.nlaunch, k_rp_fold<<<(nm + 3) / 4, 128, 0, g.stream>>>(d_grp, d_var, nm, (u32)cn, d_tot);
+      ++g.nlaunch, k_rp_accept_xyzz<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_tot, (u32)cn, d_acc + chunk_lo);
     } else {
       if (msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, (u32)(4 * cn), lay.tpp / 4, d_res, nullptr)) return 1;
-      k_rp_accept<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)cn, d_acc + chunk_lo);
+      ++g.nlaunch, k_rp_accept<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)cn, d_acc + chunk_lo);
     }
     BP_CUDA(cudaEventRecord(g.aux_free[cur], g.stream));
   }
@@ -664,18 +666,18 @@ int bp_allgather_bytes(const uint8_t* send, size_t nbytes, uint8_t* recv) {
 }
 // slice MSM on this rank -> ncclAllGather of the 128-byte XYZZ partials over NVLink -> every rank adds
 // the R partials and converts to the (identical, canonical) affine result in d_out.  All on g.stream.
-static int msm_sharded_device(const Affine* pts, const Fq* sc, size_t n, Affine* d_out) {
+static int msm_sharded_device(const Affine* pts, const Fq* sc, size_t n, Affine* d_out, MsmOpts opt = MsmOpts()) {
   int R = g_comm ? g_nranks : 1;
   XYZZ* d_part = (XYZZ*)g.ws_lr.ensure((size_t)(R + 1) * sizeof(XYZZ));
   if (!d_part) return fail("device allocation failed");
   if (n == 0) BP_CUDA(cudaMemsetAsync(d_part, 0, sizeof(XYZZ), g.stream));
-  else if (msm_run(pts, nullptr, sc, (u32)n, nullptr, 1, n, nullptr, d_part)) return 1;
+  else if (msm_run(pts, nullptr, sc, (u32)n, nullptr, 1, n, nullptr, d_part, opt)) return 1;
   const XYZZ* all = d_part;
   if (R > 1) {   // the single exchange step of the sharded MSM
     BP_NCCL(ncclAllGather(d_part, d_part + 1, sizeof(XYZZ), ncclUint8, g_comm, g.stream));
     all = d_part + 1;
   }
-  k_xyzz_sum<<<1, 32, 0, g.stream>>>(all, (u32)R, d_out);
+  ++g.nlaunch, k_xyzz_sum<<<1, 32, 0, g.stream>>>(all, (u32)R, d_out);
   BP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -701,8 +703,9 @@ int bp_msm_sharded_host(const uint8_t* pts64, const uint8_t* sc32, size_t n, uin
   Fq* d_sc = (Fq*)g.ws_sc.ensure((n ? n : 1) * sizeof(Fq));
   Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
   if (!d_pts || !d_sc || !d_out) return fail("device allocation failed");
-  if (n && upload_operands(d_pts, pts64, d_sc, sc32, n)) return 1;
-  if (msm_sharded_device(d_pts, d_sc, n, d_out)) return 1;
+  MsmOpts opt;
+  if (n && upload_operands(d_pts, pts64, d_sc, sc32, n, &opt)) return 1;
+  if (msm_sharded_device(d_pts, d_sc, n, d_out, opt)) { cudaStreamSynchronize(g.copy_stream); return 1; }
   BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
@@ -782,7 +785,7 @@ extern "C" int bp_lift_x_batch(const uint8_t* xs32, const uint8_t* want, size_t 
   if (!d_x || !d_out || !d_flags) return fail("device allocation failed");
   BP_CUDA(cudaMemcpyAsync(d_x, xs32, n * 32, cudaMemcpyHostToDevice, g.stream));
   if (want) BP_CUDA(cudaMemcpyAsync(d_flags, want, n, cudaMemcpyHostToDevice, g.stream));
-  k_lift_x<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(d_x, want ? d_flags : nullptr, (u32)n, d_out, d_flags + n);
+  ++g.nlaunch, k_lift_x<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(d_x, want ? d_flags : nullptr, (u32)n, d_out, d_flags + n);
   BP_CUDA(cudaMemcpyAsync(out64, d_out, n * 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaMemcpyAsync(ok, d_flags + n, n, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
@@ -806,7 +809,7 @@ extern "C" int bp_point_add(const uint8_t a64[64], const uint8_t b64[64], uint8_
   if (!d) return fail("device allocation failed");
   BP_CUDA(cudaMemcpyAsync(d, a64, 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(d + 1, b64, 64, cudaMemcpyHostToDevice, g.stream));
-  k_point_add<<<1, 32, 0, g.stream>>>(d, d + 2);
+  ++g.nlaunch, k_point_add<<<1, 32, 0, g.stream>>>(d, d + 2);
   BP_CUDA(cudaMemcpyAsync(out64, d + 2, 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;

@@ -41,16 +41,14 @@ struct Ctx {
   cudaEvent_t ev[8];
   cudaEvent_t ev_a, ev_b, ev_k0, ev_k1;
   cudaStream_t copy_stream = nullptr;           // uploads of points overlap the scalar-only stages
-  cudaEvent_t ev_pts = nullptr, ev_copy_gate = nullptr, pts_ready = nullptr;
+  cudaEvent_t ev_pts = nullptr, ev_copy_gate = nullptr;
   // large host-operand MSMs: the points arrive in two halves (ev_half[0], ev_half[1]); msm_run then runs the MSM as two
   // half-size MSMs over one sort so that the first half is accumulated while the second is still on the wire
   cudaEvent_t ev_half[2] = {nullptr, nullptr}, ev_sc = nullptr;
-  bool halves_pending = false;
-  size_t halves_split = 0;
   DevBuf ws_halfoff;
   bool profiling = false;
   int force_c = 0, last_c = 0;
-  unsigned msm_skip_below = 0;                  // msm_run: terms with point index below this are left to the caller (see k_digits)
+  unsigned long long nlaunch = 0;               // kernels launched by this library so far (bp_launch_count)
   size_t last_nb = 0;
   // MSM workspaces
   DevBuf ws_pts, ws_sc, ws_off, ws_out, ws_digits, ws_entries, ws_count, ws_start, ws_cursor, ws_tiles, ws_buckets, ws_segsum,
@@ -118,19 +116,20 @@ struct Ctx {
   // IPA round graphs: one instantiated graph per vector length, valid while no workspace has been reallocated
   bool use_graphs = true;
   DevBuf ws_ipa_rp;
-  struct GraphRec { cudaGraphExec_t exec; unsigned long long gen; const void* tab; };
+  struct GraphRec { cudaGraphExec_t exec; unsigned long long gen; const void* tab; unsigned nk; };   // nk = kernel nodes
   std::map<size_t, GraphRec> ipa_graphs;
   // `tab` = the fixed-base table the captured round reads (nullptr: bucket-method round); part of the key
+  unsigned ipa_graph_kernels(size_t n, const void* tab) { auto it = ipa_graphs.find(2 * n + (tab ? 1 : 0)); return it == ipa_graphs.end() ? 0u : it->second.nk; }
   cudaGraphExec_t ipa_graph_lookup(size_t n, const void* tab) {
     auto it = ipa_graphs.find(2 * n + (tab ? 1 : 0));
     if (it == ipa_graphs.end()) return nullptr;
     if (it->second.gen != alloc_generation() || it->second.tab != tab) { cudaGraphExecDestroy(it->second.exec); ipa_graphs.erase(it); return nullptr; }
     return it->second.exec;
   }
-  void ipa_graph_store(size_t n, const void* tab, cudaGraphExec_t e) {
+  void ipa_graph_store(size_t n, const void* tab, cudaGraphExec_t e, unsigned nk) {
     auto it = ipa_graphs.find(2 * n + (tab ? 1 : 0));
     if (it != ipa_graphs.end()) cudaGraphExecDestroy(it->second.exec);
-    ipa_graphs[2 * n + (tab ? 1 : 0)] = GraphRec{e, alloc_generation(), tab};
+    ipa_graphs[2 * n + (tab ? 1 : 0)] = GraphRec{e, alloc_generation(), tab, nk};
   }
   unsigned char* pin_bytes_p = nullptr; size_t pin_bytes_cap = 0;
   unsigned char* pinned_bytes(size_t bytes) {

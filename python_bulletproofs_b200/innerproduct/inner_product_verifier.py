@@ -116,7 +116,31 @@ class Verifier2(_Checker):
 
     def _device_ready(self):
         n = len(self.g)
-        return n >= 1 and n & (n - 1) == 0 and len(self.h) == n
+        log_n = n.bit_length() - 1
+        pr = self.proof
+        # the fused device entry points take exactly log2(n) challenges and L/R pairs; any other proof shape goes through
+        # _verify_generic, which evaluates the reference's two multiexps as written (all of Ls/Rs/xs, its exceptions)
+        return n >= 1 and n & (n - 1) == 0 and len(self.h) == n and len(pr.xs) == len(pr.Ls) == len(pr.Rs) == log_n
+
+    def _verify_generic(self):
+        """inner_product_verifier.py:127-147 literally, for proof shapes the fused calls do not take."""
+        q = SUPERCURVE.q
+        proof, n = self.proof, len(self.g)
+        log_n = n.bit_length() - 1
+        _ = [proof.xs[j] for j in range(log_n)]                       # IndexError when challenges are missing, as get_ss would
+        ss = self.get_ss(proof.xs)
+        a, b = int(proof.a % q), int(proof.b % q)
+        hsc = self._h_scale
+        if isinstance(hsc, (bytes, bytearray)):
+            hsc = nat.unpack_scalars(hsc, n)
+        bsc = [b * pow(int(s.x), -1, q) % q * (int(hsc[i]) if hsc is not None else 1) % q for i, s in enumerate(ss)]
+        LHS = PipSECP256k1.multiexp(list(self.g) + list(self.h) + [self.u], [a * int(s.x) % q for s in ss] + bsc + [a * b % q])
+        x2 = [int(x % q) ** 2 % q for x in proof.xs]
+        xi2 = [pow(int(x % q), -2, q) for x in proof.xs]
+        RHS = self.P + PipSECP256k1.multiexp(list(proof.Ls) + list(proof.Rs), x2 + xi2)
+        self.assertThat(LHS == RHS)
+        print("OK")
+        return True
 
     def _call(self, p1):
         proof = self.proof
@@ -155,6 +179,8 @@ class Verifier2(_Checker):
     def verify(self):
         self.verify_transcript()
         self._check_challenges()
+        if not self._device_ready():
+            return self._verify_generic()
         self.assertThat(self._call(None))
         print("OK")
         return True

@@ -18,6 +18,11 @@ class Point:
     __slots__ = ("x", "y", "curve", "_pk")
 
     def __init__(self, x, y, curve=secp256k1):
+        # fastecdsa's Point raises ValueError for coordinates that are not on the curve; so does this one -- every point a
+        # verifier receives (V, A, S, T1, T2, L_j, R_j, u_new, P_new) is thereby on secp256k1 before it reaches the device
+        # formulas (which assume curve points; the C ABI's batch verifier checks its packed inputs itself)
+        if curve is not None and not (0 <= x < curve.p and 0 <= y < curve.p and curve.is_point_on_curve((x, y))):
+            raise ValueError("coordinates are not on curve <%s>\n\tx=%x\n\ty=%x" % (curve, x, y))
         self.x, self.y, self.curve = x, y, curve
         self._pk = None        # (x, y, 64-byte wire form) cached by _native.pack_point; revalidated against x, y on use
 
@@ -27,7 +32,8 @@ class Point:
         xy = nat.unpack_xy(b, off)
         if xy is None:
             return cls.IDENTITY_ELEMENT
-        pt = cls(xy[0], xy[1], secp256k1)
+        pt = cls.__new__(cls)              # device output: canonical curve point, no need to re-check
+        pt.x, pt.y, pt.curve = xy[0], xy[1], secp256k1
         pt._pk = (pt.x, pt.y, bytes(b[off:off + 64]))
         return pt
 
@@ -48,7 +54,9 @@ class Point:
     def __neg__(self):
         if self._is_identity():
             return self
-        return Point(self.x, (-self.y) % self.curve.p, self.curve)
+        pt = Point.__new__(Point)
+        pt.x, pt.y, pt.curve, pt._pk = self.x, (-self.y) % self.curve.p, self.curve, None
+        return pt
 
     def __sub__(self, other):
         return self + (-other)

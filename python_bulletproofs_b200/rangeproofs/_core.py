@@ -80,6 +80,8 @@ def prove(vs, n, g, h, gs, hs, gammas, u, group, transcript: Transcript):
         return _prove_python(vs, n, g, h, gs, hs, gammas, u, group, transcript)
     m = len(vs)
     nm = n * m
+    # shape checks the reference makes in vector_commitment / NIProver (commitments.py:10, inner_product_prover.py:14)
+    assert len(gs) == len(hs) == nm and len(gammas) == m
     bits = bytes((v.x >> i) & 1 for v in vs for i in range(n))              # aL, value-major
     t0 = transcript.digest
     alpha = mod_hash(b"alpha" + t0, q).x
@@ -210,6 +212,7 @@ class VerifierCore:
         q = self.proof.taux.p
         proof, g, h, gs, hs = self.proof, self.g, self.h, self.gs, self.hs
         nm, m = len(gs), len(Vs)
+        assert m >= 1 and nm % m == 0 and len(hs) == nm          # vector_commitment / Verifier2 shapes (commitments.py:10)
         n = nm // m
         xv, yv, zv = self.x.x % q, self.y.x % q, self.z.x % q
         zpows = [pow(zv, j + 2, q) for j in range(m + 1)]

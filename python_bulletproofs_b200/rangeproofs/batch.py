@@ -49,6 +49,11 @@ class PackedBatch:
             if len(pr.innerProof.proof2.xs) != log_n or len(pr.innerProof.proof2.Ls) != log_n or len(pr.innerProof.proof2.Rs) != log_n:
                 raise ValueError("proof shape does not match the generator count")
             r, t, s = pack_proof(V, pr, log_n)
+            # The C transcript check compares the decimal of the REDUCED challenge with the transcript slot; the reference
+            # compares str(xs[i]) of the raw ModP.x (inner_product_verifier.py:121-125).  An unreduced xs[i] (= hash + q)
+            # is therefore sent down the step-by-step path (start index past the end = verdict "defer").
+            if any(not (0 <= int(getattr(x, "x", x)) < nat.Q) for x in pr.innerProof.proof2.xs):
+                s = 0xFFFFFFFF
             recs.append(r)
             trs.append(t)
             sts.append(s)
