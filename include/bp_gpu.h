@@ -189,6 +189,18 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
                        const uint8_t* transcripts, const uint64_t* tr_off, const uint32_t* start_transcript,
                        uint8_t* accept);
 size_t bp_rp_proof_stride(size_t n);
+/* Proof-sharded form: this rank verifies its block of `nproofs` proofs, then every rank's accept
+ * bytes -- padded to `width` >= the largest block -- are all-gathered device to device (one ncclAllGather over NVLink, the
+ * single exchange step) and copied out once: accept_all = nranks x width bytes, rank-major.  Needs bp_nccl_init for more
+ * than one rank.  Every rank must call it (nproofs may be 0). */
+int bp_rp_verify_batch_gather(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g64[64], const uint8_t h64[64],
+                              const uint8_t u64_[64], size_t n, const uint8_t* proofs, size_t proof_stride, size_t nproofs,
+                              const uint8_t* transcripts, const uint64_t* tr_off, const uint32_t* start_transcript,
+                              size_t width, uint8_t* accept_all);
+/* measurements of the last batch call: [0] wall ms, [1] host transcript-check ms (sum over chunks), [2] device span ms
+ * (CUDA events on the library stream: first chunk's first kernel .. last accept kernel), [3] chunks, [4] host threads,
+ * [5] table mode (0 bucket method, 1 byte tables, 2 16-bit tables), [6] proofs */
+int bp_rp_verify_stats(double out7[7]);
 
 /* ---- host-side Fiat-Shamir helpers (exported for tests; src/utils/utils.py:84-111) -------------- */
 int bp_mod_hash(const uint8_t* msg, size_t len, uint8_t out32[32]);            /* mod_hash(msg, q) */

@@ -16,6 +16,7 @@
 #include "ipa.cuh"
 #include "transcript.h"
 #include "verify.cuh"
+#include "svar.cuh"
 #include "fixedbase.cuh"
 #include "rp_algebra.h"
 #include <nccl.h>

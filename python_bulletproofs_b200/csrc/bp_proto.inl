@@ -414,23 +414,43 @@ size_t bp_rp_proof_stride(size_t n) {
   return 5 * 64 + 3 * 32 + 2 * 64 + 2 * 32 + L * 32 + 2 * L * 64;
 }
 
-// split `s` at '&' like bytes.split(b"&")
-static void split_amp(const uint8_t* s, size_t n, std::vector<std::pair<size_t, size_t>>& out) {
-  out.clear();
-  size_t st = 0;
-  for (size_t i = 0; i <= n; i++) if (i == n || s[i] == '&') { out.push_back({st, i - st}); st = i + 1; }
+}  // extern "C"
+namespace bp {
+struct RpStats { double wall_ms = 0, host_ms = 0, gpu_ms = 0; unsigned chunks = 0, threads = 0, table_mode = 0; size_t nproofs = 0; };
+static RpStats g_rp_stats;
+// chunk lengths of a batch: the host checks of the FIRST chunk are the only ones the GPU cannot hide, and every chunk pays
+// fixed latency chains (inversions, the 96-doubling tails), so: a short first chunk, then growing ones, at most 4096 proofs
+static void rp_chunk_plan(size_t nproofs, bool tables, std::vector<size_t>& lens) {
+  lens.clear();
+  if (const char* e = getenv("BP_VERIFY_CHUNK")) {
+    size_t ch = (size_t)atol(e); if (ch == 0) ch = 1;
+    for (size_t lo = 0; lo < nproofs; lo += ch) lens.push_back(nproofs - lo < ch ? nproofs - lo : ch);
+    return;
+  }
+  if (!tables) { const size_t ch = nproofs < 4096 ? nproofs : 2048; for (size_t lo = 0; lo < nproofs; lo += ch) lens.push_back(nproofs - lo < ch ? nproofs - lo : ch); return; }
+  if (nproofs < 512) { lens.push_back(nproofs); return; }
+  size_t left = nproofs, next = nproofs / 8 < 256 ? 256 : (nproofs / 8 > 1024 ? 1024 : nproofs / 8);
+  while (left) {
+    size_t len = next < left ? next : left;
+    if (left - len < 128) len = left;                 // no tiny last chunk
+    lens.push_back(len); left -= len;
+    next = next * 2 > 4096 ? 4096 : next * 2;
+  }
 }
-static bool slot_eq(const uint8_t* base, const std::pair<size_t, size_t>& sl, const std::string& v) {
-  return sl.second == v.size() && memcmp(base + sl.first, v.data(), v.size()) == 0;
-}
+}  // namespace bp
+extern "C" {
 
-int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g64[64], const uint8_t h64[64],
+// gather_out != nullptr: after the batch every rank's accept bytes (padded to gather_width) are all-gathered on the device
+// through NCCL and copied out once (rank-major) -- no host round trip between the verification and the exchange
+static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g64[64], const uint8_t h64[64],
                        const uint8_t u64_[64], size_t n, const uint8_t* proofs, size_t proof_stride, size_t nproofs,
                        const uint8_t* transcripts, const uint64_t* tr_off, const uint32_t* start_transcript,
-                       uint8_t* accept) {
+                       uint8_t* accept, uint8_t* gather_out, size_t gather_width) {
   BP_NEED_INIT();
   if (n == 0 || (n & (n - 1)) || n > 128) return fail("bp_rp_verify_batch: n must be a power of two <= 128");
-  if (nproofs == 0) return 0;
+  if (gather_out && gather_width < nproofs) return fail("bp_rp_verify_batch_gather: width smaller than this rank's block");
+  if (nproofs == 0 && !gather_out) return 0;
+  const auto t_call0 = std::chrono::steady_clock::now();
   RpLayout lay = rp_layout((u32)n);
   const u32 L = lay.L;
   if (proof_stride < bp_rp_proof_stride(n)) return fail("bp_rp_verify_batch: proof_stride too small");
@@ -440,16 +460,17 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
                oa = 544, ob = 576, oXs = 608, oLs = oXs + 32 * L, oRs = oLs + 64 * L;
   // The batch is cut into chunks: while the GPU evaluates the equations of chunk i, the host threads run the
   // transcript checks of chunk i+1 (pinned, double-buffered staging so the uploads are truly asynchronous).
-  // chunk length: measured on B200 at 8192 proofs -- table path 1024/2048/4096/8192 -> 26.5/22.3/19.8/24.4 ms (the
-  // latency-bound kernels are paid per chunk, the host checks of the first chunk are exposed); bucket path: 2048 best
-  size_t CH = fb_enabled() ? (nproofs <= 4096 ? nproofs : 4096) : (nproofs < 4096 ? nproofs : 2048);
-  if (getenv("BP_VERIFY_CHUNK")) { CH = (size_t)atol(getenv("BP_VERIFY_CHUNK")); if (CH > nproofs) CH = nproofs; if (CH == 0) CH = 1; }
-  const size_t sc_bytes = CH * lay.nsc * 32, pt_bytes = CH * lay.npt * 64;
-  uint8_t* stage = g.pinned_stage(2 * (sc_bytes + pt_bytes));
+  std::vector<size_t> chunk_len;
+  rp_chunk_plan(nproofs, fb_enabled(), chunk_len);
+  size_t CH = 1;
+  for (size_t l : chunk_len) if (l > CH) CH = l;
+  const size_t sc_bytes = CH * lay.nsc * 32, pt_bytes = CH * lay.npt * 64, ok_bytes = (CH + 63) & ~(size_t)63;
+  const size_t stage_each = sc_bytes + pt_bytes + ok_bytes;
+  uint8_t* stage = g.pinned_stage(2 * stage_each + (gather_out ? (size_t)g_nranks * gather_width + 64 : 0));
   if (!stage) return fail("pinned staging allocation failed");
-  uint8_t* hsc_buf[2] = {stage, stage + sc_bytes + pt_bytes};
-  uint8_t* hpt_buf[2] = {stage + sc_bytes, stage + 2 * sc_bytes + pt_bytes};
-  std::vector<uint8_t> host_ok(nproofs, 1);
+  uint8_t* hsc_buf[2] = {stage, stage + stage_each};
+  uint8_t* hpt_buf[2] = {stage + sc_bytes, stage + stage_each + sc_bytes};
+  uint8_t* hok_buf[2] = {stage + sc_bytes + pt_bytes, stage + stage_each + sc_bytes + pt_bytes};   // host verdicts of the chunk
   size_t chunk_lo = 0;
   int cur = 0;
   // ---- host: transcript checks + challenge extraction, threaded over proofs --------------------
@@ -461,7 +482,25 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
   }
   if (nthreads > 64) nthreads = 64;
   auto work = [&](size_t lo, size_t hi) {
-    std::vector<std::pair<size_t, size_t>> sl;
+    // no heap traffic per proof: slots are (offset, length) pairs in a small stack array, points and scalars are compared in
+    // place (b64_point_eq / decimal_slot_eq) instead of through std::string round trips
+    struct Slot { size_t first, second; };
+    Slot sl_stack[64];
+    std::vector<Slot> sl_heap;
+    // the first `need` slots of s.split(b"&"); returns how many exist (<= need)
+    auto split_first = [&](const uint8_t* s, size_t n, size_t need, Slot*& sl) -> size_t {
+      sl = sl_stack;
+      if (need > 64) { if (need > n + 1) need = n + 1; sl_heap.resize(need); sl = sl_heap.data(); }
+      size_t cnt = 0, st = 0;
+      while (cnt < need) {
+        const uint8_t* amp = st <= n ? (const uint8_t*)memchr(s + st, '&', n - st) : nullptr;
+        const size_t end = amp ? (size_t)(amp - s) : n;
+        sl[cnt].first = st; sl[cnt].second = end - st; cnt++;
+        if (!amp) break;
+        st = end + 1;
+      }
+      return cnt;
+    };
     for (size_t p = lo; p < hi; p++) {
       const uint8_t* pr = proofs + p * proof_stride;
       uint8_t* sc = hsc_buf[cur] + (p - chunk_lo) * lay.nsc * 32;
@@ -470,104 +509,127 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
       memcpy(pt + 64 * RP_T1, pr + oT1, 64); memcpy(pt + 64 * RP_T2, pr + oT2, 64);
       memcpy(pt + 64 * RP_UNEW, pr + oUnew, 64); memcpy(pt + 64 * RP_PNEW, pr + oPnew, 64);
       memcpy(pt + 64 * RP_LS, pr + oLs, 64 * L); memcpy(pt + 64 * (RP_LS + L), pr + oRs, 64 * L);
-      memset(sc, 0, lay.nsc * 32);
       memcpy(sc + 32 * RS_THAT, pr + oThat, 32); memcpy(sc + 32 * RS_TAUX, pr + oTaux, 32); memcpy(sc + 32 * RS_MU, pr + oMu, 32);
       memcpy(sc + 32 * RS_A, pr + oa, 32); memcpy(sc + 32 * RS_B, pr + ob, 32);
       memcpy(sc + 32 * RS_XS, pr + oXs, 32 * L);
       uint8_t verdict = 1;
+      Slot* sl = nullptr;
       // --- RangeVerifier.verify_transcript                         rangeproof_verifier.py:42-53
       const uint8_t* t0 = transcripts + tr_off[3 * p];
       size_t t0n = tr_off[3 * p + 1] - tr_off[3 * p];
-      split_amp(t0, t0n, sl);
       Fq y = fq_one(), z = fq_one(), x = fq_one(), x1 = fq_one();
-      if (sl.size() < 8) verdict = 2;                                 // reference would raise IndexError
-      else if (!slot_eq(t0, sl[1], point_to_b64(pr + oA)) || !slot_eq(t0, sl[2], point_to_b64(pr + oS))) verdict = 0;
-      else if (!decimal_to_fq(t0 + sl[3].first, sl[3].second, &y) || !decimal_to_fq(t0 + sl[4].first, sl[4].second, &z)) verdict = 2;
-      else if (!slot_eq(t0, sl[5], point_to_b64(pr + oT1)) || !slot_eq(t0, sl[6], point_to_b64(pr + oT2))) verdict = 0;
-      else if (!decimal_to_fq(t0 + sl[7].first, sl[7].second, &x)) verdict = 2;
+      if (split_first(t0, t0n, 8, sl) < 8) verdict = 2;               // reference would raise IndexError
+      else if (!b64_point_eq(t0 + sl[1].first, sl[1].second, pr + oA) || !b64_point_eq(t0 + sl[2].first, sl[2].second, pr + oS)) verdict = 0;
+      else if (!decimal_to_fq_fast(t0 + sl[3].first, sl[3].second, &y) || !decimal_to_fq_fast(t0 + sl[4].first, sl[4].second, &z)) verdict = 2;
+      else if (!b64_point_eq(t0 + sl[5].first, sl[5].second, pr + oT1) || !b64_point_eq(t0 + sl[6].first, sl[6].second, pr + oT2)) verdict = 0;
+      else if (!decimal_to_fq_fast(t0 + sl[7].first, sl[7].second, &x)) verdict = 2;
       if (verdict == 1 && fq_is_zero(y)) verdict = 2;                 // y.inv() raises in the reference
       // --- Verifier1.verify_transcript                             inner_product_verifier.py:36-42
       if (verdict == 1) {
         const uint8_t* t1 = transcripts + tr_off[3 * p + 1];
         size_t t1n = tr_off[3 * p + 2] - tr_off[3 * p + 1];
-        split_amp(t1, t1n, sl);
-        if (sl.size() < 2) verdict = 2;
+        if (split_first(t1, t1n, 2, sl) < 2) verdict = 2;
         else {
-          std::string pre((const char*)t1 + sl[0].first, sl[0].second); pre += '&';
-          x1 = mod_hash_q((const uint8_t*)pre.data(), pre.size());
-          if (!slot_eq(t1, sl[1], fq_to_decimal(x1))) verdict = 0;
+          // parts[0] + b"&" is the transcript up to and including its first '&'
+          x1 = mod_hash_q(t1, sl[0].second + 1);
+          if (!decimal_slot_eq(t1 + sl[1].first, sl[1].second, x1)) verdict = 0;
         }
       }
       // --- Verifier2.verify_transcript                             inner_product_verifier.py:104-125
       if (verdict == 1) {
         const uint8_t* t2 = transcripts + tr_off[3 * p + 2];
         size_t t2n = tr_off[3 * p + 3] - tr_off[3 * p + 2];
-        split_amp(t2, t2n, sl);
-        size_t st = start_transcript[p];
-        if (sl.size() < st + 3 * (size_t)L) verdict = L ? 2 : 1;
+        const size_t st = start_transcript[p], need = st + 3 * (size_t)L;
+        if (L && split_first(t2, t2n, need, sl) < need) verdict = 2;
         RunningModHash rh;
         for (u32 j = 0; j < L && verdict == 1; j++) {
-          const auto& sL = sl[st + 3 * j]; const auto& sR = sl[st + 3 * j + 1]; const auto& sX = sl[st + 3 * j + 2];
-          if (!slot_eq(t2, sL, point_to_b64(pr + oLs + 64 * j)) || !slot_eq(t2, sR, point_to_b64(pr + oRs + 64 * j))) { verdict = 0; break; }
+          const Slot& sL = sl[st + 3 * j]; const Slot& sR = sl[st + 3 * j + 1]; const Slot& sX = sl[st + 3 * j + 2];
+          if (!b64_point_eq(t2 + sL.first, sL.second, pr + oLs + 64 * j) || !b64_point_eq(t2 + sR.first, sR.second, pr + oRs + 64 * j)) { verdict = 0; break; }
           Fq xj; fq_from_le(&xj, pr + oXs + 32 * j);
-          std::string xs_dec = fq_to_decimal(xj);
-          // b"&".join(parts[:idx]) + b"&" is the transcript prefix up to and including the '&' before slot idx
+          // b"&".join(parts[:idx]) + b"&" is the transcript prefix up to and including the '&' before slot idx;
+          // str(xs[j]) == slot == str(expected)  <=>  the slot is the canonical decimal of both
           Fq want = rh.challenge(t2, sX.first);
-          if (!slot_eq(t2, sX, xs_dec) || !slot_eq(t2, sX, fq_to_decimal(want))) { verdict = 0; break; }
+          if (!fq_eq(xj, want) || !decimal_slot_eq(t2 + sX.first, sX.second, want)) { verdict = 0; break; }
         }
       }
       fq_to_le(sc + 32 * RS_Y, y); fq_to_le(sc + 32 * RS_Z, z); fq_to_le(sc + 32 * RS_X, x); fq_to_le(sc + 32 * RS_X1, x1);
-      host_ok[p] = verdict;
+      hok_buf[cur][p - chunk_lo] = verdict;
     }
   };
   // ---- device buffers and the shared generator table -----------------------------------------------
   // The per-chunk inputs (scalar records, proof points, inverses, expanded terms) are double-buffered: chunk i+1 is
   // uploaded, inverted and expanded on a side stream while chunk i is still in its lookups / bucket pass on the main one.
+  const u32 nv = 5 + 2 * L;
   size_t Tc = CH * lay.tpp, npts = lay.fixed + 2 * CH * lay.npt;
+  const size_t gwidth = gather_out ? gather_width : nproofs;
   Affine* table = (Affine*)g.ws_pts.ensure(npts * sizeof(Affine));
   Fq* psc2 = (Fq*)g.ws_small.ensure(2 * CH * lay.nsc * sizeof(Fq));
   Fq* tsc2 = (Fq*)g.ws_terms_sc.ensure(2 * Tc * sizeof(Fq));
   u32* tidx2 = (u32*)g.ws_idx.ensure(2 * Tc * sizeof(u32));
   u32* d_off2 = (u32*)g.ws_off.ensure(2 * (4 * CH + 1) * sizeof(u32));
   Affine* d_res = (Affine*)g.ws_out.ensure(4 * CH * sizeof(Affine));
-  uint8_t* d_acc = (uint8_t*)g.ws_misc.ensure(nproofs);
+  // accept bytes of this rank [gwidth] | all ranks [R * gwidth] | host verdicts [gwidth] | off-curve flags [2 * CH]
+  uint8_t* d_acc = (uint8_t*)g.ws_misc.ensure((size_t)(g_nranks + 2) * gwidth + 2 * CH + 256);
   Fq* d_inv2 = (Fq*)g.ws_a.ensure(2 * CH * (lay.L + 1) * sizeof(Fq));
   if (!table || !psc2 || !tsc2 || !tidx2 || !d_off2 || !d_res || !d_acc || !d_inv2) return fail("device allocation failed");
+  uint8_t* d_all = d_acc + gwidth; uint8_t* d_hok = d_all + (size_t)g_nranks * gwidth; uint8_t* d_bad2 = d_hok + gwidth;
   if (g.ensure_aux()) return 1;
   if (g.ensure_stage_events()) return 1;
+  if (gather_out) BP_CUDA(cudaMemsetAsync(d_acc, 0, gwidth, g.stream));      // padding bytes of the gathered block
   BP_CUDA(cudaMemcpyAsync(table, gs64, n * 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + n, hs64, n * 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n, g64, 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n + 1, h64, 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n + 2, u64_, 64, cudaMemcpyHostToDevice, g.stream));
-  ++g.nlaunch, k_sum_points<<<1, 128, 0, g.stream>>>(table, (u32)n, table + 2 * n + 3);          // Gsum
-  ++g.nlaunch, k_sum_points<<<1, 128, 0, g.stream>>>(table + n, (u32)n, table + 2 * n + 4);      // Hsum
+  // Gsum = sum gs_i, Hsum = sum hs_i: per-generator-set constants (they are rows of the fixed-base table, so they must be in
+  // place before fb_get builds it); kept across calls and confirmed against the generator bytes
+  {
+    const FbSrc src = {{gs64, hs64, g64, h64, u64_}, {n * 64, n * 64, 64, 64, 64}, 5};
+    Affine* sums = (Affine*)g.ws_rp_sums.ensure(2 * sizeof(Affine));
+    if (!sums) return fail("device allocation failed");
+    if (g.rp_sums_gen == alloc_generation() && !g.rp_sums_src.empty() && src.equals(g.rp_sums_src)) {
+      BP_CUDA(cudaMemcpyAsync(table + 2 * n + 3, sums, 2 * sizeof(Affine), cudaMemcpyDeviceToDevice, g.stream));
+    } else {
+      ++g.nlaunch, k_sum_points<<<1, 128, 0, g.stream>>>(table, (u32)n, table + 2 * n + 3);          // Gsum
+      ++g.nlaunch, k_sum_points<<<1, 128, 0, g.stream>>>(table + n, (u32)n, table + 2 * n + 4);      // Hsum
+      BP_CUDA(cudaMemcpyAsync(sums, table + 2 * n + 3, 2 * sizeof(Affine), cudaMemcpyDeviceToDevice, g.stream));
+      g.rp_sums_src = src.copy(); g.rp_sums_gen = alloc_generation();
+    }
+  }
   // Repeated generator set: its terms (2n+1 of E4, n+4 of E2, ...: 202 of the 220 terms of a 64-bit proof) are read from
-  // the fixed-base table, 32 lookups each with no doublings and no bucket reduction; only the ~21 proof-specific terms
-  // (V, A, S, T1, T2, u', P', L_j, R_j) still go through the bucket method.  Each equation is still checked exactly.
+  // the fixed-base table with no doublings and no bucket reduction; the ~21 proof-specific terms (V, A, S, T1, T2, u', P',
+  // L_j, R_j) take the window-parallel path of svar.cuh.  Each equation is still checked exactly.
   const Affine *fbtab = nullptr, *fbtab16 = nullptr;
-  XYZZ *d_lanes = nullptr, *d_var = nullptr, *d_tot = nullptr;
+  XYZZ *d_lanes = nullptr, *d_var2 = nullptr, *d_tot = nullptr, *sv_T2 = nullptr, *sv_A2 = nullptr, *sv_G2 = nullptr;
+  Fq* vsc2 = nullptr; uint4* kd2 = nullptr; u32* kfl2 = nullptr;
+  uint64_t fbkey = 0;
   if (fb_enabled()) {
     const FbSrc src = {{gs64, hs64, g64, h64, u64_}, {n * 64, n * 64, 64, 64, 64}, 5};
-    const uint64_t key = src.hash(0x72707631ull);
-    fbtab = fb_get(key, src, table, lay.fixed);
-    fbtab16 = fb_get16(key, fbtab, lay.fixed);
+    fbkey = src.hash(0x72707631ull);
+    fbtab = fb_get(fbkey, src, table, lay.fixed);
+    fbtab16 = fb_get16(fbkey, fbtab, lay.fixed);
     if (fbtab) {
       d_lanes = (XYZZ*)g.ws_fb_lanes.ensure(4 * CH * (128 + 16) * sizeof(XYZZ));
-      d_var = (XYZZ*)g.ws_fb_var.ensure(2 * 4 * CH * sizeof(XYZZ));
-      if (!d_lanes || !d_var) return fail("device allocation failed");
-      d_tot = d_var + 4 * CH;
+      d_var2 = (XYZZ*)g.ws_fb_var.ensure(3 * 4 * CH * sizeof(XYZZ));
+      sv_T2 = (XYZZ*)g.ws_sv_tab.ensure(2 * CH * (size_t)nv * BP_SV_ENT * sizeof(XYZZ));
+      sv_A2 = (XYZZ*)g.ws_sv_acc.ensure(2 * CH * (size_t)(96 + 12) * sizeof(XYZZ));
+      vsc2 = (Fq*)g.ws_sv_sc.ensure(2 * CH * (size_t)nv * (sizeof(Fq) + 2 * sizeof(uint4) + sizeof(u32)));
+      if (!d_lanes || !d_var2 || !sv_T2 || !sv_A2 || !vsc2) return fail("device allocation failed");
+      d_tot = d_var2 + 8 * CH;
+      sv_G2 = sv_A2 + 2 * CH * (size_t)96;
+      kd2 = (uint4*)(vsc2 + 2 * CH * (size_t)nv);
+      kfl2 = (u32*)(kd2 + 2 * CH * (size_t)nv * 2);
+      if (g.ensure_var_stream()) return 1;
     }
   }
   const u32 bd = n < 32 ? 32 : (u32)n;
   const size_t smem = (2 * L + 1 + bd) * sizeof(Fq);
+  const bool timing = getenv("BP_VERIFY_TIMING") != nullptr;
+  double host_ms = 0;
   int chunk_no = 0;
-  // chunk lengths: CH, except that a large batch on the table path starts with two short chunks (1/4 and 3/4 of CH) -- the
-  // host checks of the first chunk are the only ones not hidden behind GPU work, so the GPU should start early
-  const bool ramp = fb_enabled() && nproofs >= 2 * CH && CH >= 1024 && !getenv("BP_VERIFY_CHUNK");
-  size_t this_len = ramp ? CH / 4 : CH;
-  for (chunk_lo = 0; chunk_lo < nproofs; chunk_lo += this_len, this_len = (ramp && chunk_no == 0) ? CH - CH / 4 : CH, chunk_no++) {
-    const size_t chunk_hi = chunk_lo + this_len < nproofs ? chunk_lo + this_len : nproofs, cn = chunk_hi - chunk_lo;
+  chunk_lo = 0;
+  for (size_t ci = 0; ci < chunk_len.size(); chunk_lo += chunk_len[ci], ci++, chunk_no++) {
+    const size_t cn = chunk_len[ci], chunk_hi = chunk_lo + cn;
     cur = chunk_no & 1;
     if (chunk_no >= 2) BP_CUDA(cudaEventSynchronize(g.stage_ev[cur]));       // staging buffer free again?
     auto t_h0 = std::chrono::steady_clock::now();
@@ -581,18 +643,26 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
         if (lo < hi) work(lo, hi);
       }
     }
-    if (getenv("BP_VERIFY_TIMING")) fprintf(stderr, "chunk %d: host %.3f ms (%u threads)\n", chunk_no,
-        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h0).count(), nthreads);
-    // side stream: upload, invert, expand into the buffers of parity `cur` (free once the main stream is done with
-    // chunk i-2); main stream: lookups / bucket pass / accept bits
+    const double h_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h0).count();
+    host_ms += h_ms;
+    if (timing) fprintf(stderr, "chunk %d (%zu proofs): host %.3f ms (%u threads)\n", chunk_no, cn, h_ms, nthreads);
+    // side stream: upload, invert, expand (and the variable points' small tables) into the buffers of parity `cur` (free once
+    // the main stream is done with chunk i-2); main stream: table lookups, fold, accept; var stream: the window-parallel
+    // pass over the proof-specific terms, concurrent with the lookups of the same chunk
     Fq* psc = psc2 + (size_t)cur * CH * lay.nsc; Fq* d_inv = d_inv2 + (size_t)cur * CH * (lay.L + 1);
     Fq* tsc = tsc2 + (size_t)cur * Tc; u32* tidx = tidx2 + (size_t)cur * Tc; u32* d_off = d_off2 + (size_t)cur * (4 * CH + 1);
+    uint8_t* d_bad = d_bad2 + (size_t)cur * CH;
     const u32 pt_base = lay.fixed + (u32)(cur * CH * lay.npt);
-    if (chunk_no == 0) { BP_CUDA(cudaEventRecord(g.aux_free[0], g.stream)); BP_CUDA(cudaEventRecord(g.aux_free[1], g.stream)); }   // generator table ready
+    if (chunk_no == 0) {   // generator table ready
+      BP_CUDA(cudaEventRecord(g.aux_free[0], g.stream)); BP_CUDA(cudaEventRecord(g.aux_free[1], g.stream));
+      BP_CUDA(cudaEventRecord(g.ev_rp0, g.stream));
+    }
     BP_CUDA(cudaStreamWaitEvent(g.aux_stream, g.aux_free[cur], 0));
     BP_CUDA(cudaMemcpyAsync(table + pt_base, hpt_buf[cur], cn * lay.npt * 64, cudaMemcpyHostToDevice, g.aux_stream));
     BP_CUDA(cudaMemcpyAsync(psc, hsc_buf[cur], cn * lay.nsc * 32, cudaMemcpyHostToDevice, g.aux_stream));
+    BP_CUDA(cudaMemcpyAsync(d_hok + chunk_lo, hok_buf[cur], cn, cudaMemcpyHostToDevice, g.aux_stream));
     BP_CUDA(cudaEventRecord(g.stage_ev[cur], g.aux_stream));
+    BP_CUDA(cudaMemsetAsync(d_bad, 0, cn, g.aux_stream));
     ++g.nlaunch, k_reduce_scalars<<<(unsigned)((cn * lay.nsc + 127) / 128), 128, 0, g.aux_stream>>>(psc, (u32)(cn * lay.nsc));
     if (cn <= 8) {
       // a handful of proofs (RangeVerifier.verify routes single proofs here): the one field inversion per proof is a
@@ -611,28 +681,83 @@ int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g
     } else {
       ++g.nlaunch, k_rp_invert<<<(unsigned)((cn + 63) / 64), 64, 0, g.aux_stream>>>(psc, lay, (u32)cn, d_inv);
     }
-    ++g.nlaunch, k_rp_expand<<<(unsigned)cn, bd, smem, g.aux_stream>>>(psc, d_inv, lay, (u32)cn, pt_base, tsc, tidx, d_off);
-    BP_CUDA(cudaEventRecord(g.aux_ready[cur], g.aux_stream));
-    BP_CUDA(cudaStreamWaitEvent(g.stream, g.aux_ready[cur], 0));
+    Fq* vsc = fbtab ? vsc2 + (size_t)cur * CH * nv : nullptr;
+    ++g.nlaunch, k_rp_expand<<<(unsigned)cn, bd, smem, g.aux_stream>>>(psc, d_inv, lay, (u32)cn, pt_base, tsc, tidx, d_off, vsc);
     if (fbtab) {
       const u32 nm = (u32)(4 * cn);
+      XYZZ* sv_T = sv_T2 + (size_t)cur * CH * nv * BP_SV_ENT; XYZZ* sv_A = sv_A2 + (size_t)cur * CH * 96; XYZZ* sv_G = sv_G2 + (size_t)cur * CH * 12;
+      uint4* kd = kd2 + (size_t)cur * CH * nv * 2; u32* kfl = kfl2 + (size_t)cur * CH * nv;
+      XYZZ* d_var = d_var2 + (size_t)cur * 4 * CH;
+      const Affine* cpts = table + pt_base;
+      ++g.nlaunch, k_sv_table<<<(unsigned)((cn * lay.npt + 127) / 128), 128, 0, g.aux_stream>>>(cpts, lay, (u32)cn, vsc, sv_T, kd, kfl, d_bad, d_var + 2 * cn);
+      BP_CUDA(cudaEventRecord(g.aux_ready[cur], g.aux_stream));
+      BP_CUDA(cudaStreamWaitEvent(g.stream, g.aux_ready[cur], 0));
+      BP_CUDA(cudaStreamWaitEvent(g.var_stream, g.aux_ready[cur], 0));
+      ++g.nlaunch, k_sv_main<<<(unsigned)((cn * 32 + 127) / 128), 128, 0, g.var_stream>>>(cpts, lay, (u32)cn, sv_T, kd, kfl, sv_A);
+      ++g.nlaunch, k_sv_comb1<<<(unsigned)((cn * 12 + 127) / 128), 128, 0, g.var_stream>>>(sv_A, (u32)(cn * 12), sv_G);
+      ++g.nlaunch, k_sv_comb2<<<(unsigned)((cn * 12 + 127) / 128), 128, 0, g.var_stream>>>(sv_G, cpts, lay, (u32)cn, d_var);
+      BP_CUDA(cudaEventRecord(g.var_done[cur], g.var_stream));
       if (fbtab16) ++g.nlaunch, k_rp_lookup16<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
       else ++g.nlaunch, k_rp_lookup<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
-      MsmOpts skip; skip.skip_below = lay.fixed;                           // bucket pass: proof-specific terms only
-      if (msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, nm, (lay.npt + 2 + 3) / 4, nullptr, d_var, skip)) return 1;
       XYZZ* d_grp = d_lanes + (size_t)4 * CH * 128;
       ++g.nlaunch, k_rp_fold8<<<(nm * 16 + 127) / 128, 128, 0, g.stream>>>(d_lanes, nm, (u32)cn, d_grp);
+      BP_CUDA(cudaStreamWaitEvent(g.stream, g.var_done[cur], 0));
       ++g.nlaunch, k_rp_fold<<<(nm + 3) / 4, 128, 0, g.stream>>>(d_grp, d_var, nm, (u32)cn, d_tot);
-      ++g.nlaunch, k_rp_accept_xyzz<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_tot, (u32)cn, d_acc + chunk_lo);
+      ++g.nlaunch, k_rp_accept_xyzz<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_tot, (u32)cn, d_bad, d_hok + chunk_lo, d_acc + chunk_lo);
     } else {
+      ++g.nlaunch, k_rp_check_points<<<(unsigned)((cn * lay.npt + 127) / 128), 128, 0, g.aux_stream>>>(table + pt_base, lay.npt, (u32)cn, d_bad);
+      BP_CUDA(cudaEventRecord(g.aux_ready[cur], g.aux_stream));
+      BP_CUDA(cudaStreamWaitEvent(g.stream, g.aux_ready[cur], 0));
       if (msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, (u32)(4 * cn), lay.tpp / 4, d_res, nullptr)) return 1;
-      ++g.nlaunch, k_rp_accept<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)cn, d_acc + chunk_lo);
+      ++g.nlaunch, k_rp_accept<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)cn, d_bad, d_hok + chunk_lo, d_acc + chunk_lo);
     }
     BP_CUDA(cudaEventRecord(g.aux_free[cur], g.stream));
   }
-  BP_CUDA(cudaMemcpyAsync(accept, d_acc, nproofs, cudaMemcpyDeviceToHost, g.stream));
-  BP_CUDA(cudaStreamSynchronize(g.stream));
-  for (size_t p = 0; p < nproofs; p++) if (host_ok[p] != 1) accept[p] = host_ok[p];
+  if (nproofs) BP_CUDA(cudaEventRecord(g.ev_rp1, g.stream));
+  if (gather_out) {
+    // the single exchange step of the sharded batch: accept bytes all-gathered device to device over NVLink
+    const uint8_t* all = d_acc;
+    if (g_comm && g_nranks > 1) { BP_NCCL(ncclAllGather(d_acc, d_all, gwidth, ncclUint8, g_comm, g.stream)); all = d_all; }
+    uint8_t* pin = stage + 2 * stage_each;
+    BP_CUDA(cudaMemcpyAsync(pin, all, (size_t)g_nranks * gwidth, cudaMemcpyDeviceToHost, g.stream));
+    BP_CUDA(cudaStreamSynchronize(g.stream));
+    memcpy(gather_out, pin, (size_t)g_nranks * gwidth);
+    if (accept) memcpy(accept, pin + (size_t)g_rank * gwidth, nproofs);
+  } else {
+    BP_CUDA(cudaMemcpyAsync(accept, d_acc, nproofs, cudaMemcpyDeviceToHost, g.stream));
+    BP_CUDA(cudaStreamSynchronize(g.stream));
+  }
+  RpStats& st = g_rp_stats;
+  st.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
+  st.host_ms = host_ms; st.chunks = (unsigned)chunk_len.size(); st.threads = nthreads; st.nproofs = nproofs;
+  st.table_mode = fbtab16 ? 2u : (fbtab ? 1u : 0u);
+  float gms = 0;
+  if (nproofs && cudaEventElapsedTime(&gms, g.ev_rp0, g.ev_rp1) != cudaSuccess) { cudaGetLastError(); gms = -1.f; }
+  st.gpu_ms = gms;
+  if (timing) fprintf(stderr, "batch of %zu: wall %.3f ms, host checks %.3f ms, device span %.3f ms, %u chunks\n", nproofs, st.wall_ms, host_ms, gms, st.chunks);
+  return 0;
+}
+
+int bp_rp_verify_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g64[64], const uint8_t h64[64],
+                       const uint8_t u64_[64], size_t n, const uint8_t* proofs, size_t proof_stride, size_t nproofs,
+                       const uint8_t* transcripts, const uint64_t* tr_off, const uint32_t* start_transcript,
+                       uint8_t* accept) {
+  return rp_verify_batch_impl(gs64, hs64, g64, h64, u64_, n, proofs, proof_stride, nproofs, transcripts, tr_off, start_transcript,
+                              accept, nullptr, 0);
+}
+int bp_rp_verify_batch_gather(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g64[64], const uint8_t h64[64],
+                              const uint8_t u64_[64], size_t n, const uint8_t* proofs, size_t proof_stride, size_t nproofs,
+                              const uint8_t* transcripts, const uint64_t* tr_off, const uint32_t* start_transcript,
+                              size_t width, uint8_t* accept_all) {
+  return rp_verify_batch_impl(gs64, hs64, g64, h64, u64_, n, proofs, proof_stride, nproofs, transcripts, tr_off, start_transcript,
+                              nullptr, accept_all, width);
+}
+// [0] wall ms of the last batch call, [1] host transcript-check ms (sum over chunks), [2] device span ms (first chunk's
+// first kernel .. last accept kernel, CUDA events on the library stream), [3] chunks, [4] host threads, [5] table mode
+// (0 bucket method, 1 byte tables, 2 16-bit tables), [6] proofs
+int bp_rp_verify_stats(double out7[7]) {
+  const RpStats& st = g_rp_stats;
+  out7[0] = st.wall_ms; out7[1] = st.host_ms; out7[2] = st.gpu_ms; out7[3] = st.chunks; out7[4] = st.threads; out7[5] = st.table_mode; out7[6] = (double)st.nproofs;
   return 0;
 }
 

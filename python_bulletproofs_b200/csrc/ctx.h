@@ -4,6 +4,7 @@
 #include <cstddef>
 #include <map>
 #include <string>
+#include <vector>
 
 namespace bp {
 
@@ -55,6 +56,20 @@ struct Ctx {
       ws_winsum, ws_misc, ws_flush, ws_entry_bucket, ws_part, ws_big, ws_phi, ws_segrun, ws_grpsum, ws_winpart, ws_fb_lanes, ws_fb_var;
   // IPA / verifier workspaces
   DevBuf ws_g, ws_h, ws_a, ws_b, ws_g2, ws_h2, ws_a2, ws_b2, ws_idx, ws_lr, ws_terms_sc, ws_small;
+  DevBuf ws_sv_tab, ws_sv_acc, ws_sv_sc, ws_rp_sums;      // batch verifier: variable-point tables / window sums / split scalars; Gsum, Hsum
+  std::vector<unsigned char> rp_sums_src; unsigned long long rp_sums_gen = 0;   // generator bytes the kept sums belong to
+  cudaStream_t var_stream = nullptr;                      // batch verifier: proof-specific terms, concurrent with the table lookups
+  cudaEvent_t var_done[2] = {nullptr, nullptr}, ev_rp0 = nullptr, ev_rp1 = nullptr;
+  int ensure_var_stream() {
+    if (!var_stream) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&var_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return fail("stream creation failed");
+    }
+    for (int i = 0; i < 2; i++)
+      if (!var_done[i] && cudaEventCreateWithFlags(&var_done[i], cudaEventDisableTiming) != cudaSuccess) return fail("event creation failed");
+    return 0;
+  }
   // pipelined single-MSM path: 2 accumulate streams, one reduce stream per window, one Horner stream
   unsigned pipeline_min_terms = 0xFFFFFFFFu;   // off by default: on B200 the tail kernels starve behind the resident accumulate blocks
   cudaStream_t ps_acc[2] = {nullptr, nullptr}, ps_red[20] = {nullptr}, ps_hor = nullptr;
@@ -109,6 +124,7 @@ struct Ctx {
     return 0;
   }
   int ensure_stage_events() {
+    if (!ev_rp0 && (cudaEventCreate(&ev_rp0) != cudaSuccess || cudaEventCreate(&ev_rp1) != cudaSuccess)) return fail("event creation failed");
     for (int i = 0; i < 2; i++)
       if (!stage_ev[i] && cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming) != cudaSuccess) return fail("event creation failed");
     return 0;
@@ -145,7 +161,8 @@ struct Ctx {
   void free_all() {
     DevBuf* all[] = {&ws_pts, &ws_sc, &ws_off, &ws_out, &ws_digits, &ws_entries, &ws_count, &ws_start, &ws_cursor, &ws_tiles,
                      &ws_buckets, &ws_segsum, &ws_winsum, &ws_misc, &ws_flush, &ws_g, &ws_h, &ws_a, &ws_b, &ws_g2, &ws_h2,
-                     &ws_a2, &ws_b2, &ws_idx, &ws_lr, &ws_terms_sc, &ws_small, &ws_entry_bucket, &ws_part, &ws_big, &ws_phi, &ws_segrun, &ws_grpsum, &ws_winpart, &ws_fb_lanes, &ws_fb_var};
+                     &ws_a2, &ws_b2, &ws_idx, &ws_lr, &ws_terms_sc, &ws_small, &ws_entry_bucket, &ws_part, &ws_big, &ws_phi, &ws_segrun, &ws_grpsum, &ws_winpart, &ws_fb_lanes, &ws_fb_var, &ws_sv_tab, &ws_sv_acc, &ws_sv_sc, &ws_rp_sums, &ws_halfoff};
+    rp_sums_src.clear();
     for (DevBuf* b : all) b->release();
   }
 };

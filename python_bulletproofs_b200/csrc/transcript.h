@@ -159,6 +159,67 @@ inline std::string point_to_b64(const uint8_t pt[64]) {
   return o;
 }
 
+// ---- allocation-free forms for the batch verifier's per-proof transcript checks ------------------------------
+// point_to_b64(pt) == slot, without building a std::string
+inline bool b64_point_eq(const uint8_t* slot, size_t len, const uint8_t pt[64]) {
+  static const char* A = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+  bool ident = true;
+  for (int i = 0; i < 64; i++) if (pt[i]) { ident = false; break; }
+  if (ident) return len == 4 && memcmp(slot, "AA==", 4) == 0;          // base64(b"\x00")
+  if (len != 44) return false;
+  uint8_t raw[33];
+  raw[0] = (pt[32] & 1) ? 3 : 2;
+  for (int i = 0; i < 32; i++) raw[1 + i] = pt[31 - i];
+  char o[44];
+  for (int i = 0, k = 0; i < 33; i += 3, k += 4) {
+    uint32_t v = (uint32_t)raw[i] << 16 | (uint32_t)raw[i + 1] << 8 | raw[i + 2];
+    o[k] = A[(v >> 18) & 63]; o[k + 1] = A[(v >> 12) & 63]; o[k + 2] = A[(v >> 6) & 63]; o[k + 3] = A[v & 63];
+  }
+  return memcmp(slot, o, 44) == 0;
+}
+
+// Plain 256-bit value of a run of ASCII digits (no reduction).  Returns 0 = not a plain digit run / empty, 1 = value in *out,
+// 2 = digits only but the value does not fit 256 bits.  *canonical = no superfluous leading zero (the form str(int) prints).
+inline int decimal_to_u256(const uint8_t* s, size_t n, Fq* out, bool* canonical) {
+  if (n == 0) return 0;
+  *canonical = !(n > 1 && s[0] == '0');
+  static const uint64_t P10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull,
+                                   10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull, 100000000000000ull,
+                                   1000000000000000ull, 10000000000000000ull, 100000000000000000ull, 1000000000000000000ull,
+                                   10000000000000000000ull};
+  uint64_t w[4] = {0, 0, 0, 0};
+  bool overflow = false;
+  for (size_t i = 0; i < n;) {                     // nineteen digits at a time: w = w * 10^k + chunk
+    size_t k = n - i < 19 ? n - i : 19;
+    uint64_t chunk = 0;
+    for (size_t j = 0; j < k; j++) {
+      unsigned d = (unsigned)s[i + j] - '0';
+      if (d > 9) return 0;
+      chunk = chunk * 10 + d;
+    }
+    unsigned __int128 cy = chunk;
+    for (int l = 0; l < 4; l++) { cy += (unsigned __int128)w[l] * P10[k]; w[l] = (uint64_t)cy; cy >>= 64; }
+    if (cy) overflow = true;
+    i += k;
+  }
+  if (overflow) return 2;
+  for (int l = 0; l < 4; l++) { out->v[2 * l] = (uint32_t)w[l]; out->v[2 * l + 1] = (uint32_t)(w[l] >> 32); }
+  return 1;
+}
+// slot == str(x) for a reduced scalar x: the slot must be the canonical decimal of exactly that integer
+inline bool decimal_slot_eq(const uint8_t* s, size_t n, const Fq& x) {
+  Fq v; bool canon;
+  return decimal_to_u256(s, n, &v, &canon) == 1 && canon && fq_eq(v, x);
+}
+// int(slot) mod q for a plain run of digits; fast path for values below 2^256, decimal_to_fq otherwise
+inline bool decimal_to_fq_fast(const uint8_t* s, size_t n, Fq* out) {
+  Fq v; bool canon;
+  int rc = decimal_to_u256(s, n, &v, &canon);
+  if (rc == 1) { *out = fq_reduce(v); return true; }
+  if (rc == 0) return false;
+  return decimal_to_fq(s, n, out);
+}
+
 inline void fq_from_le(Fq* r, const uint8_t* b) { memcpy(r->v, b, 32); }
 inline void fq_to_le(uint8_t* b, const Fq& a) { memcpy(b, a.v, 32); }
 

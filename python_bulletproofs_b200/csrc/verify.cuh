@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(64) k_rp_invert(const Fq* __restrict__ psc, Rp
 // One block per proof, n threads (n >= 32 rounded up by the launcher; extra threads idle).
 // Writes the proof's tpp term scalars / point indices and its 4 MSM offsets.
 __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, const Fq* __restrict__ inv, RpLayout lay, u32 nproofs, u32 pt_base, Fq* __restrict__ tsc,
-                                                    u32* __restrict__ tidx, u32* __restrict__ offsets) {
+                                                    u32* __restrict__ tidx, u32* __restrict__ offsets, Fq* __restrict__ vsc) {
+  // vsc (optional): the 5 + 2L full-width scalars on proof-specific points, in the order of svar.cuh (V, T1, T2, S, u_new, L_j, R_j)
   extern __shared__ Fq sm[];      // [0..L) x_j (mont) | [L..2L) x_j^-1 (mont) | 2L: y^-1 (mont) | 2L+1 .. : reduction scratch (blockDim)
   const u32 p = blockIdx.x, i = threadIdx.x, n = lay.n, L = lay.L;
   if (p >= nproofs) return;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
     Fq x2 = fq_from_mont(fq_mont(xm[i], xm[i])), xi2 = fq_from_mont(fq_mont(xim[i], xim[i]));
     st_fq(tsc + tb4 + 2 * n + 2 + i, fq_neg(x2));       tidx[tb4 + 2 * n + 2 + i] = pb + RP_LS + i;        // L_j : -x_j^2
     st_fq(tsc + tb4 + 2 * n + 2 + L + i, fq_neg(xi2));  tidx[tb4 + 2 * n + 2 + L + i] = pb + RP_LS + L + i; // R_j : -x_j^-2
+    if (vsc) { Fq* V = vsc + (size_t)p * (5 + 2 * L); st_fq(V + 5 + i, fq_neg(x2)); st_fq(V + 5 + L + i, fq_neg(xi2)); }
   }
   if (i == 0) {
     const Fq one = fq_one(), m1 = fq_neg(one);
@@ -157,6 +159,10 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
     // E4 non-generator terms
     st_fq(tsc + tb4 + 2 * n + 0, fq_mul(a, b)); tidx[tb4 + 2 * n + 0] = pb + RP_UNEW;
     st_fq(tsc + tb4 + 2 * n + 1, m1);           tidx[tb4 + 2 * n + 1] = pb + RP_PNEW;
+    if (vsc) {
+      Fq* V = vsc + (size_t)p * (5 + 2 * L);
+      st_fq(V + 0, fq_neg(z2)); st_fq(V + 1, fq_neg(x)); st_fq(V + 2, fq_neg(x2)); st_fq(V + 3, x); st_fq(V + 4, fq_mul(a, b));
+    }
     offsets[p] = (u32)tb1; offsets[nproofs + p] = (u32)tb2; offsets[2 * nproofs + p] = (u32)tb3; offsets[3 * nproofs + p] = (u32)tb4;
     if (p == nproofs - 1) offsets[4 * nproofs] = nproofs * lay.tpp;
   }
@@ -177,10 +183,13 @@ __global__ void __launch_bounds__(128) k_sum_points(const Affine* __restrict__ p
 }
 
 // accept[p] = all four MSM results of proof p are the identity
-__global__ void k_rp_accept(const Affine* __restrict__ res, u32 nproofs, uint8_t* __restrict__ accept) {
+// hok[p] = the host's transcript verdict (1 = passed; 0 reject / 2 defer override whatever the equations say)
+__global__ void k_rp_accept(const Affine* __restrict__ res, u32 nproofs, const uint8_t* __restrict__ bad, const uint8_t* __restrict__ hok,
+                            uint8_t* __restrict__ accept) {
   u32 p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs) return;
-  bool ok = true;
+  if (hok[p] != 1) { accept[p] = hok[p]; return; }
+  bool ok = bad[p] == 0;                                 // a proof with a point off the curve is rejected (svar.cuh)
   for (u32 e = 0; e < 4; e++) ok = ok && affine_is_identity(ld_affine(res + e * nproofs + p));
   accept[p] = ok ? 1 : 0;
 }
@@ -293,10 +302,12 @@ __global__ void __launch_bounds__(128) k_rp_fold(const XYZZ* __restrict__ part, 
 }
 
 // same decision from XYZZ sums (table path: fixed-generator part + other terms already added): identity <=> ZZ == 0
-__global__ void k_rp_accept_xyzz(const XYZZ* __restrict__ res, u32 nproofs, uint8_t* __restrict__ accept) {
+__global__ void k_rp_accept_xyzz(const XYZZ* __restrict__ res, u32 nproofs, const uint8_t* __restrict__ bad, const uint8_t* __restrict__ hok,
+                                 uint8_t* __restrict__ accept) {
   u32 p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs) return;
-  bool ok = true;
+  if (hok[p] != 1) { accept[p] = hok[p]; return; }
+  bool ok = bad[p] == 0;
   for (u32 e = 0; e < 4; e++) ok = ok && xyzz_is_identity(ld_xyzz(res + e * nproofs + p));
   accept[p] = ok ? 1 : 0;
 }

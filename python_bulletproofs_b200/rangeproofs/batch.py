@@ -73,6 +73,34 @@ def verify_packed(batch: PackedBatch, g, h, gs, hs, u, first=0, count=None):
     return accept.raw[:count]
 
 
+def verify_packed_sharded(batch: PackedBatch, g, h, gs, hs, u, rank, world):
+    """Proof-sharded batch: this rank verifies its contiguous block, the accept bytes of all ranks are
+    all-gathered on the device (one ncclAllGather inside bp_rp_verify_batch_gather) -> accept bytes of the WHOLE batch on
+    every rank.  `world` > 1 needs sharding.init_nccl() first."""
+    from ..sharding import all_slices
+    slices = all_slices(batch.nproofs, world)
+    first, last = slices[rank]
+    count = last - first
+    width = max(b - a for a, b in slices) if slices else 0
+    out = ctypes.create_string_buffer(max(width * world, 1))
+    tr_off = ctypes.cast(ctypes.byref(batch.tr_off, 8 * 3 * first), ctypes.POINTER(ctypes.c_uint64))
+    starts = ctypes.cast(ctypes.byref(batch.starts, 4 * first), ctypes.POINTER(ctypes.c_uint32))
+    recs = ctypes.c_char_p(batch.records[first * batch.stride:(first + count) * batch.stride])
+    nat.check(nat.load().bp_rp_verify_batch_gather(
+        nat.pack_points(gs), nat.pack_points(hs), nat.pack_point(g), nat.pack_point(h), nat.pack_point(u), batch.n,
+        recs, batch.stride, count, batch.blob, tr_off, starts, width, out))
+    raw = out.raw
+    return b"".join(raw[r * width:r * width + (b - a)] for r, (a, b) in enumerate(slices))
+
+
+def verify_stats():
+    """dict of the last batch call's measurements (bp_rp_verify_stats)."""
+    v = (ctypes.c_double * 7)()
+    nat.check(nat.load().bp_rp_verify_stats(v))
+    return {"wall_ms": v[0], "host_check_ms": v[1], "device_span_ms": v[2], "chunks": int(v[3]), "host_threads": int(v[4]),
+            "table_mode": int(v[5]), "proofs": int(v[6])}
+
+
 def verify_range_proofs_batch(Vs, g, h, gs, hs, u, proofs):
     """-> list[bool].  A proof the C layer cannot classify (exotic numeric transcript slot) is replayed
     through RangeVerifier so that the reference's exception type (ValueError / IndexError) surfaces."""

@@ -194,9 +194,11 @@ def test_range_transcript_tamper_value_error(golden):
         RangeVerifier(V, g, h, gs, hs, u, proof).verify()
 
 
-@pytest.mark.parametrize("n,count", [(8, 40), (64, 24)])
+@pytest.mark.parametrize("n,count", [(8, 40), (64, 64), (128, 16), (2, 16)])
 def test_batch_verify_decisions(n, count):
-    """bp_rp_verify_batch vs the oracle verifier, proof by proof, incl. corrupted proofs of every kind."""
+    """bp_rp_verify_batch vs the oracle verifier, proof by proof, incl. corrupted proofs of every kind (>= 64
+    decisions at 64 bits).  The batch runs three times: bucket method (first sight of the generator set), byte tables, 16-bit
+    tables -- the decisions must not depend on the path."""
     seeds = ["b0", "b1", "b2", "b3", "b4"]
     ogs, ohs, og, oh, ou = gens(n, seeds)
     gs, hs, g, h, u = [P_(t) for t in ogs], [P_(t) for t in ohs], P_(og), P_(oh), P_(ou)
@@ -223,12 +225,80 @@ def test_batch_verify_decisions(n, count):
             pr.innerProof.u_new = pr.innerProof.u_new + g
         Vs.append(V); proofs.append(pr)
         oVs.append(T_(V)); oproofs.append(po.range_from_json(range_json(pr)))
-    got = verify_range_proofs_batch(Vs, g, h, gs, hs, u, proofs)
     want = [po.range_verify([oV], og, oh, ogs, ohs, ou, opr) for oV, opr in zip(oVs, oproofs)]
-    assert got == want
+    for _ in range(3):
+        assert verify_range_proofs_batch(Vs, g, h, gs, hs, u, proofs) == want
     assert want.count(True) == sum(1 for i in range(count) if i % 8 in (0, 7))
     # the class API agrees proof by proof
     for i in (0, 1, 4):
+        assert quiet(RangeVerifier(Vs[i], g, h, gs, hs, u, proofs[i]).verify) is want[i]
+
+
+def _small_batch(n, count, tag):
+    seeds = [tag + "%d" % i for i in range(5)]
+    ogs, ohs, og, oh, ou = gens(n, seeds)
+    gs, hs, g, h, u = [P_(t) for t in ogs], [P_(t) for t in ohs], P_(og), P_(oh), P_(ou)
+    rng = random.Random(11)
+    Vs, proofs = [], []
+    for i in range(count):
+        v = rng.getrandbits(n)
+        gamma = mod_hash(b"gm%d" % i, Q)
+        Vs.append(commitment(g, h, M_(v), gamma))
+        proofs.append(NIRangeProver(M_(v), n, g, h, gs, hs, gamma, u, secp256k1, b"q%d" % i).prove())
+    return gs, hs, g, h, u, Vs, proofs
+
+
+def test_batch_verify_rejects_points_off_the_curve():
+    """Proof-supplied coordinates that are not on secp256k1 (fastecdsa's Point constructor would raise ValueError, so the
+    reference can never see them) are rejected by the C ABI on every path, and Point() itself raises."""
+    from python_bulletproofs_b200.rangeproofs.batch import PackedBatch, verify_packed
+    n, count = 16, 12
+    gs, hs, g, h, u, Vs, proofs = _small_batch(n, count, "oc")
+    batch = PackedBatch.from_proofs(Vs, proofs, n)
+    stride, L = batch.stride, 4
+    rec = bytearray(batch.records)
+    off = {"V": 0, "A": 64, "S": 128, "T1": 192, "T2": 256, "u_new": 416, "P_new": 480, "L0": 608 + 32 * L, "R3": 608 + 32 * L + 64 * L + 64 * 3}
+    for k, (name, o) in enumerate(off.items()):
+        base = (k + 1) * stride + o
+        if k % 2 == 0:
+            rec[base + 32] ^= 1                      # y altered: (x, y') is not on the curve
+        else:
+            rec[base:base + 32] = (ecc.P + 5).to_bytes(32, "little")     # x >= p: not canonical
+    batch.records = bytes(rec)
+    want = bytes([1] + [0] * len(off) + [1] * (count - 1 - len(off)))
+    for _ in range(3):                                # bucket method, byte tables, 16-bit tables
+        assert verify_packed(batch, g, h, gs, hs, u) == want
+    with pytest.raises(ValueError):
+        Point(5, 7, secp256k1)
+    with pytest.raises(ValueError):
+        Point(ecc.P + 1, 2, secp256k1)
+    assert Point(0, 0, None) == Point.IDENTITY_ELEMENT
+
+
+def test_batch_verify_transcript_slot_forms():
+    """Slots are compared as the reference compares them: str(x) == slot for the challenge slots (a leading zero or a
+    value + q is a different string), int(slot) for y, z, x (leading zeros are the same number)."""
+    n, count = 8, 6
+    gs, hs, g, h, u, Vs, proofs = _small_batch(n, count, "ts")
+    def edit(tr, slot, fn):
+        parts = tr.split(b"&"); parts[slot] = fn(parts[slot]); return b"&".join(parts)
+    # 1: leading zero in a Protocol-2 challenge slot -> reject; 2: challenge + q in that slot -> reject
+    p2 = proofs[1].innerProof.proof2
+    p2.transcript = edit(p2.transcript, p2.start_transcript + 2, lambda s: b"0" + s)
+    p2 = proofs[2].innerProof.proof2
+    p2.transcript = edit(p2.transcript, p2.start_transcript + 2, lambda s: str(int(s) + Q).encode())
+    # 3: leading zeros in the y slot of the range transcript -> same number, still accepted
+    proofs[3].transcript = edit(proofs[3].transcript, 3, lambda s: b"000" + s)
+    # 4: Protocol-1 challenge slot with a leading zero -> reject
+    proofs[4].innerProof.transcript = edit(proofs[4].innerProof.transcript, 1, lambda s: b"0" + s)
+    # 5: z slot replaced by z + q -> same residue, accepted (ModP arithmetic reduces)
+    proofs[5].transcript = edit(proofs[5].transcript, 4, lambda s: str(int(s) + Q).encode())
+    want = [True, False, False, True, False, True]
+    ogs, ohs, og, oh, ou = [T_(t) for t in gs], [T_(t) for t in hs], T_(g), T_(h), T_(u)
+    assert [po.range_verify([T_(V)], og, oh, ogs, ohs, ou, po.range_from_json(range_json(pr))) for V, pr in zip(Vs, proofs)] == want
+    for _ in range(3):
+        assert verify_range_proofs_batch(Vs, g, h, gs, hs, u, proofs) == want
+    for i in range(count):
         assert quiet(RangeVerifier(Vs[i], g, h, gs, hs, u, proofs[i]).verify) is want[i]
 
 
