@@ -609,7 +609,7 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
     fbtab = fb_get(fbkey, src, table, lay.fixed);
     fbtab16 = fb_get16(fbkey, fbtab, lay.fixed);
     if (fbtab) {
-      d_lanes = (XYZZ*)g.ws_fb_lanes.ensure(4 * CH * (128 + 16) * sizeof(XYZZ));
+      d_lanes = (XYZZ*)g.ws_fb_lanes.ensure(4 * CH * (BP_RP_SLOTS + 8) * sizeof(XYZZ));
       d_var2 = (XYZZ*)g.ws_fb_var.ensure(3 * 4 * CH * sizeof(XYZZ));
       sv_T2 = (XYZZ*)g.ws_sv_tab.ensure(2 * CH * (size_t)nv * BP_SV_ENT * sizeof(XYZZ));
       sv_A2 = (XYZZ*)g.ws_sv_acc.ensure(2 * CH * (size_t)(96 + 12) * sizeof(XYZZ));
@@ -622,8 +622,8 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
       if (g.ensure_var_stream()) return 1;
     }
   }
-  const u32 bd = n < 32 ? 32 : (u32)n;
-  const size_t smem = (2 * L + 1 + bd) * sizeof(Fq);
+  const u32 bd = 2 * n < 64 ? 64 : (u32)(2 * n);           // k_rp_expand: g side and h side of every position
+  const size_t smem = (5 * n + 32 + 2 * L) * sizeof(Fq);
   const bool timing = getenv("BP_VERIFY_TIMING") != nullptr;
   double host_ms = 0;
   int chunk_no = 0;
@@ -695,12 +695,12 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
       BP_CUDA(cudaStreamWaitEvent(g.var_stream, g.aux_ready[cur], 0));
       ++g.nlaunch, k_sv_main<<<(unsigned)((cn * 32 + 127) / 128), 128, 0, g.var_stream>>>(cpts, lay, (u32)cn, sv_T, kd, kfl, sv_A);
       ++g.nlaunch, k_sv_comb1<<<(unsigned)((cn * 12 + 127) / 128), 128, 0, g.var_stream>>>(sv_A, (u32)(cn * 12), sv_G);
-      ++g.nlaunch, k_sv_comb2<<<(unsigned)((cn * 12 + 127) / 128), 128, 0, g.var_stream>>>(sv_G, cpts, lay, (u32)cn, d_var);
+      ++g.nlaunch, k_sv_comb2<<<(unsigned)((cn * 3 + 127) / 128), 128, 0, g.var_stream>>>(sv_G, cpts, lay, (u32)cn, d_var);
       BP_CUDA(cudaEventRecord(g.var_done[cur], g.var_stream));
-      if (fbtab16) ++g.nlaunch, k_rp_lookup16<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
-      else ++g.nlaunch, k_rp_lookup<<<(unsigned)cn, 256, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
-      XYZZ* d_grp = d_lanes + (size_t)4 * CH * 128;
-      ++g.nlaunch, k_rp_fold8<<<(nm * 16 + 127) / 128, 128, 0, g.stream>>>(d_lanes, nm, (u32)cn, d_grp);
+      if (fbtab16) ++g.nlaunch, k_rp_lookup16<<<(unsigned)cn, 128, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
+      else ++g.nlaunch, k_rp_lookup<<<(unsigned)cn, 128, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
+      XYZZ* d_grp = d_lanes + (size_t)4 * CH * BP_RP_SLOTS;
+      ++g.nlaunch, k_rp_fold8<<<(nm * 8 + 127) / 128, 128, 0, g.stream>>>(d_lanes, nm, (u32)cn, d_grp);
       BP_CUDA(cudaStreamWaitEvent(g.stream, g.var_done[cur], 0));
       ++g.nlaunch, k_rp_fold<<<(nm + 3) / 4, 128, 0, g.stream>>>(d_grp, d_var, nm, (u32)cn, d_tot);
       ++g.nlaunch, k_rp_accept_xyzz<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_tot, (u32)cn, d_bad, d_hok + chunk_lo, d_acc + chunk_lo);
@@ -984,6 +984,9 @@ __global__ void k_test_fq(int op, const Fq* a, const Fq* b, u32 n, Fq* out) {
     case 2: r = fq_sub(x, y); break;
     case 3: r = fq_inv(x); break;
     case 4: r = fq_neg(x); break;
+    case 5: r = fq_mul_dev(x, y); break;              // standard-form product of fqdev.cuh (pseudo-Mersenne folds)
+    case 6: r = fq_inv_dev(x); break;
+    case 7: r = fq_sqr_dev(x); break;
     default: r = x;
   }
   st_fq(out + i, r);
@@ -1018,7 +1021,8 @@ int bp_test_fq(int op, int on_device, const uint8_t* a32, const uint8_t* b32, si
   for (size_t i = 0; i < n; i++) {   // same fq.cuh code on the host
     Fq x, y, r; fq_from_le(&x, a32 + 32 * i); fq_from_le(&y, b32 + 32 * i); x = fq_reduce(x); y = fq_reduce(y);
     switch (op) { case 0: r = fq_mul(x, y); break; case 1: r = fq_add(x, y); break; case 2: r = fq_sub(x, y); break;
-                  case 3: r = fq_inv(x); break; case 4: r = fq_neg(x); break; default: r = x; }
+                  case 3: case 6: r = fq_inv(x); break; case 4: r = fq_neg(x); break; case 5: r = fq_mul(x, y); break;
+                  case 7: r = fq_mul(x, x); break; default: r = x; }
     fq_to_le(out32 + 32 * i, r);
   }
   return 0;

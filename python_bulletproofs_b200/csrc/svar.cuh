@@ -12,7 +12,7 @@
 //   k_sv_main   one WARP per proof, lane = 4-bit window position w of the 128-bit GLV halves: for every sub-term one table
 //               read + one addition per lane, no doublings:  A_w = sum_i d_{i,w} * P_i   (per equation)
 //   k_sv_comb1  one thread per (proof, equation, 8 windows): Horner with 4 doublings per step
-//   k_sv_comb2  one quad per (proof, equation): the remaining 96 doublings as 4-lane cooperative operations, plus the
+//   k_sv_comb2  one thread per (proof, equation): the remaining 96 doublings (Jacobian doubling chains), plus the
 //               unit-scalar terms; result = the variable part of "MSM == identity", added to the table part by k_rp_fold
 // Work per 64-bit proof: 119 table operations, ~1020 additions, 624 doublings -- 0.6 of the bucket pass's multiplications and
 // no latency chain longer than 96 doublings.
@@ -147,6 +147,34 @@ __global__ void __launch_bounds__(128, 4) k_sv_main(const Affine* __restrict__ p
   }
 }
 
+// ---- doubling chains in Jacobian coordinates -----------------------------------------------------------------------------
+// The tails below are chains of doublings with an occasional addition.  A Jacobian doubling on a = 0 (dbl-2009-l) costs
+// 2M + 5S = 369 IMAD.WIDE against 6M + 3S = 567 for the XYZZ doubling, and the change of coordinates is cheap:
+//   XYZZ (X, Y, ZZ, ZZZ) -> Jacobian (X*ZZ, Y*ZZZ, ZZ)      [x = X*ZZ/ZZ^2, y = Y*ZZZ/ZZ^3 with ZZ^3 = ZZZ^2]        2M
+//   Jacobian (X, Y, Z)   -> XYZZ (X, Y, Z^2, Z^3)                                                                     1M + 1S
+struct Jac { Fp X, Y, Z; };
+BP_DI Jac jac_from_xyzz(const XYZZ& p) { Jac r; r.X = fp_mul(p.X, p.ZZ); r.Y = fp_mul(p.Y, p.ZZZ); r.Z = p.ZZ; return r; }
+BP_DI XYZZ xyzz_from_jac(const Jac& p) { XYZZ r; r.X = p.X; r.Y = p.Y; r.ZZ = fp_sqr(p.Z); r.ZZZ = fp_mul(r.ZZ, p.Z); return r; }
+BP_DI Jac jac_dbl(const Jac& p) {          // the identity (Z = 0) stays the identity
+  Jac r;
+  const Fp A = fp_sqr(p.X), B = fp_sqr(p.Y), C = fp_sqr(B);
+  const Fp XB = fp_add(p.X, B);
+  const Fp D = fp_dbl(fp_sub(fp_sub(fp_sqr(XB), A), C));
+  const Fp E = fp_add(fp_dbl(A), A);
+  const Fp F = fp_sqr(E);
+  r.X = fp_sub(F, fp_dbl(D));
+  r.Y = fp_sub(fp_mul(E, fp_sub(D, r.X)), fp_dbl(fp_dbl(fp_dbl(C))));
+  r.Z = fp_dbl(fp_mul(p.Y, p.Z));
+  return r;
+}
+// 2^k * p
+__device__ __noinline__ XYZZ xyzz_dbl_k(const XYZZ& p, int k) {
+  Jac j = jac_from_xyzz(p);
+#pragma unroll 1
+  for (int d = 0; d < k; d++) j = jac_dbl(j);
+  return xyzz_from_jac(j);
+}
+
 // One thread per (proof, equation, group of 8 windows): G = sum_{j<8} 16^j A_{8g+j}
 __global__ void __launch_bounds__(128) k_sv_comb1(const XYZZ* __restrict__ Aw, u32 total, XYZZ* __restrict__ G) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;     // (p*3 + e)*4 + g
@@ -155,41 +183,34 @@ __global__ void __launch_bounds__(128) k_sv_comb1(const XYZZ* __restrict__ Aw, u
   XYZZ acc = ld_xyzz(A + 7);
 #pragma unroll 1
   for (int j = 6; j >= 0; j--) {
-#pragma unroll 1
-    for (int d = 0; d < 4; d++) acc = xyzz_dbl_ni(acc);
+    acc = xyzz_dbl_k(acc, 4);
     XYZZ v = ld_xyzz(A + j);
     xyzz_add_ni(acc, v);
   }
   st_xyzz(G + t, acc);
 }
 
-// One quad per (equation kind, proof): sum_g 2^(32g) G_g by Horner (96 cooperative doublings), then the unit-scalar terms
-// (E2: + A - P_new, E4: - P_new).  Quads are ordered kind-major like the MSM index m = E*cn + p of verify.cuh; the result
-// goes to var[m] (E3's slot was written by k_sv_table).  Control flow is identical in every quad (selects only).
+// One thread per (equation kind, proof): sum_g 2^(32g) G_g by Horner (96 doublings), then the unit-scalar terms
+// (E2: + A - P_new, E4: - P_new).  Threads are ordered kind-major like the MSM index m = E*cn + p of verify.cuh; the result
+// goes to var[m] (E3's slot was written by k_sv_table).  Thread form on purpose: the 4-lane cooperative form has the
+// shorter chain but costs ~3x the multiplier-pipe time, and this kernel runs underneath the table lookups of the same chunk.
 __global__ void __launch_bounds__(128) k_sv_comb2(const XYZZ* __restrict__ G, const Affine* __restrict__ pts, RpLayout lay, u32 cn,
                                                   XYZZ* __restrict__ var) {
-  u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
-  const bool active = q < 3 * cn;
-  if (!active) q = 3 * cn - 1;
+  const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 3 * cn) return;
   const u32 eq = q / cn, p = q % cn;
   const XYZZ* Gp = G + ((size_t)p * 3 + eq) * 4;
   XYZZ acc = ld_xyzz(Gp + 3);
 #pragma unroll 1
   for (int g4 = 2; g4 >= 0; g4--) {
-#pragma unroll 1
-    for (int d = 0; d < 32; d++) acc = coop_dbl(acc, role, base);
+    acc = xyzz_dbl_k(acc, 32);
     XYZZ v = ld_xyzz(Gp + g4);
-    acc = coop_add(acc, v, role, base);
+    xyzz_add_ni(acc, v);
   }
   const Affine* PP = pts + (size_t)p * lay.npt;
-  XYZZ ua = xyzz_from_affine(ld_affine(PP + RP_A));
-  XYZZ up = xyzz_neg(xyzz_from_affine(ld_affine(PP + RP_PNEW)));
-  ua = sel_xyzz(eq == 1u, ua, xyzz_identity());
-  up = sel_xyzz(eq >= 1u, up, xyzz_identity());
-#pragma unroll 1
-  for (int k = 0; k < 2; k++) acc = coop_add(acc, k == 0 ? ua : up, role, base);
-  if (active && role == 0) st_xyzz(var + (size_t)(eq == 2u ? 3u : eq) * cn + p, acc);
+  if (eq == 1u) { const Affine A = ld_affine(PP + RP_A); xyzz_madd_ni(acc, A); }
+  if (eq >= 1u) { const Affine Pn = affine_neg(ld_affine(PP + RP_PNEW)); xyzz_madd_ni(acc, Pn); }
+  st_xyzz(var + (size_t)(eq == 2u ? 3u : eq) * cn + p, acc);
 }
 
 }  // namespace bp

@@ -16,6 +16,7 @@
 #pragma once
 #include "ec.cuh"
 #include "fq.cuh"
+#include "fqdev.cuh"
 #include "ipa.cuh"
 #include "fixedbase.cuh"
 
@@ -52,50 +53,74 @@ __global__ void __launch_bounds__(64) k_rp_invert(const Fq* __restrict__ psc, Rp
   Fq acc = fq_one();
   for (u32 i = 0; i < cnt; i++) {
     Fq v = ld_fq(S + (i == 0 ? RS_Y : RS_XS + i - 1));
-    acc = fq_mul(acc, v);
+    acc = fq_mul_ni(acc, v);
     st_fq(out + i, acc);
   }
-  Fq t = fq_inv(acc);                                   // (v_0 ... v_L)^-1
+  Fq t = fq_inv_dev(acc);                               // (v_0 ... v_L)^-1
   for (int i = (int)cnt - 1; i >= 0; i--) {
     Fq v = ld_fq(S + (i == 0 ? RS_Y : RS_XS + i - 1));
     Fq prev = i > 0 ? ld_fq(out + i - 1) : fq_one();
-    st_fq(out + i, fq_mul(t, prev));                    // v_i^-1 = t * (v_0 ... v_{i-1})
-    t = fq_mul(t, v);
+    st_fq(out + i, fq_mul_ni(t, prev));                 // v_i^-1 = t * (v_0 ... v_{i-1})
+    t = fq_mul_ni(t, v);
   }
 }
 
-// One block per proof, n threads (n >= 32 rounded up by the launcher; extra threads idle).
-// Writes the proof's tpp term scalars / point indices and its 4 MSM offsets.
-__global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, const Fq* __restrict__ inv, RpLayout lay, u32 nproofs, u32 pt_base, Fq* __restrict__ tsc,
+// One block per proof, 2n threads (at least 64): thread i < n is the "g side" of position i, thread n + i its "h side".
+// Writes the proof's tpp term scalars / point indices, its 4 MSM offsets and (optionally) the variable scalars of svar.cuh.
+// All arithmetic in standard form (fqdev.cuh).  Shared work instead of per-thread exponentiations:
+//   y^i and y^-i      one Hillis-Steele product scan each (log2 n multiplications per thread; g side y, h side y^-1)
+//   s_i               = A[i >> lo] * B[i & (2^lo - 1)] with the two half-products tabulated by the first threads;
+//                     s_i^-1 = s_{n-1-i} (complemented bits)
+__global__ void __launch_bounds__(256) k_rp_expand(const Fq* __restrict__ psc, const Fq* __restrict__ inv, RpLayout lay, u32 nproofs, u32 pt_base, Fq* __restrict__ tsc,
                                                     u32* __restrict__ tidx, u32* __restrict__ offsets, Fq* __restrict__ vsc) {
   // vsc (optional): the 5 + 2L full-width scalars on proof-specific points, in the order of svar.cuh (V, T1, T2, S, u_new, L_j, R_j)
-  extern __shared__ Fq sm[];      // [0..L) x_j (mont) | [L..2L) x_j^-1 (mont) | 2L: y^-1 (mont) | 2L+1 .. : reduction scratch (blockDim)
-  const u32 p = blockIdx.x, i = threadIdx.x, n = lay.n, L = lay.L;
+  extern __shared__ Fq sm[];      // scan[2][2n] | sv[n] | AB[32] | xs[2L]
+  const u32 p = blockIdx.x, t = threadIdx.x, n = lay.n, L = lay.L;
   if (p >= nproofs) return;
   const Fq* S = psc + (size_t)p * lay.nsc;
-  Fq* xm = sm; Fq* xim = sm + L; Fq* yim = sm + 2 * L; Fq* red = sm + 2 * L + 1;
-  // inverses come from k_rp_invert
   const Fq* IV = inv + (size_t)p * (L + 1);
-  if (i < L) { xm[i] = fq_to_mont(ld_fq(S + RS_XS + i)); xim[i] = fq_to_mont(ld_fq(IV + 1 + i)); }
-  if (i == L) { *yim = fq_to_mont(ld_fq(IV)); }
-  __syncthreads();
-  const Fq y = ld_fq(S + RS_Y), z = ld_fq(S + RS_Z), x = ld_fq(S + RS_X), x1 = ld_fq(S + RS_X1);
-  const Fq that = ld_fq(S + RS_THAT), taux = ld_fq(S + RS_TAUX), mu = ld_fq(S + RS_MU), a = ld_fq(S + RS_A), b = ld_fq(S + RS_B);
-  const Fq ym = fq_to_mont(y), zm = fq_to_mont(z), R1 = fq_const_r();
-  const Fq z2m = fq_mont(zm, zm);
-  // y^i, y^-i (Montgomery) by square-and-multiply on the bits of i
-  Fq yi = R1, yii = R1;
-  if (i < n) {
-    for (int bit = 31 - __clz(i | 1); bit >= 0; bit--) {
-      yi = fq_mont(yi, yi); yii = fq_mont(yii, yii);
-      if ((i >> bit) & 1) { yi = fq_mont(yi, ym); yii = fq_mont(yii, *yim); }
-    }
+  Fq* scan0 = sm; Fq* scan1 = sm + 2 * n; Fq* sv = sm + 4 * n; Fq* AB = sm + 5 * n; Fq* xs = sm + 5 * n + 32;
+  const bool hside = t >= n && t < 2 * n, gside = t < n;
+  const u32 i = hside ? t - n : t;
+  const Fq y = ld_fq(S + RS_Y), z = ld_fq(S + RS_Z);
+  if (t < L) { xs[t] = ld_fq(S + RS_XS + t); xs[L + t] = ld_fq(IV + 1 + t); }
+  // ---- product scans: scan[t] = base for position >= 1, 1 for position 0
+  {
+    const Fq base = hside ? ld_fq(IV) : y;
+    if (t < 2 * n) scan0[t] = i == 0 ? fq_one() : base;
   }
-  // block sum of y^i for delta(y, z)
-  red[i] = i < n ? yi : fq_zero();
   __syncthreads();
-  for (u32 off = blockDim.x >> 1; off > 0; off >>= 1) {
-    if (i < off) red[i] = fq_add(red[i], red[i + off]);
+  Fq* src = scan0; Fq* dst = scan1;
+  for (u32 off = 1; off < n; off <<= 1) {
+    if (t < 2 * n) {
+      Fq v = src[t];
+      if (i >= off) v = fq_mul_ni(v, src[t - off]);
+      dst[t] = v;
+    }
+    __syncthreads();
+    Fq* tmp = src; src = dst; dst = tmp;
+  }
+  const Fq ypw = t < 2 * n ? src[t] : fq_zero();          // g side: y^i, h side: y^-i
+  // ---- s-vector half products: A over the top `hi` challenge bits, B over the low `lo` bits (bit j counted from the MSB)
+  const u32 lo = L / 2, hi = L - lo;
+  if (t < (1u << hi) + (1u << lo)) {
+    const bool isB = t >= (1u << hi);
+    const u32 idx = isB ? t - (1u << hi) : t, nb = isB ? lo : hi, j0 = isB ? hi : 0u;
+    Fq acc = fq_one();
+    for (u32 j = 0; j < nb; j++) {
+      const bool bit = (idx >> (nb - 1 - j)) & 1u;
+      acc = fq_mul_ni(acc, bit ? xs[j0 + j] : xs[L + j0 + j]);
+    }
+    AB[(isB ? 16u : 0u) + idx] = acc;
+  }
+  __syncthreads();
+  if (gside) sv[i] = fq_mul_ni(AB[i >> lo], AB[16 + (i & ((1u << lo) - 1u))]);
+  // block sum of y^i for delta(y, z): reuse the scan buffer that is not `src`
+  Fq* red = dst;
+  if (t < 2 * n) red[t] = gside ? ypw : fq_zero();
+  __syncthreads();
+  for (u32 off = n >> 1; off > 0; off >>= 1) {
+    if (t < off) red[t] = fq_add(red[t], red[t + off]);
     __syncthreads();
   }
   const Fq sum_y = red[0];
@@ -107,38 +132,36 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
                tb3 = (size_t)nproofs * (len1 + len2) + (size_t)p * len3, tb4 = (size_t)nproofs * (len1 + len2 + len3) + (size_t)p * len4;
   const u32 pb = pt_base + p * lay.npt;                  // point base of this proof (pt_base >= lay.fixed: after the generators)
   const u32 iG = 2 * n, iH = 2 * n + 1, iU = 2 * n + 2, iGsum = 2 * n + 3, iHsum = 2 * n + 4;
-  if (i < n) {
-    // ---- E2, generator terms
+  const Fq a = ld_fq(S + RS_A), b = ld_fq(S + RS_B);
+  if (gside) {
+    st_fq(tsc + tb4 + i, fq_mul_ni(a, sv[i]));                   tidx[tb4 + i] = i;          // a * s_i
+  }
+  if (hside) {
+    const Fq z2 = fq_mul_ni(z, z);
     Fq two_i = fq_zero(); if (i < 256) two_i.v[i >> 5] = 1u << (i & 31);   // 2^i, standard form (host enforces n <= 128)
     two_i = fq_reduce(two_i);
-    Fq hs_sc = fq_from_mont(fq_mont(fq_mont(z2m, fq_to_mont(two_i)), yii));              // z^2 * 2^i * y^-i  (z*hs_i is in Hsum)
-    st_fq(tsc + tb2 + 2 + i, hs_sc);              tidx[tb2 + 2 + i] = n + i;         // hs_i
-    // ---- E4, generator terms: s_i = prod_j (bit_j(i) ? x_j : x_j^-1), bit j counted from the MSB
-    Fq s = R1, sinv = R1;
-    for (u32 j = 0; j < L; j++) {
-      bool bit = (i >> (L - 1 - j)) & 1;
-      s = fq_mont(s, bit ? xm[j] : xim[j]);
-      sinv = fq_mont(sinv, bit ? xim[j] : xm[j]);
-    }
-    st_fq(tsc + tb4 + i, fq_mont(a, s));                         tidx[tb4 + i] = i;          // a * s_i
-    st_fq(tsc + tb4 + n + i, fq_mont(fq_mont(b, sinv), yii));  tidx[tb4 + n + i] = n + i;   // b * s_i^-1 * y^-i
+    // ---- E2: z^2 * 2^i * y^-i on hs_i  (z*hs_i is in Hsum)
+    st_fq(tsc + tb2 + 2 + i, fq_mul_ni(fq_mul_ni(z2, two_i), ypw));   tidx[tb2 + 2 + i] = n + i;
+    // ---- E4: b * s_i^-1 * y^-i on hs_i
+    st_fq(tsc + tb4 + n + i, fq_mul_ni(fq_mul_ni(b, sv[n - 1 - i]), ypw));  tidx[tb4 + n + i] = n + i;
   }
-  if (i < L) {
-    Fq x2 = fq_from_mont(fq_mont(xm[i], xm[i])), xi2 = fq_from_mont(fq_mont(xim[i], xim[i]));
-    st_fq(tsc + tb4 + 2 * n + 2 + i, fq_neg(x2));       tidx[tb4 + 2 * n + 2 + i] = pb + RP_LS + i;        // L_j : -x_j^2
-    st_fq(tsc + tb4 + 2 * n + 2 + L + i, fq_neg(xi2));  tidx[tb4 + 2 * n + 2 + L + i] = pb + RP_LS + L + i; // R_j : -x_j^-2
-    if (vsc) { Fq* V = vsc + (size_t)p * (5 + 2 * L); st_fq(V + 5 + i, fq_neg(x2)); st_fq(V + 5 + L + i, fq_neg(xi2)); }
+  if (t < L) {
+    const Fq x2 = fq_mul_ni(xs[t], xs[t]), xi2 = fq_mul_ni(xs[L + t], xs[L + t]);
+    st_fq(tsc + tb4 + 2 * n + 2 + t, fq_neg(x2));       tidx[tb4 + 2 * n + 2 + t] = pb + RP_LS + t;        // L_j : -x_j^2
+    st_fq(tsc + tb4 + 2 * n + 2 + L + t, fq_neg(xi2));  tidx[tb4 + 2 * n + 2 + L + t] = pb + RP_LS + L + t; // R_j : -x_j^-2
+    if (vsc) { Fq* V = vsc + (size_t)p * (5 + 2 * L); st_fq(V + 5 + t, fq_neg(x2)); st_fq(V + 5 + L + t, fq_neg(xi2)); }
   }
-  if (i == 0) {
+  if (t == 32 || (blockDim.x <= 32 && t == 0)) {         // a thread of the second warp: the first one carries the table work above
+    const Fq x = ld_fq(S + RS_X), x1 = ld_fq(S + RS_X1);
+    const Fq that = ld_fq(S + RS_THAT), taux = ld_fq(S + RS_TAUX), mu = ld_fq(S + RS_MU);
     const Fq one = fq_one(), m1 = fq_neg(one);
-    const Fq z2 = fq_from_mont(z2m), z3 = fq_mont(z2, zm);
+    const Fq z2 = fq_mul_ni(z, z), z3 = fq_mul_ni(z2, z);
     // delta = (z - z^2) * sum y^i - z^3 * (2^n - 1)
     Fq two_n = fq_zero();
     if (n < 256) two_n.v[n >> 5] = 1u << (n & 31);
     two_n = fq_reduce(two_n);
-    if (n >= 256) two_n = fq_pow_u64(fq_from_u64(2), n);
-    Fq delta = fq_sub(fq_mont(fq_sub(z, z2), sum_y), fq_mul(z3, fq_sub(two_n, one)));
-    Fq x2 = fq_mul(x, x);
+    Fq delta = fq_sub(fq_mul_ni(fq_sub(z, z2), sum_y), fq_mul_ni(z3, fq_sub(two_n, one)));
+    Fq x2 = fq_mul_ni(x, x);
     // E1
     st_fq(tsc + tb1 + 0, fq_sub(that, delta));  tidx[tb1 + 0] = iG;
     st_fq(tsc + tb1 + 1, taux);                 tidx[tb1 + 1] = iH;
@@ -149,7 +172,7 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
     st_fq(tsc + tb2 + 0, one);                  tidx[tb2 + 0] = pb + RP_A;
     st_fq(tsc + tb2 + 1, x);                    tidx[tb2 + 1] = pb + RP_S;
     st_fq(tsc + tb2 + 2 + n + 0, fq_neg(mu));              tidx[tb2 + 2 + n + 0] = iH;
-    st_fq(tsc + tb2 + 2 + n + 1, fq_mul(x1, that));        tidx[tb2 + 2 + n + 1] = iU;
+    st_fq(tsc + tb2 + 2 + n + 1, fq_mul_ni(x1, that));     tidx[tb2 + 2 + n + 1] = iU;
     st_fq(tsc + tb2 + 2 + n + 2, m1);                      tidx[tb2 + 2 + n + 2] = pb + RP_PNEW;
     st_fq(tsc + tb2 + 2 + n + 3, fq_neg(z));               tidx[tb2 + 2 + n + 3] = iGsum;        // sum_i (-z) * gs_i
     st_fq(tsc + tb2 + 2 + n + 4, z);                       tidx[tb2 + 2 + n + 4] = iHsum;        // sum_i z * hs_i
@@ -157,11 +180,12 @@ __global__ void __launch_bounds__(128) k_rp_expand(const Fq* __restrict__ psc, c
     st_fq(tsc + tb3 + 0, x1);                   tidx[tb3 + 0] = iU;
     st_fq(tsc + tb3 + 1, m1);                   tidx[tb3 + 1] = pb + RP_UNEW;
     // E4 non-generator terms
-    st_fq(tsc + tb4 + 2 * n + 0, fq_mul(a, b)); tidx[tb4 + 2 * n + 0] = pb + RP_UNEW;
+    const Fq ab = fq_mul_ni(a, b);
+    st_fq(tsc + tb4 + 2 * n + 0, ab);           tidx[tb4 + 2 * n + 0] = pb + RP_UNEW;
     st_fq(tsc + tb4 + 2 * n + 1, m1);           tidx[tb4 + 2 * n + 1] = pb + RP_PNEW;
     if (vsc) {
       Fq* V = vsc + (size_t)p * (5 + 2 * L);
-      st_fq(V + 0, fq_neg(z2)); st_fq(V + 1, fq_neg(x)); st_fq(V + 2, fq_neg(x2)); st_fq(V + 3, x); st_fq(V + 4, fq_mul(a, b));
+      st_fq(V + 0, fq_neg(z2)); st_fq(V + 1, fq_neg(x)); st_fq(V + 2, fq_neg(x2)); st_fq(V + 3, x); st_fq(V + 4, ab);
     }
     offsets[p] = (u32)tb1; offsets[nproofs + p] = (u32)tb2; offsets[2 * nproofs + p] = (u32)tb3; offsets[3 * nproofs + p] = (u32)tb4;
     if (p == nproofs - 1) offsets[4 * nproofs] = nproofs * lay.tpp;
@@ -195,85 +219,96 @@ __global__ void k_rp_accept(const Affine* __restrict__ res, u32 nproofs, const u
 }
 
 // ---- table path of the batch verifier: balanced lookups -------------------------------------------------------------
-// One block of 256 threads per proof.  The four equations have very different numbers of generator terms (2, n+4, 1,
-// 2n+1), so the 8 warps are dealt out as E1:1, E2:2, E3:1, E4:4; warp slice s of an equation takes its terms s, s+nw,
-// s+2nw, ... and lane l owns byte-window l (one table lookup + one mixed addition per (term, lane)).  Terms on
-// proof-specific points (idx >= nfixed) are skipped: they go through the bucket pass.  Lane sums land in
-// part[(4p+e)*128 + 32*s + l].
-__global__ void __launch_bounds__(256) k_rp_lookup(const Affine* __restrict__ tab, const u32* __restrict__ idx, const Fq* __restrict__ sc,
+// One block of 128 threads per proof.  The four equations have very different numbers of generator terms (2, n+4, 1,
+// 2n+1), so the 4 warps are dealt out as E4: 2 (interleaved term slices), E2: 1, E1 and E3: 1 (one after the other).  Table
+// entries carry their window weight, so any lane may add any (term, window) entry: the number of lanes per equation only
+// sets how many partial sums the fold kernels must add afterwards (64 / 32 / 32 / 32 here; 128 / 64 / 32 / 32 with the 256-
+// thread layout of round 1, whose folds cost a third of the lookups).  Terms on proof-specific points (idx >= nfixed) are
+// skipped: they take the window-parallel pass of svar.cuh.  Lane sums land in part[(e*nproofs + p)*64 + 32*s + lane].
+#define BP_RP_SLOTS 64
+BP_DI void rp_warp_role(u32 warp, u32 pass, u32& e, u32& nw, u32& s) {
+  if (warp < 2) { e = 3u; nw = 2u; s = warp; }
+  else if (warp == 2) { e = 1u; nw = 1u; s = 0u; }
+  else { e = pass == 0 ? 0u : 2u; nw = 1u; s = 0u; }
+}
+// byte tables: lane = byte window of one term per step
+__global__ void __launch_bounds__(128) k_rp_lookup(const Affine* __restrict__ tab, const u32* __restrict__ idx, const Fq* __restrict__ sc,
                                                    const u32* __restrict__ offsets, u32 nproofs, u32 nfixed, XYZZ* __restrict__ part) {
   const u32 p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p >= nproofs) return;
-  // warp -> (equation, slice, slices of that equation)
-  const u32 e = warp < 4 ? 3u : (warp < 6 ? 1u : (warp == 6 ? 0u : 2u));
-  const u32 nw = e == 3 ? 4u : (e == 1 ? 2u : 1u);
-  const u32 s = e == 3 ? warp : (e == 1 ? warp - 4 : 0u);
-  const u32 lo = __ldg(offsets + e * nproofs + p), hi = __ldg(offsets + e * nproofs + p + 1);
-  XYZZ acc = xyzz_identity();
-  for (u32 t = lo + s; t < hi; t += nw) {
-    const u32 gi = __ldg(idx + t);
-    if (gi >= nfixed) continue;
-    const u32* kw = reinterpret_cast<const u32*>(sc + t);
-    Fq k;
+#pragma unroll 1
+  for (u32 pass = 0; pass < (warp == 3 ? 2u : 1u); pass++) {
+    u32 e, nw, s;
+    rp_warp_role(warp, pass, e, nw, s);
+    const u32 lo = __ldg(offsets + e * nproofs + p), hi = __ldg(offsets + e * nproofs + p + 1);
+    XYZZ acc = xyzz_identity();
+    for (u32 t = lo + s; t < hi; t += nw) {
+      const u32 gi = __ldg(idx + t);
+      if (gi >= nfixed) continue;
+      const u32* kw = reinterpret_cast<const u32*>(sc + t);
+      Fq k;
 #pragma unroll
-    for (int i = 0; i < 8; i++) k.v[i] = __ldg(kw + i);
-    k = fq_reduce(k);
-    const u32 d = (k.v[lane >> 2] >> (8 * (lane & 3))) & 0xFFu;
-    if (d) { Affine q = ld_affine(tab + fb_index(gi, lane, d)); xyzz_madd_ni(acc, q); }
+      for (int i = 0; i < 8; i++) k.v[i] = __ldg(kw + i);
+      k = fq_reduce(k);
+      const u32 d = (k.v[lane >> 2] >> (8 * (lane & 3))) & 0xFFu;
+      if (d) { Affine q = ld_affine(tab + fb_index(gi, lane, d)); xyzz_madd_ni(acc, q); }
+    }
+    st_xyzz(part + ((size_t)(e * nproofs + p) * BP_RP_SLOTS + 32 * s + lane), acc);
   }
-  st_xyzz(part + ((size_t)(e * nproofs + p) * 128 + 32 * s + lane), acc);
 }
 // Same with the 16-bit table: lane l owns window l & 15 of the (l >> 4)-th of two terms taken per step, so a term costs 16
 // lookups; the table lives in HBM (8.9 GB), hence the next entry is loaded into registers under the current addition.
-__global__ void __launch_bounds__(256) k_rp_lookup16(const Affine* __restrict__ tab16, const u32* __restrict__ idx, const Fq* __restrict__ sc,
+__global__ void __launch_bounds__(128) k_rp_lookup16(const Affine* __restrict__ tab16, const u32* __restrict__ idx, const Fq* __restrict__ sc,
                                                      const u32* __restrict__ offsets, u32 nproofs, u32 nfixed, XYZZ* __restrict__ part) {
   const u32 p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p >= nproofs) return;
-  const u32 e = warp < 4 ? 3u : (warp < 6 ? 1u : (warp == 6 ? 0u : 2u));
-  const u32 nw = e == 3 ? 4u : (e == 1 ? 2u : 1u);
-  const u32 s = e == 3 ? warp : (e == 1 ? warp - 4 : 0u);
-  const u32 lo = __ldg(offsets + e * nproofs + p), hi = __ldg(offsets + e * nproofs + p + 1);
   const u32 win = lane & 15u, sub = lane >> 4;
-  XYZZ acc = xyzz_identity();
-  Affine cur; cur.x = fp_zero(); cur.y = fp_zero();
-  bool have = false;
-  for (u32 t = lo + 2 * s + sub; ; t += 2 * nw) {
-    // fetch the entry of term t (if any) while the previous one is being added
-    Affine nxt; nxt.x = fp_zero(); nxt.y = fp_zero();
-    bool nhave = false;
-    const bool in = t < hi;
-    if (in) {
-      const u32 gi = __ldg(idx + t);
-      if (gi < nfixed) {
-        const u32* kw = reinterpret_cast<const u32*>(sc + t);
-        Fq k;
+#pragma unroll 1
+  for (u32 pass = 0; pass < (warp == 3 ? 2u : 1u); pass++) {
+    u32 e, nw, s;
+    rp_warp_role(warp, pass, e, nw, s);
+    const u32 lo = __ldg(offsets + e * nproofs + p), hi = __ldg(offsets + e * nproofs + p + 1);
+    XYZZ acc = xyzz_identity();
+    Affine cur; cur.x = fp_zero(); cur.y = fp_zero();
+    bool have = false;
+    for (u32 t = lo + 2 * s + sub; ; t += 2 * nw) {
+      // fetch the entry of term t (if any) while the previous one is being added
+      Affine nxt; nxt.x = fp_zero(); nxt.y = fp_zero();
+      bool nhave = false;
+      const bool in = t < hi;
+      if (in) {
+        const u32 gi = __ldg(idx + t);
+        if (gi < nfixed) {
+          const u32* kw = reinterpret_cast<const u32*>(sc + t);
+          Fq k;
 #pragma unroll
-        for (int i = 0; i < 8; i++) k.v[i] = __ldg(kw + i);
-        k = fq_reduce(k);
-        const u32 d = (k.v[win >> 1] >> (16 * (win & 1))) & 0xFFFFu;
-        if (d) { nxt = ld_affine(tab16 + fb_index16(gi, win, d)); nhave = true; }
+          for (int i = 0; i < 8; i++) k.v[i] = __ldg(kw + i);
+          k = fq_reduce(k);
+          const u32 d = (k.v[win >> 1] >> (16 * (win & 1))) & 0xFFFFu;
+          if (d) { nxt = ld_affine(tab16 + fb_index16(gi, win, d)); nhave = true; }
+        }
       }
+      if (have) xyzz_madd_ni(acc, cur);
+      cur = nxt; have = nhave;
+      if (!__any_sync(BP_FULL_MASK, in)) break;          // both term slots of the warp are past the end
     }
-    if (have) xyzz_madd_ni(acc, cur);
-    cur = nxt; have = nhave;
-    if (!__any_sync(BP_FULL_MASK, in)) break;          // both term slots of the warp are past the end
+    st_xyzz(part + ((size_t)(e * nproofs + p) * BP_RP_SLOTS + 32 * s + lane), acc);
   }
-  st_xyzz(part + ((size_t)(e * nproofs + p) * 128 + 32 * s + lane), acc);
 }
-// Fold, step 1 (throughput form): one thread adds 8 consecutive lane sums; 16 group sums per equation slot
+// Fold, step 1 (throughput form): one thread adds 8 consecutive lane sums; 8 (E4) or 4 group sums per equation slot
 __global__ void __launch_bounds__(128) k_rp_fold8(const XYZZ* __restrict__ part, u32 nmsm, u32 nproofs, XYZZ* __restrict__ grp) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;          // (m, group of 8)
-  const u32 m = t >> 4, gq = t & 15;
+  const u32 m = t >> 3, gq = t & 7;
   if (m >= nmsm) return;
-  const u32 e = m / nproofs, ng = e == 3 ? 16u : (e == 1 ? 8u : 4u);
+  const u32 e = m / nproofs, ng = e == 3 ? 8u : 4u;
   if (gq >= ng) return;
-  const XYZZ* src = part + (size_t)m * 128 + 8 * gq;
+  const XYZZ* src = part + (size_t)m * BP_RP_SLOTS + 8 * gq;
   XYZZ v = ld_xyzz(src);
 #pragma unroll 1
   for (int j = 1; j < 8; j++) { XYZZ x = ld_xyzz(src + j); xyzz_add_ni(v, x); }
-  st_xyzz(grp + (size_t)m * 16 + gq, v);
+  st_xyzz(grp + (size_t)m * 8 + gq, v);
 }
-// Fold, step 2: one warp per equation: its <= 16 group sums + the bucket pass's partial `other[m]` -> out[m]
+// Fold, step 2: one warp per equation: its <= 8 group sums + the variable part `other[m]` -> out[m]
 __global__ void __launch_bounds__(128) k_rp_fold(const XYZZ* __restrict__ part, const XYZZ* __restrict__ other, u32 nmsm, u32 nproofs,
                                                  XYZZ* __restrict__ out) {
   __shared__ XYZZ sm[4][8];
@@ -281,12 +316,11 @@ __global__ void __launch_bounds__(128) k_rp_fold(const XYZZ* __restrict__ part, 
   u32 m = blockIdx.x * 4 + warp;
   const bool live = m < nmsm;
   if (!live) m = nmsm - 1;
-  const u32 e = m / nproofs, nl = e == 3 ? 16u : (e == 1 ? 8u : 4u);
+  const u32 e = m / nproofs, nl = e == 3 ? 8u : 4u;
   const int role = lane & 3, base = lane & ~3;
   const u32 q = lane >> 2;
-  const XYZZ* src = part + (size_t)m * 16;
+  const XYZZ* src = part + (size_t)m * 8;
   XYZZ v = q < nl ? ld_xyzz(src + q) : xyzz_identity();
-  if (nl > 8) { XYZZ x = ld_xyzz(src + q + 8); v = coop_add(v, x, role, base); }       // warp-uniform (one equation per warp)
   if (role == 0) st_xyzz(&sm[warp][q], v);
   __syncwarp();
 #pragma unroll 1

@@ -75,6 +75,23 @@ def test_fq_inv(dev):
     assert got == [pow(x, -1, Q) for x in a]
 
 
+def test_fq_device_standard_form_arithmetic():
+    """fqdev.cuh: product / square with the pseudo-Mersenne folds (q = 2^256 - c) and the windowed inversion, on operands
+    chosen to exercise every fold (all-ones limbs, values just below q, products just above multiples of 2^256)."""
+    rng = random.Random(77)
+    edge = [0, 1, 2, Q - 1, Q - 2, (Q + 1) // 2, 2 ** 128, 2 ** 128 - 1, 2 ** 255, Q - 2 ** 128, 2 ** 256 - Q, 2 ** 129 + 12345]
+    a = edge + [rng.getrandbits(256) % Q for _ in range(3000)]
+    b = [Q - 1] * len(edge) + [rng.getrandbits(256) % Q for _ in range(3000)]
+    a += edge; b += edge[::-1]
+    got = _un(call_test("bp_test_fq", 5, _le(a), _le(b), len(a), 32, 1))
+    assert got == [x * y % Q for x, y in zip(a, b)]
+    got = _un(call_test("bp_test_fq", 7, _le(a), _le(a), len(a), 32, 1))
+    assert got == [x * x % Q for x in a]
+    inv_in = [1, 2, Q - 1, Q - 2, 2 ** 128] + [rng.getrandbits(256) % Q or 1 for _ in range(200)]
+    got = _un(call_test("bp_test_fq", 6, _le(inv_in), _le(inv_in), len(inv_in), 32, 1))
+    assert got == [pow(x, -1, Q) for x in inv_in]
+
+
 def test_ec_ops_including_exceptional_cases():
     rng = random.Random(9)
     base = [ecc.py_mul(ecc.G, rng.getrandbits(256)) for _ in range(24)]
