@@ -40,8 +40,11 @@ def synth_inputs(n, seed):
     scalars uniform 256-bit (reduced mod q on the device)."""
     from python_bulletproofs_b200 import _native as nat
     rng = random.Random(seed)
-    pts = nat.scalar_mul_batch_bytes(nat.pack_xy(GX, GY) * n, rng.randbytes(32 * n), n)
-    return pts, rng.randbytes(32 * n)
+
+    def rb(nbytes, step=1 << 26):       # random.randbytes is limited to < 2^28 bytes per call
+        return b"".join(rng.randbytes(min(step, nbytes - o)) for o in range(0, nbytes, step))
+    pts = nat.scalar_mul_batch_bytes(nat.pack_xy(GX, GY) * n, rb(32 * n), n)
+    return pts, rb(32 * n)
 
 
 class ClockSampler:
@@ -103,6 +106,39 @@ def pinned_copy(nat, data):
     return buf
 
 
+def ncu_record():
+    """Counters of the dominant kernel taken from the committed ncu capture (profiles/r2_ncu_metrics.json, written by
+    tools/ncu_metrics.sh from one `ncu --set full` run of this same bench command); None when absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_metrics.json")) as f:
+            return json.load(f)
+    except Exception:   # noqa: BLE001
+        return None
+
+
+def launches(lib):
+    v = ctypes.c_uint64()
+    lib.bp_launch_count(ctypes.byref(v))
+    return v.value
+
+
+def run_ref_runner(argv, timeout=900):
+    """oracle/ref_runner.py as a subprocess (fork()-free next to a CUDA context) -> dict, or None when the reference copy is absent."""
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):     # torchrun pins these to 1; the CPU arm uses every host core
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, "-m", "oracle.ref_runner"] + argv, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return None
+    if out.returncode != 0:
+        return None
+    try:
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception:   # noqa: BLE001
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     from python_bulletproofs_b200 import _native as nat, sharding
@@ -132,7 +168,9 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
     t0 = time.time()
+    l0 = launches(lib)
     nat.check(lib.bp_bench_msm_sharded(hp, hs, 0, n, args.warmup, args.steps, 1, times, out))
+    gpu_launches = (launches(lib) - l0) * args.steps // (args.steps + args.warmup)      # kernels of the K timed steps (every step launches the same set)
     t1 = time.time()
     if dist is not None:
         dist.barrier()
@@ -170,15 +208,22 @@ def run_ours(args):
     achieved = issued_macs / (acc * 1e-3) / 1e12
     peak = macs.value / 1e12
     nominal = 148 * 64 * 1965.0 * 1e6 / 1e12
+    ncu = ncu_record() or {}
+    kacc = ncu.get("k_accumulate", {})
     roofline = {"bound": "imad", "kernel": "k_accumulate", "achieved": round(achieved, 3), "peak": round(peak, 3),
-                "unit": "T IMAD.WIDE (32x32+64 limb-MAC)/s", "frac": round(achieved / peak, 4), "traffic": 1547183120,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch, ncu --set full with its default cache flush between replay passes, i.e. cold L2 (profiles/r1_accumulate_v3_ncu.txt); algorithmic bytes: 16.78 M gathers x (64 B point + 8 B entry) = 1.21 GB",
+                "unit": "T IMAD.WIDE (32x32+64 limb-MAC)/s", "frac": round(achieved / peak, 4),
+                "traffic": kacc.get("dram_bytes"),
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch from profiles/r2_ncu_metrics.json "
+                                "(ncu --set full, cold L2: its default cache flush between replay passes); algorithmic bytes: one gathered 64 B "
+                                "point + 8 B entry per mixed add = %.2f GB" % (ent.value * 72 / 1e9),
                 "peak_source": "measured in this process: bp_imad_peak, data-dependent IMAD.WIDE.U32 stream (SASS checked); "
                                "IMAD.WIDE issues at half the 32-bit IMAD rate on B200, with or without the carry predicate",
                 "nominal_imad32_peak": round(nominal, 2),
-                "ncu_pipe_fmaheavy_active_pct": 80.4,
+                "ncu_pipe_fmaheavy_active_pct": kacc.get("pipe_fmaheavy_active_pct"),
+                "ncu_source": ncu.get("source"),
                 "window_bits": c, "windows": W, "glv": True, "mixed_adds_per_launch": ent.value, "kernel_ms": round(acc, 4),
                 "share_of_step": round(acc / med[6], 3),
+                "whole_step_frac": round(issued_macs / (total_ms / args.steps * 1e-3) / 1e12 / peak, 4),
                 "issued_limb_macs_per_launch": issued_macs,
                 "algorithmic_limb_macs_per_launch_survey_units": alg_macs,
                 "algorithmic_rate_survey_units_T_per_s": round(alg_macs / (acc * 1e-3) / 1e12, 3),
@@ -198,7 +243,8 @@ def run_ours(args):
     e2e_t = e2e_t[2:]
     assert out.raw.hex() == result_hex, "end-to-end result differs from resident result"
     e2e = {"value": round(world * n / (sum(e2e_t) / len(e2e_t)) / 1e6, 3), "unit": "Mpts/s", "h2d_bytes_per_step": 96 * n,
-           "d2h_bytes_per_step": 64, "api": "bp_msm_sharded_host (C ABI, pinned host buffers)" if world > 1 else "bp_msm / bp_msm_sharded_host (C ABI, pinned host buffers)"}
+           "d2h_bytes_per_step": 64, "h2d_gbs_per_rank": round(96 * n / (sum(e2e_t) / len(e2e_t)) / 1e9, 2),
+           "api": "bp_msm_sharded_host (C ABI, pinned host buffers)" if world > 1 else "bp_msm / bp_msm_sharded_host (C ABI, pinned host buffers)"}
     lib.bp_host_free(pp)
     lib.bp_host_free(ps)
     clocks = sampler.stop(t0, time.time())       # sampled from the start of the timed region through the e2e loop
@@ -218,6 +264,30 @@ def run_ours(args):
                 tot = ecc.point_add(tot, ecc.unpack_point(pb))
             sharded_ok = ecc.pack_point(tot).hex() == result_hex
 
+    # ---- strong scaling (ONE N-point MSM cut into contiguous slices [r*T/R, (r+1)*T/R)): totals 2^a, 2^b
+    strong = []
+    for lgt in args.strong:
+        T = 1 << lgt
+        lo, hi = sharding.slice_bounds(T, rank, world)
+        m = hi - lo
+        if m <= n:
+            sp, ss, free = hp, hs, False
+        else:
+            spts, ssc = synth_inputs(m, 0xB2000000 + lgt + 1000 * rank + 77)
+            sp, ss, free = ctypes.c_uint64(), ctypes.c_uint64(), True
+            nat.check(lib.bp_points_upload(spts, m, ctypes.byref(sp)))
+            nat.check(lib.bp_scalars_upload(ssc, m, ctypes.byref(ss)))
+            del spts, ssc
+        st = (ctypes.c_float * 5)()
+        if dist is not None:
+            dist.barrier()
+        nat.check(lib.bp_bench_msm_sharded(sp, ss, 0, m, 3, 5, 1, st, out))
+        ms = max_over_ranks(dist, float(sum(st)) / 5)
+        strong.append({"terms_total": T, "terms_per_gpu": m, "ms_per_msm": round(ms, 4), "value": round(T / (ms * 1e-3) / 1e6, 2), "unit": "Mpts/s"})
+        if free:
+            lib.bp_handle_free(sp)
+            lib.bp_handle_free(ss)
+
     line = {"metric": METRIC, "value": round(value, 3), "unit": "Mpts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (256-bit modular integer)", "data": "synthetic",
@@ -225,19 +295,23 @@ def run_ours(args):
                        "terms_per_gpu": n, "terms_total": world * n, "window_bits": c,
                        "l2": "flushed between steps (256 MiB memset outside the timed events)",
                        "parallelism": "slice%d" % world, "seed": "0xB2000000+lgn(+1000*rank), points k_i*G"},
-            "gpu_launches": 13 * args.steps,
-            "clocks": clocks, "e2e": e2e, "roofline": roofline, "stages_ms": stages, "result": result_hex}
+            "gpu_launches": gpu_launches,
+            "clocks": clocks, "e2e": e2e, "roofline": roofline, "stages_ms": stages, "result": result_hex,
+            "strong_scaling": {"scaling": "strong", "note": "one MSM of terms_total terms cut into contiguous slices, one per GPU; "
+                               "slice MSM + ncclAllGather of the 128-byte partials + sum, max over ranks", "points": strong}}
 
     if rank == 0 and world == 1:
+        line["sweep"] = msm_sweep(lib, nat, hp, hs, args.lgn)
         line["cpu_baseline"], bit_exact = cpu_baseline(pts, sc, n, result_hex)
         line["bit_exact_vs_oracle"] = bit_exact
     if sharded_ok is not None:
         line["sharded_result_equals_sum_of_slices"] = sharded_ok
     if not args.no_verify:
         try:
-            line["verify"] = bench_verify(args, nat, dist, rank, world)
+            line["verify"] = bench_verify(args, nat, dist, rank, world, peak)
         except Exception as e:   # noqa: BLE001  -- the headline metric must still print
-            line["verify"] = {"error": repr(e)}
+            import traceback
+            line["verify"] = {"error": repr(e), "trace": traceback.format_exc()[-600:]}
     lib.bp_handle_free(hp)
     lib.bp_handle_free(hs)
     if rank == 0:
@@ -255,12 +329,29 @@ def measured_hbm():
         return 6650.0
 
 
+def msm_sweep(lib, nat, hp, hs, lgmax):
+    """BASELINE config 3: the resident MSM at 2^10 ... 2^lgmax terms (prefixes of the same resident vectors), L2 flushed
+    between iterations, median of 5 after 2 warm-up calls."""
+    out = ctypes.create_string_buffer(64)
+    rows = {}
+    for lg in range(10, lgmax + 1):
+        ts = (ctypes.c_float * 5)()
+        nat.check(lib.bp_bench_msm(hp, hs, 1 << lg, 2, 5, 1, ts, out))
+        ms = statistics.median(ts)
+        rows[str(lg)] = {"ms": round(ms, 4), "mpts_per_s": round((1 << lg) / ms / 1e3, 2), "window_bits": lib.bp_msm_last_window()}
+    return rows
+
+
 def cpu_baseline(pts, sc, n, gpu_hex):
-    """The oracle port (C, bucket method, all host threads) on the SAME 2^lgn inputs, plus the
-    reference's own subset-table algorithm restated in C on a 2^12 sample (it is impractical beyond
-    ~2^14)."""
+    """CPU baseline of the MSM leg, timed on this box's host cores:
+      * kind "reference": the reference's OWN Pippenger.multiexp (unmodified src/ from baseline/_ref over the fastecdsa stand-in),
+        one 2^10-term slice of the workload per core -- its best operating point (throughput falls from 2^10
+        on) -- plus single calls at 2^12 for the sweep; 2^13 and beyond take > 39 s per call (2^20: 2.3 G table entries,
+        cannot run);
+      * beside it the oracle port (C, bucket method, all host threads) on the SAME 2^lgn inputs, which also checks the GPU
+        result bit for bit, and the reference's subset-table algorithm restated in C at 2^12."""
     from oracle import ecc
-    cores = ecc.max_threads()
+    cores = os.cpu_count() or 1
     t = time.perf_counter()
     res = ecc.msm_bytes(pts, sc, n, "bucket", cores)
     dt = time.perf_counter() - t
@@ -269,92 +360,243 @@ def cpu_baseline(pts, sc, n, gpu_hex):
     t = time.perf_counter()
     ecc.msm_bytes(pts[:64 * ns], sc[:32 * ns], ns, "subset", 1)
     dts = time.perf_counter() - t
-    return ({"value": round(n / dt / 1e6, 4), "unit": "Mpts/s", "cores": cores, "kind": "port",
-             "sample": "full workload (2^%d terms) once, oracle/ecc_oracle.c bucket MSM on %d OpenMP threads, %.2f s; "
-                       "reference's subset-table algorithm restated in C, 1 thread, 2^12 terms: %.4f Mpts/s"
-                       % (n.bit_length() - 1, cores, dt, ns / dts / 1e6)}, bit_exact)
+    port = {"value": round(n / dt / 1e6, 4), "unit": "Mpts/s", "cores": cores, "kind": "port",
+            "sample": "full workload (2^%d terms) once, oracle/ecc_oracle.c bucket MSM on %d OpenMP threads, %.2f s; "
+                      "reference's subset-table algorithm restated in C, 1 thread, 2^12 terms: %.4f Mpts/s"
+                      % (n.bit_length() - 1, cores, dt, ns / dts / 1e6)}
+    r10 = run_ref_runner(["msm", "--lgn", "10", "--procs", str(cores), "--reps", "3"])
+    if not r10:
+        return port, bit_exact
+    r12 = run_ref_runner(["msm", "--lgn", "12", "--procs", str(cores), "--reps", "1"])
+    walls = r10["wall_s"][1:] or r10["wall_s"]
+    val = cores * 1024 * len(walls) / sum(walls) / 1e6
+    base = {"value": round(val, 6), "unit": "Mpts/s", "cores": cores, "kind": "reference",
+            "sample": "reference Pippenger.multiexp (src/pippenger/pippenger.py:22-61, unmodified, plain-Python fastecdsa stand-in), one 2^10-term "
+                      "slice of the C3 workload per core on %d processes, %d timed rounds of %.2f s (first round dropped); one core: %.0f pts/s"
+                      % (cores, len(walls), sum(walls) / len(walls), r10["pts_per_s_one_core"]),
+            "sweep_one_core_pts_per_s": {"10": round(r10["pts_per_s_one_core"], 1)},
+            "beyond": "2^13: 39 s per call, 2^14: 100 s (BASELINE.md 2.1, survey container); 2^16 and up impractical, 2^20 impossible (2.3 G table entries)",
+            "port": port}
+    if r12:
+        base["sweep_one_core_pts_per_s"]["12"] = round(4096 / r12["mean_single_call_s"], 1)
+    return base, bit_exact
 
 
-# ---- secondary metric: batch verification of 64-bit range proofs (config 5) ----------------------
-def bench_verify(args, nat, dist, rank, world):
+# ---- second half of the metric: batch verification of 64-bit range proofs (config 5) ----------------------
+def verify_work_model(n=64):
+    """IMAD.WIDE (32x32+64 multiply-accumulates) this implementation issues per verified n-bit proof on the table path:
+    72 per field multiplication, 45 per squaring (csrc/fp.cuh); Z_q products 120 (csrc/fqdev.cuh)."""
+    L = n.bit_length() - 1
+    M, S = 72, 45
+    madd, add, jdbl, mdbl = 8 * M + 2 * S, 12 * M + 2 * S, 2 * M + 5 * S, 4 * M + 3 * S
+    nfix = (2 * n + 1) + (n + 4) + 1 + 2                       # generator terms of E4, E2, E3, E1
+    nv = 5 + 2 * L                                             # proof-specific points with a full scalar
+    fixed = nfix * 16 * madd                                   # 16-bit windows: one lookup + mixed add per (term, window)
+    fold = (8 * 7 + 3 * 4 * 7 + 7 + 3 * 3 + 4) * add           # lane sums -> one point per equation, + the variable part
+    table = nv * (mdbl + 6 * madd) + (nv + 2) * (2 * S + M)    # 2P..8P per point, curve check of all proof points
+    main = 2 * nv * 32 * (15 / 16) * add + nv * 32 * (15 / 16) * M      # lane = window: one addition per (sub-term, window); beta*X on the phi half
+    comb1 = 3 * 4 * 7 * (4 * jdbl + 3 * M + S + add)
+    comb2 = 3 * 3 * (32 * jdbl + 3 * M + S + add) + 3 * madd
+    zq = (2 * n * 14 + 334) * 120                              # term scalars (k_rp_expand) + one inversion per proof
+    parts = {"fixed_base_lookups": fixed, "fold": fold, "variable_tables": table, "variable_window_sums": main,
+             "horner_tails": comb1 + comb2, "scalar_field": zq}
+    return {k: int(v) for k, v in parts.items()}, int(sum(parts.values())), nfix, nv
+
+
+def bench_verify(args, nat, dist, rank, world, imad_peak):
     import contextlib
     import io
-    from python_bulletproofs_b200 import Point, secp256k1
+    from python_bulletproofs_b200 import Point, secp256k1, sharding
     from python_bulletproofs_b200.rangeproofs import NIRangeProver
-    from python_bulletproofs_b200.rangeproofs.batch import PackedBatch, verify_packed
+    from python_bulletproofs_b200.rangeproofs.batch import PackedBatch, verify_local_gather, verify_stats
     from python_bulletproofs_b200.utils import ModP, commitment, mod_hash, elliptic_hash
     q, nbits = secp256k1.q, 64
     seeds = [b"seed%d" % i for i in range(5)]
     gs = [elliptic_hash(str(i).encode() + seeds[0], secp256k1) for i in range(nbits)]
     hs = [elliptic_hash(str(i).encode() + seeds[1], secp256k1) for i in range(nbits)]
     g, h, u = (elliptic_hash(s, secp256k1) for s in seeds[2:5])
+    total = args.verify_proofs
+    slices = sharding.all_slices(total, world)
+    lo, hi = slices[rank]
+    counts = [b - a for a, b in slices]
     rng = random.Random(5)
-    distinct = args.verify_distinct
+    vals = [rng.getrandbits(64) for _ in range(total)]         # SURVEY.md 8(d) C5 stream: v_i in index order
+    # ---- every proof of the batch is distinct; rank r proves (and verifies) its own block [lo, hi)
     Vs, proofs = [], []
     t = time.perf_counter()
-    for i in range(distinct):
-        v = rng.getrandbits(64)
+    for i in range(lo, hi):
         gamma = mod_hash(b"gamma%d" % i, q)
-        Vs.append(commitment(g, h, ModP(v, q), gamma))
-        pr = NIRangeProver(ModP(v, q), nbits, g, h, gs, hs, gamma, u, secp256k1, b"p%d" % i).prove()
+        Vs.append(commitment(g, h, ModP(vals[i], q), gamma))
+        pr = NIRangeProver(ModP(vals[i], q), nbits, g, h, gs, hs, gamma, u, secp256k1, b"p%d" % i).prove()
         if i % 16 == 15:       # every 16th proof corrupted: flip one decimal digit of t_hat
             s = str(pr.t_hat.x)
             pr.t_hat = ModP(int(s[:-1] + ("1" if s[-1] != "1" else "2")), q)
         proofs.append(pr)
-    prove_s = (time.perf_counter() - t) / distinct
-    total = args.verify_proofs
-    reps = (total + distinct - 1) // distinct
-    batch = PackedBatch.from_proofs((Vs * reps)[:total], (proofs * reps)[:total], nbits)
-    lo, hi = (0, total) if world == 1 else __import__("python_bulletproofs_b200.sharding", fromlist=["x"]).slice_bounds(total, rank, world)
-    times = []
+    prove_s = (time.perf_counter() - t) / max(hi - lo, 1)
+    local = PackedBatch.from_proofs(Vs, proofs, nbits)
+    h2d = len(local.records) + len(local.blob)
+    times, spans, hosts = [], [], []
     acc = b""
-    for it in range(2 + 8):      # the first calls build the generator tables (byte windows, then 16-bit windows)
+    lib = nat.load()
+    l0 = 0
+    for it in range(4 + args.verify_reps):      # the first calls build the generator tables (byte windows, then 16-bit windows)
+        if it == 4:
+            l0 = launches(lib)
         if dist is not None:
             dist.barrier()
         a = time.perf_counter()
-        acc = verify_packed(batch, g, h, gs, hs, u, lo, hi - lo)
-        if world > 1:
-            from python_bulletproofs_b200 import sharding
-            acc = sharding.gather_accept(acc, [b - a_ for a_, b in sharding.all_slices(total, world)])
+        acc = verify_local_gather(local, g, h, gs, hs, u, counts)
         times.append(max_over_ranks(dist, time.perf_counter() - a))
-    best = min(times[2:])
-    want = bytes([0 if (i % distinct) % 16 == 15 else 1 for i in range(total)])
-    return {"metric": "64-bit range-proof verifies/s", "value": round(total / best, 1), "unit": "verifies/s", "n_gpus": world,
-            "scaling": "strong", "proofs": total, "distinct_proofs": distinct, "decisions_ok": acc == want,
-            "rejected": acc.count(b"\x00"), "ms_per_batch": round(best * 1e3, 2),
-            "note": "end to end through bp_rp_verify_batch with HOST buffers (packed proofs + transcripts H2D, accept bytes D2H); "
-                    "proofs made by the GPU prover (%.1f ms/proof), %d distinct proofs tiled to %d, every 16th corrupted" % (prove_s * 1e3, distinct, total)}
+        st = verify_stats()
+        spans.append(max_over_ranks(dist, st["device_span_ms"]))
+        hosts.append(st["host_check_ms"])
+    nl = (launches(lib) - l0) // max(args.verify_reps, 1)
+    times, spans, hosts = times[4:], spans[4:], hosts[4:]
+    med, best = statistics.median(times), min(times)
+    want = bytes([0 if i % 16 == 15 else 1 for i in range(total)])
+    res = {"metric": "64-bit range-proof verifies/s", "value": round(total / med, 1), "unit": "verifies/s", "n_gpus": world,
+           "scaling": "strong", "proofs": total, "distinct_proofs": total, "proofs_per_gpu": counts[0],
+           "ms_per_batch": round(med * 1e3, 3), "ms_per_batch_best": round(best * 1e3, 3), "value_best": round(total / best, 1),
+           "batches_timed": len(times), "decisions_ok": acc == want, "rejected": acc.count(b"\x00"),
+           "gpu_launches_per_batch": nl,
+           "e2e": {"value": round(total / med, 1), "unit": "verifies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": total,
+                   "api": "bp_rp_verify_batch_gather (C ABI): packed proofs + transcripts in HOST memory -> host transcript checks, H2D, "
+                          "device equations, ncclAllGather of the accept bytes, D2H"},
+           "device_span_ms": round(statistics.median(spans), 3), "host_check_ms": round(statistics.median(hosts), 3),
+           "stats": st,
+           "note": "timed region = the whole call from host buffers (max over ranks, median of %d batches after 4 warm-up batches that "
+                   "build the generator tables); proofs made by the GPU prover (%.2f ms/proof), all distinct, every 16th corrupted"
+                   % (len(times), prove_s * 1e3)}
+    # ---- roofline of the verify leg: issued IMAD.WIDE of the table path / device span / measured IMAD.WIDE peak
+    parts, per_proof, nfix, nv = verify_work_model(nbits)
+    span = statistics.median(spans)
+    ach = per_proof * counts[0] / (span * 1e-3) / 1e12         # per GPU (every rank runs the same work over its block)
+    res["roofline"] = {"bound": "imad", "kernel": "batch verifier, all kernels of one batch (k_rp_lookup16 dominant)",
+                       "achieved": round(ach, 3), "peak": round(imad_peak, 3), "unit": "T IMAD.WIDE (32x32+64 limb-MAC)/s per GPU",
+                       "frac": round(ach / imad_peak, 4), "imad_wide_per_proof": per_proof, "imad_wide_per_proof_parts": parts,
+                       "generator_terms_per_proof": nfix, "proof_point_terms_per_proof": nv + 4,
+                       "gpu_ms": round(span, 3), "gpu_ms_note": "CUDA events on the library stream: first kernel of the first chunk .. last accept kernel "
+                       "(includes any wait for host transcript checks between chunks), max over ranks",
+                       "kernel_list": "profiles/r2_verify_kernels.csv (ncu --metrics gpu__time_duration.sum of one batch)", "traffic": None}
+    if rank == 0:
+        # ---- decisions against the ORACLE verifier: the first 128 proofs of this rank's block (incl. every corrupted one in
+        #      the sample), and the prover's output against the oracle prover on 16 proofs (byte-identical transcripts)
+        from oracle import protocol_oracle as po
+        T_ = lambda p_: None if p_.curve is None else (p_.x, p_.y)      # noqa: E731
+        ogs, ohs, og, oh, ou = [T_(x) for x in gs], [T_(x) for x in hs], T_(g), T_(h), T_(u)
+        sample = min(128, hi - lo)
+        dec_ok, corrupted = True, 0
+        for k in range(sample):
+            pr = proofs[k]
+            ip, p2 = pr.innerProof, pr.innerProof.proof2
+            op = {"taux": pr.taux.x % q, "mu": pr.mu.x % q, "t_hat": pr.t_hat.x % q, "T1": T_(pr.T1), "T2": T_(pr.T2), "A": T_(pr.A), "S": T_(pr.S),
+                  "transcript": pr.transcript,
+                  "ip": {"u_new": T_(ip.u_new), "P_new": T_(ip.P_new), "transcript": ip.transcript,
+                         "p2": {"a": p2.a.x % q, "b": p2.b.x % q, "xs": [x.x % q for x in p2.xs], "Ls": [T_(x) for x in p2.Ls],
+                                "Rs": [T_(x) for x in p2.Rs], "transcript": p2.transcript, "start": p2.start_transcript}}}
+            ok = po.range_verify([T_(Vs[k])], og, oh, ogs, ohs, ou, op)
+            corrupted += 0 if ok else 1
+            dec_ok = dec_ok and (acc[lo + k] == (1 if ok else 0))
+        res["decisions_vs_oracle"] = {"proofs": sample, "rejected_by_oracle": corrupted, "all_equal": dec_ok}
+        same = True
+        for k in range(min(args.verify_prover_check, hi - lo)):
+            i = lo + k
+            if i % 16 == 15:
+                continue
+            gamma = mod_hash(b"gamma%d" % i, q)
+            opr = po.range_prove([vals[i]], nbits, og, oh, ogs, ohs, [gamma.x], ou, b"p%d" % i)
+            same = same and proofs[k].transcript == opr["transcript"] and proofs[k].innerProof.proof2.transcript == opr["ip"]["p2"]["transcript"]
+        res["prover_vs_oracle"] = {"proofs": min(args.verify_prover_check, hi - lo), "byte_identical_transcripts": same}
+        if world == 1:
+            res["cpu_baseline"] = verify_cpu_baseline(Vs, proofs, og, oh, ogs, ohs, ou, T_, q)
+    return res
+
+
+def verify_cpu_baseline(Vs, proofs, og, oh, ogs, ohs, ou, T_, q):
+    """The reference's own RangeVerifier.verify (unmodified src/ from baseline/_ref, fastecdsa stand-in) fanned out over all host
+    cores by proof on a 64-proof sample of the same C5 stream (proved by the reference's own prover in the workers, untimed);
+    falls back to the oracle port (protocol_oracle.range_verify, one core) when the reference copy is absent."""
+    cores = os.cpu_count() or 1
+    r = run_ref_runner(["verify", "--count", "64", "--procs", str(cores)], timeout=1200)
+    if r:
+        want = "".join("0" if i % 16 == 15 else "1" for i in range(64))
+        return {"value": round(r["verifies_per_s"], 3), "unit": "verifies/s", "cores": r["procs"], "kind": "reference",
+                "sample": "64 proofs of the C5 stream, reference RangeVerifier.verify (src/rangeproofs/rangeproof_verifier.py:55-86) on %d processes, "
+                          "%.1f s; one core: %.3f verifies/s; reference decisions equal the expected pattern: %s"
+                          % (r["procs"], r["wall_s"], r["verifies_per_s_one_core"], r["decisions"] == want)}
+    from oracle import protocol_oracle as po
+    t = time.perf_counter()
+    cnt = min(64, len(proofs))
+    for k in range(cnt):
+        pr = proofs[k]
+        ip, p2 = pr.innerProof, pr.innerProof.proof2
+        op = {"taux": pr.taux.x % q, "mu": pr.mu.x % q, "t_hat": pr.t_hat.x % q, "T1": T_(pr.T1), "T2": T_(pr.T2), "A": T_(pr.A), "S": T_(pr.S),
+              "transcript": pr.transcript,
+              "ip": {"u_new": T_(ip.u_new), "P_new": T_(ip.P_new), "transcript": ip.transcript,
+                     "p2": {"a": p2.a.x % q, "b": p2.b.x % q, "xs": [x.x % q for x in p2.xs], "Ls": [T_(x) for x in p2.Ls],
+                            "Rs": [T_(x) for x in p2.Rs], "transcript": p2.transcript, "start": p2.start_transcript}}}
+        po.range_verify([T_(Vs[k])], og, oh, ogs, ohs, ou, op)
+    dt = time.perf_counter() - t
+    return {"value": round(cnt / dt, 2), "unit": "verifies/s", "cores": 1, "kind": "port",
+            "sample": "%d proofs, oracle/protocol_oracle.range_verify over the C oracle, one core" % cnt}
 
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """Reference arm: the CPU implementation of the path (oracle port; the reference itself is pure
-    Python + an absent third-party C extension and cannot travel), all host threads, same metric."""
+    """Reference arm: the reference's own CPU implementation of the path on this box's host cores -- the UNMODIFIED Python of
+    baseline/_ref (a copy of /root/reference/src made by build(); its absent third-party fastecdsa extension replaced by the
+    plain-Python stand-in), every host core busy: one 2^10-term slice of the C3 workload per core and step (the reference is
+    single threaded, and 2^10 is where its throughput peaks; at 2^20 its table would need 2.3 G entries).  Same metric, unit
+    and JSON keys as the GPU arm; plus a "verify" object for the second half of the metric.  When the reference copy is
+    absent the oracle port (C, OpenMP, all cores) is timed instead and says so ("kind": "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import ecc
-    cores = ecc.max_threads()
-    lgs = min(args.lgn, 18)
-    ns = 1 << lgs
-    rng = random.Random(0xB2000000 + args.lgn)
-    base = [ecc.py_mul(ecc.G, rng.getrandbits(256)) for _ in range(16)]
-    pts_l = ecc.scalar_mul_batch([base[i % 16] for i in range(ns)], [rng.getrandbits(256) for _ in range(ns)])
-    pts, sc = ecc.pack_points(pts_l), rng.randbytes(32 * ns)
-    ts = []
-    for it in range(args.warmup + args.steps):
-        t = time.perf_counter()
-        ecc.msm_bytes(pts, sc, ns, "bucket", cores)
-        ts.append(time.perf_counter() - t)
-    ts = ts[args.warmup:]
-    val = round(ns * len(ts) / sum(ts) / 1e6, 4)
-    sample = "2^%d-term sample of the 2^%d workload per step, oracle/ecc_oracle.c bucket MSM, %d OpenMP threads" % (lgs, args.lgn, cores)
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpts/s", "n_gpus": args.gpus, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": round(1e3 * sum(ts) / len(ts), 3), "higher_is_better": True, "scaling": "weak",
-                      "vs_baseline": None, "dtype": "u64x4 (256-bit modular integer, CPU)", "data": "synthetic",
-                      "config": {"workload": "C3: standalone MSM, 2^%d secp256k1 points (CPU arm: bounded sample)" % args.lgn, "sample_terms": ns},
-                      "cpu_baseline": {"value": val, "unit": "Mpts/s", "cores": cores, "kind": "port", "sample": sample},
-                      "e2e": {"value": val, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+    cores = os.cpu_count() or 1
+    steps, warm = args.steps, args.warmup
+    r = run_ref_runner(["msm", "--lgn", "10", "--procs", str(cores), "--reps", str(steps + max(warm, 1))], timeout=3000)
+    line = None
+    if r:
+        walls = r["wall_s"][max(warm, 1):]
+        val = round(cores * 1024 * len(walls) / sum(walls) / 1e6, 6)
+        sample = ("reference Pippenger.multiexp (unmodified src/pippenger/pippenger.py over the plain-Python fastecdsa stand-in), one 2^10-term slice of the "
+                  "2^%d workload per core and step, %d processes" % (args.lgn, cores))
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpts/s", "n_gpus": args.gpus, "steps": len(walls),
+                "warmup": max(warm, 1), "ms_per_step": round(1e3 * sum(walls) / len(walls), 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "Python int (256-bit modular integer, CPU)", "data": "synthetic",
+                "config": {"workload": "C3: standalone MSM, 2^%d secp256k1 points (CPU arm: bounded sample)" % args.lgn, "sample_terms": cores * 1024},
+                "cpu_baseline": {"value": val, "unit": "Mpts/s", "cores": cores, "kind": "reference", "sample": sample,
+                                 "one_core_pts_per_s": round(r["pts_per_s_one_core"], 1)},
+                "e2e": {"value": val, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        v = run_ref_runner(["verify", "--count", "64", "--procs", str(cores)], timeout=1500)
+        if v:
+            line["verify"] = {"impl": "reference", "metric": "64-bit range-proof verifies/s", "value": round(v["verifies_per_s"], 3), "unit": "verifies/s",
+                              "cores": v["procs"], "kind": "reference", "one_core": round(v["verifies_per_s_one_core"], 3),
+                              "sample": "64 proofs of the C5 stream (reference prover, untimed), reference RangeVerifier.verify fanned out by proof over %d "
+                                        "processes, %.1f s" % (v["procs"], v["wall_s"])}
+    if line is None:
+        from oracle import ecc
+        lgs = min(args.lgn, 18)
+        ns = 1 << lgs
+        rng = random.Random(0xB2000000 + args.lgn)
+        base = [ecc.py_mul(ecc.G, rng.getrandbits(256)) for _ in range(16)]
+        pts_l = ecc.scalar_mul_batch([base[i % 16] for i in range(ns)], [rng.getrandbits(256) for _ in range(ns)])
+        pts, sc = ecc.pack_points(pts_l), rng.randbytes(32 * ns)
+        ts = []
+        for it in range(warm + steps):
+            t = time.perf_counter()
+            ecc.msm_bytes(pts, sc, ns, "bucket", cores)        # explicit thread count: torchrun exports OMP_NUM_THREADS=1
+            ts.append(time.perf_counter() - t)
+        ts = ts[warm:]
+        val = round(ns * len(ts) / sum(ts) / 1e6, 4)
+        sample = "2^%d-term sample of the 2^%d workload per step, oracle/ecc_oracle.c bucket MSM, %d OpenMP threads (reference copy baseline/_ref absent)" % (lgs, args.lgn, cores)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpts/s", "n_gpus": args.gpus, "steps": steps,
+                "warmup": warm, "ms_per_step": round(1e3 * sum(ts) / len(ts), 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64x4 (256-bit modular integer, CPU)", "data": "synthetic",
+                "config": {"workload": "C3: standalone MSM, 2^%d secp256k1 points (CPU arm: bounded sample)" % args.lgn, "sample_terms": ns},
+                "cpu_baseline": {"value": val, "unit": "Mpts/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -364,8 +606,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lgn", type=int, default=20)
+    ap.add_argument("--strong", type=lambda s: [int(x) for x in s.split(",") if x], default=[20, 23])
     ap.add_argument("--verify-proofs", type=int, default=8192)
-    ap.add_argument("--verify-distinct", type=int, default=64)
+    ap.add_argument("--verify-reps", type=int, default=12)
+    ap.add_argument("--verify-prover-check", type=int, default=16)
     ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

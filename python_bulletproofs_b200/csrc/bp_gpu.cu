@@ -34,6 +34,57 @@ int fail(const char* fmt, ...) {
   return 1;
 }
 
+// ---- bucket reduction + window combination (the "tails") of nmsm MSMs whose nmsm * sh.U bucket units are complete ----------
+static int msm_tails(const XYZZ* buckets, const MsmShape& sh, u32 nmsm, Affine* out_affine, XYZZ* out_xyzz, bool prof, cudaStream_t st) {
+  const size_t nmw = (size_t)nmsm * sh.U;
+  XYZZ* segsum = (XYZZ*)g.ws_segsum.ensure(nmw * sh.nseg * sizeof(XYZZ));
+  XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure(nmw * sizeof(XYZZ));
+  if (!segsum || !winsum) return fail("workspace allocation failed");
+  size_t nsegs = nmw * sh.nseg;
+  const bool plain_tails = nmsm >= 2048 && sh.H <= 512;     // big batch of small MSMs: throughput forms
+  const XYZZ* ws;
+  if (plain_tails) {
+    ++g.nlaunch, k_reduce_unit_plain<<<(unsigned)((nmw + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);
+    ws = segsum;
+    if (prof) cudaEventRecord(g.ev[5], st);
+    // Horner + output: one thread per MSM saturates the machine only for very many MSMs; below that the chain of
+    // ~126 doublings is pure latency and the 4-lane form (2.3 -> 1.3 us per doubling) wins
+    if (nmsm <= 12288 && !out_affine) ++g.nlaunch, k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+    else ++g.nlaunch, k_combine_plain<<<(unsigned)((nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+  } else {
+    XYZZ* seg_run = (XYZZ*)g.ws_segrun.ensure(nsegs * sizeof(XYZZ));
+    if (!seg_run) return fail("workspace allocation failed");
+    if (sh.seg_plain) ++g.nlaunch, k_reduce_seg_plain<<<(unsigned)((nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
+    else ++g.nlaunch, k_reduce_seg<<<(unsigned)((4 * nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
+    // level 2: groups of G = 8 segments (measured at 2^20, c = 16 after the thread-per-segment first level:
+    // G = 4 / 8 / 16 / 32 -> reduce stage 0.390 / 0.296 / 0.335 / 0.423 ms; the quad form pays ~2.4x the multiplications'
+    // issue cost in glue, so many small groups turn it throughput bound)
+    // (quad first level, S = 8, c = 13: G = 2 / 4 / 8 / 16 -> reduce stage 0.148 / 0.157 / 0.179 / 0.235 ms at 2^16)
+    const u32 Gmax = sh.seg_plain ? 8 : 2;
+    u32 G = sh.nseg < Gmax ? sh.nseg : Gmax, ngrp = sh.nseg / G;
+    int lgS = 0, lgG = 0, ubits = 0;
+    while ((1u << lgS) < sh.S) lgS++;
+    while ((1u << lgG) < G) lgG++;
+    while ((1u << ubits) < ngrp * (1u + sh.dbl)) ubits++;
+    XYZZ* grpsum = (XYZZ*)g.ws_grpsum.ensure(nmw * ngrp * sizeof(XYZZ));
+    if (!grpsum) return fail("workspace allocation failed");
+    ++g.nlaunch, k_reduce_grp<<<(unsigned)((4 * nmw * ngrp + 127) / 128), 128, 0, st>>>(seg_run, segsum, sh, nmw, 0, G, lgS, lgG, ubits, grpsum);
+    ws = grpsum;
+    if (ngrp >= 1024) {
+      // level 3 in two steps: 64 quads per block sum 256 groups each, then one small block per unit adds the partials
+      const u32 split = ngrp / 256;   // ngrp is a power of two
+      XYZZ* partial = (XYZZ*)g.ws_winpart.ensure(nmw * split * sizeof(XYZZ));
+      if (!partial) return fail("workspace allocation failed");
+      ++g.nlaunch, k_window_sum<<<(unsigned)(nmw * split), 256, 0, st>>>(grpsum, 256, partial);
+      ++g.nlaunch, k_window_sum<<<(unsigned)nmw, split < 8 ? 32 : 4 * split, 0, st>>>(partial, split, winsum);
+      ws = winsum;
+    } else if (ngrp > 1) { ++g.nlaunch, k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(grpsum, ngrp, winsum); ws = winsum; }
+    if (prof) cudaEventRecord(g.ev[5], st);
+    ++g.nlaunch, k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+  }
+  return 0;
+}
+
 // ---- the MSM pipeline on device-resident operands ----------------------------------------------
 // points/point_idx/scalars/offsets are device pointers; out_affine/out_xyzz device (either may be null)
 static int msm_run_pipelined(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, Affine* out_affine, XYZZ* out_xyzz);
@@ -141,48 +192,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
   }
   if (prof) cudaEventRecord(g.ev[4], st);
-  size_t nsegs = nmw * sh.nseg;
-  const bool plain_tails = nmsm >= 2048 && sh.H <= 512;     // big batch of small MSMs: throughput forms
-  const XYZZ* ws;
-  if (plain_tails) {
-    ++g.nlaunch, k_reduce_unit_plain<<<(unsigned)((nmw + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);
-    ws = segsum;
-    if (prof) cudaEventRecord(g.ev[5], st);
-    // Horner + output: one thread per MSM saturates the machine only for very many MSMs; below that the chain of
-    // ~126 doublings is pure latency and the 4-lane form (2.3 -> 1.3 us per doubling) wins
-    if (nmsm <= 12288 && !out_affine) ++g.nlaunch, k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
-    else ++g.nlaunch, k_combine_plain<<<(unsigned)((nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
-  } else {
-    XYZZ* seg_run = (XYZZ*)g.ws_segrun.ensure(nsegs * sizeof(XYZZ));
-    if (!seg_run) return fail("workspace allocation failed");
-    if (sh.seg_plain) ++g.nlaunch, k_reduce_seg_plain<<<(unsigned)((nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
-    else ++g.nlaunch, k_reduce_seg<<<(unsigned)((4 * nsegs + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, seg_run, segsum);
-    // level 2: groups of G = 8 segments (measured at 2^20, c = 16 after the thread-per-segment first level:
-    // G = 4 / 8 / 16 / 32 -> reduce stage 0.390 / 0.296 / 0.335 / 0.423 ms; the quad form pays ~2.4x the multiplications'
-    // issue cost in glue, so many small groups turn it throughput bound)
-    // (quad first level, S = 8, c = 13: G = 2 / 4 / 8 / 16 -> reduce stage 0.148 / 0.157 / 0.179 / 0.235 ms at 2^16)
-    const u32 Gmax = sh.seg_plain ? 8 : 2;
-    u32 G = sh.nseg < Gmax ? sh.nseg : Gmax, ngrp = sh.nseg / G;
-    int lgS = 0, lgG = 0, ubits = 0;
-    while ((1u << lgS) < sh.S) lgS++;
-    while ((1u << lgG) < G) lgG++;
-    while ((1u << ubits) < ngrp * (1u + sh.dbl)) ubits++;
-    XYZZ* grpsum = (XYZZ*)g.ws_grpsum.ensure(nmw * ngrp * sizeof(XYZZ));
-    if (!grpsum) return fail("workspace allocation failed");
-    ++g.nlaunch, k_reduce_grp<<<(unsigned)((4 * nmw * ngrp + 127) / 128), 128, 0, st>>>(seg_run, segsum, sh, nmw, 0, G, lgS, lgG, ubits, grpsum);
-    ws = grpsum;
-    if (ngrp >= 1024) {
-      // level 3 in two steps: 64 quads per block sum 256 groups each, then one small block per unit adds the partials
-      const u32 split = ngrp / 256;   // ngrp is a power of two
-      XYZZ* partial = (XYZZ*)g.ws_winpart.ensure(nmw * split * sizeof(XYZZ));
-      if (!partial) return fail("workspace allocation failed");
-      ++g.nlaunch, k_window_sum<<<(unsigned)(nmw * split), 256, 0, st>>>(grpsum, 256, partial);
-      ++g.nlaunch, k_window_sum<<<(unsigned)nmw, split < 8 ? 32 : 4 * split, 0, st>>>(partial, split, winsum);
-      ws = winsum;
-    } else if (ngrp > 1) { ++g.nlaunch, k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(grpsum, ngrp, winsum); ws = winsum; }
-    if (prof) cudaEventRecord(g.ev[5], st);
-    ++g.nlaunch, k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
-  }
+  if (msm_tails(buckets, sh, nmsm, out_affine, out_xyzz, prof, st)) return 1;
   if (halves) ++g.nlaunch, k_xyzz_pair<<<1, 32, 0, st>>>(pair_out, final_affine, final_xyzz);      // result = half 0 + half 1
   if (prof) cudaEventRecord(g.ev[6], st);
   BP_CUDA(cudaGetLastError());
@@ -278,6 +288,67 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
   return 0;
 }
 
+// ---- single MSM over a resident point vector with precomputed window multiples (msm.cuh, "pre" path) -----------------------
+// pre = [W][stride] affine multiples 2^(c*w) * P_i; the MSM covers points first .. first+T-1 of the vector.
+static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq* scalars, u32 T, Affine* out_affine, XYZZ* out_xyzz) {
+  cudaStream_t st = g.stream;
+  const PreShape ps = pre_shape(c);
+  MsmShape sh;                                         // shape of the tails: ONE unit of H buckets, nothing to combine
+  sh.c = c; sh.W = 1; sh.U = 1; sh.dbl = 0; sh.H = ps.H;
+  const double ent_bound = (double)ps.W * (double)T;
+  sh.chunk = ent_bound <= 1300000.0 ? 8 : (ent_bound <= 2600000.0 ? 16 : BP_CHUNK);
+  sh.seg_plain = (double)sh.H / 4 >= 32768.0 ? 1 : 0;
+  sh.S = sh.seg_plain ? 4 : (sh.H < 8 ? sh.H : 8);
+  sh.nseg = sh.H / sh.S;
+  g.last_c = c; g.last_nb = sh.H;
+  const bool prof = g.profiling;
+  if (prof) for (int i = 0; i < 7; i++) cudaEventRecord(g.ev[i], st), (void)0;
+  if (T == 0) {
+    BP_CUDA(cudaMemsetAsync(out_affine ? (void*)out_affine : (void*)out_xyzz, 0, out_affine ? sizeof(Affine) : sizeof(XYZZ), st));
+    if (out_affine && out_xyzz) BP_CUDA(cudaMemsetAsync(out_xyzz, 0, sizeof(XYZZ), st));
+    return 0;
+  }
+  if ((unsigned long long)ps.W * stride >= (1ull << 30)) return fail("msm: too many terms for 30-bit point indices");
+  const size_t nb = sh.H, emax = (size_t)ps.W * T, nchunks = (emax + sh.chunk - 1) / sh.chunk;
+  int* digits = (int*)g.ws_digits.ensure(emax * sizeof(int));
+  uint2* entries = (uint2*)g.ws_entries.ensure(emax * sizeof(uint2));
+  u32* count = (u32*)g.ws_count.ensure((nb + 1) * sizeof(u32));
+  u32* start = (u32*)g.ws_start.ensure((nb + 1) * sizeof(u32));
+  u32* cursor = (u32*)g.ws_cursor.ensure((nb + 1) * sizeof(u32));
+  const size_t ntiles = (nb + 1 + BP_SCAN_TILE - 1) / BP_SCAN_TILE;
+  u32* tiles = (u32*)g.ws_tiles.ensure(ntiles * sizeof(u32));
+  XYZZ* buckets = (XYZZ*)g.ws_buckets.ensure(nb * sizeof(XYZZ));
+  XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * nchunks * sizeof(XYZZ));
+  const size_t big_cap = emax / ((size_t)sh.chunk * BP_FIXUP_SERIAL_MAX) + 16;
+  u32* big = (u32*)g.ws_big.ensure((big_cap + 3) * sizeof(u32));
+  if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !part || !big) return fail("workspace allocation failed");
+  u32* zero_word = big + big_cap + 2;
+  BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
+  if (prof) cudaEventRecord(g.ev[0], st);
+  ++g.nlaunch, k_digits_pre<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, ps, digits, count);
+  if (prof) cudaEventRecord(g.ev[1], st);
+  ++g.nlaunch, k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
+  ++g.nlaunch, k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
+  ++g.nlaunch, k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
+  if (prof) cudaEventRecord(g.ev[2], st);
+  BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+  ++g.nlaunch, k_scatter_pre<<<(T + 255) / 256, 256, 0, st>>>(digits, T, ps, stride, first, cursor, entries);
+  if (prof) cudaEventRecord(g.ev[3], st);
+  BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));
+  BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
+  BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));
+  if (prof) cudaEventRecord(g.ev_k0, st);
+  ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pre, nullptr, nullptr, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
+  if (prof) cudaEventRecord(g.ev_k1, st);
+  ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big + 1);
+  ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
+  if (prof) cudaEventRecord(g.ev[4], st);
+  if (msm_tails(buckets, sh, 1, out_affine, out_xyzz, prof, st)) return 1;
+  if (prof) cudaEventRecord(g.ev[6], st);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 #include "bp_fixed.inl"
 
 // Host operands -> device: scalars first on the compute stream (the digit/sort stages only need them), points on a
@@ -319,7 +390,8 @@ static int msm_to_host(const Affine* d_pts, const Fq* d_sc, size_t n, uint8_t* o
   return 0;
 }
 
-struct HandleRec { void* p; size_t n; int kind; };   // kind 0 = points, 1 = scalars
+// kind 0 = points, 1 = scalars; pre/pre_c: precomputed window multiples of a point vector (bp_points_precompute)
+struct HandleRec { void* p; size_t n; int kind; Affine* pre = nullptr; int pre_c = 0; };
 static std::map<bp_handle, HandleRec> g_handles;
 static bp_handle g_next_handle = 1;
 static std::mutex g_mu;
@@ -482,7 +554,7 @@ int bp_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g.inited) return 0;
   cudaStreamSynchronize(g.stream);
-  for (auto& kv : g_handles) cudaFree(kv.second.p);
+  for (auto& kv : g_handles) { cudaFree(kv.second.p); if (kv.second.pre) cudaFree(kv.second.pre); }
   g_handles.clear();
   fb_release_all();
   g.free_all();
@@ -588,7 +660,8 @@ static int upload(const uint8_t* src, size_t n, size_t elt, int kind, bp_handle*
   if (n) BP_CUDA(cudaMemcpy(p, src, n * elt, cudaMemcpyHostToDevice));
   std::lock_guard<std::mutex> lk(g_mu);
   *h = g_next_handle++;
-  g_handles[*h] = HandleRec{p, n, kind};
+  HandleRec rec; rec.p = p; rec.n = n; rec.kind = kind;
+  g_handles[*h] = rec;
   return 0;
 }
 int bp_points_upload(const uint8_t* pts64, size_t n, bp_handle* h) { return upload(pts64, n, 64, 0, h); }
@@ -599,7 +672,55 @@ int bp_handle_free(bp_handle h) {
   if (it == g_handles.end()) return fail("bad handle");
   cudaStreamSynchronize(g.stream);
   cudaFree(it->second.p);
+  if (it->second.pre) cudaFree(it->second.pre);
   g_handles.erase(it);
+  return 0;
+}
+
+// MSM over points [first, first + n) of a resident vector: through its precomputed window multiples when it has them
+static int handle_msm(const HandleRec& P, size_t first, const Fq* d_sc, size_t n, Affine* out_affine, XYZZ* out_xyzz) {
+  if (P.pre && g.force_c == 0) return msm_run_pre(P.pre, (u32)P.n, (u32)first, P.pre_c, d_sc, (u32)n, out_affine, out_xyzz);
+  return msm_run((const Affine*)P.p + first, nullptr, d_sc, (u32)n, nullptr, 1, n, out_affine, out_xyzz);
+}
+
+static int handle_msm_to_host(const HandleRec& P, size_t first, const Fq* d_sc, size_t n, uint8_t* out64) {
+  Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
+  if (!d_out) return fail("workspace allocation failed");
+  if (handle_msm(P, first, d_sc, n, d_out, nullptr)) return 1;
+  BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int bp_points_precompute(bp_handle points, int window_bits) {
+  BP_NEED_INIT();
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_handles.find(points);
+  if (it == g_handles.end() || it->second.kind != 0) return fail("bad handle %llu", (unsigned long long)points);
+  HandleRec& P = it->second;
+  if (window_bits < 0 || (window_bits > 0 && window_bits < 8) || window_bits > 20) return fail("bp_points_precompute: window_bits 0 (automatic) or 8..20");
+  const int c = window_bits ? window_bits : pre_pick_window(P.n);
+  if (P.pre && P.pre_c == c) return 0;
+  const PreShape ps = pre_shape(c);
+  if (P.n == 0) return 0;
+  if ((unsigned long long)ps.W * P.n >= (1ull << 30)) return fail("bp_points_precompute: vector too long for 30-bit point indices");
+  cudaStreamSynchronize(g.stream);
+  if (P.pre) { cudaFree(P.pre); P.pre = nullptr; P.pre_c = 0; }
+  Affine* pre = nullptr;
+  if (cudaMalloc((void**)&pre, (size_t)ps.W * P.n * sizeof(Affine)) != cudaSuccess) { cudaGetLastError(); return fail("bp_points_precompute: out of device memory (%zu bytes)", (size_t)ps.W * P.n * sizeof(Affine)); }
+  ++g.nlaunch, k_pre_build<<<(unsigned)((P.n + 127) / 128), 128, 0, g.stream>>>((const Affine*)P.p, (u32)P.n, ps, pre);
+  cudaError_t e = cudaStreamSynchronize(g.stream);
+  if (e != cudaSuccess) { cudaGetLastError(); cudaFree(pre); return fail("k_pre_build failed: %s", cudaGetErrorString(e)); }
+  P.pre = pre; P.pre_c = c;
+  return 0;
+}
+int bp_points_pre_info(bp_handle points, int* window_bits, int* windows, uint64_t* bytes) {
+  HandleRec P;
+  if (get_handle(points, 0, &P)) return 1;
+  const PreShape ps = pre_shape(P.pre_c ? P.pre_c : 8);
+  if (window_bits) *window_bits = P.pre ? P.pre_c : 0;
+  if (windows) *windows = P.pre ? ps.W : 0;
+  if (bytes) *bytes = P.pre ? (uint64_t)ps.W * P.n * sizeof(Affine) : 0;
   return 0;
 }
 
@@ -612,7 +733,7 @@ int bp_msm_h(bp_handle points, const uint8_t* sc32, size_t n, uint8_t out64[64])
   Fq* d_sc = (Fq*)g.ws_sc.ensure(n * sizeof(Fq));
   if (!d_sc) return fail("device allocation failed");
   BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
-  return msm_to_host((const Affine*)P.p, d_sc, n, out64);
+  return handle_msm_to_host(P, 0, d_sc, n, out64);
 }
 
 int bp_msm_hh(bp_handle points, bp_handle scalars, size_t n, uint8_t out64[64]) {
@@ -621,7 +742,7 @@ int bp_msm_hh(bp_handle points, bp_handle scalars, size_t n, uint8_t out64[64]) 
   if (get_handle(points, 0, &P) || get_handle(scalars, 1, &S)) return 1;
   if (n > P.n || n > S.n) return fail("bp_msm_hh: n exceeds the uploaded vectors");
   if (n == 0) { memset(out64, 0, 64); return 0; }
-  return msm_to_host((const Affine*)P.p, (const Fq*)S.p, n, out64);
+  return handle_msm_to_host(P, 0, (const Fq*)S.p, n, out64);
 }
 
 int bp_msm_hh_partial(bp_handle points, bp_handle scalars, size_t first, size_t n, uint8_t out128[128]) {
@@ -631,7 +752,7 @@ int bp_msm_hh_partial(bp_handle points, bp_handle scalars, size_t first, size_t 
   if (first + n > P.n || first + n > S.n) return fail("bp_msm_hh_partial: slice exceeds the uploaded vectors");
   if (n == 0) { memset(out128, 0, 128); return 0; }
   XYZZ* d_out = (XYZZ*)g.ws_out.ensure(sizeof(XYZZ));
-  if (msm_run((const Affine*)P.p + first, nullptr, (const Fq*)S.p + first, (u32)n, nullptr, 1, n, nullptr, d_out)) return 1;
+  if (handle_msm(P, first, (const Fq*)S.p + first, n, nullptr, d_out)) return 1;
   BP_CUDA(cudaMemcpyAsync(out128, d_out, 128, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
@@ -714,7 +835,7 @@ int bp_bench_msm(bp_handle points, bp_handle scalars, size_t n, int warmup, int 
   for (int it = 0; it < warmup + iters; it++) {
     if (d_flush) BP_CUDA(cudaMemsetAsync(d_flush, it & 0xff, flush_bytes, g.stream));
     BP_CUDA(cudaEventRecord(g.ev_a, g.stream));
-    if (msm_run((const Affine*)P.p, nullptr, (const Fq*)S.p, (u32)n, nullptr, 1, n, d_out, nullptr)) return 1;
+    if (handle_msm(P, 0, (const Fq*)S.p, n, d_out, nullptr)) return 1;
     BP_CUDA(cudaEventRecord(g.ev_b, g.stream));
     BP_CUDA(cudaEventSynchronize(g.ev_b));
     float ms = 0;

@@ -791,12 +791,14 @@ int bp_allgather_bytes(const uint8_t* send, size_t nbytes, uint8_t* recv) {
 }
 // slice MSM on this rank -> ncclAllGather of the 128-byte XYZZ partials over NVLink -> every rank adds
 // the R partials and converts to the (identical, canonical) affine result in d_out.  All on g.stream.
-static int msm_sharded_device(const Affine* pts, const Fq* sc, size_t n, Affine* d_out, MsmOpts opt = MsmOpts()) {
+// hrec (optional): the slice is points [first, first + n) of that resident handle (which may carry precomputed multiples)
+static int msm_sharded_device(const Affine* pts, const Fq* sc, size_t n, Affine* d_out, MsmOpts opt = MsmOpts(), const HandleRec* hrec = nullptr,
+                              size_t first = 0) {
   int R = g_comm ? g_nranks : 1;
   XYZZ* d_part = (XYZZ*)g.ws_lr.ensure((size_t)(R + 1) * sizeof(XYZZ));
   if (!d_part) return fail("device allocation failed");
   if (n == 0) BP_CUDA(cudaMemsetAsync(d_part, 0, sizeof(XYZZ), g.stream));
-  else if (msm_run(pts, nullptr, sc, (u32)n, nullptr, 1, n, nullptr, d_part, opt)) return 1;
+  else if (hrec ? handle_msm(*hrec, first, sc, n, nullptr, d_part) : msm_run(pts, nullptr, sc, (u32)n, nullptr, 1, n, nullptr, d_part, opt)) return 1;
   const XYZZ* all = d_part;
   if (R > 1) {   // the single exchange step of the sharded MSM
     BP_NCCL(ncclAllGather(d_part, d_part + 1, sizeof(XYZZ), ncclUint8, g_comm, g.stream));
@@ -814,7 +816,7 @@ int bp_msm_sharded(bp_handle points, bp_handle scalars, size_t first, size_t n, 
   if (first + n > P.n || first + n > S.n) return fail("bp_msm_sharded: slice exceeds the uploaded vectors");
   Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
   if (!d_out) return fail("device allocation failed");
-  if (msm_sharded_device((const Affine*)P.p + first, (const Fq*)S.p + first, n, d_out)) return 1;
+  if (msm_sharded_device((const Affine*)P.p + first, (const Fq*)S.p + first, n, d_out, MsmOpts(), &P, first)) return 1;
   BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
@@ -848,7 +850,7 @@ int bp_bench_msm_sharded(bp_handle points, bp_handle scalars, size_t first, size
   for (int it = 0; it < warmup + iters; it++) {
     if (d_flush) BP_CUDA(cudaMemsetAsync(d_flush, it & 0xff, flush_bytes, g.stream));
     BP_CUDA(cudaEventRecord(g.ev_a, g.stream));
-    if (msm_sharded_device((const Affine*)P.p + first, (const Fq*)S.p + first, n, d_out)) return 1;
+    if (msm_sharded_device((const Affine*)P.p + first, (const Fq*)S.p + first, n, d_out, MsmOpts(), &P, first)) return 1;
     BP_CUDA(cudaEventRecord(g.ev_b, g.stream));
     BP_CUDA(cudaEventSynchronize(g.ev_b));
     float ms = 0;

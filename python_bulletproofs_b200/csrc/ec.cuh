@@ -134,6 +134,12 @@ BP_DI Fp ld_fp(const Fp* p) {
   Fp r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
   return r;
 }
+BP_DI Fp ld_fp_plain(const Fp* p) {       // coherent load: for kernels that re-read what they wrote
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Fp r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
 BP_DI Affine ld_affine(const Affine* p) { Affine r; r.x = ld_fp(&p->x); r.y = ld_fp(&p->y); return r; }
 BP_DI void st_fp(Fp* p, const Fp& a) {
   uint4* q = reinterpret_cast<uint4*>(p);

@@ -552,4 +552,106 @@ __global__ void __launch_bounds__(128) k_combine(const XYZZ* __restrict__ winsum
   if (out) st_affine(out + m, xyzz_to_affine(acc, nmsm <= 2));
 }
 
+// ---- resident point vectors with precomputed window multiples ("pre" path) ---------------------------------------------------
+// For a point vector that stays in HBM across many MSMs (bp_points_precompute: the generator vectors of a commitment scheme, the
+// resident operand of the C3 benchmark) the multiples 2^(c*w) * P_i, w = 0 .. W-1, are stored once (W * 64 bytes per point:
+// 0.94 GB for 2^20 points at c = 19 -- HBM3e capacity spent to delete work).  Every signed c-bit digit of a 256-bit scalar then
+// addresses a ready-made point, so ALL windows share ONE unit of 2^(c-1) buckets:
+//   * no Horner chain over windows (the 112 dependent doublings of k_combine), one bucket reduction instead of U of them;
+//   * the bucket unit no longer multiplies with the window count, so the window can widen (c = 19: 14 mixed additions per
+//     point instead of 16) while the reduction stays at 2^18 buckets;
+//   * no endomorphism split: a 256-bit scalar over W windows costs the same additions as two 128-bit halves over W/2, and the
+//     digit kernel loses its two 256x256-bit products per scalar, k_phi disappears.
+// Same sort / accumulate / fix-up / reduce kernels as the plain path: an entry's point index is w * stride + first + t.
+struct PreShape { int c, W; u32 H; };
+inline PreShape pre_shape(int c) { PreShape p; p.c = c; p.W = (257 + c - 1) / c; p.H = 1u << (c - 1); return p; }
+inline int pre_pick_window(size_t n) {     // multiplications: W(c) * n mixed additions (10) + 2 * 2^(c-1) bucket additions (14, ~3x for the latency-bound tails)
+  int best = 8; double bc = 1e300;
+  for (int c = 8; c <= 20; c++) {
+    const double W = (257 + c - 1) / c, cost = W * (double)n * 10.0 + 2.0 * (double)(1u << (c - 1)) * 14.0 * 3.0;
+    if (cost < bc) { bc = cost; best = c; }
+  }
+  return best;
+}
+
+// One thread per point: out[w * n + i] = 2^(c*w) * P_i (canonical affine), one inversion per point (Montgomery's trick over the
+// W Z coordinates), doublings in Jacobian coordinates (2M + 5S).
+#define BP_PRE_MAXW 33
+__global__ void __launch_bounds__(128) k_pre_build(const Affine* __restrict__ pts, u32 n, PreShape ps, Affine* __restrict__ out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Affine P = ld_affine(pts + i);
+  st_affine(out + i, P);
+  if (affine_is_identity(P)) {
+    for (int w = 1; w < ps.W; w++) st_affine(out + (size_t)w * n + i, P);
+    return;
+  }
+  // Jacobian chain: J_w = 2^(c*w) P; X, Y parked in the output slots, Z products kept in local memory
+  Fp X = P.x, Y = P.y, Z = fp_one();
+  Fp zs[BP_PRE_MAXW], pre[BP_PRE_MAXW];
+  Fp acc = fp_one();
+  for (int w = 1; w < ps.W; w++) {
+#pragma unroll 1
+    for (int d = 0; d < ps.c; d++) {
+      const Fp A = fp_sqr(X), B = fp_sqr(Y), C = fp_sqr(B);
+      const Fp D = fp_dbl(fp_sub(fp_sub(fp_sqr(fp_add(X, B)), A), C));
+      const Fp E = fp_add(fp_dbl(A), A);
+      const Fp X3 = fp_sub(fp_sqr(E), fp_dbl(D));
+      const Fp Z3 = fp_dbl(fp_mul(Y, Z));
+      Y = fp_sub(fp_mul(E, fp_sub(D, X3)), fp_dbl(fp_dbl(fp_dbl(C))));
+      X = X3; Z = Z3;
+    }
+    Affine t; t.x = X; t.y = Y;
+    st_affine(out + (size_t)w * n + i, t);          // Jacobian X, Y for now
+    zs[w] = Z;
+    acc = fp_mul(acc, Z);
+    pre[w] = acc;                                   // Z_1 ... Z_w  (never zero: P has prime order)
+  }
+  Fp inv = fp_inv(acc);
+  for (int w = ps.W - 1; w >= 1; w--) {
+    const Fp zi = w > 1 ? fp_mul(inv, pre[w - 1]) : inv;      // Z_w^-1
+    inv = fp_mul(inv, zs[w]);
+    const Fp zi2 = fp_sqr(zi), zi3 = fp_mul(zi2, zi);
+    Affine* slot = out + (size_t)w * n + i;
+    Affine t;
+    t.x = fp_canon(fp_mul(ld_fp_plain(&slot->x), zi2));
+    t.y = fp_canon(fp_mul(ld_fp_plain(&slot->y), zi3));
+    st_affine(slot, t);
+  }
+}
+
+// One thread per term: k mod q -> W signed c-bit digits (the top window keeps its digit: W*c >= 257 leaves it below 2^(c-1)),
+// histogram over the single bucket unit.  digits is [W][T].
+__global__ void __launch_bounds__(256) k_digits_pre(const Fq* __restrict__ scalars, u32 T, PreShape ps, int* __restrict__ digits,
+                                                    u32* __restrict__ bucket_count) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + t);
+  uint4 a = __ldg(sp), b = __ldg(sp + 1);
+  Fq k; k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
+  k = fq_reduce(k);                                   // es = [ei % order]   pippenger.py:26
+  u32 carry = 0;
+  for (int w = 0; w < ps.W; w++) {
+    const u32 d = scalar_bits(k, w * ps.c, ps.c) + carry;
+    int sd;
+    if (w + 1 < ps.W && d > ps.H) { sd = (int)d - (int)(2u * ps.H); carry = 1; } else { sd = (int)d; carry = 0; }
+    digits[(size_t)w * T + t] = sd;
+    if (sd != 0) atomicAdd(bucket_count + ((sd < 0 ? (u32)(-sd) : (u32)sd) - 1u), 1u);
+  }
+}
+
+// counting-sort scatter: entry = {point index | sign << 31, bucket}, point index = w * stride + first + t
+__global__ void __launch_bounds__(256) k_scatter_pre(const int* __restrict__ digits, u32 T, PreShape ps, u32 stride, u32 first,
+                                                     u32* __restrict__ cursor, uint2* __restrict__ entries) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  for (int w = 0; w < ps.W; w++) {
+    const int sd = digits[(size_t)w * T + t];
+    if (sd == 0) continue;
+    const u32 bkt = (sd < 0 ? (u32)(-sd) : (u32)sd) - 1u;
+    const u32 pos = atomicAdd(cursor + bkt, 1u);        // cursor[] starts at bucket_start[]: absolute slot
+    entries[pos] = make_uint2(((u32)w * stride + first + t) | (sd < 0 ? 0x80000000u : 0u), bkt);
+  }
+}
+
 }  // namespace bp

@@ -73,10 +73,22 @@ def verify_packed(batch: PackedBatch, g, h, gs, hs, u, first=0, count=None):
     return accept.raw[:count]
 
 
+def verify_local_gather(local: PackedBatch, g, h, gs, hs, u, counts):
+    """This rank's block `local` (counts[rank] proofs) is verified, then the accept bytes of all ranks are all-gathered on the
+    device (the one ncclAllGather inside bp_rp_verify_batch_gather) -> accept bytes of the WHOLE batch, on every rank.
+    More than one rank needs sharding.init_nccl() first."""
+    width = max(counts) if counts else 0
+    out = ctypes.create_string_buffer(max(width * len(counts), 1))
+    nat.check(nat.load().bp_rp_verify_batch_gather(
+        nat.pack_points(gs), nat.pack_points(hs), nat.pack_point(g), nat.pack_point(h), nat.pack_point(u), local.n,
+        local.records, local.stride, local.nproofs, local.blob, local.tr_off, local.starts, width, out))
+    raw = out.raw
+    return b"".join(raw[r * width:r * width + c] for r, c in enumerate(counts))
+
+
 def verify_packed_sharded(batch: PackedBatch, g, h, gs, hs, u, rank, world):
-    """Proof-sharded batch: this rank verifies its contiguous block, the accept bytes of all ranks are
-    all-gathered on the device (one ncclAllGather inside bp_rp_verify_batch_gather) -> accept bytes of the WHOLE batch on
-    every rank.  `world` > 1 needs sharding.init_nccl() first."""
+    """Proof-sharded batch from a batch every rank holds in full: rank r verifies the contiguous block
+    sharding.slice_bounds(nproofs, r, world); returns the accept bytes of the whole batch."""
     from ..sharding import all_slices
     slices = all_slices(batch.nproofs, world)
     first, last = slices[rank]
