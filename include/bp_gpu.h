@@ -47,6 +47,15 @@ int bp_msm(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64
 int bp_points_upload(const uint8_t* pts64, size_t n, bp_handle* h);
 int bp_scalars_upload(const uint8_t* sc32, size_t n, bp_handle* h);
 int bp_handle_free(bp_handle h);
+/* Precomputed window multiples for a resident point vector (fixed generators: the setting of every Bulletproofs commitment
+ * call site, src/utils/commitments.py:9-13): stores 2^(c*w) * P_i for the W = ceil(257/c) windows of a 256-bit scalar
+ * (W * 64 bytes per point; window_bits = 0 picks c from the vector length, 19 at 2^20 points = 0.94 GB).  Every later
+ * MSM over the handle (bp_msm_h, bp_msm_hh, bp_msm_hh_partial, bp_msm_sharded, bp_bench_msm*) then needs no doublings at
+ * all: one shared bucket unit, no Horner chain, 14 instead of 16 mixed additions per point.  Same canonical result.
+ * bp_msm_set_window(c > 0) forces the plain bucket method again. */
+int bp_points_precompute(bp_handle points, int window_bits);
+int bp_points_pre_info(bp_handle points, int* window_bits, int* windows, uint64_t* bytes);
+int bp_msm_set_pre_chunk(int entries);   /* experiment switch: entries per accumulation thread on that path (0 = automatic) */
 int bp_msm_h(bp_handle points, const uint8_t* sc32, size_t n, uint8_t out64[64]);     /* scalars from host */
 int bp_msm_hh(bp_handle points, bp_handle scalars, size_t n, uint8_t out64[64]);      /* all resident */
 /* XYZZ partial (4 x 32-byte LE: X, Y, ZZ, ZZZ) of a point slice, for sharding over GPUs

@@ -146,9 +146,9 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   size_t emax = (size_t)sh.W * 2 * T, nchunks = (emax + sh.chunk - 1) / sh.chunk;
   const size_t hchunks = ((size_t)sh.W * 2 * (T - T_half > T_half ? T - T_half : T_half) + sh.chunk - 1) / sh.chunk + 1;      // per part (the larger one)
   XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * (halves ? 2 * hchunks : nchunks) * sizeof(XYZZ));
-  size_t big_cap = emax / ((size_t)sh.chunk * BP_FIXUP_SERIAL_MAX) + 16;
-  u32* big = (u32*)g.ws_big.ensure((big_cap + 3) * sizeof(u32));
-  u32* zero_word = big + big_cap + 2;
+  const u32 big_cap = (u32)(emax / ((size_t)sh.chunk * (BP_FIXUP_SERIAL_MAX - 1)) + 16);      // buckets that can span that many chunks
+  u32* big = (u32*)g.ws_big.ensure((2 * (size_t)big_cap + 4) * sizeof(u32));
+  u32* zero_word = big + 2 * (size_t)big_cap + 3;
   if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !segsum || !winsum || !part || !big || !phi)
     return fail("workspace allocation failed");
 
@@ -178,8 +178,9 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
       ++g.nlaunch, k_accumulate<<<(unsigned)((hchunks + 127) / 128), 128, 0, st>>>(points, nullptr, phi, start, entries, gs, start + (k + 1) * hb, sh.chunk, buckets, part_k);
       if (prof && k == 1) cudaEventRecord(g.ev_k1, st);
       if (k == 1) BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));
-      ++g.nlaunch, k_fixup<<<(unsigned)((hb + 127) / 128), 128, 0, st>>>(start, k * hb, hb, gs, sh.chunk, part_k, buckets, big, big + 1);
-      ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, gs, sh.chunk, part_k, buckets, big, big + 1);
+      ++g.nlaunch, k_fixup<<<(unsigned)((hb + 127) / 128), 128, 0, st>>>(start, k * hb, hb, gs, sh.chunk, part_k, buckets, big, big_cap);
+      ++g.nlaunch, k_fixup_mid<<<2 * g.sm_count, 256, 0, st>>>(start, gs, sh.chunk, part_k, buckets, big, big_cap);
+      ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, gs, sh.chunk, part_k, buckets, big);
     }
   } else {
     if (opt.pts_ready) BP_CUDA(cudaStreamWaitEvent(st, opt.pts_ready, 0));   // points may still be uploading
@@ -188,8 +189,9 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     if (prof) cudaEventRecord(g.ev_k0, st);
     ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
     if (prof) cudaEventRecord(g.ev_k1, st);
-    ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big + 1);
-    ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
+    ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big_cap);
+    ++g.nlaunch, k_fixup_mid<<<2 * g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big_cap);
+    ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big);
   }
   if (prof) cudaEventRecord(g.ev[4], st);
   if (msm_tails(buckets, sh, nmsm, out_affine, out_xyzz, prof, st)) return 1;
@@ -234,8 +236,8 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
   XYZZ* hacc = winsum + W;                                   // Horner accumulator
   const size_t wchunks = ((size_t)2 * T + sh.chunk - 1) / sh.chunk + 1;      // a window holds at most 2T entries
   XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * W * wchunks * sizeof(XYZZ));
-  const size_t big_cap = (size_t)2 * T / ((size_t)sh.chunk * BP_FIXUP_SERIAL_MAX) + 16;
-  u32* big = (u32*)g.ws_big.ensure(W * (big_cap + 2) * sizeof(u32));
+  const u32 big_cap = (u32)((size_t)2 * T / ((size_t)sh.chunk * (BP_FIXUP_SERIAL_MAX - 1)) + 16);
+  u32* big = (u32*)g.ws_big.ensure(W * (2 * (size_t)big_cap + 2) * sizeof(u32));
   if (!digits || !entries || !phi || !count || !start || !cursor || !tiles || !buckets || !segsum || !seg_run || !grpsum || !winsum || !part || !big)
     return fail("workspace allocation failed");
   int lgS = 0, lgG = 0, ubits = 0;
@@ -245,7 +247,7 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
 
   if (g.profiling) cudaEventRecord(g.ev[0], st);
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
-  BP_CUDA(cudaMemsetAsync(big, 0, W * (big_cap + 2) * sizeof(u32), st));
+  BP_CUDA(cudaMemsetAsync(big, 0, W * (2 * (size_t)big_cap + 2) * sizeof(u32), st));
   ++g.nlaunch, k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
   ++g.nlaunch, k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, nullptr, 1, sh, digits, count, nullptr, 0);
   ++g.nlaunch, k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
@@ -262,13 +264,14 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
     cudaStream_t sa = g.ps_acc[k & 1], sr = g.ps_red[w], shh = g.ps_hor;
     const u32* gs = start + (size_t)w * sh.H;
     XYZZ* part_w = part + 2 * (size_t)w * wchunks;
-    u32* big_w = big + (size_t)w * (big_cap + 2);
+    u32* big_w = big + (size_t)w * (2 * (size_t)big_cap + 2);
     ++g.nlaunch, k_accumulate<<<(unsigned)((wchunks + 127) / 128), 128, g.pipe_acc_smem, sa>>>(points, point_idx, phi, start, entries, gs, gs + sh.H, sh.chunk, buckets, part_w);
     BP_CUDA(cudaEventRecord(g.pe_acc[w], sa));
     BP_CUDA(cudaStreamWaitEvent(sr, g.pe_acc[w], 0));
     // everything after the accumulation of window w is a latency chain on few SMs: it lives on the window's own stream
-    ++g.nlaunch, k_fixup<<<(unsigned)((sh.H + 63) / 64), 64, 0, sr>>>(start, (size_t)w * sh.H, sh.H, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
-    ++g.nlaunch, k_fixup_big<<<32, 64, 0, sr>>>(start, gs, sh.chunk, part_w, buckets, big_w, big_w + 1);
+    ++g.nlaunch, k_fixup<<<(unsigned)((sh.H + 63) / 64), 64, 0, sr>>>(start, (size_t)w * sh.H, sh.H, gs, sh.chunk, part_w, buckets, big_w, big_cap);
+    ++g.nlaunch, k_fixup_mid<<<16, 256, 0, sr>>>(start, gs, sh.chunk, part_w, buckets, big_w, big_cap);
+    ++g.nlaunch, k_fixup_big<<<32, 64, 0, sr>>>(start, gs, sh.chunk, part_w, buckets, big_w);
     const XYZZ* bw = buckets + (size_t)w * sh.H;
     ++g.nlaunch, k_reduce_seg<<<(unsigned)((4 * (size_t)sh.nseg + 31) / 32), 32, 0, sr>>>(bw, sh, 1, seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg);
     ++g.nlaunch, k_reduce_grp<<<(unsigned)((4 * (size_t)ngrp + 31) / 32), 32, 0, sr>>>(seg_run + (size_t)w * sh.nseg, segsum + (size_t)w * sh.nseg, sh, 1, (u32)w, G, lgS, lgG,
@@ -297,6 +300,7 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
   sh.c = c; sh.W = 1; sh.U = 1; sh.dbl = 0; sh.H = ps.H;
   const double ent_bound = (double)ps.W * (double)T;
   sh.chunk = ent_bound <= 1300000.0 ? 8 : (ent_bound <= 2600000.0 ? 16 : BP_CHUNK);
+  if (g.pre_chunk) sh.chunk = g.pre_chunk;
   sh.seg_plain = (double)sh.H / 4 >= 32768.0 ? 1 : 0;
   sh.S = sh.seg_plain ? 4 : (sh.H < 8 ? sh.H : 8);
   sh.nseg = sh.H / sh.S;
@@ -319,10 +323,10 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
   u32* tiles = (u32*)g.ws_tiles.ensure(ntiles * sizeof(u32));
   XYZZ* buckets = (XYZZ*)g.ws_buckets.ensure(nb * sizeof(XYZZ));
   XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * nchunks * sizeof(XYZZ));
-  const size_t big_cap = emax / ((size_t)sh.chunk * BP_FIXUP_SERIAL_MAX) + 16;
-  u32* big = (u32*)g.ws_big.ensure((big_cap + 3) * sizeof(u32));
+  const u32 big_cap = (u32)(emax / ((size_t)sh.chunk * (BP_FIXUP_SERIAL_MAX - 1)) + 16);
+  u32* big = (u32*)g.ws_big.ensure((2 * (size_t)big_cap + 4) * sizeof(u32));
   if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !part || !big) return fail("workspace allocation failed");
-  u32* zero_word = big + big_cap + 2;
+  u32* zero_word = big + 2 * (size_t)big_cap + 3;
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
   if (prof) cudaEventRecord(g.ev[0], st);
   ++g.nlaunch, k_digits_pre<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, ps, digits, count);
@@ -340,10 +344,31 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
   if (prof) cudaEventRecord(g.ev_k0, st);
   ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pre, nullptr, nullptr, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
   if (prof) cudaEventRecord(g.ev_k1, st);
-  ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big + 1);
-  ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big + 1);
+  ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big_cap);
+  ++g.nlaunch, k_fixup_mid<<<2 * g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big_cap);
+  ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big);
   if (prof) cudaEventRecord(g.ev[4], st);
-  if (msm_tails(buckets, sh, 1, out_affine, out_xyzz, prof, st)) return 1;
+  if (sh.H < 4096) {                                   // small unit: the running-sum tails of the plain path
+    if (msm_tails(buckets, sh, 1, out_affine, out_xyzz, prof, st)) return 1;
+  } else {
+    // H = R x C buckets: marginal sums by factors of 8 (rows contiguous, columns strided), weighted stage on R + C points
+    int lgH = c - 1, lgC = (lgH + 1) / 2, lgR = lgH - lgC;
+    const u32 C = 1u << lgC, R = 1u << lgR;
+    XYZZ* ping = (XYZZ*)g.ws_segsum.ensure(((size_t)nb / 4 + (size_t)nb / 32 + 4096) * sizeof(XYZZ));
+    XYZZ* wsum = (XYZZ*)g.ws_winsum.ensure((size_t)(C + R + 2) * sizeof(XYZZ));
+    if (!ping || !wsum) return fail("workspace allocation failed");
+    // level 1: factors of 8 (rows contiguous, columns strided) in one launch
+    const u32 Kr = C >= 8 ? 8u : C, Kc = R >= 8 ? 8u : R;
+    const u32 np_r = C / Kr, np_c = R / Kc;              // partial sums per row / per column (<= 128 for c <= 20)
+    XYZZ* rpart = ping; XYZZ* cpart = ping + ((size_t)nb / 8 + 2048);
+    const u32 nrow_out = R * np_r, ncol_out = np_c * C;
+    ++g.nlaunch, k_pre_marginals<<<dim3(((nrow_out > ncol_out ? nrow_out : ncol_out) + 127) / 128, 2), 128, 0, st>>>(buckets, rpart, nrow_out, Kr, buckets, cpart, np_c, C, Kc);
+    if (prof) cudaEventRecord(g.ev[5], st);
+    ++g.nlaunch, k_pre_rowcol<<<C + R, 64, 0, st>>>(rpart, np_r, cpart, np_c, C, R, wsum);
+    XYZZ* two = wsum + C + R;
+    ++g.nlaunch, k_pre_total<<<2, 256, 0, st>>>(wsum, C, R, two);
+    ++g.nlaunch, k_pre_finish<<<1, 32, 0, st>>>(two, lgC, out_affine, out_xyzz);
+  }
   if (prof) cudaEventRecord(g.ev[6], st);
   BP_CUDA(cudaGetLastError());
   return 0;
@@ -595,6 +620,7 @@ int bp_msm_last_entries(uint64_t* entries) {      // non-zero digits = mixed add
   return 0;
 }
 int bp_launch_count(uint64_t* launches) { *launches = g.nlaunch; return 0; }
+int bp_msm_set_pre_chunk(int entries) { g.pre_chunk = entries > 0 ? (unsigned)entries : 0; return 0; }   /* experiment switch */
 int bp_msm_set_profiling(int on) { g.profiling = on != 0; return 0; }
 int bp_msm_set_pipeline_min(size_t min_terms) { g.pipeline_min_terms = min_terms ? (unsigned)min_terms : 0xFFFFFFFFu; return 0; }
 int bp_msm_stage_ms(float out7[7]) {

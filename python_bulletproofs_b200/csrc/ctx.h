@@ -49,6 +49,7 @@ struct Ctx {
   DevBuf ws_halfoff;
   bool profiling = false;
   int force_c = 0, last_c = 0;
+  bool pre_attr_set = false; unsigned pre_chunk = 0;
   unsigned long long nlaunch = 0;               // kernels launched by this library so far (bp_launch_count)
   size_t last_nb = 0;
   // MSM workspaces

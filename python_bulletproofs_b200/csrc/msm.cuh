@@ -321,11 +321,13 @@ BP_DI const XYZZ* bucket_piece(const XYZZ* part, u32 s, u32 c0, u32 c, u32 CL) {
   return part + 2 * (size_t)c;
 }
 
-// one thread per bucket: buckets spanning up to BP_FIXUP_SERIAL_MAX chunks are summed here, larger
-// ones are queued for k_fixup_big (one block each).
+// one thread per bucket: buckets spanning up to BP_FIXUP_SERIAL_MAX chunks are summed here, larger ones are queued: up to
+// BP_FIXUP_WARP_MAX chunks for k_fixup_mid (one warp each), beyond that for k_fixup_big (one block each).
+// queue layout (u32 words): [0] big count, [1] mid count, [2 .. 2+cap) big list, [2+cap .. 2+2cap) mid list
+#define BP_FIXUP_WARP_MAX 2048
 __global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_start, size_t b0, size_t nb, const u32* __restrict__ gs_ptr, u32 CL,
-                                               const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, u32* __restrict__ big_count,
-                                               u32* __restrict__ big_list) {
+                                               const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, u32* __restrict__ queue, u32 cap) {
+  u32* big_count = queue; u32* mid_count = queue + 1; u32* big_list = queue + 2; u32* mid_list = queue + 2 + cap;
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   b += b0;
@@ -335,18 +337,43 @@ __global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_st
   s -= gs; e -= gs;
   u32 c0 = s / CL, c1 = (e - 1) / CL;
   if (c0 == c1) return;
-  if (c1 - c0 >= BP_FIXUP_SERIAL_MAX) { big_list[atomicAdd(big_count, 1u)] = (u32)b; return; }
+  if (c1 - c0 >= BP_FIXUP_WARP_MAX) { big_list[atomicAdd(big_count, 1u)] = (u32)b; return; }
+  if (c1 - c0 >= BP_FIXUP_SERIAL_MAX) { mid_list[atomicAdd(mid_count, 1u)] = (u32)b; return; }
   XYZZ acc = ld_xyzz(bucket_piece(part, s, c0, c0, CL));
   for (u32 c = c0 + 1; c <= c1; c++) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add(acc, v); }
   st_xyzz(buckets + b, acc);
 }
 
+// persistent warps over the queue of medium buckets: 32 lanes stride over the pieces, tree in shared memory
+__global__ void __launch_bounds__(256) k_fixup_mid(const u32* __restrict__ bucket_start, const u32* __restrict__ gs_ptr, u32 CL,
+                                                   const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, const u32* __restrict__ queue, u32 cap) {
+  __shared__ XYZZ sm[8][32];
+  const u32 n = queue[1], warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32* mid_list = queue + 2 + cap;
+  const u32 gs = __ldg(gs_ptr);
+  for (u32 q = blockIdx.x * 8 + warp; q < n; q += gridDim.x * 8) {
+    const u32 b = mid_list[q];
+    const u32 s = __ldg(bucket_start + b) - gs, e = __ldg(bucket_start + b + 1) - gs;
+    const u32 c0 = s / CL, c1 = (e - 1) / CL;
+    XYZZ acc = xyzz_identity();
+    for (u32 c = c0 + lane; c <= c1; c += 32) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add_ni(acc, v); }
+    sm[warp][lane] = acc;
+    __syncwarp();
+    for (int off = 16; off > 0; off >>= 1) {
+      if ((int)lane < off) { XYZZ v = sm[warp][lane + off]; xyzz_add_ni(acc, v); sm[warp][lane] = acc; }
+      __syncwarp();
+    }
+    if (lane == 0) st_xyzz(buckets + b, acc);
+    __syncwarp();
+  }
+}
+
 // persistent blocks over the queue of giant buckets: 256 threads stride over the pieces, tree in shared memory
 __global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucket_start, const u32* __restrict__ gs_ptr, u32 CL,
-                                                   const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets,
-                                                   const u32* __restrict__ big_count, const u32* __restrict__ big_list) {
+                                                   const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, const u32* __restrict__ queue) {
   __shared__ XYZZ sm[256];
-  u32 n = *big_count;
+  const u32* big_list = queue + 2;
+  u32 n = queue[0];
   const u32 gs = __ldg(gs_ptr);
   for (u32 q = blockIdx.x; q < n; q += gridDim.x) {
     u32 b = big_list[q];
@@ -563,20 +590,24 @@ __global__ void __launch_bounds__(128) k_combine(const XYZZ* __restrict__ winsum
 //   * no endomorphism split: a 256-bit scalar over W windows costs the same additions as two 128-bit halves over W/2, and the
 //     digit kernel loses its two 256x256-bit products per scalar, k_phi disappears.
 // Same sort / accumulate / fix-up / reduce kernels as the plain path: an entry's point index is w * stride + first + t.
-struct PreShape { int c, W; u32 H; };
-inline PreShape pre_shape(int c) { PreShape p; p.c = c; p.W = (257 + c - 1) / c; p.H = 1u << (c - 1); return p; }
-inline int pre_pick_window(size_t n) {     // multiplications: W(c) * n mixed additions (10) + 2 * 2^(c-1) bucket additions (14, ~3x for the latency-bound tails)
-  int best = 8; double bc = 1e300;
-  for (int c = 8; c <= 20; c++) {
-    const double W = (257 + c - 1) / c, cost = W * (double)n * 10.0 + 2.0 * (double)(1u << (c - 1)) * 14.0 * 3.0;
-    if (cost < bc) { bc = cost; best = c; }
-  }
-  return best;
+// The 257 bits a signed recoding of k < q needs are dealt out EVENLY over the W = ceil(257/c) windows (widths c or c-1): a top
+// window of only a few bits would put its whole share of the entries into a handful of buckets (hot atomics in the sort,
+// buckets cut into hundreds of chunks).
+#define BP_PRE_MAXW 33
+struct PreShape { int c, W; u32 H; unsigned short off[BP_PRE_MAXW + 1]; };   // window w covers scalar bits [off[w], off[w+1])
+inline PreShape pre_shape(int c) {
+  PreShape p; p.c = c; p.W = (257 + c - 1) / c; p.H = 1u << (c - 1);
+  const int base = 257 / p.W, extra = 257 % p.W;           // `extra` windows of base + 1 bits (the low ones), the rest base bits
+  int o = 0;
+  for (int w = 0; w <= BP_PRE_MAXW; w++) { p.off[w] = (unsigned short)o; if (w < p.W) o += base + (w < extra ? 1 : 0); }
+  return p;
+}
+inline int pre_pick_window(size_t n) {     // measured on B200 (profiles/r2_pre_window_sweep.txt): best window per vector length
+  return n < ((size_t)1 << 13) ? 13 : (n < ((size_t)1 << 15) ? 15 : (n < ((size_t)1 << 19) ? 17 : 18));
 }
 
-// One thread per point: out[w * n + i] = 2^(c*w) * P_i (canonical affine), one inversion per point (Montgomery's trick over the
+// One thread per point: out[w * n + i] = 2^off[w] * P_i (canonical affine), one inversion per point (Montgomery's trick over the
 // W Z coordinates), doublings in Jacobian coordinates (2M + 5S).
-#define BP_PRE_MAXW 33
 __global__ void __launch_bounds__(128) k_pre_build(const Affine* __restrict__ pts, u32 n, PreShape ps, Affine* __restrict__ out) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -592,7 +623,7 @@ __global__ void __launch_bounds__(128) k_pre_build(const Affine* __restrict__ pt
   Fp acc = fp_one();
   for (int w = 1; w < ps.W; w++) {
 #pragma unroll 1
-    for (int d = 0; d < ps.c; d++) {
+    for (int d = ps.off[w - 1]; d < ps.off[w]; d++) {
       const Fp A = fp_sqr(X), B = fp_sqr(Y), C = fp_sqr(B);
       const Fp D = fp_dbl(fp_sub(fp_sub(fp_sqr(fp_add(X, B)), A), C));
       const Fp E = fp_add(fp_dbl(A), A);
@@ -620,8 +651,7 @@ __global__ void __launch_bounds__(128) k_pre_build(const Affine* __restrict__ pt
   }
 }
 
-// One thread per term: k mod q -> W signed c-bit digits (the top window keeps its digit: W*c >= 257 leaves it below 2^(c-1)),
-// histogram over the single bucket unit.  digits is [W][T].
+// One thread per term: k mod q -> W signed digits of the windows of `ps`, histogram over the single bucket unit.  digits is [W][T].
 __global__ void __launch_bounds__(256) k_digits_pre(const Fq* __restrict__ scalars, u32 T, PreShape ps, int* __restrict__ digits,
                                                     u32* __restrict__ bucket_count) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -632,9 +662,12 @@ __global__ void __launch_bounds__(256) k_digits_pre(const Fq* __restrict__ scala
   k = fq_reduce(k);                                   // es = [ei % order]   pippenger.py:26
   u32 carry = 0;
   for (int w = 0; w < ps.W; w++) {
-    const u32 d = scalar_bits(k, w * ps.c, ps.c) + carry;
+    const int width = ps.off[w + 1] - ps.off[w];
+    const u32 half = 1u << (width - 1);
+    const u32 d = scalar_bits(k, ps.off[w], width) + carry;
     int sd;
-    if (w + 1 < ps.W && d > ps.H) { sd = (int)d - (int)(2u * ps.H); carry = 1; } else { sd = (int)d; carry = 0; }
+    // (the top window holds bit 256, which is clear: its digit stays <= half without recoding)
+    if (w + 1 < ps.W && d > half) { sd = (int)d - (int)(2u * half); carry = 1; } else { sd = (int)d; carry = 0; }
     digits[(size_t)w * T + t] = sd;
     if (sd != 0) atomicAdd(bucket_count + ((sd < 0 ? (u32)(-sd) : (u32)sd) - 1u), 1u);
   }
@@ -652,6 +685,106 @@ __global__ void __launch_bounds__(256) k_scatter_pre(const int* __restrict__ dig
     const u32 pos = atomicAdd(cursor + bkt, 1u);        // cursor[] starts at bucket_start[]: absolute slot
     entries[pos] = make_uint2(((u32)w * stride + first + t) | (sd < 0 ? 0x80000000u : 0u), bkt);
   }
+}
+
+// ---- reduction of ONE large bucket unit (H = R x C buckets, b = hi*C + lo) -----------------------------------------------------
+//   sum_b (b+1) B_b  =  sum_lo (lo+1) * Col_lo  +  C * sum_hi hi * Row_hi,     Col_lo = sum_hi B[hi][lo],  Row_hi = sum_lo B[hi][lo]
+// The 2H additions of the marginal sums are plain sums (trees of independent thread-level additions, throughput bound); only
+// the R + C marginals enter a weighted stage, each with a <= 10-bit weight (double-and-add per element, then a tree).  The
+// running-sum form of the plain path (k_reduce_seg / k_reduce_grp) carries a dependent chain through every level instead.
+// One launch reduces rows and columns by a factor K each (blockIdx.y = 0: rows, contiguous; 1: columns, strided):
+//   rows: out[i] = sum_{k<K} in[i*K + k]           (i < nrow_out)
+//   cols: out[g*C + lo] = sum_{k<K} in[(g*K + k)*C + lo]   (g < ncol_groups, lo < C)
+__global__ void __launch_bounds__(128) k_pre_marginals(const XYZZ* __restrict__ row_in, XYZZ* __restrict__ row_out, u32 nrow_out, u32 Krow,
+                                                       const XYZZ* __restrict__ col_in, XYZZ* __restrict__ col_out, u32 ncol_groups, u32 C, u32 Kcol) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.y == 0) {
+    if (i >= nrow_out || Krow == 0) return;
+    const XYZZ* src = row_in + (size_t)i * Krow;
+    XYZZ acc = ld_xyzz(src);
+#pragma unroll 1
+    for (u32 k = 1; k < Krow; k++) { XYZZ v = ld_xyzz(src + k); xyzz_add_ni(acc, v); }
+    st_xyzz(row_out + i, acc);
+  } else {
+    if (i >= ncol_groups * C || Kcol == 0) return;
+    const u32 gq = i / C, lo = i % C;
+    const XYZZ* src = col_in + (size_t)gq * Kcol * C + lo;
+    XYZZ acc = ld_xyzz(src);
+#pragma unroll 1
+    for (u32 k = 1; k < Kcol; k++) { XYZZ v = ld_xyzz(src + (size_t)k * C); xyzz_add_ni(acc, v); }
+    st_xyzz(col_out + i, acc);
+  }
+}
+// Second level + weights: one block of 64 threads = 16 quads per marginal (blocks 0 .. C-1: column lo, weight lo + 1; blocks
+// C .. C+R-1: row hi, weight hi).  4-lane cooperative operations throughout (coop4.cuh: ~2 us per addition against ~4-8 us for
+// a lone thread's out-of-line call): the quads add the marginal's np partial sums (np <= 128, a power of two), a shared-memory
+// tree joins them, the first quad multiplies by the <= 11-bit weight (double-and-add) and stores wsum[block].
+__global__ void __launch_bounds__(64) k_pre_rowcol(const XYZZ* __restrict__ rowpart, u32 np_r, const XYZZ* __restrict__ colpart, u32 np_c,
+                                                   u32 C, u32 R, XYZZ* __restrict__ wsum) {
+  __shared__ XYZZ sm[16];
+  const u32 bq = blockIdx.x, t = threadIdx.x, q = t >> 2;
+  const int lane = t & 31, role = lane & 3, base = lane & ~3;
+  const bool is_col = bq < C;
+  const u32 j = is_col ? bq : bq - C, np = is_col ? np_c : np_r;
+  XYZZ acc = xyzz_identity();
+  for (u32 e0 = 0; e0 < np; e0 += 16) {                  // uniform trip count; quads past the end add the identity
+    const u32 e = e0 + q;
+    XYZZ v = e < np ? ld_xyzz(is_col ? colpart + (size_t)e * C + j : rowpart + (size_t)j * np_r + e) : xyzz_identity();
+    acc = coop_add(acc, v, role, base);
+  }
+  if (role == 0) sm[q] = acc;
+  __syncthreads();
+  for (u32 off = 8; off > 0; off >>= 1) {
+    XYZZ v = q < off ? sm[q + off] : xyzz_identity();
+    acc = coop_add(acc, v, role, base);
+    __syncthreads();
+    if (q < off && role == 0) sm[q] = acc;
+    __syncthreads();
+  }
+  if (t >= 32) return;                                   // the first warp (quad 0 holds the sum; its other quads shadow it)
+  acc = sm[0];
+  const u32 wgt = is_col ? j + 1 : j;
+  XYZZ r = xyzz_identity();
+  for (int bit = 31 - __clz(wgt | 1u); bit >= 0; bit--) {
+    r = coop_dbl(r, role, base);
+    XYZZ s2 = coop_add(r, acc, role, base);
+    r = sel_xyzz((wgt >> bit) & 1u, s2, r);
+  }
+  if (t == 0) st_xyzz(wsum + bq, r);
+}
+// sums[side] = sum of wsum[side == 0 ? 0 .. C : C .. C+R): one block of 256 threads = 64 quads per side
+__global__ void __launch_bounds__(256) k_pre_total(const XYZZ* __restrict__ wsum, u32 C, u32 R, XYZZ* __restrict__ sums) {
+  __shared__ XYZZ sm[64];
+  const u32 side = blockIdx.x, t = threadIdx.x, q = t >> 2, n = side == 0 ? C : R;
+  const int lane = t & 31, role = lane & 3, base = lane & ~3;
+  const XYZZ* src = wsum + (side == 0 ? 0u : C);
+  XYZZ acc = xyzz_identity();
+  for (u32 e0 = 0; e0 < n; e0 += 64) {
+    const u32 e = e0 + q;
+    XYZZ v = e < n ? ld_xyzz(src + e) : xyzz_identity();
+    acc = coop_add(acc, v, role, base);
+  }
+  if (role == 0) sm[q] = acc;
+  __syncthreads();
+  for (u32 off = 32; off > 0; off >>= 1) {
+    XYZZ v = q < off ? sm[q + off] : xyzz_identity();
+    acc = coop_add(acc, v, role, base);
+    __syncthreads();
+    if (q < off && role == 0) sm[q] = acc;
+    __syncthreads();
+  }
+  if (t == 0) st_xyzz(sums + side, acc);
+}
+// result = sums[0] + 2^lgC * sums[1]  (sums[0] = weighted columns, sums[1] = weighted rows); one quad
+__global__ void __launch_bounds__(32) k_pre_finish(const XYZZ* __restrict__ sums, int lgC, Affine* __restrict__ out, XYZZ* __restrict__ out_xyzz) {
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  XYZZ acc = ld_xyzz(sums + 1);
+  for (int d = 0; d < lgC; d++) acc = coop_dbl(acc, role, base);
+  XYZZ v = ld_xyzz(sums);
+  acc = coop_add(acc, v, role, base);
+  if (threadIdx.x != 0) return;
+  if (out_xyzz) st_xyzz(out_xyzz, acc);
+  if (out) st_affine(out, xyzz_to_affine(acc, true));
 }
 
 }  // namespace bp

@@ -36,6 +36,13 @@ class DevicePoints(_Handle):
         super().__init__(raw, len(raw) // 64)
 
 
+    def precompute(self, window_bits=0):
+        """Store the window multiples 2^(c*w) * P_i next to the vector (bp_points_precompute): later multiexps over this handle
+        run without doublings.  Worth it for vectors that are used again and again (generators)."""
+        nat.check(nat.load().bp_points_precompute(self.handle, window_bits))
+        return self
+
+
 class DeviceScalars(_Handle):
     _upload = "bp_scalars_upload"
 

@@ -209,3 +209,73 @@ def test_device_resident_handles_and_pipelined_path():
         lib.bp_msm_set_window(0)
         lib.bp_msm_set_pipeline_min(0)
     dp.free(); ds.free()
+
+
+@pytest.mark.parametrize("c", [0, 8, 11, 16, 19, 20])
+def test_msm_precomputed_window_multiples(c):
+    """bp_points_precompute: the MSM over a handle that carries 2^(c*w) * P_i (one shared bucket unit, no doublings) returns
+    the same canonical point as the plain path and the oracle -- full vector, slices, adversarial scalars, identity points."""
+    from python_bulletproofs_b200.device import DevicePoints, DeviceScalars
+    n = 3000
+    pts = fast_points(n, 4242)
+    pts[7] = None                                        # an identity among the points
+    pts[100] = pts[101]                                  # a repeated point
+    pts[200] = ecc.point_neg(pts[201])                   # P and -P
+    rng = random.Random(c)
+    lib = nat.load()
+    dp = DevicePoints(raw=ecc.pack_points(pts)).precompute(c)
+    wb, nw, nbytes = ctypes.c_int(), ctypes.c_int(), ctypes.c_uint64()
+    nat.check(lib.bp_points_pre_info(dp.handle, ctypes.byref(wb), ctypes.byref(nw), ctypes.byref(nbytes)))
+    assert wb.value == (c or wb.value) and nw.value == (257 + wb.value - 1) // wb.value and nbytes.value == nw.value * n * 64
+    out = ctypes.create_string_buffer(64)
+    scalar_sets = {
+        "uniform": [rng.getrandbits(256) for _ in range(n)],                      # unreduced: reduced on the device
+        "edge": [[0, 1, Q - 1, Q, Q + 1, 2 ** 256 - 1, 2 ** 255, (Q - 1) // 2, (Q + 1) // 2, 2 ** 128][i % 10] for i in range(n)],
+        "same": [rng.getrandbits(256) % Q] * n,
+        "top_window": [(Q - 1) - rng.randrange(0, 1 << 20) for _ in range(n)],
+        "pow2": [1 << rng.randrange(0, 256) for _ in range(n)],
+    }
+    for name, ks in scalar_sets.items():
+        sb = b"".join(int(k % 2 ** 256).to_bytes(32, "little") for k in ks)
+        want = ecc.msm(pts, [k % Q for k in ks])
+        nat.check(lib.bp_msm_h(dp.handle, sb, n, out))
+        assert ecc.unpack_point(out.raw) == want, name
+        assert lib.bp_msm_last_window() == wb.value
+        ds = DeviceScalars(raw=sb)
+        nat.check(lib.bp_msm_hh(dp.handle, ds.handle, n, out))
+        assert ecc.unpack_point(out.raw) == want, name
+        # a slice in the middle of the vector (XYZZ partial) and a prefix
+        part = ctypes.create_string_buffer(128)
+        nat.check(lib.bp_msm_hh_partial(dp.handle, ds.handle, 500, 1234, part))
+        nat.check(lib.bp_xyzz_sum(part.raw, 1, out))
+        assert ecc.unpack_point(out.raw) == ecc.msm(pts[500:1734], [k % Q for k in ks[500:1734]]), name
+        nat.check(lib.bp_msm_hh(dp.handle, ds.handle, 33, out))
+        assert ecc.unpack_point(out.raw) == ecc.msm(pts[:33], [k % Q for k in ks[:33]]), name
+        ds.free()
+    # a forced window switches back to the plain bucket method on the same handle
+    try:
+        nat.check(lib.bp_msm_set_window(13))
+        sb = b"".join(int(k).to_bytes(32, "little") for k in scalar_sets["uniform"])
+        nat.check(lib.bp_msm_h(dp.handle, sb, n, out))
+        assert ecc.unpack_point(out.raw) == ecc.msm(pts, [k % Q for k in scalar_sets["uniform"]])
+    finally:
+        lib.bp_msm_set_window(0)
+    dp.free()
+
+
+def test_msm_precomputed_2p18_vs_plain_and_oracle():
+    n = 1 << 18
+    from python_bulletproofs_b200.device import DevicePoints, DeviceScalars
+    lib = nat.load()
+    rng = random.Random(18)
+    base = nat.scalar_mul_batch_bytes(nat.pack_xy(*ecc.G) * n, rng.randbytes(32 * n), n)
+    sb = rng.randbytes(32 * n)
+    dp, ds = DevicePoints(raw=base), DeviceScalars(raw=sb)
+    out = ctypes.create_string_buffer(64)
+    nat.check(lib.bp_msm_hh(dp.handle, ds.handle, n, out))
+    plain = out.raw
+    dp.precompute(0)
+    nat.check(lib.bp_msm_hh(dp.handle, ds.handle, n, out))
+    assert out.raw == plain
+    assert ecc.pack_point(ecc.msm_bytes(base, sb, n, "bucket", ecc.max_threads())) == plain
+    dp.free(); ds.free()

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--lgn", default="16,18,20")
     ap.add_argument("--c", default="0")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--pre", default="", help="comma list of window widths for bp_points_precompute (0 = automatic); timed after the plain runs")
     args = ap.parse_args()
     lib = nat.load()
     nat.init(0)
@@ -58,6 +59,24 @@ def main():
                 lgn, lib.bp_msm_last_window(), best, sorted(times)[len(times) // 2], n / best / 1e3)
                 + " ".join("%s=%.3f" % (nm, v) for nm, v in zip(names, stage)), flush=True)
     lib.bp_msm_set_window(0)
+    lib.bp_msm_set_pre_chunk(int(os.environ.get("BP_PRE_CHUNK", "0")))
+    for pc in [int(x) for x in args.pre.split(",") if x != ""]:
+        for lgn in [int(x) for x in args.lgn.split(",")]:
+            n = 1 << lgn
+            hq = ctypes.c_uint64()
+            nat.check(lib.bp_points_upload(pts, n, ctypes.byref(hq)))
+            nat.check(lib.bp_points_precompute(hq, pc))
+            times = (ctypes.c_float * args.iters)()
+            nat.check(lib.bp_bench_msm(hq, hs, n, 2, args.iters, 1, times, out))
+            best = min(times)
+            lib.bp_msm_set_profiling(1)
+            nat.check(lib.bp_msm_hh(hq, hs, n, out))
+            nat.check(lib.bp_msm_stage_ms(stage))
+            lib.bp_msm_set_profiling(0)
+            print("PRE n=2^%d c=%d: best %.3f ms median %.3f ms -> %.1f Mpts/s | " % (
+                lgn, lib.bp_msm_last_window(), best, sorted(times)[len(times) // 2], n / best / 1e3)
+                + " ".join("%s=%.3f" % (nm, v) for nm, v in zip(names, stage)), flush=True)
+            lib.bp_handle_free(hq)
 
 
 if __name__ == "__main__":
