@@ -325,7 +325,7 @@ def run_ours(args):
                                "slice MSM + ncclAllGather of the 128-byte partials + sum, max over ranks", "points": strong}}
 
     if rank == 0 and world == 1:
-        line["sweep"] = msm_sweep(lib, nat, hp, hs, args.lgn)
+        line["sweep"] = msm_sweep(lib, nat, pts, hs, args.lgn, not args.no_precompute)
         line["cpu_baseline"], bit_exact = cpu_baseline(pts, sc, n, result_hex)
         line["bit_exact_vs_oracle"] = bit_exact
     if sharded_ok is not None:
@@ -353,16 +353,30 @@ def measured_hbm():
         return 6650.0
 
 
-def msm_sweep(lib, nat, hp, hs, lgmax):
-    """BASELINE config 3: the resident MSM at 2^10 ... 2^lgmax terms (prefixes of the same resident vectors), L2 flushed
-    between iterations, median of 5 after 2 warm-up calls."""
+def msm_sweep(lib, nat, pts, hs, lgmax, precompute):
+    """BASELINE config 3: the resident MSM at 2^10 ... 2^lgmax terms (prefixes of the same point / scalar vectors), L2 flushed
+    between iterations, median of 5 after 2 warm-up calls; per size the plain bucket method and, with `precompute`, the same
+    vector carrying its window multiples."""
     out = ctypes.create_string_buffer(64)
     rows = {}
     for lg in range(10, lgmax + 1):
+        m = 1 << lg
+        h = ctypes.c_uint64()
+        nat.check(lib.bp_points_upload(pts, m, ctypes.byref(h)))
         ts = (ctypes.c_float * 5)()
-        nat.check(lib.bp_bench_msm(hp, hs, 1 << lg, 2, 5, 1, ts, out))
+        nat.check(lib.bp_bench_msm(h, hs, m, 2, 5, 1, ts, out))
         ms = statistics.median(ts)
-        rows[str(lg)] = {"ms": round(ms, 4), "mpts_per_s": round((1 << lg) / ms / 1e3, 2), "window_bits": lib.bp_msm_last_window()}
+        row = {"ms_plain": round(ms, 4), "mpts_per_s_plain": round(m / ms / 1e3, 2), "window_bits_plain": lib.bp_msm_last_window()}
+        if precompute:
+            plain_hex = out.raw.hex()
+            nat.check(lib.bp_points_precompute(h, 0))
+            nat.check(lib.bp_bench_msm(h, hs, m, 2, 5, 1, ts, out))
+            ms = statistics.median(ts)
+            row.update({"ms": round(ms, 4), "mpts_per_s": round(m / ms / 1e3, 2), "window_bits": lib.bp_msm_last_window(), "same_result": out.raw.hex() == plain_hex})
+        else:
+            row.update({"ms": row["ms_plain"], "mpts_per_s": row["mpts_per_s_plain"], "window_bits": row["window_bits_plain"]})
+        rows[str(lg)] = row
+        lib.bp_handle_free(h)
     return rows
 
 

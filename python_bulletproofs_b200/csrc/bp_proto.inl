@@ -429,6 +429,12 @@ static void rp_chunk_plan(size_t nproofs, bool tables, std::vector<size_t>& lens
   }
   if (!tables) { const size_t ch = nproofs < 4096 ? nproofs : 2048; for (size_t lo = 0; lo < nproofs; lo += ch) lens.push_back(nproofs - lo < ch ? nproofs - lo : ch); return; }
   if (nproofs < 512) { lens.push_back(nproofs); return; }
+  if (nproofs <= 2048) {   // latency regime (measured: every chunk costs ~0.7 ms of dependent kernels): two chunks, so that the
+                           // host checks of the second run under the first one's device work
+    const size_t a = (nproofs / 4 + 63) & ~(size_t)63;
+    lens.push_back(a); lens.push_back(nproofs - a);
+    return;
+  }
   size_t left = nproofs, next = nproofs / 8 < 256 ? 256 : (nproofs / 8 > 1024 ? 1024 : nproofs / 8);
   while (left) {
     size_t len = next < left ? next : left;
@@ -692,11 +698,11 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
       ++g.nlaunch, k_sv_table<<<(unsigned)((cn * lay.npt + 127) / 128), 128, 0, g.aux_stream>>>(cpts, lay, (u32)cn, vsc, sv_T, kd, kfl, d_bad, d_var + 2 * cn);
       BP_CUDA(cudaEventRecord(g.aux_ready[cur], g.aux_stream));
       BP_CUDA(cudaStreamWaitEvent(g.stream, g.aux_ready[cur], 0));
-      BP_CUDA(cudaStreamWaitEvent(g.var_stream, g.aux_ready[cur], 0));
-      ++g.nlaunch, k_sv_main<<<(unsigned)((cn * 32 + 127) / 128), 128, 0, g.var_stream>>>(cpts, lay, (u32)cn, sv_T, kd, kfl, sv_A);
-      ++g.nlaunch, k_sv_comb1<<<(unsigned)((cn * 12 + 127) / 128), 128, 0, g.var_stream>>>(sv_A, (u32)(cn * 12), sv_G);
-      ++g.nlaunch, k_sv_comb2<<<(unsigned)((cn * 3 + 127) / 128), 128, 0, g.var_stream>>>(sv_G, cpts, lay, (u32)cn, d_var);
-      BP_CUDA(cudaEventRecord(g.var_done[cur], g.var_stream));
+      BP_CUDA(cudaStreamWaitEvent(g.var_stream[cur], g.aux_ready[cur], 0));
+      ++g.nlaunch, k_sv_main<<<(unsigned)((cn * 32 + 127) / 128), 128, 0, g.var_stream[cur]>>>(cpts, lay, (u32)cn, sv_T, kd, kfl, sv_A);
+      ++g.nlaunch, k_sv_comb1<<<(unsigned)((cn * 12 + 127) / 128), 128, 0, g.var_stream[cur]>>>(sv_A, (u32)(cn * 12), sv_G);
+      ++g.nlaunch, k_sv_comb2<<<(unsigned)((cn * 3 + 127) / 128), 128, 0, g.var_stream[cur]>>>(sv_G, cpts, lay, (u32)cn, d_var);
+      BP_CUDA(cudaEventRecord(g.var_done[cur], g.var_stream[cur]));
       if (fbtab16) ++g.nlaunch, k_rp_lookup16<<<(unsigned)cn, 128, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
       else ++g.nlaunch, k_rp_lookup<<<(unsigned)cn, 128, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
       XYZZ* d_grp = d_lanes + (size_t)4 * CH * BP_RP_SLOTS;
@@ -989,6 +995,7 @@ __global__ void k_test_fq(int op, const Fq* a, const Fq* b, u32 n, Fq* out) {
     case 5: r = fq_mul_dev(x, y); break;              // standard-form product of fqdev.cuh (pseudo-Mersenne folds)
     case 6: r = fq_inv_dev(x); break;
     case 7: r = fq_sqr_dev(x); break;
+    case 8: r = fq_inv_gcd(x); break;
     default: r = x;
   }
   st_fq(out + i, r);
@@ -1023,7 +1030,7 @@ int bp_test_fq(int op, int on_device, const uint8_t* a32, const uint8_t* b32, si
   for (size_t i = 0; i < n; i++) {   // same fq.cuh code on the host
     Fq x, y, r; fq_from_le(&x, a32 + 32 * i); fq_from_le(&y, b32 + 32 * i); x = fq_reduce(x); y = fq_reduce(y);
     switch (op) { case 0: r = fq_mul(x, y); break; case 1: r = fq_add(x, y); break; case 2: r = fq_sub(x, y); break;
-                  case 3: case 6: r = fq_inv(x); break; case 4: r = fq_neg(x); break; case 5: r = fq_mul(x, y); break;
+                  case 3: case 6: case 8: r = fq_inv(x); break; case 4: r = fq_neg(x); break; case 5: r = fq_mul(x, y); break;
                   case 7: r = fq_mul(x, x); break; default: r = x; }
     fq_to_le(out32 + 32 * i, r);
   }

@@ -59,13 +59,15 @@ struct Ctx {
   DevBuf ws_g, ws_h, ws_a, ws_b, ws_g2, ws_h2, ws_a2, ws_b2, ws_idx, ws_lr, ws_terms_sc, ws_small;
   DevBuf ws_sv_tab, ws_sv_acc, ws_sv_sc, ws_rp_sums;      // batch verifier: variable-point tables / window sums / split scalars; Gsum, Hsum
   std::vector<unsigned char> rp_sums_src; unsigned long long rp_sums_gen = 0;   // generator bytes the kept sums belong to
-  cudaStream_t var_stream = nullptr;                      // batch verifier: proof-specific terms, concurrent with the table lookups
+  cudaStream_t var_stream[2] = {nullptr, nullptr};        // batch verifier: proof-specific terms, concurrent with the table lookups (one per chunk parity,
+                                                          // so that the doubling chains of consecutive chunks overlap)
   cudaEvent_t var_done[2] = {nullptr, nullptr}, ev_rp0 = nullptr, ev_rp1 = nullptr;
   int ensure_var_stream() {
-    if (!var_stream) {
+    for (int i = 0; i < 2; i++) {
+      if (var_stream[i]) continue;
       int lo = 0, hi = 0;
       cudaDeviceGetStreamPriorityRange(&lo, &hi);
-      if (cudaStreamCreateWithPriority(&var_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return fail("stream creation failed");
+      if (cudaStreamCreateWithPriority(&var_stream[i], cudaStreamNonBlocking, hi) != cudaSuccess) return fail("stream creation failed");
     }
     for (int i = 0; i < 2; i++)
       if (!var_done[i] && cudaEventCreateWithFlags(&var_done[i], cudaEventDisableTiming) != cudaSuccess) return fail("event creation failed");

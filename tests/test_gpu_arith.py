@@ -90,6 +90,9 @@ def test_fq_device_standard_form_arithmetic():
     inv_in = [1, 2, Q - 1, Q - 2, 2 ** 128] + [rng.getrandbits(256) % Q or 1 for _ in range(200)]
     got = _un(call_test("bp_test_fq", 6, _le(inv_in), _le(inv_in), len(inv_in), 32, 1))
     assert got == [pow(x, -1, Q) for x in inv_in]
+    inv_in = [0] + inv_in + [1 << k for k in range(0, 256, 5)]                  # binary extended GCD form (0 -> 0)
+    got = _un(call_test("bp_test_fq", 8, _le(inv_in), _le(inv_in), len(inv_in), 32, 1))
+    assert got == [pow(x % Q, -1, Q) if x % Q else 0 for x in inv_in]
 
 
 def test_ec_ops_including_exceptional_cases():
