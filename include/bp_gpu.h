@@ -146,9 +146,14 @@ int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64],
                  size_t n, const uint8_t* transcript, size_t transcript_len, uint8_t* Ls64, uint8_t* Rs64, uint8_t* xs32,
                  uint8_t a_out32[32], uint8_t b_out32[32], uint8_t* transcript_out, size_t tout_cap, size_t* tout_len);
 
-/* From the second round on, each round's device work (fold with the previous challenge, L/R term construction, batched
- * MSM, copy-out of L and R) is one CUDA-graph launch; bp_ipa_set_graphs(0) switches to plain stream launches. */
-int bp_ipa_set_graphs(int on);
+/* How the host's Fiat-Shamir step (one SHA-256 per round, inner_product_prover.py:102-106) meets the device work of a proof:
+ *   1 (default)  the whole proof is enqueued once; the stream waits on a mapped host word for every challenge and signals
+ *                every L, R pair through another one (stream wait-value / write-value operations) while the calling thread
+ *                polls: no stream synchronisation, launch or callback thread between two rounds;
+ *   2            the same sequence with the host side as host nodes (cudaLaunchHostFunc), captured into ONE CUDA graph per
+ *                vector length and replayed: one launch per proof;
+ *   0            plain stream launches, one cudaStreamSynchronize per round. */
+int bp_ipa_set_graphs(int mode);
 
 /* Same, with the h generators given as (h, hscale): the effective generators are hscale_i * h_i, which are never
  * materialised (hscale32 = NULL means all ones).  The range-proof prover passes hs with hscale_i = y^-i instead of the

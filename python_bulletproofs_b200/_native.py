@@ -106,6 +106,10 @@ def load():
             raise BpGpuError(
                 "libbpgpu.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `make -C python_bulletproofs_b200/csrc`; there is no CPU fallback" % LIB_PATH)
+        # The batch verifier's host checks run on an OpenMP worker pool.  libgomp's idle workers spin by default; with one
+        # process per GPU sharing the host (torchrun) the spinning pools of eight ranks starve each other's main threads and the
+        # batch time jitters by milliseconds.  libgomp reads this at load time, so it has to be in the environment before dlopen.
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)

@@ -1,4 +1,6 @@
 #include <chrono>
+#include <atomic>
+#include <cuda.h>
 // bp_proto.inl -- host drivers of the protocol-level entry points (included by bp_gpu.cu):
 // IPA folding rounds with the Fiat-Shamir transcript on the host, the Verifier2 equation,
 // batch range-proof verification, and the NCCL plumbing for sharded MSM / batches.
@@ -9,6 +11,11 @@ static ncclComm_t g_comm = nullptr;
 static int g_rank = 0, g_nranks = 1;
 void nccl_shutdown() { if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; } g_rank = 0; g_nranks = 1; }
 
+#define BP_CU(call)                                                                           \
+  do {                                                                                        \
+    CUresult r__ = (call);                                                                    \
+    if (r__ != CUDA_SUCCESS) return ::bp::fail("%s failed: CUresult %d", #call, (int)r__);    \
+  } while (0)
 #define BP_NCCL(call)                                                                         \
   do {                                                                                        \
     ncclResult_t r__ = (call);                                                                \
@@ -16,6 +23,30 @@ void nccl_shutdown() { if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; 
   } while (0)
 
 struct ChallengeForms { Fq x, xinv, xm, xim; };
+static ChallengeForms challenge_forms(const Fq& x);
+// context of the IPA prover's host nodes (see bp_ipa_prove_hs)
+struct IpaHostCtx {
+  std::string digest; RunningModHash rh; size_t round = 0, n = 0;
+  IpaRound* h_rp = nullptr; uint8_t* h_lr = nullptr;
+  std::vector<uint8_t> Ls, Rs, xs;
+};
+static IpaHostCtx g_ipa_host;
+// transcript.add_list_points([L, R]); x = get_modp(q); add_number(x)      inner_product_prover.py:102-106
+static void CUDART_CB ipa_host_round(void* p) {
+  IpaHostCtx& c = *(IpaHostCtx*)p;
+  const size_t r = c.round;
+  memcpy(c.Ls.data() + 64 * r, c.h_lr, 64);
+  memcpy(c.Rs.data() + 64 * r, c.h_lr + 64, 64);
+  c.digest += point_to_b64(c.h_lr); c.digest += '&';
+  c.digest += point_to_b64(c.h_lr + 64); c.digest += '&';
+  Fq x = c.rh.challenge((const uint8_t*)c.digest.data(), c.digest.size());
+  fq_to_le(c.xs.data() + 32 * r, x);
+  c.digest += fq_to_decimal(x); c.digest += '&';
+  ChallengeForms f = challenge_forms(x);
+  c.h_rp->fold = 1; c.h_rp->xm = f.xm; c.h_rp->xim = f.xim;      // applied at the start of the next round / the last fold
+  c.h_rp->m = (u32)(c.n >> (r + 1));
+  c.round = r + 1;
+}
 static ChallengeForms challenge_forms(const Fq& x) {
   ChallengeForms c; c.x = x; c.xinv = fq_inv_host(x); c.xm = fq_to_mont(x); c.xim = fq_to_mont(c.xinv);
   return c;
@@ -33,7 +64,11 @@ static int fold_step(const Affine* P, Affine* P2, const Fq* a, const Fq* b, Fq* 
 
 extern "C" {
 
-int bp_ipa_set_graphs(int on) { g.use_graphs = on != 0; return 0; }
+int bp_ipa_set_graphs(int mode) {
+  if (mode < 0 || mode > 2) return fail("bp_ipa_set_graphs: 0 = synchronise per round, 1 = mapped-flag handshake (default), 2 = one CUDA graph with host nodes");
+  g.ipa_mode = mode;
+  return 0;
+}
 
 int bp_sha256(const uint8_t* msg, size_t len, uint8_t out32[32]) {
   Sha256 s; s.update(msg, len); s.final(out32);
@@ -187,7 +222,6 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
                     size_t* tout_len) {
   BP_NEED_INIT();
   if (n == 0 || (n & (n - 1))) return fail("bp_ipa_prove: n must be a power of two");   // inner_product_prover.py:52
-  std::string digest((const char*)transcript, transcript_len);
   // ping-pong buffers
   Affine* PA = (Affine*)g.ws_g.ensure((2 * n + 1) * sizeof(Affine));
   Affine* PB = (Affine*)g.ws_g2.ensure((n + 1) * sizeof(Affine));
@@ -228,67 +262,116 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
     const FbSrc src = {{u64_, g64, h64}, {64, n * 64, n * 64}, 3};
     tab = fb_get(src.hash(0x69706131ull), src, PA, 2 * n + 1);
   }
-  size_t round = 0;
-  RunningModHash rh;
   const u32 n1 = (u32)n + 1;
   u32 h_off[3] = {0, n1, 2 * n1};
   if (n > 1) BP_CUDA(cudaMemcpyAsync(d_off, h_off, sizeof h_off, cudaMemcpyHostToDevice, g.stream));
-  // One round on the stream: parameters up, fold with the previous challenge, L/R terms, batched MSM, L and R down.
-  auto enqueue_round = [&]() -> int {
-    BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
-    ++g.nlaunch, k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
-    ++g.nlaunch, k_build_lr_sv<<<1, 256, 0, g.stream>>>(a, b, cg, ch, (u32)n, &d_rp->m, tsc, tidx);
-    if (tab ? fb_msm_run(tab, tidx, tsc, d_off, 2, n1, 0, d_lr, nullptr) : msm_run(PA, tidx, tsc, 2 * n1, d_off, 2, n1, d_lr, nullptr)) return 1;
-    BP_CUDA(cudaMemcpyAsync(h_lr, d_lr, 128, cudaMemcpyDeviceToHost, g.stream));
+  u32 L = 0; while (((size_t)1 << L) < n) L++;
+  // Host side of a round (Fiat-Shamir, inner_product_prover.py:102-106): runs as a HOST NODE of the stream / graph
+  // (cudaLaunchHostFunc), between the copy-out of L, R and the copy-in of the next round's parameters -- the stream is never
+  // synchronised inside the proof.  The context lives in one static object (the library is single threaded by contract).
+  IpaHostCtx& hc = g_ipa_host;
+  hc.digest.assign((const char*)transcript, transcript_len);
+  hc.rh = RunningModHash();
+  hc.round = 0; hc.n = n; hc.h_rp = h_rp; hc.h_lr = h_lr;
+  hc.Ls.assign(64 * (size_t)(L ? L : 1), 0); hc.Rs.assign(64 * (size_t)(L ? L : 1), 0); hc.xs.assign(32 * (size_t)(L ? L : 1), 0);
+  uint8_t* h_ab = pin + 384;                        // pinned landing zone of the final a, b
+  volatile u32* f_g2c = (volatile u32*)(pin + 448);  // device -> host: rounds whose L, R have landed
+  volatile u32* f_c2g = (volatile u32*)(pin + 452);  // host -> device: rounds whose challenge is in h_rp
+  // Three ways to run the same sequence (bp_ipa_set_graphs): per round [parameters up | fold with the previous challenge |
+  // L/R terms | batched MSM | L, R down | Fiat-Shamir on the host], then the last fold and a, b down.
+  //   1 (default) the whole proof is enqueued ONCE; the stream itself waits on a mapped host word for each challenge
+  //     (cuStreamWaitValue32) and signals each L, R pair through another (cuStreamWriteValue32) while this thread polls:
+  //     no stream synchronisation, no launch and no callback thread between two rounds;
+  //   2 the sequence with the host side as HOST NODES (cudaLaunchHostFunc), captured into ONE CUDA graph per (n, table)
+  //     and replayed: one launch per proof (the callback thread's wake-up costs more than the handshake of mode 1);
+  //   0 stream launches with one cudaStreamSynchronize per round (the baseline the other two are measured against).
+  int mode = g.ipa_mode;
+  if (mode == 1 && !g.memops_ready()) mode = 2;
+  auto enqueue_proof = [&](int md) -> int {
+    u32 r = 0;
+    for (size_t m = n; m > 1; m >>= 1, r++) {
+      if (md == 1 && r > 0) BP_CU(g.cuWaitValue32(g.stream, (CUdeviceptr)(uintptr_t)f_c2g, r, CU_STREAM_WAIT_VALUE_GEQ));
+      BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
+      ++g.nlaunch, k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
+      ++g.nlaunch, k_build_lr_sv<<<1, 256, 0, g.stream>>>(a, b, cg, ch, (u32)n, &d_rp->m, tsc, tidx);
+      if (tab ? fb_msm_run(tab, tidx, tsc, d_off, 2, n1, 0, d_lr, nullptr) : msm_run(PA, tidx, tsc, 2 * n1, d_off, 2, n1, d_lr, nullptr)) return 1;
+      BP_CUDA(cudaMemcpyAsync(h_lr, d_lr, 128, cudaMemcpyDeviceToHost, g.stream));
+      if (md == 2) BP_CUDA(cudaLaunchHostFunc(g.stream, ipa_host_round, &hc));
+      else if (md == 1) BP_CU(g.cuWriteValue32(g.stream, (CUdeviceptr)(uintptr_t)f_g2c, r + 1, 0));
+      else { BP_CUDA(cudaStreamSynchronize(g.stream)); ipa_host_round(&hc); }
+    }
+    if (n > 1) {   // last fold: a, b of length 1   (inner_product_prover.py:109-110)
+      if (md == 1) BP_CU(g.cuWaitValue32(g.stream, (CUdeviceptr)(uintptr_t)f_c2g, r, CU_STREAM_WAIT_VALUE_GEQ));
+      BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
+      ++g.nlaunch, k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
+    }
+    BP_CUDA(cudaMemcpyAsync(h_ab, a, 32, cudaMemcpyDeviceToHost, g.stream));
+    BP_CUDA(cudaMemcpyAsync(h_ab + 32, b, 32, cudaMemcpyDeviceToHost, g.stream));
     return 0;
   };
   memset(h_rp, 0, sizeof(IpaRound));
-  cudaGraphExec_t gexec = nullptr;
-  for (size_t m = n; m > 1; m >>= 1, round++) {
-    h_rp->m = (u32)m;
-    // Round 0 runs eagerly (it also sizes every workspace); from round 1 on the same device work is ONE graph launch.
-    // The graph is captured once per n and reused across proofs while the workspaces keep their addresses.
-    if (round == 0 || !g.use_graphs) {
-      if (enqueue_round()) return 1;
-    } else {
-      if (!gexec) gexec = g.ipa_graph_lookup(n, tab);
-      if (!gexec) {
-        cudaGraph_t graph = nullptr;
-        const unsigned long long l0 = g.nlaunch;
-        BP_CUDA(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed));
-        int rc = enqueue_round();
-        const unsigned nk = (unsigned)(g.nlaunch - l0);
-        g.nlaunch = l0;                                  // captured, not launched: counted at every cudaGraphLaunch below
-        cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
-        if (rc || ce != cudaSuccess || !graph) { cudaGetLastError(); return fail("CUDA graph capture of the IPA round failed"); }
+  h_rp->m = (u32)n;
+  *f_g2c = 0; *f_c2g = 0;
+  bool done = false;
+  if (mode == 2 && n > 1 && g.ipa_sized_ok(n, tab)) {
+    // The first proof of a vector length runs eagerly (it sizes every workspace); from the second one on the same sequence
+    // is ONE CUDA-graph launch, captured once per (n, table) and valid while no workspace has moved.
+    cudaGraphExec_t gexec = g.ipa_graph_lookup(n, tab);
+    if (!gexec) {
+      cudaGraph_t graph = nullptr;
+      const unsigned long long l0 = g.nlaunch, gen0 = alloc_generation();
+      BP_CUDA(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed));
+      int rc = enqueue_proof(2);
+      cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+      const unsigned nk = (unsigned)(g.nlaunch - l0);
+      g.nlaunch = l0;                                  // captured, not launched: counted at every cudaGraphLaunch below
+      if (rc || ce != cudaSuccess || !graph || gen0 != alloc_generation()) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);            // (a workspace grew during the capture: run this proof eagerly, retry next time)
+      } else {
         ce = cudaGraphInstantiate(&gexec, graph, 0);
         cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) { cudaGetLastError(); return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
-        g.ipa_graph_store(n, tab, gexec, nk);
+        if (ce != cudaSuccess) { cudaGetLastError(); gexec = nullptr; }
+        else g.ipa_graph_store(n, tab, gexec, nk);
       }
+    }
+    if (gexec) {
       BP_CUDA(cudaGraphLaunch(gexec, g.stream));
       g.nlaunch += g.ipa_graph_kernels(n, tab);
+      done = true;
     }
-    BP_CUDA(cudaStreamSynchronize(g.stream));
-    memcpy(Ls64 + 64 * round, h_lr, 64);
-    memcpy(Rs64 + 64 * round, h_lr + 64, 64);
-    // transcript.add_list_points([L, R]); x = get_modp(q); add_number(x)      inner_product_prover.py:102-106
-    digest += point_to_b64(h_lr); digest += '&';
-    digest += point_to_b64(h_lr + 64); digest += '&';
-    Fq x = rh.challenge((const uint8_t*)digest.data(), digest.size());
-    fq_to_le(xs32 + 32 * round, x);
-    digest += fq_to_decimal(x); digest += '&';
-    ChallengeForms c = challenge_forms(x);
-    h_rp->fold = 1; h_rp->xm = c.xm; h_rp->xim = c.xim;      // applied at the start of the next round (or below)
   }
-  if (n > 1) {   // last fold: a, b of length 1   (inner_product_prover.py:109-110)
-    h_rp->m = 1;
-    BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
-    ++g.nlaunch, k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
+  if (!done && mode == 1 && n > 1) {
+    if (enqueue_proof(1)) { *f_c2g = 0x7FFFFFFFu; cudaStreamSynchronize(g.stream); return 1; }
+    // this thread's side of the handshake: wait for L, R of round r, hash, publish the challenge
+    const auto t_start = std::chrono::steady_clock::now();
+    for (u32 r = 0; r < L; r++) {
+      unsigned spins = 0;
+      while (*f_g2c < r + 1) {
+        if ((++spins & 0x3FFFu) == 0) {
+          if (cudaStreamQuery(g.stream) != cudaErrorNotReady ||
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 10.0) {
+            *f_c2g = 0x7FFFFFFFu;                      // release every pending wait so that the stream drains
+            cudaError_t e = cudaStreamSynchronize(g.stream);
+            return fail("bp_ipa_prove: device side of round %u did not complete (%s)", r, cudaGetErrorString(e));
+          }
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      ipa_host_round(&hc);
+      std::atomic_thread_fence(std::memory_order_release);
+      *f_c2g = r + 1;
+    }
+    done = true;
   }
-  BP_CUDA(cudaMemcpyAsync(a_out32, a, 32, cudaMemcpyDeviceToHost, g.stream));
-  BP_CUDA(cudaMemcpyAsync(b_out32, b, 32, cudaMemcpyDeviceToHost, g.stream));
+  if (!done) {
+    if (enqueue_proof(mode == 1 ? 0 : mode)) return 1;
+    g.ipa_mark_sized(n, tab);
+  }
   BP_CUDA(cudaStreamSynchronize(g.stream));
+  if (L) { memcpy(Ls64, hc.Ls.data(), 64 * (size_t)L); memcpy(Rs64, hc.Rs.data(), 64 * (size_t)L); memcpy(xs32, hc.xs.data(), 32 * (size_t)L); }
+  memcpy(a_out32, h_ab, 32); memcpy(b_out32, h_ab + 32, 32);
+  const std::string& digest = hc.digest;
   if (tout_len) *tout_len = digest.size();
   if (digest.size() > tout_cap) return fail("bp_ipa_prove: transcript buffer too small (%zu needed)", digest.size());
   memcpy(transcript_out, digest.data(), digest.size());
@@ -484,6 +567,7 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
   if (nthreads == 0) nthreads = 1;
   if (const char* lws = getenv("LOCAL_WORLD_SIZE")) {      // one process per GPU on a shared host (torchrun): share the cores
     long w = atol(lws);
+    // (the calling thread is one of them: OpenMP's master thread works in the parallel region)
     if (w > 1) nthreads = nthreads / (unsigned)w ? nthreads / (unsigned)w : 1;
   }
   if (nthreads > 64) nthreads = 64;
@@ -1030,7 +1114,7 @@ int bp_test_fq(int op, int on_device, const uint8_t* a32, const uint8_t* b32, si
   for (size_t i = 0; i < n; i++) {   // same fq.cuh code on the host
     Fq x, y, r; fq_from_le(&x, a32 + 32 * i); fq_from_le(&y, b32 + 32 * i); x = fq_reduce(x); y = fq_reduce(y);
     switch (op) { case 0: r = fq_mul(x, y); break; case 1: r = fq_add(x, y); break; case 2: r = fq_sub(x, y); break;
-                  case 3: case 6: case 8: r = fq_inv(x); break; case 4: r = fq_neg(x); break; case 5: r = fq_mul(x, y); break;
+                  case 3: case 6: case 8: r = fq_inv(x); break; case 9: r = fq_inv_host(x); break; case 4: r = fq_neg(x); break; case 5: r = fq_mul(x, y); break;
                   case 7: r = fq_mul(x, x); break; default: r = x; }
     fq_to_le(out32 + 32 * i, r);
   }

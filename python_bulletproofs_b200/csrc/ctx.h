@@ -1,7 +1,9 @@
 // ctx.h -- per-process device context of libbpgpu: one GPU, one stream, grow-only workspaces.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <cstddef>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -132,12 +134,41 @@ struct Ctx {
       if (!stage_ev[i] && cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming) != cudaSuccess) return fail("event creation failed");
     return 0;
   }
-  // IPA round graphs: one instantiated graph per vector length, valid while no workspace has been reallocated
-  bool use_graphs = true;
+  // IPA prover: how the host's Fiat-Shamir step meets the stream (bp_ipa_set_graphs; see bp_ipa_prove_hs)
+  // Default 1, except under a CUDA tool (ncu, compute-sanitizer: they inject through CUDA_INJECTION64_PATH and run each launch
+  // to completion inside the launch call, which can never happen behind a stream wait that the same thread has yet to release)
+  // where it is 0; BP_IPA_MODE overrides both.
+  static int default_ipa_mode() {
+    if (const char* e = getenv("BP_IPA_MODE")) { int m = atoi(e); if (m >= 0 && m <= 2) return m; }
+    if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return 0;
+    return 1;
+  }
+  int ipa_mode = default_ipa_mode();
+  // stream memory operations, resolved through the runtime (no link-time dependency on libcuda)
+  CUresult (*cuWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*cuWriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  int memops_state = 0;        // 0 = not probed, 1 = available, -1 = not available
+  bool memops_ready() {
+    if (memops_state == 0) {
+      cudaDriverEntryPointQueryResult q1, q2;
+      void *f1 = nullptr, *f2 = nullptr;
+      const bool ok = cudaGetDriverEntryPoint("cuStreamWaitValue32", &f1, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess && f1 &&
+                      cudaGetDriverEntryPoint("cuStreamWriteValue32", &f2, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess && f2;
+      if (!ok) cudaGetLastError();
+      cuWaitValue32 = (decltype(cuWaitValue32))f1; cuWriteValue32 = (decltype(cuWriteValue32))f2;
+      memops_state = ok ? 1 : -1;
+    }
+    return memops_state == 1;
+  }
+  // IPA proof graphs (mode 2): one instantiated graph per vector length, valid while no workspace has been reallocated
   DevBuf ws_ipa_rp;
   struct GraphRec { cudaGraphExec_t exec; unsigned long long gen; const void* tab; unsigned nk; };   // nk = kernel nodes
   std::map<size_t, GraphRec> ipa_graphs;
   // `tab` = the fixed-base table the captured round reads (nullptr: bucket-method round); part of the key
+  // (n, table) pairs whose eager proof has sized every workspace, with the allocation generation at that moment
+  std::map<size_t, unsigned long long> ipa_sized;
+  void ipa_mark_sized(size_t n, const void* tab) { ipa_sized[2 * n + (tab ? 1 : 0)] = alloc_generation(); }
+  bool ipa_sized_ok(size_t n, const void* tab) { auto it = ipa_sized.find(2 * n + (tab ? 1 : 0)); return it != ipa_sized.end() && it->second == alloc_generation(); }
   unsigned ipa_graph_kernels(size_t n, const void* tab) { auto it = ipa_graphs.find(2 * n + (tab ? 1 : 0)); return it == ipa_graphs.end() ? 0u : it->second.nk; }
   cudaGraphExec_t ipa_graph_lookup(size_t n, const void* tab) {
     auto it = ipa_graphs.find(2 * n + (tab ? 1 : 0));

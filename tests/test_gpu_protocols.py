@@ -118,6 +118,27 @@ def test_ipa_golden(golden, name):
         assert quiet(Verifier2(g, h, u, P2, proof2).verify) is case["verify2"]
 
 
+@pytest.mark.parametrize("mode", [0, 2, 1])
+def test_ipa_prover_round_loop_modes(golden, mode):
+    """bp_ipa_set_graphs: the three ways the host's Fiat-Shamir step meets the stream (per-round synchronisation, one CUDA
+    graph with host nodes, mapped-flag handshake) produce the same bytes -- checked against the golden C2 proof (n = 2^10,
+    recorded from the unmodified reference) and the small cases, several proofs in a row so that mode 2 replays its graph."""
+    lib = nat.load()
+    try:
+        nat.check(lib.bp_ipa_set_graphs(mode))
+        for name in ("ipa_c2", "ipa_small"):
+            for case in golden(name)["cases"]:
+                N = case["N"]
+                g, h, u, a, b = ipa_inputs(N, case["seeds"])
+                g, h, u = [P_(t) for t in g], [P_(t) for t in h], P_(u)
+                a, b = [M_(v) for v in a], [M_(v) for v in b]
+                P2 = vector_commitment(g, h, a, b) + inner_product(a, b) * u
+                for _ in range(3):
+                    assert p2_json(FastNIProver2(g, h, u, P2, a, b, secp256k1).prove()) == case["proof2"]
+    finally:
+        lib.bp_ipa_set_graphs(1)
+
+
 def test_ipa_soundness_smoke():
     """src/tests/test_innerprod.py:33-98,226-268: wrong P / a / b / u / transcript => Proof invalid."""
     N = 8

@@ -94,9 +94,11 @@ def test_host_fq_arithmetic_matches_bigint():
         assert nat.load().bp_test_fq(op, 0, le(a), le(b), len(a), out) == 0
         got = [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(len(a))]
         assert got == [fn(x % Q, y % Q) for x, y in zip(a, b)], op
-    nz = [x % Q or 1 for x in a]
-    nat.load().bp_test_fq(3, 0, le(nz), le(nz), len(nz), out)
-    assert [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(len(nz))] == [pow(x, -1, Q) for x in nz]
+    nz = [x % Q or 1 for x in a] + [2, 3, Q - 2, (Q + 1) // 2, 2 ** 255 % Q] + [1 << k for k in range(1, 256, 9)]
+    out = ctypes.create_string_buffer(32 * len(nz))
+    for op in (3, 9):           # 3: portable Fermat form (shared with the device), 9: fq_inv_host, the binary extended GCD of the IPA round loop
+        nat.load().bp_test_fq(op, 0, le(nz), le(nz), len(nz), out)
+        assert [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(len(nz))] == [pow(x, -1, Q) for x in nz], op
 
 
 def test_modp_quirks_and_api_shapes():

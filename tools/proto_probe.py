@@ -58,7 +58,7 @@ for total in (1024, 8192):
     acc = T("C5 verify_packed %d proofs" % total, lambda: verify_packed(batch, g1, h1, gs, hs, u1))
     assert acc == b"\x01" * total
 # effect of the CUDA-graph replay of the IPA rounds
-for on in (0, 1):
+for on in (0, 2, 1):
     nat.load().bp_ipa_set_graphs(on)
-    T("C2 IPA prove n=1024, graphs=%d" % on, lambda: NIProver(g, h, u, P, c, a, b, secp256k1, b"s").prove(), reps=5)
-    T("C1 range prove n=64, graphs=%d" % on, lambda: NIRangeProver(v, n, g1, h1, gs, hs, gamma, u1, secp256k1, b"x").prove(), reps=5)
+    T("C2 IPA prove n=1024, mode=%d" % on, lambda: NIProver(g, h, u, P, c, a, b, secp256k1, b"s").prove(), reps=5)
+    T("C1 range prove n=64, mode=%d" % on, lambda: NIRangeProver(v, n, g1, h1, gs, hs, gamma, u1, secp256k1, b"x").prove(), reps=5)
