@@ -313,9 +313,32 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
     return 0;
   }
   if ((unsigned long long)ps.W * stride >= (1ull << 30)) return fail("msm: too many terms for 30-bit point indices");
-  const size_t nb = sh.H, emax = (size_t)ps.W * T, nchunks = (emax + sh.chunk - 1) / sh.chunk;
+  const size_t nb = sh.H, emax = (size_t)ps.W * T;
+  // batched-affine pair passes ahead of the XYZZ accumulation (affine.cuh) when the buckets are deep enough for the padding to
+  // 2^P entries to stay small: P = 3 from ~64 entries per bucket
+  int P = g.aff_passes >= 0 ? g.aff_passes : ((double)emax >= 48.0 * (double)nb && emax >= ((size_t)1 << 22) ? 3 : 0);
+  if (P > 6) P = 6;
+  const u32 amask = (1u << P) - 1u;
+  const size_t emax_pad = P ? emax + nb * amask : emax;                 // every bucket rounded up to a multiple of 2^P entries
+  if (emax_pad >= 0xFFFFFFF0ull) return fail("msm: too many entries");
+  if (P) {                                                              // the XYZZ stage sees 1/2^P of the entries
+    const double red = (double)(emax_pad >> P);
+    sh.chunk = red <= 1300000.0 ? 8 : (red <= 2600000.0 ? 16 : BP_CHUNK);
+    if (g.pre_chunk) sh.chunk = g.pre_chunk;
+  }
+  const size_t nchunks = ((P ? (emax_pad >> P) : emax) + sh.chunk - 1) / sh.chunk;
   int* digits = (int*)g.ws_digits.ensure(emax * sizeof(int));
-  uint2* entries = (uint2*)g.ws_entries.ensure(emax * sizeof(uint2));
+  uint2* entries = (uint2*)g.ws_entries.ensure(emax_pad * sizeof(uint2));
+  Affine *aff_a = nullptr, *aff_b = nullptr; Fp* aff_scr = nullptr; u32 *aff_ctr = nullptr, *red_start = nullptr; uint2* red_ent = nullptr;
+  if (P) {
+    aff_a = (Affine*)g.ws_aff_a.ensure((emax_pad / 2 + 1) * sizeof(Affine));
+    aff_b = (Affine*)g.ws_aff_b.ensure((emax_pad / 4 + 1) * sizeof(Affine));
+    aff_scr = (Fp*)g.ws_aff_scr.ensure((size_t)4 * g.sm_count * 128 * BP_AFF_B * sizeof(Fp));
+    aff_ctr = (u32*)g.ws_aff_ctr.ensure(8 * sizeof(u32));
+    red_start = (u32*)g.ws_aff_start.ensure((nb + 1) * sizeof(u32));
+    red_ent = (uint2*)g.ws_aff_ent.ensure(((emax_pad >> P) + 1) * sizeof(uint2));
+    if (!aff_a || !aff_b || !aff_scr || !aff_ctr || !red_start || !red_ent) return fail("workspace allocation failed");
+  }
   u32* count = (u32*)g.ws_count.ensure((nb + 1) * sizeof(u32));
   u32* start = (u32*)g.ws_start.ensure((nb + 1) * sizeof(u32));
   u32* cursor = (u32*)g.ws_cursor.ensure((nb + 1) * sizeof(u32));
@@ -331,22 +354,38 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
   if (prof) cudaEventRecord(g.ev[0], st);
   ++g.nlaunch, k_digits_pre<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, ps, digits, count);
   if (prof) cudaEventRecord(g.ev[1], st);
-  ++g.nlaunch, k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
+  ++g.nlaunch, k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1, amask);
   ++g.nlaunch, k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
   ++g.nlaunch, k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
   if (prof) cudaEventRecord(g.ev[2], st);
   BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+  if (P) ++g.nlaunch, k_aff_pad<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(start, count, (u32)nb, entries);
   ++g.nlaunch, k_scatter_pre<<<(T + 255) / 256, 256, 0, st>>>(digits, T, ps, stride, first, cursor, entries);
   if (prof) cudaEventRecord(g.ev[3], st);
   BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));
   BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));
   if (prof) cudaEventRecord(g.ev_k0, st);
-  ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pre, nullptr, nullptr, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
+  const Affine* acc_pts = pre; const u32* acc_start = start; const uint2* acc_ent = entries;
+  if (P) {
+    // batched-affine pair passes (affine.cuh): the list halves P times, then the XYZZ accumulation takes over at 1/2^P of the additions
+    BP_CUDA(cudaMemsetAsync(aff_ctr, 0, 8 * sizeof(u32), st));
+    const unsigned grid = 4 * (unsigned)g.sm_count;
+    const Affine* src = nullptr;
+    for (int p = 0; p < P; p++) {
+      Affine* dst = (p & 1) ? aff_b : aff_a;
+      if (p == 0) ++g.nlaunch, k_aff_pass<BP_AFF_B, true><<<grid, 128, 0, st>>>(pre, nullptr, nullptr, entries, nullptr, start + nb, 0, dst, aff_scr, aff_ctr);
+      else ++g.nlaunch, k_aff_pass<BP_AFF_B, false><<<grid, 128, 0, st>>>(nullptr, nullptr, nullptr, nullptr, src, start + nb, (u32)p, dst, aff_scr, aff_ctr + p);
+      src = dst;
+    }
+    ++g.nlaunch, k_aff_index<<<(unsigned)(((emax_pad >> P) > nb + 1 ? (emax_pad >> P) : nb + 1) + 255) / 256, 256, 0, st>>>(start, (u32)nb, entries, P, red_start, red_ent);
+    acc_pts = src; acc_start = red_start; acc_ent = red_ent;
+  }
+  ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(acc_pts, nullptr, nullptr, acc_start, acc_ent, zero_word, acc_start + nb, sh.chunk, buckets, part);
   if (prof) cudaEventRecord(g.ev_k1, st);
-  ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big_cap);
-  ++g.nlaunch, k_fixup_mid<<<2 * g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big_cap);
-  ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big);
+  ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(acc_start, 0, nb, zero_word, sh.chunk, part, buckets, big, big_cap);
+  ++g.nlaunch, k_fixup_mid<<<2 * g.sm_count, 256, 0, st>>>(acc_start, zero_word, sh.chunk, part, buckets, big, big_cap);
+  ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(acc_start, zero_word, sh.chunk, part, buckets, big);
   if (prof) cudaEventRecord(g.ev[4], st);
   if (sh.H < 4096) {                                   // small unit: the running-sum tails of the plain path
     if (msm_tails(buckets, sh, 1, out_affine, out_xyzz, prof, st)) return 1;
@@ -620,6 +659,7 @@ int bp_msm_last_entries(uint64_t* entries) {      // non-zero digits = mixed add
   return 0;
 }
 int bp_launch_count(uint64_t* launches) { *launches = g.nlaunch; return 0; }
+int bp_msm_set_affine_passes(int passes) { g.aff_passes = passes < 0 ? -1 : (passes > 6 ? 6 : passes); return 0; }   /* experiment switch */
 int bp_msm_set_pre_chunk(int entries) { g.pre_chunk = entries > 0 ? (unsigned)entries : 0; return 0; }   /* experiment switch */
 int bp_msm_set_profiling(int on) { g.profiling = on != 0; return 0; }
 int bp_msm_set_pipeline_min(size_t min_terms) { g.pipeline_min_terms = min_terms ? (unsigned)min_terms : 0xFFFFFFFFu; return 0; }

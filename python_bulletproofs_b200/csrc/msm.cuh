@@ -189,12 +189,13 @@ __global__ void __launch_bounds__(128) k_phi(const Affine* __restrict__ points, 
 
 // ---- exclusive scan of u32 counts (3 passes; totals < 2^32) ---------------------------------------
 #define BP_SCAN_TILE 2048
-__global__ void __launch_bounds__(256) k_scan_tiles(const u32* __restrict__ in, u32* __restrict__ out, u32* __restrict__ tile_sum, size_t n) {
+// amask = 2^P - 1 rounds every count up to a multiple of 2^P first (bucket starts aligned for the pair passes of affine.cuh)
+__global__ void __launch_bounds__(256) k_scan_tiles(const u32* __restrict__ in, u32* __restrict__ out, u32* __restrict__ tile_sum, size_t n, u32 amask = 0) {
   __shared__ u32 sm[256];
   size_t base = (size_t)blockIdx.x * BP_SCAN_TILE + (size_t)threadIdx.x * 8;
   u32 v[8], s = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
+  for (int i = 0; i < 8; i++) { v[i] = base + i < n ? (in[base + i] + amask) & ~amask : 0; s += v[i]; }
   sm[threadIdx.x] = s;
   __syncthreads();
   for (int off = 1; off < 256; off <<= 1) {
@@ -788,3 +789,5 @@ __global__ void __launch_bounds__(32) k_pre_finish(const XYZZ* __restrict__ sums
 }
 
 }  // namespace bp
+
+#include "affine.cuh"

@@ -263,6 +263,46 @@ def test_msm_precomputed_window_multiples(c):
     dp.free()
 
 
+@pytest.mark.parametrize("passes", [1, 2, 3, 5])
+@pytest.mark.parametrize("c", [8, 11])
+def test_msm_batched_affine_pair_passes(c, passes):
+    """affine.cuh: the pairwise affine passes ahead of the XYZZ accumulation (bp_msm_set_affine_passes), forced on a small
+    vector so that every special case sits in the pair sums: repeated points with equal scalars (P + P in one bucket), P and -P
+    (sum = identity, then identity + point in the next pass), identity inputs, all-equal scalars (one deep bucket per window),
+    zero scalars (empty buckets, padding only) -- against the oracle."""
+    from python_bulletproofs_b200.device import DevicePoints
+    n = 2500
+    pool = fast_points(12, 777)
+    rng = random.Random(1000 * c + passes)
+    pts = [pool[rng.randrange(12)] for _ in range(n)]                 # 12 distinct points: most pairs inside a bucket are P + P
+    for i in range(0, n, 7):
+        pts[i] = ecc.point_neg(pts[i - 1]) if i else pts[i]           # P, -P neighbours
+    pts[5] = None; pts[6] = None
+    lib = nat.load()
+    dp = DevicePoints(raw=ecc.pack_points(pts)).precompute(c)
+    out = ctypes.create_string_buffer(64)
+    few = [rng.getrandbits(256) % Q for _ in range(3)]
+    scalar_sets = {
+        "few_values": [few[rng.randrange(3)] for _ in range(n)],
+        "pairs_cancel": [few[0]] * n,
+        "uniform": [rng.getrandbits(256) for _ in range(n)],
+        "sparse": [0 if i % 5 else rng.getrandbits(256) for i in range(n)],
+        "small": [rng.randrange(0, 4) for _ in range(n)],
+    }
+    try:
+        nat.check(lib.bp_msm_set_affine_passes(passes))
+        for name, ks in scalar_sets.items():
+            sb = b"".join(int(k % 2 ** 256).to_bytes(32, "little") for k in ks)
+            nat.check(lib.bp_msm_h(dp.handle, sb, n, out))
+            assert ecc.unpack_point(out.raw) == ecc.msm(pts, [k % Q for k in ks]), name
+            for m in (1, 2, 31, 1025):
+                nat.check(lib.bp_msm_h(dp.handle, sb, m, out))
+                assert ecc.unpack_point(out.raw) == ecc.msm(pts[:m], [k % Q for k in ks[:m]]), (name, m)
+    finally:
+        lib.bp_msm_set_affine_passes(-1)
+    dp.free()
+
+
 def test_msm_precomputed_2p18_vs_plain_and_oracle():
     n = 1 << 18
     from python_bulletproofs_b200.device import DevicePoints, DeviceScalars

@@ -60,6 +60,7 @@ def main():
                 + " ".join("%s=%.3f" % (nm, v) for nm, v in zip(names, stage)), flush=True)
     lib.bp_msm_set_window(0)
     lib.bp_msm_set_pre_chunk(int(os.environ.get("BP_PRE_CHUNK", "0")))
+    lib.bp_msm_set_affine_passes(int(os.environ.get("BP_AFF_PASSES", "-1")))
     for pc in [int(x) for x in args.pre.split(",") if x != ""]:
         for lgn in [int(x) for x in args.lgn.split(",")]:
             n = 1 << lgn
