@@ -314,9 +314,11 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
   }
   if ((unsigned long long)ps.W * stride >= (1ull << 30)) return fail("msm: too many terms for 30-bit point indices");
   const size_t nb = sh.H, emax = (size_t)ps.W * T;
-  // batched-affine pair passes ahead of the XYZZ accumulation (affine.cuh) when the buckets are deep enough for the padding to
-  // 2^P entries to stay small: P = 3 from ~64 entries per bucket
-  int P = g.aff_passes >= 0 ? g.aff_passes : ((double)emax >= 48.0 * (double)nb && emax >= ((size_t)1 << 22) ? 3 : 0);
+  // batched-affine pair passes ahead of the XYZZ accumulation (affine.cuh): OFF unless bp_msm_set_affine_passes asks for them.
+  // Measured at 2^20 (profiles/r2_affine_passes.txt): passes 1.44 + 0.64 + 0.35 ms + 0.24 ms XYZZ remainder against 1.80 ms for
+  // the XYZZ accumulation alone -- a shared inversion costs ~18-40 k warp instructions whoever executes it, and one MSM of this
+  // size has only ~250 k warp-level additions per pass to spread it over.
+  int P = g.aff_passes > 0 ? g.aff_passes : 0;
   if (P > 6) P = 6;
   const u32 amask = (1u << P) - 1u;
   const size_t emax_pad = P ? emax + nb * amask : emax;                 // every bucket rounded up to a multiple of 2^P entries
