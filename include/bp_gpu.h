@@ -155,6 +155,10 @@ int bp_ipa_prove(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[64],
  *                vector length and replayed: one launch per proof;
  *   0            plain stream launches, one cudaStreamSynchronize per round. */
 int bp_ipa_set_graphs(int mode);
+/* Table rounds of proofs with n <= 4096 as two launches per round (scalar work of the round in one block reading the mapped
+ * parameter block; table MSM whose last block reduces and writes L, R into mapped host memory): on by default, 0 = the
+ * four-launch form with copy operations. */
+int bp_ipa_set_fast_rounds(int on);
 
 /* Same, with the h generators given as (h, hscale): the effective generators are hscale_i * h_i, which are never
  * materialised (hscale32 = NULL means all ones).  The range-proof prover passes hs with hscale_i = y^-i instead of the
@@ -247,6 +251,8 @@ int bp_pipe_probe(int mode, int iters, double* ops_per_s, float* ms);
 int bp_test_fp(int op, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32);
 int bp_test_ec(int op, const uint8_t* a64, const uint8_t* b64, size_t n, uint8_t* out64);
 int bp_test_fq(int op, int on_device, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32);
+/* host F_p (csrc/fp_host.h): count <= 8 XYZZ points (128 bytes each) -> canonical affine, as the IPA prover's host step finishes L and R */
+int bp_test_xyzz_to_affine_host(const uint8_t* xyzz128, size_t count, uint8_t* out64);
 
 /* ---- multi-GPU (one process per GPU) ---------------------------------------------------------------
  * NCCL communicator over the ranks of a torchrun job; `unique_id` is the 128-byte ncclUniqueId

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "bp_ipa_prove": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
                                     c_u8p, c_sz, ctypes.POINTER(c_sz)]),
     "bp_ipa_set_graphs": (ctypes.c_int, [ctypes.c_int]),
+    "bp_ipa_set_fast_rounds": (ctypes.c_int, [ctypes.c_int]),
     "bp_ipa_prove_hs": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
                                        c_u8p, c_sz, ctypes.POINTER(c_sz)]),
     "bp_ipa_verify1_eq_hs": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
@@ -82,6 +83,7 @@ PROTOTYPES = {
     "bp_test_fp": (ctypes.c_int, [ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_test_ec": (ctypes.c_int, [ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_test_fq": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
+    "bp_test_xyzz_to_affine_host": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
     "bp_nccl_unique_id": (ctypes.c_int, [c_u8p]),
     "bp_nccl_init": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u8p]),
     "bp_msm_sharded": (ctypes.c_int, [c_h, c_h, c_sz, c_sz, c_u8p]),

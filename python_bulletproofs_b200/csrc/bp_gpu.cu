@@ -18,10 +18,12 @@
 #include "verify.cuh"
 #include "svar.cuh"
 #include "fixedbase.cuh"
+#include "ipa_round.cuh"
 #include "rp_algebra.h"
 #include <nccl.h>
 #include <thread>
 
+#include "fp_host.h"
 namespace bp {
 
 thread_local std::string g_err;

@@ -28,6 +28,7 @@ static ChallengeForms challenge_forms(const Fq& x);
 struct IpaHostCtx {
   std::string digest; RunningModHash rh; size_t round = 0, n = 0;
   IpaRound* h_rp = nullptr; uint8_t* h_lr = nullptr;
+  bool lr_xyzz = false;            // h_lr holds L, R in XYZZ coordinates (2 x 128 bytes): finished here (fp_host.h)
   std::vector<uint8_t> Ls, Rs, xs;
 };
 static IpaHostCtx g_ipa_host;
@@ -35,6 +36,7 @@ static IpaHostCtx g_ipa_host;
 static void CUDART_CB ipa_host_round(void* p) {
   IpaHostCtx& c = *(IpaHostCtx*)p;
   const size_t r = c.round;
+  if (c.lr_xyzz) { uint8_t aff[128]; xyzz_to_affine_host(c.h_lr, 2, aff); memcpy(c.h_lr, aff, 128); }
   memcpy(c.Ls.data() + 64 * r, c.h_lr, 64);
   memcpy(c.Rs.data() + 64 * r, c.h_lr + 64, 64);
   c.digest += point_to_b64(c.h_lr); c.digest += '&';
@@ -64,6 +66,7 @@ static int fold_step(const Affine* P, Affine* P2, const Fq* a, const Fq* b, Fq* 
 
 extern "C" {
 
+int bp_ipa_set_fast_rounds(int on) { g.ipa_fast = on != 0; return 0; }
 int bp_ipa_set_graphs(int mode) {
   if (mode < 0 || mode > 2) return fail("bp_ipa_set_graphs: 0 = synchronise per round, 1 = mapped-flag handshake (default), 2 = one CUDA graph with host nodes");
   g.ipa_mode = mode;
@@ -245,10 +248,10 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   // coefficient vectors of the folded generators over the original ones (see k_build_lr_sv); P = PA is never rewritten
   Fq* cg = (Fq*)g.ws_h.ensure(2 * n * sizeof(Fq));
   IpaRound* d_rp = (IpaRound*)g.ws_ipa_rp.ensure(sizeof(IpaRound));
-  uint8_t* pin = g.pinned_bytes(512);
+  uint8_t* pin = g.pinned_bytes(1024);
   if (!cg || !d_rp || !pin) return fail("device allocation failed");
   IpaRound* h_rp = (IpaRound*)pin;                 // pinned mirror of the round parameters
-  uint8_t* h_lr = pin + 256;                       // pinned landing zone of L, R
+  uint8_t* h_lr = pin + 256;                       // pinned landing zone of L, R (affine 2 x 64 bytes, or XYZZ 2 x 128 bytes)
   Fq* ch = cg + n;
   ++g.nlaunch, k_fill_one_mont<<<(unsigned)((2 * n + 127) / 128), 128, 0, g.stream>>>(cg, (u32)(2 * n));
   if (hscale32) {   // effective generators h_i' = hscale_i * h_i (e.g. y^-i, rangeproof_prover.py:77): start ch there
@@ -272,11 +275,11 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   IpaHostCtx& hc = g_ipa_host;
   hc.digest.assign((const char*)transcript, transcript_len);
   hc.rh = RunningModHash();
-  hc.round = 0; hc.n = n; hc.h_rp = h_rp; hc.h_lr = h_lr;
+  hc.round = 0; hc.n = n; hc.h_rp = h_rp; hc.h_lr = h_lr; hc.lr_xyzz = false;
   hc.Ls.assign(64 * (size_t)(L ? L : 1), 0); hc.Rs.assign(64 * (size_t)(L ? L : 1), 0); hc.xs.assign(32 * (size_t)(L ? L : 1), 0);
-  uint8_t* h_ab = pin + 384;                        // pinned landing zone of the final a, b
-  volatile u32* f_g2c = (volatile u32*)(pin + 448);  // device -> host: rounds whose L, R have landed
-  volatile u32* f_c2g = (volatile u32*)(pin + 452);  // host -> device: rounds whose challenge is in h_rp
+  uint8_t* h_ab = pin + 512;                        // pinned landing zone of the final a, b
+  volatile u32* f_g2c = (volatile u32*)(pin + 576);  // device -> host: rounds whose L, R have landed
+  volatile u32* f_c2g = (volatile u32*)(pin + 580);  // host -> device: rounds whose challenge is in h_rp
   // Three ways to run the same sequence (bp_ipa_set_graphs): per round [parameters up | fold with the previous challenge |
   // L/R terms | batched MSM | L, R down | Fiat-Shamir on the host], then the last fold and a, b down.
   //   1 (default) the whole proof is enqueued ONCE; the stream itself waits on a mapped host word for each challenge
@@ -287,21 +290,52 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   //   0 stream launches with one cudaStreamSynchronize per round (the baseline the other two are measured against).
   int mode = g.ipa_mode;
   if (mode == 1 && !g.memops_ready()) mode = 2;
+  // Table rounds of a small proof (n <= 4096) are latency chains: TWO launches per round and no copy operation -- the round's
+  // scalar work in one block that reads the parameters straight from the mapped host block (k_ipa_round_prep), then the table
+  // MSM whose last block also reduces and writes L, R into mapped host memory (k_fb_msm with a ticket).
+  const bool fast = tab != nullptr && n <= 4096 && g.ipa_fast;
+  u32* d_ticket = nullptr; XYZZ* d_part = nullptr; Fq* cg2 = nullptr;
+  const u32 nbx = (u32)((n1 + 31) / 32);
+  if (fast) {
+    const bool fresh = g.ws_ipa_ticket.p == nullptr;
+    d_ticket = (u32*)g.ws_ipa_ticket.ensure(4 * sizeof(u32));
+    d_part = (XYZZ*)fb.blockpart.ensure((size_t)2 * nbx * sizeof(XYZZ));
+    cg2 = (Fq*)g.ws_h2.ensure(2 * n * sizeof(Fq));
+    if (!d_ticket || !d_part || !cg2) return fail("workspace allocation failed");
+    if (fresh) BP_CUDA(cudaMemsetAsync(d_ticket, 0, 4 * sizeof(u32), g.stream));      // the last block of every launch leaves it at zero
+  }
+  hc.lr_xyzz = fast;
+  const size_t nkey = n | (fast ? (size_t)1 << 40 : 0);      // captured proof graphs are specific to the round form
+  const unsigned prep_threads = n >= 1024 ? 1024u : (n <= 32 ? 32u : (unsigned)n);
+  IpaState st[2] = {{a, b, cg, ch}, {aB, bB, cg2, cg2 ? cg2 + n : nullptr}};      // fast rounds ping-pong the scalar state (k_ipa_round)
   auto enqueue_proof = [&](int md) -> int {
     u32 r = 0;
+    int cur = 0;
     for (size_t m = n; m > 1; m >>= 1, r++) {
       if (md == 1 && r > 0) BP_CU(g.cuWaitValue32(g.stream, (CUdeviceptr)(uintptr_t)f_c2g, r, CU_STREAM_WAIT_VALUE_GEQ));
-      BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
-      ++g.nlaunch, k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
-      ++g.nlaunch, k_build_lr_sv<<<1, 256, 0, g.stream>>>(a, b, cg, ch, (u32)n, &d_rp->m, tsc, tidx);
-      if (tab ? fb_msm_run(tab, tidx, tsc, d_off, 2, n1, 0, d_lr, nullptr) : msm_run(PA, tidx, tsc, 2 * n1, d_off, 2, n1, d_lr, nullptr)) return 1;
-      BP_CUDA(cudaMemcpyAsync(h_lr, d_lr, 128, cudaMemcpyDeviceToHost, g.stream));
+      if (fast) {
+        // (the parameter block goes down by a copy: 66 blocks reading the same mapped host words cost ~50 us of serialised PCIe reads)
+        BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
+        ++g.nlaunch, k_ipa_round<<<dim3(nbx, 2), 256, 0, g.stream>>>(tab, st[cur], st[cur ^ 1], (u32)n, d_rp, d_part, d_ticket, (XYZZ*)h_lr);
+        cur ^= 1;
+      } else {
+        BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
+        ++g.nlaunch, k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
+        ++g.nlaunch, k_build_lr_sv<<<1, 256, 0, g.stream>>>(a, b, cg, ch, (u32)n, &d_rp->m, tsc, tidx);
+        if (tab ? fb_msm_run(tab, tidx, tsc, d_off, 2, n1, 0, d_lr, nullptr) : msm_run(PA, tidx, tsc, 2 * n1, d_off, 2, n1, d_lr, nullptr)) return 1;
+        BP_CUDA(cudaMemcpyAsync(h_lr, d_lr, 128, cudaMemcpyDeviceToHost, g.stream));
+      }
       if (md == 2) BP_CUDA(cudaLaunchHostFunc(g.stream, ipa_host_round, &hc));
       else if (md == 1) BP_CU(g.cuWriteValue32(g.stream, (CUdeviceptr)(uintptr_t)f_g2c, r + 1, 0));
       else { BP_CUDA(cudaStreamSynchronize(g.stream)); ipa_host_round(&hc); }
     }
     if (n > 1) {   // last fold: a, b of length 1   (inner_product_prover.py:109-110)
       if (md == 1) BP_CU(g.cuWaitValue32(g.stream, (CUdeviceptr)(uintptr_t)f_c2g, r, CU_STREAM_WAIT_VALUE_GEQ));
+      if (fast) {
+        ++g.nlaunch, k_ipa_round_prep<<<1, prep_threads, 0, g.stream>>>(st[cur].a, st[cur].b, st[cur].cg, st[cur].ch, (u32)n, h_rp, tsc, tidx, 0, (Fq*)h_ab);
+        BP_CUDA(cudaGetLastError());
+        return 0;
+      }
       BP_CUDA(cudaMemcpyAsync(d_rp, h_rp, sizeof(IpaRound), cudaMemcpyHostToDevice, g.stream));
       ++g.nlaunch, k_round_fold<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(a, b, cg, ch, (u32)n, d_rp);
     }
@@ -313,10 +347,10 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
   h_rp->m = (u32)n;
   *f_g2c = 0; *f_c2g = 0;
   bool done = false;
-  if (mode == 2 && n > 1 && g.ipa_sized_ok(n, tab)) {
+  if (mode == 2 && n > 1 && g.ipa_sized_ok(nkey, tab)) {
     // The first proof of a vector length runs eagerly (it sizes every workspace); from the second one on the same sequence
     // is ONE CUDA-graph launch, captured once per (n, table) and valid while no workspace has moved.
-    cudaGraphExec_t gexec = g.ipa_graph_lookup(n, tab);
+    cudaGraphExec_t gexec = g.ipa_graph_lookup(nkey, tab);
     if (!gexec) {
       cudaGraph_t graph = nullptr;
       const unsigned long long l0 = g.nlaunch, gen0 = alloc_generation();
@@ -332,20 +366,24 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
         ce = cudaGraphInstantiate(&gexec, graph, 0);
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) { cudaGetLastError(); gexec = nullptr; }
-        else g.ipa_graph_store(n, tab, gexec, nk);
+        else g.ipa_graph_store(nkey, tab, gexec, nk);
       }
     }
     if (gexec) {
       BP_CUDA(cudaGraphLaunch(gexec, g.stream));
-      g.nlaunch += g.ipa_graph_kernels(n, tab);
+      g.nlaunch += g.ipa_graph_kernels(nkey, tab);
       done = true;
     }
   }
   if (!done && mode == 1 && n > 1) {
+    const auto t_enq0 = std::chrono::steady_clock::now();
     if (enqueue_proof(1)) { *f_c2g = 0x7FFFFFFFu; cudaStreamSynchronize(g.stream); return 1; }
     // this thread's side of the handshake: wait for L, R of round r, hash, publish the challenge
     const auto t_start = std::chrono::steady_clock::now();
+    static const bool timing = getenv("BP_IPA_TIMING") != nullptr;      // per-round wait / host times on stderr (development aid)
+    double t_wait[40], t_host[40];
     for (u32 r = 0; r < L; r++) {
+      const auto t_r0 = std::chrono::steady_clock::now();
       unsigned spins = 0;
       while (*f_g2c < r + 1) {
         if ((++spins & 0x3FFFu) == 0) {
@@ -358,15 +396,26 @@ int bp_ipa_prove_hs(const uint8_t* g64, const uint8_t* h64, const uint8_t* hscal
         }
       }
       std::atomic_thread_fence(std::memory_order_acquire);
+      const auto t_r1 = std::chrono::steady_clock::now();
       ipa_host_round(&hc);
       std::atomic_thread_fence(std::memory_order_release);
       *f_c2g = r + 1;
+      if (timing && r < 40) {
+        t_wait[r] = std::chrono::duration<double, std::micro>(t_r1 - t_r0).count();
+        t_host[r] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_r1).count();
+      }
+    }
+    if (timing) {
+      fprintf(stderr, "ipa n=%zu fast=%d enqueue..first wait start %.1f us; per round wait/host us:", n, (int)fast,
+              std::chrono::duration<double, std::micro>(t_start - t_enq0).count());
+      for (u32 r = 0; r < L && r < 40; r++) fprintf(stderr, " %.0f/%.0f", t_wait[r], t_host[r]);
+      fprintf(stderr, "\n");
     }
     done = true;
   }
   if (!done) {
     if (enqueue_proof(mode == 1 ? 0 : mode)) return 1;
-    g.ipa_mark_sized(n, tab);
+    g.ipa_mark_sized(nkey, tab);
   }
   BP_CUDA(cudaStreamSynchronize(g.stream));
   if (L) { memcpy(Ls64, hc.Ls.data(), 64 * (size_t)L); memcpy(Rs64, hc.Rs.data(), 64 * (size_t)L); memcpy(xs32, hc.xs.data(), 32 * (size_t)L); }
@@ -1107,6 +1156,11 @@ int bp_test_ec(int op, const uint8_t* a64, const uint8_t* b64, size_t n, uint8_t
   BP_NEED_INIT();
   if (n == 0) return 0;
   return run_test_kernel<decltype(&k_test_ec), Affine>(k_test_ec, op, a64, b64, n, out64, 64);
+}
+int bp_test_xyzz_to_affine_host(const uint8_t* xyzz128, size_t count, uint8_t* out64) {      // host-only: needs no GPU
+  if (count > 8) return fail("bp_test_xyzz_to_affine_host: at most 8 points");
+  xyzz_to_affine_host(xyzz128, count, out64);
+  return 0;
 }
 int bp_test_fq(int op, int on_device, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32) {
   if (n == 0) return 0;

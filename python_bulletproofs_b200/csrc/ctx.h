@@ -146,6 +146,8 @@ struct Ctx {
     return 1;
   }
   int ipa_mode = default_ipa_mode();
+  bool ipa_fast = true;        // two-launch table rounds for n <= 4096 (bp_ipa_set_fast_rounds)
+  DevBuf ws_ipa_ticket;
   // stream memory operations, resolved through the runtime (no link-time dependency on libcuda)
   CUresult (*cuWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
   CUresult (*cuWriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;

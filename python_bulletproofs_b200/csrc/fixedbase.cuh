@@ -76,9 +76,89 @@ __global__ void __launch_bounds__(64) k_fb_build(const Affine* __restrict__ pts,
 // consecutive terms: thread = (term, group of 4 byte-windows) does up to 4 mixed additions, then the block folds its
 // 256 partial sums with 4-lane cooperative additions (3 serial + 6 tree levels) into blockpart[m * nbx + blockIdx.x].
 // idx (optional) maps a term to its table row (without it term j of every MSM reads row j); scalars are 32-byte values reduced mod q here (pippenger.py:26).
+// ticket / out_final (optional, both or neither): the block that finishes LAST for its MSM (atomic ticket) also does step 2 --
+// it adds the nbx block sums and writes the canonical affine result to out_final[m] (or the XYZZ sum to out_final_xyzz[m]), which may be mapped host memory (the
+// latency-bound IPA rounds: one launch and no copy-out per round instead of two launches and a copy).
+BP_DI XYZZ ld_xyzz_cg(const XYZZ* p) {       // L2 loads: partial sums written by other blocks of the same launch
+  XYZZ r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 w[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = __ldcg(q + i);
+  Fp* f = &r.X;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    f[i].v[0] = w[2 * i].x; f[i].v[1] = w[2 * i].y; f[i].v[2] = w[2 * i].z; f[i].v[3] = w[2 * i].w;
+    f[i].v[4] = w[2 * i + 1].x; f[i].v[5] = w[2 * i + 1].y; f[i].v[6] = w[2 * i + 1].z; f[i].v[7] = w[2 * i + 1].w;
+  }
+  return r;
+}
+// Tail of a table-MSM block (256 threads, `acc` = this thread's partial sum).  Phase 0: the block's 256 partial sums -> one (each
+// quad adds its 4, then a tree over the 64 quads) -> blockpart[m * nbx + blockIdx.x].  Phase 1 (only the block that finishes last
+// for its MSM, when a ticket is given): the nbx block sums -> one -> out_final[m] (canonical affine) or out_final_xyzz[m].
+// Both phases run through ONE loop with ONE cooperative-addition site (code size: these kernels are latency chains).
+BP_DI void fb_block_tail(XYZZ* sm, u32* s_last, const XYZZ& acc, u32 m, u32 nbx, XYZZ* __restrict__ blockpart, u32* __restrict__ ticket,
+                         Affine* __restrict__ out_final, XYZZ* __restrict__ out_final_xyzz) {
+  st_xyzz(&sm[threadIdx.x], acc);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const u32 q = threadIdx.x >> 2;
+#pragma unroll 1
+  for (int phase = 0; phase < 2; phase++) {
+    // serial steps (each quad adds further operands to its own sum), then a tree over `width` quads -- only as many levels as
+    // there are live sums (3 block sums of a 64-wide proof: 2 levels, not 6)
+    const u32 nserial = phase == 0 ? 3u : (nbx + 63) / 64 - 1;
+    u32 width = 64;
+    if (phase == 1) { width = 1; while (width < nbx && width < 64) width <<= 1; }
+    u32 nlev = 0; while ((1u << nlev) < width) nlev++;
+    XYZZ v = phase == 0 ? ld_xyzz(&sm[4 * q]) : (q < nbx ? ld_xyzz_cg(blockpart + (size_t)m * nbx + q) : xyzz_identity());
+    if (nserial == 0) {                                          // nothing to add before the tree: publish the loaded sums
+      __syncthreads();
+      if (q < width && role == 0) st_xyzz(&sm[q], v);
+      __syncthreads();
+    }
+#pragma unroll 1
+    for (u32 st = 0; st < nserial + nlev; st++) {
+      XYZZ x;
+      if (st < nserial) {
+        if (phase == 0) x = ld_xyzz(&sm[4 * q + st + 1]);
+        else { const u32 i = (st + 1) * 64 + q; x = i < nbx ? ld_xyzz_cg(blockpart + (size_t)m * nbx + i) : xyzz_identity(); }
+      } else {
+        const u32 off = (width >> 1) >> (st - nserial);
+        x = q < off ? ld_xyzz(&sm[q + off]) : xyzz_identity();
+      }
+      v = coop_add(v, x, role, base);
+      if (st + 1 >= nserial) {                                   // publish: after the last serial step and after every tree level
+        const u32 live = st + 1 == nserial ? width : (width >> 1) >> (st - nserial);
+        __syncthreads();
+        if (q < live && role == 0) st_xyzz(&sm[q], v);
+        __syncthreads();
+      }
+    }
+    if (phase == 0) {
+      if (threadIdx.x == 0) st_xyzz(blockpart + (size_t)m * nbx + blockIdx.x, v);
+      if (!ticket) return;
+      if (threadIdx.x == 0) {
+        __threadfence();                                         // the block sum is visible before the ticket is taken
+        *s_last = atomicAdd(ticket + m, 1u) == nbx - 1 ? 1u : 0u;
+      }
+      __syncthreads();
+      if (!*s_last) return;
+      __threadfence();
+    } else if (threadIdx.x == 0) {
+      ticket[m] = 0;                                             // ready for the next launch
+      if (out_final_xyzz) st_xyzz(out_final_xyzz + m, v);         // the caller finishes the conversion (IPA rounds: on the host)
+      else st_affine(out_final + m, xyzz_to_affine(v, true));
+      __threadfence_system();
+    }
+  }
+}
 __global__ void __launch_bounds__(256) k_fb_msm(const Affine* __restrict__ tab, const u32* __restrict__ idx, const Fq* __restrict__ sc,
-                                                const u32* __restrict__ offsets, u32 single_n, XYZZ* __restrict__ blockpart) {
+                                                const u32* __restrict__ offsets, u32 single_n, XYZZ* __restrict__ blockpart,
+                                                u32* __restrict__ ticket = nullptr, Affine* __restrict__ out_final = nullptr,
+                                                XYZZ* __restrict__ out_final_xyzz = nullptr) {
   __shared__ XYZZ sm[256];
+  __shared__ u32 s_last;
   const u32 m = blockIdx.y, nbx = gridDim.x;
   const u32 lo = offsets ? offsets[m] : 0u, hi = offsets ? offsets[m + 1] : single_n;
   const u32 t = lo + blockIdx.x * 32 + (threadIdx.x >> 3), grp = threadIdx.x & 7;
@@ -97,25 +177,7 @@ __global__ void __launch_bounds__(256) k_fb_msm(const Affine* __restrict__ tab, 
       if (d) { Affine p = ld_affine(tab + fb_index(gi, 4 * grp + j, d)); xyzz_madd_ni(acc, p); }
     }
   }
-  st_xyzz(&sm[threadIdx.x], acc);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
-  const u32 q = threadIdx.x >> 2;
-  XYZZ v = ld_xyzz(&sm[4 * q]);
-#pragma unroll 1
-  for (int j = 1; j < 4; j++) { XYZZ x = ld_xyzz(&sm[4 * q + j]); v = coop_add(v, x, role, base); }
-  __syncthreads();
-  if (role == 0) st_xyzz(&sm[q], v);
-  __syncthreads();
-#pragma unroll 1
-  for (u32 off = 32; off > 0; off >>= 1) {
-    XYZZ x = (q < off) ? ld_xyzz(&sm[q + off]) : xyzz_identity();
-    v = coop_add(v, x, role, base);
-    __syncthreads();
-    if (q < off && role == 0) st_xyzz(&sm[q], v);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) st_xyzz(blockpart + (size_t)m * nbx + blockIdx.x, v);
+  fb_block_tail(sm, &s_last, acc, m, nbx, blockpart, ticket, out_final, out_final_xyzz);
 }
 
 // Table MSM, step 2: one block per MSM adds its nbx block sums (quads stride over them, then a tree) and writes the

@@ -207,6 +207,78 @@ __global__ void __launch_bounds__(128) k_round_fold(Fq* __restrict__ a, Fq* __re
     st_fq(b + t, fq_add(fq_mont(blo, xim), fq_mont(bhi, xm)));
   }
 }
+// One round's scalar work in ONE block (n <= 4096; the latency-bound small proofs): k_round_fold, a block barrier, then
+// k_build_lr_sv (build = 1) or, after the last challenge, the copy-out of the final a, b (build = 0, ab_out may be mapped host
+// memory).  rp may live in mapped host memory too: it is read once into shared memory.
+__global__ void __launch_bounds__(1024) k_ipa_round_prep(Fq* __restrict__ a, Fq* __restrict__ b, Fq* __restrict__ cg, Fq* __restrict__ ch, u32 n,
+                                                         const IpaRound* __restrict__ rp, Fq* __restrict__ tsc, u32* __restrict__ tidx,
+                                                         int build, Fq* __restrict__ ab_out) {
+  __shared__ IpaRound s_rp;
+  __shared__ Fq sl[32], sr[32];
+  if (threadIdx.x < sizeof(IpaRound) / 4) ((u32*)&s_rp)[threadIdx.x] = ((const volatile u32*)rp)[threadIdx.x];
+  __syncthreads();
+  const u32 m = s_rp.m;
+  if (s_rp.fold) {                                             // (k_round_fold) m = new length, 2m = old length
+    const Fq xm = s_rp.xm, xim = s_rp.xim;
+    for (u32 t = threadIdx.x; t < n; t += blockDim.x) {
+      const bool hi = (t % (2 * m)) >= m;
+      st_fq(cg + t, fq_mont(ld_fq(cg + t), hi ? xm : xim));
+      st_fq(ch + t, fq_mont(ld_fq(ch + t), hi ? xim : xm));
+      if (t < m) {
+        Fq alo = ld_fq(a + t), ahi = ld_fq(a + m + t), blo = ld_fq(b + t), bhi = ld_fq(b + m + t);
+        st_fq(a + t, fq_add(fq_mont(alo, xm), fq_mont(ahi, xim)));
+        st_fq(b + t, fq_add(fq_mont(blo, xim), fq_mont(bhi, xm)));
+      }
+    }
+    __syncthreads();                                           // the folded a, b, cg, ch are visible to the whole block
+  }
+  if (!build) {
+    if (threadIdx.x == 0) { st_fq(ab_out, ld_fq(a)); st_fq(ab_out + 1, ld_fq(b)); __threadfence_system(); }
+    return;
+  }
+  const u32 k = m >> 1, n1 = n + 1;                             // (k_build_lr_sv)
+  Fq accl = fq_zero(), accr = fq_zero();
+  for (u32 i = threadIdx.x; i < k; i += blockDim.x) {
+    accl = fq_add(accl, fq_mont(ld_fq(a + i), ld_fq(b + k + i)));
+    accr = fq_add(accr, fq_mont(ld_fq(a + k + i), ld_fq(b + i)));
+  }
+  for (u32 t = threadIdx.x; t < n; t += blockDim.x) {
+    const u32 i = t % m, blk = t / m;
+    const bool hi = i >= k;
+    const u32 slot = blk * k + (hi ? i - k : i);
+    const Fq cgt = ld_fq(cg + t), cht = ld_fq(ch + t);
+    if (hi) {
+      st_fq(tsc + slot, fq_mont(ld_fq(a + i - k), cgt));              tidx[slot] = 1 + t;
+      st_fq(tsc + n1 + n / 2 + slot, fq_mont(ld_fq(b + i - k), cht)); tidx[n1 + n / 2 + slot] = 1 + n + t;
+    } else {
+      st_fq(tsc + n1 + slot, fq_mont(ld_fq(a + i + k), cgt));         tidx[n1 + slot] = 1 + t;
+      st_fq(tsc + n / 2 + slot, fq_mont(ld_fq(b + i + k), cht));      tidx[n / 2 + slot] = 1 + n + t;
+    }
+  }
+  // inner products: lane sums by shuffles, warp sums through shared memory
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int off = 16; off > 0; off >>= 1) {
+    Fq xl, xr;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { xl.v[i] = __shfl_down_sync(0xFFFFFFFFu, accl.v[i], off); xr.v[i] = __shfl_down_sync(0xFFFFFFFFu, accr.v[i], off); }
+    accl = fq_add(accl, xl); accr = fq_add(accr, xr);
+  }
+  if (lane == 0) { sl[warp] = accl; sr[warp] = accr; }
+  __syncthreads();
+  if (warp == 0) {
+    accl = lane < nw ? sl[lane] : fq_zero(); accr = lane < nw ? sr[lane] : fq_zero();
+    for (int off = 16; off > 0; off >>= 1) {
+      Fq xl, xr;
+#pragma unroll
+      for (int i = 0; i < 8; i++) { xl.v[i] = __shfl_down_sync(0xFFFFFFFFu, accl.v[i], off); xr.v[i] = __shfl_down_sync(0xFFFFFFFFu, accr.v[i], off); }
+      accl = fq_add(accl, xl); accr = fq_add(accr, xr);
+    }
+    if (lane == 0) {
+      st_fq(tsc + n, fq_to_mont(accl));       tidx[n] = 0;             // (sum * R^-1) * R ; point u
+      st_fq(tsc + n1 + n, fq_to_mont(accr));  tidx[n1 + n] = 0;
+    }
+  }
+}
 __global__ void __launch_bounds__(128) k_to_mont(Fq* __restrict__ v, u32 n) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) st_fq(v + t, fq_to_mont(fq_reduce(ld_fq(v + t))));

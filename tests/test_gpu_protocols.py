@@ -118,14 +118,16 @@ def test_ipa_golden(golden, name):
         assert quiet(Verifier2(g, h, u, P2, proof2).verify) is case["verify2"]
 
 
+@pytest.mark.parametrize("fast", [1, 0])
 @pytest.mark.parametrize("mode", [0, 2, 1])
-def test_ipa_prover_round_loop_modes(golden, mode):
+def test_ipa_prover_round_loop_modes(golden, mode, fast):
     """bp_ipa_set_graphs: the three ways the host's Fiat-Shamir step meets the stream (per-round synchronisation, one CUDA
     graph with host nodes, mapped-flag handshake) produce the same bytes -- checked against the golden C2 proof (n = 2^10,
     recorded from the unmodified reference) and the small cases, several proofs in a row so that mode 2 replays its graph."""
     lib = nat.load()
     try:
         nat.check(lib.bp_ipa_set_graphs(mode))
+        nat.check(lib.bp_ipa_set_fast_rounds(fast))      # two-launch table rounds (k_ipa_round_prep + ticketed k_fb_msm) or the four-launch form
         for name in ("ipa_c2", "ipa_small"):
             for case in golden(name)["cases"]:
                 N = case["N"]
@@ -137,6 +139,7 @@ def test_ipa_prover_round_loop_modes(golden, mode):
                     assert p2_json(FastNIProver2(g, h, u, P2, a, b, secp256k1).prove()) == case["proof2"]
     finally:
         lib.bp_ipa_set_graphs(1)
+        lib.bp_ipa_set_fast_rounds(1)
 
 
 def test_ipa_soundness_smoke():

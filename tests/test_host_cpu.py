@@ -226,3 +226,32 @@ def test_host_c_range_proof_algebra_matches_python_formulas():
         assert (nat.unpack_scalars(vy, nm), nat.unpack_scalars(vh, nm), vd) == (yinv, hsc, delta)
     with pytest.raises(nat.BpGpuError):
         nat.rp_verifier_scalars(4, 1, 0, 5)                        # y = 0: "modular inverse does not exist"
+
+
+def test_host_xyzz_to_affine_matches_bigint():
+    """csrc/fp_host.h: the host finish of the IPA prover's L, R (XYZZ -> canonical affine, one shared inversion) against
+    big-int arithmetic: random re-projections of curve points (lazy residues up to 2^256 - 1 included) and the identity."""
+    import random
+    from oracle import ecc
+    P = ecc.P if hasattr(ecc, "P") else 2 ** 256 - 2 ** 32 - 977
+    rng = random.Random(99)
+    pts = [ecc.py_mul(ecc.G, rng.getrandbits(200) + 1) for _ in range(6)]
+    le = lambda v: int(v).to_bytes(32, "little")      # noqa: E731
+    for trial in range(20):
+        recs, want = [], []
+        cnt = rng.randrange(1, 9)
+        for i in range(cnt):
+            if rng.random() < 0.2:
+                recs.append(le(rng.getrandbits(256)) + le(rng.getrandbits(256)) + le(0 if rng.random() < 0.5 else P) + le(rng.getrandbits(256)))
+                want.append(bytes(64))
+                continue
+            x, y = pts[rng.randrange(6)]
+            z = rng.randrange(1, P)
+            zz, zzz = z * z % P, z * z * z % P
+            vals = [x * zz % P, y * zzz % P, zz, zzz]
+            vals = [v + P if rng.random() < 0.3 and v + P < 2 ** 256 else v for v in vals]       # non-canonical representatives
+            recs.append(b"".join(le(v) for v in vals))
+            want.append(le(x) + le(y))
+        out = ctypes.create_string_buffer(64 * cnt)
+        assert nat.load().bp_test_xyzz_to_affine_host(b"".join(recs), cnt, out) == 0
+        assert out.raw == b"".join(want), trial
