@@ -28,7 +28,7 @@ struct FbCache {
   size_t max_points = 4200;        // largest point set that gets a table (2049 of a 1024-wide IPA, 2 * 2048 + 1 commitments)
   int mode = 1;
   unsigned long long clock = 0, hits = 0, builds = 0;
-  DevBuf scratch, blockpart;
+  DevBuf scratch, blockpart, tickets;
 };
 static FbCache fb;
 
@@ -146,11 +146,32 @@ static int fb_msm_run(const Affine* tab, const u32* d_idx, const Fq* d_sc, const
   return 0;
 }
 
+// The same for a caller that wants the results in HOST memory right away (commitments and statements of a prover: a handful of
+// MSMs, each a latency chain): ONE launch -- the last block of every MSM reduces the block sums (ticket) and writes the XYZZ sum
+// into mapped pinned memory -- and the host finishes the affine conversion (fp_host.h: ~2 us against a ~45 us lone-thread
+// inversion on the device plus a second launch and a copy).
+static int fb_msm_run_host(const Affine* tab, const u32* d_idx, const Fq* d_sc, const u32* d_offsets, u32 nmsm, size_t max_terms,
+                           u32 single_n, uint8_t* out64) {
+  const u32 nbx = (u32)((max_terms + 31) / 32);
+  if (nbx == 0 || nmsm == 0) return 0;
+  XYZZ* part = (XYZZ*)fb.blockpart.ensure((size_t)nmsm * nbx * sizeof(XYZZ));
+  const bool fresh = fb.tickets.p == nullptr || fb.tickets.cap < nmsm * sizeof(u32);
+  u32* ticket = (u32*)fb.tickets.ensure(nmsm * sizeof(u32));
+  uint8_t* hx = g.pinned2((size_t)nmsm * 128);
+  if (!part || !ticket || !hx) return fail("workspace allocation failed");
+  if (fresh) BP_CUDA(cudaMemsetAsync(ticket, 0, fb.tickets.cap, g.stream));      // every launch leaves its tickets at zero
+  ++g.nlaunch, k_fb_msm<<<dim3(nbx, nmsm), 256, 0, g.stream>>>(tab, d_idx, d_sc, d_offsets, single_n, part, ticket, nullptr, (XYZZ*)hx);
+  BP_CUDA(cudaGetLastError());
+  BP_CUDA(cudaStreamSynchronize(g.stream));
+  for (u32 i = 0; i < nmsm; i += 8) xyzz_to_affine_host(hx + 128 * (size_t)i, nmsm - i < 8 ? nmsm - i : 8, out64 + 64 * (size_t)i);
+  return 0;
+}
+
 static void fb_release_all() {
   for (auto& kv : fb.tabs) cudaFree(kv.second.tab);
   for (auto& kv : fb.tabs16) cudaFree(kv.second.tab);
   fb.tabs16.clear(); fb.seen16.clear();
   fb.tabs.clear(); fb.seen.clear(); fb.bytes = 0;
-  fb.scratch.release(); fb.blockpart.release();
+  fb.scratch.release(); fb.blockpart.release(); fb.tickets.release();
 }
 

@@ -693,10 +693,7 @@ int bp_msm(const uint8_t* pts64, const uint8_t* sc32, size_t n, uint8_t out64[64
       Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
       if (!d_out) return fail("workspace allocation failed");
       BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
-      if (fb_msm_run(tab, nullptr, d_sc, nullptr, 1, n, (u32)n, d_out, nullptr)) return 1;
-      BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
-      BP_CUDA(cudaStreamSynchronize(g.stream));
-      return 0;
+      return fb_msm_run_host(tab, nullptr, d_sc, nullptr, 1, n, (u32)n, out64);
     }
   }
   MsmOpts opt;
@@ -864,6 +861,7 @@ int bp_msm_batch(const uint8_t* pts64, const uint8_t* sc32, const uint32_t* offs
       BP_CUDA(cudaMemcpyAsync(d_pts, pts64, maxlen * 64, cudaMemcpyHostToDevice, g.stream));
       const Affine* tab = fb_get(key, src, d_pts, maxlen);
       if (tab) {
+        if (nmsm <= 64) return fb_msm_run_host(tab, nullptr, d_sc, d_off, (u32)nmsm, maxlen, 0, out64);
         if (fb_msm_run(tab, nullptr, d_sc, d_off, (u32)nmsm, maxlen, 0, d_out, nullptr)) return 1;
         BP_CUDA(cudaMemcpyAsync(out64, d_out, nmsm * 64, cudaMemcpyDeviceToHost, g.stream));
         BP_CUDA(cudaStreamSynchronize(g.stream));

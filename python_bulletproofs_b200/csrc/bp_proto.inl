@@ -529,7 +529,8 @@ int bp_ipa_statement(const uint8_t* g64, const uint8_t* h64, const uint8_t u64_[
     const FbSrc src = {{u64_, g64, h64}, {64, n * 64, n * 64}, 3};
     tab = fb_get(src.hash(0x69706131ull), src, PA, T);
   }
-  if (tab ? fb_msm_run(tab, nullptr, d_sc, nullptr, 1, T, (u32)T, d_out, nullptr) : msm_run(PA, nullptr, d_sc, (u32)T, nullptr, 1, T, d_out, nullptr)) return 1;
+  if (tab) return fb_msm_run_host(tab, nullptr, d_sc, nullptr, 1, T, (u32)T, P_out64);
+  if (msm_run(PA, nullptr, d_sc, (u32)T, nullptr, 1, T, d_out, nullptr)) return 1;
   BP_CUDA(cudaMemcpyAsync(P_out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;

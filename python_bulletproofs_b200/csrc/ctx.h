@@ -194,6 +194,16 @@ struct Ctx {
     pin_bytes_cap = bytes;
     return pin_bytes_p;
   }
+  // second pinned block: XYZZ results of small table MSMs that the host finishes (fb_msm_run_host)
+  unsigned char* pin2_p = nullptr; size_t pin2_cap = 0;
+  unsigned char* pinned2(size_t bytes) {
+    if (bytes <= pin2_cap) return pin2_p;
+    if (pin2_p) cudaFreeHost(pin2_p);
+    pin2_p = nullptr; pin2_cap = 0;
+    if (cudaHostAlloc((void**)&pin2_p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    pin2_cap = bytes;
+    return pin2_p;
+  }
   unsigned* h_pin = nullptr;
   unsigned* pinned_u32() { if (!h_pin && cudaHostAlloc((void**)&h_pin, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h_pin = nullptr; } return h_pin; }
   void free_all() {
