@@ -26,6 +26,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the batch verifier's OpenMP workers must sleep, not spin, between chunks: with one process per GPU on a shared host the spinning
+# pools starve each other (read by libgomp when it is loaded, so it has to be set before any import that pulls it in)
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 
 GX = 0x79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798
 GY = 0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8
@@ -324,7 +327,7 @@ def run_ours(args):
             "strong_scaling": {"scaling": "strong", "note": "one MSM of terms_total terms cut into contiguous slices, one per GPU; "
                                "slice MSM + ncclAllGather of the 128-byte partials + sum, max over ranks", "points": strong}}
 
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not os.environ.get("BP_BENCH_NO_SWEEP"):      # (left out under ncu: tools/ncu_metrics.sh)
         line["sweep"] = msm_sweep(lib, nat, pts, hs, args.lgn, not args.no_precompute)
         line["cpu_baseline"], bit_exact = cpu_baseline(pts, sc, n, result_hex)
         line["bit_exact_vs_oracle"] = bit_exact
