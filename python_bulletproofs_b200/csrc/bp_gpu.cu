@@ -93,37 +93,34 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
 // Per-call options of msm_run (passed by value: nothing a failed call could leave behind for the next one).
 //   skip_below  terms whose point index is below this count as zero scalars (the caller evaluates them elsewhere, see k_digits)
 //   pts_ready   event the points are complete at (host-operand MSM whose points upload on the copy stream)
-//   halves      the points arrive in two parts (g.ev_half[0], g.ev_half[1]), the first `split` terms first (upload_operands)
-struct MsmOpts { u32 skip_below = 0; cudaEvent_t pts_ready = nullptr; bool halves = false; size_t split = 0; };
+//   halves      the points arrive in `parts` equal parts (g.ev_half[0 .. parts-1], upload_operands)
+struct MsmOpts { u32 skip_below = 0; cudaEvent_t pts_ready = nullptr; bool halves = false; int parts = 0; };
 int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, const u32* d_offsets, u32 nmsm,
             size_t terms_per_msm, Affine* out_affine, XYZZ* out_xyzz, MsmOpts opt = MsmOpts()) {
   if (nmsm == 1 && T >= g.pipeline_min_terms && !g.profiling) {
     if (opt.pts_ready) BP_CUDA(cudaStreamWaitEvent(g.stream, opt.pts_ready, 0));
-    if (opt.halves) BP_CUDA(cudaStreamWaitEvent(g.stream, g.ev_half[1], 0));
+    if (opt.halves) BP_CUDA(cudaStreamWaitEvent(g.stream, g.ev_half[opt.parts - 1], 0));
     return msm_run_pipelined(points, point_idx, scalars, T, out_affine, out_xyzz);
   }
   cudaStream_t st = g.stream;
-  // host-operand MSM whose points are still arriving in two halves (upload_operands): run it as TWO half-size MSMs over one
-  // digit/sort pass -- buckets (half, unit, digit) -- accumulate the first half while the second is on the wire, reduce both
-  // in one batch of tails and add the two results
-  const bool halves = opt.halves && nmsm == 1 && !point_idx && !d_offsets && T >= 4;
-  if (opt.halves && !halves) BP_CUDA(cudaStreamWaitEvent(st, g.ev_half[1], 0));      // (cannot happen today: such MSMs have >= 2^17 terms)
-  const u32 T_half = halves && opt.split > 0 && opt.split < T ? (u32)opt.split : T / 2;   // terms in the first part
-  XYZZ* pair_out = nullptr;
-  Affine* final_affine = out_affine; XYZZ* final_xyzz = out_xyzz;
+  // host-operand MSM whose points are still arriving in K parts (upload_operands): ONE digit/sort pass with the part as the major
+  // sort key -- bucket ids (part, unit, digit) -- then one accumulation per part as it lands, all parts adding into the SAME
+  // bucket values (k_accumulate's `into`), so the reduction and combination are those of a single MSM
+  const bool halves = opt.halves && nmsm == 1 && !point_idx && !d_offsets && T >= 64 && opt.parts >= 2 && opt.parts <= 8;
+  if (opt.halves && !halves) BP_CUDA(cudaStreamWaitEvent(st, g.ev_half[opt.parts - 1], 0));      // (cannot happen today: such MSMs have >= 2^17 terms)
+  const u32 K = halves ? (u32)opt.parts : 1;
+  u32 h_ho[9];
+  for (u32 k = 0; k <= K; k++) h_ho[k] = (u32)((unsigned long long)T * k / K);      // part k = terms [h_ho[k], h_ho[k+1])
   if (halves) {
-    u32* d_ho = (u32*)g.ws_halfoff.ensure(4 * sizeof(u32) + 2 * sizeof(XYZZ));
+    u32* d_ho = (u32*)g.ws_halfoff.ensure(16 * sizeof(u32));
     if (!d_ho) return fail("workspace allocation failed");
-    const u32 h_ho[3] = {0, T_half, T};
-    BP_CUDA(cudaMemcpyAsync(d_ho, h_ho, sizeof h_ho, cudaMemcpyHostToDevice, st));    // (pageable 12-byte copy: staged by the driver)
-    d_offsets = d_ho; nmsm = 2; terms_per_msm = T_half;
-    pair_out = (XYZZ*)(d_ho + 4);
-    out_affine = nullptr; out_xyzz = pair_out;
+    BP_CUDA(cudaMemcpyAsync(d_ho, h_ho, (K + 1) * sizeof(u32), cudaMemcpyHostToDevice, st));    // (pageable copy: staged by the driver)
+    d_offsets = d_ho; nmsm = K; terms_per_msm = (T + K - 1) / K;
   }
   MsmShape sh = msm_shape(terms_per_msm, nmsm, g.force_c);
   g.last_c = sh.c;
-  g.last_nb = (size_t)nmsm * sh.U * sh.H;
-  size_t nmw = (size_t)nmsm * sh.U, nb = nmw * sh.H;
+  g.last_nb = (size_t)(halves ? 1 : nmsm) * sh.U * sh.H;
+  size_t nmw = (size_t)nmsm * sh.U, nb = nmw * sh.H;      // bucket ids of the sort (K parts: K * hb)
   bool prof = g.profiling;
   if (prof) for (int i = 0; i < 7; i++) cudaEventRecord(g.ev[i], st), (void)0;
   if (T == 0) {   // all identities
@@ -141,13 +138,14 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   u32* cursor = (u32*)g.ws_cursor.ensure((nb + 1) * sizeof(u32));
   size_t ntiles = (nb + 1 + BP_SCAN_TILE - 1) / BP_SCAN_TILE;
   u32* tiles = (u32*)g.ws_tiles.ensure(ntiles * sizeof(u32));
-  XYZZ* buckets = (XYZZ*)g.ws_buckets.ensure(nb * sizeof(XYZZ));
+  const size_t nbv = halves ? nb / K : nb;                  // bucket VALUES (the K parts share one set)
+  XYZZ* buckets = (XYZZ*)g.ws_buckets.ensure(nbv * sizeof(XYZZ));
   XYZZ* segsum = (XYZZ*)g.ws_segsum.ensure(nmw * sh.nseg * sizeof(XYZZ));
   XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure(nmw * sizeof(XYZZ));
   // every (term, window) pair is at most one entry, so E <= W*T: size the chunk structures for the bound
   size_t emax = (size_t)sh.W * 2 * T, nchunks = (emax + sh.chunk - 1) / sh.chunk;
-  const size_t hchunks = ((size_t)sh.W * 2 * (T - T_half > T_half ? T - T_half : T_half) + sh.chunk - 1) / sh.chunk + 1;      // per part (the larger one)
-  XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * (halves ? 2 * hchunks : nchunks) * sizeof(XYZZ));
+  const size_t hchunks = ((size_t)sh.W * 2 * ((T + K - 1) / K + 1) + sh.chunk - 1) / sh.chunk + 1;      // per part
+  XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * (halves ? K * hchunks : nchunks) * sizeof(XYZZ));
   const u32 big_cap = (u32)(emax / ((size_t)sh.chunk * (BP_FIXUP_SERIAL_MAX - 1)) + 16);      // buckets that can span that many chunks
   u32* big = (u32*)g.ws_big.ensure((2 * (size_t)big_cap + 4) * sizeof(u32));
   u32* zero_word = big + 2 * (size_t)big_cap + 3;
@@ -156,6 +154,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
 
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
   if (prof) cudaEventRecord(g.ev[0], st);
+  g.dbg_rec(4, st);
   ++g.nlaunch, k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count, opt.skip_below ? point_idx : nullptr, opt.skip_below);
   if (prof) cudaEventRecord(g.ev[1], st);
   ++g.nlaunch, k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
@@ -165,24 +164,26 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));   // cursors start at the bucket offsets
   ++g.nlaunch, k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, cursor, entries);
   if (prof) cudaEventRecord(g.ev[3], st);
-  BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));          // empty buckets = identity (ZZ = 0)
+  g.dbg_rec(5, st);
+  BP_CUDA(cudaMemsetAsync(buckets, 0, nbv * sizeof(XYZZ), st));         // empty buckets = identity (ZZ = 0)
   BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
   BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));   // [0] = queue length, kept zero word for gs = 0 lives at big[big_cap + 1]
   if (halves) {
-    const size_t hb = (size_t)sh.U * sh.H;                  // buckets of one half; entries of half k are [start[k*hb], start[(k+1)*hb])
-    for (int k = 0; k < 2; k++) {
-      const u32 t0 = k ? T_half : 0, tn = k ? T - T_half : T_half;
-      BP_CUDA(cudaStreamWaitEvent(st, g.ev_half[k], 0));    // this half of the points has landed
+    const size_t hb = (size_t)sh.U * sh.H;                  // buckets of one part; entries of part k are [start[k*hb], start[(k+1)*hb])
+    for (u32 k = 0; k < K; k++) {
+      const u32 t0 = h_ho[k], tn = h_ho[k + 1] - h_ho[k];
+      BP_CUDA(cudaStreamWaitEvent(st, g.ev_half[k], 0));    // this part of the points has landed
       ++g.nlaunch, k_phi<<<(tn + 127) / 128, 128, 0, st>>>(points + t0, nullptr, tn, phi + t0);
-      const u32* gs = k ? start + hb : zero_word;
+      const u32* gs = k ? start + k * hb : zero_word;
       XYZZ* part_k = part + 2 * (size_t)k * hchunks;
       if (prof && k == 0) cudaEventRecord(g.ev_k0, st);
-      ++g.nlaunch, k_accumulate<<<(unsigned)((hchunks + 127) / 128), 128, 0, st>>>(points, nullptr, phi, start, entries, gs, start + (k + 1) * hb, sh.chunk, buckets, part_k);
-      if (prof && k == 1) cudaEventRecord(g.ev_k1, st);
-      if (k == 1) BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));
-      ++g.nlaunch, k_fixup<<<(unsigned)((hb + 127) / 128), 128, 0, st>>>(start, k * hb, hb, gs, sh.chunk, part_k, buckets, big, big_cap);
-      ++g.nlaunch, k_fixup_mid<<<2 * g.sm_count, 256, 0, st>>>(start, gs, sh.chunk, part_k, buckets, big, big_cap);
-      ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, gs, sh.chunk, part_k, buckets, big);
+      ++g.nlaunch, k_accumulate<<<(unsigned)((hchunks + 127) / 128), 128, 0, st>>>(points, nullptr, phi, start, entries, gs, start + (k + 1) * hb, sh.chunk, buckets, part_k, (u32)hb, k ? 1 : 0);
+      if (prof && k == K - 1) cudaEventRecord(g.ev_k1, st);
+      if (k) BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));
+      ++g.nlaunch, k_fixup<<<(unsigned)((hb + 127) / 128), 128, 0, st>>>(start, k * hb, hb, gs, sh.chunk, part_k, buckets, big, big_cap, (u32)hb);
+      ++g.nlaunch, k_fixup_mid<<<2 * g.sm_count, 256, 0, st>>>(start, gs, sh.chunk, part_k, buckets, big, big_cap, (u32)hb);
+      ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, gs, sh.chunk, part_k, buckets, big, (u32)hb);
+      g.dbg_rec(6 + (k == K - 1 ? 1 : 0), st);
     }
   } else {
     if (opt.pts_ready) BP_CUDA(cudaStreamWaitEvent(st, opt.pts_ready, 0));   // points may still be uploading
@@ -196,8 +197,7 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big);
   }
   if (prof) cudaEventRecord(g.ev[4], st);
-  if (msm_tails(buckets, sh, nmsm, out_affine, out_xyzz, prof, st)) return 1;
-  if (halves) ++g.nlaunch, k_xyzz_pair<<<1, 32, 0, st>>>(pair_out, final_affine, final_xyzz);      // result = half 0 + half 1
+  if (msm_tails(buckets, sh, halves ? 1 : nmsm, out_affine, out_xyzz, prof, st)) return 1;
   if (prof) cudaEventRecord(g.ev[6], st);
   BP_CUDA(cudaGetLastError());
   return 0;
@@ -422,28 +422,49 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
 // Host operands -> device: scalars first on the compute stream (the digit/sort stages only need them), points on a
 // second stream so that their (twice as large) upload overlaps those stages; msm_run waits for the points right
 // before the first kernel that reads them.  The pipelined/profiling paths simply wait up front.
+// Large host -> device copies go down in pieces: on the B200 hosts measured here one cudaMemcpyAsync of 32-96 MiB from pinned
+// memory runs at 18-38 GB/s, the same bytes as <= 8 MiB copies back to back at 52 GB/s (tools/h2d_probe.py, profiles/r2_h2d_probe.txt).
+static size_t h2d_piece() {
+  static const size_t v = [] { const char* e = getenv("BP_H2D_PIECE_MIB"); long m = e ? atol(e) : 6; return (size_t)(m > 0 ? m : 6) << 20; }();
+  return v;
+}
+static cudaError_t h2d_chunked(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  const size_t piece = h2d_piece();
+  for (size_t off = 0; off < bytes; off += piece) {
+    const size_t len = bytes - off < piece ? bytes - off : piece;
+    cudaError_t e = cudaMemcpyAsync((char*)dst + off, (const char*)src + off, len, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
 static int upload_operands(Affine* d_pts, const uint8_t* pts64, Fq* d_sc, const uint8_t* sc32, size_t n, MsmOpts* opt) {
   *opt = MsmOpts();
   BP_CUDA(cudaEventRecord(g.ev_copy_gate, g.stream));                     // earlier work may still read d_pts
   BP_CUDA(cudaStreamWaitEvent(g.copy_stream, g.ev_copy_gate, 0));
   if (n >= ((size_t)1 << 17) && g.force_c == 0 && !g.profiling && n < g.pipeline_min_terms) {
-    // big MSM: everything on the copy stream in the order it is needed -- scalars, first half of the points, second half --
-    // each at full link speed; msm_run sorts as soon as the scalars are in and accumulates half by half (see there)
-    // first part 3/8 of the points: its accumulation then ends about when the rest has landed (measured link / kernel rates)
-    const size_t h = n * 3 / 8;
-    opt->split = h;
-    BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.copy_stream));
+    // big MSM: everything on the copy stream in the order it is needed -- scalars, then the points in K equal parts -- msm_run
+    // sorts as soon as the scalars are in and accumulates part by part into one set of buckets (see there).  K = 4: the
+    // accumulation of a quarter (0.49 ms) roughly matches its upload (0.44 ms at the 36-38 GB/s this host sustains), so the GPU
+    // neither waits for the last part nor starts late (profiles/r2_e2e_timeline.txt)
+    static const int parts = [] { const char* e = getenv("BP_E2E_PARTS"); int v = e ? atoi(e) : 4; return v >= 2 && v <= 8 ? v : 4; }();
+    opt->parts = parts;
+    g.dbg_rec(0, g.copy_stream);
+    BP_CUDA(h2d_chunked(d_sc, sc32, n * 32, g.copy_stream));
+    g.dbg_rec(1, g.copy_stream);
     BP_CUDA(cudaEventRecord(g.ev_sc, g.copy_stream));
-    BP_CUDA(cudaMemcpyAsync(d_pts, pts64, h * 64, cudaMemcpyHostToDevice, g.copy_stream));
-    BP_CUDA(cudaEventRecord(g.ev_half[0], g.copy_stream));
-    BP_CUDA(cudaMemcpyAsync(d_pts + h, pts64 + h * 64, (n - h) * 64, cudaMemcpyHostToDevice, g.copy_stream));
-    BP_CUDA(cudaEventRecord(g.ev_half[1], g.copy_stream));
+    for (int k = 0; k < parts; k++) {                      // part k = terms [n*k/K, n*(k+1)/K)  (the same cut as msm_run's)
+      const size_t lo = (size_t)((unsigned long long)n * k / parts), hi = (size_t)((unsigned long long)n * (k + 1) / parts);
+      BP_CUDA(h2d_chunked(d_pts + lo, pts64 + lo * 64, (hi - lo) * 64, g.copy_stream));
+      BP_CUDA(cudaEventRecord(g.ev_half[k], g.copy_stream));
+      if (k == 0) g.dbg_rec(2, g.copy_stream);
+      if (k == parts - 1) g.dbg_rec(3, g.copy_stream);
+    }
     BP_CUDA(cudaStreamWaitEvent(g.stream, g.ev_sc, 0));
     opt->halves = true;
     return 0;
   }
-  BP_CUDA(cudaMemcpyAsync(d_sc, sc32, n * 32, cudaMemcpyHostToDevice, g.stream));
-  BP_CUDA(cudaMemcpyAsync(d_pts, pts64, n * 64, cudaMemcpyHostToDevice, g.copy_stream));
+  BP_CUDA(h2d_chunked(d_sc, sc32, n * 32, g.stream));
+  BP_CUDA(h2d_chunked(d_pts, pts64, n * 64, g.copy_stream));
   BP_CUDA(cudaEventRecord(g.ev_pts, g.copy_stream));
   opt->pts_ready = g.ev_pts;
   return 0;
@@ -613,7 +634,7 @@ int bp_init(int device) {
   BP_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
   BP_CUDA(cudaEventCreateWithFlags(&g.ev_pts, cudaEventDisableTiming)); BP_CUDA(cudaEventCreateWithFlags(&g.ev_copy_gate, cudaEventDisableTiming));
   BP_CUDA(cudaEventCreateWithFlags(&g.ev_sc, cudaEventDisableTiming));
-  for (int i = 0; i < 2; i++) BP_CUDA(cudaEventCreateWithFlags(&g.ev_half[i], cudaEventDisableTiming));
+  for (int i = 0; i < 8; i++) BP_CUDA(cudaEventCreateWithFlags(&g.ev_half[i], cudaEventDisableTiming));
   g.inited = true;
   return 0;
 }

@@ -971,10 +971,19 @@ int bp_msm_sharded_host(const uint8_t* pts64, const uint8_t* sc32, size_t n, uin
   Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
   if (!d_pts || !d_sc || !d_out) return fail("device allocation failed");
   MsmOpts opt;
+  g.dbg_e2e = getenv("BP_E2E_TIMING") != nullptr;
   if (n && upload_operands(d_pts, pts64, d_sc, sc32, n, &opt)) return 1;
   if (msm_sharded_device(d_pts, d_sc, n, d_out, opt)) { cudaStreamSynchronize(g.copy_stream); return 1; }
+  g.dbg_rec(8, g.stream);
   BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
+  if (g.dbg_e2e && opt.halves) {
+    float t[9] = {0};
+    for (int i = 1; i < 9; i++) if (g.dbg_ev[i]) cudaEventElapsedTime(&t[i], g.dbg_ev[0], g.dbg_ev[i]);
+    fprintf(stderr, "e2e timeline (ms from copy start): scalars in %.3f | points part 0 in %.3f | part 1 in %.3f || digits start %.3f | sorted %.3f | acc 0 done %.3f | acc 1 done %.3f | result %.3f\n",
+            t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]);
+    g.dbg_e2e = false;
+  }
   return 0;
 }
 

@@ -265,7 +265,10 @@ BP_DI const Affine* entry_point_ptr(const Affine* __restrict__ points, const u32
 __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* __restrict__ points, const u32* __restrict__ point_idx, const Affine* __restrict__ phi,
                                                     const u32* __restrict__ bucket_start, const uint2* __restrict__ entries,
                                                     const u32* __restrict__ gs_ptr, const u32* __restrict__ ge_ptr, u32 CL,
-                                                    XYZZ* __restrict__ buckets, XYZZ* __restrict__ part) {
+                                                    XYZZ* __restrict__ buckets, XYZZ* __restrict__ part, u32 hb = 0, int into = 0) {
+  // hb / into: a host-operand MSM whose points arrive in K parts is sorted as K MSMs -- bucket id (part, unit, digit), hb
+  // buckets per part -- but all parts accumulate into ONE set of hb bucket values: the value of bucket id b lives at b % hb, and
+  // from the second part on (into = 1) the first piece of every bucket starts from the stored value instead of the identity.
   // entry range [gs, ge) of this launch (all windows, or one window of the pipelined single-MSM path); both bounds
   // are bucket_start[] words, read on the device so that no host round trip separates the sort from the accumulation
   u32 chunk = blockIdx.x * blockDim.x + threadIdx.x;
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* _
   u32 s = __ldg(bucket_start + b), e = __ldg(bucket_start + b + 1);
   bool first = true;
   XYZZ acc = xyzz_identity();
+  if (into && s >= cs) acc = ld_xyzz(buckets + b % hb);                  // this chunk holds the first piece of bucket b
 #if BP_ACC_PIPELINE
   // software pipeline: the point of entry i+1 is loaded into registers while the mixed addition of entry i runs
   Affine pnext = ld_affine(entry_point_ptr(points, point_idx, phi, ent.x));
@@ -287,10 +291,10 @@ __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* _
   for (u32 i = cs; i < ce; i++) {
     if (i == e) {                                                      // previous run is complete
       if (first && s < cs) st_xyzz(part + 2 * (size_t)chunk, acc);     // it began in an earlier chunk
-      else st_xyzz(buckets + b, acc);                                  // whole bucket inside this chunk
+      else st_xyzz(buckets + (hb ? b % hb : b), acc);                  // whole bucket inside this chunk
       first = false;
-      acc = xyzz_identity();
       b = ent.y;                                                       // next non-empty bucket (ent = entries[i])
+      acc = into ? ld_xyzz(buckets + b % hb) : xyzz_identity();
       s = e; e = __ldg(bucket_start + b + 1);
     }
     u32 cur = ent.x;
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* _
   }
   if (e > ce) st_xyzz(part + 2 * (size_t)chunk + (first ? 0 : 1), acc);   // run continues in the next chunk
   else if (first && s < cs) st_xyzz(part + 2 * (size_t)chunk, acc);
-  else st_xyzz(buckets + b, acc);
+  else st_xyzz(buckets + (hb ? b % hb : b), acc);
 }
 
 // s, c0, c are relative to the launch's first entry gs
@@ -327,7 +331,7 @@ BP_DI const XYZZ* bucket_piece(const XYZZ* part, u32 s, u32 c0, u32 c, u32 CL) {
 // queue layout (u32 words): [0] big count, [1] mid count, [2 .. 2+cap) big list, [2+cap .. 2+2cap) mid list
 #define BP_FIXUP_WARP_MAX 2048
 __global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_start, size_t b0, size_t nb, const u32* __restrict__ gs_ptr, u32 CL,
-                                               const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, u32* __restrict__ queue, u32 cap) {
+                                               const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, u32* __restrict__ queue, u32 cap, u32 hb = 0) {
   u32* big_count = queue; u32* mid_count = queue + 1; u32* big_list = queue + 2; u32* mid_list = queue + 2 + cap;
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
@@ -342,12 +346,12 @@ __global__ void __launch_bounds__(128) k_fixup(const u32* __restrict__ bucket_st
   if (c1 - c0 >= BP_FIXUP_SERIAL_MAX) { mid_list[atomicAdd(mid_count, 1u)] = (u32)b; return; }
   XYZZ acc = ld_xyzz(bucket_piece(part, s, c0, c0, CL));
   for (u32 c = c0 + 1; c <= c1; c++) { XYZZ v = ld_xyzz(bucket_piece(part, s, c0, c, CL)); xyzz_add(acc, v); }
-  st_xyzz(buckets + b, acc);
+  st_xyzz(buckets + (hb ? b % hb : b), acc);
 }
 
 // persistent warps over the queue of medium buckets: 32 lanes stride over the pieces, tree in shared memory
 __global__ void __launch_bounds__(256) k_fixup_mid(const u32* __restrict__ bucket_start, const u32* __restrict__ gs_ptr, u32 CL,
-                                                   const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, const u32* __restrict__ queue, u32 cap) {
+                                                   const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, const u32* __restrict__ queue, u32 cap, u32 hb = 0) {
   __shared__ XYZZ sm[8][32];
   const u32 n = queue[1], warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32* mid_list = queue + 2 + cap;
@@ -364,14 +368,14 @@ __global__ void __launch_bounds__(256) k_fixup_mid(const u32* __restrict__ bucke
       if ((int)lane < off) { XYZZ v = sm[warp][lane + off]; xyzz_add_ni(acc, v); sm[warp][lane] = acc; }
       __syncwarp();
     }
-    if (lane == 0) st_xyzz(buckets + b, acc);
+    if (lane == 0) st_xyzz(buckets + (hb ? b % hb : b), acc);
     __syncwarp();
   }
 }
 
 // persistent blocks over the queue of giant buckets: 256 threads stride over the pieces, tree in shared memory
 __global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucket_start, const u32* __restrict__ gs_ptr, u32 CL,
-                                                   const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, const u32* __restrict__ queue) {
+                                                   const XYZZ* __restrict__ part, XYZZ* __restrict__ buckets, const u32* __restrict__ queue, u32 hb = 0) {
   __shared__ XYZZ sm[256];
   const u32* big_list = queue + 2;
   u32 n = queue[0];
@@ -388,7 +392,7 @@ __global__ void __launch_bounds__(256) k_fixup_big(const u32* __restrict__ bucke
       if (threadIdx.x < off) { XYZZ v = sm[threadIdx.x + off]; xyzz_add_ni(acc, v); sm[threadIdx.x] = acc; }
       __syncthreads();
     }
-    if (threadIdx.x == 0) st_xyzz(buckets + b, acc);
+    if (threadIdx.x == 0) st_xyzz(buckets + (hb ? b % hb : b), acc);
     __syncthreads();
   }
 }
