@@ -553,7 +553,7 @@ struct RpStats { double wall_ms = 0, host_ms = 0, gpu_ms = 0; unsigned chunks = 
 static RpStats g_rp_stats;
 // chunk lengths of a batch: the host checks of the FIRST chunk are the only ones the GPU cannot hide, and every chunk pays
 // fixed latency chains (inversions, the 96-doubling tails), so: a short first chunk, then growing ones, at most 4096 proofs
-static void rp_chunk_plan(size_t nproofs, bool tables, std::vector<size_t>& lens) {
+static void rp_chunk_plan(size_t nproofs, bool tables, unsigned nthreads, std::vector<size_t>& lens) {
   lens.clear();
   if (const char* e = getenv("BP_VERIFY_CHUNK")) {
     size_t ch = (size_t)atol(e); if (ch == 0) ch = 1;
@@ -561,11 +561,16 @@ static void rp_chunk_plan(size_t nproofs, bool tables, std::vector<size_t>& lens
     return;
   }
   if (!tables) { const size_t ch = nproofs < 4096 ? nproofs : 2048; for (size_t lo = 0; lo < nproofs; lo += ch) lens.push_back(nproofs - lo < ch ? nproofs - lo : ch); return; }
-  if (nproofs < 512) { lens.push_back(nproofs); return; }
-  if (nproofs <= 2048) {   // latency regime (measured: every chunk costs ~0.7 ms of dependent kernels): two chunks, so that the
-                           // host checks of the second run under the first one's device work
-    const size_t a = (nproofs / 4 + 63) & ~(size_t)63;
-    lens.push_back(a); lens.push_back(nproofs - a);
+  // latency regime: every chunk costs ~0.8 ms of dependent kernels.  The host work in front of a chunk is only the staging pass
+  // (~1.5 us per proof per core; the transcript verdicts run after the last chunk is enqueued), so a small batch is ONE chunk
+  // (measured, 16 threads: 512 / 1024 / 2048 proofs as one chunk 0.96 / 1.48 / 2.31 ms, as 1/4 + 3/4 1.02 / 1.49 / 2.38 ms)
+  // -- unless few host threads make that staging pass itself long (one process per GPU sharing the host: 4 threads, 1024 proofs =
+  // 0.38 ms before the GPU starts): then a first quarter gets the device going (1.47 against 1.53 ms)
+  if (nproofs <= 2048) {
+    if (nproofs >= 512 && (double)nproofs * 1.5 / (double)(nthreads ? nthreads : 1) > 200.0) {
+      const size_t a = (nproofs / 4 + 63) & ~(size_t)63;
+      lens.push_back(a); lens.push_back(nproofs - a);
+    } else lens.push_back(nproofs);
     return;
   }
   size_t left = nproofs, next = nproofs / 8 < 256 ? 256 : (nproofs / 8 > 1024 ? 1024 : nproofs / 8);
@@ -599,20 +604,6 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
                oa = 544, ob = 576, oXs = 608, oLs = oXs + 32 * L, oRs = oLs + 64 * L;
   // The batch is cut into chunks: while the GPU evaluates the equations of chunk i, the host threads run the
   // transcript checks of chunk i+1 (pinned, double-buffered staging so the uploads are truly asynchronous).
-  std::vector<size_t> chunk_len;
-  rp_chunk_plan(nproofs, fb_enabled(), chunk_len);
-  size_t CH = 1;
-  for (size_t l : chunk_len) if (l > CH) CH = l;
-  const size_t sc_bytes = CH * lay.nsc * 32, pt_bytes = CH * lay.npt * 64, ok_bytes = (CH + 63) & ~(size_t)63;
-  const size_t stage_each = sc_bytes + pt_bytes + ok_bytes;
-  uint8_t* stage = g.pinned_stage(2 * stage_each + (gather_out ? (size_t)g_nranks * gather_width + 64 : 0));
-  if (!stage) return fail("pinned staging allocation failed");
-  uint8_t* hsc_buf[2] = {stage, stage + stage_each};
-  uint8_t* hpt_buf[2] = {stage + sc_bytes, stage + stage_each + sc_bytes};
-  uint8_t* hok_buf[2] = {stage + sc_bytes + pt_bytes, stage + stage_each + sc_bytes + pt_bytes};   // host verdicts of the chunk
-  size_t chunk_lo = 0;
-  int cur = 0;
-  // ---- host: transcript checks + challenge extraction, threaded over proofs --------------------
   unsigned nthreads = std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
   if (const char* lws = getenv("LOCAL_WORLD_SIZE")) {      // one process per GPU on a shared host (torchrun): share the cores
@@ -621,7 +612,27 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
     if (w > 1) nthreads = nthreads / (unsigned)w ? nthreads / (unsigned)w : 1;
   }
   if (nthreads > 64) nthreads = 64;
-  auto work = [&](size_t lo, size_t hi) {
+  std::vector<size_t> chunk_len;
+  rp_chunk_plan(nproofs, fb_enabled(), nthreads, chunk_len);
+  size_t CH = 1;
+  for (size_t l : chunk_len) if (l > CH) CH = l;
+  const size_t sc_bytes = CH * lay.nsc * 32, pt_bytes = CH * lay.npt * 64, ok_bytes = (CH + 63) & ~(size_t)63;
+  const size_t stage_each = sc_bytes + pt_bytes + ok_bytes;
+  const size_t hok_bytes = (nproofs + 63) & ~(size_t)63;
+  uint8_t* stage = g.pinned_stage(2 * stage_each + hok_bytes + (gather_out ? (size_t)g_nranks * gather_width + 64 : 0));
+  if (!stage) return fail("pinned staging allocation failed");
+  uint8_t* hok_all = stage + 2 * stage_each;                // host verdicts of the whole batch (verdict pass, after the chunk loop)
+  uint8_t* hsc_buf[2] = {stage, stage + stage_each};
+  uint8_t* hpt_buf[2] = {stage + sc_bytes, stage + stage_each + sc_bytes};
+  size_t chunk_lo = 0;
+  int cur = 0;
+  // ---- host: transcript checks + challenge extraction, threaded over proofs --------------------
+  // Two passes over a proof.  stage_pass: what the DEVICE needs -- proof points and scalars into the pinned staging buffers, y, z, x
+  // parsed from their transcript slots, x1 re-derived (one hash) -- ~1.5 us per proof, on the critical path in front of the chunk's
+  // upload.  Otherwise: the VERDICT of the reference's three verify_transcript methods (base64 comparisons, the running hash of every
+  // IPA round), ~3 us per proof, which nothing on the device waits for: it runs after all chunks are enqueued, underneath the
+  // device work, and is merged into the accept bytes at the end (k_rp_merge_host).
+  auto work = [&](size_t lo, size_t hi, bool stage_pass) {
     // no heap traffic per proof: slots are (offset, length) pairs in a small stack array, points and scalars are compared in
     // place (b64_point_eq / decimal_slot_eq) instead of through std::string round trips
     struct Slot { size_t first, second; };
@@ -643,21 +654,33 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
     };
     for (size_t p = lo; p < hi; p++) {
       const uint8_t* pr = proofs + p * proof_stride;
-      uint8_t* sc = hsc_buf[cur] + (p - chunk_lo) * lay.nsc * 32;
-      uint8_t* pt = hpt_buf[cur] + (p - chunk_lo) * lay.npt * 64;
-      memcpy(pt + 64 * RP_V, pr + oV, 64); memcpy(pt + 64 * RP_A, pr + oA, 64); memcpy(pt + 64 * RP_S, pr + oS, 64);
-      memcpy(pt + 64 * RP_T1, pr + oT1, 64); memcpy(pt + 64 * RP_T2, pr + oT2, 64);
-      memcpy(pt + 64 * RP_UNEW, pr + oUnew, 64); memcpy(pt + 64 * RP_PNEW, pr + oPnew, 64);
-      memcpy(pt + 64 * RP_LS, pr + oLs, 64 * L); memcpy(pt + 64 * (RP_LS + L), pr + oRs, 64 * L);
-      memcpy(sc + 32 * RS_THAT, pr + oThat, 32); memcpy(sc + 32 * RS_TAUX, pr + oTaux, 32); memcpy(sc + 32 * RS_MU, pr + oMu, 32);
-      memcpy(sc + 32 * RS_A, pr + oa, 32); memcpy(sc + 32 * RS_B, pr + ob, 32);
-      memcpy(sc + 32 * RS_XS, pr + oXs, 32 * L);
-      uint8_t verdict = 1;
       Slot* sl = nullptr;
-      // --- RangeVerifier.verify_transcript                         rangeproof_verifier.py:42-53
       const uint8_t* t0 = transcripts + tr_off[3 * p];
-      size_t t0n = tr_off[3 * p + 1] - tr_off[3 * p];
+      const size_t t0n = tr_off[3 * p + 1] - tr_off[3 * p];
+      const uint8_t* t1 = transcripts + tr_off[3 * p + 1];
+      const size_t t1n = tr_off[3 * p + 2] - tr_off[3 * p + 1];
       Fq y = fq_one(), z = fq_one(), x = fq_one(), x1 = fq_one();
+      if (stage_pass) {
+        uint8_t* sc = hsc_buf[cur] + (p - chunk_lo) * lay.nsc * 32;
+        uint8_t* pt = hpt_buf[cur] + (p - chunk_lo) * lay.npt * 64;
+        memcpy(pt + 64 * RP_V, pr + oV, 64); memcpy(pt + 64 * RP_A, pr + oA, 64); memcpy(pt + 64 * RP_S, pr + oS, 64);
+        memcpy(pt + 64 * RP_T1, pr + oT1, 64); memcpy(pt + 64 * RP_T2, pr + oT2, 64);
+        memcpy(pt + 64 * RP_UNEW, pr + oUnew, 64); memcpy(pt + 64 * RP_PNEW, pr + oPnew, 64);
+        memcpy(pt + 64 * RP_LS, pr + oLs, 64 * L); memcpy(pt + 64 * (RP_LS + L), pr + oRs, 64 * L);
+        memcpy(sc + 32 * RS_THAT, pr + oThat, 32); memcpy(sc + 32 * RS_TAUX, pr + oTaux, 32); memcpy(sc + 32 * RS_MU, pr + oMu, 32);
+        memcpy(sc + 32 * RS_A, pr + oa, 32); memcpy(sc + 32 * RS_B, pr + ob, 32);
+        memcpy(sc + 32 * RS_XS, pr + oXs, 32 * L);
+        // (a proof whose slots do not parse is rejected or deferred by the verdict pass; the device then works on ones)
+        if (split_first(t0, t0n, 8, sl) >= 8) {
+          if (!decimal_to_fq_fast(t0 + sl[3].first, sl[3].second, &y) || !decimal_to_fq_fast(t0 + sl[4].first, sl[4].second, &z) ||
+              !decimal_to_fq_fast(t0 + sl[7].first, sl[7].second, &x) || fq_is_zero(y)) { y = fq_one(); z = fq_one(); x = fq_one(); }
+        }
+        if (split_first(t1, t1n, 2, sl) >= 2) x1 = mod_hash_q(t1, sl[0].second + 1);
+        fq_to_le(sc + 32 * RS_Y, y); fq_to_le(sc + 32 * RS_Z, z); fq_to_le(sc + 32 * RS_X, x); fq_to_le(sc + 32 * RS_X1, x1);
+        continue;
+      }
+      uint8_t verdict = 1;
+      // --- RangeVerifier.verify_transcript                         rangeproof_verifier.py:42-53
       if (split_first(t0, t0n, 8, sl) < 8) verdict = 2;               // reference would raise IndexError
       else if (!b64_point_eq(t0 + sl[1].first, sl[1].second, pr + oA) || !b64_point_eq(t0 + sl[2].first, sl[2].second, pr + oS)) verdict = 0;
       else if (!decimal_to_fq_fast(t0 + sl[3].first, sl[3].second, &y) || !decimal_to_fq_fast(t0 + sl[4].first, sl[4].second, &z)) verdict = 2;
@@ -666,8 +689,6 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
       if (verdict == 1 && fq_is_zero(y)) verdict = 2;                 // y.inv() raises in the reference
       // --- Verifier1.verify_transcript                             inner_product_verifier.py:36-42
       if (verdict == 1) {
-        const uint8_t* t1 = transcripts + tr_off[3 * p + 1];
-        size_t t1n = tr_off[3 * p + 2] - tr_off[3 * p + 1];
         if (split_first(t1, t1n, 2, sl) < 2) verdict = 2;
         else {
           // parts[0] + b"&" is the transcript up to and including its first '&'
@@ -692,8 +713,7 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
           if (!fq_eq(xj, want) || !decimal_slot_eq(t2 + sX.first, sX.second, want)) { verdict = 0; break; }
         }
       }
-      fq_to_le(sc + 32 * RS_Y, y); fq_to_le(sc + 32 * RS_Z, z); fq_to_le(sc + 32 * RS_X, x); fq_to_le(sc + 32 * RS_X1, x1);
-      hok_buf[cur][p - chunk_lo] = verdict;
+      hok_all[p] = verdict;
     }
   };
   // ---- device buffers and the shared generator table -----------------------------------------------
@@ -765,6 +785,7 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
   const u32 bd = 2 * n < 64 ? 64 : (u32)(2 * n);           // k_rp_expand: g side and h side of every position
   const size_t smem = (5 * n + 32 + 2 * L) * sizeof(Fq);
   const bool timing = getenv("BP_VERIFY_TIMING") != nullptr;
+  static const size_t sv_latency_max = [] { const char* e = getenv("BP_SV_LATENCY_MAX"); return e ? (size_t)atol(e) : (size_t)1536; }();
   double host_ms = 0;
   int chunk_no = 0;
   chunk_lo = 0;
@@ -780,7 +801,7 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
 #pragma omp parallel for schedule(static, 1) num_threads((int)nt)
       for (long t = 0; t < nt; t++) {
         size_t lo = chunk_lo + (size_t)t * per, hi = lo + per < chunk_hi ? lo + per : chunk_hi;
-        if (lo < hi) work(lo, hi);
+        if (lo < hi) work(lo, hi, true);
       }
     }
     const double h_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h0).count();
@@ -800,7 +821,6 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
     BP_CUDA(cudaStreamWaitEvent(g.aux_stream, g.aux_free[cur], 0));
     BP_CUDA(cudaMemcpyAsync(table + pt_base, hpt_buf[cur], cn * lay.npt * 64, cudaMemcpyHostToDevice, g.aux_stream));
     BP_CUDA(cudaMemcpyAsync(psc, hsc_buf[cur], cn * lay.nsc * 32, cudaMemcpyHostToDevice, g.aux_stream));
-    BP_CUDA(cudaMemcpyAsync(d_hok + chunk_lo, hok_buf[cur], cn, cudaMemcpyHostToDevice, g.aux_stream));
     BP_CUDA(cudaEventRecord(g.stage_ev[cur], g.aux_stream));
     BP_CUDA(cudaMemsetAsync(d_bad, 0, cn, g.aux_stream));
     ++g.nlaunch, k_reduce_scalars<<<(unsigned)((cn * lay.nsc + 127) / 128), 128, 0, g.aux_stream>>>(psc, (u32)(cn * lay.nsc));
@@ -835,7 +855,10 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
       BP_CUDA(cudaStreamWaitEvent(g.var_stream[cur], g.aux_ready[cur], 0));
       ++g.nlaunch, k_sv_main<<<(unsigned)((cn * 32 + 127) / 128), 128, 0, g.var_stream[cur]>>>(cpts, lay, (u32)cn, sv_T, kd, kfl, sv_A);
       ++g.nlaunch, k_sv_comb1<<<(unsigned)((cn * 12 + 127) / 128), 128, 0, g.var_stream[cur]>>>(sv_A, (u32)(cn * 12), sv_G);
-      ++g.nlaunch, k_sv_comb2<<<(unsigned)((cn * 3 + 127) / 128), 128, 0, g.var_stream[cur]>>>(sv_G, cpts, lay, (u32)cn, d_var);
+      if (cn <= sv_latency_max)        // small chunk: the 96 doublings of the last stage as 4-lane cooperative operations
+        ++g.nlaunch, k_sv_comb2q<<<(unsigned)((cn * 12 + 127) / 128), 128, 0, g.var_stream[cur]>>>(sv_G, cpts, lay, (u32)cn, d_var);
+      else
+        ++g.nlaunch, k_sv_comb2<<<(unsigned)((cn * 3 + 127) / 128), 128, 0, g.var_stream[cur]>>>(sv_G, cpts, lay, (u32)cn, d_var);
       BP_CUDA(cudaEventRecord(g.var_done[cur], g.var_stream[cur]));
       if (fbtab16) ++g.nlaunch, k_rp_lookup16<<<(unsigned)cn, 128, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
       else ++g.nlaunch, k_rp_lookup<<<(unsigned)cn, 128, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
@@ -843,22 +866,38 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
       ++g.nlaunch, k_rp_fold8<<<(nm * 8 + 127) / 128, 128, 0, g.stream>>>(d_lanes, nm, (u32)cn, d_grp);
       BP_CUDA(cudaStreamWaitEvent(g.stream, g.var_done[cur], 0));
       ++g.nlaunch, k_rp_fold<<<(nm + 3) / 4, 128, 0, g.stream>>>(d_grp, d_var, nm, (u32)cn, d_tot);
-      ++g.nlaunch, k_rp_accept_xyzz<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_tot, (u32)cn, d_bad, d_hok + chunk_lo, d_acc + chunk_lo);
+      ++g.nlaunch, k_rp_accept_xyzz<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_tot, (u32)cn, d_bad, nullptr, d_acc + chunk_lo);
     } else {
       ++g.nlaunch, k_rp_check_points<<<(unsigned)((cn * lay.npt + 127) / 128), 128, 0, g.aux_stream>>>(table + pt_base, lay.npt, (u32)cn, d_bad);
       BP_CUDA(cudaEventRecord(g.aux_ready[cur], g.aux_stream));
       BP_CUDA(cudaStreamWaitEvent(g.stream, g.aux_ready[cur], 0));
       if (msm_run(table, tidx, tsc, (u32)(cn * lay.tpp), d_off, (u32)(4 * cn), lay.tpp / 4, d_res, nullptr)) return 1;
-      ++g.nlaunch, k_rp_accept<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)cn, d_bad, d_hok + chunk_lo, d_acc + chunk_lo);
+      ++g.nlaunch, k_rp_accept<<<(unsigned)((cn + 127) / 128), 128, 0, g.stream>>>(d_res, (u32)cn, d_bad, nullptr, d_acc + chunk_lo);
     }
     BP_CUDA(cudaEventRecord(g.aux_free[cur], g.stream));
   }
-  if (nproofs) BP_CUDA(cudaEventRecord(g.ev_rp1, g.stream));
+  if (nproofs) {
+    // verdict pass over the whole batch, underneath the device work enqueued above
+    auto t_v0 = std::chrono::steady_clock::now();
+    const long nt = (long)(nthreads > nproofs ? (unsigned)nproofs : nthreads);
+    const size_t per = (nproofs + (size_t)nt - 1) / (size_t)nt;
+#pragma omp parallel for schedule(static, 1) num_threads((int)nt)
+    for (long t = 0; t < nt; t++) {
+      size_t lo = (size_t)t * per, hi = lo + per < nproofs ? lo + per : nproofs;
+      if (lo < hi) work(lo, hi, false);
+    }
+    const double v_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_v0).count();
+    host_ms += v_ms;
+    if (timing) fprintf(stderr, "verdict pass (%zu proofs): host %.3f ms (%u threads)\n", nproofs, v_ms, nthreads);
+    BP_CUDA(cudaMemcpyAsync(d_hok, hok_all, nproofs, cudaMemcpyHostToDevice, g.stream));
+    ++g.nlaunch, k_rp_merge_host<<<(unsigned)((nproofs + 255) / 256), 256, 0, g.stream>>>(d_hok, (u32)nproofs, d_acc);
+    BP_CUDA(cudaEventRecord(g.ev_rp1, g.stream));
+  }
   if (gather_out) {
     // the single exchange step of the sharded batch: accept bytes all-gathered device to device over NVLink
     const uint8_t* all = d_acc;
     if (g_comm && g_nranks > 1) { BP_NCCL(ncclAllGather(d_acc, d_all, gwidth, ncclUint8, g_comm, g.stream)); all = d_all; }
-    uint8_t* pin = stage + 2 * stage_each;
+    uint8_t* pin = stage + 2 * stage_each + hok_bytes;
     BP_CUDA(cudaMemcpyAsync(pin, all, (size_t)g_nranks * gwidth, cudaMemcpyDeviceToHost, g.stream));
     BP_CUDA(cudaStreamSynchronize(g.stream));
     memcpy(gather_out, pin, (size_t)g_nranks * gwidth);

@@ -213,4 +213,35 @@ __global__ void __launch_bounds__(128) k_sv_comb2(const XYZZ* __restrict__ G, co
   st_xyzz(var + (size_t)(eq == 2u ? 3u : eq) * cn + p, acc);
 }
 
+// ---- latency form of the last Horner stage for small chunks (<= ~1500 proofs: a rank's share of a sharded batch) ------------------
+// With a thousand proofs in flight k_sv_comb2 is a single-thread chain of 96 doublings on 24 blocks (215 us); as 4-lane cooperative
+// operations (coop4.cuh) it takes 152 us.  Measured and NOT kept for the other two stages: four warps per proof in k_sv_main
+// (286 against 254 us: at 1024 proofs that kernel is already multiplier-bound, 1.1 M full additions) and a 4-lane k_sv_comb1
+// (109 against 111 us: 28 doublings + 7 additions whose ~24 KB loop body is fetched cold by too few warps).
+// one QUAD per (equation kind, proof): sum_g 2^(32g) G_g by Horner (96 doublings), then the unit-scalar terms
+__global__ void __launch_bounds__(128) k_sv_comb2q(const XYZZ* __restrict__ G, const Affine* __restrict__ pts, RpLayout lay, u32 cn,
+                                                   XYZZ* __restrict__ var) {
+  u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const bool live = q < 3 * cn;
+  if (!live) q = 3 * cn - 1;
+  const u32 eq = q / cn, p = q % cn;
+  const XYZZ* Gp = G + ((size_t)p * 3 + eq) * 4;
+  XYZZ acc = ld_xyzz(Gp + 3);
+#pragma unroll 1
+  for (int g4 = 2; g4 >= 0; g4--) {
+#pragma unroll 1
+    for (int d = 0; d < 32; d++) acc = coop_dbl(acc, role, base);
+    XYZZ v = ld_xyzz(Gp + g4);
+    acc = coop_add(acc, v, role, base);
+  }
+  const Affine* PP = pts + (size_t)p * lay.npt;
+  // unit-scalar terms (E1: none, E2: + A - P_new, E4: - P_new); every quad runs both additions, the unused ones add the identity
+  XYZZ a1 = eq == 1u ? xyzz_from_affine(ld_affine(PP + RP_A)) : xyzz_identity();
+  XYZZ a2 = eq >= 1u ? xyzz_from_affine(affine_neg(ld_affine(PP + RP_PNEW))) : xyzz_identity();
+  acc = coop_add(acc, a1, role, base);
+  acc = coop_add(acc, a2, role, base);
+  if (live && role == 0) st_xyzz(var + (size_t)(eq == 2u ? 3u : eq) * cn + p, acc);
+}
+
 }  // namespace bp

@@ -250,7 +250,7 @@ __global__ void k_rp_accept(const Affine* __restrict__ res, u32 nproofs, const u
                             uint8_t* __restrict__ accept) {
   u32 p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs) return;
-  if (hok[p] != 1) { accept[p] = hok[p]; return; }
+  if (hok && hok[p] != 1) { accept[p] = hok[p]; return; }
   bool ok = bad[p] == 0;                                 // a proof with a point off the curve is rejected (svar.cuh)
   for (u32 e = 0; e < 4; e++) ok = ok && affine_is_identity(ld_affine(res + e * nproofs + p));
   accept[p] = ok ? 1 : 0;
@@ -378,10 +378,16 @@ __global__ void k_rp_accept_xyzz(const XYZZ* __restrict__ res, u32 nproofs, cons
                                  uint8_t* __restrict__ accept) {
   u32 p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs) return;
-  if (hok[p] != 1) { accept[p] = hok[p]; return; }
+  if (hok && hok[p] != 1) { accept[p] = hok[p]; return; }
   bool ok = bad[p] == 0;
   for (u32 e = 0; e < 4; e++) ok = ok && xyzz_is_identity(ld_xyzz(res + e * nproofs + p));
   accept[p] = ok ? 1 : 0;
+}
+
+// host verdicts (transcript checks: 1 = passed, 0 = reject, 2 = the reference would raise) override the device's decisions
+__global__ void k_rp_merge_host(const uint8_t* __restrict__ hok, u32 nproofs, uint8_t* __restrict__ accept) {
+  const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nproofs && hok[p] != 1) accept[p] = hok[p];
 }
 
 }  // namespace bp

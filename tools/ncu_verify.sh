@@ -11,7 +11,8 @@ rows=list(csv.reader(l for l in open("gpurun_out/verify_kernels.csv") if l.start
 h=rows[0]; ki=h.index("Kernel Name"); mi=h.index("Metric Name"); vi=h.index("Metric Value"); gi=h.index("Grid Size")
 t=[(r[ki].split("(")[0], r[gi], float(r[vi].replace(",",""))) for r in rows[1:] if r[mi].startswith("gpu__time")]
 # last call = everything after the last k_reduce_scalars whose grid belongs to chunk 0 ... simply: the last 4 chunks x 11 kernels
-last=t[-44:]
+import os
+last=t[-int(os.environ.get("BP_NCU_LAST","44")):]
 tot={}
 for k,g,v in last:
     tot[k]=tot.get(k,0)+v
