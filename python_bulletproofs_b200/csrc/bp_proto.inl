@@ -736,6 +736,19 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
   if (g.ensure_aux()) return 1;
   if (g.ensure_stage_events()) return 1;
   if (gather_out) BP_CUDA(cudaMemsetAsync(d_acc, 0, gwidth, g.stream));      // padding bytes of the gathered block
+  // Steady state (both generator tables of this set exist and match the caller's bytes): every generator term is a table lookup and
+  // nothing reads the generator rows of `table` -- skip their five uploads from pageable memory and the two sums (~0.1 ms per call).
+  bool warm = false;
+  if (fb_enabled()) {
+    const FbSrc src = {{gs64, hs64, g64, h64, u64_}, {n * 64, n * 64, 64, 64, 64}, 5};
+    const uint64_t k2 = src.hash(0x72707631ull) ^ ((uint64_t)lay.fixed * 0xD6E8FEB86659FD93ull);
+    auto it = fb.tabs.find(k2);
+    if (it != fb.tabs.end() && it->second.n == lay.fixed && src.equals(it->second.src)) {
+      auto it16 = fb.tabs16.find(k2);
+      warm = it16 != fb.tabs16.end() && it16->second.n == lay.fixed && it16->second.parent == it->second.tab;
+    }
+  }
+  if (!warm) {
   BP_CUDA(cudaMemcpyAsync(table, gs64, n * 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + n, hs64, n * 64, cudaMemcpyHostToDevice, g.stream));
   BP_CUDA(cudaMemcpyAsync(table + 2 * n, g64, 64, cudaMemcpyHostToDevice, g.stream));
@@ -755,6 +768,7 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
       BP_CUDA(cudaMemcpyAsync(sums, table + 2 * n + 3, 2 * sizeof(Affine), cudaMemcpyDeviceToDevice, g.stream));
       g.rp_sums_src = src.copy(); g.rp_sums_gen = alloc_generation();
     }
+  }
   }
   // Repeated generator set: its terms (2n+1 of E4, n+4 of E2, ...: 202 of the 220 terms of a 64-bit proof) are read from
   // the fixed-base table with no doublings and no bucket reduction; the ~21 proof-specific terms (V, A, S, T1, T2, u', P',
