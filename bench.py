@@ -550,7 +550,77 @@ def bench_verify(args, nat, dist, rank, world, imad_peak):
         res["prover_vs_oracle"] = {"proofs": min(args.verify_prover_check, hi - lo), "byte_identical_transcripts": same}
         if world == 1:
             res["cpu_baseline"] = verify_cpu_baseline(Vs, proofs, og, oh, ogs, ohs, ou, T_, q)
+            try:
+                res["aggregated"] = bench_verify_aggregated(nat, q)
+            except Exception as e:   # noqa: BLE001
+                res["aggregated"] = {"error": repr(e)}
     return res
+
+
+def bench_verify_aggregated(nat, q, m=16, nbits=64, distinct=32, total=1024):
+    """Widening row (BASELINE config 4 as a batch): `total` aggregated range proofs (m values x nbits bits, n*m = 1024 generators per
+    side) through bp_rp_verify_aggreg_batch in one call -- `distinct` different proofs tiled (proving 1024 of them would take the
+    bench 3 s more for nothing: the verifier does the same work per record), every 8th distinct proof corrupted; decisions of the
+    distinct proofs checked against the oracle verifier; the class API (AggregRangeVerifier.verify, proof by proof) timed beside it."""
+    import contextlib
+    import io
+    from oracle import protocol_oracle as po
+    from python_bulletproofs_b200 import secp256k1
+    from python_bulletproofs_b200.rangeproofs import AggregNIRangeProver, AggregRangeVerifier
+    from python_bulletproofs_b200.rangeproofs.batch import PackedAggregBatch, pack_generators, verify_aggreg_packed
+    from python_bulletproofs_b200.utils import ModP, commitment, mod_hash, elliptic_hash
+    nm = nbits * m
+    gs = [elliptic_hash(str(i).encode() + b"agg0", secp256k1) for i in range(nm)]
+    hs = [elliptic_hash(str(i).encode() + b"agg1", secp256k1) for i in range(nm)]
+    g, h, u = (elliptic_hash(s_, secp256k1) for s_ in (b"agg2", b"agg3", b"agg4"))
+    rng = random.Random(16)
+    Vl, pl = [], []
+    t = time.perf_counter()
+    for i in range(distinct):
+        vs = [ModP(rng.getrandbits(nbits), q) for _ in range(m)]
+        gammas = [mod_hash(b"ag%d_%d" % (i, j), q) for j in range(m)]
+        Vl.append([commitment(g, h, vs[j], gammas[j]) for j in range(m)])
+        pr = AggregNIRangeProver(vs, nbits, g, h, gs, hs, gammas, u, secp256k1, b"y%d" % i).prove()
+        if i % 8 == 7:
+            pr.mu = ModP((pr.mu.x + 1) % q, q)
+        pl.append(pr)
+    prove_ms = (time.perf_counter() - t) / distinct * 1e3
+    batch = PackedAggregBatch.from_proofs(Vl * (total // distinct), pl * (total // distinct), nbits)
+    packed = pack_generators(g, h, gs, hs, u)
+    ts, acc = [], b""
+    for it in range(3 + 5):                    # the first calls meet the generator set for the first time and build its table
+        a = time.perf_counter()
+        acc = verify_aggreg_packed(batch, g, h, gs, hs, u, packed)
+        ts.append(time.perf_counter() - a)
+    med = statistics.median(ts[3:])
+    want = bytes([0 if i % 8 == 7 else 1 for i in range(distinct)]) * (total // distinct)
+    T_ = lambda p_: None if p_.curve is None else (p_.x, p_.y)      # noqa: E731
+    ogs, ohs, og, oh, ou = [T_(x) for x in gs], [T_(x) for x in hs], T_(g), T_(h), T_(u)
+    dec_ok = True
+    for k in (0, 7):                           # one intact, one corrupted proof against the oracle's AggregRangeVerifier restatement
+        pr = pl[k]
+        ip, p2 = pr.innerProof, pr.innerProof.proof2
+        op = {"taux": pr.taux.x % q, "mu": pr.mu.x % q, "t_hat": pr.t_hat.x % q, "T1": T_(pr.T1), "T2": T_(pr.T2), "A": T_(pr.A), "S": T_(pr.S),
+              "transcript": pr.transcript,
+              "ip": {"u_new": T_(ip.u_new), "P_new": T_(ip.P_new), "transcript": ip.transcript,
+                     "p2": {"a": p2.a.x % q, "b": p2.b.x % q, "xs": [x.x % q for x in p2.xs], "Ls": [T_(x) for x in p2.Ls],
+                            "Rs": [T_(x) for x in p2.Rs], "transcript": p2.transcript, "start": p2.start_transcript}}}
+        dec_ok = dec_ok and (po.range_verify([T_(V) for V in Vl[k]], og, oh, ogs, ohs, ou, op) == (acc[k] == 1))
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = time.perf_counter()
+        for k in range(4):
+            AggregRangeVerifier(Vl[k], g, h, gs, hs, u, pl[k]).verify()
+        one_ms = (time.perf_counter() - a) / 4 * 1e3
+    # generator terms: 3 * nm + 6 table terms x 32 byte-window lookups, one mixed addition (666 IMAD.WIDE) each
+    return {"workload": "%d aggregated range proofs of m = %d values x %d bits (n*m = %d generators per side), %d distinct, one call of "
+                        "bp_rp_verify_aggreg_batch from host buffers" % (total, m, nbits, nm, distinct),
+            "ms_per_batch": round(med * 1e3, 3), "proofs_per_s": round(total / med, 1), "values_per_s": round(total * m / med, 1),
+            "decisions_ok": acc == want, "decisions_vs_oracle_ok": dec_ok, "rejected": acc.count(b"\x00"),
+            "class_api_ms_per_proof": round(one_ms, 3), "speedup_vs_class_api": round(one_ms / (med * 1e3 / total), 1),
+            "prove_ms_per_proof": round(prove_ms, 3),
+            "table_lookups_per_proof": (3 * nm + 6) * 32,
+            "imad_wide_T_per_s": round((3 * nm + 6) * 32 * 666 * total / med / 1e12, 3),
+            "reference": "AggregRangeVerifier.verify, src/rangeproofs/rangeproof_aggreg_verifier.py:42-108: 20.0 s per proof on one core (BASELINE.md 2.2)"}
 
 
 def verify_cpu_baseline(Vs, proofs, og, oh, ogs, ohs, ou, T_, q):

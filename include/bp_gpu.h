@@ -216,6 +216,19 @@ int bp_rp_verify_batch_gather(const uint8_t* gs64, const uint8_t* hs64, const ui
                               const uint8_t u64_[64], size_t n, const uint8_t* proofs, size_t proof_stride, size_t nproofs,
                               const uint8_t* transcripts, const uint64_t* tr_off, const uint32_t* start_transcript,
                               size_t width, uint8_t* accept_all);
+/* Batch verification of AGGREGATED range proofs (m values x n bits each, n*m a power of two <= 2048) over one generator set:
+ * the data-parallel form of AggregRangeVerifier(Vs_i, g, h, gs, hs, u, proof_i).verify() for every i
+ * (/root/reference/src/rangeproofs/rangeproof_aggreg_verifier.py:42-108), same decisions; m = 1 is RangeVerifier.verify.
+ * Record of one proof (little-endian scalars, 64-byte affine points), L = log2(n*m):
+ *   V_0..V_{m-1} | A | S | T1 | T2 | taux | mu | t_hat | u_new | P_new | a | b | xs[L] | Ls[L] | Rs[L]      (bp_rp_aggreg_proof_stride bytes)
+ * transcripts / tr_off / start_transcript and the accept bytes (1 accept, 0 reject, 2 = replay through the Python classes: the
+ * reference would raise) as for bp_rp_verify_batch.  Host: transcript checks and every term scalar (OpenMP, csrc/rp_algebra.h);
+ * device: generator terms from the set's byte table (bucket method until the set has one), proof-specific terms through the batched
+ * bucket MSM, four exact identity checks per proof (csrc/bp_aggreg.inl). */
+size_t bp_rp_aggreg_proof_stride(size_t n, size_t m);
+int bp_rp_verify_aggreg_batch(const uint8_t* gs64, const uint8_t* hs64, const uint8_t g64[64], const uint8_t h64[64], const uint8_t u64_[64],
+                              size_t n, size_t m, const uint8_t* proofs, size_t proof_stride, size_t nproofs, const uint8_t* transcripts,
+                              const uint64_t* tr_off, const uint32_t* start_transcript, uint8_t* accept);
 /* measurements of the last batch call: [0] wall ms, [1] host transcript-check ms (sum over chunks), [2] device span ms
  * (CUDA events on the library stream: first chunk's first kernel .. last accept kernel), [3] chunks, [4] host threads,
  * [5] table mode (0 bucket method, 1 byte tables, 2 16-bit tables), [6] proofs */

@@ -72,6 +72,9 @@ PROTOTYPES = {
     "bp_rp_verify_batch_gather": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_u8p, c_sz, c_sz, c_u8p,
                                                  ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), c_sz, c_u8p]),
     "bp_rp_verify_stats": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double)]),
+    "bp_rp_aggreg_proof_stride": (c_sz, [c_sz, c_sz]),
+    "bp_rp_verify_aggreg_batch": (ctypes.c_int, [c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_sz, c_sz, c_u8p,
+                                                 ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), c_u8p]),
     "bp_mod_hash": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
     "bp_mod_hash_indexed": (ctypes.c_int, [c_u8p, c_sz, ctypes.c_uint32, ctypes.c_uint32, c_u8p]),
     "bp_sha256": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),

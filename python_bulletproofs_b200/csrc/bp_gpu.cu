@@ -970,3 +970,4 @@ int bp_imad_peak(int iters, double* macs_per_s, float* ms_out) { BP_NEED_INIT();
 
 }  // extern "C"
 #include "bp_proto.inl"
+#include "bp_aggreg.inl"

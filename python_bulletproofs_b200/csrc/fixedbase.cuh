@@ -283,6 +283,29 @@ __global__ void __launch_bounds__(256) k_fb_lookup_warp(const Affine* __restrict
   }
   st_xyzz(part + (size_t)32 * m + lane, acc);
 }
+// The same for batches of LARGE table MSMs (aggregated range proofs: 2048 generator terms in one equation): one warp per
+// (MSM, slice of `slice` consecutive terms), lane = byte-window; an empty slice writes identities.  part[(m * nsl + s) * 32 + lane];
+// k_fb_fold_warp then folds the 32 lane sums of every slice and k_fb_finish adds the nsl slice sums of every MSM.
+__global__ void __launch_bounds__(256) k_fb_lookup_slice(const Affine* __restrict__ tab, const u32* __restrict__ idx, const Fq* __restrict__ sc,
+                                                         const u32* __restrict__ offsets, u32 nmsm, u32 nsl, u32 slice, XYZZ* __restrict__ part) {
+  const u32 w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= nmsm * nsl) return;
+  const u32 m = w / nsl, s = w % nsl;
+  const u32 lo = __ldg(offsets + m) + s * slice, end = __ldg(offsets + m + 1);
+  const u32 hi = lo + slice < end ? lo + slice : end;
+  XYZZ acc = xyzz_identity();
+  for (u32 t = lo; t < hi; t++) {                     // (lo >= hi: empty slice)
+    const u32 gi = __ldg(idx + t);
+    const u32* kw = reinterpret_cast<const u32*>(sc + t);
+    Fq k;
+#pragma unroll
+    for (int i = 0; i < 8; i++) k.v[i] = __ldg(kw + i);
+    k = fq_reduce(k);
+    const u32 d = (k.v[lane >> 2] >> (8 * (lane & 3))) & 0xFFu;
+    if (d) { Affine p = ld_affine(tab + fb_index(gi, lane, d)); xyzz_madd_ni(acc, p); }
+  }
+  st_xyzz(part + (size_t)32 * w + lane, acc);
+}
 // Step 2: one warp per MSM = 8 quads: each quad adds 4 lane sums, then a 3-level tree; optionally adds `other[m]` (the
 // caller's partial for the same MSM) and writes out[m].
 __global__ void __launch_bounds__(128) k_fb_fold_warp(const XYZZ* __restrict__ part, const XYZZ* __restrict__ other, u32 nmsm,

@@ -135,3 +135,93 @@ def verify_range_proofs_batch(Vs, g, h, gs, hs, u, proofs):
         else:
             out.append(a == 1)
     return out
+
+
+# ---- aggregated proofs (m values per proof) ---------------------------------------------------------------------------------
+def pack_aggreg_proof(Vs, proof, log_nm):
+    """One aggregated proof in the wire layout of bp_rp_verify_aggreg_batch (include/bp_gpu.h)."""
+    ip = proof.innerProof
+    p2 = ip.proof2
+    le = lambda s: (s % nat.Q).to_bytes(32, "little")          # noqa: E731
+    rec = [nat.pack_point(V) for V in Vs]
+    rec += [nat.pack_point(proof.A), nat.pack_point(proof.S), nat.pack_point(proof.T1), nat.pack_point(proof.T2),
+            le(proof.taux), le(proof.mu), le(proof.t_hat), nat.pack_point(ip.u_new), nat.pack_point(ip.P_new), le(p2.a), le(p2.b)]
+    rec += [le(x) for x in p2.xs[:log_nm]]
+    rec += [nat.pack_point(L) for L in p2.Ls[:log_nm]] + [nat.pack_point(R) for R in p2.Rs[:log_nm]]
+    return b"".join(rec), (proof.transcript, ip.transcript, p2.transcript), p2.start_transcript
+
+
+class PackedAggregBatch(PackedBatch):
+    """A batch of aggregated proofs, each over m commitments of n bits (n * m generators per side)."""
+
+    def __init__(self, n, m, records, transcripts, starts):
+        super().__init__(n, records, transcripts, starts)
+        self.m = m
+        if not records:
+            self.stride = nat.load().bp_rp_aggreg_proof_stride(n, m)
+
+    @classmethod
+    def from_proofs(cls, Vs_list, proofs, n):
+        if not proofs:
+            return cls(n, 1, [], [], [])
+        m = len(Vs_list[0])
+        log_nm = (n * m).bit_length() - 1
+        recs, trs, sts = [], [], []
+        for Vs, pr in zip(Vs_list, proofs):
+            p2 = pr.innerProof.proof2
+            if len(Vs) != m:
+                raise ValueError("every proof of a batch aggregates the same number of commitments")
+            if len(p2.xs) != log_nm or len(p2.Ls) != log_nm or len(p2.Rs) != log_nm:
+                raise ValueError("proof shape does not match the generator count")
+            r, t, s = pack_aggreg_proof(Vs, pr, log_nm)
+            if any(not (0 <= int(getattr(x, "x", x)) < nat.Q) for x in p2.xs):      # unreduced challenge: step-by-step path (see PackedBatch)
+                s = 0xFFFFFFFF
+            recs.append(r)
+            trs.append(t)
+            sts.append(s)
+        return cls(n, m, recs, trs, sts)
+
+
+def pack_generators(g, h, gs, hs, u):
+    """The five generator arguments in wire form; a caller that verifies many batches over one generator set packs them once."""
+    return nat.pack_points(gs), nat.pack_points(hs), nat.pack_point(g), nat.pack_point(h), nat.pack_point(u)
+
+
+def verify_aggreg_packed(batch: PackedAggregBatch, g, h, gs, hs, u, packed=None):
+    """accept bytes (1 accept / 0 reject / 2 defer-to-Python) of a batch of aggregated proofs (packed = pack_generators(...))."""
+    accept = ctypes.create_string_buffer(max(batch.nproofs, 1))
+    gs_b, hs_b, g_b, h_b, u_b = packed if packed is not None else pack_generators(g, h, gs, hs, u)
+    nat.check(nat.load().bp_rp_verify_aggreg_batch(gs_b, hs_b, g_b, h_b, u_b, batch.n, batch.m,
+                                                   batch.records, batch.stride, batch.nproofs, batch.blob, batch.tr_off, batch.starts, accept))
+    return accept.raw[:batch.nproofs]
+
+
+def verify_aggreg_range_proofs_batch(Vs_list, g, h, gs, hs, u, proofs):
+    """-> list[bool]: AggregRangeVerifier(Vs_i, g, h, gs, hs, u, proof_i).verify() for every i, in one call
+    (rangeproof_aggreg_verifier.py:42-108).  A proof the C layer cannot classify is replayed through AggregRangeVerifier so that
+    the reference's exception type surfaces."""
+    from .rangeproof_aggreg_verifier import AggregRangeVerifier
+    if len(Vs_list) != len(proofs):
+        raise Exception('Different number of commitments and proofs')
+    if not proofs:
+        return []
+    m = len(Vs_list[0])
+    if len(gs) % m:
+        raise ValueError("generator count is not a multiple of the number of commitments")
+    batch = PackedAggregBatch.from_proofs(Vs_list, proofs, len(gs) // m)
+    acc = verify_aggreg_packed(batch, g, h, gs, hs, u)
+    out = []
+    for i, a in enumerate(acc):
+        if a == 2:
+            import contextlib, io
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    out.append(bool(AggregRangeVerifier(Vs_list[i], g, h, gs, hs, u, proofs[i]).verify()))
+            except Exception as e:   # noqa: BLE001
+                if str(e) == "Proof invalid":
+                    out.append(False)
+                else:
+                    raise
+        else:
+            out.append(a == 1)
+    return out

@@ -258,6 +258,47 @@ def test_batch_verify_decisions(n, count):
         assert quiet(RangeVerifier(Vs[i], g, h, gs, hs, u, proofs[i]).verify) is want[i]
 
 
+@pytest.mark.parametrize("n,m,count", [(8, 2, 24), (16, 4, 16), (8, 1, 16), (64, 16, 3)])
+def test_aggreg_batch_verify_decisions(n, m, count):
+    """bp_rp_verify_aggreg_batch (aggregated proofs, m values x n bits, up to 1024 generators per side) vs the oracle's
+    AggregRangeVerifier restatement, proof by proof, incl. corrupted proofs of every kind.  Run three times: bucket method over the
+    generator rows (first sight of the set), then the set's byte table -- the decisions must not depend on the path."""
+    from python_bulletproofs_b200.rangeproofs import AggregNIRangeProver, AggregRangeVerifier, verify_aggreg_range_proofs_batch
+    seeds = ["ab%d_%d_%d" % (n, m, i) for i in range(5)]
+    nm = n * m
+    ogs, ohs, og, oh, ou = gens(nm, seeds)
+    gs, hs, g, h, u = [P_(t) for t in ogs], [P_(t) for t in ohs], P_(og), P_(oh), P_(ou)
+    rng = random.Random(1000 * n + m)
+    Vs_list, proofs, oVs_list, oproofs = [], [], [], []
+    for i in range(count):
+        vs = [M_(rng.getrandbits(n)) for _ in range(m)]
+        gammas = [mod_hash(b"ga%d_%d" % (i, j), Q) for j in range(m)]
+        Vs = [commitment(g, h, vs[j], gammas[j]) for j in range(m)]
+        pr = AggregNIRangeProver(vs, n, g, h, gs, hs, gammas, u, secp256k1, b"ap%d" % i).prove()
+        kind = i % 8
+        if kind == 1:
+            s = str(pr.t_hat.x); pr.t_hat = M_(int(s[:-1] + ("1" if s[-1] != "1" else "2")))
+        elif kind == 2:
+            Vs[m - 1] = Vs[m - 1] + g
+        elif kind == 3:
+            pr.innerProof.proof2.b = pr.innerProof.proof2.b + M_(1)
+        elif kind == 4:
+            t = bytearray(pr.innerProof.proof2.transcript); t[-5] = ord("1") if t[-5] != ord("1") else ord("2")
+            pr.innerProof.proof2.transcript = bytes(t)
+        elif kind == 5:
+            pr.taux = pr.taux + M_(1)
+        elif kind == 6:
+            pr.innerProof.P_new = pr.innerProof.P_new + h
+        Vs_list.append(Vs); proofs.append(pr)
+        oVs_list.append([T_(V) for V in Vs]); oproofs.append(po.range_from_json(range_json(pr)))
+    want = [po.range_verify(oVs, og, oh, ogs, ohs, ou, opr) for oVs, opr in zip(oVs_list, oproofs)]
+    for _ in range(3):
+        assert verify_aggreg_range_proofs_batch(Vs_list, g, h, gs, hs, u, proofs) == want
+    assert want.count(True) == sum(1 for i in range(count) if i % 8 in (0, 7))
+    for i in (0, 1):                                      # the class API agrees
+        assert quiet(AggregRangeVerifier(Vs_list[i], g, h, gs, hs, u, proofs[i]).verify) is want[i]
+
+
 def _small_batch(n, count, tag):
     seeds = [tag + "%d" % i for i in range(5)]
     ogs, ohs, og, oh, ou = gens(n, seeds)
