@@ -93,8 +93,85 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
 // Per-call options of msm_run (passed by value: nothing a failed call could leave behind for the next one).
 //   skip_below  terms whose point index is below this count as zero scalars (the caller evaluates them elsewhere, see k_digits)
 //   pts_ready   event the points are complete at (host-operand MSM whose points upload on the copy stream)
-//   halves      the points arrive in `parts` equal parts (g.ev_half[0 .. parts-1], upload_operands)
-struct MsmOpts { u32 skip_below = 0; cudaEvent_t pts_ready = nullptr; bool halves = false; int parts = 0; };
+//   halves      the points arrive in `parts` equal parts (g.ev_half[0 .. parts-1], upload_operands);
+//   split_sort  ... each behind its own scalars (g.ev_part_sc[k]): sort part by part (msm_run_parts)
+struct MsmOpts { u32 skip_below = 0; cudaEvent_t pts_ready = nullptr; bool halves = false; int parts = 0; bool split_sort = false; };
+// Host-operand MSM whose operands arrive in K parts, each part = its scalars followed by its points (upload_operands): every part
+// is sorted on its own as soon as its scalars are in (digits, scan, scatter over T/K terms) and accumulated as soon as its points
+// are in, all parts adding into ONE bucket set (k_accumulate's `into`); reduction and combination are those of a single MSM.
+// Against one sort over all scalars (the part as the major sort key) the chain no longer starts with the upload of ALL scalars
+// plus a full-size sort: the first quarter's sort runs while the second quarter is on the wire.
+static int msm_run_parts(const Affine* points, const Fq* scalars, u32 T, u32 K, Affine* out_affine, XYZZ* out_xyzz) {
+  cudaStream_t st = g.stream;
+  if (g.ensure_aux()) return 1;
+  cudaStream_t ss = g.aux_stream;                           // the sorts: atomics / memory bound, they run under the previous part's accumulation
+  const u32 Tp = (T + K - 1) / K + 1;                       // terms of the largest part (bound)
+  MsmShape sh = msm_shape(Tp, 1, g.force_c);
+  g.last_c = sh.c;
+  const size_t nb = (size_t)sh.U * sh.H;
+  g.last_nb = nb;
+  const bool prof = g.profiling;
+  if (prof) for (int i = 0; i < 7; i++) cudaEventRecord(g.ev[i], st), (void)0;
+  const size_t emax = (size_t)sh.W * 2 * Tp, nchunks = (emax + sh.chunk - 1) / sh.chunk;
+  const size_t ntiles = (nb + 1 + BP_SCAN_TILE - 1) / BP_SCAN_TILE;
+  // sort buffers twice (parity of the part): part k+1 is sorted while part k is accumulated
+  int* digits2 = (int*)g.ws_digits.ensure(2 * emax * sizeof(int));
+  uint2* entries2 = (uint2*)g.ws_entries.ensure(2 * emax * sizeof(uint2));
+  u32* count2 = (u32*)g.ws_count.ensure(2 * (nb + 1) * sizeof(u32));
+  u32* start2 = (u32*)g.ws_start.ensure(2 * (nb + 1) * sizeof(u32));
+  u32* cursor2 = (u32*)g.ws_cursor.ensure(2 * (nb + 1) * sizeof(u32));
+  u32* tiles2 = (u32*)g.ws_tiles.ensure(2 * ntiles * sizeof(u32));
+  Affine* phi = (Affine*)g.ws_phi.ensure((size_t)Tp * sizeof(Affine));
+  XYZZ* buckets = (XYZZ*)g.ws_buckets.ensure(nb * sizeof(XYZZ));
+  XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * nchunks * sizeof(XYZZ));
+  const u32 big_cap = (u32)(emax / ((size_t)sh.chunk * (BP_FIXUP_SERIAL_MAX - 1)) + 16);
+  u32* big = (u32*)g.ws_big.ensure((2 * (size_t)big_cap + 4) * sizeof(u32));
+  if (!digits2 || !entries2 || !phi || !count2 || !start2 || !cursor2 || !tiles2 || !buckets || !part || !big) return fail("workspace allocation failed");
+  u32* zero_word = big + 2 * (size_t)big_cap + 3;
+  BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));
+  BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
+  BP_CUDA(cudaEventRecord(g.aux_free[0], st)); BP_CUDA(cudaEventRecord(g.aux_free[1], st));      // earlier work on the sort buffers is done
+  for (u32 k = 0; k < K; k++) {
+    const u32 t0 = (u32)((unsigned long long)T * k / K), tn = (u32)((unsigned long long)T * (k + 1) / K) - t0;
+    if (tn == 0) continue;
+    const u32 par = k & 1u;
+    int* digits = digits2 + (size_t)par * emax; uint2* entries = entries2 + (size_t)par * emax;
+    u32* count = count2 + (size_t)par * (nb + 1); u32* start = start2 + (size_t)par * (nb + 1); u32* cursor = cursor2 + (size_t)par * (nb + 1);
+    u32* tiles = tiles2 + (size_t)par * ntiles;
+    // ---- sort stream: this part's scalars -> digits, histogram, scan, scatter
+    BP_CUDA(cudaStreamWaitEvent(ss, g.ev_part_sc[k], 0));   // its scalars have landed
+    BP_CUDA(cudaStreamWaitEvent(ss, g.aux_free[par], 0));   // the accumulation of part k-2 has released these buffers
+    if (k == 0) g.dbg_rec(4, ss);
+    BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), ss));
+    ++g.nlaunch, k_digits<<<(tn + 255) / 256, 256, 0, ss>>>(scalars + t0, tn, nullptr, 1, sh, digits, count, nullptr, 0);
+    ++g.nlaunch, k_scan_tiles<<<(unsigned)ntiles, 256, 0, ss>>>(count, start, tiles, nb + 1);
+    ++g.nlaunch, k_scan_sums<<<1, 1024, 0, ss>>>(tiles, ntiles);
+    ++g.nlaunch, k_scan_add<<<(unsigned)ntiles, 256, 0, ss>>>(start, tiles, nb + 1, nullptr);
+    BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, ss));
+    ++g.nlaunch, k_scatter<<<(2 * tn + 255) / 256, 256, 0, ss>>>(digits, tn, nullptr, 1, sh, cursor, entries);
+    if (k == 0) g.dbg_rec(5, ss);
+    BP_CUDA(cudaEventRecord(g.aux_ready[par], ss));
+    // ---- main stream: accumulate into the shared buckets
+    BP_CUDA(cudaStreamWaitEvent(st, g.aux_ready[par], 0));
+    BP_CUDA(cudaStreamWaitEvent(st, g.ev_half[k], 0));      // ... and its points
+    BP_CUDA(cudaMemsetAsync(big, 0, 2 * sizeof(u32), st));
+    ++g.nlaunch, k_phi<<<(tn + 127) / 128, 128, 0, st>>>(points + t0, nullptr, tn, phi);
+    if (prof && k == 0) cudaEventRecord(g.ev_k0, st);
+    ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points + t0, nullptr, phi, start, entries, zero_word, start + nb, sh.chunk, buckets, part, (u32)nb, k ? 1 : 0);
+    if (prof && k == K - 1) cudaEventRecord(g.ev_k1, st);
+    ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big_cap, (u32)nb);
+    ++g.nlaunch, k_fixup_mid<<<2 * g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big_cap, (u32)nb);
+    ++g.nlaunch, k_fixup_big<<<g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, (u32)nb);
+    BP_CUDA(cudaEventRecord(g.aux_free[par], st));
+    g.dbg_rec(6 + (k == K - 1 ? 1 : 0), st);
+  }
+  if (prof) for (int i = 0; i <= 4; i++) cudaEventRecord(g.ev[i], st), (void)0;
+  if (msm_tails(buckets, sh, 1, out_affine, out_xyzz, prof, st)) return 1;
+  if (prof) cudaEventRecord(g.ev[6], st);
+  BP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, const u32* d_offsets, u32 nmsm,
             size_t terms_per_msm, Affine* out_affine, XYZZ* out_xyzz, MsmOpts opt = MsmOpts()) {
   if (nmsm == 1 && T >= g.pipeline_min_terms && !g.profiling) {
@@ -106,6 +183,8 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   // host-operand MSM whose points are still arriving in K parts (upload_operands): ONE digit/sort pass with the part as the major
   // sort key -- bucket ids (part, unit, digit) -- then one accumulation per part as it lands, all parts adding into the SAME
   // bucket values (k_accumulate's `into`), so the reduction and combination are those of a single MSM
+  if (opt.halves && opt.split_sort && nmsm == 1 && !point_idx && !d_offsets && T >= 64 && opt.parts >= 2 && opt.parts <= 8)
+    return msm_run_parts(points, scalars, T, (u32)opt.parts, out_affine, out_xyzz);
   const bool halves = opt.halves && nmsm == 1 && !point_idx && !d_offsets && T >= 64 && opt.parts >= 2 && opt.parts <= 8;
   if (opt.halves && !halves) BP_CUDA(cudaStreamWaitEvent(st, g.ev_half[opt.parts - 1], 0));      // (cannot happen today: such MSMs have >= 2^17 terms)
   const u32 K = halves ? (u32)opt.parts : 1;
@@ -447,13 +526,21 @@ static int upload_operands(Affine* d_pts, const uint8_t* pts64, Fq* d_sc, const 
     // accumulation of a quarter (0.49 ms) roughly matches its upload (0.44 ms at the 36-38 GB/s this host sustains), so the GPU
     // neither waits for the last part nor starts late (profiles/r2_e2e_timeline.txt)
     static const int parts = [] { const char* e = getenv("BP_E2E_PARTS"); int v = e ? atoi(e) : 4; return v >= 2 && v <= 8 ? v : 4; }();
-    opt->parts = parts;
+    static const bool split_sort = [] { const char* e = getenv("BP_E2E_ONE_SORT"); return !(e && atoi(e)); }();
+    opt->parts = parts; opt->split_sort = split_sort;
     g.dbg_rec(0, g.copy_stream);
-    BP_CUDA(h2d_chunked(d_sc, sc32, n * 32, g.copy_stream));
-    g.dbg_rec(1, g.copy_stream);
+    if (!split_sort) {
+      BP_CUDA(h2d_chunked(d_sc, sc32, n * 32, g.copy_stream));
+      g.dbg_rec(1, g.copy_stream);
+    }
     BP_CUDA(cudaEventRecord(g.ev_sc, g.copy_stream));
     for (int k = 0; k < parts; k++) {                      // part k = terms [n*k/K, n*(k+1)/K)  (the same cut as msm_run's)
       const size_t lo = (size_t)((unsigned long long)n * k / parts), hi = (size_t)((unsigned long long)n * (k + 1) / parts);
+      if (split_sort) {                                    // the part's scalars first: its sort starts while its points are on the wire
+        BP_CUDA(h2d_chunked(d_sc + lo, sc32 + lo * 32, (hi - lo) * 32, g.copy_stream));
+        BP_CUDA(cudaEventRecord(g.ev_part_sc[k], g.copy_stream));
+        if (k == 0) g.dbg_rec(1, g.copy_stream);
+      }
       BP_CUDA(h2d_chunked(d_pts + lo, pts64 + lo * 64, (hi - lo) * 64, g.copy_stream));
       BP_CUDA(cudaEventRecord(g.ev_half[k], g.copy_stream));
       if (k == 0) g.dbg_rec(2, g.copy_stream);
@@ -635,6 +722,7 @@ int bp_init(int device) {
   BP_CUDA(cudaEventCreateWithFlags(&g.ev_pts, cudaEventDisableTiming)); BP_CUDA(cudaEventCreateWithFlags(&g.ev_copy_gate, cudaEventDisableTiming));
   BP_CUDA(cudaEventCreateWithFlags(&g.ev_sc, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++) BP_CUDA(cudaEventCreateWithFlags(&g.ev_half[i], cudaEventDisableTiming));
+  for (int i = 0; i < 8; i++) BP_CUDA(cudaEventCreateWithFlags(&g.ev_part_sc[i], cudaEventDisableTiming));
   g.inited = true;
   return 0;
 }

@@ -47,7 +47,7 @@ struct Ctx {
   cudaEvent_t ev_pts = nullptr, ev_copy_gate = nullptr;
   // large host-operand MSMs: the points arrive in two halves (ev_half[0], ev_half[1]); msm_run then runs the MSM as two
   // half-size MSMs over one sort so that the first half is accumulated while the second is still on the wire
-  cudaEvent_t ev_half[8] = {nullptr}, ev_sc = nullptr;
+  cudaEvent_t ev_half[8] = {nullptr}, ev_part_sc[8] = {nullptr}, ev_sc = nullptr;
   DevBuf ws_halfoff;
   cudaEvent_t dbg_ev[12] = {nullptr}; bool dbg_e2e = false;      // BP_E2E_TIMING: timeline of a host-operand MSM (development aid)
   void dbg_rec(int i, cudaStream_t st) { if (!dbg_e2e) return; if (!dbg_ev[i]) cudaEventCreate(&dbg_ev[i]); cudaEventRecord(dbg_ev[i], st); }
