@@ -191,7 +191,24 @@ def pack_scalar(k):
 
 
 def pack_scalars(ks):
-    return b"".join([(k % Q).to_bytes(32, "little") for k in ks])
+    """32-byte little-endian wire form of a scalar list (ints or ModP-like objects with .x), reduced mod q."""
+    try:                # the common case -- every value already in [0, 2^256): no big-int division per element
+        return b"".join([getattr(k, "x", k).to_bytes(32, "little") for k in ks]) if _all_reduced(ks) else _pack_scalars_slow(ks)
+    except (OverflowError, AttributeError):
+        return _pack_scalars_slow(ks)
+
+
+def _all_reduced(ks):
+    q = Q
+    for k in ks:
+        v = getattr(k, "x", k)
+        if not (0 <= v < q):
+            return False
+    return True
+
+
+def _pack_scalars_slow(ks):
+    return b"".join([(int(getattr(k, "x", k)) % Q).to_bytes(32, "little") for k in ks])
 
 
 def unpack_scalars(b, n):
