@@ -638,6 +638,27 @@ __global__ void __launch_bounds__(256) k_pipe_probe(u32* out, u32 seed, int iter
 #pragma unroll
       for (int i = 0; i < 9; i++) s ^= acc[j][i];
     if (s == 0x1234567u) out[0] = s;
+  } else if (MODE == 10 || MODE == 11) {
+    // 10: DFMA alone (fp64 pipe); 11: the same 32 DFMA per iteration interleaved with 32 IMAD.WIDE (fmaheavy pipe): do the two issue
+    // side by side?  (next-step question of DESIGN.md 5: 52-bit limbs on the FP64 pipe next to / instead of 32-bit limbs on IMAD.WIDE)
+    double f[16];
+    u64 p[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { f[i] = (double)(a + i) * 1.0000001; p[i] = ((u64)(a + i) << 32) | (b + 7 * i); }
+    const double m = 1.0 + (double)(b & 7) * 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(f[i]) : "d"(m), "d"(f[(i + 5) & 15]));
+          if (MODE == 11) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p[i]) : "r"((u32)p[i]), "r"((u32)(p[i] >> 32)));
+        }
+    }
+    double sd = 0; u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { sd += f[i]; s ^= p[i]; }
+    if (sd == 1.2345 || s == 0x1234567u) out[0] = (u32)s;
   } else if (MODE == 4) {
     u32 p[16];
 #pragma unroll
@@ -1042,7 +1063,9 @@ static int pipe_probe(int mode, int iters, double* ops_per_s, float* ms_out) {
       case 7: ++g.nlaunch, k_pipe_probe<7><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
       case 8: ++g.nlaunch, k_pipe_probe<8><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
       case 9: ++g.nlaunch, k_pipe_probe<9><<<1, 32, 0, g.stream>>>(d, 12345u, n); break;
-      default: return fail("bp_pipe_probe: mode 0..9");
+      case 10: ++g.nlaunch, k_pipe_probe<10><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      case 11: ++g.nlaunch, k_pipe_probe<11><<<blocks, 256, 0, g.stream>>>(d, 12345u, n); break;
+      default: return fail("bp_pipe_probe: mode 0..11");
     }
     BP_CUDA(cudaEventRecord(g.ev_b, g.stream));
     BP_CUDA(cudaEventSynchronize(g.ev_b));

@@ -10,8 +10,9 @@ nat.init(0)
 lib = nat.load()
 names = {0: "IMAD.WIDE.U32 Rd,Ra,Rb,RZ (32x32->64 product)", 1: "IMAD (32-bit mad.lo + accumulate)",
          2: "IMAD.WIDE.U32(.X) carry-chained rows (as in fp_mul)", 3: "fp_mul (field multiplications)",
-         4: "32-bit add (IADD3 + IMAD.IADD, both pipes)", 5: "fp_sqr (field squarings)"}
-for mode in (0, 1, 2, 4, 3, 5):
+         4: "32-bit add (IADD3 + IMAD.IADD, both pipes)", 5: "fp_sqr (field squarings)",
+         10: "DFMA (fma.rz.f64) alone", 11: "DFMA interleaved 1:1 with IMAD.WIDE (counted: DFMA only)"}
+for mode in (0, 1, 2, 4, 10, 11, 3, 5):
     for iters in ((1 << 14), (1 << 16)) if mode not in (3, 5) else ((1 << 9), (1 << 11)):
         ops, ms = ctypes.c_double(), ctypes.c_float()
         nat.check(lib.bp_pipe_probe(mode, iters, ctypes.byref(ops), ctypes.byref(ms)))
