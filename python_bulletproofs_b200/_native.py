@@ -31,6 +31,7 @@ PROTOTYPES = {
     "bp_points_precompute": (ctypes.c_int, [c_h, ctypes.c_int]),
     "bp_msm_set_pre_chunk": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_affine_passes": (ctypes.c_int, [ctypes.c_int]),
+    "bp_msm_set_small_graphs": (ctypes.c_int, [ctypes.c_int]),
     "bp_points_pre_info": (ctypes.c_int, [c_h, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint64)]),
     "bp_msm_h": (ctypes.c_int, [c_h, c_u8p, c_sz, c_u8p]),
     "bp_msm_hh": (ctypes.c_int, [c_h, c_h, c_sz, c_u8p]),

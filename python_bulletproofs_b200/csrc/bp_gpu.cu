@@ -874,11 +874,69 @@ int bp_handle_free(bp_handle h) {
   return 0;
 }
 
+// Small MSMs over a resident vector (<= 2^16 terms) are ~18 short stream operations: as a CUDA graph, captured the second time the
+// same (vector, slice, scalars, output) combination is seen and replayed while no workspace has moved, the gaps between them
+// shrink from a launch each to a graph-node hand-over (bp_msm_set_small_graphs(0) turns it off; profiling runs eagerly).
+struct PreGraph { const void* pre; u32 stride, first; int c; const void* sc; u32 T; void* oa; void* ox; unsigned long long gen, stamp; cudaGraphExec_t exec; unsigned nk; int seen; };
+static std::vector<PreGraph> g_pre_graphs;
+static unsigned long long g_pre_graph_clock = 0;
+static bool g_small_graphs = true;
+static void pre_graphs_clear() { for (auto& e : g_pre_graphs) if (e.exec) cudaGraphExecDestroy(e.exec); g_pre_graphs.clear(); }
+static int msm_run_pre_small(const Affine* pre, u32 stride, u32 first, int c, const Fq* scalars, u32 T, Affine* out_affine, XYZZ* out_xyzz) {
+  if (!g_small_graphs || T == 0 || T > (1u << 16) || g.profiling || g.aff_passes > 0 || g.pre_chunk)
+    return msm_run_pre(pre, stride, first, c, scalars, T, out_affine, out_xyzz);
+  PreGraph* hit = nullptr;
+  for (auto& e : g_pre_graphs)
+    if (e.pre == pre && e.stride == stride && e.first == first && e.c == c && e.sc == scalars && e.T == T && e.oa == out_affine && e.ox == out_xyzz) { hit = &e; break; }
+  if (hit && hit->exec && hit->gen == alloc_generation()) {
+    hit->stamp = ++g_pre_graph_clock;
+    BP_CUDA(cudaGraphLaunch(hit->exec, g.stream));
+    g.nlaunch += hit->nk;
+    const PreShape ps = pre_shape(c);
+    g.last_c = c; g.last_nb = ps.H;
+    return 0;
+  }
+  if (!hit) {                                             // first sighting: run eagerly (this also sizes every workspace)
+    if (g_pre_graphs.size() >= 32) {                      // drop the least recently used
+      size_t v = 0;
+      for (size_t i = 1; i < g_pre_graphs.size(); i++) if (g_pre_graphs[i].stamp < g_pre_graphs[v].stamp) v = i;
+      if (g_pre_graphs[v].exec) cudaGraphExecDestroy(g_pre_graphs[v].exec);
+      g_pre_graphs.erase(g_pre_graphs.begin() + (long)v);
+    }
+    g_pre_graphs.push_back(PreGraph{pre, stride, first, c, scalars, T, out_affine, out_xyzz, 0, ++g_pre_graph_clock, nullptr, 0, 1});
+    return msm_run_pre(pre, stride, first, c, scalars, T, out_affine, out_xyzz);
+  }
+  // seen before (or its graph went stale with a workspace move): capture, instantiate, launch
+  if (hit->exec) { cudaGraphExecDestroy(hit->exec); hit->exec = nullptr; }
+  cudaGraph_t graph = nullptr;
+  const unsigned long long l0 = g.nlaunch, gen0 = alloc_generation();
+  BP_CUDA(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed));
+  const int rc = msm_run_pre(pre, stride, first, c, scalars, T, out_affine, out_xyzz);
+  const cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+  const unsigned nk = (unsigned)(g.nlaunch - l0);
+  g.nlaunch = l0;
+  if (rc || ce != cudaSuccess || !graph || gen0 != alloc_generation()) {      // (a workspace grew during the capture: eager this time)
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    return msm_run_pre(pre, stride, first, c, scalars, T, out_affine, out_xyzz);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ci != cudaSuccess || !exec) { cudaGetLastError(); return msm_run_pre(pre, stride, first, c, scalars, T, out_affine, out_xyzz); }
+  hit->exec = exec; hit->nk = nk; hit->gen = gen0; hit->stamp = ++g_pre_graph_clock;
+  BP_CUDA(cudaGraphLaunch(exec, g.stream));
+  g.nlaunch += nk;
+  return 0;
+}
+
 // MSM over points [first, first + n) of a resident vector: through its precomputed window multiples when it has them
 static int handle_msm(const HandleRec& P, size_t first, const Fq* d_sc, size_t n, Affine* out_affine, XYZZ* out_xyzz) {
-  if (P.pre && g.force_c == 0) return msm_run_pre(P.pre, (u32)P.n, (u32)first, P.pre_c, d_sc, (u32)n, out_affine, out_xyzz);
+  if (P.pre && g.force_c == 0) return msm_run_pre_small(P.pre, (u32)P.n, (u32)first, P.pre_c, d_sc, (u32)n, out_affine, out_xyzz);
   return msm_run((const Affine*)P.p + first, nullptr, d_sc, (u32)n, nullptr, 1, n, out_affine, out_xyzz);
 }
+
+extern "C" int bp_msm_set_small_graphs(int on) { g_small_graphs = on != 0; if (!on) { if (g.inited) cudaStreamSynchronize(g.stream); pre_graphs_clear(); } return 0; }
 
 static int handle_msm_to_host(const HandleRec& P, size_t first, const Fq* d_sc, size_t n, uint8_t* out64) {
   Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
