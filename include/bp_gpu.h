@@ -55,7 +55,7 @@ int bp_handle_free(bp_handle h);
  * bp_msm_set_window(c > 0) forces the plain bucket method again. */
 int bp_points_precompute(bp_handle points, int window_bits);
 int bp_points_pre_info(bp_handle points, int* window_bits, int* windows, uint64_t* bytes);
-int bp_msm_set_small_graphs(int on);      /* MSMs of <= 2^16 terms over a precomputed vector as replayed CUDA graphs (default on) */
+int bp_msm_set_small_graphs(int on);      /* MSMs of <= 2^17 terms over a precomputed vector as replayed CUDA graphs (default on) */
 int bp_msm_set_affine_passes(int passes); /* batched-affine pair passes ahead of the XYZZ accumulation on that path: experiment switch, <= 0 = off (default): measured slower at 2^20, see DESIGN.md 5 */
 int bp_msm_set_pre_chunk(int entries);   /* experiment switch: entries per accumulation thread on that path (0 = automatic) */
 int bp_msm_h(bp_handle points, const uint8_t* sc32, size_t n, uint8_t out64[64]);     /* scalars from host */

@@ -874,7 +874,7 @@ int bp_handle_free(bp_handle h) {
   return 0;
 }
 
-// Small MSMs over a resident vector (<= 2^16 terms) are ~18 short stream operations: as a CUDA graph, captured the second time the
+// Small MSMs over a resident vector (<= 2^17 terms) are ~18 short stream operations: as a CUDA graph, captured the second time the
 // same (vector, slice, scalars, output) combination is seen and replayed while no workspace has moved, the gaps between them
 // shrink from a launch each to a graph-node hand-over (bp_msm_set_small_graphs(0) turns it off; profiling runs eagerly).
 struct PreGraph { const void* pre; u32 stride, first; int c; const void* sc; u32 T; void* oa; void* ox; unsigned long long gen, stamp; cudaGraphExec_t exec; unsigned nk; int seen; };
@@ -883,7 +883,7 @@ static unsigned long long g_pre_graph_clock = 0;
 static bool g_small_graphs = true;
 static void pre_graphs_clear() { for (auto& e : g_pre_graphs) if (e.exec) cudaGraphExecDestroy(e.exec); g_pre_graphs.clear(); }
 static int msm_run_pre_small(const Affine* pre, u32 stride, u32 first, int c, const Fq* scalars, u32 T, Affine* out_affine, XYZZ* out_xyzz) {
-  if (!g_small_graphs || T == 0 || T > (1u << 16) || g.profiling || g.aff_passes > 0 || g.pre_chunk)
+  if (!g_small_graphs || T == 0 || T > (1u << 17) || g.profiling || g.aff_passes > 0 || g.pre_chunk)
     return msm_run_pre(pre, stride, first, c, scalars, T, out_affine, out_xyzz);
   PreGraph* hit = nullptr;
   for (auto& e : g_pre_graphs)
