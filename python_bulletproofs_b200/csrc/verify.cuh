@@ -294,6 +294,9 @@ __global__ void __launch_bounds__(128) k_rp_lookup(const Affine* __restrict__ ta
     st_xyzz(part + ((size_t)(e * nproofs + p) * BP_RP_SLOTS + 32 * s + lane), acc);
   }
 }
+// (Measured and not kept, round 2: cutting the block's 101 steps into four equal ranges, segment sums merged through shared memory --
+// the E1/E3 warp is idle after 2 steps while the others take 33-34 -- left the kernel at 3.29 ms per 8192 proofs: it is not bound by
+// the longest warp of a block but by the chip-wide rate of dependent table-load + addition chains.)
 // Same with the 16-bit table: lane l owns window l & 15 of the (l >> 4)-th of two terms taken per step, so a term costs 16
 // lookups; the table lives in HBM (8.9 GB), hence the next entry is loaded into registers under the current addition.
 __global__ void __launch_bounds__(128) k_rp_lookup16(const Affine* __restrict__ tab16, const u32* __restrict__ idx, const Fq* __restrict__ sc,
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(128) k_rp_lookup16(const Affine* __restrict__ 
           if (d) { nxt = ld_affine(tab16 + fb_index16(gi, win, d)); nhave = true; }
         }
       }
-      if (have) xyzz_madd_ni(acc, cur);
+      if (have) xyzz_madd(acc, cur);                     // inlined: 128 registers, no stack traffic for the accumulator (7.40 -> 7.33 ms per 8192 proofs)
       cur = nxt; have = nhave;
       if (!__any_sync(BP_FULL_MASK, in)) break;          // both term slots of the warp are past the end
     }
