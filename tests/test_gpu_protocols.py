@@ -299,6 +299,45 @@ def test_aggreg_batch_verify_decisions(n, m, count):
         assert quiet(AggregRangeVerifier(Vs_list[i], g, h, gs, hs, u, proofs[i]).verify) is want[i]
 
 
+def test_aggreg_batch_verify_off_curve_points_and_slot_forms():
+    """bp_rp_verify_aggreg_batch on inputs the class API can never build or compares as strings: proof points that are not on
+    secp256k1 (fastecdsa's constructor would raise) are rejected on both paths; a leading zero in a challenge slot is a
+    different string (reject), leading zeros in the y slot are the same number (accept)."""
+    from python_bulletproofs_b200.rangeproofs import AggregNIRangeProver
+    from python_bulletproofs_b200.rangeproofs.batch import PackedAggregBatch, verify_aggreg_packed
+    n, m, count = 8, 2, 8
+    nm, L = n * m, 4
+    ogs, ohs, og, oh, ou = gens(nm, ["aoc%d" % i for i in range(5)])
+    gs, hs, g, h, u = [P_(t) for t in ogs], [P_(t) for t in ohs], P_(og), P_(oh), P_(ou)
+    rng = random.Random(77)
+    Vs_list, proofs = [], []
+    for i in range(count):
+        vs = [M_(rng.getrandbits(n)) for _ in range(m)]
+        gammas = [mod_hash(b"gq%d_%d" % (i, j), Q) for j in range(m)]
+        Vs_list.append([commitment(g, h, vs[j], gammas[j]) for j in range(m)])
+        proofs.append(AggregNIRangeProver(vs, n, g, h, gs, hs, gammas, u, secp256k1, b"aq%d" % i).prove())
+    def edit(tr, slot, fn):
+        parts = tr.split(b"&"); parts[slot] = fn(parts[slot]); return b"&".join(parts)
+    p2 = proofs[5].innerProof.proof2
+    p2.transcript = edit(p2.transcript, p2.start_transcript + 2, lambda s_: b"0" + s_)          # reject
+    proofs[6].transcript = edit(proofs[6].transcript, 3, lambda s_: b"00" + s_)                # same number: accept
+    batch = PackedAggregBatch.from_proofs(Vs_list, proofs, n)
+    stride = batch.stride
+    assert stride == nat.load().bp_rp_aggreg_proof_stride(n, m) == 64 * m + 4 * 64 + 3 * 32 + 2 * 64 + 2 * 32 + 32 * L + 128 * L
+    rec = bytearray(batch.records)
+    oV1, oT1, oPnew, oR0 = 64, 64 * m + 128, 64 * m + 256 + 96 + 64, 64 * m + 256 + 96 + 128 + 64 + 32 * L + 64 * L
+    for k, o in enumerate((oV1, oT1, oPnew, oR0)):
+        base = (k + 1) * stride + o
+        if k % 2 == 0:
+            rec[base + 32] ^= 1                                  # y altered: not on the curve
+        else:
+            rec[base:base + 32] = (ecc.P + 5).to_bytes(32, "little")      # x >= p: not canonical
+    batch.records = bytes(rec)
+    want = bytes([1, 0, 0, 0, 0, 0, 1, 1])
+    for _ in range(3):                                           # bucket method over the generator rows, then the byte table
+        assert verify_aggreg_packed(batch, g, h, gs, hs, u) == want
+
+
 def _small_batch(n, count, tag):
     seeds = [tag + "%d" % i for i in range(5)]
     ogs, ohs, og, oh, ou = gens(n, seeds)
