@@ -45,8 +45,8 @@ gs4, hs4, g4, h4, u4 = gens(n * m, b"agg")
 vs = [ModP((0x9E3779B97F4A7C15 * (j + 1)) % 2 ** 64, q) for j in range(m)]
 gammas = [mod_hash(b"g%d" % j, q) for j in range(m)]
 Vs = [commitment(g4, h4, vs[j], gammas[j]) for j in range(m)]
-pr4 = T("C4 aggregated prove m=16 x 64", lambda: AggregNIRangeProver(vs, n, g4, h4, gs4, hs4, gammas, u4, secp256k1, b"y").prove(), reps=2)
-T("C4 aggregated verify", lambda: AggregRangeVerifier(Vs, g4, h4, gs4, hs4, u4, pr4).verify(), reps=2)
+pr4 = T("C4 aggregated prove m=16 x 64", lambda: AggregNIRangeProver(vs, n, g4, h4, gs4, hs4, gammas, u4, secp256k1, b"y").prove(), reps=6)
+T("C4 aggregated verify", lambda: AggregRangeVerifier(Vs, g4, h4, gs4, hs4, u4, pr4).verify(), reps=6)
 # C5
 rng = random.Random(5)
 Vl, pl = [], []
