@@ -518,7 +518,7 @@ def bench_verify(args, nat, dist, rank, world, imad_peak):
                        "generator_terms_per_proof": nfix, "proof_point_terms_per_proof": nv + 4,
                        "gpu_ms": round(span, 3), "gpu_ms_note": "CUDA events on the library stream: first kernel of the first chunk .. last accept kernel "
                        "(includes any wait for host transcript checks between chunks), max over ranks",
-                       "kernel_list": "profiles/r2_verify_kernels.csv (ncu --metrics gpu__time_duration.sum of one batch)", "traffic": None}
+                       "kernel_list": "profiles/r2_verify_kernels_v3.csv (ncu --metrics gpu__time_duration.sum of one batch, tools/ncu_verify.sh)", "traffic": None}
     if rank == 0:
         # ---- decisions against the ORACLE verifier: the first 128 proofs of this rank's block (incl. every corrupted one in
         #      the sample), and the prover's output against the oracle prover on 16 proofs (byte-identical transcripts)
