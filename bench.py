@@ -557,7 +557,7 @@ def bench_verify(args, nat, dist, rank, world, imad_peak):
     return res
 
 
-def bench_verify_aggregated(nat, q, m=16, nbits=64, distinct=32, total=1024):
+def bench_verify_aggregated(nat, q, m=16, nbits=64, distinct=32, total=2048):
     """Widening row (BASELINE config 4 as a batch): `total` aggregated range proofs (m values x nbits bits, n*m = 1024 generators per
     side) through bp_rp_verify_aggreg_batch in one call -- `distinct` different proofs tiled (proving 1024 of them would take the
     bench 3 s more for nothing: the verifier does the same work per record), every 8th distinct proof corrupted; decisions of the
