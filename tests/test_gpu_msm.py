@@ -104,6 +104,28 @@ def test_host_operand_msm_in_two_halves(n):
     lib.bp_handle_free(hp)
 
 
+@pytest.mark.parametrize("n", [(1 << 17) + 12345, (1 << 17), 300007])
+def test_msm_host_operands_in_parts(n):
+    """bp_msm with HOST operands of >= 2^17 terms takes them as K x [scalars | points], sorts every part on a side stream and
+    accumulates all parts into one bucket set (msm_run_parts): odd sizes (uneven parts), repeated points (P + P across parts),
+    P and -P, identity points, adversarial scalars -- against the oracle."""
+    base = fast_points(64, 99)
+    rng = random.Random(n)
+    pts = [base[rng.randrange(64)] for _ in range(n)]
+    for i in range(0, n, 1001):
+        pts[i] = None
+    for i in range(5, n, 4099):
+        pts[i] = ecc.point_neg(pts[i - 1]) if pts[i - 1] is not None else pts[i]
+    ks = [rng.getrandbits(256) for _ in range(n)]
+    for i in range(0, n, 53):
+        ks[i] = [0, 1, Q - 1, Q, 2 ** 256 - 1, 2 ** 128, ks[1]][(i // 53) % 7]
+    pb = ecc.pack_points(pts)
+    sb = b"".join(k.to_bytes(32, "little") for k in ks)
+    want = ecc.msm_bytes(pb, sb, n, "bucket", ecc.max_threads())
+    for _ in range(2):
+        assert gpu_msm_raw(pb, sb, n) == want
+
+
 def test_msm_full_size_properties():
     """BASELINE size 2^20: slice additivity + linearity + agreement with the multi-threaded oracle."""
     n = 1 << 20
