@@ -555,15 +555,6 @@ __global__ void __launch_bounds__(32) k_finish(const XYZZ* __restrict__ acc_in, 
   if (out) st_affine(out, xyzz_to_affine(acc, true));
 }
 
-// result of a host-operand MSM that ran as two halves: out = in[0] + in[1]
-__global__ void __launch_bounds__(32) k_xyzz_pair(const XYZZ* __restrict__ in, Affine* __restrict__ out, XYZZ* __restrict__ out_xyzz) {
-  if (threadIdx.x != 0) return;
-  XYZZ acc = ld_xyzz(in), v = ld_xyzz(in + 1);
-  xyzz_add_ni(acc, v);
-  if (out_xyzz) st_xyzz(out_xyzz, acc);
-  if (out) st_affine(out, xyzz_to_affine(acc, true));
-}
-
 // one QUAD per msm: Horner over windows (c doublings each), then canonical affine (optionally XYZZ partials for sharding)
 __global__ void __launch_bounds__(128) k_combine(const XYZZ* __restrict__ winsum, MsmShape sh, size_t nmsm, Affine* __restrict__ out,
                                                  XYZZ* __restrict__ out_xyzz) {
