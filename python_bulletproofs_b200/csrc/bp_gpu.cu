@@ -748,10 +748,12 @@ int bp_init(int device) {
   return 0;
 }
 
+static void pre_graphs_clear();
 int bp_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g.inited) return 0;
   cudaStreamSynchronize(g.stream);
+  pre_graphs_clear();
   for (auto& kv : g_handles) { cudaFree(kv.second.p); if (kv.second.pre) cudaFree(kv.second.pre); }
   g_handles.clear();
   fb_release_all();
