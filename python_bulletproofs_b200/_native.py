@@ -29,6 +29,8 @@ PROTOTYPES = {
     "bp_scalars_upload": (ctypes.c_int, [c_u8p, c_sz, ctypes.POINTER(c_h)]),
     "bp_handle_free": (ctypes.c_int, [c_h]),
     "bp_points_precompute": (ctypes.c_int, [c_h, ctypes.c_int]),
+    "bp_msm_set_chunk_fit": (ctypes.c_int, [ctypes.c_int]),
+    "bp_msm_set_tails2d": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_pre_chunk": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_affine_passes": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_small_graphs": (ctypes.c_int, [ctypes.c_int]),

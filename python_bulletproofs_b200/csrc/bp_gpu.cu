@@ -39,11 +39,13 @@ int fail(const char* fmt, ...) {
 // ---- bucket reduction + window combination (the "tails") of nmsm MSMs whose nmsm * sh.U bucket units are complete ----------
 static int msm_tails(const XYZZ* buckets, const MsmShape& sh, u32 nmsm, Affine* out_affine, XYZZ* out_xyzz, bool prof, cudaStream_t st) {
   const size_t nmw = (size_t)nmsm * sh.U;
-  XYZZ* segsum = (XYZZ*)g.ws_segsum.ensure(nmw * sh.nseg * sizeof(XYZZ));
-  XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure(nmw * sizeof(XYZZ));
+  const bool plain_tails = nmsm >= 2048 && sh.H <= 512;     // big batch of small MSMs: throughput forms
+  const bool tails2d = !plain_tails && sh.seg_plain && sh.H >= 4096 && g.tails2d;
+  const size_t nb_all = nmw * sh.H;
+  XYZZ* segsum = (XYZZ*)g.ws_segsum.ensure((tails2d ? nb_all / 4 + 4096 : nmw * sh.nseg) * sizeof(XYZZ));
+  XYZZ* winsum = (XYZZ*)g.ws_winsum.ensure((tails2d ? 2 : 1) * nmw * sizeof(XYZZ));
   if (!segsum || !winsum) return fail("workspace allocation failed");
   size_t nsegs = nmw * sh.nseg;
-  const bool plain_tails = nmsm >= 2048 && sh.H <= 512;     // big batch of small MSMs: throughput forms
   const XYZZ* ws;
   if (plain_tails) {
     ++g.nlaunch, k_reduce_unit_plain<<<(unsigned)((nmw + 127) / 128), 128, 0, st>>>(buckets, sh, nmw, segsum);
@@ -53,6 +55,29 @@ static int msm_tails(const XYZZ* buckets, const MsmShape& sh, u32 nmsm, Affine* 
     // ~126 doublings is pure latency and the 4-lane form (2.3 -> 1.3 us per doubling) wins
     if (nmsm <= 12288 && !out_affine) ++g.nlaunch, k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
     else ++g.nlaunch, k_combine_plain<<<(unsigned)((nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
+  } else if (tails2d) {
+    // wide units (a large single MSM at c = 16: 9 units of 2^15 buckets): the 2-D marginal reduction of the pre path, all units
+    // side by side -- plain sums of independent thread-level additions down to R + C marginals per unit, only those take a
+    // (<= 9-bit) weight.  Unit u's window sum leaves k_pre_total as two addends; k_combine (pair mode) adds them in its Horner pass.
+    // Parity-green, measured on B200 and left OFF (gpurun_out/tails2d.log): reduce stage 0.300 -> 0.452 ms at 2^20 (2^17: 0.308 ->
+    // 0.450), e2e 2^20 3.48 -> 3.66 ms.  What is a latency chain for ONE unit (pre path: 0.06 + 0.13 ms) turns throughput bound
+    // for nine: 3456 weighted-marginal blocks of 16 quads are three waves of the 4-lane cooperative form, which pays ~2.4x the
+    // multiplications' issue cost in glue; the running-sum levels below do 2 additions per bucket in thread-level form instead.
+    const int lgH = sh.c - 1, lgC = (lgH + 1) / 2, lgR = lgH - lgC;
+    const u32 C = 1u << lgC, R = 1u << lgR;
+    const size_t nb = nb_all;
+    XYZZ* ping = segsum; XYZZ* two = winsum;
+    XYZZ* wsum = (XYZZ*)g.ws_grpsum.ensure(nmw * (size_t)(C + R) * sizeof(XYZZ));
+    if (!wsum) return fail("workspace allocation failed");
+    const u32 Kr = 8, Kc = 8, np_r = C / Kr, np_c = R / Kc;
+    XYZZ* rpart = ping; XYZZ* cpart = ping + (nb / 8 + 2048);
+    const u32 nrow_out = R * np_r, ncol_out = np_c * C;
+    ++g.nlaunch, k_pre_marginals<<<dim3(((nrow_out > ncol_out ? nrow_out : ncol_out) + 127) / 128, 2, (unsigned)nmw), 128, 0, st>>>(
+        buckets, rpart, nrow_out, Kr, buckets, cpart, np_c, C, Kc, sh.H);
+    ++g.nlaunch, k_pre_rowcol<<<dim3(C + R, (unsigned)nmw), 64, 0, st>>>(rpart, np_r, cpart, np_c, C, R, wsum, (u32)sh.U, sh.dbl);
+    ++g.nlaunch, k_pre_total<<<dim3(2, (unsigned)nmw), 256, 0, st>>>(wsum, C, R, two, lgC);
+    if (prof) cudaEventRecord(g.ev[5], st);
+    ++g.nlaunch, k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(two, sh, nmsm, out_affine, out_xyzz, 1);
   } else {
     XYZZ* seg_run = (XYZZ*)g.ws_segrun.ensure(nsegs * sizeof(XYZZ));
     if (!seg_run) return fail("workspace allocation failed");
@@ -380,7 +405,7 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
   MsmShape sh;                                         // shape of the tails: ONE unit of H buckets, nothing to combine
   sh.c = c; sh.W = 1; sh.U = 1; sh.dbl = 0; sh.H = ps.H;
   const double ent_bound = (double)ps.W * (double)T;
-  sh.chunk = ent_bound <= 1300000.0 ? 8 : (ent_bound <= 2600000.0 ? 16 : BP_CHUNK);
+  sh.chunk = acc_chunk(ent_bound);
   if (g.pre_chunk) sh.chunk = g.pre_chunk;
   sh.seg_plain = (double)sh.H / 4 >= 32768.0 ? 1 : 0;
   sh.S = sh.seg_plain ? 4 : (sh.H < 8 ? sh.H : 8);
@@ -406,7 +431,7 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
   if (emax_pad >= 0xFFFFFFF0ull) return fail("msm: too many entries");
   if (P) {                                                              // the XYZZ stage sees 1/2^P of the entries
     const double red = (double)(emax_pad >> P);
-    sh.chunk = red <= 1300000.0 ? 8 : (red <= 2600000.0 ? 16 : BP_CHUNK);
+    sh.chunk = acc_chunk(red);
     if (g.pre_chunk) sh.chunk = g.pre_chunk;
   }
   const size_t nchunks = ((P ? (emax_pad >> P) : emax) + sh.chunk - 1) / sh.chunk;
@@ -735,6 +760,7 @@ int bp_init(int device) {
   BP_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail("bp_init: device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
   g.device = device; g.sm_count = prop.multiProcessorCount;
+  acc_slots() = (unsigned)g.sm_count * BP_ACC_MINB * 128u;
   BP_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (int i = 0; i < 8; i++) BP_CUDA(cudaEventCreate(&g.ev[i]));
   BP_CUDA(cudaEventCreate(&g.ev_a)); BP_CUDA(cudaEventCreate(&g.ev_b));
@@ -796,6 +822,7 @@ int bp_msm_last_entries(uint64_t* entries) {      // non-zero digits = mixed add
 }
 int bp_launch_count(uint64_t* launches) { *launches = g.nlaunch; return 0; }
 int bp_msm_set_affine_passes(int passes) { g.aff_passes = passes < 0 ? -1 : (passes > 6 ? 6 : passes); return 0; }   /* experiment switch */
+int bp_msm_set_tails2d(int on) { g.tails2d = on != 0; return 0; }   /* experiment switch */
 int bp_msm_set_pre_chunk(int entries) { g.pre_chunk = entries > 0 ? (unsigned)entries : 0; return 0; }   /* experiment switch */
 int bp_msm_set_profiling(int on) { g.profiling = on != 0; return 0; }
 int bp_msm_set_pipeline_min(size_t min_terms) { g.pipeline_min_terms = min_terms ? (unsigned)min_terms : 0xFFFFFFFFu; return 0; }
@@ -938,6 +965,12 @@ static int handle_msm(const HandleRec& P, size_t first, const Fq* d_sc, size_t n
   return msm_run((const Affine*)P.p + first, nullptr, d_sc, (u32)n, nullptr, 1, n, out_affine, out_xyzz);
 }
 
+extern "C" int bp_msm_set_chunk_fit(int on) {   /* experiment switch; cached small-MSM graphs carry the chunk they were captured with */
+  acc_chunk_fit() = on ? 1 : 0;
+  if (g.inited) cudaStreamSynchronize(g.stream);
+  pre_graphs_clear();
+  return 0;
+}
 extern "C" int bp_msm_set_small_graphs(int on) { g_small_graphs = on != 0; if (!on) { if (g.inited) cudaStreamSynchronize(g.stream); pre_graphs_clear(); } return 0; }
 
 static int handle_msm_to_host(const HandleRec& P, size_t first, const Fq* d_sc, size_t n, uint8_t* out64) {

@@ -54,6 +54,7 @@ struct Ctx {
   bool profiling = false;
   int force_c = 0, last_c = 0;
   bool pre_attr_set = false; unsigned pre_chunk = 0;
+  bool tails2d = false;       // 2-D marginal bucket reduction for the wide units of a large plain MSM (bp_msm_set_tails2d): measured slower, off
   int aff_passes = -1;                          // batched-affine pair passes ahead of the XYZZ accumulation: <= 0 = off (default), 1..6 = that many passes (bp_msm_set_affine_passes)
   DevBuf ws_aff_a, ws_aff_b, ws_aff_scr, ws_aff_ent, ws_aff_start, ws_aff_ctr;
   unsigned long long nlaunch = 0;               // kernels launched by this library so far (bp_launch_count)

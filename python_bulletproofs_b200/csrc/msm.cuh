@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include "ec.cuh"
 #include "fq.cuh"
 #include "glv.cuh"
@@ -46,6 +47,25 @@ struct MsmShape {
   u32 nseg;       // segments per window
 };
 #define BP_GLV_BITS 128
+
+// Entries per accumulation thread.  Every k_accumulate thread performs exactly `chunk` mixed additions and BP_ACC_MINB blocks
+// of 128 threads are resident per SM, so a launch runs in waves of acc_slots() threads that all end together: a last wave that
+// is only partly filled costs as much as a full one.  The chunk is therefore the smallest one that fills a whole number of
+// waves at the size class's target (8 / 16 / BP_CHUNK entries: small problems want short chains, large ones few partial sums).
+//   2^20 terms, c = 18 (pre path): 15.7 M entries / 32 = 6.49 waves -> 7 waves of 32 additions; at 30 entries the 7 waves are full.
+// Measured on B200 and left OFF (gpurun_out/chunkfit.log): 2^20 pre path 2.385 -> 2.407 ms (chunk 32 -> 30), e2e 2^20 3.476 -> 3.509 ms
+// (parts: 32 -> 28), 2^16 pre 0.422 -> 0.426 ms (8 -> 7) -- the blocks of a launch do not end together (gather latencies differ
+// from block to block), so the last wave is not a step, and the extra partial sums cost what the fit gains.
+inline unsigned& acc_slots() { static unsigned v = 148u * 512u; return v; }     // set from the device's SM count in bp_init
+inline int& acc_chunk_fit() { static int v = 0; return v; }                     // bp_msm_set_chunk_fit; OFF: measured no gain, see above
+inline u32 acc_chunk(double entries) {
+  const u32 target = entries <= 1300000.0 ? 8 : (entries <= 2600000.0 ? 16 : BP_CHUNK);
+  const double slots = (double)acc_slots();
+  if (!acc_chunk_fit() || entries <= slots * target) return target;             // (less than one wave: nothing to fit)
+  const double waves = ceil(entries / (slots * target));
+  const u32 cl = (u32)ceil(entries / (waves * slots));
+  return cl < 4 ? 4 : cl;
+}
 
 inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
   MsmShape s;
@@ -74,10 +94,7 @@ inline MsmShape msm_shape(size_t terms_per_msm, size_t nmsm, int force_c = 0) {
   s.dbl = (BP_GLV_BITS % s.c) == 0 ? 1 : 0;
   s.U = s.W + s.dbl;
   s.H = 1u << (s.c - 1);
-  {   // entries per accumulation thread: enough threads for ~2 waves of the 148 x 512 resident slots, at most BP_CHUNK
-    double entries = 2.0 * n * s.W * (double)nmsm;
-    s.chunk = entries <= 1300000.0 ? 8 : (entries <= 2600000.0 ? 16 : BP_CHUNK);
-  }
+  s.chunk = acc_chunk(2.0 * n * s.W * (double)nmsm);
   // first reduction level: with >= 32768 segments in flight a thread per segment of 4 buckets saturates the SMs
   // (k_reduce_seg_plain); below that the 4-lane cooperative form over 8 buckets has the shorter chain
   s.seg_plain = (nmsm <= 8 && (double)s.U * s.H / 4 >= 32768.0) ? 1 : 0;
@@ -556,19 +573,26 @@ __global__ void __launch_bounds__(32) k_finish(const XYZZ* __restrict__ acc_in, 
 }
 
 // one QUAD per msm: Horner over windows (c doublings each), then canonical affine (optionally XYZZ partials for sharding)
+// pair = 1: a unit's window sum arrives as two addends, winsum[2u] + winsum[2u + 1] (column and row side of the 2-D bucket
+// reduction, k_pre_total)
 __global__ void __launch_bounds__(128) k_combine(const XYZZ* __restrict__ winsum, MsmShape sh, size_t nmsm, Affine* __restrict__ out,
-                                                 XYZZ* __restrict__ out_xyzz) {
+                                                 XYZZ* __restrict__ out_xyzz, int pair = 0) {
   size_t m = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
   const bool active = m < nmsm;
   if (!active) m = nmsm - 1;
-  const XYZZ* ws = winsum + m * sh.U;
-  XYZZ acc = ld_xyzz(ws + sh.U - 1);
-  if (sh.dbl) { XYZZ v = ld_xyzz(ws + sh.U - 2); acc = coop_add(acc, v, role, base); }   // both units of the top window
+  const int np = pair ? 2 : 1;
+  const XYZZ* ws = winsum + m * sh.U * np;
+  XYZZ acc = ld_xyzz(ws + (size_t)(sh.U - 1) * np);
+#pragma unroll 1
+  for (int k = 1; k < np * (1 + sh.dbl); k++) {                                            // second addend / both units of the top window
+    XYZZ v = ld_xyzz(ws + (size_t)(sh.U - 1 - k / np) * np + k % np);
+    acc = coop_add(acc, v, role, base);
+  }
   for (int w = sh.W - 2; w >= 0; w--) {
     for (int d = 0; d < sh.c; d++) acc = coop_dbl(acc, role, base);
-    XYZZ v = ld_xyzz(ws + w);
-    acc = coop_add(acc, v, role, base);
+#pragma unroll 1
+    for (int k = 0; k < np; k++) { XYZZ v = ld_xyzz(ws + (size_t)w * np + k); acc = coop_add(acc, v, role, base); }
   }
   if (!active || role != 0) return;
   if (out_xyzz) st_xyzz(out_xyzz + m, acc);
@@ -691,9 +715,15 @@ __global__ void __launch_bounds__(256) k_scatter_pre(const int* __restrict__ dig
 // One launch reduces rows and columns by a factor K each (blockIdx.y = 0: rows, contiguous; 1: columns, strided):
 //   rows: out[i] = sum_{k<K} in[i*K + k]           (i < nrow_out)
 //   cols: out[g*C + lo] = sum_{k<K} in[(g*K + k)*C + lo]   (g < ncol_groups, lo < C)
+// blockIdx.z = bucket unit (plain path: the U units of an MSM are reduced side by side; `H` buckets apart on the input side, one
+// unit's worth of partial sums apart on the output side)
 __global__ void __launch_bounds__(128) k_pre_marginals(const XYZZ* __restrict__ row_in, XYZZ* __restrict__ row_out, u32 nrow_out, u32 Krow,
-                                                       const XYZZ* __restrict__ col_in, XYZZ* __restrict__ col_out, u32 ncol_groups, u32 C, u32 Kcol) {
+                                                       const XYZZ* __restrict__ col_in, XYZZ* __restrict__ col_out, u32 ncol_groups, u32 C, u32 Kcol,
+                                                       u32 H = 0) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t unit = blockIdx.z;
+  row_in += unit * H; col_in += unit * H;
+  row_out += unit * nrow_out; col_out += unit * ((size_t)ncol_groups * C);
   if (blockIdx.y == 0) {
     if (i >= nrow_out || Krow == 0) return;
     const XYZZ* src = row_in + (size_t)i * Krow;
@@ -715,9 +745,13 @@ __global__ void __launch_bounds__(128) k_pre_marginals(const XYZZ* __restrict__ 
 // C .. C+R-1: row hi, weight hi).  4-lane cooperative operations throughout (coop4.cuh: ~2 us per addition against ~4-8 us for
 // a lone thread's out-of-line call): the quads add the marginal's np partial sums (np <= 128, a power of two), a shared-memory
 // tree joins them, the first quad multiplies by the <= 11-bit weight (double-and-add) and stores wsum[block].
+// blockIdx.y = bucket unit; unit u with U > 0, dbl and u % U == U - 1 is the second unit of an MSM's top window, whose bucket
+// weights continue at H: its row weights are hi + R.
 __global__ void __launch_bounds__(64) k_pre_rowcol(const XYZZ* __restrict__ rowpart, u32 np_r, const XYZZ* __restrict__ colpart, u32 np_c,
-                                                   u32 C, u32 R, XYZZ* __restrict__ wsum) {
+                                                   u32 C, u32 R, XYZZ* __restrict__ wsum, u32 U = 0, int dbl = 0) {
   __shared__ XYZZ sm[16];
+  const size_t unit = blockIdx.y;
+  rowpart += unit * ((size_t)R * np_r); colpart += unit * ((size_t)np_c * C); wsum += unit * (C + R);
   const u32 bq = blockIdx.x, t = threadIdx.x, q = t >> 2;
   const int lane = t & 31, role = lane & 3, base = lane & ~3;
   const bool is_col = bq < C;
@@ -739,7 +773,7 @@ __global__ void __launch_bounds__(64) k_pre_rowcol(const XYZZ* __restrict__ rowp
   }
   if (t >= 32) return;                                   // the first warp (quad 0 holds the sum; its other quads shadow it)
   acc = sm[0];
-  const u32 wgt = is_col ? j + 1 : j;
+  const u32 wgt = is_col ? j + 1 : j + ((dbl && U && unit % U == U - 1) ? R : 0u);
   XYZZ r = xyzz_identity();
   for (int bit = 31 - __clz(wgt | 1u); bit >= 0; bit--) {
     r = coop_dbl(r, role, base);
@@ -749,8 +783,11 @@ __global__ void __launch_bounds__(64) k_pre_rowcol(const XYZZ* __restrict__ rowp
   if (t == 0) st_xyzz(wsum + bq, r);
 }
 // sums[side] = sum of wsum[side == 0 ? 0 .. C : C .. C+R): one block of 256 threads = 64 quads per side
-__global__ void __launch_bounds__(256) k_pre_total(const XYZZ* __restrict__ wsum, u32 C, u32 R, XYZZ* __restrict__ sums) {
+// blockIdx.y = bucket unit; ndbl > 0: the row side is multiplied by 2^ndbl here (plain path: C = 2^ndbl, the two sums of a unit
+// then simply add up to its window sum in k_combine's pair mode)
+__global__ void __launch_bounds__(256) k_pre_total(const XYZZ* __restrict__ wsum, u32 C, u32 R, XYZZ* __restrict__ sums, int ndbl = 0) {
   __shared__ XYZZ sm[64];
+  wsum += (size_t)blockIdx.y * (C + R); sums += 2 * (size_t)blockIdx.y;
   const u32 side = blockIdx.x, t = threadIdx.x, q = t >> 2, n = side == 0 ? C : R;
   const int lane = t & 31, role = lane & 3, base = lane & ~3;
   const XYZZ* src = wsum + (side == 0 ? 0u : C);
@@ -768,6 +805,10 @@ __global__ void __launch_bounds__(256) k_pre_total(const XYZZ* __restrict__ wsum
     __syncthreads();
     if (q < off && role == 0) sm[q] = acc;
     __syncthreads();
+  }
+  if (side == 1 && ndbl > 0 && t < 32) {                  // first warp: quad 0 holds the sum, the other quads shadow it
+    acc = sm[0];
+    for (int d = 0; d < ndbl; d++) acc = coop_dbl(acc, role, base);
   }
   if (t == 0) st_xyzz(sums + side, acc);
 }

@@ -341,3 +341,30 @@ def test_msm_precomputed_2p18_vs_plain_and_oracle():
     assert out.raw == plain
     assert ecc.pack_point(ecc.msm_bytes(base, sb, n, "bucket", ecc.max_threads())) == plain
     dp.free(); ds.free()
+
+
+def test_msm_experiment_switches_keep_the_result():
+    """bp_msm_set_tails2d (2-D marginal bucket reduction of the plain path's nine wide units, k_combine pair mode) and
+    bp_msm_set_chunk_fit (wave-fitted entries per accumulation thread, any chunk length): both measured slower and off by default,
+    both must give the bit-identical point -- resident operands (plain and precomputed) and host operands in parts."""
+    n = 1 << 18
+    from python_bulletproofs_b200.device import DevicePoints, DeviceScalars
+    lib = nat.load()
+    rng = random.Random(181)
+    base = nat.scalar_mul_batch_bytes(nat.pack_xy(*ecc.G) * n, rng.randbytes(32 * n), n)
+    sb = rng.randbytes(32 * n)
+    want = ecc.pack_point(ecc.msm_bytes(base, sb, n, "bucket", ecc.max_threads()))
+    dp, ds, dq = DevicePoints(raw=base), DeviceScalars(raw=sb), DevicePoints(raw=base).precompute(0)
+    out = ctypes.create_string_buffer(64)
+    try:
+        for tails2d, fit in ((1, 0), (0, 1), (1, 1)):
+            nat.check(lib.bp_msm_set_tails2d(tails2d)); nat.check(lib.bp_msm_set_chunk_fit(fit))
+            nat.check(lib.bp_msm_hh(dp.handle, ds.handle, n, out)); assert out.raw == want, (tails2d, fit, "plain")
+            nat.check(lib.bp_msm_hh(dq.handle, ds.handle, n, out)); assert out.raw == want, (tails2d, fit, "pre")
+            nat.check(lib.bp_msm(base, sb, n, out)); assert out.raw == want, (tails2d, fit, "host operands")
+            m = (1 << 16) + 77                                        # small-graph path of the precomputed vector, odd length
+            nat.check(lib.bp_msm_hh(dq.handle, ds.handle, m, out))
+            assert out.raw == ecc.pack_point(ecc.msm_bytes(base, sb, m, "bucket", ecc.max_threads())), (tails2d, fit, m)
+    finally:
+        lib.bp_msm_set_tails2d(0); lib.bp_msm_set_chunk_fit(0)
+    dp.free(); ds.free(); dq.free()

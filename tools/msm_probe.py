@@ -32,6 +32,8 @@ def main():
     args = ap.parse_args()
     lib = nat.load()
     nat.init(0)
+    lib.bp_msm_set_tails2d(int(os.environ.get("BP_TAILS2D", "0")))
+    lib.bp_msm_set_chunk_fit(int(os.environ.get("BP_CHUNK_FIT", "0")))
     macs, ms = ctypes.c_double(), ctypes.c_float()
     nat.check(lib.bp_imad_peak(4096, ctypes.byref(macs), ctypes.byref(ms)))
     print("imad peak: %.3f T limb-MAC/s (%.2f ms)" % (macs.value / 1e12, ms.value), flush=True)
