@@ -213,6 +213,9 @@ def run_ours(args):
     lib.bp_msm_set_profiling(0)
     med = [statistics.median(r[i] for r in stage_rows) for i in range(7)]
     stages = {k: round(float(v), 4) for k, v in zip(["digits", "scan", "scatter", "accumulate_stage", "reduce", "combine", "total"], med)}
+    if pre_c.value > 0 and n >= (1 << 18):
+        stages["note"] = ("slot sort: 'digits' is the one scattered pass (k_scatter_slots_pre: digits, slot atomics, entry stores), "
+                          "'scatter' the gated fallback that returns at once")
     c = lib.bp_msm_last_window()
     pre = pre_c.value > 0
     # windows: precomputed path = ceil(257 / c) windows of a 256-bit scalar; plain path = GLV halves < 2^128, ceil(128 / c) windows each
@@ -231,13 +234,17 @@ def run_ours(args):
     peak = macs.value / 1e12
     nominal = 148 * 64 * 1965.0 * 1e6 / 1e12
     ncu = ncu_record() or {}
-    kacc = ncu.get("k_accumulate", {})
-    roofline = {"bound": "imad", "kernel": "k_accumulate", "achieved": round(achieved, 3), "peak": round(peak, 3),
+    # the accumulation kernel of this launch: over the slot layout (precomputed path, >= 2^18 terms: msm.cuh slot sort, 4-byte
+    # entries) or over the compact sorted list (8-byte entries); same chunks, same mixed additions
+    kname = "k_accumulate_slots" if pre and n >= (1 << 18) else "k_accumulate"
+    ent_bytes = 4 if kname == "k_accumulate_slots" else 8
+    kacc = ncu.get(kname) or ncu.get("k_accumulate", {})
+    roofline = {"bound": "imad", "kernel": kname, "achieved": round(achieved, 3), "peak": round(peak, 3),
                 "unit": "T IMAD.WIDE (32x32+64 limb-MAC)/s", "frac": round(achieved / peak, 4),
                 "traffic": kacc.get("dram_bytes"),
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch from profiles/r2_ncu_metrics.json "
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one %s launch from profiles/r2_ncu_metrics.json "
                                 "(ncu --set full, cold L2: its default cache flush between replay passes); algorithmic bytes: one gathered 64 B "
-                                "point + 8 B entry per mixed add = %.2f GB" % (ent.value * 72 / 1e9),
+                                "point + %d B entry per mixed add = %.2f GB" % (kname, ent_bytes, ent.value * (64 + ent_bytes) / 1e9),
                 "peak_source": "measured in this process: bp_imad_peak, data-dependent IMAD.WIDE.U32 stream (SASS checked); "
                                "IMAD.WIDE issues at half the 32-bit IMAD rate on B200, with or without the carry predicate",
                 "nominal_imad32_peak": round(nominal, 2),
@@ -250,8 +257,8 @@ def run_ours(args):
                 "algorithmic_limb_macs_per_launch_survey_units": alg_macs,
                 "algorithmic_rate_survey_units_T_per_s": round(alg_macs / (acc * 1e-3) / 1e12, 3),
                 "whole_msm_algorithmic_limb_macs_per_pt": round((alg_macs + (1 if pre else (W + (1 if 128 % c == 0 else 0))) * (1 << (c - 1)) * 2 * FIELD_MULS_PER_ADD * LIMB_MACS_PER_FIELD_MUL) / n, 1),
-                "hbm": {"bound": "hbm", "achieved": round(ent.value * 72 / (acc * 1e-3) / 1e9, 1), "unit": "GB/s",
-                        "peak": measured_hbm(), "note": "gathered 64 B point + 8 B entry per mixed add; not the binding resource"}}
+                "hbm": {"bound": "hbm", "achieved": round(ent.value * (64 + ent_bytes) / (acc * 1e-3) / 1e9, 1), "unit": "GB/s",
+                        "peak": measured_hbm(), "note": "gathered 64 B point + %d B entry per mixed add; not the binding resource" % ent_bytes}}
 
     # ---- end to end through the C ABI with pinned HOST buffers (H2D + MSM + D2H inside the timed region)
     pp, ps = pinned_copy(nat, pts), pinned_copy(nat, sc)

@@ -31,6 +31,8 @@ PROTOTYPES = {
     "bp_points_precompute": (ctypes.c_int, [c_h, ctypes.c_int]),
     "bp_msm_set_chunk_fit": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_tails2d": (ctypes.c_int, [ctypes.c_int]),
+    "bp_msm_set_pre_fused": (ctypes.c_int, [ctypes.c_int]),
+    "bp_msm_set_pre_slots": (ctypes.c_int, [ctypes.c_int, c_sz]),
     "bp_msm_set_pre_chunk": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_affine_passes": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_small_graphs": (ctypes.c_int, [ctypes.c_int]),

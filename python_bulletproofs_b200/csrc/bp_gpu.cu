@@ -435,7 +435,7 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
     if (g.pre_chunk) sh.chunk = g.pre_chunk;
   }
   const size_t nchunks = ((P ? (emax_pad >> P) : emax) + sh.chunk - 1) / sh.chunk;
-  int* digits = (int*)g.ws_digits.ensure(emax * sizeof(int));
+  int* digits = g.pre_fused ? nullptr : (int*)g.ws_digits.ensure(emax * sizeof(int));      // fused: the scatter pass recomputes the digits
   uint2* entries = (uint2*)g.ws_entries.ensure(emax_pad * sizeof(uint2));
   Affine *aff_a = nullptr, *aff_b = nullptr; Fp* aff_scr = nullptr; u32 *aff_ctr = nullptr, *red_start = nullptr; uint2* red_ent = nullptr;
   if (P) {
@@ -456,11 +456,26 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
   XYZZ* part = (XYZZ*)g.ws_part.ensure(2 * nchunks * sizeof(XYZZ));
   const u32 big_cap = (u32)(emax / ((size_t)sh.chunk * (BP_FIXUP_SERIAL_MAX - 1)) + 16);
   u32* big = (u32*)g.ws_big.ensure((2 * (size_t)big_cap + 4) * sizeof(u32));
-  if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !part || !big) return fail("workspace allocation failed");
+  if ((!digits && !g.pre_fused) || !entries || !count || !start || !cursor || !tiles || !buckets || !part || !big) return fail("workspace allocation failed");
   u32* zero_word = big + 2 * (size_t)big_cap + 3;
+  // slot sort (msm.cuh): one scattered pass instead of histogram + scatter for large MSMs; the exact counting sort stays queued
+  // behind it as the fallback, gated on the overflow word
+  const bool use_slots = g.pre_slots > 0 && P == 0 && T >= g.pre_slots_min;
+  u32 cap = 0; u32* slots = nullptr; u32* overflow = nullptr;
+  if (use_slots) {
+    double lam = 0;                                                      // mean load of the fullest buckets: the low ones, which every window reaches
+    for (int w = 0; w < ps.W; w++) lam += (double)T / (double)(1u << (ps.off[w + 1] - ps.off[w] - 1));
+    cap = g.pre_slots == 2 ? 8u : (u32)(lam + 9.5 * sqrt(lam) + 8.0);    // (mode 2: a test hook that makes every large bucket overflow)
+    cap = (cap + 7u) & ~7u;
+    slots = (u32*)g.ws_slots.ensure(nb * (size_t)cap * sizeof(u32));
+    overflow = (u32*)g.ws_slots_ovf.ensure(64);
+    if (!slots || !overflow) return fail("workspace allocation failed");
+    BP_CUDA(cudaMemsetAsync(overflow, 0, sizeof(u32), st));
+  }
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
   if (prof) cudaEventRecord(g.ev[0], st);
-  ++g.nlaunch, k_digits_pre<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, ps, digits, count);
+  if (use_slots) ++g.nlaunch, k_scatter_slots_pre<4><<<(T + 255) / 256, 256, 0, st>>>(scalars, T, ps, stride, first, cap, count, slots, overflow);
+  else ++g.nlaunch, k_digits_pre<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, ps, digits, count);
   if (prof) cudaEventRecord(g.ev[1], st);
   ++g.nlaunch, k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1, amask);
   ++g.nlaunch, k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
@@ -468,7 +483,7 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
   if (prof) cudaEventRecord(g.ev[2], st);
   BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
   if (P) ++g.nlaunch, k_aff_pad<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(start, count, (u32)nb, entries);
-  ++g.nlaunch, k_scatter_pre<<<(T + 255) / 256, 256, 0, st>>>(digits, T, ps, stride, first, cursor, entries);
+  ++g.nlaunch, k_scatter_pre<<<(T + 255) / 256, 256, 0, st>>>(use_slots ? nullptr : digits, scalars, T, ps, stride, first, cursor, entries, overflow);
   if (prof) cudaEventRecord(g.ev[3], st);
   BP_CUDA(cudaMemsetAsync(buckets, 0, nb * sizeof(XYZZ), st));
   BP_CUDA(cudaMemsetAsync(zero_word, 0, sizeof(u32), st));
@@ -489,7 +504,8 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
     ++g.nlaunch, k_aff_index<<<(unsigned)(((emax_pad >> P) > nb + 1 ? (emax_pad >> P) : nb + 1) + 255) / 256, 256, 0, st>>>(start, (u32)nb, entries, P, red_start, red_ent);
     acc_pts = src; acc_start = red_start; acc_ent = red_ent;
   }
-  ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(acc_pts, nullptr, nullptr, acc_start, acc_ent, zero_word, acc_start + nb, sh.chunk, buckets, part);
+  if (use_slots) ++g.nlaunch, k_accumulate_slots<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pre, start, (u32)nb, slots, cap, overflow, sh.chunk, buckets, part);
+  ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(acc_pts, nullptr, nullptr, acc_start, acc_ent, zero_word, acc_start + nb, sh.chunk, buckets, part, 0, 0, overflow);
   if (prof) cudaEventRecord(g.ev_k1, st);
   ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(acc_start, 0, nb, zero_word, sh.chunk, part, buckets, big, big_cap);
   ++g.nlaunch, k_fixup_mid<<<2 * g.sm_count, 256, 0, st>>>(acc_start, zero_word, sh.chunk, part, buckets, big, big_cap);
@@ -823,6 +839,13 @@ int bp_msm_last_entries(uint64_t* entries) {      // non-zero digits = mixed add
 int bp_launch_count(uint64_t* launches) { *launches = g.nlaunch; return 0; }
 int bp_msm_set_affine_passes(int passes) { g.aff_passes = passes < 0 ? -1 : (passes > 6 ? 6 : passes); return 0; }   /* experiment switch */
 int bp_msm_set_tails2d(int on) { g.tails2d = on != 0; return 0; }   /* experiment switch */
+int bp_msm_set_pre_fused(int on) { if (g.inited) cudaStreamSynchronize(g.stream); g.pre_fused = on != 0; pre_graphs_clear(); return 0; }   /* experiment switch */
+int bp_msm_set_pre_slots(int mode, size_t min_terms) {   /* 0 = exact counting sort only, 1 = slot sort for MSMs of >= min_terms terms (0 = keep), 2 = same with 8 slots per bucket (test hook: forces the fallback) */
+  if (g.inited) cudaStreamSynchronize(g.stream);
+  g.pre_slots = mode; if (min_terms) g.pre_slots_min = (unsigned)min_terms;
+  pre_graphs_clear();
+  return 0;
+}
 int bp_msm_set_pre_chunk(int entries) { g.pre_chunk = entries > 0 ? (unsigned)entries : 0; return 0; }   /* experiment switch */
 int bp_msm_set_profiling(int on) { g.profiling = on != 0; return 0; }
 int bp_msm_set_pipeline_min(size_t min_terms) { g.pipeline_min_terms = min_terms ? (unsigned)min_terms : 0xFFFFFFFFu; return 0; }

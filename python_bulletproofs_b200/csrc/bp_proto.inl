@@ -990,6 +990,8 @@ static int msm_sharded_device(const Affine* pts, const Fq* sc, size_t n, Affine*
   int R = g_comm ? g_nranks : 1;
   XYZZ* d_part = (XYZZ*)g.ws_lr.ensure((size_t)(R + 1) * sizeof(XYZZ));
   if (!d_part) return fail("device allocation failed");
+  if (R == 1 && n > 0)      // one rank: nothing to exchange or add, the MSM's own last kernel converts to the canonical affine point
+    return hrec ? handle_msm(*hrec, first, sc, n, d_out, nullptr) : msm_run(pts, nullptr, sc, (u32)n, nullptr, 1, n, d_out, nullptr, opt);
   if (n == 0) BP_CUDA(cudaMemsetAsync(d_part, 0, sizeof(XYZZ), g.stream));
   else if (hrec ? handle_msm(*hrec, first, sc, n, nullptr, d_part) : msm_run(pts, nullptr, sc, (u32)n, nullptr, 1, n, nullptr, d_part, opt)) return 1;
   const XYZZ* all = d_part;

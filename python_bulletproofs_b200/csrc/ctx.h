@@ -54,6 +54,9 @@ struct Ctx {
   bool profiling = false;
   int force_c = 0, last_c = 0;
   bool pre_attr_set = false; unsigned pre_chunk = 0;
+  bool pre_fused = true;      // pre path: no digit array between the histogram and the scatter pass, the scatter recomputes the digits (bp_msm_set_pre_fused)
+  int pre_slots = 1; unsigned pre_slots_min = 1u << 18;   // slot sort of the precomputed path (bp_msm_set_pre_slots)
+  DevBuf ws_slots, ws_slots_ovf;
   bool tails2d = false;       // 2-D marginal bucket reduction for the wide units of a large plain MSM (bp_msm_set_tails2d): measured slower, off
   int aff_passes = -1;                          // batched-affine pair passes ahead of the XYZZ accumulation: <= 0 = off (default), 1..6 = that many passes (bp_msm_set_affine_passes)
   DevBuf ws_aff_a, ws_aff_b, ws_aff_scr, ws_aff_ent, ws_aff_start, ws_aff_ctr;
@@ -213,7 +216,7 @@ struct Ctx {
     DevBuf* all[] = {&ws_pts, &ws_sc, &ws_off, &ws_out, &ws_digits, &ws_entries, &ws_count, &ws_start, &ws_cursor, &ws_tiles,
                      &ws_buckets, &ws_segsum, &ws_winsum, &ws_misc, &ws_flush, &ws_g, &ws_h, &ws_a, &ws_b, &ws_g2, &ws_h2,
                      &ws_a2, &ws_b2, &ws_idx, &ws_lr, &ws_terms_sc, &ws_small, &ws_entry_bucket, &ws_part, &ws_big, &ws_phi, &ws_segrun, &ws_grpsum, &ws_winpart, &ws_fb_lanes, &ws_fb_var, &ws_sv_tab, &ws_sv_acc, &ws_sv_sc, &ws_rp_sums, &ws_halfoff,
-                     &ws_aff_a, &ws_aff_b, &ws_aff_scr, &ws_aff_ent, &ws_aff_start, &ws_aff_ctr, &ws_ipa_rp, &ws_ipa_ticket};
+                     &ws_aff_a, &ws_aff_b, &ws_aff_scr, &ws_aff_ent, &ws_aff_start, &ws_aff_ctr, &ws_ipa_rp, &ws_ipa_ticket, &ws_slots, &ws_slots_ovf};
     rp_sums_src.clear();
     for (DevBuf* b : all) b->release();
   }

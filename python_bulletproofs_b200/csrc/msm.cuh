@@ -282,7 +282,9 @@ BP_DI const Affine* entry_point_ptr(const Affine* __restrict__ points, const u32
 __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate(const Affine* __restrict__ points, const u32* __restrict__ point_idx, const Affine* __restrict__ phi,
                                                     const u32* __restrict__ bucket_start, const uint2* __restrict__ entries,
                                                     const u32* __restrict__ gs_ptr, const u32* __restrict__ ge_ptr, u32 CL,
-                                                    XYZZ* __restrict__ buckets, XYZZ* __restrict__ part, u32 hb = 0, int into = 0) {
+                                                    XYZZ* __restrict__ buckets, XYZZ* __restrict__ part, u32 hb = 0, int into = 0,
+                                                    const u32* __restrict__ run_if = nullptr) {
+  if (run_if && __ldg(run_if) == 0) return;                              // fallback of the slot sort (k_scatter_slots_pre)
   // hb / into: a host-operand MSM whose points arrive in K parts is sorted as K MSMs -- bucket id (part, unit, digit), hb
   // buckets per part -- but all parts accumulate into ONE set of hb bucket values: the value of bucket id b lives at b % hb, and
   // from the second part on (into = 1) the first piece of every bucket starts from the stored value instead of the identity.
@@ -671,40 +673,137 @@ __global__ void __launch_bounds__(128) k_pre_build(const Affine* __restrict__ pt
   }
 }
 
-// One thread per term: k mod q -> W signed digits of the windows of `ps`, histogram over the single bucket unit.  digits is [W][T].
+// signed digit of window w of the reduced scalar k (carry = the recoding carry out of window w-1, updated)
+BP_DI int pre_digit(const Fq& k, const PreShape& ps, int w, u32& carry) {
+  // window w covers bits [off, off + width): the `extra` low windows are one bit wider (pre_shape) -- computed, not read from
+  // ps.off[]: a dynamically indexed kernel parameter is copied to local memory, 2 more LSU requests per digit in kernels that
+  // are bound by exactly those
+  const int base = 257 / ps.W, extra = 257 % ps.W;
+  const int width = base + (w < extra ? 1 : 0), off = w * base + (w < extra ? w : extra);
+  const u32 half = 1u << (width - 1);
+  const u32 d = scalar_bits(k, off, width) + carry;
+  // (the top window holds bit 256, which is clear: its digit stays <= half without recoding)
+  if (w + 1 < ps.W && d > half) { carry = 1; return (int)d - (int)(2u * half); }
+  carry = 0;
+  return (int)d;
+}
+BP_DI Fq pre_load_scalar(const Fq* __restrict__ scalars, u32 t) {
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + t);
+  uint4 a = __ldg(sp), b = __ldg(sp + 1);
+  Fq k; k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
+  return fq_reduce(k);                                  // es = [ei % order]   pippenger.py:26
+}
+// One thread per term: k mod q -> W signed digits of the windows of `ps`, histogram over the single bucket unit.  digits is [W][T]
+// (null: the scatter pass derives the digits again from the scalar -- 32 bytes read instead of 4 W written and read back).
 __global__ void __launch_bounds__(256) k_digits_pre(const Fq* __restrict__ scalars, u32 T, PreShape ps, int* __restrict__ digits,
                                                     u32* __restrict__ bucket_count) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  const uint4* sp = reinterpret_cast<const uint4*>(scalars + t);
-  uint4 a = __ldg(sp), b = __ldg(sp + 1);
-  Fq k; k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
-  k = fq_reduce(k);                                   // es = [ei % order]   pippenger.py:26
+  const Fq k = pre_load_scalar(scalars, t);
   u32 carry = 0;
   for (int w = 0; w < ps.W; w++) {
-    const int width = ps.off[w + 1] - ps.off[w];
-    const u32 half = 1u << (width - 1);
-    const u32 d = scalar_bits(k, ps.off[w], width) + carry;
-    int sd;
-    // (the top window holds bit 256, which is clear: its digit stays <= half without recoding)
-    if (w + 1 < ps.W && d > half) { sd = (int)d - (int)(2u * half); carry = 1; } else { sd = (int)d; carry = 0; }
-    digits[(size_t)w * T + t] = sd;
+    const int sd = pre_digit(k, ps, w, carry);
+    if (digits) digits[(size_t)w * T + t] = sd;
     if (sd != 0) atomicAdd(bucket_count + ((sd < 0 ? (u32)(-sd) : (u32)sd) - 1u), 1u);
   }
 }
 
 // counting-sort scatter: entry = {point index | sign << 31, bucket}, point index = w * stride + first + t
-__global__ void __launch_bounds__(256) k_scatter_pre(const int* __restrict__ digits, u32 T, PreShape ps, u32 stride, u32 first,
-                                                     u32* __restrict__ cursor, uint2* __restrict__ entries) {
+__global__ void __launch_bounds__(256) k_scatter_pre(const int* __restrict__ digits, const Fq* __restrict__ scalars, u32 T, PreShape ps, u32 stride, u32 first,
+                                                     u32* __restrict__ cursor, uint2* __restrict__ entries, const u32* __restrict__ run_if = nullptr) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
+  if (run_if && __ldg(run_if) == 0) return;             // fallback of the slot sort: runs only when a bucket overflowed its slots
+  Fq k;
+  if (!digits) k = pre_load_scalar(scalars, t);
+  u32 carry = 0;
   for (int w = 0; w < ps.W; w++) {
-    const int sd = digits[(size_t)w * T + t];
+    const int sd = digits ? digits[(size_t)w * T + t] : pre_digit(k, ps, w, carry);
     if (sd == 0) continue;
     const u32 bkt = (sd < 0 ? (u32)(-sd) : (u32)sd) - 1u;
     const u32 pos = atomicAdd(cursor + bkt, 1u);        // cursor[] starts at bucket_start[]: absolute slot
     entries[pos] = make_uint2(((u32)w * stride + first + t) | (sd < 0 ? 0x80000000u : 0u), bkt);
   }
+}
+
+// ---- slot sort: ONE scattered pass instead of histogram + scatter -------------------------------------------------------------
+// Both passes of the counting sort run at the same ~0.47 scattered L2 requests per clock and SM (15.7 M RED in 111 us, 15.7 M ATOM +
+// 15.7 M 8-byte stores in 232 us at 2^20; profiles/r2_sort_ncu.txt) -- what counts is the NUMBER of scattered requests per entry:
+// three.  For scalars whose digits spread evenly the histogram can be skipped: bucket b owns a fixed range of `cap` 4-byte slots
+// (cap = mean + 9.5 sigma of the fullest buckets' Poisson load), one returning atomic on count[b] hands out the slot, the entry is
+// stored there: two requests per entry, and the atomics leave count[] exactly as the histogram pass would.  The exclusive scan
+// of count[] still runs: k_accumulate_slots cuts the COMPACT index space [0, E) into equal chunks (same load balance, same
+// partial sums, same fix-up kernels) and maps index i of bucket b to slots[b * cap + (i - start[b])].  An entry that finds its
+// bucket full bumps *overflow; then this path's accumulation returns at once and the exact counting sort + k_accumulate, queued
+// behind it and gated on the same word, do the work (scalars with thousands of equal digits: range-proof vectors).
+// B = windows handled together: the B returning atomics of a group are issued back to back, then the B stores (B = 1 / 4 / 8:
+// 2.280 / 2.275 / 2.283 ms per 2^20-term MSM -- the pass is bound by the request rate, not by the latency of one atomic)
+template <int B>
+__global__ void __launch_bounds__(256) k_scatter_slots_pre(const Fq* __restrict__ scalars, u32 T, PreShape ps, u32 stride, u32 first, u32 cap,
+                                                           u32* __restrict__ count, u32* __restrict__ slots, u32* __restrict__ overflow) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const Fq k = pre_load_scalar(scalars, t);
+  u32 carry = 0;
+  for (int w0 = 0; w0 < ps.W; w0 += B) {
+    int sd[B]; u32 r[B];
+#pragma unroll
+    for (int j = 0; j < B; j++) sd[j] = w0 + j < ps.W ? pre_digit(k, ps, w0 + j, carry) : 0;
+#pragma unroll
+    for (int j = 0; j < B; j++)
+      if (sd[j] != 0) r[j] = atomicAdd(count + ((sd[j] < 0 ? (u32)(-sd[j]) : (u32)sd[j]) - 1u), 1u);
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+      if (sd[j] == 0) continue;
+      const u32 bkt = (sd[j] < 0 ? (u32)(-sd[j]) : (u32)sd[j]) - 1u;
+      if (r[j] < cap) slots[(size_t)bkt * cap + r[j]] = ((u32)(w0 + j) * stride + first + t) | (sd[j] < 0 ? 0x80000000u : 0u);
+      else atomicAdd(overflow, 1u);
+    }
+  }
+}
+// k_accumulate over the slot layout (precomputed path: direct point indices, no phi, no parts).  bucket_start[0 .. nb] is the
+// exclusive scan of the bucket counts; chunk boundaries, part[] and buckets[] are exactly those of k_accumulate.
+__global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate_slots(const Affine* __restrict__ points, const u32* __restrict__ bucket_start, u32 nb,
+                                                                       const u32* __restrict__ slots, u32 cap, const u32* __restrict__ overflow, u32 CL,
+                                                                       XYZZ* __restrict__ buckets, XYZZ* __restrict__ part) {
+  if (__ldg(overflow) != 0) return;
+  const u32 chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 E = __ldg(bucket_start + nb);
+  const u32 cs = chunk * CL;
+  if (cs >= E) return;
+  const u32 ce = cs + CL < E ? cs + CL : E;
+  u32 b = 0;
+  {   // the bucket that holds compact index cs: the largest b with bucket_start[b] <= cs (empty buckets share their successor's start)
+    u32 hi = nb;
+    while (hi - b > 1) { const u32 mid = (b + hi) >> 1; if (__ldg(bucket_start + mid) <= cs) b = mid; else hi = mid; }
+  }
+  u32 s = __ldg(bucket_start + b), e = __ldg(bucket_start + b + 1);
+  const u32* sp = slots + (size_t)b * cap - s;                            // entry i of bucket b
+  bool first = true;
+  XYZZ acc = xyzz_identity();
+  u32 ent = __ldg(sp + cs);
+  for (u32 i = cs; i < ce; i++) {
+    if (i == e) {                                                        // previous run is complete
+      if (first && s < cs) st_xyzz(part + 2 * (size_t)chunk, acc);       // it began in an earlier chunk
+      else st_xyzz(buckets + b, acc);                                    // whole bucket inside this chunk
+      first = false;
+      do { b++; s = e; e = __ldg(bucket_start + b + 1); } while (e == s);      // next non-empty bucket (i < E: there is one)
+      acc = xyzz_identity();
+      sp = slots + (size_t)b * cap - s;
+      ent = __ldg(sp + i);
+    }
+    const u32 cur = ent;
+    if (i + 1 < ce && i + 1 < e) {                                       // (across a bucket boundary the entry is fetched after the flush)
+      ent = __ldg(sp + i + 1);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(points + (ent & 0x7FFFFFFFu)));
+    }
+    Affine p = ld_affine(points + (cur & 0x7FFFFFFFu));
+    if (cur >> 31) p.y = fp_neg(p.y);
+    xyzz_madd(acc, p);
+  }
+  if (e > ce) st_xyzz(part + 2 * (size_t)chunk + (first ? 0 : 1), acc);   // run continues in the next chunk
+  else if (first && s < cs) st_xyzz(part + 2 * (size_t)chunk, acc);
+  else st_xyzz(buckets + b, acc);
 }
 
 // ---- reduction of ONE large bucket unit (H = R x C buckets, b = hi*C + lo) -----------------------------------------------------

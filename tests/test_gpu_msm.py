@@ -368,3 +368,35 @@ def test_msm_experiment_switches_keep_the_result():
     finally:
         lib.bp_msm_set_tails2d(0); lib.bp_msm_set_chunk_fit(0)
     dp.free(); ds.free(); dq.free()
+
+
+def test_msm_slot_sort_and_its_fallback():
+    """Sort stage of the precomputed path (msm.cuh, k_scatter_slots_pre / k_accumulate_slots): slot sort on, off, and with 8 slots per
+    bucket so that every bucket overflows and the gated exact counting sort does the work; uniform scalars, scalars with thousands
+    of equal digits (overflow with the regular slot count), all-zero and single-term corner cases -- bit-identical points."""
+    n = 1 << 18
+    from python_bulletproofs_b200.device import DevicePoints
+    lib = nat.load()
+    rng = random.Random(182)
+    base = nat.scalar_mul_batch_bytes(nat.pack_xy(*ecc.G) * n, rng.randbytes(32 * n), n)
+    few = [rng.getrandbits(256) % Q for _ in range(3)]
+    sets = {
+        "uniform": rng.randbytes(32 * n),
+        "few_values": b"".join(few[rng.randrange(3)].to_bytes(32, "little") for _ in range(n)),          # 3 hot buckets per window
+        "small": b"".join(rng.randrange(0, 1 << 20).to_bytes(32, "little") for _ in range(n)),             # only the low windows
+        "zero": bytes(32 * n),
+    }
+    want = {name: ecc.pack_point(ecc.msm_bytes(base, sb, n, "bucket", ecc.max_threads())) for name, sb in sets.items()}
+    dq = DevicePoints(raw=base).precompute(0)
+    out = ctypes.create_string_buffer(64)
+    try:
+        for mode in (1, 2, 0):
+            nat.check(lib.bp_msm_set_pre_slots(mode, 1 << 12))
+            for name, sb in sets.items():
+                nat.check(lib.bp_msm_h(dq.handle, sb, n, out)); assert out.raw == want[name], (mode, name)
+            m = 5000                                                      # short vector, above the lowered threshold
+            nat.check(lib.bp_msm_h(dq.handle, sets["uniform"], m, out))
+            assert out.raw == ecc.pack_point(ecc.msm_bytes(base, sets["uniform"], m, "bucket", ecc.max_threads())), (mode, m)
+    finally:
+        lib.bp_msm_set_pre_slots(1, 1 << 18)
+    dq.free()

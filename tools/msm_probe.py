@@ -33,6 +33,8 @@ def main():
     lib = nat.load()
     nat.init(0)
     lib.bp_msm_set_tails2d(int(os.environ.get("BP_TAILS2D", "0")))
+    lib.bp_msm_set_pre_slots(int(os.environ.get("BP_PRE_SLOTS", "1")), int(os.environ.get("BP_PRE_SLOTS_MIN", "0")))
+    lib.bp_msm_set_pre_fused(int(os.environ.get("BP_PRE_FUSED", "1")))
     lib.bp_msm_set_chunk_fit(int(os.environ.get("BP_CHUNK_FIT", "0")))
     macs, ms = ctypes.c_double(), ctypes.c_float()
     nat.check(lib.bp_imad_peak(4096, ctypes.byref(macs), ctypes.byref(ms)))

@@ -44,8 +44,15 @@ def summary(rep, title, path):
 
 def main():
     os.makedirs(PR, exist_ok=True)
-    rec = {"source": "profiles/r2_accumulate_ncu.txt, profiles/r2_rp_lookup16_ncu.txt (tools/ncu_metrics.sh + tools/ncu_extract.py)"}
-    for name, rep, title, txt in (("k_accumulate", "r2_accumulate.ncu-rep", "k_accumulate, precomputed-window path, 2^20 terms, c = 18 (the bench's dominant kernel)", "r2_accumulate_ncu.txt"),
+    rec = {}
+    try:      # captures that are no longer in gpurun_out/ keep their committed record
+        rec = json.load(open(os.path.join(PR, "r2_ncu_metrics.json")))
+    except Exception:   # noqa: BLE001
+        pass
+    rec["source"] = ("profiles/r2_accumulate_slots_ncu.txt, profiles/r2_accumulate_ncu.txt, profiles/r2_rp_lookup16_ncu.txt "
+                     "(tools/ncu_metrics.sh, tools/ncu_final.sh + tools/ncu_extract.py)")
+    for name, rep, title, txt in (("k_accumulate_slots", "r2_accumulate_slots.ncu-rep", "k_accumulate_slots, precomputed-window path after the slot sort, 2^20 terms, c = 18 (the bench's dominant kernel)", "r2_accumulate_slots_ncu.txt"),
+                                  ("k_accumulate", "r2_accumulate.ncu-rep", "k_accumulate, precomputed-window path, 2^20 terms, c = 18 (compact sorted list; the dominant kernel before the slot sort)", "r2_accumulate_ncu.txt"),
                                   ("k_rp_lookup16", "r2_lookup16.ncu-rep", "k_rp_lookup16, 16-bit generator table, one chunk of an 8192-proof batch", "r2_rp_lookup16_ncu.txt")):
         p = os.path.join(GO, rep)
         if not os.path.exists(p):
