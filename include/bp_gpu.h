@@ -61,6 +61,7 @@ int bp_msm_set_chunk_fit(int on);       /* experiment switch: 1 = entries per ac
 int bp_msm_set_tails2d(int on);         /* experiment switch: 1 = 2-D marginal bucket reduction for the wide units of a large plain MSM, 0 (default; measured faster) = running sums */
 int bp_msm_set_pre_fused(int on);       /* experiment switch: 1 (default) = the scatter pass of the precomputed path recomputes the digits, 0 = digit array in between */
 int bp_msm_set_pre_slots(int mode, size_t min_terms);   /* precomputed path, sort stage: 1 (default) = slot sort (one scattered pass; exact counting sort as gated fallback) for MSMs of >= min_terms terms (default 2^18; 0 keeps the value), 0 = exact counting sort only, 2 = test hook, 8 slots per bucket so that the fallback runs */
+int bp_msm_set_host_finish(int on);     /* 1 (default): an MSM whose result goes to the host (bp_msm, bp_msm_sharded_host on one rank; bucket method without precomputed multiples) hands its window sums to the host, which runs the Horner chain and the affine conversion; 0 = k_combine on the device */
 int bp_msm_set_pre_chunk(int entries);   /* experiment switch: entries per accumulation thread on that path (0 = automatic) */
 int bp_msm_h(bp_handle points, const uint8_t* sc32, size_t n, uint8_t out64[64]);     /* scalars from host */
 int bp_msm_hh(bp_handle points, bp_handle scalars, size_t n, uint8_t out64[64]);      /* all resident */
@@ -271,6 +272,9 @@ int bp_test_ec(int op, const uint8_t* a64, const uint8_t* b64, size_t n, uint8_t
 int bp_test_fq(int op, int on_device, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32);
 /* host F_p (csrc/fp_host.h): count <= 8 XYZZ points (128 bytes each) -> canonical affine, as the IPA prover's host step finishes L and R */
 int bp_test_xyzz_to_affine_host(const uint8_t* xyzz128, size_t count, uint8_t* out64);
+/* host Horner over the U window sums (XYZZ, 128 bytes each) of one MSM, as bp_msm finishes a host-result MSM (csrc/fp_host.h: horner_host);
+   U = W + dbl, unit U-1 (and U-2 when dbl) the top window */
+int bp_test_horner_host(const uint8_t* winsum128, int c, int W, int U, int dbl, uint8_t out64[64]);
 
 /* ---- multi-GPU (one process per GPU) ---------------------------------------------------------------
  * NCCL communicator over the ranks of a torchrun job; `unique_id` is the 128-byte ncclUniqueId

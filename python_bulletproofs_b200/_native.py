@@ -33,6 +33,7 @@ PROTOTYPES = {
     "bp_msm_set_tails2d": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_pre_fused": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_pre_slots": (ctypes.c_int, [ctypes.c_int, c_sz]),
+    "bp_msm_set_host_finish": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_pre_chunk": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_affine_passes": (ctypes.c_int, [ctypes.c_int]),
     "bp_msm_set_small_graphs": (ctypes.c_int, [ctypes.c_int]),
@@ -92,6 +93,7 @@ PROTOTYPES = {
     "bp_test_ec": (ctypes.c_int, [ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_test_fq": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_test_xyzz_to_affine_host": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
+    "bp_test_horner_host": (ctypes.c_int, [c_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_u8p]),
     "bp_nccl_unique_id": (ctypes.c_int, [c_u8p]),
     "bp_nccl_init": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u8p]),
     "bp_msm_sharded": (ctypes.c_int, [c_h, c_h, c_sz, c_sz, c_u8p]),

@@ -107,6 +107,10 @@ static int msm_tails(const XYZZ* buckets, const MsmShape& sh, u32 nmsm, Affine* 
       ws = winsum;
     } else if (ngrp > 1) { ++g.nlaunch, k_window_sum<<<(unsigned)nmw, 256, 0, st>>>(grpsum, ngrp, winsum); ws = winsum; }
     if (prof) cudaEventRecord(g.ev[5], st);
+    if (g.hf_want && nmsm == 1 && out_affine && !out_xyzz) {      // the caller finishes the Horner chain on the host (msm_finish_to_host)
+      g.hf.ws = ws; g.hf.c = sh.c; g.hf.W = sh.W; g.hf.U = sh.U; g.hf.dbl = sh.dbl; g.hf.pending = true;
+      return 0;
+    }
     ++g.nlaunch, k_combine<<<(unsigned)((4 * (size_t)nmsm + 127) / 128), 128, 0, st>>>(ws, sh, nmsm, out_affine, out_xyzz);
   }
   return 0;
@@ -120,7 +124,8 @@ static int msm_run_pipelined(const Affine* points, const u32* point_idx, const F
 //   pts_ready   event the points are complete at (host-operand MSM whose points upload on the copy stream)
 //   halves      the points arrive in `parts` equal parts (g.ev_half[0 .. parts-1], upload_operands);
 //   split_sort  ... each behind its own scalars (g.ev_part_sc[k]): sort part by part (msm_run_parts)
-struct MsmOpts { u32 skip_below = 0; cudaEvent_t pts_ready = nullptr; bool halves = false; int parts = 0; bool split_sort = false; };
+//   host_finish the result goes to the host: leave the window sums for horner_host instead of running k_combine (g.hf)
+struct MsmOpts { u32 skip_below = 0; cudaEvent_t pts_ready = nullptr; bool halves = false; int parts = 0; bool split_sort = false; bool host_finish = false; };
 // Host-operand MSM whose operands arrive in K parts, each part = its scalars followed by its points (upload_operands): every part
 // is sorted on its own as soon as its scalars are in (digits, scan, scatter over T/K terms) and accumulated as soon as its points
 // are in, all parts adding into ONE bucket set (k_accumulate's `into`); reduction and combination are those of a single MSM.
@@ -197,8 +202,10 @@ static int msm_run_parts(const Affine* points, const Fq* scalars, u32 T, u32 K, 
   return 0;
 }
 
+struct HfScope { HfScope(bool want) { g.hf_want = want && g.hf_enabled; g.hf.pending = false; } ~HfScope() { g.hf_want = false; } };
 int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T, const u32* d_offsets, u32 nmsm,
             size_t terms_per_msm, Affine* out_affine, XYZZ* out_xyzz, MsmOpts opt = MsmOpts()) {
+  HfScope hf_scope(opt.host_finish && nmsm == 1 && !g.profiling);
   if (nmsm == 1 && T >= g.pipeline_min_terms && !g.profiling) {
     if (opt.pts_ready) BP_CUDA(cudaStreamWaitEvent(g.stream, opt.pts_ready, 0));
     if (opt.halves) BP_CUDA(cudaStreamWaitEvent(g.stream, g.ev_half[opt.parts - 1], 0));
@@ -598,13 +605,28 @@ static int upload_operands(Affine* d_pts, const uint8_t* pts64, Fq* d_sc, const 
   return 0;
 }
 
-static int msm_to_host(const Affine* d_pts, const Fq* d_sc, size_t n, uint8_t* out64, MsmOpts opt = MsmOpts()) {
-  Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
-  if (!d_out) { cudaStreamSynchronize(g.copy_stream); return fail("workspace allocation failed"); }
-  if (msm_run(d_pts, nullptr, d_sc, (u32)n, nullptr, 1, n, d_out, nullptr, opt)) { cudaStreamSynchronize(g.copy_stream); return 1; }
+// Result of the MSM just enqueued on g.stream -> host: either the affine point k_combine wrote to d_out, or -- host-finished
+// Horner -- the window sums, combined here (fp_host.h)
+static int msm_finish_to_host(const Affine* d_out, uint8_t* out64) {
+  if (g.hf.pending) {
+    g.hf.pending = false;
+    uint8_t ws[132 * 128];                        // c = 1: 128 windows + the second unit of the top one
+    if (g.hf.U > 132) return fail("host finish: too many window sums");
+    BP_CUDA(cudaMemcpyAsync(ws, g.hf.ws, (size_t)g.hf.U * 128, cudaMemcpyDeviceToHost, g.stream));
+    BP_CUDA(cudaStreamSynchronize(g.stream));
+    horner_host(ws, g.hf.c, g.hf.W, g.hf.U, g.hf.dbl, out64);
+    return 0;
+  }
   BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
   BP_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
+}
+static int msm_to_host(const Affine* d_pts, const Fq* d_sc, size_t n, uint8_t* out64, MsmOpts opt = MsmOpts()) {
+  Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
+  if (!d_out) { cudaStreamSynchronize(g.copy_stream); return fail("workspace allocation failed"); }
+  opt.host_finish = true;
+  if (msm_run(d_pts, nullptr, d_sc, (u32)n, nullptr, 1, n, d_out, nullptr, opt)) { cudaStreamSynchronize(g.copy_stream); return 1; }
+  return msm_finish_to_host(d_out, out64);
 }
 
 // kind 0 = points, 1 = scalars; pre/pre_c: precomputed window multiples of a point vector (bp_points_precompute)
@@ -846,6 +868,7 @@ int bp_msm_set_pre_slots(int mode, size_t min_terms) {   /* 0 = exact counting s
   pre_graphs_clear();
   return 0;
 }
+int bp_msm_set_host_finish(int on) { g.hf_enabled = on != 0; return 0; }   /* 1 (default): host-result MSMs of the plain path finish their Horner chain on the host */
 int bp_msm_set_pre_chunk(int entries) { g.pre_chunk = entries > 0 ? (unsigned)entries : 0; return 0; }   /* experiment switch */
 int bp_msm_set_profiling(int on) { g.profiling = on != 0; return 0; }
 int bp_msm_set_pipeline_min(size_t min_terms) { g.pipeline_min_terms = min_terms ? (unsigned)min_terms : 0xFFFFFFFFu; return 0; }

@@ -1026,12 +1026,13 @@ int bp_msm_sharded_host(const uint8_t* pts64, const uint8_t* sc32, size_t n, uin
   Affine* d_out = (Affine*)g.ws_out.ensure(sizeof(Affine));
   if (!d_pts || !d_sc || !d_out) return fail("device allocation failed");
   MsmOpts opt;
+  g.hf.pending = false;
   g.dbg_e2e = getenv("BP_E2E_TIMING") != nullptr;
   if (n && upload_operands(d_pts, pts64, d_sc, sc32, n, &opt)) return 1;
+  opt.host_finish = true;                       // (takes effect with one rank only: R > 1 exchanges XYZZ partials on the device)
   if (msm_sharded_device(d_pts, d_sc, n, d_out, opt)) { cudaStreamSynchronize(g.copy_stream); return 1; }
   g.dbg_rec(8, g.stream);
-  BP_CUDA(cudaMemcpyAsync(out64, d_out, 64, cudaMemcpyDeviceToHost, g.stream));
-  BP_CUDA(cudaStreamSynchronize(g.stream));
+  if (msm_finish_to_host(d_out, out64)) return 1;
   if (g.dbg_e2e && opt.halves) {
     float t[9] = {0};
     for (int i = 1; i < 9; i++) if (g.dbg_ev[i]) cudaEventElapsedTime(&t[i], g.dbg_ev[0], g.dbg_ev[i]);
@@ -1225,6 +1226,11 @@ int bp_test_ec(int op, const uint8_t* a64, const uint8_t* b64, size_t n, uint8_t
 int bp_test_xyzz_to_affine_host(const uint8_t* xyzz128, size_t count, uint8_t* out64) {      // host-only: needs no GPU
   if (count > 8) return fail("bp_test_xyzz_to_affine_host: at most 8 points");
   xyzz_to_affine_host(xyzz128, count, out64);
+  return 0;
+}
+int bp_test_horner_host(const uint8_t* winsum128, int c, int W, int U, int dbl, uint8_t out64[64]) {      // host-only: needs no GPU
+  if (c < 1 || W < 1 || U != W + (dbl ? 1 : 0)) return fail("bp_test_horner_host: bad shape");
+  horner_host(winsum128, c, W, U, dbl, out64);
   return 0;
 }
 int bp_test_fq(int op, int on_device, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32) {

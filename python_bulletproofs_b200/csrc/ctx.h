@@ -55,6 +55,10 @@ struct Ctx {
   int force_c = 0, last_c = 0;
   bool pre_attr_set = false; unsigned pre_chunk = 0;
   bool pre_fused = true;      // pre path: no digit array between the histogram and the scatter pass, the scatter recomputes the digits (bp_msm_set_pre_fused)
+  // host-finished Horner (fp_host.h: horner_host): a host-result MSM on the plain path leaves its U window sums where `ws` points
+  // instead of launching k_combine; the caller copies them out and finishes on a host core
+  struct HostFinish { const void* ws = nullptr; int c = 0, W = 0, U = 0, dbl = 0; bool pending = false; } hf;
+  bool hf_want = false, hf_enabled = true;
   int pre_slots = 1; unsigned pre_slots_min = 1u << 18;   // slot sort of the precomputed path (bp_msm_set_pre_slots)
   DevBuf ws_slots, ws_slots_ovf;
   bool tails2d = false;       // 2-D marginal bucket reduction for the wide units of a large plain MSM (bp_msm_set_tails2d): measured slower, off

@@ -59,7 +59,83 @@ inline void inv(uint64_t r[4], const uint64_t a[4]) {
   }
   memcpy(r, is_one(u) ? x1 : x2, 32);
 }
+inline void add(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {      // canonical operands and result
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) { c += (u128)a[i] + b[i]; r[i] = (uint64_t)c; c >>= 64; }
+  if ((uint64_t)c) { c = PC; for (int i = 0; i < 4; i++) { c += r[i]; r[i] = (uint64_t)c; c >>= 64; } }      // - 2^256 + PC = - p
+  canon(r);
+}
+inline void sub(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {
+  u128 bw = 0;
+  for (int i = 0; i < 4; i++) { u128 d = (u128)a[i] - b[i] - (uint64_t)bw; r[i] = (uint64_t)d; bw = (d >> 64) & 1; }
+  if ((uint64_t)bw) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)r[i] + P64[i]; r[i] = (uint64_t)c; c >>= 64; } }
+}
+inline void dbl(uint64_t r[4], const uint64_t a[4]) { add(r, a, a); }
+
+// Jacobian points (x = X/Z^2, y = Y/Z^3; Z = 0: the identity) for the serial tails the host takes over from the device
+struct JacH { uint64_t X[4], Y[4], Z[4]; };
+inline void jac_from_xyzz(JacH& r, const uint8_t* xyzz) {      // (X, Y, ZZ, ZZZ) -> (X*ZZ, Y*ZZZ, ZZ)   [ZZ^3 = ZZZ^2]
+  uint64_t X[4], Y[4], ZZ[4], ZZZ[4];
+  memcpy(X, xyzz, 32); canon(X); memcpy(Y, xyzz + 32, 32); canon(Y);
+  memcpy(ZZ, xyzz + 64, 32); canon(ZZ); memcpy(ZZZ, xyzz + 96, 32); canon(ZZZ);
+  mul(r.X, X, ZZ); mul(r.Y, Y, ZZZ); memcpy(r.Z, ZZ, 32);
+  if (is_zero(ZZZ)) memset(r.Z, 0, 32);
+}
+inline void jac_dbl(JacH& p) {                                  // dbl-2009-l (a = 0): 2M + 5S; the identity stays the identity
+  uint64_t A[4], B[4], C[4], D[4], E[4], F[4], t[4];
+  mul(A, p.X, p.X); mul(B, p.Y, p.Y); mul(C, B, B);
+  add(t, p.X, B); mul(t, t, t); sub(t, t, A); sub(t, t, C); dbl(D, t);
+  dbl(E, A); add(E, E, A);
+  mul(F, E, E);
+  mul(p.Z, p.Y, p.Z); dbl(p.Z, p.Z);
+  dbl(t, D); sub(p.X, F, t);
+  sub(t, D, p.X); mul(t, E, t);
+  dbl(C, C); dbl(C, C); dbl(C, C);
+  sub(p.Y, t, C);
+}
+inline void jac_add(JacH& p, const JacH& q) {                    // complete: identities, P + P, P - P
+  if (is_zero(q.Z)) return;
+  if (is_zero(p.Z)) { p = q; return; }
+  uint64_t Z1Z1[4], Z2Z2[4], U1[4], U2[4], S1[4], S2[4], H[4], R[4], HH[4], HHH[4], V[4], t[4];
+  mul(Z1Z1, p.Z, p.Z); mul(Z2Z2, q.Z, q.Z);
+  mul(U1, p.X, Z2Z2); mul(U2, q.X, Z1Z1);
+  mul(S1, p.Y, q.Z); mul(S1, S1, Z2Z2);
+  mul(S2, q.Y, p.Z); mul(S2, S2, Z1Z1);
+  sub(H, U2, U1); sub(R, S2, S1);
+  if (is_zero(H)) {
+    if (is_zero(R)) { jac_dbl(p); return; }
+    memset(&p, 0, sizeof(p)); return;
+  }
+  mul(HH, H, H); mul(HHH, H, HH); mul(V, U1, HH);
+  mul(t, p.Z, q.Z); mul(p.Z, t, H);
+  mul(p.X, R, R); sub(p.X, p.X, HHH); dbl(t, V); sub(p.X, p.X, t);
+  sub(t, V, p.X); mul(t, R, t); mul(S1, S1, HHH); sub(p.Y, t, S1);
+}
+inline void jac_to_affine(const JacH& p, uint8_t out64[64]) {   // canonical (x, y); the identity becomes 64 zero bytes
+  if (is_zero(p.Z)) { memset(out64, 0, 64); return; }
+  uint64_t zi[4], zi2[4], x[4], y[4];
+  inv(zi, p.Z); mul(zi2, zi, zi);
+  mul(x, p.X, zi2); mul(zi2, zi2, zi); mul(y, p.Y, zi2);
+  memcpy(out64, x, 32); memcpy(out64 + 32, y, 32);
+}
 }  // namespace fph
+
+// Horner over the window sums of ONE MSM, on the host (k_combine's job: /root/reference/src/pippenger/pippenger.py:56-60, the loop
+// that squares c times and multiplies the next window in): winsum = U XYZZ points (128 bytes each) as the bucket reduction left
+// them, unit U-1 (and U-2 when `dbl`) the top window.  112 dependent doublings at c = 16: ~0.23 ms as a 4-lane chain on the
+// device (1.4 us per doubling at 2 GHz with 32-bit multipliers), ~30 us on a host core -- which the result is headed for anyway.
+inline void horner_host(const uint8_t* winsum, int c, int W, int U, int dblunits, uint8_t out64[64]) {
+  using namespace fph;
+  JacH acc, v;
+  jac_from_xyzz(acc, winsum + 128 * (size_t)(U - 1));
+  if (dblunits) { jac_from_xyzz(v, winsum + 128 * (size_t)(U - 2)); jac_add(acc, v); }
+  for (int w = W - 2; w >= 0; w--) {
+    for (int d = 0; d < c; d++) jac_dbl(acc);
+    jac_from_xyzz(v, winsum + 128 * (size_t)w);
+    jac_add(acc, v);
+  }
+  jac_to_affine(acc, out64);
+}
 
 // count XYZZ points (128 little-endian bytes each: X, Y, ZZ, ZZZ, lazy residues < 2^256) -> canonical affine (64 bytes each);
 // the identity (ZZ = 0 mod p) becomes 64 zero bytes.  One shared inversion (Montgomery's trick over the ZZZ values).

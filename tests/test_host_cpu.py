@@ -255,3 +255,49 @@ def test_host_xyzz_to_affine_matches_bigint():
         out = ctypes.create_string_buffer(64 * cnt)
         assert nat.load().bp_test_xyzz_to_affine_host(b"".join(recs), cnt, out) == 0
         assert out.raw == b"".join(want), trial
+
+
+def test_host_horner_over_window_sums_matches_oracle():
+    """fp_host.h: horner_host -- the Horner chain over the window sums that host-result MSMs (bp_msm) hand to the host instead of
+    running k_combine: sum_w 2^(c*w) * S_w with complete Jacobian arithmetic (identity sums, equal sums: P + P, opposite sums: P - P,
+    non-canonical coordinate representatives), for shapes with and without a second unit of the top window -- against the oracle."""
+    import random
+    P = 2 ** 256 - 2 ** 32 - 977
+    rng = random.Random(1234)
+    le = lambda v: int(v).to_bytes(32, "little")      # noqa: E731
+    base = [ecc.py_mul(ecc.G, rng.getrandbits(250) + 1) for _ in range(5)]
+
+    def rec(pt):
+        if pt is None:
+            return le(rng.getrandbits(256)) + le(rng.getrandbits(256)) + le(0 if rng.random() < 0.5 else P) + le(0)
+        x, y = pt
+        z = rng.randrange(1, P)
+        zz, zzz = z * z % P, z * z * z % P
+        vals = [x * zz % P, y * zzz % P, zz, zzz]
+        vals = [v + P if rng.random() < 0.3 and v + P < 2 ** 256 else v for v in vals]
+        return b"".join(le(v) for v in vals)
+
+    lib = nat.load()
+    for c, W, dbl in ((16, 8, 1), (13, 10, 0), (5, 26, 0), (1, 128, 1), (8, 16, 1), (3, 43, 0)):
+        for trial in range(4):
+            U = W + dbl
+            sums = []
+            for u in range(U):
+                r = rng.random()
+                sums.append(None if r < 0.2 else base[rng.randrange(5)])
+            if trial == 1:                       # top window: both units the same point (P + P), next window its negation after the doublings' input
+                sums[U - 1] = base[0]
+                if dbl:
+                    sums[U - 2] = base[0]
+            if trial == 2 and dbl:               # P - P in the top window
+                sums[U - 1] = base[1]; sums[U - 2] = ecc.point_neg(base[1])
+            if trial == 3:                       # everything empty
+                sums = [None] * U
+            want = None
+            for u in range(U):
+                w = u if u < W else W - 1        # the second unit of the top window carries the top window's weight
+                if sums[u] is not None:
+                    want = ecc.point_add(want, ecc.py_mul(sums[u], 1 << (c * w)))
+            out = ctypes.create_string_buffer(64)
+            assert lib.bp_test_horner_host(b"".join(rec(s_) for s_ in sums), c, W, U, dbl, out) == 0
+            assert out.raw == ecc.pack_point(want), (c, W, dbl, trial)

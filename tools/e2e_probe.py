@@ -6,6 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 nat.init(0); lib = nat.load()
 lib.bp_msm_set_tails2d(int(os.environ.get("BP_TAILS2D", "0")))
+lib.bp_msm_set_host_finish(int(os.environ.get("BP_HOST_FINISH", "1")))
 lib.bp_msm_set_chunk_fit(int(os.environ.get("BP_CHUNK_FIT", "0")))
 lgn = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 n = 1 << lgn
