@@ -9,6 +9,7 @@ export BP_BENCH_NO_SWEEP=1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/r2_launches_bench.csv \
     python bench.py --steps 2 --warmup 1 --no-verify --strong "" > gpurun_out/r2_launches_bench.log 2>&1
 tail -c 300 gpurun_out/r2_launches_bench.log; echo
+[ "$1" = "list" ] && exit 0      # (the three full captures are ~27 MB each; gpurun brings back at most 64 MiB per call: take them in a second call)
 for k in k_digits_pre k_scatter_pre; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/r2_${k#k_} \
       env BP_PRE_SLOTS=0 python tools/msm_probe.py --lgn 20 --c 16 --iters 2 --pre 0 > gpurun_out/r2_${k#k_}.log 2>&1
