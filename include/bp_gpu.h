@@ -272,6 +272,8 @@ int bp_test_ec(int op, const uint8_t* a64, const uint8_t* b64, size_t n, uint8_t
 int bp_test_fq(int op, int on_device, const uint8_t* a32, const uint8_t* b32, size_t n, uint8_t* out32);
 /* host F_p (csrc/fp_host.h): count <= 8 XYZZ points (128 bytes each) -> canonical affine, as the IPA prover's host step finishes L and R */
 int bp_test_xyzz_to_affine_host(const uint8_t* xyzz128, size_t count, uint8_t* out64);
+/* host sum of canonical affine points (64 zero bytes = identity): the rank partials of a sharded host-result MSM (csrc/fp_host.h) */
+int bp_test_affine_sum_host(const uint8_t* pts64, size_t count, uint8_t out64[64]);
 /* host Horner over the U window sums (XYZZ, 128 bytes each) of one MSM, as bp_msm finishes a host-result MSM (csrc/fp_host.h: horner_host);
    U = W + dbl, unit U-1 (and U-2 when dbl) the top window */
 int bp_test_horner_host(const uint8_t* winsum128, int c, int W, int U, int dbl, uint8_t out64[64]);

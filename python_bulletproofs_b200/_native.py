@@ -93,6 +93,7 @@ PROTOTYPES = {
     "bp_test_ec": (ctypes.c_int, [ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_test_fq": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
     "bp_test_xyzz_to_affine_host": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
+    "bp_test_affine_sum_host": (ctypes.c_int, [c_u8p, c_sz, c_u8p]),
     "bp_test_horner_host": (ctypes.c_int, [c_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_u8p]),
     "bp_nccl_unique_id": (ctypes.c_int, [c_u8p]),
     "bp_nccl_init": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u8p]),

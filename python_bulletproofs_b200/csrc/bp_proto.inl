@@ -1029,7 +1029,23 @@ int bp_msm_sharded_host(const uint8_t* pts64, const uint8_t* sc32, size_t n, uin
   g.hf.pending = false;
   g.dbg_e2e = getenv("BP_E2E_TIMING") != nullptr;
   if (n && upload_operands(d_pts, pts64, d_sc, sc32, n, &opt)) return 1;
-  opt.host_finish = true;                       // (takes effect with one rank only: R > 1 exchanges XYZZ partials on the device)
+  opt.host_finish = true;
+  const int R = g_comm ? g_nranks : 1;
+  if (R > 1 && g.hf_enabled && !g.profiling) {
+    // several ranks, host result: every rank finishes its own slice on the host (Horner chain + affine conversion, fp_host.h), the
+    // 64-byte affine partials are all-gathered (NCCL, through a device staging word) and added on every rank in rank order --
+    // instead of k_combine (0.23 ms) + all-gather of XYZZ partials + k_xyzz_sum with its lone-thread inversion
+    uint8_t mine[64];
+    if (n == 0) memset(mine, 0, 64);
+    else {
+      if (msm_run(d_pts, nullptr, d_sc, (u32)n, nullptr, 1, n, d_out, nullptr, opt)) { cudaStreamSynchronize(g.copy_stream); return 1; }
+      if (msm_finish_to_host(d_out, mine)) return 1;
+    }
+    std::vector<uint8_t> all((size_t)64 * R);
+    if (bp_allgather_bytes(mine, 64, all.data())) return 1;
+    affine_sum_host(all.data(), (size_t)R, out64);
+    return 0;
+  }
   if (msm_sharded_device(d_pts, d_sc, n, d_out, opt)) { cudaStreamSynchronize(g.copy_stream); return 1; }
   g.dbg_rec(8, g.stream);
   if (msm_finish_to_host(d_out, out64)) return 1;
@@ -1226,6 +1242,10 @@ int bp_test_ec(int op, const uint8_t* a64, const uint8_t* b64, size_t n, uint8_t
 int bp_test_xyzz_to_affine_host(const uint8_t* xyzz128, size_t count, uint8_t* out64) {      // host-only: needs no GPU
   if (count > 8) return fail("bp_test_xyzz_to_affine_host: at most 8 points");
   xyzz_to_affine_host(xyzz128, count, out64);
+  return 0;
+}
+int bp_test_affine_sum_host(const uint8_t* pts64, size_t count, uint8_t out64[64]) {      // host-only: needs no GPU
+  affine_sum_host(pts64, count, out64);
   return 0;
 }
 int bp_test_horner_host(const uint8_t* winsum128, int c, int W, int U, int dbl, uint8_t out64[64]) {      // host-only: needs no GPU

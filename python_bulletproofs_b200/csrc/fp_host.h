@@ -120,6 +120,21 @@ inline void jac_to_affine(const JacH& p, uint8_t out64[64]) {   // canonical (x,
 }
 }  // namespace fph
 
+// sum of `count` canonical affine points (64 bytes each, 64 zero bytes = the identity) -> canonical affine: the partial results of
+// the ranks of a sharded host-result MSM, added on every rank in the same order
+inline void affine_sum_host(const uint8_t* pts64, size_t count, uint8_t out64[64]) {
+  using namespace fph;
+  JacH acc; memset(&acc, 0, sizeof(acc));
+  for (size_t i = 0; i < count; i++) {
+    JacH q; memset(&q, 0, sizeof(q));
+    memcpy(q.X, pts64 + 64 * i, 32); memcpy(q.Y, pts64 + 64 * i + 32, 32);
+    if (is_zero(q.X) && is_zero(q.Y)) continue;
+    q.Z[0] = 1;
+    jac_add(acc, q);
+  }
+  jac_to_affine(acc, out64);
+}
+
 // Horner over the window sums of ONE MSM, on the host (k_combine's job: /root/reference/src/pippenger/pippenger.py:56-60, the loop
 // that squares c times and multiplies the next window in): winsum = U XYZZ points (128 bytes each) as the bucket reduction left
 // them, unit U-1 (and U-2 when `dbl`) the top window.  112 dependent doublings at c = 16: ~0.23 ms as a 4-lane chain on the

@@ -301,3 +301,21 @@ def test_host_horner_over_window_sums_matches_oracle():
             out = ctypes.create_string_buffer(64)
             assert lib.bp_test_horner_host(b"".join(rec(s_) for s_ in sums), c, W, U, dbl, out) == 0
             assert out.raw == ecc.pack_point(want), (c, W, dbl, trial)
+
+
+def test_host_affine_sum_matches_oracle():
+    """fp_host.h: affine_sum_host -- the rank partials of a sharded host-result MSM added on the host: identities, repeated points
+    (P + P), opposite points, a single point, nothing at all."""
+    import random
+    rng = random.Random(77)
+    base = [ecc.py_mul(ecc.G, rng.getrandbits(250) + 1) for _ in range(4)]
+    lib = nat.load()
+    cases = [[], [None], [base[0]], [base[0], base[0]], [base[1], ecc.point_neg(base[1])], [None, base[2], None, base[3], base[2], ecc.point_neg(base[3])],
+             [base[i % 4] for i in range(8)]]
+    for pts in cases:
+        want = None
+        for p_ in pts:
+            want = ecc.point_add(want, p_)
+        out = ctypes.create_string_buffer(64)
+        assert lib.bp_test_affine_sum_host(b"".join(ecc.pack_point(p_) for p_ in pts), len(pts), out) == 0
+        assert out.raw == ecc.pack_point(want), pts
