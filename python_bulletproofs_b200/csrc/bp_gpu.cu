@@ -263,17 +263,34 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
   if (!digits || !entries || !count || !start || !cursor || !tiles || !buckets || !segsum || !winsum || !part || !big || !phi)
     return fail("workspace allocation failed");
 
+  // slot sort (msm.cuh): one scattered pass for one large MSM; the exact counting sort stays queued behind it, gated on the overflow word
+  // (only where a bucket holds >= 48 entries: at a bucket boundary k_accumulate_slots fetches the next entry AFTER the flush, an
+  //  exposed load per boundary -- 2^18 terms, 16 entries per bucket: accumulate 0.567 -> 0.624 ms, the whole MSM 1.19 -> 1.23 ms;
+  //  2^20 terms, 64 per bucket: 2.870 -> 2.798 ms.  Mode 2, the test hook, takes every size.)
+  const bool use_slots = g.pre_slots > 0 && nmsm == 1 && !halves && !d_offsets && !point_idx && !opt.skip_below && T >= g.pre_slots_min &&
+                         (g.pre_slots == 2 || 2.0 * (double)T / (double)sh.H >= 48.0 || g.pre_slots_any);
+  u32 cap = 0; u32* slots = nullptr; u32* overflow = nullptr;
+  if (use_slots) {
+    const double lam = 2.0 * (double)T / (double)sh.H;                   // every unit takes 2T sub-terms over H buckets
+    cap = g.pre_slots == 2 ? 8u : (u32)(lam + 9.5 * sqrt(lam) + 8.0);
+    cap = (cap + 7u) & ~7u;
+    slots = (u32*)g.ws_slots.ensure(nb * (size_t)cap * sizeof(u32));
+    overflow = (u32*)g.ws_slots_ovf.ensure(64);
+    if (!slots || !overflow) return fail("workspace allocation failed");
+    BP_CUDA(cudaMemsetAsync(overflow, 0, sizeof(u32), st));
+  }
   BP_CUDA(cudaMemsetAsync(count, 0, (nb + 1) * sizeof(u32), st));
   if (prof) cudaEventRecord(g.ev[0], st);
   g.dbg_rec(4, st);
-  ++g.nlaunch, k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count, opt.skip_below ? point_idx : nullptr, opt.skip_below);
+  if (use_slots) ++g.nlaunch, k_digits_slots<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, sh, digits, cap, count, slots, overflow);
+  else ++g.nlaunch, k_digits<<<(T + 255) / 256, 256, 0, st>>>(scalars, T, d_offsets, nmsm, sh, digits, count, opt.skip_below ? point_idx : nullptr, opt.skip_below);
   if (prof) cudaEventRecord(g.ev[1], st);
   ++g.nlaunch, k_scan_tiles<<<(unsigned)ntiles, 256, 0, st>>>(count, start, tiles, nb + 1);
   ++g.nlaunch, k_scan_sums<<<1, 1024, 0, st>>>(tiles, ntiles);
   ++g.nlaunch, k_scan_add<<<(unsigned)ntiles, 256, 0, st>>>(start, tiles, nb + 1, nullptr);
   if (prof) cudaEventRecord(g.ev[2], st);
   BP_CUDA(cudaMemcpyAsync(cursor, start, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));   // cursors start at the bucket offsets
-  ++g.nlaunch, k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, cursor, entries);
+  ++g.nlaunch, k_scatter<<<(2 * T + 255) / 256, 256, 0, st>>>(digits, T, d_offsets, nmsm, sh, cursor, entries, overflow);
   if (prof) cudaEventRecord(g.ev[3], st);
   g.dbg_rec(5, st);
   BP_CUDA(cudaMemsetAsync(buckets, 0, nbv * sizeof(XYZZ), st));         // empty buckets = identity (ZZ = 0)
@@ -301,7 +318,8 @@ int msm_run(const Affine* points, const u32* point_idx, const Fq* scalars, u32 T
     ++g.nlaunch, k_phi<<<(T + 127) / 128, 128, 0, st>>>(points, point_idx, T, phi);
     // E (= start[nb]) stays on the device: launch for the upper bound W*T, threads past E exit at once
     if (prof) cudaEventRecord(g.ev_k0, st);
-    ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, sh.chunk, buckets, part);
+    if (use_slots) ++g.nlaunch, k_accumulate_slots<true><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, phi, start, (u32)nb, slots, cap, overflow, sh.chunk, buckets, part);
+    ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(points, point_idx, phi, start, entries, zero_word, start + nb, sh.chunk, buckets, part, 0, 0, overflow);
     if (prof) cudaEventRecord(g.ev_k1, st);
     ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(start, 0, nb, zero_word, sh.chunk, part, buckets, big, big_cap);
     ++g.nlaunch, k_fixup_mid<<<2 * g.sm_count, 256, 0, st>>>(start, zero_word, sh.chunk, part, buckets, big, big_cap);
@@ -511,7 +529,7 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
     ++g.nlaunch, k_aff_index<<<(unsigned)(((emax_pad >> P) > nb + 1 ? (emax_pad >> P) : nb + 1) + 255) / 256, 256, 0, st>>>(start, (u32)nb, entries, P, red_start, red_ent);
     acc_pts = src; acc_start = red_start; acc_ent = red_ent;
   }
-  if (use_slots) ++g.nlaunch, k_accumulate_slots<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pre, start, (u32)nb, slots, cap, overflow, sh.chunk, buckets, part);
+  if (use_slots) ++g.nlaunch, k_accumulate_slots<false><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pre, nullptr, start, (u32)nb, slots, cap, overflow, sh.chunk, buckets, part);
   ++g.nlaunch, k_accumulate<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(acc_pts, nullptr, nullptr, acc_start, acc_ent, zero_word, acc_start + nb, sh.chunk, buckets, part, 0, 0, overflow);
   if (prof) cudaEventRecord(g.ev_k1, st);
   ++g.nlaunch, k_fixup<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(acc_start, 0, nb, zero_word, sh.chunk, part, buckets, big, big_cap);
@@ -865,6 +883,7 @@ int bp_msm_set_pre_fused(int on) { if (g.inited) cudaStreamSynchronize(g.stream)
 int bp_msm_set_pre_slots(int mode, size_t min_terms) {   /* 0 = exact counting sort only, 1 = slot sort for MSMs of >= min_terms terms (0 = keep), 2 = same with 8 slots per bucket (test hook: forces the fallback) */
   if (g.inited) cudaStreamSynchronize(g.stream);
   g.pre_slots = mode; if (min_terms) g.pre_slots_min = (unsigned)min_terms;
+  g.pre_slots_any = min_terms != 0 && min_terms < (1u << 18);      // a lowered threshold (tests) also lifts the plain path's bucket-load condition
   pre_graphs_clear();
   return 0;
 }

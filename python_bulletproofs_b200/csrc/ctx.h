@@ -59,7 +59,7 @@ struct Ctx {
   // instead of launching k_combine; the caller copies them out and finishes on a host core
   struct HostFinish { const void* ws = nullptr; int c = 0, W = 0, U = 0, dbl = 0; bool pending = false; } hf;
   bool hf_want = false, hf_enabled = true;
-  int pre_slots = 1; unsigned pre_slots_min = 1u << 18;   // slot sort of the precomputed path (bp_msm_set_pre_slots)
+  int pre_slots = 1; unsigned pre_slots_min = 1u << 18; bool pre_slots_any = false;   // slot sort of the precomputed path (bp_msm_set_pre_slots)
   DevBuf ws_slots, ws_slots_ovf;
   bool tails2d = false;       // 2-D marginal bucket reduction for the wide units of a large plain MSM (bp_msm_set_tails2d): measured slower, off
   int aff_passes = -1;                          // batched-affine pair passes ahead of the XYZZ accumulation: <= 0 = off (default), 1..6 = that many passes (bp_msm_set_affine_passes)

@@ -170,9 +170,10 @@ __global__ void __launch_bounds__(256) k_digits(const Fq* __restrict__ scalars, 
 // one thread per sub-term: entry = {term | phi-flag << 30 | sign << 31, bucket}; cursor[b] starts at bucket_start[b], so the
 // atomic hands out absolute slots (one L2 transaction less per entry than offset + separate base load)
 __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits, u32 T, const u32* __restrict__ offsets, u32 nmsm,
-                                                 MsmShape sh, u32* __restrict__ cursor, uint2* __restrict__ entries) {
+                                                 MsmShape sh, u32* __restrict__ cursor, uint2* __restrict__ entries, const u32* __restrict__ run_if = nullptr) {
   u32 st = blockIdx.x * blockDim.x + threadIdx.x;
   if (st >= 2 * T) return;
+  if (run_if && __ldg(run_if) == 0) return;           // fallback of the slot sort (k_digits_slots): runs only when a bucket overflowed
   u32 t = st >> 1;
   u32 m = nmsm > 1 ? find_msm(offsets, nmsm, t) : 0;
   for (int w = 0; w < sh.W; w++) {
@@ -190,6 +191,41 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits,
     if (sd == 0) continue;
     u32 pos = base + (u32)__popc(peers & ((1u << lane) - 1));     // cursor[] was initialised to bucket_start[]: absolute slot
     entries[pos] = make_uint2(t | ((st & 1u) << 30) | (sd < 0 ? 0x80000000u : 0u), b);
+  }
+}
+
+// Slot sort of the plain path (one MSM, >= 2^18 terms; see "slot sort" further down): k_digits with the histogram atomic turned
+// into the slot hand-out -- digits, one returning atomic and one 4-byte store per entry in a single pass; the digit array is
+// still written (coalesced, free) because the gated fallback k_scatter reads it.  Entry = term | phi-flag << 30 | sign << 31.
+__global__ void __launch_bounds__(256) k_digits_slots(const Fq* __restrict__ scalars, u32 T, MsmShape sh, int* __restrict__ digits, u32 cap,
+                                                      u32* __restrict__ count, u32* __restrict__ slots, u32* __restrict__ overflow) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + t);
+  uint4 a = __ldg(sp), b = __ldg(sp + 1);
+  Fq k; k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
+  k = fq_reduce(k);
+  Fq half[2];
+  bool hneg[2];
+  glv_split(k, half[0], hneg[0], half[1], hneg[1]);
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const Fq kk = half[j];
+    const bool neg = hneg[j];
+    u32 carry = 0;
+    for (int w = 0; w < sh.W; w++) {
+      u32 d = scalar_bits(kk, w * sh.c, sh.c) + carry;
+      int sd;
+      if (w + 1 < sh.W && d > sh.H) { sd = (int)d - (int)(2u * sh.H); carry = 1; } else { sd = (int)d; carry = 0; }
+      if (neg) sd = -sd;
+      digits[(size_t)w * (2 * (size_t)T) + 2 * t + j] = sd;
+      if (sd == 0) continue;
+      const u32 mag = sd < 0 ? (u32)(-sd) : (u32)sd;
+      const u32 bkt = (u32)w * sh.H + (mag - 1);
+      const u32 r = atomicAdd(count + bkt, 1u);
+      if (r < cap) slots[(size_t)bkt * cap + r] = t | ((u32)j << 30) | (sd < 0 ? 0x80000000u : 0u);
+      else atomicAdd(overflow, 1u);
+    }
   }
 }
 
@@ -763,7 +799,15 @@ __global__ void __launch_bounds__(256) k_scatter_slots_pre(const Fq* __restrict_
 }
 // k_accumulate over the slot layout (precomputed path: direct point indices, no phi, no parts).  bucket_start[0 .. nb] is the
 // exclusive scan of the bucket counts; chunk boundaries, part[] and buckets[] are exactly those of k_accumulate.
-__global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate_slots(const Affine* __restrict__ points, const u32* __restrict__ bucket_start, u32 nb,
+// PHI: entries carry the phi flag of the plain path (bit 30: the point is phi[t], materialised per term by k_phi)
+template <bool PHI>
+BP_DI const Affine* slot_point_ptr(const Affine* __restrict__ points, const Affine* __restrict__ phi, u32 e) {
+  if (PHI) return ((e & 0x40000000u) ? phi : points) + (e & 0x3FFFFFFFu);
+  return points + (e & 0x7FFFFFFFu);
+}
+template <bool PHI>
+__global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate_slots(const Affine* __restrict__ points, const Affine* __restrict__ phi,
+                                                                       const u32* __restrict__ bucket_start, u32 nb,
                                                                        const u32* __restrict__ slots, u32 cap, const u32* __restrict__ overflow, u32 CL,
                                                                        XYZZ* __restrict__ buckets, XYZZ* __restrict__ part) {
   if (__ldg(overflow) != 0) return;
@@ -795,9 +839,9 @@ __global__ void __launch_bounds__(128, BP_ACC_MINB) k_accumulate_slots(const Aff
     const u32 cur = ent;
     if (i + 1 < ce && i + 1 < e) {                                       // (across a bucket boundary the entry is fetched after the flush)
       ent = __ldg(sp + i + 1);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(points + (ent & 0x7FFFFFFFu)));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(slot_point_ptr<PHI>(points, phi, ent)));
     }
-    Affine p = ld_affine(points + (cur & 0x7FFFFFFFu));
+    Affine p = ld_affine(slot_point_ptr<PHI>(points, phi, cur));
     if (cur >> 31) p.y = fp_neg(p.y);
     xyzz_madd(acc, p);
   }

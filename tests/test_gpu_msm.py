@@ -388,15 +388,17 @@ def test_msm_slot_sort_and_its_fallback():
     }
     want = {name: ecc.pack_point(ecc.msm_bytes(base, sb, n, "bucket", ecc.max_threads())) for name, sb in sets.items()}
     dq = DevicePoints(raw=base).precompute(0)
+    dp = DevicePoints(raw=base)                                          # plain path: k_digits_slots, k_accumulate_slots<true>
     out = ctypes.create_string_buffer(64)
     try:
         for mode in (1, 2, 0):
             nat.check(lib.bp_msm_set_pre_slots(mode, 1 << 12))
             for name, sb in sets.items():
                 nat.check(lib.bp_msm_h(dq.handle, sb, n, out)); assert out.raw == want[name], (mode, name)
+                nat.check(lib.bp_msm_h(dp.handle, sb, n, out)); assert out.raw == want[name], (mode, name, "plain")
             m = 5000                                                      # short vector, above the lowered threshold
             nat.check(lib.bp_msm_h(dq.handle, sets["uniform"], m, out))
             assert out.raw == ecc.pack_point(ecc.msm_bytes(base, sets["uniform"], m, "bucket", ecc.max_threads())), (mode, m)
     finally:
         lib.bp_msm_set_pre_slots(1, 1 << 18)
-    dq.free()
+    dq.free(); dp.free()
