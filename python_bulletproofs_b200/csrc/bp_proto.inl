@@ -874,8 +874,12 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
       else
         ++g.nlaunch, k_sv_comb2<<<(unsigned)((cn * 3 + 127) / 128), 128, 0, g.var_stream[cur]>>>(sv_G, cpts, lay, (u32)cn, d_var);
       BP_CUDA(cudaEventRecord(g.var_done[cur], g.var_stream[cur]));
-      if (fbtab16) ++g.nlaunch, k_rp_lookup16<<<(unsigned)cn, 128, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
-      else ++g.nlaunch, k_rp_lookup<<<(unsigned)cn, 128, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
+      static const unsigned rp_block = [] { const char* e = getenv("BP_RP_WARPS"); return e && atoi(e) == 4 ? 128u : 96u; }();      // verify.cuh: rp_warp_role
+      // (8192 proofs: 128-thread blocks 7.43-7.46 ms, 96-thread blocks at 5 per SM 7.30-7.36 ms, at 6 per SM -- 96 registers, 230 bytes
+      //  of spills -- 7.50-7.59 ms; gpurun_out/rpwarps2.log)
+      if (fbtab16 && rp_block == 96) ++g.nlaunch, k_rp_lookup16<96, 5><<<(unsigned)cn, rp_block, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
+      else if (fbtab16) ++g.nlaunch, k_rp_lookup16<128, 4><<<(unsigned)cn, rp_block, 0, g.stream>>>(fbtab16, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
+      else ++g.nlaunch, k_rp_lookup<<<(unsigned)cn, rp_block, 0, g.stream>>>(fbtab, tidx, tsc, d_off, (u32)cn, lay.fixed, d_lanes);
       XYZZ* d_grp = d_lanes + (size_t)4 * CH * BP_RP_SLOTS;
       ++g.nlaunch, k_rp_fold8<<<(nm * 8 + 127) / 128, 128, 0, g.stream>>>(d_lanes, nm, (u32)cn, d_grp);
       BP_CUDA(cudaStreamWaitEvent(g.stream, g.var_done[cur], 0));

@@ -264,8 +264,13 @@ __global__ void k_rp_accept(const Affine* __restrict__ res, u32 nproofs, const u
 // thread layout of round 1, whose folds cost a third of the lookups).  Terms on proof-specific points (idx >= nfixed) are
 // skipped: they take the window-parallel pass of svar.cuh.  Lane sums land in part[(e*nproofs + p)*64 + 32*s + lane].
 #define BP_RP_SLOTS 64
+// Blocks of 96 threads (the default): the E1 / E3 warp of the 128-thread layout is idle after 4 of ~34 steps, a quarter of the
+// resident warps of a kernel whose occupancy the registers cap at 16 warps per SM; with three warps per proof -- warp 2 takes
+// E2, then E1, then E3: 38 steps against 33 of the E4 warps -- six blocks are resident (18 warps, all busy).
+BP_DI u32 rp_warp_passes(u32 warp) { return blockDim.x == 96 ? (warp == 2 ? 3u : 1u) : (warp == 3 ? 2u : 1u); }
 BP_DI void rp_warp_role(u32 warp, u32 pass, u32& e, u32& nw, u32& s) {
   if (warp < 2) { e = 3u; nw = 2u; s = warp; }
+  else if (blockDim.x == 96) { e = pass == 0 ? 1u : (pass == 1 ? 0u : 2u); nw = 1u; s = 0u; }
   else if (warp == 2) { e = 1u; nw = 1u; s = 0u; }
   else { e = pass == 0 ? 0u : 2u; nw = 1u; s = 0u; }
 }
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(128) k_rp_lookup(const Affine* __restrict__ ta
   const u32 p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p >= nproofs) return;
 #pragma unroll 1
-  for (u32 pass = 0; pass < (warp == 3 ? 2u : 1u); pass++) {
+  for (u32 pass = 0; pass < rp_warp_passes(warp); pass++) {
     u32 e, nw, s;
     rp_warp_role(warp, pass, e, nw, s);
     const u32 lo = __ldg(offsets + e * nproofs + p), hi = __ldg(offsets + e * nproofs + p + 1);
@@ -299,13 +304,14 @@ __global__ void __launch_bounds__(128) k_rp_lookup(const Affine* __restrict__ ta
 // the longest warp of a block but by the chip-wide rate of dependent table-load + addition chains.)
 // Same with the 16-bit table: lane l owns window l & 15 of the (l >> 4)-th of two terms taken per step, so a term costs 16
 // lookups; the table lives in HBM (8.9 GB), hence the next entry is loaded into registers under the current addition.
-__global__ void __launch_bounds__(128) k_rp_lookup16(const Affine* __restrict__ tab16, const u32* __restrict__ idx, const Fq* __restrict__ sc,
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_rp_lookup16(const Affine* __restrict__ tab16, const u32* __restrict__ idx, const Fq* __restrict__ sc,
                                                      const u32* __restrict__ offsets, u32 nproofs, u32 nfixed, XYZZ* __restrict__ part) {
   const u32 p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p >= nproofs) return;
   const u32 win = lane & 15u, sub = lane >> 4;
 #pragma unroll 1
-  for (u32 pass = 0; pass < (warp == 3 ? 2u : 1u); pass++) {
+  for (u32 pass = 0; pass < rp_warp_passes(warp); pass++) {
     u32 e, nw, s;
     rp_warp_role(warp, pass, e, nw, s);
     const u32 lo = __ldg(offsets + e * nproofs + p), hi = __ldg(offsets + e * nproofs + p + 1);
