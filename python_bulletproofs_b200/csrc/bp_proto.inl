@@ -774,7 +774,8 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
   // the fixed-base table with no doublings and no bucket reduction; the ~21 proof-specific terms (V, A, S, T1, T2, u', P',
   // L_j, R_j) take the window-parallel path of svar.cuh.  Each equation is still checked exactly.
   const Affine *fbtab = nullptr, *fbtab16 = nullptr;
-  XYZZ *d_lanes = nullptr, *d_var2 = nullptr, *d_tot = nullptr, *sv_T2 = nullptr, *sv_A2 = nullptr, *sv_G2 = nullptr;
+  XYZZ *d_lanes = nullptr, *d_var2 = nullptr, *d_tot = nullptr, *sv_A2 = nullptr, *sv_G2 = nullptr;
+  Affine* sv_T2 = nullptr;
   Fq* vsc2 = nullptr; uint4* kd2 = nullptr; u32* kfl2 = nullptr;
   uint64_t fbkey = 0;
   if (fb_enabled()) {
@@ -785,7 +786,8 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
     if (fbtab) {
       d_lanes = (XYZZ*)g.ws_fb_lanes.ensure(4 * CH * (BP_RP_SLOTS + 8) * sizeof(XYZZ));
       d_var2 = (XYZZ*)g.ws_fb_var.ensure(3 * 4 * CH * sizeof(XYZZ));
-      sv_T2 = (XYZZ*)g.ws_sv_tab.ensure(2 * CH * (size_t)nv * BP_SV_ENT * sizeof(XYZZ));
+      // affine tables of the proof points (two parities) + the scratch of k_sv_table: its XYZZ chain and prefix products
+      sv_T2 = (Affine*)g.ws_sv_tab.ensure(CH * (size_t)nv * BP_SV_ENT * (2 * sizeof(Affine) + sizeof(XYZZ) + sizeof(Fp)));
       sv_A2 = (XYZZ*)g.ws_sv_acc.ensure(2 * CH * (size_t)(96 + 12) * sizeof(XYZZ));
       vsc2 = (Fq*)g.ws_sv_sc.ensure(2 * CH * (size_t)nv * (sizeof(Fq) + 2 * sizeof(uint4) + sizeof(u32)));
       if (!d_lanes || !d_var2 || !sv_T2 || !sv_A2 || !vsc2) return fail("device allocation failed");
@@ -859,11 +861,13 @@ static int rp_verify_batch_impl(const uint8_t* gs64, const uint8_t* hs64, const 
     ++g.nlaunch, k_rp_expand<<<(unsigned)cn, bd, smem, g.aux_stream>>>(psc, d_inv, lay, (u32)cn, pt_base, tsc, tidx, d_off, vsc);
     if (fbtab) {
       const u32 nm = (u32)(4 * cn);
-      XYZZ* sv_T = sv_T2 + (size_t)cur * CH * nv * BP_SV_ENT; XYZZ* sv_A = sv_A2 + (size_t)cur * CH * 96; XYZZ* sv_G = sv_G2 + (size_t)cur * CH * 12;
+      Affine* sv_T = sv_T2 + (size_t)cur * CH * nv * BP_SV_ENT;
+      XYZZ* sv_scr = (XYZZ*)(sv_T2 + 2 * CH * (size_t)nv * BP_SV_ENT); Fp* sv_pre = (Fp*)(sv_scr + CH * (size_t)nv * BP_SV_ENT);
+      XYZZ* sv_A = sv_A2 + (size_t)cur * CH * 96; XYZZ* sv_G = sv_G2 + (size_t)cur * CH * 12;
       uint4* kd = kd2 + (size_t)cur * CH * nv * 2; u32* kfl = kfl2 + (size_t)cur * CH * nv;
       XYZZ* d_var = d_var2 + (size_t)cur * 4 * CH;
       const Affine* cpts = table + pt_base;
-      ++g.nlaunch, k_sv_table<<<(unsigned)((cn * lay.npt + 127) / 128), 128, 0, g.aux_stream>>>(cpts, lay, (u32)cn, vsc, sv_T, kd, kfl, d_bad, d_var + 2 * cn);
+      ++g.nlaunch, k_sv_table<<<(unsigned)((cn * lay.npt + 127) / 128), 128, 0, g.aux_stream>>>(cpts, lay, (u32)cn, vsc, sv_T, sv_scr, sv_pre, kd, kfl, d_bad, d_var + 2 * cn);
       BP_CUDA(cudaEventRecord(g.aux_ready[cur], g.aux_stream));
       BP_CUDA(cudaStreamWaitEvent(g.stream, g.aux_ready[cur], 0));
       BP_CUDA(cudaStreamWaitEvent(g.var_stream[cur], g.aux_ready[cur], 0));

@@ -22,6 +22,7 @@
 #include "glv.cuh"
 #include "coop4.cuh"
 #include "verify.cuh"
+#include "msm.cuh"
 
 namespace bp {
 
@@ -58,56 +59,86 @@ __global__ void __launch_bounds__(128) k_rp_check_points(const Affine* __restric
 
 // One thread per (proof, point slot).  pts = the chunk's proof points (npt per proof), vsc = its variable scalars (nv per proof,
 // written by k_rp_expand).  bad[] must be zeroed beforehand.  var_e3[p] receives -u_new (the whole variable part of E3).
+// The multiples 2P .. 8P leave the kernel in AFFINE form (T: 64 bytes per entry), so that k_sv_main's ~1300 additions per proof
+// are mixed additions (8M + 2S instead of 12M + 2S): the chain is built in XYZZ (parked in `scr`, with the prefix products of the
+// ZZZ values in `pre`), the product of a thread's seven ZZZ is inverted together with those of the 31 other lanes
+// (warp_batch_inverse, affine.cuh: two shuffle scans, one binary GCD per warp) and the thread walks back through its entries
+// (Montgomery's trick).  No thread leaves before the shared inversion; threads without a table contribute 1.
 __global__ void __launch_bounds__(128) k_sv_table(const Affine* __restrict__ pts, RpLayout lay, u32 cn, const Fq* __restrict__ vsc,
-                                                  XYZZ* __restrict__ T, uint4* __restrict__ kd, u32* __restrict__ kflags,
+                                                  Affine* __restrict__ T, XYZZ* scr, Fp* pre, uint4* __restrict__ kd, u32* __restrict__ kflags,
                                                   uint8_t* __restrict__ bad, XYZZ* __restrict__ var_e3) {
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= cn * lay.npt) return;
-  const u32 p = t / lay.npt, slot = t % lay.npt, nv = 5 + 2 * lay.L;
-  const Affine P = ld_affine(pts + t);
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  const bool in_range = t < cn * lay.npt;
+  const u32 p = in_range ? t / lay.npt : 0u, slot = in_range ? t % lay.npt : 0u, nv = 5 + 2 * lay.L;
+  Affine P; P.x = fp_zero(); P.y = fp_zero();
+  if (in_range) P = ld_affine(pts + t);
   const bool ok = affine_on_curve(P);
-  if (!ok) bad[p] = 1;
+  if (in_range && !ok) bad[p] = 1;
   const bool ident = affine_is_identity(P) || !ok;         // (a rejected proof's garbage never enters the formulas)
-  if (slot == RP_UNEW) {
+  if (in_range && slot == RP_UNEW) {
     XYZZ e = xyzz_identity();
     if (!ident) { e.X = P.x; e.Y = fp_neg(P.y); e.ZZ = fp_one(); e.ZZZ = fp_one(); }
     st_xyzz(var_e3 + p, e);
   }
-  const u32 v = sv_term(slot);
-  if (v == BP_SV_NONE) return;
-  const size_t idx = (size_t)p * nv + v;
-  // k = k1 + k2*lambda, |k_i| < 2^128; signed 4-bit digits d_w = nibble_w(|k_i| + 0x0888..8) - 8 for w < 31 (in [-8, 7]) and the
-  // top window unrecoded, d_31 = (|k_i| + 0x0888..8) >> 124 in [0, 16]
-  Fq k = fq_reduce(ld_fq(vsc + idx)), m[2];
-  bool neg[2];
-  glv_split(k, m[0], neg[0], m[1], neg[1]);
-  u32 flags = (neg[0] ? 1u : 0u) | (neg[1] ? 2u : 0u);
+  const u32 v = in_range ? sv_term(slot) : BP_SV_NONE;
+  const bool var = v != BP_SV_NONE;
+  const size_t idx = (size_t)p * nv + (var ? v : 0u);
+  if (var) {
+    // k = k1 + k2*lambda, |k_i| < 2^128; signed 4-bit digits d_w = nibble_w(|k_i| + 0x0888..8) - 8 for w < 31 (in [-8, 7]) and the
+    // top window unrecoded, d_31 = (|k_i| + 0x0888..8) >> 124 in [0, 16]
+    Fq k = fq_reduce(ld_fq(vsc + idx)), m[2];
+    bool neg[2];
+    glv_split(k, m[0], neg[0], m[1], neg[1]);
+    u32 flags = (neg[0] ? 1u : 0u) | (neg[1] ? 2u : 0u);
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const u32 C[4] = {0x88888888u, 0x88888888u, 0x88888888u, 0x08888888u};
-    u32 r[4];
-    u64 cy = 0;
+    for (int h = 0; h < 2; h++) {
+      const u32 C[4] = {0x88888888u, 0x88888888u, 0x88888888u, 0x08888888u};
+      u32 r[4];
+      u64 cy = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { cy += (u64)m[h].v[i] + C[i]; r[i] = (u32)cy; cy >>= 32; }
-    if (cy) flags |= 4u << h;
-    kd[2 * idx + h] = make_uint4(r[0], r[1], r[2], r[3]);
+      for (int i = 0; i < 4; i++) { cy += (u64)m[h].v[i] + C[i]; r[i] = (u32)cy; cy >>= 32; }
+      if (cy) flags |= 4u << h;
+      kd[2 * idx + h] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    kflags[idx] = flags;
   }
-  kflags[idx] = flags;
-  XYZZ* out = T + idx * BP_SV_ENT;
-  if (ident) {
-    const XYZZ z = xyzz_identity();
-    for (int j = 0; j < BP_SV_ENT; j++) st_xyzz(out + j, z);
-    return;
+  const bool tab = var && !ident;
+  Affine* out = T + idx * BP_SV_ENT;
+  XYZZ* sc = scr + idx * BP_SV_ENT;
+  Fp* pr = pre + idx * BP_SV_ENT;
+  Fp prod = fp_one();
+  if (var && ident) {
+    Affine z; z.x = fp_zero(); z.y = fp_zero();
+    for (int j = 0; j < BP_SV_ENT; j++) st_affine(out + j, z);
   }
-  XYZZ acc = xyzz_mdbl(P);
-  st_xyzz(out, acc);
+  if (tab) {
+    XYZZ acc = xyzz_mdbl(P);
 #pragma unroll 1
-  for (int j = 1; j < BP_SV_ENT; j++) { xyzz_madd_ni(acc, P); st_xyzz(out + j, acc); }
+    for (int j = 0; j < BP_SV_ENT; j++) {
+      if (j) xyzz_madd_ni(acc, P);
+      st_xyzz(sc + j, acc);
+      st_fp(pr + j, prod);                                 // ZZZ_0 .. ZZZ_{j-1}
+      prod = fp_mul(prod, acc.ZZZ);                        // (never zero: jP, j <= 8, of a point of prime order)
+    }
+  }
+  Fp inv = warp_batch_inverse(prod, lane);                 // 1 / (ZZZ_0 .. ZZZ_6) of this thread
+  if (!tab) return;
+#pragma unroll 1
+  for (int j = BP_SV_ENT - 1; j >= 0; j--) {
+    XYZZ e;
+    e.X = ld_fp_plain(&sc[j].X); e.Y = ld_fp_plain(&sc[j].Y); e.ZZ = ld_fp_plain(&sc[j].ZZ); e.ZZZ = ld_fp_plain(&sc[j].ZZZ);
+    const Fp zi3 = fp_mul(inv, ld_fp_plain(pr + j));       // ZZZ_j^-1
+    inv = fp_mul(inv, e.ZZZ);
+    const Fp zi2 = fp_mul(fp_sqr(e.ZZ), fp_sqr(zi3));      // ZZ^-1 = ZZ^2 * ZZZ^-2
+    Affine a;
+    a.x = fp_mul(e.X, zi2); a.y = fp_mul(e.Y, zi3);
+    st_affine(out + j, a);
+  }
 }
 
 // One warp per proof; lane = window.  Aw[(p*3 + e)*32 + w] = sum over the sub-terms of equation e (0: E1, 1: E2, 2: E4) of
 // digit_w * (P or phi(P)).
-__global__ void __launch_bounds__(128, 4) k_sv_main(const Affine* __restrict__ pts, RpLayout lay, u32 cn, const XYZZ* __restrict__ T,
+__global__ void __launch_bounds__(128, 4) k_sv_main(const Affine* __restrict__ pts, RpLayout lay, u32 cn, const Affine* __restrict__ T,
                                                     const uint4* __restrict__ kd, const u32* __restrict__ kflags, XYZZ* __restrict__ Aw) {
   const u32 p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (p >= cn) return;                                    // whole warps
@@ -135,12 +166,10 @@ __global__ void __launch_bounds__(128, 4) k_sv_main(const Affine* __restrict__ p
       for (int rep = any0 ? 0 : 1; rep < 2; rep++) {
         const u32 mm = rep == 0 ? m0 : m1;
         if (mm == 0u) continue;
-        XYZZ e;
-        if (mm == 1u) e = xyzz_from_affine(ld_affine(pts + (size_t)p * lay.npt + sv_slot(v)));
-        else e = ld_xyzz(T + idx * BP_SV_ENT + (mm - 2u));
-        if (h) e.X = fp_mul(e.X, beta);                    // phi(X, Y, ZZ, ZZZ) = (beta X, Y, ZZ, ZZZ)
-        if (neg) e.Y = fp_neg(e.Y);
-        xyzz_add(acc, e);
+        Affine e = ld_affine(mm == 1u ? pts + (size_t)p * lay.npt + sv_slot(v) : T + idx * BP_SV_ENT + (mm - 2u));
+        if (h) e.x = fp_mul(e.x, beta);                    // phi(x, y) = (beta x, y)
+        if (neg) e.y = fp_neg(e.y);
+        xyzz_madd(acc, e);
       }
     }
     st_xyzz(Aw + ((size_t)p * 3 + eq) * 32 + lane, acc);
