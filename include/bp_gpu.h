@@ -60,7 +60,7 @@ int bp_msm_set_affine_passes(int passes); /* batched-affine pair passes ahead of
 int bp_msm_set_chunk_fit(int on);       /* experiment switch: 1 = entries per accumulation thread fitted to whole waves of resident threads, 0 (default; measured no gain) = the fixed 8 / 16 / 32 */
 int bp_msm_set_tails2d(int on);         /* experiment switch: 1 = 2-D marginal bucket reduction for the wide units of a large plain MSM, 0 (default; measured faster) = running sums */
 int bp_msm_set_pre_fused(int on);       /* experiment switch: 1 (default) = the scatter pass of the precomputed path recomputes the digits, 0 = digit array in between */
-int bp_msm_set_pre_slots(int mode, size_t min_terms);   /* precomputed path, sort stage: 1 (default) = slot sort (one scattered pass; exact counting sort as gated fallback) for MSMs of >= min_terms terms (default 2^18; 0 keeps the value), 0 = exact counting sort only, 2 = test hook, 8 slots per bucket so that the fallback runs */
+int bp_msm_set_pre_slots(int mode, size_t min_terms);   /* sort stage of one large resident MSM (precomputed path; plain path where a bucket holds >= 48 entries, i.e. from 2^20 terms): 1 (default) = slot sort (one scattered pass; exact counting sort as gated fallback) for MSMs of >= min_terms terms (default 2^18; 0 keeps the value), 0 = exact counting sort only, 2 = test hook, 8 slots per bucket so that the fallback runs */
 int bp_msm_set_host_finish(int on);     /* 1 (default): an MSM whose result goes to the host (bp_msm, bp_msm_sharded_host on one rank; bucket method without precomputed multiples) hands its window sums to the host, which runs the Horner chain and the affine conversion; 0 = k_combine on the device */
 int bp_msm_set_pre_chunk(int entries);   /* experiment switch: entries per accumulation thread on that path (0 = automatic) */
 int bp_msm_h(bp_handle points, const uint8_t* sc32, size_t n, uint8_t out64[64]);     /* scalars from host */
