@@ -542,13 +542,18 @@ static int msm_run_pre(const Affine* pre, u32 stride, u32 first, int c, const Fq
     // H = R x C buckets: marginal sums by factors of 8 (rows contiguous, columns strided), weighted stage on R + C points
     int lgH = c - 1, lgC = (lgH + 1) / 2, lgR = lgH - lgC;
     const u32 C = 1u << lgC, R = 1u << lgR;
-    XYZZ* ping = (XYZZ*)g.ws_segsum.ensure(((size_t)nb / 4 + (size_t)nb / 32 + 4096) * sizeof(XYZZ));
+    // level 1: factors of K (rows contiguous, columns strided) in one launch
+    // K = 8 for the 2^17-bucket unit of large MSMs, 4 below (gpurun_out/prek.log: 2^16 terms, c = 17: K = 8 / 4 / 2 -> 0.432 / 0.416 /
+    // 0.414 ms, the first level is a latency chain of K - 1 lone-thread additions there; 2^20 terms, c = 18: 2.268 / 2.284 / 2.303 ms,
+    // twice the partial sums cost the weighted stage more than the shorter first level saves)
+    static const u32 Kenv = [] { const char* e = getenv("BP_PRE_K"); int v = e ? atoi(e) : 0; return (u32)(v == 8 || v == 4 || v == 2 ? v : 0); }();
+    const u32 Kpre = Kenv ? Kenv : (sh.H >= (1u << 17) ? 8u : 4u);
+    const u32 Kr = C >= Kpre ? Kpre : C, Kc = R >= Kpre ? Kpre : R;
+    const u32 np_r = C / Kr, np_c = R / Kc;              // partial sums per row / per column
+    XYZZ* ping = (XYZZ*)g.ws_segsum.ensure(((size_t)nb / Kr + (size_t)nb / Kc + 8192) * sizeof(XYZZ));
     XYZZ* wsum = (XYZZ*)g.ws_winsum.ensure((size_t)(C + R + 2) * sizeof(XYZZ));
     if (!ping || !wsum) return fail("workspace allocation failed");
-    // level 1: factors of 8 (rows contiguous, columns strided) in one launch
-    const u32 Kr = C >= 8 ? 8u : C, Kc = R >= 8 ? 8u : R;
-    const u32 np_r = C / Kr, np_c = R / Kc;              // partial sums per row / per column (<= 128 for c <= 20)
-    XYZZ* rpart = ping; XYZZ* cpart = ping + ((size_t)nb / 8 + 2048);
+    XYZZ* rpart = ping; XYZZ* cpart = ping + ((size_t)nb / Kr + 4096);
     const u32 nrow_out = R * np_r, ncol_out = np_c * C;
     ++g.nlaunch, k_pre_marginals<<<dim3(((nrow_out > ncol_out ? nrow_out : ncol_out) + 127) / 128, 2), 128, 0, st>>>(buckets, rpart, nrow_out, Kr, buckets, cpart, np_c, C, Kc);
     if (prof) cudaEventRecord(g.ev[5], st);
